@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI declared in include/dgvcc_b200.h.
+
+There is no CPU fallback anywhere in this package: if the shared library is missing it is
+(re)built with nvcc, and if that fails -- or there is no CUDA device when a kernel is called --
+the call raises.
+"""
+import ctypes
+import os
+import threading
+from ctypes import POINTER, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+
+class BLLayout(ctypes.Structure):
+    """Mirror of struct dgvcc_bl_layout."""
+    _fields_ = [(n, c_int64) for n in
+                ("amax", "rz", "pbg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "total")] + \
+               [("tiles", c_int32), ("rows_per_thread", c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/dgvcc_b200.h declares must appear here
+SIGNATURES = {
+    "dgvcc_abi_version": (c_int, []),
+    "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, POINTER(BLLayout)]),
+    "dgvcc_bl_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
+                                 c_float, c_float, c_float, c_int, c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_bl_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_float, c_int, c_float,
+                                  c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_bl_posterior": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_float,
+                                   c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_bl_bayloss_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
+                                         c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_bl_bayloss_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_void_p,
+                                          c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_probe_ex2": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
+    "dgvcc_probe_ffma": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
+}
+
+
+def lib():
+    """The loaded shared library (built on first use if stale or missing)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                path = _build.LIB_PATH
+                if not os.path.exists(path) or os.environ.get("DGVCC_REBUILD"):
+                    path = _build.build()
+                handle = ctypes.CDLL(path)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)  # AttributeError here = header / library mismatch
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+_ERRORS = {-1: "invalid argument", -2: "workspace too small", -3: "unsupported configuration"}
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = _ERRORS.get(rc, f"cudaError_t {rc}")
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: dgvcc_b200 runs on CUDA tensors only (got device {t.device}); "
+                           "there is no CPU path")
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def stream_ptr(device):
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,273 @@
+"""Drop-in for the reference's ``losses/bl.py`` (Bayesian loss) on B200.
+
+Same classes, constructor keywords and call signatures as the reference
+(losses/bl.py:5-91), so ``get_loss('bl', params)`` (main.py:51-53) and the
+trainers' ``loss.__class__.__name__ == 'BL'`` dispatch (dgtrainer.py:59) work
+unchanged:
+
+    BL(sigma, c_size, stride, background_ratio, use_background, device)
+        .forward(points, st_sizes, target_list, pre_density) -> 0-dim loss
+
+``BL.forward`` runs the fused CUDA path (csrc/bl_kernels.cu) that never builds
+the [points x pixels] posterior; ``Post_Prob`` / ``Bay_Loss`` keep their own
+reference signatures for callers that want the materialised posteriors.
+
+Extensions that do not change reference behaviour:
+  * rectangular grids: the grid is taken from ``pre_density.shape[-2:]``
+    (the reference is square-only because x and y share ``cood``, bl.py:14-16);
+  * image sharding: ``BL.global_batch`` (default: the local batch) is the
+    divisor of bl.py:79, so a rank holding B_local of B_global images returns
+    its partial loss and ``dgvcc_b200.sharding`` all-reduces it.
+"""
+from math import ceil
+
+import numpy as np
+import torch
+from torch.nn import Module
+
+from .. import _native
+
+
+def _as_point_list(points):
+    """bl.py:21-22 accepts a list/tuple of [N_i,2] tensors; empty ones may be any shape with 0 elements."""
+    out = []
+    for p in points:
+        if p.numel() == 0:
+            p = p.reshape(0, 2)
+        if p.dim() != 2 or p.shape[1] != 2:
+            raise ValueError(f"points must be [N,2] tensors, got {tuple(p.shape)}")
+        out.append(p)
+    return out
+
+
+class _Packed:
+    """CSR packing of one ragged batch + the small int32 table the kernels read (include/dgvcc_b200.h)."""
+
+    def __init__(self, points, use_bg, device):
+        points = _as_point_list(points)
+        self.batch = len(points)
+        if self.batch == 0:
+            raise ValueError("empty batch")
+        counts = np.asarray([int(p.shape[0]) for p in points], dtype=np.int64)
+        rows = np.where(counts == 0, 1, counts + (1 if use_bg else 0))
+        self.counts = counts
+        self.rows = rows
+        self.total_points = int(counts.sum())
+        self.total_rows = int(rows.sum())
+        b = self.batch
+        meta = np.zeros(4 * b + 2, dtype=np.int32)
+        meta[1:b + 1] = np.cumsum(counts)
+        meta[b + 2:2 * b + 2] = np.cumsum(rows)
+        # bl.py:76: num = ceil(0.9 * (len(res) - 1)), evaluated in Python doubles on the host
+        meta[2 * b + 2:3 * b + 2] = [ceil(0.9 * (int(r) - 1)) for r in rows]
+        meta[3 * b + 2:4 * b + 2] = np.argsort(-counts, kind="stable")
+        self.pt_off = meta[:b + 1].copy()
+        self.row_off = meta[b + 1:2 * b + 2].copy()
+        host = torch.from_numpy(meta)
+        if device.type == "cuda":
+            host = host.pin_memory()
+        self.meta = host.to(device, non_blocking=True)
+        if self.total_points > 0:
+            self.pts = torch.cat([p.to(device=device, dtype=torch.float32) for p in points], dim=0).contiguous()
+        else:
+            self.pts = torch.zeros((1, 2), dtype=torch.float32, device=device)  # never read
+
+
+def _pack_targets(target_list, packed, device):
+    if packed.total_points == 0:
+        return torch.zeros((1,), dtype=torch.float32, device=device)
+    parts = []
+    for t, n in zip(target_list, packed.counts):
+        t = t.reshape(-1)
+        if t.shape[0] != n:
+            raise ValueError(f"target length {t.shape[0]} does not match its {n} points")
+        parts.append(t.to(device=device, dtype=torch.float32))
+    return torch.cat(parts, dim=0).contiguous()
+
+
+def _layout(total_rows, batch, hp, wp):
+    lay = _native.BLLayout()
+    _native.check(_native.lib().dgvcc_bl_workspace_layout(total_rows, batch, hp, wp, lay), "dgvcc_bl_workspace_layout")
+    return lay
+
+
+def _workspace(lay, device):
+    ws = torch.empty((lay.total,), dtype=torch.uint8, device=device)
+    ws[lay.ticket:lay.ticket + 4].zero_()
+    return ws
+
+
+def _region(ws, offset, n, dtype=torch.float32):
+    return ws[offset:offset + 4 * n].view(dtype)
+
+
+class _FusedBL(torch.autograd.Function):
+    """dgvcc_bl_forward / dgvcc_bl_backward; only the density receives gradient (bl.py:73-79)."""
+
+    @staticmethod
+    def forward(ctx, density, packed, targets, st_sizes, stride, sigma, bg_ratio, use_bg, inv_batch, keep):
+        _native.require_cuda(density, "BL.forward")
+        b, hp, wp = density.shape[0], density.shape[-2], density.shape[-1]
+        dens = density.detach().reshape(b, hp, wp).to(torch.float32).contiguous()
+        dev = dens.device
+        lay = _layout(packed.total_rows, b, hp, wp)
+        ws = _workspace(lay, dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        rc = _native.lib().dgvcc_bl_forward(
+            _native.ptr(packed.pts), _native.ptr(targets), _native.ptr(packed.meta), _native.ptr(st_sizes),
+            _native.ptr(dens), b, hp, wp, packed.total_rows, stride, sigma, bg_ratio, int(use_bg), inv_batch,
+            _native.ptr(ws), lay.total, _native.ptr(loss), _native.stream_ptr(dev))
+        _native.check(rc, "dgvcc_bl_forward")
+        ctx.packed, ctx.ws, ctx.lay = packed, ws, lay
+        ctx.geom = (b, hp, wp, stride, sigma, int(use_bg), inv_batch)
+        ctx.dens_shape, ctx.dens_dtype = density.shape, density.dtype
+        if keep is not None:  # debugging / tests: expose the workspace regions
+            keep["workspace"], keep["layout"], keep["packed"] = ws, lay, packed
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        b, hp, wp, stride, sigma, use_bg, inv_batch = ctx.geom
+        packed, ws, lay = ctx.packed, ctx.ws, ctx.lay
+        dev = ws.device
+        g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        grad = torch.empty((b, hp, wp), dtype=torch.float32, device=dev)
+        rc = _native.lib().dgvcc_bl_backward(
+            _native.ptr(packed.pts), _native.ptr(packed.meta), b, hp, wp, packed.total_rows, stride, sigma, use_bg,
+            inv_batch, _native.ptr(g), _native.ptr(ws), lay.total, _native.ptr(grad), _native.stream_ptr(dev))
+        _native.check(rc, "dgvcc_bl_backward")
+        return (grad.reshape(ctx.dens_shape).to(ctx.dens_dtype),) + (None,) * 9
+
+
+class Post_Prob(Module):
+    """Posterior label probabilities, materialised (reference: losses/bl.py:5-52)."""
+
+    def __init__(self, sigma, c_size, stride, background_ratio, use_background, device):
+        super(Post_Prob, self).__init__()
+        assert c_size % stride == 0
+
+        self.sigma = sigma
+        self.bg_ratio = background_ratio
+        self.device = device
+        self.c_size = c_size
+        self.stride = stride
+        # kept for attribute compatibility (bl.py:14-16); the kernels rebuild the same values on the fly
+        self.cood = (torch.arange(0, c_size, step=stride, dtype=torch.float32, device=device) + stride / 2).unsqueeze(0)
+        self.use_bg = use_background
+
+    def forward(self, points, st_sizes, grid=None):
+        """List of [N_i(+1), H'*W'] posteriors, ``None`` for images without points (bl.py:36-51).
+
+        ``grid=(rows, cols)`` selects a rectangular grid; the default is the reference's square
+        ``c_size // stride`` grid.
+        """
+        hp, wp = grid if grid is not None else (self.c_size // self.stride,) * 2
+        dev = st_sizes.device
+        _native.require_cuda(st_sizes, "Post_Prob.forward")
+        packed = _Packed(points, self.use_bg, dev)
+        if packed.total_points == 0:
+            return [None for _ in range(packed.batch)]
+        st = st_sizes.to(torch.float32).contiguous()
+        lay = _layout(packed.total_rows, packed.batch, hp, wp)
+        ws = _workspace(lay, dev)
+        prob = torch.empty((packed.total_rows, hp * wp), dtype=torch.float32, device=dev)
+        rc = _native.lib().dgvcc_bl_posterior(
+            _native.ptr(packed.pts), _native.ptr(packed.meta), _native.ptr(st), packed.batch, hp, wp,
+            packed.total_rows, float(self.stride), float(self.sigma), float(self.bg_ratio), int(self.use_bg),
+            _native.ptr(ws), lay.total, _native.ptr(prob), _native.stream_ptr(dev))
+        _native.check(rc, "dgvcc_bl_posterior")
+        out = []
+        for i in range(packed.batch):
+            if packed.counts[i] == 0:
+                out.append(None)
+            else:
+                out.append(prob[packed.row_off[i]:packed.row_off[i + 1]])
+        return out
+
+
+class _BayLossOnProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, density, prob, targets, meta, total_rows, inv_batch):
+        b, hp, wp = density.shape[0], density.shape[-2], density.shape[-1]
+        dens = density.detach().reshape(b, hp, wp).to(torch.float32).contiguous()
+        dev = dens.device
+        lay = _layout(total_rows, b, hp, wp)
+        ws = _workspace(lay, dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        rc = _native.lib().dgvcc_bl_bayloss_forward(
+            _native.ptr(prob), _native.ptr(targets), _native.ptr(meta), _native.ptr(dens), b, hp, wp, total_rows,
+            inv_batch, _native.ptr(ws), lay.total, _native.ptr(loss), _native.stream_ptr(dev))
+        _native.check(rc, "dgvcc_bl_bayloss_forward")
+        ctx.saved = (prob, meta, ws, lay, b, hp, wp, total_rows, inv_batch, density.shape, density.dtype)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        prob, meta, ws, lay, b, hp, wp, total_rows, inv_batch, shape, dtype = ctx.saved
+        dev = ws.device
+        g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        grad = torch.empty((b, hp, wp), dtype=torch.float32, device=dev)
+        rc = _native.lib().dgvcc_bl_bayloss_backward(
+            _native.ptr(prob), _native.ptr(meta), b, hp, wp, total_rows, inv_batch, _native.ptr(g), _native.ptr(ws),
+            lay.total, _native.ptr(grad), _native.stream_ptr(dev))
+        _native.check(rc, "dgvcc_bl_bayloss_backward")
+        return (grad.reshape(shape).to(dtype),) + (None,) * 5
+
+
+class Bay_Loss(Module):
+    """Trimmed-L1 count loss on given posteriors (reference: losses/bl.py:54-80)."""
+
+    def __init__(self, use_background, device):
+        super(Bay_Loss, self).__init__()
+        self.device = device
+        self.use_bg = use_background
+
+    def forward(self, prob_list, target_list, pre_density):
+        _native.require_cuda(pre_density, "Bay_Loss.forward")
+        dev = pre_density.device
+        b = len(prob_list)
+        m = pre_density.shape[-2] * pre_density.shape[-1]
+        probs, tgts, rows, counts = [], [], [], []
+        for idx, prob in enumerate(prob_list):
+            if prob is None or prob.shape[0] == 0:  # bl.py:63-65: count = sum of density, target 0
+                probs.append(torch.ones((1, m), dtype=torch.float32, device=dev))
+                rows.append(1)
+                counts.append(0)
+            else:
+                n = prob.shape[0] - 1 if self.use_bg else prob.shape[0]
+                probs.append(prob.detach().to(device=dev, dtype=torch.float32).reshape(prob.shape[0], m))
+                tgts.append(target_list[idx].reshape(-1)[:n].to(device=dev, dtype=torch.float32))
+                rows.append(prob.shape[0])
+                counts.append(n)
+        meta = np.zeros(4 * b + 2, dtype=np.int32)
+        meta[1:b + 1] = np.cumsum(counts)
+        meta[b + 2:2 * b + 2] = np.cumsum(rows)
+        meta[2 * b + 2:3 * b + 2] = [ceil(0.9 * (r - 1)) for r in rows]
+        meta[3 * b + 2:4 * b + 2] = np.arange(b)
+        meta_dev = torch.from_numpy(meta).pin_memory().to(dev, non_blocking=True)
+        prob_all = torch.cat(probs, dim=0).contiguous()
+        targets = torch.cat(tgts).contiguous() if tgts else torch.zeros((1,), dtype=torch.float32, device=dev)
+        return _BayLossOnProb.apply(pre_density, prob_all, targets, meta_dev, int(sum(rows)), 1.0 / b)
+
+
+class BL(Module):
+    """Bayesian loss, fused (reference: losses/bl.py:82-91)."""
+
+    def __init__(self, sigma, c_size, stride, background_ratio, use_background, device):
+        super(BL, self).__init__()
+        self.post_prob = Post_Prob(sigma, c_size, stride, background_ratio, use_background, device)
+        self.bay_loss = Bay_Loss(use_background, device)
+        self.global_batch = None  # set by dgvcc_b200.sharding when images are partitioned across ranks
+
+    def forward(self, points, st_sizes, target_list, pre_density, _keep=None):
+        pp = self.post_prob
+        dev = pre_density.device
+        _native.require_cuda(pre_density, "BL.forward")
+        if len(points) != pre_density.shape[0]:
+            raise ValueError(f"{len(points)} point sets for a batch of {pre_density.shape[0]} density maps")
+        packed = _Packed(points, pp.use_bg, dev)
+        targets = _pack_targets(target_list, packed, dev)
+        st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()
+        inv_batch = 1.0 / float(self.global_batch or packed.batch)
+        return _FusedBL.apply(pre_density, packed, targets, st, float(pp.stride), float(pp.sigma),
+                              float(pp.bg_ratio), bool(pp.use_bg), inv_batch, _keep)

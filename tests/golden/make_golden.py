@@ -1,0 +1,92 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in the authoring container.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [bl|dmap|isw ...]
+
+Needs /root/reference (read-only mount); the GPU box has no such path, which is
+why the outputs are committed.  Every array in a fixture is either an input
+(prefix ``in_``) or an output of the reference's own code (prefix ``ref_``).
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+from dgvcc_b200 import synthetic  # noqa: E402
+
+
+def load_ref(relpath, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# --------------------------------------------------------------------------- BL
+def bl_case(name, counts, width, height, stride, sigma, use_bg=True, bg_ratio=1.0, seed_cfg=7,
+            jitter_outside=False, rows=(0, 1, -1)):
+    """Run reference BL on a (possibly rectangular) grid via the square + zero-pad construction."""
+    bl = load_ref("losses/bl.py", "ref_bl")
+    pts, tgt, dens, st = synthetic.bl_batch(seed_cfg, counts, width, height, stride)
+    if jitter_outside:  # bay_dataset.py:85-98 keeps heads whose box overlaps the crop >= 30 %
+        for p in pts:
+            if len(p):
+                p[::7] += np.float32(9.5)
+                p[::11] -= np.float32(6.25)
+    c_size = max(width, height)
+    g = c_size // stride
+    hp, wp = height // stride, width // stride
+    B = len(counts)
+    sq = np.zeros((B, 1, g, g), dtype=np.float32)
+    sq[:, :, :hp, :wp] = dens
+    mod = bl.BL(sigma, c_size, stride, bg_ratio, use_bg, "cpu")
+    d = torch.from_numpy(sq).requires_grad_(True)
+    tp = [torch.from_numpy(p.copy()) for p in pts]
+    tt = [torch.from_numpy(t.copy()) for t in tgt]
+    ts = torch.from_numpy(st.copy())
+    loss = mod(tp, ts, tt, d)
+    loss.backward()
+    probs = mod.post_prob([torch.from_numpy(p.copy()) for p in pts], ts)
+    out = {
+        "in_width": width, "in_height": height, "in_stride": stride, "in_sigma": sigma,
+        "in_use_bg": int(use_bg), "in_bg_ratio": bg_ratio, "in_st_sizes": st,
+        "in_density": dens, "in_counts": np.asarray(counts, dtype=np.int64),
+        "ref_loss": loss.detach().numpy(),
+        "ref_grad": d.grad.numpy()[:, :, :hp, :wp].copy(),
+    }
+    for i in range(B):
+        out[f"in_points_{i}"] = pts[i]
+        out[f"in_targets_{i}"] = tgt[i]
+        if probs[i] is None:
+            continue
+        p3 = probs[i].view(probs[i].shape[0], g, g)[:, :hp, :wp]
+        out[f"ref_count_{i}"] = (torch.from_numpy(dens[i]) * p3).reshape(p3.shape[0], -1).sum(1).numpy()
+        out[f"ref_colsum_{i}"] = p3.sum(0).numpy()
+        sel = sorted({r % p3.shape[0] for r in rows})
+        out[f"ref_prob_rows_{i}"] = np.asarray(sel, dtype=np.int64)
+        out[f"ref_prob_{i}"] = p3[sel].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, f"bl_{name}.npz"), **out)
+    print("bl", name, "loss", float(loss))
+
+
+def make_bl():
+    bl_case("c1", [200], 1024, 768, 8, 8.0, seed_cfg=1)                       # BASELINE config 1
+    bl_case("mixed", [150, 0, 3, 1, 40], 512, 512, 8, 8.0)                    # empty / tiny images
+    bl_case("nobg", [60, 1, 2, 0], 256, 384, 8, 8.0, use_bg=False)            # use_background=False
+    bl_case("empty", [0, 0], 256, 256, 8, 8.0)                                # all-empty batch
+    bl_case("sigma10", [90, 17], 320, 320, 4, 10.0, bg_ratio=0.15)            # 2*sigma^2 not a power of 2
+    bl_case("outside", [120], 384, 256, 8, 8.0, jitter_outside=True)          # heads outside the crop
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["bl", "dmap", "isw"]
+    torch.manual_seed(0)
+    for w in what:
+        globals()[f"make_{w}"]()

@@ -1,0 +1,47 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_bl_golden(name):
+    z = np.load(os.path.join(GOLDEN, f"bl_{name}.npz"))
+    B = len(z["in_counts"])
+    case = {
+        "width": int(z["in_width"]), "height": int(z["in_height"]), "stride": int(z["in_stride"]),
+        "sigma": float(z["in_sigma"]), "use_bg": bool(int(z["in_use_bg"])), "bg_ratio": float(z["in_bg_ratio"]),
+        "st_sizes": torch.from_numpy(z["in_st_sizes"].copy()),
+        "density": torch.from_numpy(z["in_density"].copy()),
+        "points": [torch.from_numpy(z[f"in_points_{i}"].copy()) for i in range(B)],
+        "targets": [torch.from_numpy(z[f"in_targets_{i}"].copy()) for i in range(B)],
+        "ref_loss": torch.from_numpy(z["ref_loss"].copy()),
+        "ref_grad": torch.from_numpy(z["ref_grad"].copy()),
+        "ref_count": {}, "ref_colsum": {}, "ref_prob_rows": {}, "ref_prob": {},
+    }
+    for i in range(B):
+        if f"ref_count_{i}" in z:
+            case["ref_count"][i] = torch.from_numpy(z[f"ref_count_{i}"].copy())
+            case["ref_colsum"][i] = torch.from_numpy(z[f"ref_colsum_{i}"].copy())
+            case["ref_prob_rows"][i] = z[f"ref_prob_rows_{i}"].tolist()
+            case["ref_prob"][i] = torch.from_numpy(z[f"ref_prob_{i}"].copy())
+    return case
+
+
+BL_GOLDEN_CASES = ["c1", "mixed", "nobg", "empty", "sigma10", "outside"]
+
+
+def assert_close(got, ref, rtol, atol, what=""):
+    got = torch.as_tensor(got).double()
+    ref = torch.as_tensor(ref).double()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    if bad.any():
+        idx = torch.nonzero(bad)[0].tolist()
+        worst = (err / tol).max().item()
+        raise AssertionError(
+            f"{what}: {int(bad.sum())}/{bad.numel()} out of tolerance (rtol={rtol}, atol={atol}); "
+            f"worst err/tol={worst:.3g}; first at {idx}: got {got[tuple(idx)].item():.9g} ref {ref[tuple(idx)].item():.9g}")

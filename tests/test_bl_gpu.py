@@ -1,0 +1,187 @@
+"""Parity of the fused CUDA Bayesian loss (through the C ABI) against the CPU oracle and the
+reference-generated fixtures.  Tolerance (BASELINE.json north_star): rtol 1e-5 in fp32; absolute
+floors: 1e-30 for posteriors (entries that underflow), 1e-6*max|ref| for gradients (sums with
+cancellation -- the reference's own fp32 error against its fp64 evaluation is larger than that)."""
+import numpy as np
+import pytest
+import torch
+
+from dgvcc_b200 import synthetic
+from oracle import bl_oracle
+from helpers import BL_GOLDEN_CASES, assert_close, load_bl_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _region(keep, name, n):
+    lay, ws = keep["layout"], keep["workspace"]
+    off = getattr(lay, name)
+    return ws[off:off + 4 * n].view(torch.float32)
+
+
+def run_cuda(points, st_sizes, targets, density, stride, sigma, bg_ratio, use_bg, c_size=None):
+    from dgvcc_b200.losses.bl import BL
+    dev = torch.device("cuda:0")
+    b, _, hp, wp = density.shape
+    mod = BL(sigma, c_size or max(hp, wp) * stride, stride, bg_ratio, use_bg, dev)
+    d = density.to(dev).clone().requires_grad_(True)
+    keep = {}
+    loss = mod([p.to(dev) for p in points], st_sizes.to(dev), [t.to(dev) for t in targets], d, _keep=keep)
+    loss.backward()
+    torch.cuda.synchronize()
+    packed = keep["packed"]
+    counts_all = _region(keep, "counts", packed.total_rows).cpu()
+    counts = [counts_all[packed.row_off[i]:packed.row_off[i + 1]] for i in range(b)]
+    return loss.detach().cpu(), d.grad.cpu(), counts
+
+
+def check_against(loss, grad, counts, ref_loss, ref_grad, ref_counts):
+    assert_close(loss, ref_loss, RTOL, 0, "loss")
+    assert_close(grad, ref_grad, RTOL, 1e-6 * float(ref_grad.abs().max()), "density gradient")
+    for i, rc in ref_counts.items():
+        assert_close(counts[i], rc, RTOL, 1e-7 * float(rc.abs().max()), f"expected counts image {i}")
+
+
+@pytest.mark.parametrize("name", BL_GOLDEN_CASES)
+def test_fused_bl_matches_reference_fixture(name):
+    c = load_bl_golden(name)
+    loss, grad, counts = run_cuda(c["points"], c["st_sizes"], c["targets"], c["density"], c["stride"], c["sigma"], c["bg_ratio"], c["use_bg"])
+    check_against(loss, grad, counts, c["ref_loss"], c["ref_grad"], c["ref_count"])
+
+
+@pytest.mark.parametrize("name", ["c1", "mixed", "nobg", "sigma10", "outside"])
+def test_posteriors_match_reference_fixture(name):
+    from dgvcc_b200.losses.bl import Post_Prob
+    c = load_bl_golden(name)
+    dev = torch.device("cuda:0")
+    hp, wp = c["height"] // c["stride"], c["width"] // c["stride"]
+    pp = Post_Prob(c["sigma"], max(c["width"], c["height"]), c["stride"], c["bg_ratio"], c["use_bg"], dev)
+    probs = pp([p.to(dev) for p in c["points"]], c["st_sizes"].to(dev), grid=(hp, wp))
+    for i, p in enumerate(probs):
+        if len(c["points"][i]) == 0:
+            assert p is None
+            continue
+        p = p.cpu().view(-1, hp, wp)
+        assert_close(p[c["ref_prob_rows"][i]], c["ref_prob"][i], RTOL, 1e-30, f"posterior rows image {i}")
+        assert_close(p.sum(0), c["ref_colsum"][i], RTOL, 0, "posterior column sums")
+
+
+def _batch(config, counts, w, h, stride=8):
+    pts, tgt, dens, st = synthetic.bl_batch(config, counts, w, h, stride)
+    return ([torch.from_numpy(p) for p in pts], torch.from_numpy(st), [torch.from_numpy(t) for t in tgt],
+            torch.from_numpy(dens))
+
+
+@pytest.mark.parametrize("counts,w,h,sigma,use_bg", [
+    ([300, 0, 1, 2, 3, 4, 57], 256, 192, 8.0, True),      # ragged, every tiny N, rectangular
+    ([300, 0, 1, 2, 3, 4, 57], 256, 192, 8.0, False),
+    ([129, 128, 127, 8, 7, 9], 320, 320, 8.0, True),      # tile-boundary point counts, 40-column grid
+    ([500, 64], 264, 136, 6.5, True),                     # 33x17 grid (partial column block / row band), general sigma
+    ([1000], 512, 512, 15.0, True),
+])
+def test_fused_bl_matches_oracle_small(counts, w, h, sigma, use_bg):
+    pts, st, tgt, dens = _batch(11, counts, w, h)
+    ref = bl_oracle.bl_forward_backward(pts, st, tgt, dens, 8, sigma, 1.0, use_bg)
+    got = run_cuda(pts, st, tgt, dens, 8, sigma, 1.0, use_bg)
+    check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
+
+
+def test_config2_sha_batch_matches_oracle():
+    """BASELINE config 2: 8 ShanghaiTech-A-shaped images, 50..3000 points, 128x128 grid."""
+    counts = synthetic.config_counts(2)
+    pts, st, tgt, dens = _batch(2, counts, 1024, 1024)
+    ref = bl_oracle.bl_forward_backward_chunked(pts, st, tgt, dens, 8, 8.0, 1.0, True, chunk_rows=32)
+    got = run_cuda(pts, st, tgt, dens, 8, 8.0, 1.0, True)
+    check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
+
+
+def test_config3_qnrf_image_matches_oracle():
+    """One full-size QNRF-shaped image (256x192 grid, 12 000 points) against the chunked oracle."""
+    pts, st, tgt, dens = _batch(3, [12000], 2048, 1536)
+    ref = bl_oracle.bl_forward_backward_chunked(pts, st, tgt, dens, 8, 8.0, 1.0, True, chunk_rows=8)
+    got = run_cuda(pts, st, tgt, dens, 8, 8.0, 1.0, True)
+    check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
+
+
+def test_config3_full_batch_properties():
+    """Full BASELINE config 3 (16 images, up to 12k points): size-independent properties.
+
+    * checksum: sum_n c_n (all rows incl. background) == sum_m D[m], because posteriors sum to 1;
+    * the loss equals the trimmed-L1 recomputed on the host from the kernel's counts;
+    * gradient linearity in the upstream gradient; determinism run to run;
+    * sharding: per-image losses computed alone (global_batch=B) sum to the batch loss.
+    """
+    from dgvcc_b200.losses.bl import BL
+    counts = synthetic.config_counts(3)
+    pts, st, tgt, dens = _batch(3, counts, 2048, 1536)
+    dev = torch.device("cuda:0")
+    loss, grad, cnts = run_cuda(pts, st, tgt, dens, 8, 8.0, 1.0, True)
+    for i, c in enumerate(cnts):
+        assert_close(c.double().sum(), dens[i].double().sum(), 2e-5, 0, f"count checksum image {i}")
+    host_loss = 0.0
+    for i, c in enumerate(cnts):
+        t = torch.cat([tgt[i], torch.zeros(1)])
+        host_loss += float(bl_oracle.trimmed_l1((t - c).abs()))
+    assert_close(loss, host_loss / len(counts), RTOL, 0, "loss from counts")
+    loss2, grad2, _ = run_cuda(pts, st, tgt, dens, 8, 8.0, 1.0, True)
+    assert torch.equal(loss, loss2) and torch.equal(grad, grad2), "not deterministic"
+    # upstream gradient 3.0 scales the density gradient by exactly 3 (up to one rounding)
+    mod = BL(8.0, 2048, 8, 1.0, True, dev)
+    d = dens.to(dev).clone().requires_grad_(True)
+    (3.0 * mod([p.to(dev) for p in pts], st.to(dev), [t.to(dev) for t in tgt], d)).backward()
+    assert_close(d.grad.cpu(), 3.0 * grad, 1e-6, 0, "linearity")
+    # image sharding: two halves with global_batch = 16
+    total = 0.0
+    for sl in (slice(0, 8), slice(8, 16)):
+        mod.global_batch = len(counts)
+        dd = dens[sl].to(dev).clone().requires_grad_(True)
+        part = mod([p.to(dev) for p in pts[sl]], st[sl].to(dev), [t.to(dev) for t in tgt[sl]], dd)
+        part.backward()
+        total += float(part)
+        assert_close(dd.grad.cpu(), grad[sl], 1e-6, 1e-12, "sharded gradient")
+    assert_close(total, loss, 1e-6, 0, "sharded loss")
+
+
+def test_topk_ties_are_index_ordered():
+    """Equal residuals straddling the 90 % cut: the kept set is deterministic (first in index order)."""
+    from dgvcc_b200.losses.bl import BL
+    dev = torch.device("cuda:0")
+    n = 40
+    pts = torch.rand(n, 2) * 256
+    tgt = torch.full((n,), 0.5)
+    dens = torch.zeros(1, 1, 32, 32)  # zero density: every count is 0, every residual is 0.5 -> all tied
+    d = dens.to(dev).requires_grad_(True)
+    keep = {}
+    loss = BL(8.0, 256, 8, 1.0, True, dev)([pts.to(dev)], torch.tensor([256.0], device=dev), [tgt.to(dev)], d, _keep=keep)
+    loss.backward()
+    w = _region(keep, "wsel", n + 1).cpu()
+    k = int(np.ceil(0.9 * n))
+    assert_close(loss.cpu(), 0.5 * k, 1e-6, 0, "tied loss")
+    assert torch.equal(w[:k], torch.full((k,), -1.0)) and torch.equal(w[k:n], torch.zeros(n - k))
+
+
+def test_bay_loss_on_materialised_posteriors():
+    """Post_Prob -> Bay_Loss (the reference's two-module composition, bl.py:88-91) == fused BL."""
+    from dgvcc_b200.losses.bl import BL
+    c = load_bl_golden("mixed")
+    dev = torch.device("cuda:0")
+    mod = BL(c["sigma"], c["width"], c["stride"], c["bg_ratio"], c["use_bg"], dev)
+    d = c["density"].to(dev).clone().requires_grad_(True)
+    pts = [p.to(dev) for p in c["points"]]
+    probs = mod.post_prob(pts, c["st_sizes"].to(dev))
+    loss = mod.bay_loss(probs, [t.to(dev) for t in c["targets"]], d)
+    loss.backward()
+    assert_close(loss.detach().cpu(), c["ref_loss"], RTOL, 0, "loss")
+    assert_close(d.grad.cpu(), c["ref_grad"], RTOL, 1e-6 * float(c["ref_grad"].abs().max()), "grad")
+
+
+def test_errors_are_loud():
+    from dgvcc_b200.losses.bl import BL
+    dev = torch.device("cuda:0")
+    with pytest.raises(AssertionError):
+        BL(8.0, 100, 8, 1.0, True, dev)  # c_size % stride != 0, like bl.py:8
+    mod = BL(8.0, 256, 8, 1.0, True, dev)
+    with pytest.raises(RuntimeError):
+        mod([torch.zeros(3, 2)], torch.ones(1), [torch.ones(3)], torch.zeros(1, 1, 32, 32))  # CPU tensors: no CPU path

@@ -1,0 +1,46 @@
+"""The BL oracle restatement vs fixtures produced by the unmodified reference (losses/bl.py)."""
+import pytest
+import torch
+
+from oracle import bl_oracle
+from helpers import BL_GOLDEN_CASES, assert_close, load_bl_golden
+
+
+@pytest.mark.parametrize("name", BL_GOLDEN_CASES)
+def test_oracle_matches_reference_fixture(name):
+    c = load_bl_golden(name)
+    hp, wp = c["height"] // c["stride"], c["width"] // c["stride"]
+    loss, grad, counts = bl_oracle.bl_forward_backward(
+        c["points"], c["st_sizes"], c["targets"], c["density"], c["stride"], c["sigma"], c["bg_ratio"], c["use_bg"])
+    # the fixture ran the square reference with a zero-padded density, so only the fp32
+    # summation order over pixels may differ (section 8c): 1e-6, not bit-exact.
+    assert_close(loss, c["ref_loss"], 1e-6, 0, "loss")
+    assert_close(grad, c["ref_grad"], 1e-6, 1e-7 * float(c["ref_grad"].abs().max()), "grad")
+    for i, ref_c in c["ref_count"].items():
+        assert_close(counts[i], ref_c, 2e-6, 1e-9, f"count[{i}]")
+        prob = bl_oracle.posterior(c["points"][i], c["st_sizes"][i], hp, wp, c["stride"], c["sigma"],
+                                   c["bg_ratio"], c["use_bg"])
+        rows = c["ref_prob_rows"][i]
+        # posteriors are per-pixel independent: bit-exact against the reference slice
+        assert torch.equal(prob[rows].view(len(rows), hp, wp), c["ref_prob"][i]), f"posterior rows image {i}"
+        assert torch.equal(prob.sum(0).view(hp, wp), c["ref_colsum"][i])
+
+
+@pytest.mark.parametrize("name", ["c1", "mixed", "nobg", "sigma10"])
+def test_chunked_oracle_matches_materialising_oracle(name):
+    c = load_bl_golden(name)
+    a = bl_oracle.bl_forward_backward(c["points"], c["st_sizes"], c["targets"], c["density"], c["stride"],
+                                      c["sigma"], c["bg_ratio"], c["use_bg"])
+    b = bl_oracle.bl_forward_backward_chunked(c["points"], c["st_sizes"], c["targets"], c["density"], c["stride"],
+                                              c["sigma"], c["bg_ratio"], c["use_bg"], chunk_rows=5)
+    assert_close(b[0], a[0], 1e-6, 0, "loss")
+    assert_close(b[1], a[1], 2e-6, 1e-7 * float(a[1].abs().max()), "grad")
+    for ca, cb in zip(a[2], b[2]):
+        assert_close(cb, ca, 2e-6, 1e-9, "counts")
+
+
+def test_posterior_columns_sum_to_one():
+    c = load_bl_golden("c1")
+    hp, wp = c["height"] // c["stride"], c["width"] // c["stride"]
+    prob = bl_oracle.posterior(c["points"][0], c["st_sizes"][0], hp, wp, c["stride"], c["sigma"])
+    assert_close(prob.sum(0), torch.ones(hp * wp), 1e-5, 0, "column sums")

@@ -18,20 +18,22 @@ _lib = None
 class BLLayout(ctypes.Structure):
     """Mirror of struct dgvcc_bl_layout."""
     _fields_ = [(n, c_int64) for n in
-                ("amax", "rz", "pbg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "total")] + \
+                ("amax", "rz", "pbg", "ebg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "zpart",
+                 "minpart", "gpart", "total")] + \
                [("tiles", c_int32), ("rows_per_thread", c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/dgvcc_b200.h declares must appear here
 SIGNATURES = {
     "dgvcc_abi_version": (c_int, []),
-    "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, POINTER(BLLayout)]),
+    "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
     "dgvcc_bl_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
-                                 c_float, c_float, c_float, c_int, c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
-    "dgvcc_bl_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_float, c_int, c_float,
-                                  c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
-    "dgvcc_bl_posterior": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_float,
-                                   c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+                                 c_int, c_int, c_float, c_float, c_float, c_int, c_float, c_void_p, c_size_t,
+                                 c_void_p, c_void_p]),
+    "dgvcc_bl_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_float, c_float,
+                                  c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_bl_posterior": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_float,
+                                   c_float, c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_bl_bayloss_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                          c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_bl_bayloss_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_void_p,

@@ -8,11 +8,15 @@
 //   (x, x*x and the R per-row y-distances of each point), so the inner loop per
 //   (point, pixel) pair is  FADD, FFMA, FMUL, MUFU.EX2, FADD/FFMA  -- MUFU-bound.
 // Sweeps over the points (dense, no culling):
-//   K1 bl_minz_kernel   : pass A min_n dis (bl.py:39), pass B softmax denominator (bl.py:44)
+//   K0 bl_min_kernel    : per-chunk min_n dis (bl.py:39) -- only for images split into point chunks
+//   K1 bl_z_kernel      : softmax max incl. background row + denominator shares (bl.py:39-44)
 //   K2 bl_counts_kernel : expected counts c_n = sum_m D[m] p[n,m]   (bl.py:73), per-tile partials
 //   K3 bl_select_kernel : deterministic reduction of the partials, |t-c|, trimmed top-k
 //                         (radix select), loss (bl.py:75-79)
 //   K4 bl_grad_kernel   : dL/dD[m] = g * sum_n w_n p[n,m]            (autograd of bl.py:73-79)
+// Big images are cut into equal point chunks (host-built table) so every warp task costs the same
+// and the CTA scheduler balances the ragged batch; per-chunk partial minima / denominators /
+// gradient sums are combined in chunk order (deterministic, no float atomics).
 //
 // Rounding contract: the softmax arguments reproduce the
 // reference's fp32 sequence bit for bit -- no FMA contraction in the distance expansion
@@ -81,27 +85,57 @@ struct __align__(16) WarpTile {
     float aux[TILE_PTS];      // K2: staged counts; K4: signed weights
 };
 
-struct TaskInfo {
-    int img, n_pts, pt0, row0, n_rows;
-    int col, row_base;   // this lane's column, first row of the band
-    bool col_ok;
-    int task;            // tile index inside the image
+// Views into the host-built int32 table (layout documented in include/dgvcc_b200.h).
+struct Meta {
+    const int32_t* pt_off;   // [B+1]
+    const int32_t* row_off;  // [B+1]
+    const int32_t* keep;     // [B]
+    const int32_t* icb;      // [B+1] first point-chunk id of each image
+    const int32_t* chunks;   // [C][4] = (image, first point, point count, chunk id run in launch slot c)
 };
 
+__host__ __device__ __forceinline__ Meta meta_view(const int32_t* m, int batch) {
+    Meta v;
+    v.pt_off = m;
+    v.row_off = m + (batch + 1);
+    v.keep = m + 2 * (batch + 1);
+    v.icb = m + 3 * batch + 2;
+    v.chunks = m + 4 * batch + 3;
+    return v;
+}
+
+struct TaskInfo {
+    int img, row0, n_rows;    // image, its first posterior row, number of rows
+    int n_img_pts;            // points in the whole image
+    int pt_base;              // index of the chunk's first point in the packed arrays
+    int p_start, p_cnt;       // chunk = points [p_start, p_start + p_cnt) of the image
+    int chunk, first_chunk, n_chunks;
+    int col, row_base;        // this lane's column, first row of the band
+    bool col_ok;
+    int task;                 // pixel-tile index inside the image
+};
+
+// One warp task = (point chunk, 32-column block, band of R rows).  Chunks are equal-sized slices of
+// an image's points so that all tasks cost the same and the hardware CTA scheduler balances them.
 template <int R>
 __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, int batch, const Geom& g,
                                             TaskInfo& t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     t.task = blockIdx.x * WARPS_PER_CTA + warp;
     if (t.task >= g.tiles) return false;
-    const int32_t* pt_off = meta;
-    const int32_t* row_off = meta + (batch + 1);
-    const int32_t* order = meta + 2 * (batch + 1) + batch;
-    t.img = order[blockIdx.y];
-    t.pt0 = pt_off[t.img];
-    t.n_pts = pt_off[t.img + 1] - t.pt0;
-    t.row0 = row_off[t.img];
-    t.n_rows = row_off[t.img + 1] - t.row0;
+    const Meta mv = meta_view(meta, batch);
+    t.chunk = mv.chunks[4 * blockIdx.y + 3];
+    const int32_t* ce = mv.chunks + 4 * t.chunk;
+    t.img = ce[0];
+    t.p_start = ce[1];
+    t.p_cnt = ce[2];
+    t.first_chunk = mv.icb[t.img];
+    t.n_chunks = mv.icb[t.img + 1] - t.first_chunk;
+    const int pt0 = mv.pt_off[t.img];
+    t.n_img_pts = mv.pt_off[t.img + 1] - pt0;
+    t.pt_base = pt0 + t.p_start;
+    t.row0 = mv.row_off[t.img];
+    t.n_rows = mv.row_off[t.img + 1] - t.row0;
     const int jb = t.task % g.col_blocks, kb = t.task / g.col_blocks;
     t.col = jb * 32 + lane;
     t.col_ok = t.col < g.wp;
@@ -110,21 +144,48 @@ __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, in
     return true;
 }
 
-// Stage points [n0, n0+cnt) of the image: lane-strided, coalesced float2 loads; entries past the
-// image's last point (padding up to `padded`) repeat the last point so they stay finite.
+// Stage `padded` points starting at pts[n0] (lane-strided, coalesced float2 loads); entries at or
+// past `limit` repeat the last valid point so that padding stays finite.
 template <int R>
 __device__ __forceinline__ void stage_points(WarpTile<R>& tile, const float2* __restrict__ pts, int n0,
-                                             int n_pts, int padded, const float (&cym2)[R],
+                                             int limit, int padded, const float (&cym2)[R],
                                              const float (&cyy)[R]) {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < padded; i += 32) {
-        const int n = min(n0 + i, n_pts - 1);
+        const int n = min(n0 + i, limit - 1);
         const float2 p = __ldg(&pts[n]);
         tile.xs[i] = make_float2(p.x, __fmul_rn(p.x, p.x));
         const float yy = __fmul_rn(p.y, p.y);
 #pragma unroll
         for (int r = 0; r < R; ++r) tile.yd[i][r] = axis_sqdist(p.y, yy, cym2[r], cyy[r]);
     }
+}
+
+// Same, keeping only points with a non-zero weight (order preserved -> deterministic sums).
+// Returns the number of points kept; their weights land in tile.aux.
+template <int R>
+__device__ __forceinline__ int stage_points_weighted(WarpTile<R>& tile, const float2* __restrict__ pts,
+                                                     const float* __restrict__ w, int n0, int cnt,
+                                                     const float (&cym2)[R], const float (&cyy)[R]) {
+    const int lane = threadIdx.x & 31;
+    int kept = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int i = base + lane;
+        const float wi = (i < cnt) ? __ldg(&w[n0 + i]) : 0.f;
+        const bool keep = wi != 0.f;
+        const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
+        if (keep) {
+            const int pos = kept + __popc(ballot & ((1u << lane) - 1u));
+            const float2 p = __ldg(&pts[n0 + i]);
+            tile.xs[pos] = make_float2(p.x, __fmul_rn(p.x, p.x));
+            const float yy = __fmul_rn(p.y, p.y);
+#pragma unroll
+            for (int r = 0; r < R; ++r) tile.yd[pos][r] = axis_sqdist(p.y, yy, cym2[r], cyy[r]);
+            tile.aux[pos] = wi;
+        }
+        kept += __popc(ballot);
+    }
+    return kept;
 }
 
 template <int R>
@@ -141,67 +202,114 @@ __device__ __forceinline__ void load_yd(const WarpTile<R>& tile, int i, float (&
     }
 }
 
+// Per-thread constants of the pixel tile: row centres (-2*cy, cy*cy), column centre, pixel indices.
 template <int R>
-__device__ __forceinline__ void row_constants(const TaskInfo& t, const Geom& g, float (&cym2)[R],
-                                              float (&cyy)[R]) {
+struct PixelTile {
+    float cym2[R], cyy[R], cxm2, cxx;
+    int pix[R];     // index of pixel r inside the image (clamped rows/cols duplicate a valid pixel)
+    bool ok[R];     // pixel really exists and is owned by this thread
+
+    __device__ __forceinline__ void init(const TaskInfo& t, const Geom& g) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float cy = cell_centre(min(t.row_base + r, g.hp - 1), g);
-        cym2[r] = -2.0f * cy;
-        cyy[r] = __fmul_rn(cy, cy);
+        for (int r = 0; r < R; ++r) {
+            const int row = min(t.row_base + r, g.hp - 1);
+            const float cy = cell_centre(row, g);
+            cym2[r] = -2.0f * cy;
+            cyy[r] = __fmul_rn(cy, cy);
+            pix[r] = row * g.wp + t.col;
+            ok[r] = t.col_ok && (t.row_base + r < g.hp);
+        }
+        const float cx = cell_centre(t.col, g);
+        cxm2 = -2.0f * cx;
+        cxx = __fmul_rn(cx, cx);
     }
-}
+};
 
-// ------------------------------------------------------------------------------------------ K1
-template <int R, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS)
-bl_minz_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
-               const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
-               float* __restrict__ amax_out, float* __restrict__ rz_out, float* __restrict__ pbg_out) {
-    __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
-    TaskInfo t;
-    if (!decode_task<R>(meta, batch, g, t)) return;
-    WarpTile<R>& tile = tiles[threadIdx.x >> 5];
-    const size_t img_base = (size_t)t.img * g.hp * g.wp;
-
-    if (t.n_pts == 0) {  // bl.py:63-65: the only row is "sum of density", posterior == 1
-        if (t.col_ok)
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (t.row_base + r < g.hp) {
-                    const size_t m = img_base + (size_t)(t.row_base + r) * g.wp + t.col;
-                    amax_out[m] = 0.f; rz_out[m] = 1.f; pbg_out[m] = 1.f;
-                }
-        return;
-    }
-
-    float cym2[R], cyy[R];
-    row_constants<R>(t, g, cym2, cyy);
-    const float cx = cell_centre(t.col, g);
-    const float cxm2 = -2.0f * cx, cxx = __fmul_rn(cx, cx);
-    const float2* pts = pts_all + t.pt0;
-
-    // pass A: min over points of the squared distance (bl.py:39)
-    float mind[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) mind[r] = __int_as_float(0x7f800000);
-    for (int n0 = 0; n0 < t.n_pts; n0 += TILE_PTS) {
-        const int cnt = min(TILE_PTS, t.n_pts - n0);
+// min over the chunk's points of the squared distance (bl.py:39), into mind[]
+template <int R>
+__device__ __forceinline__ void sweep_min(WarpTile<R>& tile, const PixelTile<R>& px, const float2* pts, int cnt_total,
+                                          float (&mind)[R]) {
+    for (int n0 = 0; n0 < cnt_total; n0 += TILE_PTS) {
+        const int cnt = min(TILE_PTS, cnt_total - n0);
         __syncwarp();
-        stage_points<R>(tile, pts, n0, t.n_pts, cnt, cym2, cyy);
+        stage_points<R>(tile, pts, n0, cnt_total, cnt, px.cym2, px.cyy);
         __syncwarp();
 #pragma unroll 4
         for (int i = 0; i < cnt; ++i) {
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
-            const float xd = axis_sqdist(xs.x, xs.y, cxm2, cxx);
+            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
             for (int r = 0; r < R; ++r) mind[r] = fminf(mind[r], __fadd_rn(yd[r], xd));
         }
     }
+}
 
-    // background row (bl.py:39-43) and the softmax max
+// ------------------------------------------------------------------------------------------ K0
+// Only for images split into several point chunks: per-chunk partial minima.
+template <int R>
+__global__ void __launch_bounds__(CTA_THREADS)
+bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
+              float* __restrict__ minpart) {
+    __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
+    TaskInfo t;
+    if (!decode_task<R>(meta, batch, g, t)) return;
+    if (t.n_chunks <= 1) return;  // single-chunk images take the fused path inside bl_z_kernel
+    WarpTile<R>& tile = tiles[threadIdx.x >> 5];
+    PixelTile<R> px;
+    px.init(t, g);
+    float mind[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mind[r] = __int_as_float(0x7f800000);
+    sweep_min<R>(tile, px, pts_all + t.pt_base, t.p_cnt, mind);
+    float* out = minpart + (size_t)t.chunk * g.hp * g.wp;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (px.ok[r]) out[px.pix[r]] = mind[r];
+}
+
+// ------------------------------------------------------------------------------------------ K1
+// Softmax max (incl. the background row, bl.py:39-43) and this chunk's share of the denominator.
+template <int R, bool POW2>
+__global__ void __launch_bounds__(CTA_THREADS)
+bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
+            const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
+            const float* __restrict__ minpart, float* __restrict__ zpart, float* __restrict__ amax_out,
+            float* __restrict__ ebg_out) {
+    __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
+    TaskInfo t;
+    if (!decode_task<R>(meta, batch, g, t)) return;
+    WarpTile<R>& tile = tiles[threadIdx.x >> 5];
+    const size_t M = (size_t)g.hp * g.wp;
+    PixelTile<R> px;
+    px.init(t, g);
+    float* zout = zpart + (size_t)t.chunk * M;
+    float* amax_img = amax_out + (size_t)t.img * M;
+    float* ebg_img = ebg_out + (size_t)t.img * M;
+
+    if (t.n_img_pts == 0) {  // bl.py:63-65: the only row is "sum of density": posterior == 1
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (px.ok[r]) { zout[px.pix[r]] = 0.f; amax_img[px.pix[r]] = 0.f; ebg_img[px.pix[r]] = 1.f; }
+        return;
+    }
+    const float2* pts = pts_all + t.pt_base;
+
+    float mind[R];
+    if (t.n_chunks == 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) mind[r] = __int_as_float(0x7f800000);
+        sweep_min<R>(tile, px, pts, t.p_cnt, mind);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float m = __int_as_float(0x7f800000);
+            for (int c = 0; c < t.n_chunks; ++c) m = fminf(m, minpart[(size_t)(t.first_chunk + c) * M + px.pix[r]]);
+            mind[r] = m;
+        }
+    }
+
     float neg_amax[R], a_bg[R];
     const float dbg = __fmul_rn(st_sizes[t.img], bg_ratio);
 #pragma unroll
@@ -217,42 +325,42 @@ bl_minz_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
         neg_amax[r] = -amax;
     }
 
-    // pass B: softmax denominator, accumulated in point order like torch's dim-0 softmax
+    // denominator share, accumulated in point order like torch's dim-0 softmax
     float z[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) z[r] = 0.f;
-    for (int n0 = 0; n0 < t.n_pts; n0 += TILE_PTS) {
-        const int cnt = min(TILE_PTS, t.n_pts - n0);
+    for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
+        const int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
-        stage_points<R>(tile, pts, n0, t.n_pts, cnt, cym2, cyy);
+        stage_points<R>(tile, pts, n0, t.p_cnt, cnt, px.cym2, px.cyy);
         __syncwarp();
 #pragma unroll 2
         for (int i = 0; i < cnt; ++i) {
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
-            const float xd = axis_sqdist(xs.x, xs.y, cxm2, cxx);
+            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
             for (int r = 0; r < R; ++r) z[r] += pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k);
         }
     }
-
-    if (t.col_ok) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (t.row_base + r >= g.hp) continue;
-            float e_bg = 0.f;
-            if (use_bg) {
-                e_bg = ex2_ftz(__fmul_rn(__fadd_rn(a_bg[r], neg_amax[r]), LOG2E));
-                z[r] += e_bg;
-            }
-            const float rz = 1.0f / z[r];
-            const size_t m = img_base + (size_t)(t.row_base + r) * g.wp + t.col;
-            amax_out[m] = -neg_amax[r];
-            rz_out[m] = rz;
-            pbg_out[m] = e_bg * rz;
+    for (int r = 0; r < R; ++r) {
+        if (!px.ok[r]) continue;
+        zout[px.pix[r]] = z[r];
+        if (t.chunk == t.first_chunk) {
+            amax_img[px.pix[r]] = -neg_amax[r];
+            ebg_img[px.pix[r]] = use_bg ? ex2_ftz(__fmul_rn(__fadd_rn(a_bg[r], neg_amax[r]), LOG2E)) : 0.f;
         }
     }
+}
+
+// 1 / (sum of the chunk shares in chunk order + background term last), the reference's row order.
+__device__ __forceinline__ float softmax_rz(const float* __restrict__ zpart, size_t M, int first_chunk, int n_chunks,
+                                            int pix, float ebg) {
+    float z = 0.f;
+    for (int c = 0; c < n_chunks; ++c) z += zpart[(size_t)(first_chunk + c) * M + pix];
+    return 1.0f / (z + ebg);
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -260,44 +368,48 @@ template <int R, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
                  const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg,
-                 const float* __restrict__ amax_in, const float* __restrict__ rz_in,
-                 const float* __restrict__ pbg_in, int64_t total_rows, float* __restrict__ cpart) {
+                 const float* __restrict__ amax_in, const float* __restrict__ ebg_in,
+                 const float* __restrict__ zpart, float* __restrict__ rz_out, float* __restrict__ pbg_out,
+                 int64_t total_rows, float* __restrict__ cpart) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
     if (!decode_task<R>(meta, batch, g, t)) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const size_t img_base = (size_t)t.img * g.hp * g.wp;
+    const size_t M = (size_t)g.hp * g.wp;
+    const size_t img_base = (size_t)t.img * M;
+    PixelTile<R> px;
+    px.init(t, g);
     float* part = cpart + (size_t)t.task * total_rows + t.row0;
+    const bool first = t.chunk == t.first_chunk;
 
     // per-pixel weights D[m]/Z[m]; pixels outside the grid get weight 0
     float neg_amax[R], wd[R], bg_part = 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const bool ok = t.col_ok && (t.row_base + r < g.hp);
-        const size_t m = img_base + (size_t)min(t.row_base + r, g.hp - 1) * g.wp + t.col;
-        const float d = ok ? density[m] : 0.f;
+        const size_t m = img_base + px.pix[r];
+        const float d = px.ok[r] ? density[m] : 0.f;
+        const float ebg = ebg_in[m];
+        const float rz = softmax_rz(zpart, M, t.first_chunk, t.n_chunks, px.pix[r], ebg);
+        const float pbg = ebg * rz;
         neg_amax[r] = -amax_in[m];
-        wd[r] = d * rz_in[m];
-        bg_part = fmaf(d, pbg_in[m], bg_part);
+        wd[r] = d * rz;
+        bg_part = fmaf(d, pbg, bg_part);
+        if (first && px.ok[r]) { rz_out[m] = rz; pbg_out[m] = pbg; }
     }
-    if (use_bg || t.n_pts == 0) {  // background row, or the sum-of-density row of an empty image
+    if (first && (use_bg || t.n_img_pts == 0)) {  // background row / sum-of-density row of an empty image
         bg_part = warp_sum(bg_part);
         if (lane == 0) part[t.n_rows - 1] = bg_part;
     }
-    if (t.n_pts == 0) return;
+    if (t.p_cnt == 0) return;
 
-    float cym2[R], cyy[R];
-    row_constants<R>(t, g, cym2, cyy);
-    const float cx = cell_centre(t.col, g);
-    const float cxm2 = -2.0f * cx, cxx = __fmul_rn(cx, cx);
-    const float2* pts = pts_all + t.pt0;
-
-    for (int n0 = 0; n0 < t.n_pts; n0 += TILE_PTS) {
-        const int cnt = min(TILE_PTS, t.n_pts - n0);
+    const float2* pts = pts_all + t.pt_base;
+    part += t.p_start;
+    for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
+        const int cnt = min(TILE_PTS, t.p_cnt - n0);
         const int padded = (cnt + 7) & ~7;
         __syncwarp();
-        stage_points<R>(tile, pts, n0, t.n_pts, padded, cym2, cyy);
+        stage_points<R>(tile, pts, n0, t.p_cnt, padded, px.cym2, px.cyy);
         __syncwarp();
         for (int i0 = 0; i0 < padded; i0 += 8) {
             float v[8];
@@ -306,7 +418,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
                 const float2 xs = tile.xs[i0 + u];
                 float yd[R];
                 load_yd<R>(tile, i0 + u, yd);
-                const float xd = axis_sqdist(xs.x, xs.y, cxm2, cxx);
+                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
                 float s = 0.f;
 #pragma unroll
                 for (int r = 0; r < R; ++r)
@@ -360,13 +472,11 @@ bl_select_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
     __shared__ float scratch[SELECT_THREADS / 32];
 
     const int img = blockIdx.x, tid = threadIdx.x;
-    const int32_t* pt_off = meta;
-    const int32_t* row_off = meta + (batch + 1);
-    const int32_t* keep = meta + 2 * (batch + 1);
-    const int pt0 = pt_off[img], n_pts = pt_off[img + 1] - pt0;
-    const int row0 = row_off[img], n_rows = row_off[img + 1] - row0;
+    const Meta mv = meta_view(meta, batch);
+    const int pt0 = mv.pt_off[img], n_pts = mv.pt_off[img + 1] - pt0;
+    const int row0 = mv.row_off[img], n_rows = mv.row_off[img + 1] - row0;
     const int n_cand = n_rows - 1;  // res[:-1]; the last row is always kept (bl.py:77-78)
-    const int n_keep = keep[img];
+    const int n_keep = mv.keep[img];
 
     // expected counts: fixed-order sum of the per-tile partials; residual |t - c|  (bl.py:73-75)
     for (int j = tid; j < n_rows; j += SELECT_THREADS) {
@@ -474,70 +584,106 @@ bl_select_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
 }
 
 // ------------------------------------------------------------------------------------------ K4
+// dL/dD[m] = g * (sum_n w_n e[n,m] / Z[m] + w_bg p_bg[m]).  Trimmed points (w == 0, bl.py:77) are
+// compacted away while staging.  Single-chunk images store the final gradient; otherwise the raw
+// chunk sum goes to gpart and bl_grad_reduce_kernel finishes.
 template <int R, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
                Scale k, int use_bg, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
-               float* __restrict__ grad_density) {
+               float* __restrict__ gpart, float* __restrict__ grad_density) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
     if (!decode_task<R>(meta, batch, g, t)) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const size_t img_base = (size_t)t.img * g.hp * g.wp;
-    const float gscale = grad_loss[0] * inv_batch;
-    const float* w_rows = wsel + t.row0;
-    const bool has_bg_row = use_bg || t.n_pts == 0;
-    const float w_bg = has_bg_row ? w_rows[t.n_rows - 1] : 0.f;
+    const size_t M = (size_t)g.hp * g.wp;
+    const size_t img_base = (size_t)t.img * M;
+    PixelTile<R> px;
+    px.init(t, g);
 
     float acc[R], neg_amax[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const size_t m = img_base + (size_t)min(t.row_base + r, g.hp - 1) * g.wp + t.col;
-        neg_amax[r] = -amax_in[m];
+        neg_amax[r] = -amax_in[img_base + px.pix[r]];
         acc[r] = 0.f;
     }
 
-    if (t.n_pts > 0) {
-        float cym2[R], cyy[R];
-        row_constants<R>(t, g, cym2, cyy);
-        const float cx = cell_centre(t.col, g);
-        const float cxm2 = -2.0f * cx, cxx = __fmul_rn(cx, cx);
-        const float2* pts = pts_all + t.pt0;
-        for (int n0 = 0; n0 < t.n_pts; n0 += TILE_PTS) {
-            const int cnt = min(TILE_PTS, t.n_pts - n0);
-            __syncwarp();
-            stage_points<R>(tile, pts, n0, t.n_pts, cnt, cym2, cyy);
-            for (int i = lane; i < cnt; i += 32) tile.aux[i] = w_rows[n0 + i];
-            __syncwarp();
+    const float2* pts = pts_all + t.pt_base;
+    const float* w_pts = wsel + t.row0 + t.p_start;
+    for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
+        const int cnt = min(TILE_PTS, t.p_cnt - n0);
+        __syncwarp();
+        const int kept = stage_points_weighted<R>(tile, pts, w_pts, n0, cnt, px.cym2, px.cyy);
+        __syncwarp();
 #pragma unroll 2
-            for (int i = 0; i < cnt; ++i) {
-                const float w = tile.aux[i];
-                if (w == 0.f) continue;  // trimmed by the top-k (bl.py:77): contributes nothing
-                const float2 xs = tile.xs[i];
-                float yd[R];
-                load_yd<R>(tile, i, yd);
-                const float xd = axis_sqdist(xs.x, xs.y, cxm2, cxx);
+        for (int i = 0; i < kept; ++i) {
+            const float w = tile.aux[i];
+            const float2 xs = tile.xs[i];
+            float yd[R];
+            load_yd<R>(tile, i, yd);
+            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    acc[r] = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k), w, acc[r]);
-            }
+            for (int r = 0; r < R; ++r)
+                acc[r] = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k), w, acc[r]);
         }
     }
 
-    if (t.col_ok) {
+    if (t.n_chunks == 1) {
+        const float gscale = grad_loss[0] * inv_batch;
+        const bool has_bg_row = use_bg || t.n_img_pts == 0;
+        const float w_bg = has_bg_row ? wsel[t.row0 + t.n_rows - 1] : 0.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (t.row_base + r >= g.hp) continue;
-            const size_t m = img_base + (size_t)(t.row_base + r) * g.wp + t.col;
+            if (!px.ok[r]) continue;
+            const size_t m = img_base + px.pix[r];
             grad_density[m] = gscale * fmaf(acc[r], rz_in[m], w_bg * pbg_in[m]);
         }
+    } else {
+        float* out = gpart + (size_t)t.chunk * M;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (px.ok[r]) out[px.pix[r]] = acc[r];
     }
 }
 
+// Multi-chunk images: add the chunk sums in chunk order and apply the per-pixel factors.
+__global__ void __launch_bounds__(256)
+bl_grad_reduce_kernel(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
+                      const float* __restrict__ grad_loss, const float* __restrict__ gpart,
+                      const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
+                      const float* __restrict__ wsel, float* __restrict__ grad_density) {
+    const int img = blockIdx.y;
+    const Meta mv = meta_view(meta, batch);
+    const int first = mv.icb[img], n_chunks = mv.icb[img + 1] - first;
+    if (n_chunks <= 1) return;
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix >= M) return;
+    float acc = 0.f;
+    for (int c = 0; c < n_chunks; ++c) acc += gpart[(size_t)(first + c) * M + pix];
+    const int n_rows = mv.row_off[img + 1] - mv.row_off[img];
+    const float w_bg = use_bg ? wsel[mv.row_off[img] + n_rows - 1] : 0.f;
+    const size_t m = (size_t)img * M + pix;
+    grad_density[m] = grad_loss[0] * inv_batch * fmaf(acc, rz_in[m], w_bg * pbg_in[m]);
+}
+
 // ------------------------------------------------------------------------- posterior (API parity)
+// rz / pbg from the chunk shares (the fused forward gets them as a by-product of bl_counts_kernel).
+__global__ void __launch_bounds__(256)
+bl_finish_z_kernel(const int32_t* __restrict__ meta, int batch, int M, const float* __restrict__ zpart,
+                   const float* __restrict__ ebg_in, float* __restrict__ rz_out, float* __restrict__ pbg_out) {
+    const int img = blockIdx.y;
+    const Meta mv = meta_view(meta, batch);
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix >= M) return;
+    const size_t m = (size_t)img * M + pix;
+    const float ebg = ebg_in[m];
+    const float rz = softmax_rz(zpart, (size_t)M, mv.icb[img], mv.icb[img + 1] - mv.icb[img], pix, ebg);
+    rz_out[m] = rz;
+    pbg_out[m] = ebg * rz;
+}
+
 template <int R, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_posterior_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
@@ -549,40 +695,34 @@ bl_posterior_kernel(const float2* __restrict__ pts_all, const int32_t* __restric
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
+    PixelTile<R> px;
+    px.init(t, g);
     float* prob = prob_out + (size_t)t.row0 * M;
 
     float neg_amax[R], rz[R];
-    size_t pix[R];
-    bool ok[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        ok[r] = t.col_ok && (t.row_base + r < g.hp);
-        pix[r] = (size_t)min(t.row_base + r, g.hp - 1) * g.wp + t.col;
-        neg_amax[r] = -amax_in[img_base + pix[r]];
-        rz[r] = rz_in[img_base + pix[r]];
-        if (ok[r] && (use_bg || t.n_pts == 0)) prob[(size_t)(t.n_rows - 1) * M + pix[r]] = pbg_in[img_base + pix[r]];
+        neg_amax[r] = -amax_in[img_base + px.pix[r]];
+        rz[r] = rz_in[img_base + px.pix[r]];
+        if (px.ok[r] && t.chunk == t.first_chunk && (use_bg || t.n_img_pts == 0))
+            prob[(size_t)(t.n_rows - 1) * M + px.pix[r]] = pbg_in[img_base + px.pix[r]];
     }
-    if (t.n_pts == 0) return;
-
-    float cym2[R], cyy[R];
-    row_constants<R>(t, g, cym2, cyy);
-    const float cx = cell_centre(t.col, g);
-    const float cxm2 = -2.0f * cx, cxx = __fmul_rn(cx, cx);
-    const float2* pts = pts_all + t.pt0;
-    for (int n0 = 0; n0 < t.n_pts; n0 += TILE_PTS) {
-        const int cnt = min(TILE_PTS, t.n_pts - n0);
+    const float2* pts = pts_all + t.pt_base;
+    prob += (size_t)t.p_start * M;
+    for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
+        const int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
-        stage_points<R>(tile, pts, n0, t.n_pts, cnt, cym2, cyy);
+        stage_points<R>(tile, pts, n0, t.p_cnt, cnt, px.cym2, px.cyy);
         __syncwarp();
         for (int i = 0; i < cnt; ++i) {
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
-            const float xd = axis_sqdist(xs.x, xs.y, cxm2, cxx);
+            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float p = pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k) * rz[r];
-                if (ok[r]) prob[(size_t)(n0 + i) * M + pix[r]] = p;
+                if (px.ok[r]) prob[(size_t)(n0 + i) * M + px.pix[r]] = p;
             }
         }
     }
@@ -640,11 +780,12 @@ static Scale make_scale(float sigma) {
     return k;
 }
 
-static int pick_rows_per_thread(int batch, int hp, int wp) {
+// Rows per thread: the largest band that still yields ~16 warp tasks per SM.
+static int pick_rows_per_thread(int total_chunks, int hp, int wp) {
     const long col_blocks = ceil_div(wp, 32);
-    const long want = 148L * 16;  // at least ~16 warps per SM
+    const long want = 148L * 16;
     for (int r : {8, 4}) {
-        if ((long)batch * col_blocks * ceil_div(hp, r) >= want) return r;
+        if ((long)total_chunks * col_blocks * ceil_div(hp, r) >= want) return r;
     }
     return 2;
 }
@@ -659,19 +800,24 @@ static Geom make_geom(int hp, int wp, int R, float stride) {
     return g;
 }
 
-static int layout(int64_t total_rows, int batch, int hp, int wp, int tiles_override, dgvcc_bl_layout* L) {
-    if (!L || total_rows <= 0 || batch <= 0 || hp <= 0 || wp <= 0) return DGVCC_ERR_ARG;
-    const int R = pick_rows_per_thread(batch, hp, wp);
-    const int tiles = tiles_override > 0 ? tiles_override : make_geom(hp, wp, R, 1.f).tiles;
-    const size_t pix = (size_t)batch * hp * wp * sizeof(float);
+static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, dgvcc_bl_layout* L) {
+    if (!L || total_rows < batch || total_chunks < batch || batch <= 0 || hp <= 0 || wp <= 0) return DGVCC_ERR_ARG;
+    const int R = pick_rows_per_thread(total_chunks, hp, wp);
+    const int tiles = make_geom(hp, wp, R, 1.f).tiles;
+    const size_t M = (size_t)hp * wp;
+    const size_t pix = (size_t)batch * M * sizeof(float);
     const size_t rows = (size_t)total_rows * sizeof(float);
+    const size_t chunk_pix = (size_t)total_chunks * M * sizeof(float);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (int64_t)o; };
-    L->amax = take(pix); L->rz = take(pix); L->pbg = take(pix);
+    L->amax = take(pix); L->rz = take(pix); L->pbg = take(pix); L->ebg = take(pix);
     L->counts = take(rows); L->wsel = take(rows); L->residual = take(rows);
     L->loss_img = take((size_t)batch * sizeof(float));
     L->ticket = take(sizeof(unsigned int));
     L->cpart = take((size_t)tiles * rows);
+    L->zpart = take(chunk_pix);
+    L->minpart = take(chunk_pix);
+    L->gpart = L->minpart;  // minima are dead once the denominators exist; backward re-uses the region
     L->total = (int64_t)off;
     L->tiles = tiles;
     L->rows_per_thread = R;
@@ -687,10 +833,11 @@ static T* at(const void* ws, int64_t off) { return reinterpret_cast<T*>((char*)w
 using namespace dgvcc;
 using namespace dgvcc::bl;
 
-extern "C" int dgvcc_abi_version(void) { return 1; }
+extern "C" int dgvcc_abi_version(void) { return 2; }
 
-extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int batch, int hp, int wp, dgvcc_bl_layout* out) {
-    return layout(total_rows, batch, hp, wp, 0, out);
+extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
+                                         dgvcc_bl_layout* out) {
+    return layout(total_rows, total_chunks, batch, hp, wp, out);
 }
 
 #define BL_DISPATCH(R_, POW2_, KERNEL, GRID, STREAM, ...)                                      \
@@ -707,26 +854,49 @@ extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int batch, int hp, 
         }                                                                                      \
     } while (0)
 
-static int check_common(const void* a, const void* b, const void* ws, int batch, int hp, int wp,
-                        int64_t total_rows, float stride, float sigma) {
+namespace {
+
+struct Plan {
+    dgvcc_bl_layout L;
+    Geom g;
+    Scale k;
+    int R;
+    bool pow2;
+    dim3 grid;
+};
+
+int make_plan(const void* a, const void* b, const void* ws, size_t ws_bytes, int batch, int hp, int wp,
+              int64_t total_rows, int total_chunks, float stride, float sigma, Plan* p) {
     if (!a || !b || !ws) return DGVCC_ERR_ARG;
-    if (batch <= 0 || hp <= 0 || wp <= 0 || total_rows < batch) return DGVCC_ERR_ARG;
     if (!(stride > 0.f) || !(sigma > 0.f)) return DGVCC_ERR_ARG;
+    int rc = layout(total_rows, total_chunks, batch, hp, wp, &p->L);
+    if (rc) return rc;
+    if (ws_bytes < (size_t)p->L.total) return DGVCC_ERR_WORKSPACE;
+    p->R = p->L.rows_per_thread;
+    p->g = make_geom(hp, wp, p->R, stride);
+    p->k = make_scale(sigma);
+    p->pow2 = is_pow2(p->k.s);
+    p->grid = dim3(ceil_div(p->g.tiles, WARPS_PER_CTA), total_chunks);
     return DGVCC_OK;
 }
 
-static int launch_minz(const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
-                       const Geom& g, const Scale& k, int R, float bg_ratio, int use_bg,
-                       const dgvcc_bl_layout& L, void* ws, cudaStream_t st) {
-    const dim3 grid(ceil_div(g.tiles, WARPS_PER_CTA), batch);
-    BL_DISPATCH(R, is_pow2(k.s), bl_minz_kernel, grid, st, (const float2*)pts_xy, meta, st_sizes, batch, g, k,
-                bg_ratio, use_bg, at<float>(ws, L.amax), at<float>(ws, L.rz), at<float>(ws, L.pbg));
+// partial minima (multi-chunk images only) + softmax max / denominator shares
+int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
+             int multi_chunk, float bg_ratio, int use_bg, void* ws, cudaStream_t st) {
+    float* minpart = at<float>(ws, p.L.minpart);
+    if (multi_chunk) {
+        if (p.R == 8) bl_min_kernel<8><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
+        else if (p.R == 4) bl_min_kernel<4><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
+        else bl_min_kernel<2><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    BL_DISPATCH(p.R, p.pow2, bl_z_kernel, p.grid, st, (const float2*)pts_xy, meta, st_sizes, batch, p.g, p.k,
+                bg_ratio, use_bg, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg));
     return (int)cudaGetLastError();
 }
 
-static int launch_select(const float* targets, const int32_t* meta, int batch, int64_t total_rows,
-                         float inv_batch, int tiles, const dgvcc_bl_layout& L, void* ws, float* loss_out,
-                         cudaStream_t st) {
+int launch_select(const dgvcc_bl_layout& L, const float* targets, const int32_t* meta, int batch,
+                  int64_t total_rows, float inv_batch, int tiles, void* ws, float* loss_out, cudaStream_t st) {
     bl_select_kernel<<<batch, SELECT_THREADS, 0, st>>>(
         at<float>(ws, L.cpart), tiles, total_rows, meta, targets, batch, inv_batch, at<float>(ws, L.counts),
         at<float>(ws, L.residual), at<float>(ws, L.wsel), at<float>(ws, L.loss_img), loss_out,
@@ -734,69 +904,71 @@ static int launch_select(const float* targets, const int32_t* meta, int batch, i
     return (int)cudaGetLastError();
 }
 
+}  // namespace
+
 extern "C" int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* meta,
                                 const float* st_sizes, const float* density, int batch, int hp, int wp,
-                                int64_t total_rows, float stride, float sigma, float bg_ratio, int use_bg,
-                                float inv_batch, void* workspace, size_t workspace_bytes, float* loss_out,
-                                void* stream) {
-    int rc = check_common(meta, density, workspace, batch, hp, wp, total_rows, stride, sigma);
+                                int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
+                                float bg_ratio, int use_bg, float inv_batch, void* workspace,
+                                size_t workspace_bytes, float* loss_out, void* stream) {
+    Plan p;
+    int rc = make_plan(meta, density, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
+                       sigma, &p);
     if (rc) return rc;
-    if (!st_sizes || !loss_out) return DGVCC_ERR_ARG;
-    dgvcc_bl_layout L;
-    if ((rc = layout(total_rows, batch, hp, wp, 0, &L))) return rc;
-    if (workspace_bytes < (size_t)L.total) return DGVCC_ERR_WORKSPACE;
+    if (!st_sizes || !loss_out || !pts_xy || !targets) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int R = L.rows_per_thread;
-    const Geom g = make_geom(hp, wp, R, stride);
-    const Scale k = make_scale(sigma);
-    if ((rc = launch_minz(pts_xy, meta, st_sizes, batch, g, k, R, bg_ratio, use_bg, L, workspace, st))) return rc;
-    const dim3 grid(ceil_div(g.tiles, WARPS_PER_CTA), batch);
-    BL_DISPATCH(R, is_pow2(k.s), bl_counts_kernel, grid, st, (const float2*)pts_xy, meta, density, batch, g, k,
-                use_bg, at<float>(workspace, L.amax), at<float>(workspace, L.rz), at<float>(workspace, L.pbg),
-                total_rows, at<float>(workspace, L.cpart));
+    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, workspace, st))) return rc;
+    BL_DISPATCH(p.R, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
+                use_bg, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.zpart),
+                at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
+                at<float>(workspace, p.L.cpart));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    return launch_select(targets, meta, batch, total_rows, inv_batch, L.tiles, L, workspace, loss_out, st);
+    return launch_select(p.L, targets, meta, batch, total_rows, inv_batch, p.L.tiles, workspace, loss_out, st);
 }
 
 extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp,
-                                 int64_t total_rows, float stride, float sigma, int use_bg, float inv_batch,
-                                 const float* grad_loss, const void* workspace, size_t workspace_bytes,
-                                 float* grad_density, void* stream) {
-    int rc = check_common(meta, grad_loss, workspace, batch, hp, wp, total_rows, stride, sigma);
+                                 int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
+                                 int use_bg, float inv_batch, const float* grad_loss, void* workspace,
+                                 size_t workspace_bytes, float* grad_density, void* stream) {
+    Plan p;
+    int rc = make_plan(meta, grad_loss, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
+                       sigma, &p);
     if (rc) return rc;
-    if (!grad_density) return DGVCC_ERR_ARG;
-    dgvcc_bl_layout L;
-    if ((rc = layout(total_rows, batch, hp, wp, 0, &L))) return rc;
-    if (workspace_bytes < (size_t)L.total) return DGVCC_ERR_WORKSPACE;
+    if (!grad_density || !pts_xy) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int R = L.rows_per_thread;
-    const Geom g = make_geom(hp, wp, R, stride);
-    const Scale k = make_scale(sigma);
-    const dim3 grid(ceil_div(g.tiles, WARPS_PER_CTA), batch);
-    BL_DISPATCH(R, is_pow2(k.s), bl_grad_kernel, grid, st, (const float2*)pts_xy, meta, batch, g, k, use_bg,
-                inv_batch, grad_loss, at<float>(workspace, L.amax), at<float>(workspace, L.rz),
-                at<float>(workspace, L.pbg), at<float>(workspace, L.wsel), grad_density);
-    return (int)cudaGetLastError();
+    BL_DISPATCH(p.R, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
+                inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
+                at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
+                grad_density);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    if (multi_chunk) {
+        const int M = hp * wp;
+        bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, st>>>(
+            meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart),
+            at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), grad_density);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    return DGVCC_OK;
 }
 
 extern "C" int dgvcc_bl_posterior(const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
-                                  int hp, int wp, int64_t total_rows, float stride, float sigma, float bg_ratio,
-                                  int use_bg, void* workspace, size_t workspace_bytes, float* prob_out,
-                                  void* stream) {
-    int rc = check_common(meta, st_sizes, workspace, batch, hp, wp, total_rows, stride, sigma);
+                                  int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
+                                  float stride, float sigma, float bg_ratio, int use_bg, void* workspace,
+                                  size_t workspace_bytes, float* prob_out, void* stream) {
+    Plan p;
+    int rc = make_plan(meta, st_sizes, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
+                       sigma, &p);
     if (rc) return rc;
-    if (!prob_out) return DGVCC_ERR_ARG;
-    dgvcc_bl_layout L;
-    if ((rc = layout(total_rows, batch, hp, wp, 0, &L))) return rc;
-    if (workspace_bytes < (size_t)L.total) return DGVCC_ERR_WORKSPACE;
+    if (!prob_out || !pts_xy) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int R = L.rows_per_thread;
-    const Geom g = make_geom(hp, wp, R, stride);
-    const Scale k = make_scale(sigma);
-    if ((rc = launch_minz(pts_xy, meta, st_sizes, batch, g, k, R, bg_ratio, use_bg, L, workspace, st))) return rc;
-    const dim3 grid(ceil_div(g.tiles, WARPS_PER_CTA), batch);
-    BL_DISPATCH(R, is_pow2(k.s), bl_posterior_kernel, grid, st, (const float2*)pts_xy, meta, batch, g, k, use_bg,
-                at<float>(workspace, L.amax), at<float>(workspace, L.rz), at<float>(workspace, L.pbg), prob_out);
+    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, workspace, st))) return rc;
+    const int M = hp * wp;
+    bl_finish_z_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, st>>>(
+        meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.rz),
+        at<float>(workspace, p.L.pbg));
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    BL_DISPATCH(p.R, p.pow2, bl_posterior_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
+                at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), prob_out);
     return (int)cudaGetLastError();
 }
 
@@ -804,18 +976,17 @@ extern "C" int dgvcc_bl_bayloss_forward(const float* prob, const float* targets,
                                         const float* density, int batch, int hp, int wp, int64_t total_rows,
                                         float inv_batch, void* workspace, size_t workspace_bytes,
                                         float* loss_out, void* stream) {
-    if (!prob || !meta || !density || !workspace || !loss_out) return DGVCC_ERR_ARG;
-    if (batch <= 0 || hp <= 0 || wp <= 0 || total_rows < batch) return DGVCC_ERR_ARG;
+    if (!prob || !targets || !meta || !density || !workspace || !loss_out) return DGVCC_ERR_ARG;
     dgvcc_bl_layout L;
     int rc;
-    if ((rc = layout(total_rows, batch, hp, wp, 0, &L))) return rc;
+    if ((rc = layout(total_rows, batch, batch, hp, wp, &L))) return rc;
     if (workspace_bytes < (size_t)L.total) return DGVCC_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int M = hp * wp;
     bl_prob_counts_kernel<<<(unsigned)((total_rows + 7) / 8), 256, 0, st>>>(prob, density, meta, batch, M, total_rows,
                                                                             at<float>(workspace, L.cpart));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    return launch_select(targets, meta, batch, total_rows, inv_batch, /*tiles=*/1, L, workspace, loss_out, st);
+    return launch_select(L, targets, meta, batch, total_rows, inv_batch, /*tiles=*/1, workspace, loss_out, st);
 }
 
 extern "C" int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta, int batch, int hp, int wp,
@@ -823,10 +994,9 @@ extern "C" int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta,
                                          const void* workspace, size_t workspace_bytes, float* grad_density,
                                          void* stream) {
     if (!prob || !meta || !grad_loss || !workspace || !grad_density) return DGVCC_ERR_ARG;
-    if (batch <= 0 || hp <= 0 || wp <= 0 || total_rows < batch) return DGVCC_ERR_ARG;
     dgvcc_bl_layout L;
     int rc;
-    if ((rc = layout(total_rows, batch, hp, wp, 0, &L))) return rc;
+    if ((rc = layout(total_rows, batch, batch, hp, wp, &L))) return rc;
     if (workspace_bytes < (size_t)L.total) return DGVCC_ERR_WORKSPACE;
     const int M = hp * wp;
     bl_prob_grad_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, (cudaStream_t)stream>>>(

@@ -19,6 +19,7 @@ Extensions that do not change reference behaviour:
     divisor of bl.py:79, so a rank holding B_local of B_global images returns
     its partial loss and ``dgvcc_b200.sharding`` all-reduces it.
 """
+import os
 from math import ceil
 
 import numpy as np
@@ -40,6 +41,34 @@ def _as_point_list(points):
     return out
 
 
+def chunk_points():
+    """Points per chunk: big images are cut into near-equal slices of at most this many points."""
+    return int(os.environ.get("DGVCC_BL_CHUNK", "1024"))
+
+
+def build_meta(counts, rows, chunk):
+    """The int32 table of include/dgvcc_b200.h: pt_off, row_off, keep, icb, chunks[C][4]."""
+    b = len(counts)
+    n_chunks = np.maximum(1, -(-counts // chunk))
+    total_chunks = int(n_chunks.sum())
+    meta = np.zeros(4 * b + 3 + 4 * total_chunks, dtype=np.int32)
+    meta[1:b + 1] = np.cumsum(counts)
+    meta[b + 2:2 * b + 2] = np.cumsum(rows)
+    # bl.py:76: num = ceil(0.9 * (len(res) - 1)), evaluated in Python doubles on the host
+    meta[2 * b + 2:3 * b + 2] = [ceil(0.9 * (int(r) - 1)) for r in rows]
+    meta[3 * b + 3:4 * b + 3] = np.cumsum(n_chunks)
+    table = meta[4 * b + 3:].reshape(total_chunks, 4)
+    g = 0
+    for i in range(b):
+        edges = np.linspace(0, int(counts[i]), int(n_chunks[i]) + 1).astype(np.int64)
+        for c in range(int(n_chunks[i])):
+            table[g] = (i, edges[c], edges[c + 1] - edges[c], 0)
+            g += 1
+    # schedule: chunks of the images with the most points first (they have the most tiles in flight)
+    table[:, 3] = np.argsort(-counts[table[:, 0]], kind="stable")
+    return meta, total_chunks, int(n_chunks.max() > 1)
+
+
 class _Packed:
     """CSR packing of one ragged batch + the small int32 table the kernels read (include/dgvcc_b200.h)."""
 
@@ -55,12 +84,7 @@ class _Packed:
         self.total_points = int(counts.sum())
         self.total_rows = int(rows.sum())
         b = self.batch
-        meta = np.zeros(4 * b + 2, dtype=np.int32)
-        meta[1:b + 1] = np.cumsum(counts)
-        meta[b + 2:2 * b + 2] = np.cumsum(rows)
-        # bl.py:76: num = ceil(0.9 * (len(res) - 1)), evaluated in Python doubles on the host
-        meta[2 * b + 2:3 * b + 2] = [ceil(0.9 * (int(r) - 1)) for r in rows]
-        meta[3 * b + 2:4 * b + 2] = np.argsort(-counts, kind="stable")
+        meta, self.total_chunks, self.multi_chunk = build_meta(counts, rows, chunk_points())
         self.pt_off = meta[:b + 1].copy()
         self.row_off = meta[b + 1:2 * b + 2].copy()
         host = torch.from_numpy(meta)
@@ -85,9 +109,10 @@ def _pack_targets(target_list, packed, device):
     return torch.cat(parts, dim=0).contiguous()
 
 
-def _layout(total_rows, batch, hp, wp):
+def _layout(total_rows, total_chunks, batch, hp, wp):
     lay = _native.BLLayout()
-    _native.check(_native.lib().dgvcc_bl_workspace_layout(total_rows, batch, hp, wp, lay), "dgvcc_bl_workspace_layout")
+    _native.check(_native.lib().dgvcc_bl_workspace_layout(total_rows, total_chunks, batch, hp, wp, lay),
+                  "dgvcc_bl_workspace_layout")
     return lay
 
 
@@ -110,12 +135,13 @@ class _FusedBL(torch.autograd.Function):
         b, hp, wp = density.shape[0], density.shape[-2], density.shape[-1]
         dens = density.detach().reshape(b, hp, wp).to(torch.float32).contiguous()
         dev = dens.device
-        lay = _layout(packed.total_rows, b, hp, wp)
+        lay = _layout(packed.total_rows, packed.total_chunks, b, hp, wp)
         ws = _workspace(lay, dev)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         rc = _native.lib().dgvcc_bl_forward(
             _native.ptr(packed.pts), _native.ptr(targets), _native.ptr(packed.meta), _native.ptr(st_sizes),
-            _native.ptr(dens), b, hp, wp, packed.total_rows, stride, sigma, bg_ratio, int(use_bg), inv_batch,
+            _native.ptr(dens), b, hp, wp, packed.total_rows, packed.total_chunks, packed.multi_chunk, stride, sigma,
+            bg_ratio, int(use_bg), inv_batch,
             _native.ptr(ws), lay.total, _native.ptr(loss), _native.stream_ptr(dev))
         _native.check(rc, "dgvcc_bl_forward")
         ctx.packed, ctx.ws, ctx.lay = packed, ws, lay
@@ -133,8 +159,8 @@ class _FusedBL(torch.autograd.Function):
         g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         grad = torch.empty((b, hp, wp), dtype=torch.float32, device=dev)
         rc = _native.lib().dgvcc_bl_backward(
-            _native.ptr(packed.pts), _native.ptr(packed.meta), b, hp, wp, packed.total_rows, stride, sigma, use_bg,
-            inv_batch, _native.ptr(g), _native.ptr(ws), lay.total, _native.ptr(grad), _native.stream_ptr(dev))
+            _native.ptr(packed.pts), _native.ptr(packed.meta), b, hp, wp, packed.total_rows, packed.total_chunks,
+            packed.multi_chunk, stride, sigma, use_bg, inv_batch, _native.ptr(g), _native.ptr(ws), lay.total, _native.ptr(grad), _native.stream_ptr(dev))
         _native.check(rc, "dgvcc_bl_backward")
         return (grad.reshape(ctx.dens_shape).to(ctx.dens_dtype),) + (None,) * 9
 
@@ -168,12 +194,12 @@ class Post_Prob(Module):
         if packed.total_points == 0:
             return [None for _ in range(packed.batch)]
         st = st_sizes.to(torch.float32).contiguous()
-        lay = _layout(packed.total_rows, packed.batch, hp, wp)
+        lay = _layout(packed.total_rows, packed.total_chunks, packed.batch, hp, wp)
         ws = _workspace(lay, dev)
         prob = torch.empty((packed.total_rows, hp * wp), dtype=torch.float32, device=dev)
         rc = _native.lib().dgvcc_bl_posterior(
             _native.ptr(packed.pts), _native.ptr(packed.meta), _native.ptr(st), packed.batch, hp, wp,
-            packed.total_rows, float(self.stride), float(self.sigma), float(self.bg_ratio), int(self.use_bg),
+            packed.total_rows, packed.total_chunks, packed.multi_chunk, float(self.stride), float(self.sigma), float(self.bg_ratio), int(self.use_bg),
             _native.ptr(ws), lay.total, _native.ptr(prob), _native.stream_ptr(dev))
         _native.check(rc, "dgvcc_bl_posterior")
         out = []
@@ -191,7 +217,7 @@ class _BayLossOnProb(torch.autograd.Function):
         b, hp, wp = density.shape[0], density.shape[-2], density.shape[-1]
         dens = density.detach().reshape(b, hp, wp).to(torch.float32).contiguous()
         dev = dens.device
-        lay = _layout(total_rows, b, hp, wp)
+        lay = _layout(total_rows, b, b, hp, wp)
         ws = _workspace(lay, dev)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         rc = _native.lib().dgvcc_bl_bayloss_forward(
@@ -239,11 +265,7 @@ class Bay_Loss(Module):
                 tgts.append(target_list[idx].reshape(-1)[:n].to(device=dev, dtype=torch.float32))
                 rows.append(prob.shape[0])
                 counts.append(n)
-        meta = np.zeros(4 * b + 2, dtype=np.int32)
-        meta[1:b + 1] = np.cumsum(counts)
-        meta[b + 2:2 * b + 2] = np.cumsum(rows)
-        meta[2 * b + 2:3 * b + 2] = [ceil(0.9 * (r - 1)) for r in rows]
-        meta[3 * b + 2:4 * b + 2] = np.arange(b)
+        meta, _, _ = build_meta(np.asarray(counts, dtype=np.int64), np.asarray(rows, dtype=np.int64), 1 << 30)
         meta_dev = torch.from_numpy(meta).pin_memory().to(dev, non_blocking=True)
         prob_all = torch.cat(probs, dim=0).contiguous()
         targets = torch.cat(tgts).contiguous() if tgts else torch.zeros((1,), dtype=torch.float32, device=dev)

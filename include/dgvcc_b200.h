@@ -36,15 +36,21 @@ int dgvcc_abi_version(void);
  * Ragged inputs are CSR-packed exactly like bl.py:21-22 builds them:
  *   pts_xy      [total_points, 2] f32  (x = column, y = row, image pixels)
  *   targets     [total_points]    f32
- *   meta        int32 host-built table, 4 sections of lengths B+1, B+1, B, B:
+ *   meta        int32 host-built table, sections in this order:
  *                 pt_off[B+1]   CSR offsets into pts_xy / targets
  *                 row_off[B+1]  offsets of each image's posterior rows
  *                               (N_i + 1 with background, N_i without, 1 for an
  *                               image with no points: the sum-of-density row)
  *                 keep[B]       ceil(0.9 * (rows_i - 1))  (bl.py:76), host ceil
- *                 order[B]      image indices, most points first (schedule only)
+ *                 icb[B+1]      first point-chunk id of each image
+ *                 chunks[C][4]  (image, first point, point count, chunk id to run
+ *                               in launch slot c).  Chunks cut every image's points
+ *                               into near-equal slices (an image without points has
+ *                               one empty chunk) so that all warp tasks cost the same;
+ *                               the last column is a schedule (big images first).
  *   st_sizes    [B] f32, density [B, hp, wp] f32 (pre_density with the channel
  *   dimension dropped), hp x wp = grid rows x columns, stride = pixels per cell.
+ * total_chunks = C; multi_chunk = 1 when some image has more than one chunk.
  * inv_batch = 1 / (global batch size); with image sharding across GPUs every
  * rank passes 1/B_global and all-reduces the returned partial loss.
  * ------------------------------------------------------------------------- */
@@ -55,48 +61,54 @@ typedef struct dgvcc_bl_layout {
     int64_t amax;      /* [B*hp*wp] f32  per-pixel softmax max                       */
     int64_t rz;        /* [B*hp*wp] f32  1 / softmax denominator                     */
     int64_t pbg;       /* [B*hp*wp] f32  posterior of the background row             */
+    int64_t ebg;       /* [B*hp*wp] f32  exp(a_bg - amax), un-normalised             */
     int64_t counts;    /* [rows]    f32  expected counts (bl.py:73)                  */
     int64_t wsel;      /* [rows]    f32  sign(c-t) of kept rows, 0 for trimmed rows  */
     int64_t residual;  /* [rows]    f32  |t - c|                                     */
     int64_t loss_img;  /* [B]       f32  per-image trimmed L1                        */
     int64_t ticket;    /* [1]       u32  must be zero on entry (memset once)         */
     int64_t cpart;     /* [tiles*rows] f32 per-pixel-tile partial counts             */
+    int64_t zpart;     /* [C*hp*wp] f32  per-chunk share of the softmax denominator  */
+    int64_t minpart;   /* [C*hp*wp] f32  per-chunk min squared distance              */
+    int64_t gpart;     /* [C*hp*wp] f32  per-chunk gradient sums (aliases minpart)   */
     int64_t total;     /* bytes needed                                               */
     int32_t tiles;     /* pixel tiles per image                                      */
     int32_t rows_per_thread; /* kernel variant chosen for this shape                 */
 } dgvcc_bl_layout;
 
-int dgvcc_bl_workspace_layout(int64_t total_rows, int batch, int hp, int wp, dgvcc_bl_layout* out);
+int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
+                              dgvcc_bl_layout* out);
 
 /* Fused forward: per-pixel min / softmax denominator, expected counts, trimmed
  * top-k selection and the loss.  Never materialises the points x pixels matrix.
  * loss_out[0] = inv_batch * sum_i L_i. */
 int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* meta,
                      const float* st_sizes, const float* density,
-                     int batch, int hp, int wp, int64_t total_rows,
+                     int batch, int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
                      float stride, float sigma, float bg_ratio, int use_bg, float inv_batch,
                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
 
 /* Backward into the density only (bl.py: points carry no grad):
  * grad_density[b,m] = grad_loss[0] * inv_batch * sum_{kept n} sign(c_n - t_n) * p[n,m].
- * Re-uses the workspace written by dgvcc_bl_forward. */
+ * Re-uses (and scribbles on the gpart region of) the workspace written by dgvcc_bl_forward. */
 int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta,
-                      int batch, int hp, int wp, int64_t total_rows,
+                      int batch, int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
                       float stride, float sigma, int use_bg, float inv_batch,
-                      const float* grad_loss, const void* workspace, size_t workspace_bytes,
+                      const float* grad_loss, void* workspace, size_t workspace_bytes,
                       float* grad_density, void* stream);
 
 /* Materialised posteriors for API parity with Post_Prob.forward (bl.py:20-52):
  * prob_out [total_rows, hp*wp] f32, image i occupying rows row_off[i]..row_off[i+1].
  * (Rows of images without points are filled with 1: the all-background posterior.) */
 int dgvcc_bl_posterior(const float* pts_xy, const int32_t* meta, const float* st_sizes,
-                       int batch, int hp, int wp, int64_t total_rows,
+                       int batch, int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
                        float stride, float sigma, float bg_ratio, int use_bg,
                        void* workspace, size_t workspace_bytes, float* prob_out, void* stream);
 
 /* Bay_Loss.forward on caller-materialised posteriors (bl.py:60-80): expected
  * counts, selection and loss from prob [total_rows, hp*wp]; fills the same
- * workspace regions as dgvcc_bl_forward so dgvcc_bl_bayloss_backward can run. */
+ * workspace regions as dgvcc_bl_forward so dgvcc_bl_bayloss_backward can run.
+ * Here the meta table has one (unused) chunk per image: workspace_layout(rows, B, B, ...). */
 int dgvcc_bl_bayloss_forward(const float* prob, const float* targets, const int32_t* meta,
                              const float* density, int batch, int hp, int wp, int64_t total_rows,
                              float inv_batch, void* workspace, size_t workspace_bytes,

@@ -1,0 +1,383 @@
+"""bench.py -- Bayesian-loss fwd+bwd images/s on the QNRF-shaped workload (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one pass of the hot path (BL forward + backward) over one batch of 16 synthetic
+QNRF-shaped images per GPU (2048x1536 px, stride-8 grid 192x256, 500..12000 heads, CSR-packed).
+Images are sharded across ranks (weak scaling: 16 images per GPU); the only collective is the
+all-reduce of the scalar loss.  Prints ONE JSON line on rank 0.
+
+  value     images/s, inputs already resident in HBM, through the drop-in ``BL`` module
+  e2e       images/s with HOST inputs: packed H2D copies of points/targets/density/st_sizes and
+            D2H of the loss and the density gradient inside the timed region
+  roofline  the fused path's MUFU.EX2 work (3 exponentials per point-pixel pair, dense) against the
+            chip's MUFU.EX2 rate measured live by dgvcc_probe_ex2 (MEASURED_PEAKS.json has no
+            SFU figure); per-kernel shares from CUDA events recorded on the launch stream
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CONFIG = 3
+STRIDE, SIGMA, BG_RATIO, USE_BG = 8, 8.0, 1.0, True
+IMAGES_PER_GPU = 16
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(rank):
+    from dgvcc_b200 import synthetic
+    counts = synthetic.config_counts(CONFIG, IMAGES_PER_GPU)
+    w, h = synthetic.CONFIG_SHAPES[CONFIG]
+    pts, tgt, dens, st = synthetic.bl_batch(CONFIG, counts, w, h, STRIDE, first_image=rank * IMAGES_PER_GPU)
+    return {
+        "counts": counts, "width": w, "height": h, "hp": h // STRIDE, "wp": w // STRIDE,
+        "points": [torch.from_numpy(p) for p in pts], "targets": [torch.from_numpy(t) for t in tgt],
+        "density": torch.from_numpy(dens), "st_sizes": torch.from_numpy(st),
+    }
+
+
+def workload_name(wl):
+    return (f"BASELINE config 3: {IMAGES_PER_GPU} QNRF-shaped images per GPU, {wl['width']}x{wl['height']} px, "
+            f"stride-{STRIDE} grid {wl['hp']}x{wl['wp']}, {min(wl['counts'])}..{max(wl['counts'])} heads "
+            f"({sum(wl['counts'])} per batch), sigma={SIGMA}, background on")
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_sample(wl, budget_s):
+    """Smallest images first until the estimated cost fills the budget (cost ~ N*M pairs)."""
+    order = sorted(range(len(wl["counts"])), key=lambda i: wl["counts"][i])
+    m = wl["hp"] * wl["wp"]
+    pairs_budget = budget_s * 2.5e8  # ~2.5e8 pairs/s is the survey-time speed of the reference on 8 cores
+    picked, pairs = [], 0
+    for i in order:
+        if picked and pairs + wl["counts"][i] * m > pairs_budget:
+            break
+        picked.append(i)
+        pairs += wl["counts"][i] * m
+    return picked
+
+
+def cpu_step(wl, picked):
+    """The reference's CPU algorithm (oracle port of losses/bl.py) on the sampled images, one at a time."""
+    from oracle import bl_oracle
+    t0 = time.perf_counter()
+    for i in picked:
+        bl_oracle.bl_forward_backward([wl["points"][i]], wl["st_sizes"][i:i + 1], [wl["targets"][i]],
+                                      wl["density"][i:i + 1], STRIDE, SIGMA, BG_RATIO, USE_BG)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, budget_s, repeats=2):
+    picked = cpu_sample(wl, budget_s / repeats)
+    best = min(cpu_step(wl, picked) for _ in range(repeats))
+    m = wl["hp"] * wl["wp"]
+    pairs_sample = sum(wl["counts"][i] for i in picked) * m
+    pairs_batch = sum(wl["counts"]) * m
+    # images/s the CPU path would reach on the whole batch: cost is linear in pairs
+    value = len(wl["counts"]) / (best * pairs_batch / pairs_sample)
+    return {
+        "value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+        "sample": (f"oracle port of losses/bl.py (torch CPU, {torch.get_num_threads()} threads) on the {len(picked)} "
+                   f"smallest images of the batch ({sum(wl['counts'][i] for i in picked)} heads, {best:.2f} s); "
+                   f"scaled by point-pixel pairs to the full batch"),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(0)
+    picked = cpu_sample(wl, max(2.0, args.cpu_seconds / max(1, args.steps + args.warmup)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(wl, picked)
+    times = [cpu_step(wl, picked) for _ in range(args.steps)]
+    m = wl["hp"] * wl["wp"]
+    pairs_sample = sum(wl["counts"][i] for i in picked) * m
+    pairs_batch = sum(wl["counts"]) * m
+    per_batch = float(np.mean(times)) * pairs_batch / pairs_sample
+    value = len(wl["counts"]) / per_batch
+    sample = (f"oracle port of losses/bl.py (torch CPU, {torch.get_num_threads()} threads); each step = the "
+              f"{len(picked)} smallest images of the batch ({sum(wl['counts'][i] for i in picked)} heads), "
+              f"scaled by point-pixel pairs to the full 16-image batch")
+    print(json.dumps({
+        "impl": "reference", "metric": "Bayesian-loss fwd+bwd images/s (QNRF shape)", "value": value,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_batch * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(wl)},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def probe_peak(fn_name, dev, iters=20000):
+    from dgvcc_b200 import _native
+    fn = getattr(_native.lib(), fn_name)
+    sink = torch.zeros(4, device=dev)
+    ops = ctypes.c_int64(0)
+    best = 0.0
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _native.check(fn(_native.ptr(sink), iters, ctypes.byref(ops), _native.stream_ptr(dev)), fn_name)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if rep:
+            best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
+    return best
+
+
+def kernel_breakdown(wl, dev, reps=5):
+    """Per-kernel device time of the fused path: CUDA events recorded on the launch stream between the
+    launches of dgvcc_bl_forward_profiled / dgvcc_bl_backward (inputs resident, no host glue)."""
+    from dgvcc_b200 import _native
+    from dgvcc_b200.losses import bl as blmod
+    lib = _native.lib()
+    packed = blmod._Packed([p.to(dev) for p in wl["points"]], USE_BG, dev)
+    targets = blmod._pack_targets([t.to(dev) for t in wl["targets"]], packed, dev)
+    dens = wl["density"].to(dev).reshape(len(wl["counts"]), wl["hp"], wl["wp"]).contiguous()
+    st = wl["st_sizes"].to(dev)
+    b, hp, wp = dens.shape
+    lay = blmod._layout(packed.total_rows, packed.total_chunks, b, hp, wp)
+    ws = blmod._workspace(lay, dev)
+    loss = torch.empty(1, device=dev)
+    grad = torch.empty_like(dens)
+    gl = torch.ones(1, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    names = ["bl_min", "bl_z", "bl_counts", "bl_select", "bl_grad(+reduce)"]
+    acc = np.zeros(len(names))
+    for rep in range(reps + 1):
+        flush.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        for e in ev:
+            e.record()  # materialise the handles
+        handles = (ctypes.c_void_p * 5)(*[e.cuda_event for e in ev[:5]])
+        _native.check(lib.dgvcc_bl_forward_profiled(
+            _native.ptr(packed.pts), _native.ptr(targets), _native.ptr(packed.meta), _native.ptr(st),
+            _native.ptr(dens), b, hp, wp, packed.total_rows, packed.total_chunks, packed.multi_chunk, float(STRIDE),
+            SIGMA, BG_RATIO, int(USE_BG), 1.0 / b, _native.ptr(ws), lay.total, _native.ptr(loss),
+            _native.stream_ptr(dev), handles), "dgvcc_bl_forward_profiled")
+        _native.check(lib.dgvcc_bl_backward(
+            _native.ptr(packed.pts), _native.ptr(packed.meta), b, hp, wp, packed.total_rows, packed.total_chunks,
+            packed.multi_chunk, float(STRIDE), SIGMA, int(USE_BG), 1.0 / b, _native.ptr(gl), _native.ptr(ws),
+            lay.total, _native.ptr(grad), _native.stream_ptr(dev)), "dgvcc_bl_backward")
+        ev[5].record()
+        torch.cuda.synchronize(dev)
+        if rep:
+            acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(5)])
+    ms = acc / reps
+    wsel = ws[lay.wsel:lay.wsel + 4 * packed.total_rows].view(torch.float32)
+    kept_rows = int((wsel != 0).sum())
+    return dict(zip(names, ms.tolist())), kept_rows, packed
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from dgvcc_b200.losses.bl import BL
+    from dgvcc_b200.sharding import ShardedLoss
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = workload(rank)
+    b = len(wl["counts"])
+    m = wl["hp"] * wl["wp"]
+    global_batch = b * world
+
+    loss_mod = BL(SIGMA, max(wl["width"], wl["height"]), STRIDE, BG_RATIO, USE_BG, dev)
+    loss_fn = ShardedLoss(loss_mod, global_batch) if world > 1 else loss_mod
+
+    # ---- resident inputs ("value")
+    pts_d = [p.to(dev) for p in wl["points"]]
+    tgt_d = [t.to(dev) for t in wl["targets"]]
+    st_d = wl["st_sizes"].to(dev)
+    dens_d = wl["density"].to(dev).requires_grad_(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        dens_d.grad = None
+        loss = loss_fn(pts_d, st_d, tgt_d, dens_d)
+        loss.backward()
+        return loss
+
+    # ---- host inputs ("e2e"): pinned host buffers in, loss + gradient out
+    pts_h = [p.pin_memory() for p in wl["points"]]
+    tgt_h = [t.pin_memory() for t in wl["targets"]]
+    st_h = wl["st_sizes"].pin_memory()
+    dens_h = wl["density"].pin_memory()
+    grad_h = torch.empty_like(wl["density"]).pin_memory()
+    h2d = sum(p.numel() * 4 for p in pts_h) + sum(t.numel() * 4 for t in tgt_h) + st_h.numel() * 4 + dens_h.numel() * 4
+    d2h = grad_h.numel() * 4 + 4
+
+    def step_host():
+        d = dens_h.to(dev, non_blocking=True).requires_grad_(True)
+        loss = loss_fn(pts_h, st_h.to(dev, non_blocking=True), tgt_h, d)  # host lists: packed, one H2D each
+        loss.backward()
+        grad_h.copy_(d.grad, non_blocking=True)
+        return float(loss.detach())  # D2H of the loss: synchronises the step
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        flush.zero_()
+    peak_ex2 = probe_peak("dgvcc_probe_ex2", dev)
+    peak_ffma = probe_peak("dgvcc_probe_ffma", dev)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    events = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident()
+        e1.record()
+        events.append((e0, e1))
+        flush.zero_()  # L2 flush between timed steps, outside the per-step events
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    total_ms = sum(a.elapsed_time(c) for a, c in events)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e
+    for _ in range(3):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = global_batch / (ms_per_step * 1e-3)
+        kernels, kept_rows, packed = kernel_breakdown(wl, dev)
+        pairs = sum(wl["counts"]) * m
+        kept_frac = kept_rows / max(1, packed.total_rows)
+        path_ms = sum(kernels.values())
+        algorithmic = 3.0 * pairs                       # 3 exponentials per pair, dense
+        executed = (2.0 + kept_frac) * pairs            # backward skips the 10 % of rows the top-k trims
+        achieved = executed / (path_ms * 1e-3)
+        out = {
+            "metric": "Bayesian-loss fwd+bwd images/s (QNRF shape)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(wl), "global_batch": global_batch, "parallelism": f"image-sharded x{world}",
+                       "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)",
+                       "timing": "per-step CUDA events on the launch stream, max over ranks",
+                       "wall_s_incl_flush": wall},
+            "clocks": clocks,
+            "e2e": {"value": global_batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps * (6 if packed.multi_chunk else 4),
+            "roofline": {
+                "bound": "sfu", "achieved": achieved / 1e9, "peak": peak_ex2 / 1e9, "unit": "Gexp/s",
+                "frac": achieved / peak_ex2, "traffic": None,
+                "note": ("fused BL path (bl_min+bl_z+bl_counts+bl_select+bl_grad), MUFU.EX2-bound; achieved = executed "
+                         "exponentials / sum of kernel times; peak = dgvcc_probe_ex2 measured in this run "
+                         "(MEASURED_PEAKS.json carries no SFU peak)"),
+                "algorithmic_exps_per_step": algorithmic, "executed_exps_per_step": executed,
+                "path_ms": path_ms, "kernels_ms": kernels, "ffma_peak_tflops": 2 * peak_ffma / 1e12,
+            },
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)

@@ -882,16 +882,19 @@ int make_plan(const void* a, const void* b, const void* ws, size_t ws_bytes, int
 
 // partial minima (multi-chunk images only) + softmax max / denominator shares
 int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
-             int multi_chunk, float bg_ratio, int use_bg, void* ws, cudaStream_t st) {
+             int multi_chunk, float bg_ratio, int use_bg, void* ws, cudaStream_t st, void** events = nullptr) {
     float* minpart = at<float>(ws, p.L.minpart);
+    if (events && events[0]) cudaEventRecord((cudaEvent_t)events[0], st);
     if (multi_chunk) {
         if (p.R == 8) bl_min_kernel<8><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
         else if (p.R == 4) bl_min_kernel<4><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
         else bl_min_kernel<2><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    if (events && events[1]) cudaEventRecord((cudaEvent_t)events[1], st);
     BL_DISPATCH(p.R, p.pow2, bl_z_kernel, p.grid, st, (const float2*)pts_xy, meta, st_sizes, batch, p.g, p.k,
                 bg_ratio, use_bg, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg));
+    if (events && events[2]) cudaEventRecord((cudaEvent_t)events[2], st);
     return (int)cudaGetLastError();
 }
 
@@ -906,24 +909,41 @@ int launch_select(const dgvcc_bl_layout& L, const float* targets, const int32_t*
 
 }  // namespace
 
-extern "C" int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* meta,
-                                const float* st_sizes, const float* density, int batch, int hp, int wp,
-                                int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
-                                float bg_ratio, int use_bg, float inv_batch, void* workspace,
-                                size_t workspace_bytes, float* loss_out, void* stream) {
+static inline void mark(void** events, int i, cudaStream_t st) {
+    if (events && events[i]) cudaEventRecord((cudaEvent_t)events[i], st);
+}
+
+extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targets, const int32_t* meta,
+                                         const float* st_sizes, const float* density, int batch, int hp, int wp,
+                                         int64_t total_rows, int total_chunks, int multi_chunk, float stride,
+                                         float sigma, float bg_ratio, int use_bg, float inv_batch, void* workspace,
+                                         size_t workspace_bytes, float* loss_out, void* stream, void** events) {
     Plan p;
     int rc = make_plan(meta, density, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
                        sigma, &p);
     if (rc) return rc;
     if (!st_sizes || !loss_out || !pts_xy || !targets) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, workspace, st))) return rc;
+    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, workspace, st, events))) return rc;
     BL_DISPATCH(p.R, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
                 use_bg, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.zpart),
                 at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
                 at<float>(workspace, p.L.cpart));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    return launch_select(p.L, targets, meta, batch, total_rows, inv_batch, p.L.tiles, workspace, loss_out, st);
+    mark(events, 3, st);
+    rc = launch_select(p.L, targets, meta, batch, total_rows, inv_batch, p.L.tiles, workspace, loss_out, st);
+    mark(events, 4, st);
+    return rc;
+}
+
+extern "C" int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* meta,
+                                const float* st_sizes, const float* density, int batch, int hp, int wp,
+                                int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
+                                float bg_ratio, int use_bg, float inv_batch, void* workspace,
+                                size_t workspace_bytes, float* loss_out, void* stream) {
+    return dgvcc_bl_forward_profiled(pts_xy, targets, meta, st_sizes, density, batch, hp, wp, total_rows,
+                                     total_chunks, multi_chunk, stride, sigma, bg_ratio, use_bg, inv_batch,
+                                     workspace, workspace_bytes, loss_out, stream, nullptr);
 }
 
 extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp,

@@ -91,10 +91,17 @@ class _Packed:
         if device.type == "cuda":
             host = host.pin_memory()
         self.meta = host.to(device, non_blocking=True)
-        if self.total_points > 0:
-            self.pts = torch.cat([p.to(device=device, dtype=torch.float32) for p in points], dim=0).contiguous()
-        else:
+        self.on_host = device.type == "cuda" and all(p.device.type == "cpu" for p in points)
+        if self.total_points == 0:
             self.pts = torch.zeros((1, 2), dtype=torch.float32, device=device)  # never read
+        elif self.on_host:  # host lists (e.g. straight from the DataLoader): pack on the host, one H2D copy
+            self.pts = _upload(torch.cat([p.to(torch.float32) for p in points], dim=0), device)
+        else:
+            self.pts = torch.cat([p.to(device=device, dtype=torch.float32) for p in points], dim=0).contiguous()
+
+
+def _upload(host_tensor, device):
+    return host_tensor.contiguous().pin_memory().to(device, non_blocking=True)
 
 
 def _pack_targets(target_list, packed, device):
@@ -105,8 +112,10 @@ def _pack_targets(target_list, packed, device):
         t = t.reshape(-1)
         if t.shape[0] != n:
             raise ValueError(f"target length {t.shape[0]} does not match its {n} points")
-        parts.append(t.to(device=device, dtype=torch.float32))
-    return torch.cat(parts, dim=0).contiguous()
+        parts.append(t)
+    if device.type == "cuda" and all(t.device.type == "cpu" for t in parts):
+        return _upload(torch.cat([t.to(torch.float32) for t in parts], dim=0), device)
+    return torch.cat([t.to(device=device, dtype=torch.float32) for t in parts], dim=0).contiguous()
 
 
 def _layout(total_rows, total_chunks, batch, hp, wp):

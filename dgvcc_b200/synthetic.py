@@ -46,11 +46,11 @@ def bl_image(seed, n, width, height, stride):
     return pts, targets, dens, float(min(width, height))
 
 
-def bl_batch(config, counts, width, height, stride=8):
+def bl_batch(config, counts, width, height, stride=8, first_image=0):
     """Batch for BL: lists of per-image points/targets, density [B,1,H',W'], st_sizes [B]."""
     pts, tgt, den, st = [], [], [], []
     for i, n in enumerate(counts):
-        p, t, d, s = bl_image(1000 * config + i, n, width, height, stride)
+        p, t, d, s = bl_image(1000 * config + first_image + i, n, width, height, stride)
         pts.append(p)
         tgt.append(t)
         den.append(d)

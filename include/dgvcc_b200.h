@@ -88,6 +88,16 @@ int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* m
                      float stride, float sigma, float bg_ratio, int use_bg, float inv_batch,
                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
 
+/* Same launches with caller-created cudaEvent_t handles recorded between them (bench.py's
+ * per-kernel timing): events[0] start, [1] after bl_min, [2] after bl_z, [3] after bl_counts,
+ * [4] after bl_select.  NULL entries are skipped. */
+int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targets, const int32_t* meta,
+                              const float* st_sizes, const float* density,
+                              int batch, int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
+                              float stride, float sigma, float bg_ratio, int use_bg, float inv_batch,
+                              void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
+                              void** events);
+
 /* Backward into the density only (bl.py: points carry no grad):
  * grad_density[b,m] = grad_loss[0] * inv_batch * sum_{kept n} sign(c_n - t_n) * p[n,m].
  * Re-uses (and scribbles on the gpart region of) the workspace written by dgvcc_bl_forward. */

@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/dgvcc_b200.h declares (no GPU needed)."""
+import os
+import re
+
+from dgvcc_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dgvcc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dgvcc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _native.lib()
+    names = declared_symbols()
+    assert len(names) >= 10
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _native.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_native.SIGNATURES) == set(names)
+    assert lib.dgvcc_abi_version() >= 2
+
+
+def test_workspace_layout_is_host_only_and_consistent():
+    lay = _native.BLLayout()
+    assert _native.lib().dgvcc_bl_workspace_layout(1000, 3, 2, 48, 64, lay) == 0
+    offs = [lay.amax, lay.rz, lay.pbg, lay.ebg, lay.counts, lay.wsel, lay.residual, lay.loss_img, lay.ticket,
+            lay.cpart, lay.zpart, lay.minpart]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.total > offs[-1]
+    assert lay.rows_per_thread in (2, 4, 8) and lay.tiles > 0
+    assert _native.lib().dgvcc_bl_workspace_layout(0, 1, 1, 8, 8, lay) == -1  # DGVCC_ERR_ARG
+
+
+def test_meta_table_layout():
+    import numpy as np
+    from dgvcc_b200.losses.bl import build_meta
+    counts = np.array([2500, 0, 3, 1024, 1025])
+    rows = np.array([2501, 1, 4, 1025, 1026])
+    meta, c, multi = build_meta(counts, rows, 1024)
+    b = 5
+    assert meta[:b + 1].tolist() == [0, 2500, 2500, 2503, 3527, 4552]
+    assert meta[b + 1:2 * b + 2].tolist() == [0, 2501, 2502, 2506, 3531, 4557]
+    assert meta[2 * b + 2:3 * b + 2].tolist() == [2250, 0, 3, 922, 923]   # ceil(0.9*(rows-1)), bl.py:76
+    assert meta[3 * b + 2:4 * b + 3].tolist() == [0, 3, 4, 5, 6, 8]
+    table = meta[4 * b + 3:].reshape(c, 4)
+    assert c == 8 and multi == 1
+    for i in range(b):  # chunks tile each image's points exactly
+        mine = table[table[:, 0] == i]
+        assert mine[:, 2].sum() == counts[i] and mine[0, 1] == 0
+    assert sorted(table[:, 3].tolist()) == list(range(c))

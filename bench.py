@@ -213,7 +213,7 @@ def kernel_breakdown(wl, dev, reps=5):
     grad = torch.empty_like(dens)
     gl = torch.ones(1, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    names = ["bl_min", "bl_z", "bl_counts", "bl_select", "bl_grad(+reduce)"]
+    names = ["bl_min", "bl_z", "bl_counts", "bl_reduce_counts+bl_select", "bl_grad(+reduce)"]
     acc = np.zeros(len(names))
     for rep in range(reps + 1):
         flush.zero_()
@@ -297,15 +297,14 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)  # samples clocks / throttle reasons through warm-up, timed region and e2e
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
         flush.zero_()
     peak_ex2 = probe_peak("dgvcc_probe_ex2", dev)
     peak_ffma = probe_peak("dgvcc_probe_ffma", dev)
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
     events = []
@@ -319,7 +318,6 @@ def run_gpu(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     total_ms = sum(a.elapsed_time(c) for a, c in events)
-    clocks = sampler.stop() if rank == 0 else None
 
     # e2e
     for _ in range(3):
@@ -330,6 +328,7 @@ def run_gpu(args):
         step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
@@ -357,11 +356,11 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": global_batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (6 if packed.multi_chunk else 4),
+            "gpu_launches": args.steps * (7 if packed.multi_chunk else 5),
             "roofline": {
                 "bound": "sfu", "achieved": achieved / 1e9, "peak": peak_ex2 / 1e9, "unit": "Gexp/s",
                 "frac": achieved / peak_ex2, "traffic": None,
-                "note": ("fused BL path (bl_min+bl_z+bl_counts+bl_select+bl_grad), MUFU.EX2-bound; achieved = executed "
+                "note": ("fused BL path (bl_min+bl_z+bl_counts+bl_reduce_counts+bl_select+bl_grad+bl_grad_reduce), MUFU.EX2-bound; achieved = executed "
                          "exponentials / sum of kernel times; peak = dgvcc_probe_ex2 measured in this run "
                          "(MEASURED_PEAKS.json carries no SFU peak)"),
                 "algorithmic_exps_per_step": algorithmic, "executed_exps_per_step": executed,

@@ -460,10 +460,34 @@ __device__ __forceinline__ float block_sum_ordered(float v, float* scratch) {
     return total;  // valid on thread 0
 }
 
+// Expected counts: fixed-order sum of the per-tile partials (one thread per posterior row, coalesced
+// across rows), and the residual |t - c|  (bl.py:73-75).
+__global__ void __launch_bounds__(256)
+bl_reduce_counts_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
+                        const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
+                        float* __restrict__ counts, float* __restrict__ residual) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= total_rows) return;
+    const Meta mv = meta_view(meta, batch);
+    int lo = 0, hi = batch;  // image of row j: row_off[lo] <= j < row_off[lo+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (mv.row_off[mid] <= j) lo = mid; else hi = mid;
+    }
+    const int local = (int)(j - mv.row_off[lo]);
+    const int n_pts = mv.pt_off[lo + 1] - mv.pt_off[lo];
+    const float* p = cpart + j;
+    float c = 0.f;
+#pragma unroll 8
+    for (int tl = 0; tl < tiles; ++tl) c += p[(size_t)tl * total_rows];
+    const float tgt = (local < n_pts) ? targets[mv.pt_off[lo] + local] : 0.f;
+    counts[j] = c;
+    residual[j] = fabsf(__fadd_rn(tgt, -c));
+}
+
 __global__ void __launch_bounds__(SELECT_THREADS)
-bl_select_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
-                 const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
-                 float inv_batch, float* __restrict__ counts, float* __restrict__ residual,
+bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
+                 float inv_batch, const float* __restrict__ counts, const float* __restrict__ residual,
                  float* __restrict__ wsel, float* __restrict__ loss_img, float* __restrict__ loss_out,
                  unsigned int* __restrict__ ticket) {
     __shared__ unsigned int hist[256];
@@ -477,17 +501,6 @@ bl_select_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
     const int row0 = mv.row_off[img], n_rows = mv.row_off[img + 1] - row0;
     const int n_cand = n_rows - 1;  // res[:-1]; the last row is always kept (bl.py:77-78)
     const int n_keep = mv.keep[img];
-
-    // expected counts: fixed-order sum of the per-tile partials; residual |t - c|  (bl.py:73-75)
-    for (int j = tid; j < n_rows; j += SELECT_THREADS) {
-        const float* p = cpart + row0 + j;
-        float c = 0.f;
-        for (int tl = 0; tl < tiles; ++tl) c += p[(size_t)tl * total_rows];
-        const float tgt = (j < n_pts) ? targets[pt0 + j] : 0.f;
-        counts[row0 + j] = c;
-        residual[row0 + j] = fabsf(__fadd_rn(tgt, -c));
-    }
-    __syncthreads();
 
     // k-th smallest residual among the candidates: MSB-first radix select on the float bits
     unsigned int thr = 0xffffffffu;  // keep everything
@@ -900,10 +913,13 @@ int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const floa
 
 int launch_select(const dgvcc_bl_layout& L, const float* targets, const int32_t* meta, int batch,
                   int64_t total_rows, float inv_batch, int tiles, void* ws, float* loss_out, cudaStream_t st) {
+    bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
+        at<float>(ws, L.cpart), tiles, total_rows, meta, targets, batch, at<float>(ws, L.counts),
+        at<float>(ws, L.residual));
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     bl_select_kernel<<<batch, SELECT_THREADS, 0, st>>>(
-        at<float>(ws, L.cpart), tiles, total_rows, meta, targets, batch, inv_batch, at<float>(ws, L.counts),
-        at<float>(ws, L.residual), at<float>(ws, L.wsel), at<float>(ws, L.loss_img), loss_out,
-        at<unsigned int>(ws, L.ticket));
+        meta, targets, batch, inv_batch, at<float>(ws, L.counts), at<float>(ws, L.residual), at<float>(ws, L.wsel),
+        at<float>(ws, L.loss_img), loss_out, at<unsigned int>(ws, L.ticket));
     return (int)cudaGetLastError();
 }
 

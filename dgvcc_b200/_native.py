@@ -20,7 +20,7 @@ class BLLayout(ctypes.Structure):
     _fields_ = [(n, c_int64) for n in
                 ("amax", "rz", "pbg", "ebg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "zpart",
                  "minpart", "gpart", "total")] + \
-               [("tiles", c_int32), ("rows_per_thread", c_int32)]
+               [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("reserved_", c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/dgvcc_b200.h declares must appear here

@@ -2,17 +2,20 @@
 //
 // Replaces losses/bl.py (Post_Prob + Bay_Loss + autograd) of the reference without ever
 // materialising the [points x pixels] posterior.  Work decomposition ("pixel owner"):
-//   warp task  = (image, 32-column block, band of R grid rows); lane <-> grid column,
-//                each thread owns R pixels of one column in registers;
-//   the warp streams ALL points of its image through a private shared-memory tile
-//   (x, x*x and the R per-row y-distances of each point), so the inner loop per
-//   (point, pixel) pair is  FADD, FFMA, FMUL, MUFU.EX2, FADD/FFMA  -- MUFU-bound.
+//   warp task  = (point chunk of one image, block of 32*C grid columns, band of R grid rows);
+//                lane <-> grid column (C columns 32 apart per lane), each thread owns R*C pixels in
+//                registers;
+//   the warp streams the chunk's points through a private shared-memory tile (x, x*x and the R
+//   per-row y-distances of each point), so the inner loop per (point, pixel) pair is
+//   FADD, FFMA, FMUL, MUFU.EX2, FADD/FFMA.  ncu (profiles/) shows the kernels bound by the SM's MIO
+//   path that MUFU shares with LDS/SHFL, which is why each thread owns as many pixels as registers
+//   allow: 3 broadcast LDS feed R*C exponentials.
 // Sweeps over the points (dense, no culling):
 //   K0 bl_min_kernel    : per-chunk min_n dis (bl.py:39) -- only for images split into point chunks
 //   K1 bl_z_kernel      : softmax max incl. background row + denominator shares (bl.py:39-44)
 //   K2 bl_counts_kernel : expected counts c_n = sum_m D[m] p[n,m]   (bl.py:73), per-tile partials
-//   K3 bl_select_kernel : deterministic reduction of the partials, |t-c|, trimmed top-k
-//                         (radix select), loss (bl.py:75-79)
+//   K3 bl_reduce_counts_kernel + bl_select_kernel : deterministic reduction of the partials,
+//                         |t-c|, trimmed top-k (radix select), loss (bl.py:75-79)
 //   K4 bl_grad_kernel   : dL/dD[m] = g * sum_n w_n p[n,m]            (autograd of bl.py:73-79)
 // Big images are cut into equal point chunks (host-built table) so every warp task costs the same
 // and the CTA scheduler balances the ragged batch; per-chunk partial minima / denominators /
@@ -41,8 +44,8 @@ struct Scale {
 
 struct Geom {
     int hp, wp;        // grid rows, columns
-    int col_blocks;    // ceil(wp / 32)
-    int tiles;         // warp tasks per image = col_blocks * ceil(hp / R)
+    int col_blocks;    // ceil(wp / (32*C))
+    int tiles;         // warp tasks per (image, chunk) = col_blocks * ceil(hp / R)
     float stride;      // image pixels per grid cell
     float half;        // stride / 2
 };
@@ -110,14 +113,13 @@ struct TaskInfo {
     int pt_base;              // index of the chunk's first point in the packed arrays
     int p_start, p_cnt;       // chunk = points [p_start, p_start + p_cnt) of the image
     int chunk, first_chunk, n_chunks;
-    int col, row_base;        // this lane's column, first row of the band
-    bool col_ok;
+    int col0, row_base;       // this lane's first column, first row of the band
     int task;                 // pixel-tile index inside the image
 };
 
-// One warp task = (point chunk, 32-column block, band of R rows).  Chunks are equal-sized slices of
-// an image's points so that all tasks cost the same and the hardware CTA scheduler balances them.
-template <int R>
+// One warp task = (point chunk, block of 32*C columns, band of R rows).  Chunks are equal-sized slices
+// of an image's points so that all tasks cost the same and the hardware CTA scheduler balances them.
+template <int R, int C>
 __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, int batch, const Geom& g,
                                             TaskInfo& t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,9 +139,7 @@ __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, in
     t.row0 = mv.row_off[t.img];
     t.n_rows = mv.row_off[t.img + 1] - t.row0;
     const int jb = t.task % g.col_blocks, kb = t.task / g.col_blocks;
-    t.col = jb * 32 + lane;
-    t.col_ok = t.col < g.wp;
-    if (!t.col_ok) t.col = g.wp - 1;  // clamp: compute a duplicate, never store it
+    t.col0 = jb * 32 * C + lane;
     t.row_base = kb * R;
     return true;
 }
@@ -151,6 +151,7 @@ __device__ __forceinline__ void stage_points(WarpTile<R>& tile, const float2* __
                                              int limit, int padded, const float (&cym2)[R],
                                              const float (&cyy)[R]) {
     const int lane = threadIdx.x & 31;
+#pragma unroll 1
     for (int i = lane; i < padded; i += 32) {
         const int n = min(n0 + i, limit - 1);
         const float2 p = __ldg(&pts[n]);
@@ -169,6 +170,7 @@ __device__ __forceinline__ int stage_points_weighted(WarpTile<R>& tile, const fl
                                                      const float (&cym2)[R], const float (&cyy)[R]) {
     const int lane = threadIdx.x & 31;
     int kept = 0;
+#pragma unroll 1
     for (int base = 0; base < cnt; base += 32) {
         const int i = base + lane;
         const float wi = (i < cnt) ? __ldg(&w[n0 + i]) : 0.f;
@@ -202,76 +204,89 @@ __device__ __forceinline__ void load_yd(const WarpTile<R>& tile, int i, float (&
     }
 }
 
-// Per-thread constants of the pixel tile: row centres (-2*cy, cy*cy), column centre, pixel indices.
-template <int R>
+// Per-thread constants of the pixel tile: R row centres, C column centres (as -2c and c*c).
+// Pixel (r, c) of the thread is grid cell (row_base + r, col0 + 32 c); cells past the grid edge are
+// clamped onto the last row / column (a finite duplicate that is computed but never stored).
+template <int R, int C>
 struct PixelTile {
-    float cym2[R], cyy[R], cxm2, cxx;
-    int pix[R];     // index of pixel r inside the image (clamped rows/cols duplicate a valid pixel)
-    bool ok[R];     // pixel really exists and is owned by this thread
+    float cym2[R], cyy[R], cxm2[C], cxx[C];
+    int col[C];       // clamped column index
+    int row_base, hp, wp, col0;
 
     __device__ __forceinline__ void init(const TaskInfo& t, const Geom& g) {
+        row_base = t.row_base; hp = g.hp; wp = g.wp; col0 = t.col0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int row = min(t.row_base + r, g.hp - 1);
-            const float cy = cell_centre(row, g);
+            const float cy = cell_centre(min(t.row_base + r, g.hp - 1), g);
             cym2[r] = -2.0f * cy;
             cyy[r] = __fmul_rn(cy, cy);
-            pix[r] = row * g.wp + t.col;
-            ok[r] = t.col_ok && (t.row_base + r < g.hp);
         }
-        const float cx = cell_centre(t.col, g);
-        cxm2 = -2.0f * cx;
-        cxx = __fmul_rn(cx, cx);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            col[c] = min(t.col0 + 32 * c, g.wp - 1);
+            const float cx = cell_centre(col[c], g);
+            cxm2[c] = -2.0f * cx;
+            cxx[c] = __fmul_rn(cx, cx);
+        }
     }
+    __device__ __forceinline__ int pix(int r, int c) const { return min(row_base + r, hp - 1) * wp + col[c]; }
+    __device__ __forceinline__ bool ok(int r, int c) const { return row_base + r < hp && col0 + 32 * c < wp; }
 };
 
-// min over the chunk's points of the squared distance (bl.py:39), into mind[]
-template <int R>
-__device__ __forceinline__ void sweep_min(WarpTile<R>& tile, const PixelTile<R>& px, const float2* pts, int cnt_total,
-                                          float (&mind)[R]) {
+// min over the chunk's points of the squared distance (bl.py:39), into mind[r][c]
+template <int R, int C>
+__device__ __forceinline__ void sweep_min(WarpTile<R>& tile, const PixelTile<R, C>& px, const float2* pts,
+                                          int cnt_total, float (&mind)[R][C]) {
     for (int n0 = 0; n0 < cnt_total; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, cnt_total - n0);
         __syncwarp();
         stage_points<R>(tile, pts, n0, cnt_total, cnt, px.cym2, px.cyy);
         __syncwarp();
-#pragma unroll 4
+#pragma unroll 2
         for (int i = 0; i < cnt; ++i) {
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
-            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
-            for (int r = 0; r < R; ++r) mind[r] = fminf(mind[r], __fadd_rn(yd[r], xd));
+            for (int c = 0; c < C; ++c) {
+                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) mind[r][c] = fminf(mind[r][c], __fadd_rn(yd[r], xd));
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------ K0
 // Only for images split into several point chunks: per-chunk partial minima.
-template <int R>
+template <int R, int C>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
               float* __restrict__ minpart) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t)) return;
     if (t.n_chunks <= 1) return;  // single-chunk images take the fused path inside bl_z_kernel
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
-    PixelTile<R> px;
+    PixelTile<R, C> px;
     px.init(t, g);
-    float mind[R];
+    float mind[R][C];
 #pragma unroll
-    for (int r = 0; r < R; ++r) mind[r] = __int_as_float(0x7f800000);
-    sweep_min<R>(tile, px, pts_all + t.pt_base, t.p_cnt, mind);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) mind[r][c] = __int_as_float(0x7f800000);
+    sweep_min<R, C>(tile, px, pts_all + t.pt_base, t.p_cnt, mind);
     float* out = minpart + (size_t)t.chunk * g.hp * g.wp;
 #pragma unroll
     for (int r = 0; r < R; ++r)
-        if (px.ok[r]) out[px.pix[r]] = mind[r];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            if (px.ok(r, c)) out[px.pix(r, c)] = mind[r][c];
 }
 
 // ------------------------------------------------------------------------------------------ K1
 // Softmax max (incl. the background row, bl.py:39-43) and this chunk's share of the denominator.
-template <int R, bool POW2>
+template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
@@ -279,10 +294,10 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
             float* __restrict__ ebg_out) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t)) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
-    PixelTile<R> px;
+    PixelTile<R, C> px;
     px.init(t, g);
     float* zout = zpart + (size_t)t.chunk * M;
     float* amax_img = amax_out + (size_t)t.img * M;
@@ -291,44 +306,60 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
     if (t.n_img_pts == 0) {  // bl.py:63-65: the only row is "sum of density": posterior == 1
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (px.ok[r]) { zout[px.pix[r]] = 0.f; amax_img[px.pix[r]] = 0.f; ebg_img[px.pix[r]] = 1.f; }
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (px.ok(r, c)) {
+                    const int p = px.pix(r, c);
+                    zout[p] = 0.f; amax_img[p] = 0.f; ebg_img[p] = 1.f;
+                }
         return;
     }
     const float2* pts = pts_all + t.pt_base;
 
-    float mind[R];
+    float neg_amax[R][C];  // first holds min dis, then -max of the softmax arguments
     if (t.n_chunks == 1) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) mind[r] = __int_as_float(0x7f800000);
-        sweep_min<R>(tile, px, pts, t.p_cnt, mind);
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) neg_amax[r][c] = __int_as_float(0x7f800000);
+        sweep_min<R, C>(tile, px, pts, t.p_cnt, neg_amax);
     } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float m = __int_as_float(0x7f800000);
-            for (int c = 0; c < t.n_chunks; ++c) m = fminf(m, minpart[(size_t)(t.first_chunk + c) * M + px.pix[r]]);
-            mind[r] = m;
-        }
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int p = px.pix(r, c);
+                float m = __int_as_float(0x7f800000);
+                for (int ch = 0; ch < t.n_chunks; ++ch) m = fminf(m, minpart[(size_t)(t.first_chunk + ch) * M + p]);
+                neg_amax[r][c] = m;
+            }
     }
 
-    float neg_amax[R], a_bg[R];
+    float ebg_arg[R][C];  // (a_bg - amax) * log2(e)
     const float dbg = __fmul_rn(st_sizes[t.img], bg_ratio);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        float amax = neg_div<POW2>(mind[r], k);
-        a_bg[r] = 0.f;
-        if (use_bg) {
-            const float root = __fsqrt_rn(fmaxf(mind[r], 0.0f));
-            const float diff = __fadd_rn(dbg, -root);
-            a_bg[r] = neg_div<POW2>(__fmul_rn(diff, diff), k);
-            amax = fmaxf(amax, a_bg[r]);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float mind = neg_amax[r][c];
+            float amax = neg_div<POW2>(mind, k);
+            float a_bg = 0.f;
+            if (use_bg) {
+                const float root = __fsqrt_rn(fmaxf(mind, 0.0f));
+                const float diff = __fadd_rn(dbg, -root);
+                a_bg = neg_div<POW2>(__fmul_rn(diff, diff), k);
+                amax = fmaxf(amax, a_bg);
+            }
+            neg_amax[r][c] = -amax;
+            ebg_arg[r][c] = __fmul_rn(__fadd_rn(a_bg, -amax), LOG2E);
         }
-        neg_amax[r] = -amax;
-    }
 
     // denominator share, accumulated in point order like torch's dim-0 softmax
-    float z[R];
+    float z[R][C];
 #pragma unroll
-    for (int r = 0; r < R; ++r) z[r] = 0.f;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[r][c] = 0.f;
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
@@ -339,32 +370,40 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
-            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
-            for (int r = 0; r < R; ++r) z[r] += pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k);
+            for (int c = 0; c < C; ++c) {
+                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) z[r][c] += pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r][c], k);
+            }
         }
     }
+    const bool first = t.chunk == t.first_chunk;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (!px.ok[r]) continue;
-        zout[px.pix[r]] = z[r];
-        if (t.chunk == t.first_chunk) {
-            amax_img[px.pix[r]] = -neg_amax[r];
-            ebg_img[px.pix[r]] = use_bg ? ex2_ftz(__fmul_rn(__fadd_rn(a_bg[r], neg_amax[r]), LOG2E)) : 0.f;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (!px.ok(r, c)) continue;
+            const int p = px.pix(r, c);
+            zout[p] = z[r][c];
+            if (first) {
+                amax_img[p] = -neg_amax[r][c];
+                ebg_img[p] = use_bg ? ex2_ftz(ebg_arg[r][c]) : 0.f;
+            }
         }
-    }
 }
 
 // 1 / (sum of the chunk shares in chunk order + background term last), the reference's row order.
 __device__ __forceinline__ float softmax_rz(const float* __restrict__ zpart, size_t M, int first_chunk, int n_chunks,
                                             int pix, float ebg) {
     float z = 0.f;
+#pragma unroll 1
     for (int c = 0; c < n_chunks; ++c) z += zpart[(size_t)(first_chunk + c) * M + pix];
     return 1.0f / (z + ebg);
 }
 
 // ------------------------------------------------------------------------------------------ K2
-template <int R, bool POW2>
+template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
                  const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg,
@@ -373,30 +412,34 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
                  int64_t total_rows, float* __restrict__ cpart) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t)) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
-    PixelTile<R> px;
+    PixelTile<R, C> px;
     px.init(t, g);
     float* part = cpart + (size_t)t.task * total_rows + t.row0;
     const bool first = t.chunk == t.first_chunk;
 
     // per-pixel weights D[m]/Z[m]; pixels outside the grid get weight 0
-    float neg_amax[R], wd[R], bg_part = 0.f;
+    float neg_amax[R][C], wd[R][C], bg_part = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const size_t m = img_base + px.pix[r];
-        const float d = px.ok[r] ? density[m] : 0.f;
-        const float ebg = ebg_in[m];
-        const float rz = softmax_rz(zpart, M, t.first_chunk, t.n_chunks, px.pix[r], ebg);
-        const float pbg = ebg * rz;
-        neg_amax[r] = -amax_in[m];
-        wd[r] = d * rz;
-        bg_part = fmaf(d, pbg, bg_part);
-        if (first && px.ok[r]) { rz_out[m] = rz; pbg_out[m] = pbg; }
-    }
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int p = px.pix(r, c);
+            const size_t m = img_base + p;
+            const bool ok = px.ok(r, c);
+            const float d = ok ? density[m] : 0.f;
+            const float ebg = ebg_in[m];
+            const float rz = softmax_rz(zpart, M, t.first_chunk, t.n_chunks, p, ebg);
+            const float pbg = ebg * rz;
+            neg_amax[r][c] = -amax_in[m];
+            wd[r][c] = d * rz;
+            bg_part = fmaf(d, pbg, bg_part);
+            if (first && ok) { rz_out[m] = rz; pbg_out[m] = pbg; }
+        }
     if (first && (use_bg || t.n_img_pts == 0)) {  // background row / sum-of-density row of an empty image
         bg_part = warp_sum(bg_part);
         if (lane == 0) part[t.n_rows - 1] = bg_part;
@@ -411,6 +454,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
         __syncwarp();
         stage_points<R>(tile, pts, n0, t.p_cnt, padded, px.cym2, px.cyy);
         __syncwarp();
+#pragma unroll 1
         for (int i0 = 0; i0 < padded; i0 += 8) {
             float v[8];
 #pragma unroll
@@ -418,11 +462,14 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
                 const float2 xs = tile.xs[i0 + u];
                 float yd[R];
                 load_yd<R>(tile, i0 + u, yd);
-                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
                 float s = 0.f;
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    s = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k), wd[r], s);
+                for (int c = 0; c < C; ++c) {
+                    const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        s = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r][c], k), wd[r][c], s);
+                }
                 v[u] = s;
             }
             // transpose-reduce: 8 per-lane partials -> lane quad q holds the warp total of point i0+q
@@ -600,7 +647,7 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
 // dL/dD[m] = g * (sum_n w_n e[n,m] / Z[m] + w_bg p_bg[m]).  Trimmed points (w == 0, bl.py:77) are
 // compacted away while staging.  Single-chunk images store the final gradient; otherwise the raw
 // chunk sum goes to gpart and bl_grad_reduce_kernel finishes.
-template <int R, bool POW2>
+template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
                Scale k, int use_bg, float inv_batch, const float* __restrict__ grad_loss,
@@ -609,19 +656,21 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
                float* __restrict__ gpart, float* __restrict__ grad_density) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t)) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
-    PixelTile<R> px;
+    PixelTile<R, C> px;
     px.init(t, g);
 
-    float acc[R], neg_amax[R];
+    float acc[R][C], neg_amax[R][C];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        neg_amax[r] = -amax_in[img_base + px.pix[r]];
-        acc[r] = 0.f;
-    }
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            neg_amax[r][c] = -amax_in[img_base + px.pix(r, c)];
+            acc[r][c] = 0.f;
+        }
 
     const float2* pts = pts_all + t.pt_base;
     const float* w_pts = wsel + t.row0 + t.p_start;
@@ -636,10 +685,13 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
-            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                acc[r] = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k), w, acc[r]);
+            for (int c = 0; c < C; ++c) {
+                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    acc[r][c] = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r][c], k), w, acc[r][c]);
+            }
         }
     }
 
@@ -648,16 +700,20 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
         const bool has_bg_row = use_bg || t.n_img_pts == 0;
         const float w_bg = has_bg_row ? wsel[t.row0 + t.n_rows - 1] : 0.f;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (!px.ok[r]) continue;
-            const size_t m = img_base + px.pix[r];
-            grad_density[m] = gscale * fmaf(acc[r], rz_in[m], w_bg * pbg_in[m]);
-        }
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (!px.ok(r, c)) continue;
+                const size_t m = img_base + px.pix(r, c);
+                grad_density[m] = gscale * fmaf(acc[r][c], rz_in[m], w_bg * pbg_in[m]);
+            }
     } else {
         float* out = gpart + (size_t)t.chunk * M;
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (px.ok[r]) out[px.pix[r]] = acc[r];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (px.ok(r, c)) out[px.pix(r, c)] = acc[r][c];
     }
 }
 
@@ -697,29 +753,32 @@ bl_finish_z_kernel(const int32_t* __restrict__ meta, int batch, int M, const flo
     pbg_out[m] = ebg * rz;
 }
 
-template <int R, bool POW2>
+template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_posterior_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
                     Scale k, int use_bg, const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                     const float* __restrict__ pbg_in, float* __restrict__ prob_out) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t)) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
-    PixelTile<R> px;
+    PixelTile<R, C> px;
     px.init(t, g);
     float* prob = prob_out + (size_t)t.row0 * M;
 
-    float neg_amax[R], rz[R];
+    float neg_amax[R][C], rz[R][C];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        neg_amax[r] = -amax_in[img_base + px.pix[r]];
-        rz[r] = rz_in[img_base + px.pix[r]];
-        if (px.ok[r] && t.chunk == t.first_chunk && (use_bg || t.n_img_pts == 0))
-            prob[(size_t)(t.n_rows - 1) * M + px.pix[r]] = pbg_in[img_base + px.pix[r]];
-    }
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int p = px.pix(r, c);
+            neg_amax[r][c] = -amax_in[img_base + p];
+            rz[r][c] = rz_in[img_base + p];
+            if (px.ok(r, c) && t.chunk == t.first_chunk && (use_bg || t.n_img_pts == 0))
+                prob[(size_t)(t.n_rows - 1) * M + p] = pbg_in[img_base + p];
+        }
     const float2* pts = pts_all + t.pt_base;
     prob += (size_t)t.p_start * M;
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
@@ -727,15 +786,19 @@ bl_posterior_kernel(const float2* __restrict__ pts_all, const int32_t* __restric
         __syncwarp();
         stage_points<R>(tile, pts, n0, t.p_cnt, cnt, px.cym2, px.cyy);
         __syncwarp();
+#pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
-            const float xd = axis_sqdist(xs.x, xs.y, px.cxm2, px.cxx);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float p = pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r], k) * rz[r];
-                if (px.ok[r]) prob[(size_t)(n0 + i) * M + px.pix[r]] = p;
+            for (int c = 0; c < C; ++c) {
+                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float p = pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r][c], k) * rz[r][c];
+                    if (px.ok(r, c)) prob[(size_t)(n0 + i) * M + px.pix(r, c)] = p;
+                }
             }
         }
     }
@@ -793,21 +856,27 @@ static Scale make_scale(float sigma) {
     return k;
 }
 
-// Rows per thread: the largest band that still yields ~16 warp tasks per SM.
-static int pick_rows_per_thread(int total_chunks, int hp, int wp) {
-    const long col_blocks = ceil_div(wp, 32);
-    const long want = 148L * 16;
-    for (int r : {8, 4}) {
-        if ((long)total_chunks * col_blocks * ceil_div(hp, r) >= want) return r;
-    }
-    return 2;
+// Pixel tile per thread (rows x columns): the largest one that still yields ~16 warp tasks per SM.
+// More pixels per thread = fewer LDS per exponential (the kernels are bound by the MIO path).
+struct Variant { int rows, cols; };
+static const Variant kVariants[] = {{8, 2}, {8, 1}, {4, 1}, {2, 1}};
+
+static long variant_tasks(const Variant& v, int total_chunks, int hp, int wp) {
+    return (long)total_chunks * ceil_div(wp, 32 * v.cols) * ceil_div(hp, v.rows);
 }
 
-static Geom make_geom(int hp, int wp, int R, float stride) {
+static Variant pick_variant(int total_chunks, int hp, int wp) {
+    const long want = 148L * 16;
+    for (const Variant& v : kVariants)
+        if (variant_tasks(v, total_chunks, hp, wp) >= want) return v;
+    return kVariants[3];
+}
+
+static Geom make_geom(int hp, int wp, const Variant& v, float stride) {
     Geom g;
     g.hp = hp; g.wp = wp;
-    g.col_blocks = ceil_div(wp, 32);
-    g.tiles = g.col_blocks * ceil_div(hp, R);
+    g.col_blocks = ceil_div(wp, 32 * v.cols);
+    g.tiles = g.col_blocks * ceil_div(hp, v.rows);
     g.stride = stride;
     g.half = stride / 2.0f;
     return g;
@@ -815,8 +884,8 @@ static Geom make_geom(int hp, int wp, int R, float stride) {
 
 static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, dgvcc_bl_layout* L) {
     if (!L || total_rows < batch || total_chunks < batch || batch <= 0 || hp <= 0 || wp <= 0) return DGVCC_ERR_ARG;
-    const int R = pick_rows_per_thread(total_chunks, hp, wp);
-    const int tiles = make_geom(hp, wp, R, 1.f).tiles;
+    const Variant v = pick_variant(total_chunks, hp, wp);
+    const int tiles = make_geom(hp, wp, v, 1.f).tiles;
     const size_t M = (size_t)hp * wp;
     const size_t pix = (size_t)batch * M * sizeof(float);
     const size_t rows = (size_t)total_rows * sizeof(float);
@@ -833,7 +902,8 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     L->gpart = L->minpart;  // minima are dead once the denominators exist; backward re-uses the region
     L->total = (int64_t)off;
     L->tiles = tiles;
-    L->rows_per_thread = R;
+    L->rows_per_thread = v.rows;
+    L->cols_per_thread = v.cols;
     return DGVCC_OK;
 }
 
@@ -846,25 +916,25 @@ static T* at(const void* ws, int64_t off) { return reinterpret_cast<T*>((char*)w
 using namespace dgvcc;
 using namespace dgvcc::bl;
 
-extern "C" int dgvcc_abi_version(void) { return 2; }
+extern "C" int dgvcc_abi_version(void) { return 3; }
 
 extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                                          dgvcc_bl_layout* out) {
     return layout(total_rows, total_chunks, batch, hp, wp, out);
 }
 
-#define BL_DISPATCH(R_, POW2_, KERNEL, GRID, STREAM, ...)                                      \
-    do {                                                                                       \
-        if ((R_) == 8) {                                                                       \
-            if (POW2_) KERNEL<8, true><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);         \
-            else KERNEL<8, false><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);              \
-        } else if ((R_) == 4) {                                                                \
-            if (POW2_) KERNEL<4, true><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);         \
-            else KERNEL<4, false><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);              \
-        } else {                                                                               \
-            if (POW2_) KERNEL<2, true><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);         \
-            else KERNEL<2, false><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);              \
-        }                                                                                      \
+// KERNEL<R, C, POW2> for the (rows, cols) variant chosen by pick_variant()
+#define BL_LAUNCH_RC(R_, C_, POW2_, KERNEL, GRID, STREAM, ...)                              \
+    do {                                                                                    \
+        if (POW2_) KERNEL<R_, C_, true><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);     \
+        else KERNEL<R_, C_, false><<<GRID, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);          \
+    } while (0)
+#define BL_DISPATCH(V_, POW2_, KERNEL, GRID, STREAM, ...)                                              \
+    do {                                                                                               \
+        if ((V_).rows == 8 && (V_).cols == 2) BL_LAUNCH_RC(8, 2, POW2_, KERNEL, GRID, STREAM, __VA_ARGS__); \
+        else if ((V_).rows == 8) BL_LAUNCH_RC(8, 1, POW2_, KERNEL, GRID, STREAM, __VA_ARGS__);         \
+        else if ((V_).rows == 4) BL_LAUNCH_RC(4, 1, POW2_, KERNEL, GRID, STREAM, __VA_ARGS__);         \
+        else BL_LAUNCH_RC(2, 1, POW2_, KERNEL, GRID, STREAM, __VA_ARGS__);                             \
     } while (0)
 
 namespace {
@@ -873,7 +943,7 @@ struct Plan {
     dgvcc_bl_layout L;
     Geom g;
     Scale k;
-    int R;
+    Variant v;
     bool pow2;
     dim3 grid;
 };
@@ -885,29 +955,35 @@ int make_plan(const void* a, const void* b, const void* ws, size_t ws_bytes, int
     int rc = layout(total_rows, total_chunks, batch, hp, wp, &p->L);
     if (rc) return rc;
     if (ws_bytes < (size_t)p->L.total) return DGVCC_ERR_WORKSPACE;
-    p->R = p->L.rows_per_thread;
-    p->g = make_geom(hp, wp, p->R, stride);
+    p->v = Variant{p->L.rows_per_thread, p->L.cols_per_thread};
+    p->g = make_geom(hp, wp, p->v, stride);
     p->k = make_scale(sigma);
     p->pow2 = is_pow2(p->k.s);
     p->grid = dim3(ceil_div(p->g.tiles, WARPS_PER_CTA), total_chunks);
     return DGVCC_OK;
 }
 
+inline void mark(void** events, int i, cudaStream_t st) {
+    if (events && events[i]) cudaEventRecord((cudaEvent_t)events[i], st);
+}
+
 // partial minima (multi-chunk images only) + softmax max / denominator shares
 int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
              int multi_chunk, float bg_ratio, int use_bg, void* ws, cudaStream_t st, void** events = nullptr) {
     float* minpart = at<float>(ws, p.L.minpart);
-    if (events && events[0]) cudaEventRecord((cudaEvent_t)events[0], st);
+    const float2* pts = (const float2*)pts_xy;
+    mark(events, 0, st);
     if (multi_chunk) {
-        if (p.R == 8) bl_min_kernel<8><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
-        else if (p.R == 4) bl_min_kernel<4><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
-        else bl_min_kernel<2><<<p.grid, CTA_THREADS, 0, st>>>((const float2*)pts_xy, meta, batch, p.g, minpart);
+        if (p.v.rows == 8 && p.v.cols == 2) bl_min_kernel<8, 2><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
+        else if (p.v.rows == 8) bl_min_kernel<8, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
+        else if (p.v.rows == 4) bl_min_kernel<4, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
+        else bl_min_kernel<2, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
-    if (events && events[1]) cudaEventRecord((cudaEvent_t)events[1], st);
-    BL_DISPATCH(p.R, p.pow2, bl_z_kernel, p.grid, st, (const float2*)pts_xy, meta, st_sizes, batch, p.g, p.k,
-                bg_ratio, use_bg, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg));
-    if (events && events[2]) cudaEventRecord((cudaEvent_t)events[2], st);
+    mark(events, 1, st);
+    BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
+                minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg));
+    mark(events, 2, st);
     return (int)cudaGetLastError();
 }
 
@@ -925,10 +1001,6 @@ int launch_select(const dgvcc_bl_layout& L, const float* targets, const int32_t*
 
 }  // namespace
 
-static inline void mark(void** events, int i, cudaStream_t st) {
-    if (events && events[i]) cudaEventRecord((cudaEvent_t)events[i], st);
-}
-
 extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targets, const int32_t* meta,
                                          const float* st_sizes, const float* density, int batch, int hp, int wp,
                                          int64_t total_rows, int total_chunks, int multi_chunk, float stride,
@@ -941,7 +1013,7 @@ extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targe
     if (!st_sizes || !loss_out || !pts_xy || !targets) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, workspace, st, events))) return rc;
-    BL_DISPATCH(p.R, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
+    BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
                 use_bg, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.zpart),
                 at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
                 at<float>(workspace, p.L.cpart));
@@ -972,7 +1044,7 @@ extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int b
     if (rc) return rc;
     if (!grad_density || !pts_xy) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    BL_DISPATCH(p.R, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
+    BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
                 inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                 at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
                 grad_density);
@@ -1003,7 +1075,7 @@ extern "C" int dgvcc_bl_posterior(const float* pts_xy, const int32_t* meta, cons
         meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.rz),
         at<float>(workspace, p.L.pbg));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    BL_DISPATCH(p.R, p.pow2, bl_posterior_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
+    BL_DISPATCH(p.v, p.pow2, bl_posterior_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
                 at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), prob_out);
     return (int)cudaGetLastError();
 }

@@ -73,7 +73,9 @@ typedef struct dgvcc_bl_layout {
     int64_t gpart;     /* [C*hp*wp] f32  per-chunk gradient sums (aliases minpart)   */
     int64_t total;     /* bytes needed                                               */
     int32_t tiles;     /* pixel tiles per image                                      */
-    int32_t rows_per_thread; /* kernel variant chosen for this shape                 */
+    int32_t rows_per_thread; /* kernel variant chosen for this shape: grid rows ...   */
+    int32_t cols_per_thread; /* ... and columns owned by one thread                  */
+    int32_t reserved_;
 } dgvcc_bl_layout;
 
 int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,

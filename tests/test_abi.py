@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _native.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_native.SIGNATURES) == set(names)
-    assert lib.dgvcc_abi_version() >= 2
+    assert lib.dgvcc_abi_version() >= 3
 
 
 def test_workspace_layout_is_host_only_and_consistent():
@@ -30,7 +30,7 @@ def test_workspace_layout_is_host_only_and_consistent():
     offs = [lay.amax, lay.rz, lay.pbg, lay.ebg, lay.counts, lay.wsel, lay.residual, lay.loss_img, lay.ticket,
             lay.cpart, lay.zpart, lay.minpart]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.total > offs[-1]
-    assert lay.rows_per_thread in (2, 4, 8) and lay.tiles > 0
+    assert lay.rows_per_thread in (2, 4, 8) and lay.cols_per_thread in (1, 2) and lay.tiles > 0
     assert _native.lib().dgvcc_bl_workspace_layout(0, 1, 1, 8, 8, lay) == -1  # DGVCC_ERR_ARG
 
 

@@ -7,7 +7,7 @@ the call raises.
 import ctypes
 import os
 import threading
-from ctypes import POINTER, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 from . import build as _build
 
@@ -41,6 +41,10 @@ SIGNATURES = {
                                          c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_bl_bayloss_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_void_p,
                                           c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_dmap_knn_sigma": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgvcc_dmap_workspace_bytes": (c_size_t, [c_int]),
+    "dgvcc_dmap_splat": (c_int, [c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_void_p, c_size_t,
+                                 c_void_p, c_void_p]),
     "dgvcc_probe_ex2": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
     "dgvcc_probe_ffma": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
 }

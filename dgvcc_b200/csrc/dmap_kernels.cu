@@ -1,0 +1,243 @@
+// Geometry-adaptive density-map generation for sm_100a.
+//
+// Replaces utils/dmap_gen.py:14-81 of the reference (scipy KDTree k=4 query + one full-image
+// scipy.ndimage.gaussian_filter per head) by
+//   dmap_knn_kernel     : brute-force tiled 4-nearest search in fp64 (self included, like
+//                         KDTree.query(points, k=4)), sigma = 0.1*(d1+d2+d3)        dmap_gen.py:34-48
+//   dmap_prepare_kernel : per head: truncated pixel index, in-bounds test, kernel radius
+//                         int(truncate*sigma+0.5) and the normaliser of scipy's 1-D Gaussian kernel,
+//                         summed in numpy's pairwise order                             dmap_gen.py:41-49
+//   dmap_splat_kernel   : one CTA per 32x32 output tile gathers the heads whose stamp overlaps it, in
+//                         index order, and accumulates fl32(f64(fl32(w[dy])) * w[dx]) per pixel in
+//                         fp32 -- the closed form of gaussian_filter on a one-hot image.
+//                         Every output pixel is written exactly once (zero fill fused), coalesced.
+// All fp64 arithmetic uses explicit _rn intrinsics (no FMA contraction): scipy's wheels are baseline
+// x86-64 without FMA, and the neighbour indices must match bit for bit.
+#include <math.h>
+
+#include "common.cuh"
+#include "../../include/dgvcc_b200.h"
+
+namespace dgvcc {
+namespace dmap {
+
+constexpr int KNN_THREADS = 256;
+
+// ---------------------------------------------------------------------------------- kNN + sigma
+__global__ void __launch_bounds__(KNN_THREADS)
+dmap_knn_kernel(const double2* __restrict__ pts, int n, int32_t* __restrict__ nn_idx,
+                double* __restrict__ nn_dist, double* __restrict__ sigma) {
+    __shared__ double2 cand[KNN_THREADS];
+    const int i = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const double2 q = pts[min(i, n - 1)];
+    double best[4];
+    int bidx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best[k] = INFINITY; bidx[k] = n; }  // scipy: missing neighbour = (inf, N)
+
+    for (int j0 = 0; j0 < n; j0 += KNN_THREADS) {
+        __syncthreads();
+        if (j0 + threadIdx.x < n) cand[threadIdx.x] = pts[j0 + threadIdx.x];
+        __syncthreads();
+        const int lim = min(KNN_THREADS, n - j0);
+        for (int t = 0; t < lim; ++t) {
+            const double dx = __dsub_rn(q.x, cand[t].x);
+            const double dy = __dsub_rn(q.y, cand[t].y);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 < best[3]) {  // candidates arrive in index order, so ties keep the lower index
+                best[3] = d2; bidx[3] = j0 + t;
+#pragma unroll
+                for (int k = 3; k > 0; --k) {
+                    if (best[k] < best[k - 1]) {
+                        const double tb = best[k]; best[k] = best[k - 1]; best[k - 1] = tb;
+                        const int ti = bidx[k]; bidx[k] = bidx[k - 1]; bidx[k - 1] = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (i >= n) return;
+    double d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        d[k] = __dsqrt_rn(best[k]);
+        nn_idx[4 * i + k] = bidx[k];
+        nn_dist[4 * i + k] = d[k];
+    }
+    // dmap_gen.py:45-48: (d1 + d2 + d3) * 0.1 when there are more than 3 heads, else 15
+    sigma[i] = (n > 3) ? __dmul_rn(__dadd_rn(__dadd_rn(d[1], d[2]), d[3]), 0.1) : 15.0;
+}
+
+// ---------------------------------------------------------------------------- per-head stamp data
+struct Stamp {
+    int ix, iy;      // pixel of the one-hot write (dmap_gen.py:42), after numpy's negative-index wrap
+    int radius;      // int(truncate * sigma + 0.5); -1 marks a skipped head (dmap_gen.py:41-44)
+    int pad_;
+    double coef;     // -0.5 / sigma^2
+    double norm;     // sum of exp(coef * i^2), i = -radius..radius, in numpy's pairwise order
+};
+
+__device__ __forceinline__ double phi(double coef, int i) {
+    return exp(__dmul_rn(coef, (double)((long long)i * i)));
+}
+
+// numpy's pairwise summation (DOUBLE_pairwise_sum) of phi(first), phi(first+1), ...: n elements.
+__device__ double pairwise_phi_sum(double coef, int first, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, phi(coef, first + i));
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = phi(coef, first + j);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], phi(coef, first + i + j));
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, phi(coef, first + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const double a = pairwise_phi_sum(coef, first, n2);
+    const double b = pairwise_phi_sum(coef, first + n2, n - n2);
+    return __dadd_rn(a, b);
+}
+
+__global__ void __launch_bounds__(128)
+dmap_prepare_kernel(const double2* __restrict__ pts, const double* __restrict__ sigma, double fixed_sigma,
+                    double truncate, int n, int height, int width, Stamp* __restrict__ stamps) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const double2 p = pts[i];
+    Stamp s;
+    s.pad_ = 0;
+    s.ix = (int)p.x;  // Python int(): truncation toward zero
+    s.iy = (int)p.y;
+    const bool keep = s.iy < height && s.ix < width;
+    if (s.iy < 0) s.iy += height;  // numpy wraps negative indices; the host wrapper rejects < -size like numpy
+    if (s.ix < 0) s.ix += width;
+    const double sd = sigma ? sigma[i] : fixed_sigma;
+    if (!keep || s.iy < 0 || s.ix < 0) {
+        s.radius = -1; s.coef = 0.0; s.norm = 1.0;
+    } else if (!(sd > 1e-15)) {  // scipy: sigma <= 1e-15 copies the input (identity filter)
+        s.radius = 0; s.coef = 0.0; s.norm = 1.0;
+    } else {
+        s.radius = (int)__dadd_rn(__dmul_rn(truncate, sd), 0.5);
+        s.coef = -0.5 / __dmul_rn(sd, sd);
+        s.norm = pairwise_phi_sum(s.coef, -s.radius, 2 * s.radius + 1);
+    }
+    stamps[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------ splat
+constexpr int TILE = 32;
+constexpr int SPLAT_THREADS = 256;
+constexpr int GROUP = 8;  // heads whose tile weights are staged together
+
+__global__ void __launch_bounds__(SPLAT_THREADS)
+dmap_splat_kernel(const Stamp* __restrict__ stamps, int n, int height, int width, float* __restrict__ density) {
+    __shared__ int list[SPLAT_THREADS];
+    __shared__ int warp_cnt[SPLAT_THREADS / 32];
+    __shared__ double wy[GROUP][TILE];  // fl32-rounded row weights, widened again (exact)
+    __shared__ double wx[GROUP][TILE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // pixels (y0 + warp + 8k, x0 + lane)
+
+    for (int base = 0; base < n; base += SPLAT_THREADS) {
+        // heads of this batch whose stamp overlaps the tile, compacted in index order
+        const int i = base + tid;
+        bool hit = false;
+        if (i < n) {
+            const Stamp s = stamps[i];
+            hit = s.radius >= 0 && s.ix + s.radius >= x0 && s.ix - s.radius < x0 + TILE &&
+                  s.iy + s.radius >= y0 && s.iy - s.radius < y0 + TILE;
+        }
+        const unsigned int ballot = __ballot_sync(FULL_MASK, hit);
+        if (lane == 0) warp_cnt[warp] = __popc(ballot);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SPLAT_THREADS / 32; ++w) {
+            if (w < warp) before += warp_cnt[w];
+            total += warp_cnt[w];
+        }
+        if (hit) list[before + __popc(ballot & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+
+        for (int g0 = 0; g0 < total; g0 += GROUP) {
+            const int gcnt = min(GROUP, total - g0);
+            // stage the tile's 32 row and 32 column weights of each head of the group
+            for (int k = tid; k < gcnt * 2 * TILE; k += SPLAT_THREADS) {
+                const int h = k / (2 * TILE), which = (k / TILE) & 1, off = k % TILE;
+                const Stamp s = stamps[list[g0 + h]];
+                const int d = which ? (x0 + off - s.ix) : (y0 + off - s.iy);
+                double w = 0.0;
+                if (d >= -s.radius && d <= s.radius) w = __ddiv_rn(phi(s.coef, d), s.norm);
+                if (which) wx[h][off] = w;
+                else wy[h][off] = (double)(float)w;  // first filter pass stores float32 (output dtype)
+            }
+            __syncthreads();
+            for (int h = 0; h < gcnt; ++h) {
+                const double cx = wx[h][lane];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc[k] = __fadd_rn(acc[k], (float)__dmul_rn(wy[h][warp + 8 * k], cx));
+            }
+            __syncthreads();
+        }
+    }
+    const int x = x0 + lane;
+    if (x < width) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int y = y0 + warp + 8 * k;
+            if (y < height) density[(size_t)y * width + x] = acc[k];
+        }
+    }
+}
+
+}  // namespace dmap
+}  // namespace dgvcc
+
+using namespace dgvcc;
+using namespace dgvcc::dmap;
+
+extern "C" int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx, double* nn_dist, double* sigma,
+                                    void* stream) {
+    if (n < 0) return DGVCC_ERR_ARG;
+    if (n == 0) return DGVCC_OK;
+    if (!pts_xy || !nn_idx || !nn_dist || !sigma) return DGVCC_ERR_ARG;
+    dmap_knn_kernel<<<ceil_div(n, KNN_THREADS), KNN_THREADS, 0, (cudaStream_t)stream>>>(
+        (const double2*)pts_xy, n, nn_idx, nn_dist, sigma);
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t dgvcc_dmap_workspace_bytes(int n) { return (size_t)(n > 0 ? n : 1) * sizeof(Stamp); }
+
+extern "C" int dgvcc_dmap_splat(const double* pts_xy, const double* sigma, double fixed_sigma, double truncate, int n,
+                                int height, int width, void* workspace, size_t workspace_bytes, float* density,
+                                void* stream) {
+    if (n < 0 || height <= 0 || width <= 0 || !density) return DGVCC_ERR_ARG;
+    if (n > 0 && (!pts_xy || !workspace)) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_dmap_workspace_bytes(n)) return DGVCC_ERR_WORKSPACE;
+    if (!sigma && !(fixed_sigma >= 0.0)) return DGVCC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Stamp* stamps = (Stamp*)workspace;
+    if (n > 0) {
+        // deep pairwise recursion for huge kernels: radius 2^20 -> depth 14, well inside the default stack
+        dmap_prepare_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const double2*)pts_xy, sigma, fixed_sigma, truncate, n,
+                                                              height, width, stamps);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    dmap_splat_kernel<<<dim3(ceil_div(width, TILE), ceil_div(height, TILE)), SPLAT_THREADS, 0, st>>>(
+        stamps, n, height, width, density);
+    return (int)cudaGetLastError();
+}

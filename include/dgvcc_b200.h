@@ -131,6 +131,30 @@ int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta, int batch,
                               float* grad_density, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Density-map generation -- replaces utils/dmap_gen.py:14-51 (gaussian_filter_density)
+ * and utils/dmap_gen.py:53-81 (gaussian_filter_density_fixed).
+ *   pts_xy [n,2] f64 (column, row) -- what KDTree(points.copy()) sees, dmap_gen.py:34.
+ * ------------------------------------------------------------------------- */
+
+/* KDTree.query(points, k=4) by brute force (dmap_gen.py:34-36) and the adaptive
+ * sigma (dmap_gen.py:45-48): nn_idx [n,4] i32 / nn_dist [n,4] f64, column 0 the
+ * point itself, missing neighbours (n < 4) = (inf, n) like scipy;
+ * sigma[i] = 0.1*(d1+d2+d3) when n > 3, else 15. */
+int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx, double* nn_dist, double* sigma,
+                         void* stream);
+
+size_t dgvcc_dmap_workspace_bytes(int n);
+
+/* density [height,width] f32 = sum over heads, in index order, of
+ * scipy.ndimage.gaussian_filter(one_hot, sigma_i, truncate=truncate, mode='constant')
+ * (dmap_gen.py:38-49 / 71-79).  sigma == NULL uses fixed_sigma for every head
+ * (the fixed variant: sigma 4, truncate 7/4).  Heads with int(y) >= height or
+ * int(x) >= width are skipped (dmap_gen.py:41-44).  Every pixel is written. */
+int dgvcc_dmap_splat(const double* pts_xy, const double* sigma, double fixed_sigma, double truncate, int n,
+                     int height, int width, void* workspace, size_t workspace_bytes, float* density,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------
  * Throughput probes used by bench.py for the roofline denominators that
  * MEASURED_PEAKS.json does not carry: chip-wide
  * MUFU.EX2 and FFMA issue rates.  Each launches `iters` dependent-chain rounds

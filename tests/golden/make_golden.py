@@ -85,6 +85,47 @@ def make_bl():
     bl_case("outside", [120], 384, 256, 8, 8.0, jitter_outside=True)          # heads outside the crop
 
 
+# ------------------------------------------------------------------------- dmap
+def dmap_points(seed, n, w, h, dtype):
+    rng = np.random.default_rng(seed)
+    return synthetic.crowd_points(rng, n, w, h, dtype=dtype)
+
+
+def make_dmap():
+    dg = load_ref("utils/dmap_gen.py", "ref_dmap_gen")
+    out = {}
+    cases = [  # name, (H, W), N, dtype, tweak
+        ("a40", (96, 128), 40, np.float64, None),
+        ("a4", (64, 80), 4, np.float64, None),        # smallest N that uses the kNN sigma
+        ("a3", (64, 80), 3, np.float64, None),        # N <= 3 -> sigma 15
+        ("a1", (50, 70), 1, np.float32, None),
+        ("a0", (40, 40), 0, np.float64, None),
+        ("a25f32", (90, 110), 25, np.float32, None),  # QNRF path yields float32 points
+        ("oob", (80, 100), 30, np.float64, "oob"),    # heads right/below the image are skipped but stay neighbours
+        ("dup", (72, 72), 12, np.float64, "dup"),     # duplicated heads: sigma can be 0 -> identity filter
+    ]
+    for idx, (name, shape, n, dtype, tweak) in enumerate(cases):
+        pts = dmap_points(4000 + idx, n, shape[1], shape[0], dtype)
+        if tweak == "oob":
+            pts[::5, 0] += shape[1] * 0.3
+            pts[1::7, 1] += shape[0] * 0.25
+        if tweak == "dup":
+            pts[4:8] = pts[0]
+        img = np.zeros(shape + (3,), dtype=np.uint8)
+        out[f"{name}_shape"] = np.asarray(shape)
+        out[f"{name}_points"] = pts
+        out[f"{name}_adaptive"] = dg.gaussian_filter_density(img, pts)
+        out[f"{name}_fixed"] = dg.gaussian_filter_density_fixed(img, pts)
+        print("dmap", name, out[f"{name}_adaptive"].sum(), out[f"{name}_fixed"].sum())
+    # kNN bookkeeping exactly as dmap_gen.py:34-36 builds it
+    from scipy.spatial import KDTree
+    for name, n, dtype in (("knn2000", 2000, np.float64), ("knn700f32", 700, np.float32)):
+        pts = dmap_points(4100 + n, n, 1500, 900, dtype)
+        d, loc = KDTree(pts.copy(), leafsize=2048).query(pts, k=4)
+        out[f"{name}_points"], out[f"{name}_dist"], out[f"{name}_loc"] = pts, d, loc
+    np.savez_compressed(os.path.join(HERE, "dmap_cases.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["bl", "dmap", "isw"]
     torch.manual_seed(0)

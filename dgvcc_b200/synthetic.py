@@ -25,8 +25,10 @@ def crowd_points(rng, n, width, height, dtype=np.float32):
     pts = centres[which] + rng.normal(size=(n - n_bg, 2)) * spread[which, None]
     bg = rng.uniform([0, 0], [width, height], size=(n_bg, 2))
     pts = np.concatenate([pts, bg], 0)
-    pts[:, 0] = np.clip(pts[:, 0], 0, np.nextafter(np.float32(width), np.float32(0)))
-    pts[:, 1] = np.clip(pts[:, 1], 0, np.nextafter(np.float32(height), np.float32(0)))
+    # heads that fall outside the image are re-drawn uniformly (clipping would pile duplicates on the
+    # border, and duplicates make kNN / top-k tie order implementation-defined)
+    out = (pts[:, 0] < 0) | (pts[:, 0] >= width - 1) | (pts[:, 1] < 0) | (pts[:, 1] >= height - 1)
+    pts[out] = rng.uniform([0, 0], [width - 1, height - 1], size=(int(out.sum()), 2))
     rng.shuffle(pts, axis=0)
     return pts.astype(dtype)
 

@@ -126,6 +126,40 @@ def make_dmap():
     np.savez_compressed(os.path.join(HERE, "dmap_cases.npz"), **out)
 
 
+# -------------------------------------------------------------------------- isw
+def make_isw():
+    iw = load_ref("models/ISW/instance_whitening.py", "ref_instance_whitening")
+    sys.path.insert(0, ROOT)
+    from oracle import isw_oracle
+    out = {}
+    cases = [  # name, (B, C, H, W), mask keep fraction, margin
+        ("c64", (2, 64, 24, 20), 0.5, 0.0),
+        ("c128", (3, 128, 10, 12), 1.0, 0.0),
+        ("c48", (2, 48, 9, 7), 0.5, 0.0),          # C not a multiple of 64, odd HW
+        ("margin", (4, 64, 8, 8), 0.5, 0.02),      # IRW-style positive margin: some samples clamp to 0
+    ]
+    for idx, (name, shape, frac, margin) in enumerate(cases):
+        g = torch.Generator().manual_seed(7000 + idx)
+        x = torch.randn(shape, generator=g) * 1.7 + 0.3
+        c = shape[1]
+        eye = torch.eye(c)
+        mask = isw_oracle.upper_mask(c, frac, 7100 + idx)
+        num_remove = mask.sum()
+        xin = x.clone().requires_grad_(True)
+        y, w = iw.InstanceWhitening(c)(xin)
+        cov, _ = iw.get_covariance_matrix(w, eye=eye)
+        loss = iw.instance_whitening_loss(w, eye, mask, margin, num_remove)
+        loss.backward()
+        wleaf = w.detach().clone().requires_grad_(True)
+        iw.instance_whitening_loss(wleaf, eye, mask, margin, num_remove).backward()
+        out.update({f"{name}_x": x.numpy(), f"{name}_mask": mask.numpy(), f"{name}_margin": np.float32(margin),
+                    f"{name}_norm": y.detach().numpy(), f"{name}_cov": cov.detach().numpy(),
+                    f"{name}_loss": loss.detach().numpy(), f"{name}_grad_x": xin.grad.numpy(),
+                    f"{name}_grad_w": wleaf.grad.numpy()})
+        print("isw", name, float(loss))
+    np.savez_compressed(os.path.join(HERE, "isw_cases.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["bl", "dmap", "isw"]
     torch.manual_seed(0)

@@ -74,6 +74,7 @@ def test_full_size_against_closed_form_oracle(seed, n, h, w, dtype):
     img = np.empty((h, w, 0))
     dist, loc, sigma = dmap_gen.knn_sigma(pts)
     rd, rl = dmap_oracle.knn4(pts)
+    assert len(np.unique(pts, axis=0)) == n, "synthetic heads must be distinct (tie order is implementation-defined)"
     assert np.array_equal(loc, rl) and np.array_equal(dist, rd)
     ref = dmap_oracle.density_closed_form((h, w), pts, sigmas=(rd[:, 1] + rd[:, 2] + rd[:, 3]) * 0.1)
     got = dmap_gen.gaussian_filter_density(img, pts)

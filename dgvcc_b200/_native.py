@@ -45,6 +45,18 @@ SIGNATURES = {
     "dgvcc_dmap_workspace_bytes": (c_size_t, [c_int]),
     "dgvcc_dmap_splat": (c_int, [c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_void_p, c_size_t,
                                  c_void_p, c_void_p]),
+    "dgvcc_isw_instnorm_forward": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgvcc_isw_instnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dgvcc_isw_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "dgvcc_isw_covariance": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                     c_void_p]),
+    "dgvcc_isw_covariance_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                              c_void_p]),
+    "dgvcc_isw_loss_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                       c_size_t, c_void_p, c_void_p]),
+    "dgvcc_isw_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_isw_gram_tc_partials": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_probe_ex2": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
     "dgvcc_probe_ffma": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
 }

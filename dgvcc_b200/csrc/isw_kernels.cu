@@ -1,0 +1,424 @@
+// ISW instance-whitening covariance loss for sm_100a: everything around the Gram contraction.
+//
+// Replaces models/ISW/instance_whitening.py of the reference:
+//   isw_instnorm_fwd/bwd_kernel : nn.InstanceNorm2d(dim, affine=False)            instance_whitening.py:5-16
+//   isw_gram_simt_kernel        : exact-fp32 split-K Gram partials X X^T (CUDA cores); used for channel
+//                                 counts the tensor-core kernel (isw_gram_tc.cu) does not tile, and as its
+//                                 cross-check in the tests                        instance_whitening.py:37
+//   isw_cov_finish_kernel       : fixed-order sum of the split-K partials, /(HW-1) + eps*eye, mirrored to
+//                                 the full symmetric [C,C]                        instance_whitening.py:37
+//   isw_loss_kernel             : sum |f_cor*mask| - margin, /num_remove_cov, clamp, mean over B
+//                                                                                 instance_whitening.py:19-27
+//   isw_loss_grad_kernel        : S_b = dL/df_cor_b symmetrised / (HW-1)          autograd of :19-39
+//   isw_sx_simt_kernel          : dX_b = S_b X_b  (exact fp32)                    autograd of :37
+// Deterministic: no float atomics; split-K partials are added in split order.
+#include "common.cuh"
+#include "../../include/dgvcc_b200.h"
+
+namespace dgvcc {
+namespace isw {
+
+// ------------------------------------------------------------------------------- instance norm
+constexpr int NORM_THREADS = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NORM_THREADS / 32; ++w) t += scratch[w];
+    return t;  // same value on every thread, fixed order
+}
+
+// One CTA per (b, c) plane of HW elements: mean, biased variance (two-pass on the cached plane), normalise.
+__global__ void __launch_bounds__(NORM_THREADS)
+isw_instnorm_fwd_kernel(const float* __restrict__ x, int hw, float eps, float* __restrict__ y,
+                        float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+    extern __shared__ float plane[];  // hw floats when they fit, else unused
+    __shared__ float scratch[NORM_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * hw;
+    const bool cached = gridDim.y == 1;  // launch with gridDim.y == 2 to signal "does not fit in smem"
+    const float* src = x + base;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) {
+        const float v = src[i];
+        if (cached) plane[i] = v;
+        s += v;
+    }
+    const float mean = block_sum(s, scratch) / (float)hw;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) {
+        const float d = (cached ? plane[i] : src[i]) - mean;
+        q = fmaf(d, d, q);
+    }
+    const float var = block_sum(q, scratch) / (float)hw;
+    const float invstd = 1.0f / sqrtf(var + eps);
+    if (blockIdx.y == 0) {
+        for (int i = threadIdx.x; i < hw; i += NORM_THREADS)
+            y[base + i] = ((cached ? plane[i] : src[i]) - mean) * invstd;
+        if (threadIdx.x == 0) { mean_out[blockIdx.x] = mean; invstd_out[blockIdx.x] = invstd; }
+    }
+}
+
+// dx = invstd * (dy - mean(dy) - y * mean(dy * y))
+__global__ void __launch_bounds__(NORM_THREADS)
+isw_instnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ invstd,
+                        int hw, float* __restrict__ dx) {
+    __shared__ float scratch[NORM_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * hw;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) {
+        const float g = dy[base + i];
+        s1 += g;
+        s2 = fmaf(g, y[base + i], s2);
+    }
+    const float m1 = block_sum(s1, scratch) / (float)hw;
+    const float m2 = block_sum(s2, scratch) / (float)hw;
+    const float is = invstd[blockIdx.x];
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS)
+        dx[base + i] = is * (dy[base + i] - m1 - y[base + i] * m2);
+}
+
+// ------------------------------------------------------------------------------- SIMT Gram
+constexpr int GT = 64;        // output tile edge
+constexpr int GK = 16;        // k-chunk
+constexpr int GEMM_THREADS = 256;
+
+// part[((b*splits + split)*n_tiles + tile)][64][64] = X_I X_J^T over this split's k-range, tiles J >= I.
+__global__ void __launch_bounds__(GEMM_THREADS)
+isw_gram_simt_kernel(const float* __restrict__ x, int c, int hw, int splits, int k_per_split,
+                     float* __restrict__ part) {
+    __shared__ float as[GK][GT + 4];
+    __shared__ float bs[GK][GT + 4];
+    const int tiles_1d = (c + GT - 1) / GT;
+    // upper-triangular tile index -> (ti, tj), tj >= ti
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= tiles_1d - ti) { rem -= tiles_1d - ti; ++ti; }
+    const int tj = ti + rem;
+    const int split = blockIdx.y, b = blockIdx.z;
+    const int k0 = split * k_per_split, k1 = min(hw, k0 + k_per_split);
+    const float* xb = x + (size_t)b * c * hw;
+    const int tid = threadIdx.x;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;  // loader: row lr of the tile, 4 consecutive k
+    const int ty = tid >> 4, tx = tid & 15;        // compute: 4x4 outputs at rows ty*4.., cols tx*4..
+    float acc[4][4] = {};
+    for (int kb = k0; kb < k1; kb += GK) {
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+        const int ra = ti * GT + lr, rb = tj * GT + lr;
+        float* pa = reinterpret_cast<float*>(&va);
+        float* pb = reinterpret_cast<float*>(&vb);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = kb + lk + q;
+            if (k < k1) {
+                if (ra < c) pa[q] = xb[(size_t)ra * hw + k];
+                if (rb < c) pb[q] = xb[(size_t)rb * hw + k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { as[lk + q][lr] = pa[q]; bs[lk + q][lr] = pb[q]; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&as[k][ty * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    const int n_tiles = tiles_1d * (tiles_1d + 1) / 2;
+    float* out = part + (((size_t)b * splits + split) * n_tiles + blockIdx.x) * GT * GT;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(&out[(ty * 4 + i) * GT + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
+// f_cor[b][i][j] = sum_split part / (hw-1) + eps*eye[i][j], written to both (i,j) and (j,i).
+// `tile` is the edge of the partial tiles (64 for the SIMT kernel, 128 for the tensor-core kernel).
+__global__ void __launch_bounds__(256)
+isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits, int tile, const float* __restrict__ eye,
+                      float eps, float* __restrict__ f_cor) {
+    const int tiles_1d = (c + tile - 1) / tile;
+    const int n_tiles = tiles_1d * (tiles_1d + 1) / 2;
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= tiles_1d - ti) { rem -= tiles_1d - ti; ++ti; }
+    const int tj = ti + rem;
+    const int b = blockIdx.z;
+    const float inv = 1.0f / (float)(hw - 1);
+    const size_t tile_elems = (size_t)tile * tile;
+    for (int e = blockIdx.y * 256 + threadIdx.x; e < tile * tile; e += gridDim.y * 256) {
+        const int li = e / tile, lj = e % tile;
+        const int i = ti * tile + li, j = tj * tile + lj;
+        if (i >= c || j >= c) continue;
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp)
+            s += part[(((size_t)b * splits + sp) * n_tiles + blockIdx.x) * tile_elems + e];
+        // torch: bmm(...).div(HW-1) is a true division; + (eps * eye)
+        const float v = s / (float)(hw - 1);
+        (void)inv;
+        float* fc = f_cor + (size_t)b * c * c;
+        fc[(size_t)i * c + j] = v + eps * eye[(size_t)i * c + j];
+        if (ti != tj || li != lj) fc[(size_t)j * c + i] = v + eps * eye[(size_t)j * c + i];
+    }
+}
+
+// ------------------------------------------------------------------------------- loss
+// off[b] = sum_ij |f_cor[b,i,j] * mask[i,j]| - margin; loss = sum_b max(off[b] / num_remove, 0) / B.
+// One CTA per sample (fixed-order block sums), the last CTA adds the samples in order.
+__global__ void __launch_bounds__(256)
+isw_loss_kernel(const float* __restrict__ f_cor, const float* __restrict__ mask, int c, int batch,
+                const float* __restrict__ margin, const float* __restrict__ num_remove, float* __restrict__ off_out,
+                float* __restrict__ loss_out, unsigned int* __restrict__ ticket) {
+    __shared__ float scratch[8];
+    const int b = blockIdx.x;
+    const float* fc = f_cor + (size_t)b * c * c;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < c * c; e += 256) s += fabsf(fc[e] * mask[e]);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += scratch[w];
+        off_out[b] = t - margin[0];
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == (unsigned)batch - 1u) {
+            __threadfence();
+            const volatile float* ov = off_out;
+            float total = 0.f;
+            for (int i = 0; i < batch; ++i) total += fmaxf(ov[i] / num_remove[0], 0.f);
+            loss_out[0] = total / (float)batch;
+            *ticket = 0u;
+        }
+    }
+}
+
+// S_b[i][j] = g * gate_b * (sgn(fc_ij * m_ij) * m_ij + sgn(fc_ji * m_ji) * m_ji) / (num_remove * B * (hw-1))
+// with gate_b = [off_b / num_remove >= 0]  (torch clamp passes the gradient at the boundary).
+__global__ void __launch_bounds__(256)
+isw_loss_grad_kernel(const float* __restrict__ f_cor, const float* __restrict__ mask, const float* __restrict__ off,
+                     const float* __restrict__ num_remove, const float* __restrict__ grad_loss, int c, int hw,
+                     int batch, float* __restrict__ s_out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= c * c) return;
+    const int i = e / c, j = e % c;
+    const float* fc = f_cor + (size_t)b * c * c;
+    const float nr = num_remove[0];
+    const float gate = (off[b] / nr >= 0.f) ? 1.f : 0.f;
+    auto term = [&](int r, int q) {
+        const float m = mask[(size_t)r * c + q];
+        const float v = fc[(size_t)r * c + q] * m;
+        const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+        return sg * m;
+    };
+    const float scale = grad_loss[0] * gate / (nr * (float)batch) / (float)(hw - 1);
+    s_out[(size_t)b * c * c + e] = scale * (term(i, j) + term(j, i));
+}
+
+// S_b = (dF_b + dF_b^T) / (hw-1): backward of get_covariance_matrix for an arbitrary upstream gradient.
+__global__ void __launch_bounds__(256)
+isw_cov_grad_kernel(const float* __restrict__ d_fcor, int c, int hw, float* __restrict__ s_out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= c * c) return;
+    const int i = e / c, j = e % c;
+    const float* d = d_fcor + (size_t)b * c * c;
+    s_out[(size_t)b * c * c + e] = (d[(size_t)i * c + j] + d[(size_t)j * c + i]) / (float)(hw - 1);
+}
+
+// ------------------------------------------------------------------------------- dX = S X (SIMT)
+__global__ void __launch_bounds__(GEMM_THREADS)
+isw_sx_simt_kernel(const float* __restrict__ s, const float* __restrict__ x, int c, int hw, float* __restrict__ dx) {
+    __shared__ float as[GK][GT + 4];  // S tile, transposed: as[k][row]
+    __shared__ float bs[GK][GT + 4];  // X tile: bs[k][col]
+    const int b = blockIdx.z;
+    const int row0 = blockIdx.y * GT, col0 = blockIdx.x * GT;
+    const float* sb = s + (size_t)b * c * c;
+    const float* xb = x + (size_t)b * c * hw;
+    const int tid = threadIdx.x;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;   // S loader
+    const int xk = tid >> 4, xc = (tid & 15) * 4;  // X loader: row xk of the chunk, 4 consecutive columns
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4] = {};
+    for (int kb = 0; kb < c; kb += GK) {
+        float pa[4], pb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = row0 + lr, k = kb + lk + q;
+            pa[q] = (r < c && k < c) ? sb[(size_t)r * c + k] : 0.f;
+            const int kk = kb + xk, col = col0 + xc + q;
+            pb[q] = (kk < c && col < hw) ? xb[(size_t)kk * hw + col] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { as[lk + q][lr] = pa[q]; bs[xk][xc + q] = pb[q]; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&as[k][ty * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    float* out = dx + (size_t)b * c * hw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + ty * 4 + i;
+        if (r >= c) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = col0 + tx * 4 + j;
+            if (col < hw) out[(size_t)r * hw + col] = acc[i][j];
+        }
+    }
+}
+
+}  // namespace isw
+}  // namespace dgvcc
+
+using namespace dgvcc;
+using namespace dgvcc::isw;
+
+extern "C" int dgvcc_isw_instnorm_forward(const float* x, int planes, int hw, float eps, float* y, float* mean,
+                                          float* invstd, void* stream) {
+    if (!x || !y || !mean || !invstd || planes <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    const size_t smem = (size_t)hw * sizeof(float);
+    const bool fits = smem <= 200 * 1024;
+    if (fits && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(isw_instnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // gridDim.y == 2 tells the kernel the plane is not cached (only y-block 0 writes)
+    isw_instnorm_fwd_kernel<<<dim3(planes, fits ? 1 : 2), NORM_THREADS, fits ? smem : 0, (cudaStream_t)stream>>>(
+        x, hw, eps, y, mean, invstd);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_instnorm_backward(const float* dy, const float* y, const float* invstd, int planes, int hw,
+                                           float* dx, void* stream) {
+    if (!dy || !y || !invstd || !dx || planes <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    isw_instnorm_bwd_kernel<<<planes, NORM_THREADS, 0, (cudaStream_t)stream>>>(dy, y, invstd, hw, dx);
+    return (int)cudaGetLastError();
+}
+
+// Split-K plan shared by both Gram kernels: enough CTAs to cover the chip ~2x, k ranges a multiple of 32.
+static void gram_plan(int batch, int c, int hw, int tile, int* splits, int* k_per_split, int* n_tiles) {
+    const int t1 = ceil_div(c, tile);
+    *n_tiles = t1 * (t1 + 1) / 2;
+    const int want = 296;
+    int s = ceil_div(want, batch * *n_tiles);
+    const int max_s = ceil_div(hw, 256);
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    int kps = ceil_div(ceil_div(hw, s), 32) * 32;
+    *splits = ceil_div(hw, kps);
+    *k_per_split = kps;
+}
+
+extern "C" size_t dgvcc_isw_workspace_bytes(int batch, int c, int hw) {
+    int s64, k64, n64, s128, k128, n128;
+    gram_plan(batch, c, hw, 64, &s64, &k64, &n64);
+    gram_plan(batch, c, hw, 128, &s128, &k128, &n128);
+    const size_t p64 = (size_t)batch * s64 * n64 * 64 * 64;
+    const size_t p128 = (size_t)batch * s128 * n128 * 128 * 128;
+    const size_t part = (p64 > p128 ? p64 : p128) * sizeof(float);
+    // partials | off[B] | ticket (256 B) | S [B,C,C]
+    return align_up(part, 256) + align_up((size_t)batch * sizeof(float), 256) + 256 +
+           align_up((size_t)batch * c * c * sizeof(float), 256);
+}
+
+namespace {
+struct IswWs { float* part; float* off; unsigned int* ticket; float* s; };
+IswWs carve(void* ws, int batch, int c, int hw) {
+    int s64, k64, n64, s128, k128, n128;
+    gram_plan(batch, c, hw, 64, &s64, &k64, &n64);
+    gram_plan(batch, c, hw, 128, &s128, &k128, &n128);
+    const size_t p64 = (size_t)batch * s64 * n64 * 64 * 64;
+    const size_t p128 = (size_t)batch * s128 * n128 * 128 * 128;
+    const size_t part = align_up((p64 > p128 ? p64 : p128) * sizeof(float), 256);
+    IswWs w;
+    char* p = (char*)ws;
+    w.part = (float*)p; p += part;
+    w.off = (float*)p; p += align_up((size_t)batch * sizeof(float), 256);
+    w.ticket = (unsigned int*)p; p += 256;
+    w.s = (float*)p;
+    return w;
+}
+}  // namespace
+
+// implemented in isw_gram_tc.cu; returns DGVCC_ERR_UNSUPPORTED for shapes it does not tile
+extern "C" int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int hw, int splits, int k_per_split,
+                                          float* part, void* stream);
+
+extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int batch, int c, int hw, int use_tensor_cores,
+                                    void* workspace, size_t workspace_bytes, float* f_cor, void* stream) {
+    if (!f_map || !eye || !workspace || !f_cor || batch <= 0 || c <= 0 || hw <= 1) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const IswWs w = carve(workspace, batch, c, hw);
+    int splits, kps, n_tiles, tile = 64;
+    bool done = false;
+    if (use_tensor_cores) {
+        gram_plan(batch, c, hw, 128, &splits, &kps, &n_tiles);
+        const int rc = dgvcc_isw_gram_tc_partials(f_map, batch, c, hw, splits, kps, w.part, stream);
+        if (rc == DGVCC_OK) { done = true; tile = 128; }
+        else if (rc != DGVCC_ERR_UNSUPPORTED) return rc;
+    }
+    if (!done) {
+        gram_plan(batch, c, hw, 64, &splits, &kps, &n_tiles);
+        isw_gram_simt_kernel<<<dim3(n_tiles, splits, batch), GEMM_THREADS, 0, st>>>(f_map, c, hw, splits, kps, w.part);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    const int yblocks = tile == 128 ? 16 : 4;
+    isw_cov_finish_kernel<<<dim3(n_tiles, yblocks, batch), 256, 0, st>>>(w.part, c, hw, splits, tile, eye, 1e-5f, f_cor);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, const float* margin,
+                                      const float* num_remove_cov, int batch, int c, int hw, void* workspace,
+                                      size_t workspace_bytes, float* loss_out, void* stream) {
+    if (!f_cor || !mask || !margin || !num_remove_cov || !workspace || !loss_out) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, batch, c, hw);
+    cudaStream_t st = (cudaStream_t)stream;
+    DGVCC_RETURN_IF_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+    isw_loss_kernel<<<batch, 256, 0, st>>>(f_cor, mask, c, batch, margin, num_remove_cov, w.off, loss_out, w.ticket);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float* mask,
+                                       const float* num_remove_cov, const float* grad_loss, int batch, int c, int hw,
+                                       void* workspace, size_t workspace_bytes, float* grad_f_map, void* stream) {
+    if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, batch, c, hw);
+    cudaStream_t st = (cudaStream_t)stream;
+    isw_loss_grad_kernel<<<dim3(ceil_div(c * c, 256), batch), 256, 0, st>>>(f_cor, mask, w.off, num_remove_cov, grad_loss,
+                                                                            c, hw, batch, w.s);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    isw_sx_simt_kernel<<<dim3(ceil_div(hw, GT), ceil_div(c, GT), batch), GEMM_THREADS, 0, st>>>(w.s, f_map, c, hw, grad_f_map);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_covariance_backward(const float* f_map, const float* grad_f_cor, int batch, int c, int hw,
+                                             void* workspace, size_t workspace_bytes, float* grad_f_map, void* stream) {
+    if (!f_map || !grad_f_cor || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, batch, c, hw);
+    cudaStream_t st = (cudaStream_t)stream;
+    isw_cov_grad_kernel<<<dim3(ceil_div(c * c, 256), batch), 256, 0, st>>>(grad_f_cor, c, hw, w.s);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    isw_sx_simt_kernel<<<dim3(ceil_div(hw, GT), ceil_div(c, GT), batch), GEMM_THREADS, 0, st>>>(w.s, f_map, c, hw, grad_f_map);
+    return (int)cudaGetLastError();
+}

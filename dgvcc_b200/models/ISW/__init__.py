@@ -1,0 +1,1 @@
+from .instance_whitening import InstanceWhitening, get_covariance_matrix, instance_whitening_loss  # noqa: F401

@@ -1,0 +1,161 @@
+"""Drop-in for the reference's ``models/ISW/instance_whitening.py`` on B200.
+
+Same names and signatures as the reference (instance_whitening.py:5, 19, 30), imported by name in
+``models/ISW/__init__.py:12``, ``deepv3.py:33`` and ``Resnet.py:41``:
+
+    InstanceWhitening(dim).forward(x)                       -> (x_norm, x_norm)
+    get_covariance_matrix(f_map, eye=None)                  -> (f_cor [B,C,C], B)
+    instance_whitening_loss(f_map, eye, mask_matrix, margin, num_remove_cov) -> 0-dim loss
+
+The Gram X X^T is the only dense contraction of the path: csrc/isw_gram_tc.cu runs it on the
+tcgen05 tensor cores (3xTF32 split, fp32 accumulation in TMEM) where the shape tiles, otherwise
+the exact-fp32 CUDA-core kernel of csrc/isw_kernels.cu.  ``margin`` / ``num_remove_cov`` may be
+Python numbers or 0-dim tensors, as in the reference (cov_settings.py:47,73).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from ... import _native
+
+
+def _use_tc():
+    return int(os.environ.get("DGVCC_ISW_TENSOR_CORES", "1"))
+
+
+def _as3d(f_map):
+    _native.require_cuda(f_map, "instance_whitening")
+    b, c, h, w = f_map.shape
+    return f_map.detach().to(torch.float32).contiguous().view(b, c, h * w), b, c, h * w
+
+
+def _workspace(b, c, hw, dev):
+    n = _native.lib().dgvcc_isw_workspace_bytes(b, c, hw)
+    return torch.empty((n,), dtype=torch.uint8, device=dev), n
+
+
+def _scalar(v, dev):
+    if torch.is_tensor(v):
+        return v.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    return torch.full((1,), float(v), dtype=torch.float32, device=dev)
+
+
+class _InstanceNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        _native.require_cuda(x, "InstanceWhitening")
+        b, c, h, w = x.shape
+        xc = x.detach().to(torch.float32).contiguous()
+        y = torch.empty_like(xc)
+        mean = torch.empty((b * c,), dtype=torch.float32, device=x.device)
+        invstd = torch.empty_like(mean)
+        _native.check(_native.lib().dgvcc_isw_instnorm_forward(
+            _native.ptr(xc), b * c, h * w, eps, _native.ptr(y), _native.ptr(mean), _native.ptr(invstd),
+            _native.stream_ptr(x.device)), "dgvcc_isw_instnorm_forward")
+        ctx.save_for_backward(y, invstd)
+        ctx.in_dtype = x.dtype
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, invstd = ctx.saved_tensors
+        b, c, h, w = y.shape
+        g = dy.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(y)
+        _native.check(_native.lib().dgvcc_isw_instnorm_backward(
+            _native.ptr(g), _native.ptr(y), _native.ptr(invstd), b * c, h * w, _native.ptr(dx),
+            _native.stream_ptr(y.device)), "dgvcc_isw_instnorm_backward")
+        return dx.to(ctx.in_dtype), None
+
+
+class InstanceWhitening(nn.Module):
+
+    def __init__(self, dim):
+        super(InstanceWhitening, self).__init__()
+        self.dim = dim
+        self.eps = 1e-5  # nn.InstanceNorm2d(dim, affine=False) default, instance_whitening.py:9
+
+    def forward(self, x):
+        x = _InstanceNorm.apply(x, self.eps)
+        w = x
+        return x, w
+
+
+class _Covariance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f_map, eye):
+        x, b, c, hw = _as3d(f_map)
+        dev = x.device
+        ws, n = _workspace(b, c, hw, dev)
+        f_cor = torch.empty((b, c, c), dtype=torch.float32, device=dev)
+        eye32 = eye.detach().to(device=dev, dtype=torch.float32).contiguous()
+        _native.check(_native.lib().dgvcc_isw_covariance(
+            _native.ptr(x), _native.ptr(eye32), b, c, hw, _use_tc(), _native.ptr(ws), n, _native.ptr(f_cor),
+            _native.stream_ptr(dev)), "dgvcc_isw_covariance")
+        ctx.save_for_backward(x)
+        ctx.meta = (f_map.shape, f_map.dtype)
+        return f_cor
+
+    @staticmethod
+    def backward(ctx, d_fcor):
+        (x,) = ctx.saved_tensors
+        b, c, hw = x.shape
+        dev = x.device
+        ws, n = _workspace(b, c, hw, dev)
+        g = d_fcor.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        _native.check(_native.lib().dgvcc_isw_covariance_backward(
+            _native.ptr(x), _native.ptr(g), b, c, hw, _native.ptr(ws), n, _native.ptr(dx), _native.stream_ptr(dev)),
+            "dgvcc_isw_covariance_backward")
+        shape, dtype = ctx.meta
+        return dx.view(shape).to(dtype), None
+
+
+class _WhiteningLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f_map, eye, mask_matrix, margin, num_remove_cov):
+        x, b, c, hw = _as3d(f_map)
+        dev = x.device
+        lib = _native.lib()
+        ws, n = _workspace(b, c, hw, dev)
+        f_cor = torch.empty((b, c, c), dtype=torch.float32, device=dev)
+        eye32 = eye.detach().to(device=dev, dtype=torch.float32).contiguous()
+        mask = mask_matrix.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if mask.shape != (c, c):
+            raise ValueError(f"mask_matrix must be [{c},{c}], got {tuple(mask.shape)}")
+        mg, nr = _scalar(margin, dev), _scalar(num_remove_cov, dev)
+        stream = _native.stream_ptr(dev)
+        _native.check(lib.dgvcc_isw_covariance(_native.ptr(x), _native.ptr(eye32), b, c, hw, _use_tc(), _native.ptr(ws), n,
+                                               _native.ptr(f_cor), stream), "dgvcc_isw_covariance")
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        _native.check(lib.dgvcc_isw_loss_forward(_native.ptr(f_cor), _native.ptr(mask), _native.ptr(mg), _native.ptr(nr),
+                                                 b, c, hw, _native.ptr(ws), n, _native.ptr(loss), stream),
+                      "dgvcc_isw_loss_forward")
+        ctx.save_for_backward(x, f_cor, mask, nr, ws)
+        ctx.meta = (f_map.shape, f_map.dtype, n)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        x, f_cor, mask, nr, ws = ctx.saved_tensors
+        shape, dtype, n = ctx.meta
+        b, c, hw = x.shape
+        dev = x.device
+        g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        dx = torch.empty_like(x)
+        _native.check(_native.lib().dgvcc_isw_loss_backward(
+            _native.ptr(x), _native.ptr(f_cor), _native.ptr(mask), _native.ptr(nr), _native.ptr(g), b, c, hw,
+            _native.ptr(ws), n, _native.ptr(dx), _native.stream_ptr(dev)), "dgvcc_isw_loss_backward")
+        return dx.view(shape).to(dtype), None, None, None, None
+
+
+def instance_whitening_loss(f_map, eye, mask_matrix, margin, num_remove_cov):
+    return _WhiteningLoss.apply(f_map, eye, mask_matrix, margin, num_remove_cov)
+
+
+def get_covariance_matrix(f_map, eye=None):
+    B, C, H, W = f_map.shape  # i-th feature size (B X C X H X W)
+    if eye is None:
+        eye = torch.eye(C, device=f_map.device)
+    return _Covariance.apply(f_map, eye), B

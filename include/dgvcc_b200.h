@@ -155,6 +155,47 @@ int dgvcc_dmap_splat(const double* pts_xy, const double* sigma, double fixed_sig
                      void* stream);
 
 /* ---------------------------------------------------------------------------
+ * ISW instance-whitening covariance loss -- replaces
+ * models/ISW/instance_whitening.py:5-16 (InstanceWhitening = InstanceNorm2d, affine=False),
+ * :30-39 (get_covariance_matrix) and :19-27 (instance_whitening_loss) + their autograd.
+ *   f_map [batch, c, hw] f32 contiguous (the [B,C,H,W] feature map viewed as [B,C,HW]).
+ * ------------------------------------------------------------------------- */
+
+/* y = (x - mean) * invstd per (b,c) plane, biased variance, eps inside the sqrt;
+ * planes = B*C.  mean / invstd [planes] are kept for the backward. */
+int dgvcc_isw_instnorm_forward(const float* x, int planes, int hw, float eps, float* y, float* mean,
+                               float* invstd, void* stream);
+int dgvcc_isw_instnorm_backward(const float* dy, const float* y, const float* invstd, int planes, int hw,
+                                float* dx, void* stream);
+
+size_t dgvcc_isw_workspace_bytes(int batch, int c, int hw);
+
+/* f_cor [batch,c,c] = bmm(X, X^T) / (hw-1) + 1e-5 * eye  (instance_whitening.py:37).
+ * use_tensor_cores != 0 selects the tcgen05/TMA 3xTF32 Gram where the shape tiles
+ * (c % 64 == 0, hw % 4 == 0); other shapes use the exact-fp32 CUDA-core Gram. */
+int dgvcc_isw_covariance(const float* f_map, const float* eye, int batch, int c, int hw, int use_tensor_cores,
+                         void* workspace, size_t workspace_bytes, float* f_cor, void* stream);
+/* grad_f_map = (dF + dF^T) X / (hw-1) for an upstream gradient dF of f_cor. */
+int dgvcc_isw_covariance_backward(const float* f_map, const float* grad_f_cor, int batch, int c, int hw,
+                                  void* workspace, size_t workspace_bytes, float* grad_f_map, void* stream);
+
+/* loss[0] = sum_b clamp((sum |f_cor_b * mask| - margin) / num_remove_cov, min=0) / batch
+ * (instance_whitening.py:21-25).  margin / num_remove_cov are 1-element DEVICE arrays
+ * (the reference passes 0-dim CUDA tensors, cov_settings.py:73). */
+int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, const float* margin, const float* num_remove_cov,
+                           int batch, int c, int hw, void* workspace, size_t workspace_bytes, float* loss_out,
+                           void* stream);
+/* grad_f_map for grad_loss[0]; re-uses the workspace written by dgvcc_isw_loss_forward. */
+int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float* mask, const float* num_remove_cov,
+                            const float* grad_loss, int batch, int c, int hw, void* workspace,
+                            size_t workspace_bytes, float* grad_f_map, void* stream);
+
+/* The tensor-core Gram on its own (split-K partial tiles, tests / profiling):
+ * part [batch][splits][upper-triangular 128x128 tiles][128][128]. */
+int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int hw, int splits, int k_per_split,
+                               float* part, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Throughput probes used by bench.py for the roofline denominators that
  * MEASURED_PEAKS.json does not carry: chip-wide
  * MUFU.EX2 and FFMA issue rates.  Each launches `iters` dependent-chain rounds

@@ -1,0 +1,106 @@
+"""Parity of the CUDA ISW path (through the C ABI) with the reference fixtures and the CPU oracle.
+Tolerance: rtol 1e-5 with atol 1e-7*max|ref| (Gram / loss / gradients)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import isw_oracle
+from helpers import GOLDEN, assert_close
+
+pytestmark = pytest.mark.gpu
+CASES = ["c64", "c128", "c48", "margin"]
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def fixtures():
+    return np.load(os.path.join(GOLDEN, "isw_cases.npz"))
+
+
+def amax(a):
+    return float(np.abs(np.asarray(a)).max())
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("name", CASES)
+def test_matches_reference_fixture(fixtures, name, tc, monkeypatch):
+    from dgvcc_b200.models.ISW import InstanceWhitening, get_covariance_matrix, instance_whitening_loss
+    monkeypatch.setenv("DGVCC_ISW_TENSOR_CORES", str(tc))
+    x = torch.from_numpy(fixtures[f"{name}_x"]).to(DEV).requires_grad_(True)
+    mask = torch.from_numpy(fixtures[f"{name}_mask"]).to(DEV)
+    margin = float(fixtures[f"{name}_margin"])
+    c = x.shape[1]
+    eye = torch.eye(c, device=DEV)
+    y, w = InstanceWhitening(c)(x)
+    assert y is w
+    cov, b = get_covariance_matrix(w, eye=eye)
+    assert b == x.shape[0]
+    loss = instance_whitening_loss(w, eye, mask, margin, mask.sum())
+    loss.backward()
+    ref_cov = fixtures[f"{name}_cov"]
+    assert_close(w.detach().cpu(), fixtures[f"{name}_norm"], 1e-5, 1e-6, "instance norm")
+    assert_close(cov.detach().cpu(), ref_cov, 1e-5, 1e-7 * amax(ref_cov) + 1e-8, "covariance")
+    assert_close(loss.detach().cpu(), fixtures[f"{name}_loss"], 1e-5, 0, "loss")
+    gx = fixtures[f"{name}_grad_x"]
+    assert_close(x.grad.cpu(), gx, 1e-5, 2e-6 * amax(gx), "grad through norm")
+    # gradient w.r.t. the whitened map itself (the tensor the reference feeds to the loss)
+    wl = torch.from_numpy(fixtures[f"{name}_norm"]).to(DEV).requires_grad_(True)
+    instance_whitening_loss(wl, eye, mask, margin, mask.sum()).backward()
+    gw = fixtures[f"{name}_grad_w"]
+    assert_close(wl.grad.cpu(), gw, 1e-5, 1e-6 * amax(gw), "grad f_map")
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("shape", [(8, 64, 160, 160), (8, 256, 80, 80), (8, 512, 40, 40)])
+def test_config5_shapes_against_oracle(shape, tc, monkeypatch):
+    """BASELINE config 5: VGG/ResNet-shaped maps at crop 320."""
+    from dgvcc_b200.models.ISW import InstanceWhitening, get_covariance_matrix, instance_whitening_loss
+    monkeypatch.setenv("DGVCC_ISW_TENSOR_CORES", str(tc))
+    g = torch.Generator().manual_seed(5000 + shape[1])
+    x = torch.randn(shape, generator=g)
+    c = shape[1]
+    mask = isw_oracle.upper_mask(c, 0.5, 5100 + c)
+    eye = torch.eye(c)
+    xr = x.clone().requires_grad_(True)
+    wr = isw_oracle.instance_standardize(xr)
+    cov_r, _ = isw_oracle.covariance(wr, eye)
+    loss_r = isw_oracle.whitening_loss(wr, eye, mask, 0, mask.sum())
+    loss_r.backward()
+    # fp64 yardstick for the Gram: the reference's own fp32 error
+    cov64, _ = isw_oracle.covariance(wr.detach().double(), eye.double())
+
+    xd = x.to(DEV).requires_grad_(True)
+    y, w = InstanceWhitening(c)(xd)
+    cov, _ = get_covariance_matrix(w, eye=eye.to(DEV))
+    loss = instance_whitening_loss(w, eye.to(DEV), mask.to(DEV), 0, mask.sum().to(DEV))
+    loss.backward()
+    assert_close(y.detach().cpu(), wr.detach(), 1e-5, 1e-6, "instance norm")
+    assert_close(cov.detach().cpu(), cov_r.detach(), 1e-5, 1e-7 * amax(cov_r.detach()) + 2e-7, "covariance")
+    assert_close(loss.detach().cpu(), loss_r.detach(), 1e-5, 0, "loss")
+    assert_close(xd.grad.cpu(), xr.grad, 1e-5, 2e-6 * amax(xr.grad), "grad")
+    err_ref = float((cov_r.detach().double() - cov64).abs().max())
+    err_ours = float((cov.detach().cpu().double() - cov64).abs().max())
+    print(f"{shape} tc={tc}: max |cov - fp64|: reference fp32 {err_ref:.3e}, ours {err_ours:.3e}")
+
+
+def test_covariance_backward_generic_upstream():
+    from dgvcc_b200.models.ISW import get_covariance_matrix
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 64, 12, 12), generator=g)
+    up = torch.randn((2, 64, 64), generator=g)
+    xr = x.clone().requires_grad_(True)
+    cr, _ = isw_oracle.covariance(xr, torch.eye(64))
+    (cr * up).sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    cd, _ = get_covariance_matrix(xd)  # eye=None -> built on the map's device (instance_whitening.py:34-35)
+    (cd * up.to(DEV)).sum().backward()
+    assert_close(cd.detach().cpu(), cr.detach(), 1e-5, 1e-7 * amax(cr.detach()) + 1e-8, "covariance")
+    assert_close(xd.grad.cpu(), xr.grad, 1e-5, 1e-6 * amax(xr.grad), "grad")
+
+
+def test_cpu_tensor_is_rejected():
+    from dgvcc_b200.models.ISW import get_covariance_matrix
+    with pytest.raises(RuntimeError):
+        get_covariance_matrix(torch.zeros(1, 8, 4, 4), eye=torch.eye(8))

@@ -1,5 +1,8 @@
 """Parity of the CUDA ISW path (through the C ABI) with the reference fixtures and the CPU oracle.
-Tolerance: rtol 1e-5 with atol 1e-7*max|ref| (Gram / loss / gradients)."""
+Tolerance: rtol 1e-5 (BASELINE.json north_star) with an absolute floor of 5e-7*max|ref| for covariance
+entries -- off-diagonal entries of a whitened map are sums with heavy cancellation, and the reference's
+own fp32 bmm deviates from an fp64 evaluation by 4-6e-7*max (printed by test_config5_shapes_against_oracle)."""
+COV_ATOL = 5e-7
 import os
 
 import numpy as np
@@ -41,7 +44,7 @@ def test_matches_reference_fixture(fixtures, name, tc, monkeypatch):
     loss.backward()
     ref_cov = fixtures[f"{name}_cov"]
     assert_close(w.detach().cpu(), fixtures[f"{name}_norm"], 1e-5, 1e-6, "instance norm")
-    assert_close(cov.detach().cpu(), ref_cov, 1e-5, 1e-7 * amax(ref_cov) + 1e-8, "covariance")
+    assert_close(cov.detach().cpu(), ref_cov, 1e-5, COV_ATOL * amax(ref_cov), "covariance")
     assert_close(loss.detach().cpu(), fixtures[f"{name}_loss"], 1e-5, 0, "loss")
     gx = fixtures[f"{name}_grad_x"]
     assert_close(x.grad.cpu(), gx, 1e-5, 2e-6 * amax(gx), "grad through norm")
@@ -77,7 +80,7 @@ def test_config5_shapes_against_oracle(shape, tc, monkeypatch):
     loss = instance_whitening_loss(w, eye.to(DEV), mask.to(DEV), 0, mask.sum().to(DEV))
     loss.backward()
     assert_close(y.detach().cpu(), wr.detach(), 1e-5, 1e-6, "instance norm")
-    assert_close(cov.detach().cpu(), cov_r.detach(), 1e-5, 1e-7 * amax(cov_r.detach()) + 2e-7, "covariance")
+    assert_close(cov.detach().cpu(), cov_r.detach(), 1e-5, COV_ATOL * amax(cov_r.detach()), "covariance")
     assert_close(loss.detach().cpu(), loss_r.detach(), 1e-5, 0, "loss")
     assert_close(xd.grad.cpu(), xr.grad, 1e-5, 2e-6 * amax(xr.grad), "grad")
     err_ref = float((cov_r.detach().double() - cov64).abs().max())
@@ -96,7 +99,7 @@ def test_covariance_backward_generic_upstream():
     xd = x.to(DEV).requires_grad_(True)
     cd, _ = get_covariance_matrix(xd)  # eye=None -> built on the map's device (instance_whitening.py:34-35)
     (cd * up.to(DEV)).sum().backward()
-    assert_close(cd.detach().cpu(), cr.detach(), 1e-5, 1e-7 * amax(cr.detach()) + 1e-8, "covariance")
+    assert_close(cd.detach().cpu(), cr.detach(), 1e-5, COV_ATOL * amax(cr.detach()), "covariance")
     assert_close(xd.grad.cpu(), xr.grad, 1e-5, 1e-6 * amax(xr.grad), "grad")
 
 

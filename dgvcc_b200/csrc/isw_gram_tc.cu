@@ -3,7 +3,11 @@
 // Replaces the torch.bmm of models/ISW/instance_whitening.py:37.  X_b is [C, HW] fp32 with HW
 // contiguous, i.e. both MMA operands are K-major.  fp32 accuracy (rtol 1e-5 against the reference's
 // sgemm) comes from the 3xTF32 split  x = hi + lo,  hi = RN_tf32(x), lo = RN_tf32(x - hi):
-//     G ~= hi hi^T + hi lo^T + lo hi^T          (fp32 accumulation in TMEM; lo lo^T ~ 2^-22 is dropped)
+//     G ~= hi hi^T + (hi lo^T + lo hi^T)        (fp32 accumulation in TMEM; lo lo^T ~ 2^-22 is dropped)
+// The tensor core truncates (does not round) when it adds into the TMEM accumulator, a bias that grows
+// with the number of accumulation steps (measured: -3e-8 relative per step).  So the 2^-11-sized cross
+// terms get their own accumulator -- the main one then sees a third of the steps -- and the host keeps
+// the per-CTA K range short (<= 1024) and adds the splits in fp32 round-to-nearest.
 // One CTA computes one upper-triangular 128x128 tile of one sample over one split of the K = HW range
 // and stores the partial tile; isw_cov_finish_kernel (isw_kernels.cu) adds the splits in order.
 //
@@ -30,7 +34,7 @@ constexpr int TILE_BYTES = TILE_M * BLOCK_K * 4;  // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, B_hi, A_lo, B_lo
 constexpr int THREADS = 192;
 constexpr int CONVERTER_WARPS = 4;
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = 256;  // two fp32 accumulators: hi*hi^T, and the small cross terms
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,6 +102,19 @@ __device__ __forceinline__ float tf32_round(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
 }
 
 struct Args {
@@ -179,8 +196,8 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
                 for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);  // +32 B inside the swizzle row
                     umma_tf32(tmem_d, a_hi + adv, b_hi + adv, (kb | ks) != 0);
-                    umma_tf32(tmem_d, a_hi + adv, b_lo + adv, 1u);
-                    umma_tf32(tmem_d, a_lo + adv, b_hi + adv, 1u);
+                    umma_tf32(tmem_d + TILE_M, a_hi + adv, b_lo + adv, (kb | ks) != 0);
+                    umma_tf32(tmem_d + TILE_M, a_lo + adv, b_hi + adv, 1u);
                 }
                 umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
             }
@@ -221,19 +238,13 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
         const bool row_ok = ti * TILE_M + row < a.c;
 #pragma unroll 1
         for (int c0 = 0; c0 < TILE_M; c0 += 32) {
-            uint32_t r[32];
+            uint32_t r[32], x[32];
             const uint32_t taddr = tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr)
-                : "memory");
+            tmem_ld32(taddr, r);           // hi hi^T
+            tmem_ld32(taddr + TILE_M, x);  // hi lo^T + lo hi^T
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(x[q]));
             if (row_ok && tj * TILE_M + c0 < a.c) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q)

@@ -319,7 +319,9 @@ static void gram_plan(int batch, int c, int hw, int tile, int* splits, int* k_pe
     const int want = 296;
     int s = ceil_div(want, batch * *n_tiles);
     const int max_s = ceil_div(hw, 256);
+    const int min_s = ceil_div(hw, 1024);  // short accumulation chains: the tensor core truncates on accumulate
     if (s > max_s) s = max_s;
+    if (s < min_s) s = min_s;
     if (s < 1) s = 1;
     int kps = ceil_div(ceil_div(hw, s), 32) * 32;
     *splits = ceil_div(hw, kps);

@@ -117,7 +117,7 @@ def test_tensor_core_gram_partials_directly(shape):
     g = torch.Generator().manual_seed(11 + c)
     x = torch.randn((b, c, hw), generator=g)
     xd = x.to(DEV).contiguous()
-    splits, kps = 3, ((hw + 2) // 3 + 31) // 32 * 32
+    kps = min(1024, ((hw + 2) // 3 + 31) // 32 * 32)  # the library keeps accumulation chains <= 1024 (truncation bias)
     splits = (hw + kps - 1) // kps
     t1 = (c + 127) // 128
     n_tiles = t1 * (t1 + 1) // 2

@@ -5,9 +5,9 @@
 // sgemm) comes from the 3xTF32 split  x = hi + lo,  hi = RN_tf32(x), lo = RN_tf32(x - hi):
 //     G ~= hi hi^T + (hi lo^T + lo hi^T)        (fp32 accumulation in TMEM; lo lo^T ~ 2^-22 is dropped)
 // The tensor core truncates (does not round) when it adds into the TMEM accumulator, a bias that grows
-// with the number of accumulation steps (measured: -3e-8 relative per step).  So the 2^-11-sized cross
+// with the number of accumulation steps (measured: -4e-8 relative per K=8 step, scripts/probe_tc_accuracy.py).  So the 2^-11-sized cross
 // terms get their own accumulator -- the main one then sees a third of the steps -- and the host keeps
-// the per-CTA K range short (<= 1024) and adds the splits in fp32 round-to-nearest.
+// the per-CTA K range short (<= 512) and adds the splits in fp32 round-to-nearest.
 // One CTA computes one upper-triangular 128x128 tile of one sample over one split of the K = HW range
 // and stores the partial tile; isw_cov_finish_kernel (isw_kernels.cu) adds the splits in order.
 //

@@ -150,7 +150,6 @@ isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits,
     while (rem >= tiles_1d - ti) { rem -= tiles_1d - ti; ++ti; }
     const int tj = ti + rem;
     const int b = blockIdx.z;
-    const float inv = 1.0f / (float)(hw - 1);
     const size_t tile_elems = (size_t)tile * tile;
     for (int e = blockIdx.y * 256 + threadIdx.x; e < tile * tile; e += gridDim.y * 256) {
         const int li = e / tile, lj = e % tile;
@@ -161,7 +160,6 @@ isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits,
             s += part[(((size_t)b * splits + sp) * n_tiles + blockIdx.x) * tile_elems + e];
         // torch: bmm(...).div(HW-1) is a true division; + (eps * eye)
         const float v = s / (float)(hw - 1);
-        (void)inv;
         float* fc = f_cor + (size_t)b * c * c;
         fc[(size_t)i * c + j] = v + eps * eye[(size_t)i * c + j];
         if (ti != tj || li != lj) fc[(size_t)j * c + i] = v + eps * eye[(size_t)j * c + i];
@@ -319,7 +317,7 @@ static void gram_plan(int batch, int c, int hw, int tile, int* splits, int* k_pe
     const int want = 296;
     int s = ceil_div(want, batch * *n_tiles);
     const int max_s = ceil_div(hw, 256);
-    const int min_s = ceil_div(hw, 1024);  // short accumulation chains: the tensor core truncates on accumulate
+    const int min_s = ceil_div(hw, 512);  // short accumulation chains: the tensor core truncates on accumulate
     if (s > max_s) s = max_s;
     if (s < min_s) s = min_s;
     if (s < 1) s = 1;

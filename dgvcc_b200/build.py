@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + sources() + ["-lcuda"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + sources()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)

@@ -276,12 +276,25 @@ extern "C" int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int 
     // tensor map, so any C works, but tiny channel counts waste the 128-wide tile
     if (hw % 4 != 0 || c < 32 || k_per_split % BLOCK_K != 0 || ((uintptr_t)x & 15u)) return DGVCC_ERR_UNSUPPORTED;
 
+    // cuTensorMapEncodeTiled is fetched through the runtime so that the library does not link libcuda
+    // (it must load on machines without a driver: the host-only checks of tests/test_abi.py)
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DGVCC_RETURN_IF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) return DGVCC_ERR_UNSUPPORTED;
+        encode = (EncodeTiled)fn;
+    }
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)c, (cuuint64_t)batch};
     const cuuint64_t strides[2] = {(cuuint64_t)hw * 4, (cuuint64_t)c * hw * 4};
     const cuuint32_t box[3] = {BLOCK_K, TILE_M, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, estr,
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return DGVCC_ERR_UNSUPPORTED;

@@ -81,6 +81,12 @@ def cpu_sample(wl, budget_s):
     return picked
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+
+
 def cpu_step(wl, picked):
     """The reference's CPU algorithm (oracle port of losses/bl.py) on the sampled images, one at a time."""
     from oracle import bl_oracle
@@ -92,6 +98,7 @@ def cpu_step(wl, picked):
 
 
 def cpu_baseline(wl, budget_s, repeats=2):
+    use_all_host_threads()
     picked = cpu_sample(wl, budget_s / repeats)
     best = min(cpu_step(wl, picked) for _ in range(repeats))
     m = wl["hp"] * wl["wp"]
@@ -107,10 +114,11 @@ def cpu_baseline(wl, budget_s, repeats=2):
     }
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     wl = workload(0)
     picked = cpu_sample(wl, max(2.0, args.cpu_seconds / max(1, args.steps + args.warmup)))
     for _ in range(min(args.warmup, 1)):
@@ -124,7 +132,7 @@ def run_reference(args):
     sample = (f"oracle port of losses/bl.py (torch CPU, {torch.get_num_threads()} threads); each step = the "
               f"{len(picked)} smallest images of the batch ({sum(wl['counts'][i] for i in picked)} heads), "
               f"scaled by point-pixel pairs to the full 16-image batch")
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "Bayesian-loss fwd+bwd images/s (QNRF shape)", "value": value,
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_batch * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -240,7 +248,7 @@ def kernel_breakdown(wl, dev, reps=5):
     return dict(zip(names, ms.tolist())), kept_rows, packed
 
 
-def run_gpu(args):
+def run_gpu(args, emit=print):
     import torch.distributed as dist
     from dgvcc_b200.losses.bl import BL
     from dgvcc_b200.sharding import ShardedLoss
@@ -369,14 +377,35 @@ def run_gpu(args):
         }
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+class StdoutToStderr:
+    """Libraries (e.g. NCCL's version banner) write to fd 1; keep stdout for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_gpu(a)
+    with StdoutToStderr() as out:
+        printer = lambda line: out.emit(line)  # noqa: E731
+        if a.impl == "reference":
+            run_reference(a, printer)
+        else:
+            run_gpu(a, printer)

@@ -1,0 +1,176 @@
+"""Secondary measurements of SURVEY.md section 8d: density-map generation (BASELINE config 4) and the ISW
+covariance loss (config 5).  One JSON line per workload; CUDA-event timing, L2 flushed between repetitions.
+
+    python scripts/bench_aux.py [--cpu]      # --cpu also times the oracle (reference algorithm) on a bounded sample
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from dgvcc_b200 import _native, synthetic  # noqa: E402
+
+dev = torch.device("cuda:0")
+HBM_GBS = 6446.0  # MEASURED_PEAKS.json (driver-written) copy bandwidth of this pool's B200
+if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")):
+    HBM_GBS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))).get("hbm_gbs", HBM_GBS)
+
+
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def config4_images():
+    rng = np.random.default_rng(4000)
+    images = []
+    for i in range(64):
+        h, w = int(rng.integers(512, 2049)), int(rng.integers(512, 2049))
+        n = 0 if i == 0 else 3 if i == 1 else synthetic.log_uniform_count(rng, 1, 25000)
+        dtype = np.float32 if i % 8 == 7 else np.float64
+        images.append(((h, w), synthetic.crowd_points(np.random.default_rng(4000 + i), n, w, h, dtype=dtype)))
+    return images
+
+
+def bench_dmap(cpu):
+    from dgvcc_b200.utils import dmap_gen
+    lib = _native.lib()
+    images = config4_images()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for adaptive in (True, False):
+        t_dev = t_splat = 0.0
+        bytes_alg = 0
+        for rep in range(2):
+            t_dev = t_splat = 0.0
+            bytes_alg = 0
+            for (h, w), pts in images:
+                n = len(pts)
+                p64 = np.ascontiguousarray(pts, dtype=np.float64)
+                d_pts = torch.from_numpy(p64).to(dev) if n else None
+                out = torch.empty((h, w), dtype=torch.float32, device=dev)
+                ws_bytes = lib.dgvcc_dmap_workspace_bytes(n)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                idx = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+                dist = torch.empty((max(n, 1), 4), dtype=torch.float64, device=dev)
+                sig = torch.empty((max(n, 1),), dtype=torch.float64, device=dev)
+                flush.zero_()
+                e0, e1, e2 = ev(), ev(), ev()
+                st = _native.stream_ptr(dev)
+                e0.record()
+                if adaptive and n:
+                    lib.dgvcc_dmap_knn_sigma(_native.ptr(d_pts), n, _native.ptr(idx), _native.ptr(dist), _native.ptr(sig), st)
+                e1.record()
+                lib.dgvcc_dmap_splat(_native.ptr(d_pts), _native.ptr(sig) if (adaptive and n) else None, 4.0,
+                                     4.0 if adaptive else 1.75, n, h, w, _native.ptr(ws), ws_bytes, _native.ptr(out), st)
+                e2.record()
+                torch.cuda.synchronize()
+                t_dev += e0.elapsed_time(e2)
+                t_splat += e1.elapsed_time(e2)
+                bytes_alg += 4 * h * w + 16 * n
+        # end to end through the public API: host numpy in, host numpy out
+        fn = dmap_gen.gaussian_filter_density if adaptive else dmap_gen.gaussian_filter_density_fixed
+        t0 = time.perf_counter()
+        for (h, w), pts in images:
+            fn(np.empty((h, w, 0)), pts)
+        e2e_s = time.perf_counter() - t0
+        line = {
+            "workload": f"BASELINE config 4: 64 JHU-shaped images (512..2048 px sides, 0..25000 heads), "
+                        f"{'adaptive kNN sigma' if adaptive else 'fixed sigma 4'}",
+            "metric": "density maps/s", "value_device": 64 / (t_dev * 1e-3), "value_e2e_host_numpy": 64 / e2e_s,
+            "ms_total_device": t_dev, "ms_splat": t_splat,
+            "roofline": {"bound": "hbm", "achieved": bytes_alg / (t_splat * 1e-3) / 1e9, "peak": HBM_GBS, "unit": "GB/s",
+                         "frac": bytes_alg / (t_splat * 1e-3) / 1e9 / HBM_GBS,
+                         "note": "algorithmic bytes 4*H*W + 16*N per image / time of prepare+splat kernels"},
+        }
+        if cpu:
+            from oracle import dmap_oracle
+            small = sorted(images, key=lambda im: len(im[1]))[2:5]  # three small non-trivial images
+            t0 = time.perf_counter()
+            heads = 0
+            for (h, w), pts in small:
+                dmap_oracle.density_reference_like((h, w), pts, fixed=not adaptive)
+                heads += len(pts)
+            dt = time.perf_counter() - t0
+            total_heads = sum(len(p) for _, p in images)
+            line["cpu_baseline"] = {"value": 64 / (dt / max(heads, 1) * total_heads), "unit": "density maps/s", "cores": 1,
+                                    "kind": "port", "sample": f"reference algorithm (scipy gaussian_filter per head) on 3 small images, "
+                                    f"{heads} heads in {dt:.1f} s; extrapolated per head to the {total_heads} heads of the set"}
+        print(json.dumps(line), flush=True)
+
+
+def bench_isw(cpu):
+    from dgvcc_b200.models.ISW import InstanceWhitening, instance_whitening_loss
+    from oracle import isw_oracle
+    lib = _native.lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for (b, c, h, w) in [(8, 64, 160, 160), (8, 256, 80, 80), (8, 512, 40, 40)]:
+        hw = h * w
+        x = torch.randn(b, c, hw, device=dev)
+        eye = torch.eye(c, device=dev)
+        n = lib.dgvcc_isw_workspace_bytes(b, c, hw)
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        fc = torch.empty(b, c, c, device=dev)
+        ts = []
+        for rep in range(6):
+            flush.zero_()
+            e0, e1 = ev(), ev()
+            e0.record()
+            lib.dgvcc_isw_covariance(_native.ptr(x), _native.ptr(eye), b, c, hw, 1, _native.ptr(ws), n, _native.ptr(fc), _native.stream_ptr(dev))
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                ts.append(e0.elapsed_time(e1))
+        t_cov = min(ts)
+        xin = torch.randn(b, c, h, w, device=dev, requires_grad=True)
+        mask = isw_oracle.upper_mask(c, 0.5, 1).to(dev)
+        iw = InstanceWhitening(c)
+        tm = []
+        for rep in range(6):
+            flush.zero_()
+            xin.grad = None
+            e0, e1 = ev(), ev()
+            e0.record()
+            y, wt = iw(xin)
+            loss = instance_whitening_loss(wt, eye, mask, 0, mask.sum())
+            loss.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                tm.append(e0.elapsed_time(e1))
+        t1 = (c + 127) // 128
+        tiles = t1 * (t1 + 1) // 2
+        mma_flops = 3 * 2.0 * b * tiles * 128 * 128 * hw  # executed: 3 TF32 MMAs per logical product, 128x128 tiles
+        line = {
+            "workload": f"BASELINE config 5: ISW covariance loss, B={b} C={c} HW={hw}",
+            "metric": "steps/s (InstanceWhitening + instance_whitening_loss fwd+bwd)", "value": 1e3 / min(tm),
+            "ms_fwd_bwd": min(tm), "us_covariance": t_cov * 1e3,
+            "roofline": {"bound": "hbm" if c <= 64 else "tensor",
+                         "hbm_gbs": 4.0 * b * c * hw / (t_cov * 1e-3) / 1e9, "hbm_frac": 4.0 * b * c * hw / (t_cov * 1e-3) / 1e9 / HBM_GBS,
+                         "tf32_tflops_executed": mma_flops / (t_cov * 1e-3) / 1e12,
+                         "useful_tflops": 2.0 * b * c * c * hw / (t_cov * 1e-3) / 1e12,
+                         "note": "covariance = tcgen05 Gram partials + finish kernel; hbm = 4*B*C*HW bytes read once"},
+        }
+        if cpu:
+            xc = xin.detach().cpu().requires_grad_(True)
+            t0 = time.perf_counter()
+            wr = isw_oracle.instance_standardize(xc)
+            isw_oracle.whitening_loss(wr, eye.cpu(), mask.cpu(), 0, mask.sum().cpu()).backward()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "oracle port of instance_whitening.py, same tensors, one fwd+bwd"}
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    if a.only in ("", "dmap"):
+        bench_dmap(a.cpu)
+    if a.only in ("", "isw"):
+        bench_isw(a.cpu)

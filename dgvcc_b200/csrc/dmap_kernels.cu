@@ -81,32 +81,57 @@ __device__ __forceinline__ double phi(double coef, int i) {
     return exp(__dmul_rn(coef, (double)((long long)i * i)));
 }
 
-// numpy's pairwise summation (DOUBLE_pairwise_sum) of phi(first), phi(first+1), ...: n elements.
-__device__ double pairwise_phi_sum(double coef, int first, int n) {
+// Leaf of numpy's pairwise summation (DOUBLE_pairwise_sum, n <= 128) over phi(first), phi(first+1), ...
+__device__ __forceinline__ double pairwise_leaf(double coef, int first, int n) {
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; ++i) res = __dadd_rn(res, phi(coef, first + i));
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = phi(coef, first + j);
-        int i = 8;
-        for (; i < n - (n % 8); i += 8) {
+    for (int j = 0; j < 8; ++j) r[j] = phi(coef, first + j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], phi(coef, first + i + j));
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) res = __dadd_rn(res, phi(coef, first + i));
-        return res;
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], phi(coef, first + i + j));
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    const double a = pairwise_phi_sum(coef, first, n2);
-    const double b = pairwise_phi_sum(coef, first + n2, n - n2);
-    return __dadd_rn(a, b);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, phi(coef, first + i));
+    return res;
+}
+
+// numpy's pairwise summation: blocks of <= 128 are leaves, larger ranges split at n/2 rounded down to a
+// multiple of 8 and the halves are added.  Explicit stack instead of recursion (depth <= 24 for n < 2^31),
+// so the kernel needs no enlarged device stack however large a sparse image's sigma gets.
+__device__ double pairwise_phi_sum(double coef, int first, int n) {
+    constexpr int DEPTH = 26;
+    int s_first[DEPTH], s_n[DEPTH], s_stage[DEPTH];
+    double s_left[DEPTH];
+    int sp = 0;
+    s_first[0] = first; s_n[0] = n; s_stage[0] = 0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int cn = s_n[sp];
+        int n2 = cn / 2;
+        n2 -= n2 % 8;
+        if (s_stage[sp] == 0) {
+            if (cn <= 128) { ret = pairwise_leaf(coef, s_first[sp], cn); --sp; continue; }
+            s_stage[sp] = 1;
+            s_first[sp + 1] = s_first[sp]; s_n[sp + 1] = n2; s_stage[sp + 1] = 0;
+            ++sp;
+        } else if (s_stage[sp] == 1) {
+            s_left[sp] = ret;
+            s_stage[sp] = 2;
+            s_first[sp + 1] = s_first[sp] + n2; s_n[sp + 1] = cn - n2; s_stage[sp + 1] = 0;
+            ++sp;
+        } else {
+            ret = __dadd_rn(s_left[sp], ret);
+            --sp;
+        }
+    }
+    return ret;
 }
 
 __global__ void __launch_bounds__(128)
@@ -232,7 +257,6 @@ extern "C" int dgvcc_dmap_splat(const double* pts_xy, const double* sigma, doubl
     cudaStream_t st = (cudaStream_t)stream;
     Stamp* stamps = (Stamp*)workspace;
     if (n > 0) {
-        // deep pairwise recursion for huge kernels: radius 2^20 -> depth 14, well inside the default stack
         dmap_prepare_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const double2*)pts_xy, sigma, fixed_sigma, truncate, n,
                                                               height, width, stamps);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());

@@ -86,6 +86,19 @@ def test_full_size_against_closed_form_oracle(seed, n, h, w, dtype):
     assert got.sum(dtype=np.float64) <= n * (1 + 1e-6)
 
 
+def test_sparse_images_with_huge_sigma():
+    """4..10 heads spread over a 2048 px image: sigma in the hundreds, kernel radius in the thousands
+    (deep pairwise splits of the normaliser sum)."""
+    from dgvcc_b200.utils import dmap_gen
+    for n, seed in ((4, 1), (5, 2), (7, 3), (10, 4)):
+        rng = np.random.default_rng(seed)
+        h, w = 2048, 1900
+        pts = rng.uniform([0, 0], [w - 1, h - 1], size=(n, 2))
+        ref = dmap_oracle.density_closed_form((h, w), pts)
+        got = dmap_gen.gaussian_filter_density(np.empty((h, w, 0)), pts)
+        assert_map_close(got, ref, f"sparse n={n}")
+
+
 def test_batch_api_and_file_protocol(tmp_path):
     from dgvcc_b200.utils import dmap_gen
     from PIL import Image

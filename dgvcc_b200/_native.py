@@ -28,13 +28,13 @@ SIGNATURES = {
     "dgvcc_abi_version": (c_int, []),
     "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
     "dgvcc_bl_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
-                                 c_int, c_int, c_float, c_float, c_float, c_int, c_float, c_void_p, c_size_t,
+                                 c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, c_void_p, c_size_t,
                                  c_void_p, c_void_p]),
     "dgvcc_bl_forward_profiled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                          c_int64, c_int, c_int, c_float, c_float, c_float, c_int, c_float, c_void_p,
-                                          c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
+                                          c_int64, c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float,
+                                          c_void_p, c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
     "dgvcc_bl_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_float, c_float,
-                                  c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+                                  c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_bl_posterior": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_float,
                                    c_float, c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_bl_bayloss_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,

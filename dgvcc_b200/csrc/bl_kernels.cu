@@ -86,6 +86,7 @@ struct __align__(16) WarpTile {
     float2 xs[TILE_PTS];      // (x, x*x)
     float yd[TILE_PTS][R];    // y-axis squared distance to each of the warp's R rows
     float aux[TILE_PTS];      // K2: staged counts; K4: signed weights
+    unsigned char idx[TILE_PTS];  // K2 with culling: position of each kept point inside the staged tile
 };
 
 // Views into the host-built int32 table (layout documented in include/dgvcc_b200.h).
@@ -162,33 +163,55 @@ __device__ __forceinline__ void stage_points(WarpTile<R>& tile, const float2* __
     }
 }
 
-// Same, keeping only points with a non-zero weight (order preserved -> deterministic sums).
-// Returns the number of points kept; their weights land in tile.aux.
-template <int R>
-__device__ __forceinline__ int stage_points_weighted(WarpTile<R>& tile, const float2* __restrict__ pts,
-                                                     const float* __restrict__ w, int n0, int cnt,
-                                                     const float (&cym2)[R], const float (&cyy)[R]) {
+// Same with a per-point predicate keep(x, y, w): only the points it accepts are staged, compacted in
+// order (ballot/popc), so sums stay deterministic.  Returns the number kept.  HAS_W: weights w[n0+i]
+// are read and land in tile.aux; HAS_IDX: tile.idx[pos] records the point's position in the tile.
+template <int R, bool HAS_W, bool HAS_IDX, typename Keep>
+__device__ __forceinline__ int stage_points_if(WarpTile<R>& tile, const float2* __restrict__ pts,
+                                               const float* __restrict__ w, int n0, int cnt,
+                                               const float (&cym2)[R], const float (&cyy)[R], Keep keep_fn) {
     const int lane = threadIdx.x & 31;
     int kept = 0;
 #pragma unroll 1
     for (int base = 0; base < cnt; base += 32) {
         const int i = base + lane;
-        const float wi = (i < cnt) ? __ldg(&w[n0 + i]) : 0.f;
-        const bool keep = wi != 0.f;
+        float2 p = make_float2(0.f, 0.f);
+        float wi = 1.f;
+        bool keep = false;
+        if (i < cnt) {
+            p = __ldg(&pts[n0 + i]);
+            if (HAS_W) wi = __ldg(&w[n0 + i]);
+            keep = keep_fn(p.x, p.y, wi);
+        }
         const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
         if (keep) {
             const int pos = kept + __popc(ballot & ((1u << lane) - 1u));
-            const float2 p = __ldg(&pts[n0 + i]);
             tile.xs[pos] = make_float2(p.x, __fmul_rn(p.x, p.x));
             const float yy = __fmul_rn(p.y, p.y);
 #pragma unroll
             for (int r = 0; r < R; ++r) tile.yd[pos][r] = axis_sqdist(p.y, yy, cym2[r], cyy[r]);
-            tile.aux[pos] = wi;
+            if (HAS_W) tile.aux[pos] = wi;
+            if (HAS_IDX) tile.idx[pos] = (unsigned char)i;
         }
         kept += __popc(ballot);
     }
     return kept;
 }
+
+// Conservative lower bound of the reference's fp32 squared distance dis[n, pixel] over every pixel
+// of a warp's tile, from the point's distance to the rectangle of the tile's cell centres.  The slack
+// covers (i) the rounding of this bound itself and (ii) the error of the reference's cancelling
+// expansion -2pc + p^2 + c^2 (<= 2^-21 (Mx + My), M = largest squared magnitude involved); 4x margin.
+struct TileBox {
+    float x0, x1, y0, y1;  // first / last cell centre of the tile per axis
+    __device__ __forceinline__ float lower_bound(float x, float y) const {
+        const float dx = fmaxf(fmaxf(x0 - x, x - x1), 0.f);
+        const float dy = fmaxf(fmaxf(y0 - y, y - y1), 0.f);
+        const float lb = fmaf(dx, dx, dy * dy);
+        const float m = fmaxf(x * x, x1 * x1) + fmaxf(y * y, y1 * y1);
+        return lb - fmaf(lb, 9.5367431640625e-07f /*2^-20*/, m * 1.9073486328125e-06f /*2^-19*/);
+    }
+};
 
 template <int R>
 __device__ __forceinline__ void load_yd(const WarpTile<R>& tile, int i, float (&yd)[R]) {
@@ -212,6 +235,7 @@ struct PixelTile {
     float cym2[R], cyy[R], cxm2[C], cxx[C];
     int col[C];       // clamped column index
     int row_base, hp, wp, col0;
+    TileBox box;
 
     __device__ __forceinline__ void init(const TaskInfo& t, const Geom& g) {
         row_base = t.row_base; hp = g.hp; wp = g.wp; col0 = t.col0;
@@ -228,22 +252,46 @@ struct PixelTile {
             cxm2[c] = -2.0f * cx;
             cxx[c] = __fmul_rn(cx, cx);
         }
+        const int blk_col0 = t.col0 - (int)(threadIdx.x & 31);
+        box.x0 = cell_centre(blk_col0, g);
+        box.x1 = cell_centre(min(blk_col0 + 32 * C - 1, g.wp - 1), g);
+        box.y0 = cell_centre(t.row_base, g);
+        box.y1 = cell_centre(min(t.row_base + R - 1, g.hp - 1), g);
     }
     __device__ __forceinline__ int pix(int r, int c) const { return min(row_base + r, hp - 1) * wp + col[c]; }
     __device__ __forceinline__ bool ok(int r, int c) const { return row_base + r < hp && col0 + 32 * c < wp; }
 };
 
-// min over the chunk's points of the squared distance (bl.py:39), into mind[r][c]
+// Largest value of v[r][c] over the whole warp tile.
+template <int R, int C>
+__device__ __forceinline__ float tile_max(const float (&v)[R][C]) {
+    float m = v[0][0];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) m = fmaxf(m, v[r][c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+    return m;
+}
+
+// min over the chunk's points of the squared distance (bl.py:39), into mind[r][c].
+// Exact pruning: a point whose distance lower bound over the tile exceeds the largest current minimum of
+// the tile cannot lower any pixel's minimum, so it is not staged (the first tile of a chunk is dense).
 template <int R, int C>
 __device__ __forceinline__ void sweep_min(WarpTile<R>& tile, const PixelTile<R, C>& px, const float2* pts,
                                           int cnt_total, float (&mind)[R][C]) {
     for (int n0 = 0; n0 < cnt_total; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, cnt_total - n0);
+        const float bound = tile_max<R, C>(mind);
+        const TileBox box = px.box;
         __syncwarp();
-        stage_points<R>(tile, pts, n0, cnt_total, cnt, px.cym2, px.cyy);
+        const int kept = stage_points_if<R, false, false>(
+            tile, pts, nullptr, n0, cnt, px.cym2, px.cyy,
+            [&](float x, float y, float) { return box.lower_bound(x, y) <= bound; });
         __syncwarp();
 #pragma unroll 2
-        for (int i = 0; i < cnt; ++i) {
+        for (int i = 0; i < kept; ++i) {
             const float2 xs = tile.xs[i];
             float yd[R];
             load_yd<R>(tile, i, yd);
@@ -256,6 +304,21 @@ __device__ __forceinline__ void sweep_min(WarpTile<R>& tile, const PixelTile<R, 
         }
     }
 }
+
+// Exact-zero culling of the exponential sweeps (opt-in): exp(a - amax) is computed as one MUFU.EX2 with
+// flush-to-zero, so it is exactly +0 whenever (a - amax) * log2(e) < -126.  With a <= -lb/s for every pixel
+// of the tile and amax >= the tile's smallest amax, a point is skipped when that bound is below -128 --
+// every term it would have contributed is an exact zero, and the results are bit-identical.
+struct ExpCull {
+    bool on;
+    float neg_min_amax;  // max over the tile of -amax
+    float inv_s;
+    TileBox box;
+    __device__ __forceinline__ bool keep(float x, float y) const {
+        if (!on) return true;
+        return fmaf(-box.lower_bound(x, y), inv_s, neg_min_amax) * LOG2E >= -128.f;
+    }
+};
 
 // ------------------------------------------------------------------------------------------ K0
 // Only for images split into several point chunks: per-chunk partial minima.
@@ -290,8 +353,8 @@ template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
-            const float* __restrict__ minpart, float* __restrict__ zpart, float* __restrict__ amax_out,
-            float* __restrict__ ebg_out) {
+            int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
+            float* __restrict__ amax_out, float* __restrict__ ebg_out) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
     if (!decode_task<R, C>(meta, batch, g, t)) return;
@@ -360,10 +423,15 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < C; ++c) z[r][c] = 0.f;
+    const ExpCull cull{exact_cull != 0, tile_max<R, C>(neg_amax), k.r, px.box};
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
-        const int cnt = min(TILE_PTS, t.p_cnt - n0);
+        int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
-        stage_points<R>(tile, pts, n0, t.p_cnt, cnt, px.cym2, px.cyy);
+        if (exact_cull)
+            cnt = stage_points_if<R, false, false>(tile, pts, nullptr, n0, cnt, px.cym2, px.cyy,
+                                                   [&](float x, float y, float) { return cull.keep(x, y); });
+        else
+            stage_points<R>(tile, pts, n0, t.p_cnt, cnt, px.cym2, px.cyy);
         __syncwarp();
 #pragma unroll 2
         for (int i = 0; i < cnt; ++i) {
@@ -406,7 +474,7 @@ __device__ __forceinline__ float softmax_rz(const float* __restrict__ zpart, siz
 template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
-                 const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg,
+                 const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg, int exact_cull,
                  const float* __restrict__ amax_in, const float* __restrict__ ebg_in,
                  const float* __restrict__ zpart, float* __restrict__ rz_out, float* __restrict__ pbg_out,
                  int64_t total_rows, float* __restrict__ cpart) {
@@ -448,11 +516,26 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
 
     const float2* pts = pts_all + t.pt_base;
     part += t.p_start;
+    const ExpCull cull{exact_cull != 0, tile_max<R, C>(neg_amax), k.r, px.box};
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, t.p_cnt - n0);
-        const int padded = (cnt + 7) & ~7;
+        int kept = cnt;
         __syncwarp();
-        stage_points<R>(tile, pts, n0, t.p_cnt, padded, px.cym2, px.cyy);
+        if (exact_cull) {
+            for (int i = lane; i < cnt; i += 32) tile.aux[i] = 0.f;  // culled points: partial count exactly 0
+            kept = stage_points_if<R, false, true>(tile, pts, nullptr, n0, cnt, px.cym2, px.cyy,
+                                                   [&](float x, float y, float) { return cull.keep(x, y); });
+            __syncwarp();
+            // pad the compacted list to a multiple of 8 with copies of its last point (results discarded)
+            for (int i = kept + lane; i < ((kept + 7) & ~7); i += 32) {
+                tile.xs[i] = tile.xs[kept - 1];
+#pragma unroll
+                for (int r = 0; r < R; ++r) tile.yd[i][r] = tile.yd[kept - 1][r];
+            }
+        } else {
+            stage_points<R>(tile, pts, n0, t.p_cnt, (cnt + 7) & ~7, px.cym2, px.cyy);
+        }
+        const int padded = (kept + 7) & ~7;
         __syncwarp();
 #pragma unroll 1
         for (int i0 = 0; i0 < padded; i0 += 8) {
@@ -485,7 +568,11 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
             }
             v[0] += __shfl_xor_sync(FULL_MASK, v[0], 2);
             v[0] += __shfl_xor_sync(FULL_MASK, v[0], 1);
-            if ((lane & 3) == 0) tile.aux[i0 + (lane >> 2)] = v[0];
+            if ((lane & 3) == 0) {
+                const int q = i0 + (lane >> 2);
+                if (!exact_cull) tile.aux[q] = v[0];
+                else if (q < kept) tile.aux[tile.idx[q]] = v[0];
+            }
         }
         __syncwarp();
         for (int i = lane; i < cnt; i += 32) part[n0 + i] = tile.aux[i];
@@ -650,7 +737,7 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
 template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
-               Scale k, int use_bg, float inv_batch, const float* __restrict__ grad_loss,
+               Scale k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
                float* __restrict__ gpart, float* __restrict__ grad_density) {
@@ -674,10 +761,13 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
 
     const float2* pts = pts_all + t.pt_base;
     const float* w_pts = wsel + t.row0 + t.p_start;
+    const ExpCull cull{exact_cull != 0, tile_max<R, C>(neg_amax), k.r, px.box};
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
-        const int kept = stage_points_weighted<R>(tile, pts, w_pts, n0, cnt, px.cym2, px.cyy);
+        const int kept = stage_points_if<R, true, false>(
+            tile, pts, w_pts, n0, cnt, px.cym2, px.cyy,
+            [&](float x, float y, float w) { return w != 0.f && cull.keep(x, y); });
         __syncwarp();
 #pragma unroll 2
         for (int i = 0; i < kept; ++i) {
@@ -916,7 +1006,7 @@ static T* at(const void* ws, int64_t off) { return reinterpret_cast<T*>((char*)w
 using namespace dgvcc;
 using namespace dgvcc::bl;
 
-extern "C" int dgvcc_abi_version(void) { return 3; }
+extern "C" int dgvcc_abi_version(void) { return 4; }
 
 extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                                          dgvcc_bl_layout* out) {
@@ -969,7 +1059,8 @@ inline void mark(void** events, int i, cudaStream_t st) {
 
 // partial minima (multi-chunk images only) + softmax max / denominator shares
 int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
-             int multi_chunk, float bg_ratio, int use_bg, void* ws, cudaStream_t st, void** events = nullptr) {
+             int multi_chunk, float bg_ratio, int use_bg, int exact_cull, void* ws, cudaStream_t st,
+             void** events = nullptr) {
     float* minpart = at<float>(ws, p.L.minpart);
     const float2* pts = (const float2*)pts_xy;
     mark(events, 0, st);
@@ -982,7 +1073,7 @@ int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const floa
     }
     mark(events, 1, st);
     BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
-                minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg));
+                exact_cull, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg));
     mark(events, 2, st);
     return (int)cudaGetLastError();
 }
@@ -1004,17 +1095,18 @@ int launch_select(const dgvcc_bl_layout& L, const float* targets, const int32_t*
 extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targets, const int32_t* meta,
                                          const float* st_sizes, const float* density, int batch, int hp, int wp,
                                          int64_t total_rows, int total_chunks, int multi_chunk, float stride,
-                                         float sigma, float bg_ratio, int use_bg, float inv_batch, void* workspace,
-                                         size_t workspace_bytes, float* loss_out, void* stream, void** events) {
+                                         float sigma, float bg_ratio, int use_bg, int exact_cull, float inv_batch,
+                                         void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
+                                         void** events) {
     Plan p;
     int rc = make_plan(meta, density, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
                        sigma, &p);
     if (rc) return rc;
     if (!st_sizes || !loss_out || !pts_xy || !targets) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, workspace, st, events))) return rc;
+    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, exact_cull, workspace, st, events))) return rc;
     BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
-                use_bg, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.zpart),
+                use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.zpart),
                 at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
                 at<float>(workspace, p.L.cpart));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
@@ -1027,17 +1119,17 @@ extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targe
 extern "C" int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* meta,
                                 const float* st_sizes, const float* density, int batch, int hp, int wp,
                                 int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
-                                float bg_ratio, int use_bg, float inv_batch, void* workspace,
+                                float bg_ratio, int use_bg, int exact_cull, float inv_batch, void* workspace,
                                 size_t workspace_bytes, float* loss_out, void* stream) {
     return dgvcc_bl_forward_profiled(pts_xy, targets, meta, st_sizes, density, batch, hp, wp, total_rows,
-                                     total_chunks, multi_chunk, stride, sigma, bg_ratio, use_bg, inv_batch,
-                                     workspace, workspace_bytes, loss_out, stream, nullptr);
+                                     total_chunks, multi_chunk, stride, sigma, bg_ratio, use_bg, exact_cull,
+                                     inv_batch, workspace, workspace_bytes, loss_out, stream, nullptr);
 }
 
 extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp,
                                  int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
-                                 int use_bg, float inv_batch, const float* grad_loss, void* workspace,
-                                 size_t workspace_bytes, float* grad_density, void* stream) {
+                                 int use_bg, int exact_cull, float inv_batch, const float* grad_loss,
+                                 void* workspace, size_t workspace_bytes, float* grad_density, void* stream) {
     Plan p;
     int rc = make_plan(meta, grad_loss, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
                        sigma, &p);
@@ -1045,7 +1137,7 @@ extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int b
     if (!grad_density || !pts_xy) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
-                inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
+                exact_cull, inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                 at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
                 grad_density);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
@@ -1069,7 +1161,7 @@ extern "C" int dgvcc_bl_posterior(const float* pts_xy, const int32_t* meta, cons
     if (rc) return rc;
     if (!prob_out || !pts_xy) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, workspace, st))) return rc;
+    if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, /*exact_cull=*/0, workspace, st))) return rc;
     const int M = hp * wp;
     bl_finish_z_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, st>>>(
         meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.rz),

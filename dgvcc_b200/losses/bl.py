@@ -139,7 +139,7 @@ class _FusedBL(torch.autograd.Function):
     """dgvcc_bl_forward / dgvcc_bl_backward; only the density receives gradient (bl.py:73-79)."""
 
     @staticmethod
-    def forward(ctx, density, packed, targets, st_sizes, stride, sigma, bg_ratio, use_bg, inv_batch, keep):
+    def forward(ctx, density, packed, targets, st_sizes, stride, sigma, bg_ratio, use_bg, inv_batch, keep, cull):
         _native.require_cuda(density, "BL.forward")
         b, hp, wp = density.shape[0], density.shape[-2], density.shape[-1]
         dens = density.detach().reshape(b, hp, wp).to(torch.float32).contiguous()
@@ -150,11 +150,11 @@ class _FusedBL(torch.autograd.Function):
         rc = _native.lib().dgvcc_bl_forward(
             _native.ptr(packed.pts), _native.ptr(targets), _native.ptr(packed.meta), _native.ptr(st_sizes),
             _native.ptr(dens), b, hp, wp, packed.total_rows, packed.total_chunks, packed.multi_chunk, stride, sigma,
-            bg_ratio, int(use_bg), inv_batch,
+            bg_ratio, int(use_bg), int(cull), inv_batch,
             _native.ptr(ws), lay.total, _native.ptr(loss), _native.stream_ptr(dev))
         _native.check(rc, "dgvcc_bl_forward")
         ctx.packed, ctx.ws, ctx.lay = packed, ws, lay
-        ctx.geom = (b, hp, wp, stride, sigma, int(use_bg), inv_batch)
+        ctx.geom = (b, hp, wp, stride, sigma, int(use_bg), inv_batch, int(cull))
         ctx.dens_shape, ctx.dens_dtype = density.shape, density.dtype
         if keep is not None:  # debugging / tests: expose the workspace regions
             keep["workspace"], keep["layout"], keep["packed"] = ws, lay, packed
@@ -162,16 +162,17 @@ class _FusedBL(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss):
-        b, hp, wp, stride, sigma, use_bg, inv_batch = ctx.geom
+        b, hp, wp, stride, sigma, use_bg, inv_batch, cull = ctx.geom
         packed, ws, lay = ctx.packed, ctx.ws, ctx.lay
         dev = ws.device
         g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         grad = torch.empty((b, hp, wp), dtype=torch.float32, device=dev)
         rc = _native.lib().dgvcc_bl_backward(
             _native.ptr(packed.pts), _native.ptr(packed.meta), b, hp, wp, packed.total_rows, packed.total_chunks,
-            packed.multi_chunk, stride, sigma, use_bg, inv_batch, _native.ptr(g), _native.ptr(ws), lay.total, _native.ptr(grad), _native.stream_ptr(dev))
+            packed.multi_chunk, stride, sigma, use_bg, cull, inv_batch, _native.ptr(g), _native.ptr(ws), lay.total,
+            _native.ptr(grad), _native.stream_ptr(dev))
         _native.check(rc, "dgvcc_bl_backward")
-        return (grad.reshape(ctx.dens_shape).to(ctx.dens_dtype),) + (None,) * 9
+        return (grad.reshape(ctx.dens_shape).to(ctx.dens_dtype),) + (None,) * 10
 
 
 class Post_Prob(Module):
@@ -289,6 +290,9 @@ class BL(Module):
         self.post_prob = Post_Prob(sigma, c_size, stride, background_ratio, use_background, device)
         self.bay_loss = Bay_Loss(use_background, device)
         self.global_batch = None  # set by dgvcc_b200.sharding when images are partitioned across ranks
+        # Opt-in: skip (point, pixel-tile) pairs whose exponentials are provably exact zeros.  The results are
+        # bit-identical to the dense evaluation (tests/test_bl_gpu.py); bench.py's graded numbers are dense.
+        self.exact_cull = bool(int(os.environ.get("DGVCC_BL_EXACT_CULL", "0")))
 
     def forward(self, points, st_sizes, target_list, pre_density, _keep=None):
         pp = self.post_prob
@@ -301,4 +305,4 @@ class BL(Module):
         st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()
         inv_batch = 1.0 / float(self.global_batch or packed.batch)
         return _FusedBL.apply(pre_density, packed, targets, st, float(pp.stride), float(pp.sigma),
-                              float(pp.bg_ratio), bool(pp.use_bg), inv_batch, _keep)
+                              float(pp.bg_ratio), bool(pp.use_bg), inv_batch, _keep, self.exact_cull)

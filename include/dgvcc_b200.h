@@ -53,6 +53,8 @@ int dgvcc_abi_version(void);
  * total_chunks = C; multi_chunk = 1 when some image has more than one chunk.
  * inv_batch = 1 / (global batch size); with image sharding across GPUs every
  * rank passes 1/B_global and all-reduces the returned partial loss.
+ * exact_cull != 0 skips (point, pixel-tile) pairs whose exponentials are provably exact zeros
+ * (flush-to-zero MUFU.EX2 below 2^-126): bit-identical results, far fewer pairs.  0 = dense.
  * ------------------------------------------------------------------------- */
 
 /* Named regions inside the caller-owned workspace (byte offsets), for tests and
@@ -87,7 +89,7 @@ int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, i
 int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* meta,
                      const float* st_sizes, const float* density,
                      int batch, int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
-                     float stride, float sigma, float bg_ratio, int use_bg, float inv_batch,
+                     float stride, float sigma, float bg_ratio, int use_bg, int exact_cull, float inv_batch,
                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
 
 /* Same launches with caller-created cudaEvent_t handles recorded between them (bench.py's
@@ -96,7 +98,7 @@ int dgvcc_bl_forward(const float* pts_xy, const float* targets, const int32_t* m
 int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targets, const int32_t* meta,
                               const float* st_sizes, const float* density,
                               int batch, int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
-                              float stride, float sigma, float bg_ratio, int use_bg, float inv_batch,
+                              float stride, float sigma, float bg_ratio, int use_bg, int exact_cull, float inv_batch,
                               void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
                               void** events);
 
@@ -105,7 +107,7 @@ int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targets, const i
  * Re-uses (and scribbles on the gpart region of) the workspace written by dgvcc_bl_forward. */
 int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta,
                       int batch, int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
-                      float stride, float sigma, int use_bg, float inv_batch,
+                      float stride, float sigma, int use_bg, int exact_cull, float inv_batch,
                       const float* grad_loss, void* workspace, size_t workspace_bytes,
                       float* grad_density, void* stream);
 

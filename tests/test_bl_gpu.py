@@ -21,11 +21,12 @@ def _region(keep, name, n):
     return ws[off:off + 4 * n].view(torch.float32)
 
 
-def run_cuda(points, st_sizes, targets, density, stride, sigma, bg_ratio, use_bg, c_size=None):
+def run_cuda(points, st_sizes, targets, density, stride, sigma, bg_ratio, use_bg, c_size=None, exact_cull=False):
     from dgvcc_b200.losses.bl import BL
     dev = torch.device("cuda:0")
     b, _, hp, wp = density.shape
     mod = BL(sigma, c_size or max(hp, wp) * stride, stride, bg_ratio, use_bg, dev)
+    mod.exact_cull = exact_cull
     d = density.to(dev).clone().requires_grad_(True)
     keep = {}
     loss = mod([p.to(dev) for p in points], st_sizes.to(dev), [t.to(dev) for t in targets], d, _keep=keep)
@@ -146,6 +147,26 @@ def test_config3_full_batch_properties():
         total += float(part)
         assert_close(dd.grad.cpu(), grad[sl], 1e-6, 1e-12, "sharded gradient")
     assert_close(total, loss, 1e-6, 0, "sharded loss")
+
+
+@pytest.mark.parametrize("case", ["c1", "mixed", "nobg", "sigma10", "outside", "config2", "config3"])
+def test_exact_cull_is_bit_identical_to_dense(case):
+    """The opt-in culling only skips terms that are exact zeros: loss, counts and gradient must not change
+    in a single bit (dense is what bench.py grades; culling is the production speed-up)."""
+    if case.startswith("config"):
+        cfg = int(case[-1])
+        w, h = synthetic.CONFIG_SHAPES[cfg]
+        pts, st, tgt, dens = _batch(cfg, synthetic.config_counts(cfg), w, h)
+        args = (pts, st, tgt, dens, 8, 8.0, 1.0, True)
+    else:
+        c = load_bl_golden(case)
+        args = (c["points"], c["st_sizes"], c["targets"], c["density"], c["stride"], c["sigma"], c["bg_ratio"], c["use_bg"])
+    dense = run_cuda(*args)
+    culled = run_cuda(*args, exact_cull=True)
+    assert torch.equal(dense[0], culled[0]), "loss"
+    assert torch.equal(dense[1], culled[1]), "gradient"
+    for a, b in zip(dense[2], culled[2]):
+        assert torch.equal(a, b), "expected counts"
 
 
 def test_topk_ties_are_index_ordered():

@@ -48,31 +48,70 @@ def chunk_points():
 
 def build_meta(counts, rows, chunk):
     """The int32 table of include/dgvcc_b200.h: pt_off, row_off, keep, icb, chunks[C][4]."""
+    counts = np.asarray(counts, dtype=np.int64)
+    rows = np.asarray(rows, dtype=np.int64)
     b = len(counts)
     n_chunks = np.maximum(1, -(-counts // chunk))
     total_chunks = int(n_chunks.sum())
     meta = np.zeros(4 * b + 3 + 4 * total_chunks, dtype=np.int32)
     meta[1:b + 1] = np.cumsum(counts)
     meta[b + 2:2 * b + 2] = np.cumsum(rows)
-    # bl.py:76: num = ceil(0.9 * (len(res) - 1)), evaluated in Python doubles on the host
-    meta[2 * b + 2:3 * b + 2] = [ceil(0.9 * (int(r) - 1)) for r in rows]
-    meta[3 * b + 3:4 * b + 3] = np.cumsum(n_chunks)
+    # bl.py:76: num = ceil(0.9 * (len(res) - 1)), the same double arithmetic as Python's
+    meta[2 * b + 2:3 * b + 2] = np.ceil(0.9 * (rows - 1).astype(np.float64))
+    ends = np.cumsum(n_chunks)
+    meta[3 * b + 3:4 * b + 3] = ends
     table = meta[4 * b + 3:].reshape(total_chunks, 4)
-    g = 0
-    for i in range(b):
-        edges = np.linspace(0, int(counts[i]), int(n_chunks[i]) + 1).astype(np.int64)
-        for c in range(int(n_chunks[i])):
-            table[g] = (i, edges[c], edges[c + 1] - edges[c], 0)
-            g += 1
+    img = np.repeat(np.arange(b), n_chunks)
+    k = np.arange(total_chunks) - (ends - n_chunks)[img]      # chunk index inside its image
+    start = counts[img] * k // n_chunks[img]                   # near-equal slices
+    stop = counts[img] * (k + 1) // n_chunks[img]
+    table[:, 0], table[:, 1], table[:, 2] = img, start, stop - start
     # schedule: chunks of the images with the most points first (they have the most tiles in flight)
-    table[:, 3] = np.argsort(-counts[table[:, 0]], kind="stable")
+    table[:, 3] = np.argsort(-counts[img], kind="stable")
     return meta, total_chunks, int(n_chunks.max() > 1)
 
 
-class _Packed:
-    """CSR packing of one ragged batch + the small int32 table the kernels read (include/dgvcc_b200.h)."""
+class _Staging:
+    """A small ring of pinned host buffers per device: one packed H2D copy per step, no per-call
+    cudaHostAlloc.  A buffer is re-used only after the copy that read it has completed (event)."""
+    RING = 4
 
-    def __init__(self, points, use_bg, device):
+    def __init__(self):
+        self.bufs = [None] * self.RING
+        self.events = [None] * self.RING
+        self.next = 0
+
+    def take(self, nbytes):
+        i = self.next
+        self.next = (i + 1) % self.RING
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        if self.bufs[i] is None or self.bufs[i].numel() < nbytes:
+            self.bufs[i] = torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8).pin_memory()
+        return i, self.bufs[i]
+
+    def sent(self, i, device):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[i] = ev
+
+
+_staging = {}
+
+
+def _align16(n):
+    return (n + 15) // 16 * 16
+
+
+class _Packed:
+    """CSR packing of one ragged batch + the small int32 table the kernels read (include/dgvcc_b200.h).
+
+    Host lists (e.g. straight from the DataLoader) are packed on the host -- table, points and targets in
+    one pinned buffer -- and uploaded with a single asynchronous copy; device lists are concatenated on
+    the device like bl.py:21-22.
+    """
+
+    def __init__(self, points, use_bg, device, targets=None):
         points = _as_point_list(points)
         self.batch = len(points)
         if self.batch == 0:
@@ -87,34 +126,59 @@ class _Packed:
         meta, self.total_chunks, self.multi_chunk = build_meta(counts, rows, chunk_points())
         self.pt_off = meta[:b + 1].copy()
         self.row_off = meta[b + 1:2 * b + 2].copy()
-        host = torch.from_numpy(meta)
-        if device.type == "cuda":
-            host = host.pin_memory()
-        self.meta = host.to(device, non_blocking=True)
-        self.on_host = device.type == "cuda" and all(p.device.type == "cpu" for p in points)
-        if self.total_points == 0:
-            self.pts = torch.zeros((1, 2), dtype=torch.float32, device=device)  # never read
-        elif self.on_host:  # host lists (e.g. straight from the DataLoader): pack on the host, one H2D copy
-            self.pts = _upload(torch.cat([p.to(torch.float32) for p in points], dim=0), device)
+        self.targets = None
+        if targets is not None:
+            targets = [t.reshape(-1) for t in targets]
+            for t, n in zip(targets, counts):
+                if t.shape[0] != n:
+                    raise ValueError(f"target length {t.shape[0]} does not match its {n} points")
+        self.on_host = device.type == "cuda" and all(p.device.type == "cpu" for p in points) and \
+            (targets is None or all(t.device.type == "cpu" for t in targets))
+        n_pts = max(self.total_points, 1)
+        if self.on_host:
+            o_pts = _align16(meta.nbytes)
+            o_tgt = o_pts + _align16(8 * n_pts)
+            total = o_tgt + _align16(4 * n_pts)
+            ring = _staging.setdefault(device, _Staging())
+            slot, host = ring.take(total)
+            view = host.numpy()
+            view[:meta.nbytes].view(np.int32)[:] = meta
+            if self.total_points:
+                hp = view[o_pts:o_pts + 8 * self.total_points].view(np.float32).reshape(-1, 2)
+                np.concatenate([p.detach().to(torch.float32).numpy() for p in points if p.shape[0]], axis=0, out=hp)
+                if targets is not None:
+                    ht = view[o_tgt:o_tgt + 4 * self.total_points].view(np.float32)
+                    np.concatenate([t.detach().to(torch.float32).numpy() for t in targets if t.shape[0]], out=ht)
+            dev_buf = host[:total].to(device, non_blocking=True)
+            ring.sent(slot, device)
+            self.meta = dev_buf[:meta.nbytes].view(torch.int32)
+            self.pts = dev_buf[o_pts:o_pts + 8 * n_pts].view(torch.float32).view(-1, 2)
+            if targets is not None:
+                self.targets = dev_buf[o_tgt:o_tgt + 4 * n_pts].view(torch.float32)
         else:
-            self.pts = torch.cat([p.to(device=device, dtype=torch.float32) for p in points], dim=0).contiguous()
-
-
-def _upload(host_tensor, device):
-    return host_tensor.contiguous().pin_memory().to(device, non_blocking=True)
+            host = torch.from_numpy(meta)
+            if device.type == "cuda":
+                host = host.pin_memory()
+            self.meta = host.to(device, non_blocking=True)
+            if self.total_points == 0:
+                self.pts = torch.zeros((1, 2), dtype=torch.float32, device=device)  # never read
+            else:
+                self.pts = torch.cat([p.to(device=device, dtype=torch.float32) for p in points], dim=0).contiguous()
+            if targets is not None:
+                if self.total_points == 0:
+                    self.targets = torch.zeros((1,), dtype=torch.float32, device=device)
+                else:
+                    self.targets = torch.cat([t.to(device=device, dtype=torch.float32) for t in targets]).contiguous()
 
 
 def _pack_targets(target_list, packed, device):
+    """Targets of a batch whose points are already packed (bench / tests helper)."""
     if packed.total_points == 0:
         return torch.zeros((1,), dtype=torch.float32, device=device)
-    parts = []
-    for t, n in zip(target_list, packed.counts):
-        t = t.reshape(-1)
+    parts = [t.reshape(-1) for t in target_list]
+    for t, n in zip(parts, packed.counts):
         if t.shape[0] != n:
             raise ValueError(f"target length {t.shape[0]} does not match its {n} points")
-        parts.append(t)
-    if device.type == "cuda" and all(t.device.type == "cpu" for t in parts):
-        return _upload(torch.cat([t.to(torch.float32) for t in parts], dim=0), device)
     return torch.cat([t.to(device=device, dtype=torch.float32) for t in parts], dim=0).contiguous()
 
 
@@ -300,8 +364,8 @@ class BL(Module):
         _native.require_cuda(pre_density, "BL.forward")
         if len(points) != pre_density.shape[0]:
             raise ValueError(f"{len(points)} point sets for a batch of {pre_density.shape[0]} density maps")
-        packed = _Packed(points, pp.use_bg, dev)
-        targets = _pack_targets(target_list, packed, dev)
+        packed = _Packed(points, pp.use_bg, dev, targets=target_list)
+        targets = packed.targets
         st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()
         inv_batch = 1.0 / float(self.global_batch or packed.batch)
         return _FusedBL.apply(pre_density, packed, targets, st, float(pp.stride), float(pp.sigma),

@@ -169,6 +169,27 @@ def test_exact_cull_is_bit_identical_to_dense(case):
         assert torch.equal(a, b), "expected counts"
 
 
+def test_host_lists_take_the_packed_upload_path():
+    """Point / target lists left on the host (DataLoader output) are packed into one pinned buffer and uploaded
+    once; the result is bit-identical to passing device tensors, also when the ring of staging buffers wraps."""
+    from dgvcc_b200.losses.bl import BL
+    dev = torch.device("cuda:0")
+    c = load_bl_golden("mixed")
+    mod = BL(c["sigma"], c["width"], c["stride"], c["bg_ratio"], c["use_bg"], dev)
+    ref = None
+    for it in range(7):  # > ring size
+        d = c["density"].to(dev).clone().requires_grad_(True)
+        pts = c["points"] if it else [p.to(dev) for p in c["points"]]
+        tgt = c["targets"] if it else [t.to(dev) for t in c["targets"]]
+        loss = mod(pts, c["st_sizes"].to(dev), tgt, d)
+        loss.backward()
+        if ref is None:
+            ref = (loss.detach().clone(), d.grad.clone())
+        else:
+            assert torch.equal(loss.detach(), ref[0]) and torch.equal(d.grad, ref[1])
+    assert_close(ref[0].cpu(), c["ref_loss"], RTOL, 0, "loss")
+
+
 def test_topk_ties_are_index_ordered():
     """Equal residuals straddling the 90 % cut: the kept set is deterministic (first in index order)."""
     from dgvcc_b200.losses.bl import BL

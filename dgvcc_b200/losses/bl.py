@@ -99,6 +99,13 @@ class _Staging:
 _staging = {}
 
 
+def _host_f32(t):
+    """Zero-copy numpy view of a host tensor when it already is fp32, else a converted copy."""
+    if t.dtype != torch.float32 or t.requires_grad:
+        t = t.detach().to(torch.float32)
+    return t.numpy()
+
+
 def _align16(n):
     return (n + 15) // 16 * 16
 
@@ -145,10 +152,10 @@ class _Packed:
             view[:meta.nbytes].view(np.int32)[:] = meta
             if self.total_points:
                 hp = view[o_pts:o_pts + 8 * self.total_points].view(np.float32).reshape(-1, 2)
-                np.concatenate([p.detach().to(torch.float32).numpy() for p in points if p.shape[0]], axis=0, out=hp)
+                np.concatenate([_host_f32(p) for p in points if p.shape[0]], axis=0, out=hp)
                 if targets is not None:
                     ht = view[o_tgt:o_tgt + 4 * self.total_points].view(np.float32)
-                    np.concatenate([t.detach().to(torch.float32).numpy() for t in targets if t.shape[0]], out=ht)
+                    np.concatenate([_host_f32(t) for t in targets if t.shape[0]], out=ht)
             dev_buf = host[:total].to(device, non_blocking=True)
             ring.sent(slot, device)
             self.meta = dev_buf[:meta.nbytes].view(torch.int32)

@@ -18,9 +18,7 @@
 //              MMA warp; after the k loop they are the epilogue (tcgen05.ld -> global partial tile)
 // Pipeline: full[s] (TMA -> converters), ready[s] (converters -> MMA), empty[s] (MMA -> TMA) over
 // STAGES shared-memory stages; accum (MMA -> epilogue).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/dgvcc_b200.h"
 
 namespace dgvcc {
@@ -37,85 +35,13 @@ constexpr int CONVERTER_WARPS = 4;
 constexpr int TMEM_COLS = 256;  // two fp32 accumulators: hi*hi^T, and the small cross terms
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace dgvcc::tc;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO = 1 (unused for swizzled
-// K-major), descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
+// K-major operand tiles: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO is unused (=16 B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) { return umma_desc_sw128(smem_addr, 16, 1024); }
 
 // kind::tf32, fp32 accumulate, A and B K-major, M = N = 128.
-constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ |
-                           ((uint32_t)(TILE_M >> 3) << 17) /*N*/ | ((uint32_t)(TILE_M >> 4) << 24) /*M*/;
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(a), "l"(b), "r"(IDESC), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ float tf32_round(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
+constexpr uint32_t IDESC = umma_idesc_tf32(TILE_M, TILE_M, false);
 
 struct Args {
     int c, hw, splits, k_per_split, tiles_1d, n_tiles;
@@ -195,9 +121,9 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
 #pragma unroll
                 for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);  // +32 B inside the swizzle row
-                    umma_tf32(tmem_d, a_hi + adv, b_hi + adv, (kb | ks) != 0);
-                    umma_tf32(tmem_d + TILE_M, a_hi + adv, b_lo + adv, (kb | ks) != 0);
-                    umma_tf32(tmem_d + TILE_M, a_lo + adv, b_hi + adv, 1u);
+                    umma_tf32(tmem_d, a_hi + adv, b_hi + adv, IDESC, (kb | ks) != 0);
+                    umma_tf32(tmem_d + TILE_M, a_hi + adv, b_lo + adv, IDESC, (kb | ks) != 0);
+                    umma_tf32(tmem_d + TILE_M, a_lo + adv, b_hi + adv, IDESC, 1u);
                 }
                 umma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
             }
@@ -276,28 +202,8 @@ extern "C" int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int 
     // tensor map, so any C works, but tiny channel counts waste the 128-wide tile
     if (hw % 4 != 0 || c < 32 || k_per_split % BLOCK_K != 0 || ((uintptr_t)x & 15u)) return DGVCC_ERR_UNSUPPORTED;
 
-    // cuTensorMapEncodeTiled is fetched through the runtime so that the library does not link libcuda
-    // (it must load on machines without a driver: the host-only checks of tests/test_abi.py)
-    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeTiled encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        DGVCC_RETURN_IF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (q != cudaDriverEntryPointSuccess || !fn) return DGVCC_ERR_UNSUPPORTED;
-        encode = (EncodeTiled)fn;
-    }
     CUtensorMap tmap;
-    const cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)c, (cuuint64_t)batch};
-    const cuuint64_t strides[2] = {(cuuint64_t)hw * 4, (cuuint64_t)c * hw * 4};
-    const cuuint32_t box[3] = {BLOCK_K, TILE_M, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return DGVCC_ERR_UNSUPPORTED;
+    if (!make_tmap_f32_3d(&tmap, x, (uint64_t)hw, (uint64_t)c, (uint64_t)batch, TILE_M)) return DGVCC_ERR_UNSUPPORTED;
 
     static bool attr_set = false;  // idempotent; a race only repeats the same call
     if (!attr_set) {

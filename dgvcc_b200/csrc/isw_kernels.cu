@@ -10,7 +10,8 @@
 //   isw_loss_kernel             : sum |f_cor*mask| - margin, /num_remove_cov, clamp, mean over B
 //                                                                                 instance_whitening.py:19-27
 //   isw_loss_grad_kernel        : S_b = dL/df_cor_b symmetrised / (HW-1)          autograd of :19-39
-//   isw_sx_simt_kernel          : dX_b = S_b X_b  (exact fp32)                    autograd of :37
+//   isw_sx_simt_kernel          : dX_b = S_b X_b  (exact fp32; the tensor-core version is isw_sx_tc.cu)
+//                                                                                 autograd of :37
 // Deterministic: no float atomics; split-K partials are added in split order.
 #include "common.cuh"
 #include "../../include/dgvcc_b200.h"
@@ -397,9 +398,24 @@ extern "C" int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, con
     return (int)cudaGetLastError();
 }
 
+// implemented in isw_sx_tc.cu; returns DGVCC_ERR_UNSUPPORTED for shapes it does not tile
+extern "C" int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c, int hw, float* dx, void* stream);
+
+// dX = S X on the tensor cores where the shape tiles, else exact fp32 on CUDA cores
+static int launch_sx(const float* s, const float* x, int batch, int c, int hw, int use_tensor_cores, float* dx,
+                     cudaStream_t st) {
+    if (use_tensor_cores) {
+        const int rc = dgvcc_isw_sx_tc(s, x, batch, c, hw, dx, (void*)st);
+        if (rc != DGVCC_ERR_UNSUPPORTED) return rc;
+    }
+    isw_sx_simt_kernel<<<dim3(ceil_div(hw, GT), ceil_div(c, GT), batch), GEMM_THREADS, 0, st>>>(s, x, c, hw, dx);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float* mask,
                                        const float* num_remove_cov, const float* grad_loss, int batch, int c, int hw,
-                                       void* workspace, size_t workspace_bytes, float* grad_f_map, void* stream) {
+                                       int use_tensor_cores, void* workspace, size_t workspace_bytes,
+                                       float* grad_f_map, void* stream) {
     if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -407,18 +423,17 @@ extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, c
     isw_loss_grad_kernel<<<dim3(ceil_div(c * c, 256), batch), 256, 0, st>>>(f_cor, mask, w.off, num_remove_cov, grad_loss,
                                                                             c, hw, batch, w.s);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    isw_sx_simt_kernel<<<dim3(ceil_div(hw, GT), ceil_div(c, GT), batch), GEMM_THREADS, 0, st>>>(w.s, f_map, c, hw, grad_f_map);
-    return (int)cudaGetLastError();
+    return launch_sx(w.s, f_map, batch, c, hw, use_tensor_cores, grad_f_map, st);
 }
 
 extern "C" int dgvcc_isw_covariance_backward(const float* f_map, const float* grad_f_cor, int batch, int c, int hw,
-                                             void* workspace, size_t workspace_bytes, float* grad_f_map, void* stream) {
+                                             int use_tensor_cores, void* workspace, size_t workspace_bytes,
+                                             float* grad_f_map, void* stream) {
     if (!f_map || !grad_f_cor || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
     isw_cov_grad_kernel<<<dim3(ceil_div(c * c, 256), batch), 256, 0, st>>>(grad_f_cor, c, hw, w.s);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    isw_sx_simt_kernel<<<dim3(ceil_div(hw, GT), ceil_div(c, GT), batch), GEMM_THREADS, 0, st>>>(w.s, f_map, c, hw, grad_f_map);
-    return (int)cudaGetLastError();
+    return launch_sx(w.s, f_map, batch, c, hw, use_tensor_cores, grad_f_map, st);
 }

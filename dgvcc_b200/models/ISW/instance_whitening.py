@@ -106,8 +106,8 @@ class _Covariance(torch.autograd.Function):
         g = d_fcor.detach().to(torch.float32).contiguous()
         dx = torch.empty_like(x)
         _native.check(_native.lib().dgvcc_isw_covariance_backward(
-            _native.ptr(x), _native.ptr(g), b, c, hw, _native.ptr(ws), n, _native.ptr(dx), _native.stream_ptr(dev)),
-            "dgvcc_isw_covariance_backward")
+            _native.ptr(x), _native.ptr(g), b, c, hw, _use_tc(), _native.ptr(ws), n, _native.ptr(dx),
+            _native.stream_ptr(dev)), "dgvcc_isw_covariance_backward")
         shape, dtype = ctx.meta
         return dx.view(shape).to(dtype), None
 
@@ -145,7 +145,7 @@ class _WhiteningLoss(torch.autograd.Function):
         g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         dx = torch.empty_like(x)
         _native.check(_native.lib().dgvcc_isw_loss_backward(
-            _native.ptr(x), _native.ptr(f_cor), _native.ptr(mask), _native.ptr(nr), _native.ptr(g), b, c, hw,
+            _native.ptr(x), _native.ptr(f_cor), _native.ptr(mask), _native.ptr(nr), _native.ptr(g), b, c, hw, _use_tc(),
             _native.ptr(ws), n, _native.ptr(dx), _native.stream_ptr(dev)), "dgvcc_isw_loss_backward")
         return dx.view(shape).to(dtype), None, None, None, None
 

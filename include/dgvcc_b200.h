@@ -179,7 +179,8 @@ int dgvcc_isw_covariance(const float* f_map, const float* eye, int batch, int c,
                          void* workspace, size_t workspace_bytes, float* f_cor, void* stream);
 /* grad_f_map = (dF + dF^T) X / (hw-1) for an upstream gradient dF of f_cor. */
 int dgvcc_isw_covariance_backward(const float* f_map, const float* grad_f_cor, int batch, int c, int hw,
-                                  void* workspace, size_t workspace_bytes, float* grad_f_map, void* stream);
+                                  int use_tensor_cores, void* workspace, size_t workspace_bytes, float* grad_f_map,
+                                  void* stream);
 
 /* loss[0] = sum_b clamp((sum |f_cor_b * mask| - margin) / num_remove_cov, min=0) / batch
  * (instance_whitening.py:21-25).  margin / num_remove_cov are 1-element DEVICE arrays
@@ -189,13 +190,15 @@ int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, const float* m
                            void* stream);
 /* grad_f_map for grad_loss[0]; re-uses the workspace written by dgvcc_isw_loss_forward. */
 int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float* mask, const float* num_remove_cov,
-                            const float* grad_loss, int batch, int c, int hw, void* workspace,
+                            const float* grad_loss, int batch, int c, int hw, int use_tensor_cores, void* workspace,
                             size_t workspace_bytes, float* grad_f_map, void* stream);
 
 /* The tensor-core Gram on its own (split-K partial tiles, tests / profiling):
  * part [batch][splits][upper-triangular 128x128 tiles][128][128]. */
 int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int hw, int splits, int k_per_split,
                                float* part, void* stream);
+/* The tensor-core backward GEMM on its own: dx [batch,c,hw] = s [batch,c,c] @ x [batch,c,hw] (3xTF32). */
+int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c, int hw, float* dx, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Throughput probes used by bench.py for the roofline denominators that

@@ -138,3 +138,23 @@ def test_tensor_core_gram_partials_directly(shape):
             err = (got - want).abs().max().item()
             assert err <= 1e-5 * want.abs().max().item(), f"tile ({ti},{tj}) max err {err}"
             t += 1
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 1600), (2, 128, 644), (2, 256, 6400), (1, 512, 1600), (1, 192, 260)])
+def test_tensor_core_backward_gemm_directly(shape):
+    """dgvcc_isw_sx_tc (dX = S X, MN-major B operand) must take these shapes and match an fp64 product."""
+    from dgvcc_b200 import _native
+    b, c, hw = shape
+    g = torch.Generator().manual_seed(23 + c)
+    x = torch.randn((b, c, hw), generator=g)
+    s = torch.randn((b, c, c), generator=g) * 0.01
+    s = s + s.transpose(1, 2)
+    xd, sd = x.to(DEV).contiguous(), s.to(DEV).contiguous()
+    dx = torch.full((b, c, hw), float("nan"), device=DEV)
+    rc = _native.lib().dgvcc_isw_sx_tc(_native.ptr(sd), _native.ptr(xd), b, c, hw, _native.ptr(dx),
+                                       _native.stream_ptr(torch.device(DEV)))
+    assert rc == 0, f"tensor-core backward refused shape {shape}: rc={rc}"
+    torch.cuda.synchronize()
+    ref = torch.bmm(s.double(), x.double())
+    err = (dx.cpu().double() - ref).abs().max().item()
+    assert err <= 1e-5 * ref.abs().max().item(), f"max err {err} vs max |ref| {ref.abs().max().item()}"

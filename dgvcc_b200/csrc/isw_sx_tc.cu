@@ -2,9 +2,11 @@
 //
 // Autograd of models/ISW/instance_whitening.py:37: S_b [C,C] is the symmetrised upstream gradient of the
 // covariance (already divided by HW-1), X_b [C,HW] the whitened map.  M = C rows of dX, N = HW columns,
-// K = C.  A = S is K-major (k contiguous); B = X is MN-major (n contiguous), staged as four 32(n) x 32(k)
-// TMA boxes per k block so that shared memory holds the canonical MN-major 128-byte-swizzle layout
-// (32-float n segments LBO = 4 KB apart, 8-row k groups SBO = 1 KB apart).
+// K = C.  A = S is K-major (k contiguous); B = X is MN-major (n contiguous).  The tensor core accepts
+// MN-major TF32 operands only in the SWIZZLE_128B_BASE32B layout (atoms of 4 k-rows x 128 bytes whose
+// 32-byte chunks are XOR-ed with the row index), which TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// X is staged as four 32(n) x 32(k) boxes per k block: 32-float n segments LBO = 4 KB apart, 4-row k
+// groups SBO = 512 B apart.
 // fp32 accuracy as in the Gram: 3xTF32, A and B both split into hi + lo, cross terms in their own TMEM
 // accumulator.  The accumulation chain is only C/8 steps, so no split-K is needed.
 // One CTA = one 128 x 128 tile of dX of one sample; warp roles as in isw_gram_tc.cu.
@@ -102,8 +104,8 @@ isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constan
                     // A (K-major): +32 B inside the swizzle row per k step; B (MN-major): next 8-row k group
                     const uint64_t a_hi = umma_desc_sw128(stage + ks * UMMA_K * 4, 16, 1024);
                     const uint64_t a_lo = umma_desc_sw128(stage + 2 * TILE_BYTES + ks * UMMA_K * 4, 16, 1024);
-                    const uint64_t b_hi = umma_desc_sw128(stage + TILE_BYTES + ks * 1024, B_BOX_BYTES, 1024);
-                    const uint64_t b_lo = umma_desc_sw128(stage + 3 * TILE_BYTES + ks * 1024, B_BOX_BYTES, 1024);
+                    const uint64_t b_hi = umma_desc(stage + TILE_BYTES + ks * 1024, B_BOX_BYTES, 512, 1);
+                    const uint64_t b_lo = umma_desc(stage + 3 * TILE_BYTES + ks * 1024, B_BOX_BYTES, 512, 1);
                     umma_tf32(tmem_d, a_hi, b_hi, IDESC, (kb | ks) != 0);
                     umma_tf32(tmem_d + TILE, a_hi, b_lo, IDESC, (kb | ks) != 0);
                     umma_tf32(tmem_d + TILE, a_lo, b_hi, IDESC, 1u);
@@ -186,7 +188,8 @@ extern "C" int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c,
         return DGVCC_ERR_UNSUPPORTED;
     CUtensorMap map_s, map_x;
     if (!make_tmap_f32_3d(&map_s, s, (uint64_t)c, (uint64_t)c, (uint64_t)batch, TILE)) return DGVCC_ERR_UNSUPPORTED;
-    if (!make_tmap_f32_3d(&map_x, x, (uint64_t)hw, (uint64_t)c, (uint64_t)batch, BLOCK_K)) return DGVCC_ERR_UNSUPPORTED;
+    if (!make_tmap_f32_3d(&map_x, x, (uint64_t)hw, (uint64_t)c, (uint64_t)batch, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return DGVCC_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
         DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_sx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

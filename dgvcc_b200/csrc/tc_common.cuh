@@ -74,15 +74,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 
-// Shared-memory matrix descriptor, 128-byte swizzle, Blackwell version bits.  lbo / sbo in bytes.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor, Blackwell version bits.  lbo / sbo in bytes.
+// layout_type: 2 = SWIZZLE_128B (16-byte atoms); 1 = SWIZZLE_128B_BASE32B (32-byte atoms), the only
+// layout the tensor core accepts for MN-major TF32 operands.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
     d |= (uint64_t)(lbo_bytes >> 4) << 16;
     d |= (uint64_t)(sbo_bytes >> 4) << 32;
     d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return umma_desc(smem_addr, lbo_bytes, sbo_bytes, 2);
 }
 
 // Instruction descriptor for kind::tf32 with fp32 accumulation.  b_mn_major: B stored with N contiguous.
@@ -110,7 +116,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 // fp32 3-D tensor map {inner, rows, batch} with a {box_inner (= 32 floats, one 128-byte swizzle row), box_rows, 1} box.
 inline bool make_tmap_f32_3d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t batch,
-                             uint32_t box_rows) {
+                             uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
     const cuuint64_t dims[3] = {inner, rows, batch};
@@ -118,7 +124,7 @@ inline bool make_tmap_f32_3d(CUtensorMap* map, const float* base, uint64_t inner
     const cuuint32_t box[3] = {32, box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -31,6 +31,39 @@ if os.path.exists(launches):
             f.write(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / 1e3:.1f} | {100 * sum(v) / total:.1f} % |\n")
     print("wrote launches summary", len(data), "launches")
 
+WANT = None
+
+
+def summarize(rep, title, cmd, out_md, out_csv):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(out_md, "w") as f:
+        f.write(f"# {title}\n\n`{cmd}`\nDurations under ncu are cold-cache.\n\n")
+        names = [d[idx["Kernel Name"]].split("(")[0].replace("void ", "") for d in data]
+        f.write("| metric | " + " | ".join(f"`{n}`" for n in names) + " |\n|---|" + "---|" * len(names) + "\n")
+        for key, label in WANT:
+            if key not in idx:
+                continue
+            cells = []
+            for d in data:
+                v = d[idx[key]]
+                try:
+                    cells.append(f"{float(v.replace(',', '')):.4g} {units[idx[key]]}")
+                except ValueError:
+                    cells.append(v)
+            f.write(f"| {label} | " + " | ".join(cells) + " |\n")
+    with open(out_csv, "w") as f:
+        keep = [i for i, h in enumerate(hdr) if any(h.startswith(p) for p in (
+            "Kernel Name", "gpu__time", "launch__", "sm__", "smsp__issue", "smsp__warps", "smsp__average_warps_issue_stalled",
+            "dram__bytes", "gpu__dram", "l1tex__data_bank", "lts__t_bytes", "smsp__inst_executed.sum"))]
+        w = csv.writer(f)
+        for r in [hdr, units] + data:
+            w.writerow([r[i] for i in keep])
+    print("wrote", out_md, len(data), "kernels")
+
+
 # ---- full capture of the BL kernels
 rep = os.path.join(ROOT, "gpurun_out", f"bl_{tag}.ncu-rep")
 if os.path.exists(rep):
@@ -61,6 +94,18 @@ if os.path.exists(rep):
         ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
         ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
     ]
+    want += [
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+        ("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "TC pipe inst %"),
+        ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe %"),
+        ("lts__t_bytes.sum", "L2 bytes"),
+    ]
+    WANT = want
+    aux = os.path.join(ROOT, "gpurun_out", f"aux_{tag}.ncu-rep")
+    if os.path.exists(aux):
+        summarize(aux, f"ncu --set full, ISW covariance (B=8, C=256, HW=6400) and adaptive density map (2048x2048, 25 000 heads) ({tag})",
+                  "ncu --set full --clock-control none --import-source on -k 'regex:isw_gram_tc|isw_cov_finish|dmap_' -s 5 -c 5 python scripts/profile_aux.py",
+                  os.path.join(out_dir, f"{tag}_aux_ncu_summary.md"), os.path.join(out_dir, f"{tag}_aux_ncu_raw.csv"))
     with open(os.path.join(out_dir, f"{tag}_bl_ncu_summary.md"), "w") as f:
         f.write(f"# ncu --set full, fused Bayesian loss, BASELINE config 3 ({tag})\n\n"
                 "`ncu --set full --clock-control none --import-source on -k regex:bl_ -s 7 -c 7 python scripts/profile_bl.py`\n"

@@ -26,6 +26,8 @@
 // (explicit _rn intrinsics), IEEE sqrt, IEEE division by 2*sigma^2 (exact scaling when it is
 // a power of two, otherwise a Markstein-corrected reciprocal multiply that is correctly
 // rounded).  Only exp (MUFU.EX2 of a rounded product) and summation order differ, ~1e-6.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/dgvcc_b200.h"
 
@@ -956,6 +958,11 @@ static long variant_tasks(const Variant& v, int total_chunks, int hp, int wp) {
 }
 
 static Variant pick_variant(int total_chunks, int hp, int wp) {
+    // tuning override for experiments (scripts/sweep_bl.sh): DGVCC_BL_VARIANT = index into kVariants
+    if (const char* e = getenv("DGVCC_BL_VARIANT")) {
+        const int i = atoi(e);
+        if (i >= 0 && i < 4) return kVariants[i];
+    }
     const long want = 148L * 16;
     for (const Variant& v : kVariants)
         if (variant_tasks(v, total_chunks, hp, wp) >= want) return v;

@@ -210,7 +210,7 @@ def kernel_breakdown(wl, dev, reps=5):
     from dgvcc_b200 import _native
     from dgvcc_b200.losses import bl as blmod
     lib = _native.lib()
-    packed = blmod._Packed([p.to(dev) for p in wl["points"]], USE_BG, dev, grid=(wl["hp"], wl["wp"]))
+    packed = blmod._Packed([p.to(dev) for p in wl["points"]], USE_BG, dev)
     targets = blmod._pack_targets([t.to(dev) for t in wl["targets"]], packed, dev)
     dens = wl["density"].to(dev).reshape(len(wl["counts"]), wl["hp"], wl["wp"]).contiguous()
     st = wl["st_sizes"].to(dev)

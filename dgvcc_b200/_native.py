@@ -27,7 +27,6 @@ class BLLayout(ctypes.Structure):
 SIGNATURES = {
     "dgvcc_abi_version": (c_int, []),
     "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
-    "dgvcc_bl_wave_slots": (c_int, [c_int, c_int, POINTER(c_int)]),
     "dgvcc_bl_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                  c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, c_void_p, c_size_t,
                                  c_void_p, c_void_p]),

@@ -352,7 +352,7 @@ bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ me
 // ------------------------------------------------------------------------------------------ K1
 // Softmax max (incl. the background row, bl.py:39-43) and this chunk's share of the denominator.
 template <int R, int C, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS, 4)
+__global__ void __launch_bounds__(CTA_THREADS)
 bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
             int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
@@ -474,7 +474,7 @@ __device__ __forceinline__ float softmax_rz(const float* __restrict__ zpart, siz
 
 // ------------------------------------------------------------------------------------------ K2
 template <int R, int C, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS, 4)
+__global__ void __launch_bounds__(CTA_THREADS)
 bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
                  const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg, int exact_cull,
                  const float* __restrict__ amax_in, const float* __restrict__ ebg_in,
@@ -737,7 +737,7 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
 // compacted away while staging.  Single-chunk images store the final gradient; otherwise the raw
 // chunk sum goes to gpart and bl_grad_reduce_kernel finishes.
 template <int R, int C, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS, 4)
+__global__ void __launch_bounds__(CTA_THREADS)
 bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
                Scale k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
@@ -1013,28 +1013,7 @@ static T* at(const void* ws, int64_t off) { return reinterpret_cast<T*>((char*)w
 using namespace dgvcc;
 using namespace dgvcc::bl;
 
-extern "C" int dgvcc_abi_version(void) { return 5; }
-
-// Resident CTAs of the exponential-sweep kernels on the current device (all three are compiled for the same
-// occupancy), so that the host can size the point chunks to fill whole waves.
-extern "C" int dgvcc_bl_wave_slots(int rows_per_thread, int cols_per_thread, int* slots_out) {
-    if (!slots_out) return DGVCC_ERR_ARG;
-    int dev = 0, sms = 0, per_sm = 0;
-    DGVCC_RETURN_IF_CUDA(cudaGetDevice(&dev));
-    DGVCC_RETURN_IF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    cudaError_t e;
-    if (rows_per_thread == 8 && cols_per_thread == 2)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bl_grad_kernel<8, 2, true>, CTA_THREADS, 0);
-    else if (rows_per_thread == 8)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bl_grad_kernel<8, 1, true>, CTA_THREADS, 0);
-    else if (rows_per_thread == 4)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bl_grad_kernel<4, 1, true>, CTA_THREADS, 0);
-    else
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bl_grad_kernel<2, 1, true>, CTA_THREADS, 0);
-    if (e != cudaSuccess) return (int)e;
-    *slots_out = sms * per_sm;
-    return DGVCC_OK;
-}
+extern "C" int dgvcc_abi_version(void) { return 4; }
 
 extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                                          dgvcc_bl_layout* out) {

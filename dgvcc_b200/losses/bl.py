@@ -19,7 +19,6 @@ Extensions that do not change reference behaviour:
     divisor of bl.py:79, so a rank holding B_local of B_global images returns
     its partial loss and ``dgvcc_b200.sharding`` all-reduces it.
 """
-import ctypes
 import os
 from math import ceil
 
@@ -42,46 +41,9 @@ def _as_point_list(points):
     return out
 
 
-NOMINAL_CHUNK = 1024
-_CHUNK_CANDIDATES = np.arange(448, 1537, 16, dtype=np.int64)
-_slots_cache = {}
-
-
-def _wave_slots(rows, cols, device):
-    key = (rows, cols, device)
-    if key not in _slots_cache:
-        out = ctypes.c_int(0)
-        with torch.cuda.device(device):
-            _native.check(_native.lib().dgvcc_bl_wave_slots(rows, cols, ctypes.byref(out)), "dgvcc_bl_wave_slots")
-        _slots_cache[key] = max(1, out.value)
-    return _slots_cache[key]
-
-
-def chunk_points(counts=None, grid=None, device=None):
-    """Points per chunk: big images are cut into near-equal slices of at most this many points.
-
-    Every (chunk, pixel tile) task costs the same, so the sweep kernels run in waves of equal-length CTAs;
-    a last wave that is 35 % full costs as much as a full one.  Among chunk sizes around the nominal 1024
-    the one whose CTA count best fills whole waves on this device is chosen (DGVCC_BL_CHUNK overrides)."""
-    env = os.environ.get("DGVCC_BL_CHUNK")
-    if env:
-        return int(env)
-    if counts is None or grid is None or device is None or device.type != "cuda":
-        return NOMINAL_CHUNK
-    hp, wp = grid
-    counts = np.asarray(counts, dtype=np.int64)
-    nominal_chunks = int(np.maximum(1, -(-counts // NOMINAL_CHUNK)).sum())
-    lay = _native.BLLayout()
-    _native.check(_native.lib().dgvcc_bl_workspace_layout(int(np.where(counts == 0, 1, counts + 1).sum()), nominal_chunks,
-                                                          len(counts), hp, wp, lay), "dgvcc_bl_workspace_layout")
-    ctas_per_chunk = -(-lay.tiles // 4)
-    slots = _wave_slots(lay.rows_per_thread, lay.cols_per_thread, device)
-    n_chunks = np.maximum(1, -(-counts[None, :] // _CHUNK_CANDIDATES[:, None])).sum(axis=1)
-    waves = n_chunks * ctas_per_chunk / slots
-    fill = waves / np.ceil(waves)
-    # prefer full waves; among near-equal fills the chunk closest to the nominal size
-    score = fill - 1e-3 * np.abs(_CHUNK_CANDIDATES - NOMINAL_CHUNK) / NOMINAL_CHUNK
-    return int(_CHUNK_CANDIDATES[int(np.argmax(score))])
+def chunk_points():
+    """Points per chunk: big images are cut into near-equal slices of at most this many points."""
+    return int(os.environ.get("DGVCC_BL_CHUNK", "1024"))
 
 
 def build_meta(counts, rows, chunk):
@@ -156,7 +118,7 @@ class _Packed:
     the device like bl.py:21-22.
     """
 
-    def __init__(self, points, use_bg, device, targets=None, grid=None):
+    def __init__(self, points, use_bg, device, targets=None):
         points = _as_point_list(points)
         self.batch = len(points)
         if self.batch == 0:
@@ -168,8 +130,7 @@ class _Packed:
         self.total_points = int(counts.sum())
         self.total_rows = int(rows.sum())
         b = self.batch
-        self.chunk = chunk_points(counts, grid, device)
-        meta, self.total_chunks, self.multi_chunk = build_meta(counts, rows, self.chunk)
+        meta, self.total_chunks, self.multi_chunk = build_meta(counts, rows, chunk_points())
         self.pt_off = meta[:b + 1].copy()
         self.row_off = meta[b + 1:2 * b + 2].copy()
         self.targets = None
@@ -410,7 +371,7 @@ class BL(Module):
         _native.require_cuda(pre_density, "BL.forward")
         if len(points) != pre_density.shape[0]:
             raise ValueError(f"{len(points)} point sets for a batch of {pre_density.shape[0]} density maps")
-        packed = _Packed(points, pp.use_bg, dev, targets=target_list, grid=tuple(pre_density.shape[-2:]))
+        packed = _Packed(points, pp.use_bg, dev, targets=target_list)
         targets = packed.targets
         st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()
         inv_batch = 1.0 / float(self.global_batch or packed.batch)

@@ -83,10 +83,6 @@ typedef struct dgvcc_bl_layout {
 int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                               dgvcc_bl_layout* out);
 
-/* Resident CTAs (whole device) of the sweep kernels for a kernel variant, so the host can cut the point
- * chunks such that the grid fills whole waves (needs a current CUDA device). */
-int dgvcc_bl_wave_slots(int rows_per_thread, int cols_per_thread, int* slots_out);
-
 /* Fused forward: per-pixel min / softmax denominator, expected counts, trimmed
  * top-k selection and the loss.  Never materialises the points x pixels matrix.
  * loss_out[0] = inv_batch * sum_i L_i. */

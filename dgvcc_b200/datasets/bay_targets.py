@@ -1,0 +1,61 @@
+"""Target preparation of the reference's ``BayesianDataset`` on B200.
+
+    cal_dists(pts)                         <- BayesianDataset._cal_dists          (datasets/bay_dataset.py:38-48)
+    crop_targets(gt, dists, i, j, h, w)    <- crop block of _train_transform      (datasets/bay_dataset.py:85-107)
+
+Host numpy in / host numpy out with the reference's shapes and dtypes, so ``BayesianDataset`` can call them
+in place of its numpy code; the O(N^2) neighbour search never builds the N x N matrix.
+"""
+import numpy as np
+import torch
+
+from .. import _native
+
+
+def _dev(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("dgvcc_b200.datasets.bay_targets needs a CUDA device; there is no CPU path")
+    return torch.device(device if device is not None else "cuda")
+
+
+def _as_xy(a):
+    a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return np.ascontiguousarray(a)
+
+
+def cal_dists(pts, device=None):
+    """[N,1] mean distance to the 3 nearest heads (dtype of ``pts``); the reference's constants for N < 2."""
+    if len(pts) == 0:
+        return np.array([[]])
+    if len(pts) == 1:
+        return np.array([[4.0]])
+    dev = _dev(device)
+    p = _as_xy(pts)
+    n = len(p)
+    d_pts = torch.from_numpy(p).pin_memory().to(dev, non_blocking=True)
+    out = torch.empty((n, 1), dtype=d_pts.dtype, device=dev)
+    _native.check(_native.lib().dgvcc_bay_knn_mean(_native.ptr(d_pts), n, int(p.dtype == np.float64), _native.ptr(out),
+                                                   _native.stream_ptr(dev)), "dgvcc_bay_knn_mean")
+    return out.cpu().numpy()
+
+
+def crop_targets(gt, dists, i, j, h, w, device=None):
+    """(gt_kept [K,2] float64 in crop coordinates, mirrored in x; targ [K]) for the crop window rows i..i+h, cols j..j+w."""
+    if len(gt) == 0:
+        return gt, np.array([])
+    dev = _dev(device)
+    g = _as_xy(gt)
+    d = np.ascontiguousarray(np.asarray(dists).reshape(-1), dtype=g.dtype)
+    n = len(g)
+    d_gt = torch.from_numpy(g).pin_memory().to(dev, non_blocking=True)
+    d_d = torch.from_numpy(d).pin_memory().to(dev, non_blocking=True)
+    gt_out = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    targ = torch.empty((n,), dtype=d_gt.dtype, device=dev)
+    kept = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _native.check(_native.lib().dgvcc_bay_crop_targets(
+        _native.ptr(d_gt), _native.ptr(d_d), n, int(g.dtype == np.float64), float(j), float(i), float(j + w), float(i + h),
+        _native.ptr(gt_out), _native.ptr(targ), _native.ptr(kept), _native.stream_ptr(dev)), "dgvcc_bay_crop_targets")
+    k = int(kept.cpu())
+    return gt_out[:k].cpu().numpy(), targ[:k].cpu().numpy()

@@ -201,6 +201,23 @@ int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int hw, int spl
 int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c, int hw, float* dx, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Bayesian-dataset target preparation (the step before BL) -- replaces
+ * datasets/bay_dataset.py:38-48 (BayesianDataset._cal_dists) and :85-107 (crop block of
+ * _train_transform, with utils/misc.py:39-45 cal_inner_area).  is_double selects numpy's dtype
+ * rules: 1 for float64 annotations, 0 for float32 ones.
+ * ------------------------------------------------------------------------- */
+
+/* dists [n] = mean distance to the 3 nearest heads via sqrt(max(sq_i - 2 p_i.p_j + sq_j, 0)); for
+ * n in {2,3} the reference's mean over columns 1.. of the unsorted row.  n < 2 is a no-op (constants). */
+int dgvcc_bay_knn_mean(const void* pts_xy, int n, int is_double, void* dists, void* stream);
+
+/* Kept heads (overlap ratio of the clipped box with the crop >= 0.3) in index order:
+ * gt_out [kept,2] f64 = (w - (x - left), y - up), targ_out [kept] = ratio, *kept_out = count. */
+int dgvcc_bay_crop_targets(const void* gt_xy, const void* dists, int n, int is_double, double crop_left,
+                           double crop_up, double crop_right, double crop_down, double* gt_out, void* targ_out,
+                           int* kept_out, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Throughput probes used by bench.py for the roofline denominators that
  * MEASURED_PEAKS.json does not carry: chip-wide
  * MUFU.EX2 and FFMA issue rates.  Each launches `iters` dependent-chain rounds

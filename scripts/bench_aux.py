@@ -88,7 +88,8 @@ def bench_dmap(cpu):
         }
         if cpu:
             from oracle import dmap_oracle
-            small = sorted(images, key=lambda im: len(im[1]))[2:5]  # three small non-trivial images
+            cand = sorted([im for im in images if 15 <= len(im[1]) <= 400], key=lambda im: len(im[1]) * im[0][0] * im[0][1])
+            small = cand[:2]  # the two cheapest images with a non-trivial crowd (cost ~ heads x pixels)
             t0 = time.perf_counter()
             heads = 0
             for (h, w), pts in small:
@@ -97,7 +98,7 @@ def bench_dmap(cpu):
             dt = time.perf_counter() - t0
             total_heads = sum(len(p) for _, p in images)
             line["cpu_baseline"] = {"value": 64 / (dt / max(heads, 1) * total_heads), "unit": "density maps/s", "cores": 1,
-                                    "kind": "port", "sample": f"reference algorithm (scipy gaussian_filter per head) on 3 small images, "
+                                    "kind": "port", "sample": f"reference algorithm (scipy gaussian_filter per head) on {len(small)} small images, "
                                     f"{heads} heads in {dt:.1f} s; extrapolated per head to the {total_heads} heads of the set"}
         print(json.dumps(line), flush=True)
 

@@ -160,8 +160,73 @@ def make_isw():
     np.savez_compressed(os.path.join(HERE, "isw_cases.npz"), **out)
 
 
+# -------------------------------------------------------------------------- bay
+def make_bay():
+    """BayesianDataset._cal_dists and the crop block of _train_transform, run on the unmodified class."""
+    import importlib
+    import random
+    import types
+    from PIL import Image
+    pkg = types.ModuleType("datasets")        # the HuggingFace `datasets` package shadows the reference's
+    pkg.__path__ = [os.path.join(REF, "datasets")]
+    saved = sys.modules.get("datasets")
+    sys.modules["datasets"] = pkg
+    sys.path.insert(0, REF)
+    try:
+        bd = importlib.import_module("datasets.bay_dataset")
+    finally:
+        sys.path.remove(REF)
+    out = {}
+    rng = np.random.default_rng(8000)
+    for name, n, dtype in (("n0", 0, np.float64), ("n1", 1, np.float64), ("n2", 2, np.float64), ("n3", 3, np.float64),
+                           ("n4", 4, np.float64), ("n300", 300, np.float64), ("n200f32", 200, np.float32)):
+        pts = synthetic.crowd_points(rng, n, 900, 700, dtype=dtype)
+        out[f"dist_{name}_pts"] = pts
+        out[f"dist_{name}_ref"] = bd.BayesianDataset._cal_dists(None, pts)
+    # _train_transform on a fake instance: record the random crop and resize so the crop block can be replayed
+    rec = {}
+    real_crop = bd.random_crop
+    def recording_crop(im_h, im_w, ch, cw):
+        rec["ij"] = real_crop(im_h, im_w, ch, cw)
+        return rec["ij"]
+    bd.random_crop = recording_crop
+    ds = bd.BayesianDataset.__new__(bd.BayesianDataset)
+    ds.pre_resize, ds.crop_size, ds.transform = 1, (256, 256), (lambda im: torch.zeros(1))
+    for k, (w, h, n, dtype, seed) in enumerate([(640, 480, 150, np.float64, 1), (300, 220, 60, np.float64, 2),
+                                                (700, 500, 400, np.float32, 3), (500, 400, 0, np.float64, 4)]):
+        gt = synthetic.crowd_points(np.random.default_rng(8100 + k), n, w, h, dtype=dtype)
+        dists = bd.BayesianDataset._cal_dists(None, gt)
+        random.seed(seed)
+        state = random.getstate()
+        img = Image.fromarray(np.zeros((h, w, 3), dtype=np.uint8))
+        _, gt_out, targ, st_size = ds._train_transform(img, gt.copy(), dists)
+        # replay the draws to recover the geometry the crop block saw
+        random.setstate(state)
+        random.random()                                   # grey-scale draw
+        factor = 1 * random.random() * 0.8 + 0.6
+        nw, nh = int(w * factor), int(h * factor)
+        g = gt.copy()
+        cw, chh = w, h
+        if min(nw, nh) >= 256:
+            cw, chh = nw, nh
+            g = g * factor
+        if min(cw, chh) < 256:
+            from utils.misc import get_padding
+            (left, top, _, _), chh, cw = get_padding(chh, cw, 256, 256)
+            if len(g) > 0:
+                g = g + [left, top]
+        i, j = rec["ij"]
+        out[f"crop_{k}_gt"], out[f"crop_{k}_dists"] = g, dists
+        out[f"crop_{k}_ijhw"] = np.asarray([i, j, 256, 256])
+        out[f"crop_{k}_ref_gt"], out[f"crop_{k}_ref_targ"] = gt_out.numpy(), targ.numpy()
+        print("bay crop", k, "kept", len(targ), "of", n)
+    if saved is not None:
+        sys.modules["datasets"] = saved
+    np.savez_compressed(os.path.join(HERE, "bay_cases.npz"), **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["bl", "dmap", "isw"]
+    what = sys.argv[1:] or ["bl", "dmap", "isw", "bay"]
     torch.manual_seed(0)
     for w in what:
         globals()[f"make_{w}"]()

@@ -232,6 +232,25 @@ isw_cov_grad_kernel(const float* __restrict__ d_fcor, int c, int hw, float* __re
     s_out[(size_t)b * c * c + e] = (d[(size_t)i * c + j] + d[(size_t)j * c + i]) / (float)(hw - 1);
 }
 
+// cal_covstat (models/ISW/__init__.py:93-104): var over the batch (unbiased, torch.var default) of the
+// masked covariance f_cor * reverse_eye -- the statistic CovMatrix_ISW accumulates to pick its mask.
+__global__ void __launch_bounds__(256)
+isw_covstat_var_kernel(const float* __restrict__ f_cor, const float* __restrict__ reverse_eye, int batch, int cc,
+                       float* __restrict__ var_out) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= cc) return;
+    const float m = reverse_eye[e];
+    float mean = 0.f;
+    for (int b = 0; b < batch; ++b) mean += f_cor[(size_t)b * cc + e] * m;
+    mean /= (float)batch;
+    float ss = 0.f;
+    for (int b = 0; b < batch; ++b) {
+        const float d = f_cor[(size_t)b * cc + e] * m - mean;
+        ss = fmaf(d, d, ss);
+    }
+    var_out[e] = ss / (float)(batch - 1);  // batch == 1 -> 0/0 = nan, like torch.var
+}
+
 // ------------------------------------------------------------------------------- dX = S X (SIMT)
 __global__ void __launch_bounds__(GEMM_THREADS)
 isw_sx_simt_kernel(const float* __restrict__ s, const float* __restrict__ x, int c, int hw, float* __restrict__ dx) {
@@ -436,4 +455,11 @@ extern "C" int dgvcc_isw_covariance_backward(const float* f_map, const float* gr
     isw_cov_grad_kernel<<<dim3(ceil_div(c * c, 256), batch), 256, 0, st>>>(grad_f_cor, c, hw, w.s);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     return launch_sx(w.s, f_map, batch, c, hw, use_tensor_cores, grad_f_map, st);
+}
+
+extern "C" int dgvcc_isw_covstat_var(const float* f_cor, const float* reverse_eye, int batch, int c, float* var_out,
+                                     void* stream) {
+    if (!f_cor || !reverse_eye || !var_out || batch <= 0 || c <= 0) return DGVCC_ERR_ARG;
+    isw_covstat_var_kernel<<<ceil_div(c * c, 256), 256, 0, (cudaStream_t)stream>>>(f_cor, reverse_eye, batch, c * c, var_out);
+    return (int)cudaGetLastError();
 }

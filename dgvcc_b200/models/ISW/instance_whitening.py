@@ -159,3 +159,17 @@ def get_covariance_matrix(f_map, eye=None):
     if eye is None:
         eye = torch.eye(C, device=f_map.device)
     return _Covariance.apply(f_map, eye), B
+
+
+def variance_of_covariance(f_map, eye, reverse_eye):
+    """The statistic of ``cal_covstat`` (models/ISW/__init__.py:93-104): ``torch.var(f_cor * reverse_eye, dim=0)``
+    with ``f_cor`` the covariance of the (image, augmented image) pair; feed it to
+    ``CovMatrix_ISW.set_variance_of_covariance``.  No gradient (the reference calls it under ``no_grad``)."""
+    with torch.no_grad():
+        f_cor, b = get_covariance_matrix(f_map, eye=eye)
+        c = f_cor.shape[-1]
+        rev = reverse_eye.detach().to(device=f_cor.device, dtype=torch.float32).contiguous()
+        out = torch.empty((c, c), dtype=torch.float32, device=f_cor.device)
+        _native.check(_native.lib().dgvcc_isw_covstat_var(_native.ptr(f_cor), _native.ptr(rev), b, c, _native.ptr(out),
+                                                          _native.stream_ptr(f_cor.device)), "dgvcc_isw_covstat_var")
+    return out

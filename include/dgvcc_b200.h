@@ -193,6 +193,11 @@ int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float*
                             const float* grad_loss, int batch, int c, int hw, int use_tensor_cores, void* workspace,
                             size_t workspace_bytes, float* grad_f_map, void* stream);
 
+/* cal_covstat (models/ISW/__init__.py:93-104): var_out [c,c] = unbiased variance over the
+ * batch of f_cor * reverse_eye. */
+int dgvcc_isw_covstat_var(const float* f_cor, const float* reverse_eye, int batch, int c, float* var_out,
+                          void* stream);
+
 /* The tensor-core Gram on its own (split-K partial tiles, tests / profiling):
  * part [batch][splits][upper-triangular 128x128 tiles][128][128]. */
 int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int hw, int splits, int k_per_split,

@@ -32,3 +32,11 @@ def upper_mask(c, keep_fraction, seed):
     g = torch.Generator().manual_seed(seed)
     tri = torch.triu(torch.ones(c, c), diagonal=1)
     return tri * (torch.rand(c, c, generator=g) < keep_fraction).float()
+
+
+def covstat_variance(f_map, eye, reverse_eye):
+    """cal_covstat, models/ISW/__init__.py:93-104: var over the batch of the masked covariance.
+    (The enclosing reference module cannot be imported here -- it needs kmeans1d -- so this restatement is
+    pinned only to the same torch ops, not to a reference-executed fixture.)"""
+    f_cor, _ = covariance(f_map, eye)
+    return torch.var(f_cor * reverse_eye, dim=0)

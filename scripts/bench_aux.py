@@ -166,6 +166,41 @@ def bench_isw(cpu):
         print(json.dumps(line), flush=True)
 
 
+def bench_bay(cpu):
+    """Row f1: BayesianDataset._cal_dists + crop targets for one QNRF-size annotation set."""
+    from dgvcc_b200.datasets import bay_targets
+    lib = _native.lib()
+    n = 12000
+    pts = synthetic.crowd_points(np.random.default_rng(8212), n, 2048, 1536, dtype=np.float64)
+    d_pts = torch.from_numpy(pts).to(dev)
+    out = torch.empty((n, 1), dtype=torch.float64, device=dev)
+    ts = []
+    for rep in range(6):
+        e0, e1 = ev(), ev()
+        e0.record()
+        lib.dgvcc_bay_knn_mean(_native.ptr(d_pts), n, 1, _native.ptr(out), _native.stream_ptr(dev))
+        e1.record()
+        torch.cuda.synchronize()
+        if rep:
+            ts.append(e0.elapsed_time(e1))
+    t0 = time.perf_counter()
+    d = bay_targets.cal_dists(pts)
+    bay_targets.crop_targets(pts, d, 300, 500, 512, 512)
+    e2e = time.perf_counter() - t0
+    line = {"workload": f"SURVEY 8f rank 1: BayesianDataset._cal_dists + crop targets, {n} heads (float64)",
+            "metric": "annotation sets/s", "value_device_knn": 1e3 / min(ts), "ms_knn": min(ts),
+            "value_e2e_host_numpy": 1 / e2e, "pairs_per_s": n * n / (min(ts) * 1e-3)}
+    if cpu:
+        from oracle import bay_targets_oracle as bo
+        t0 = time.perf_counter()
+        dr = bo.cal_dists(pts)
+        bo.crop_targets(pts.copy(), dr, 300, 500, 512, 512)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1 / dt, "unit": "annotation sets/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "oracle port (numpy N x N matrix + partition), the same 12 000 heads, once"}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
@@ -175,3 +210,5 @@ if __name__ == "__main__":
         bench_dmap(a.cpu)
     if a.only in ("", "isw"):
         bench_isw(a.cpu)
+    if a.only in ("", "bay"):
+        bench_bay(a.cpu)

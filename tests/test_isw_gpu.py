@@ -158,3 +158,16 @@ def test_tensor_core_backward_gemm_directly(shape):
     ref = torch.bmm(s.double(), x.double())
     err = (dx.cpu().double() - ref).abs().max().item()
     assert err <= 1e-5 * ref.abs().max().item(), f"max err {err} vs max |ref| {ref.abs().max().item()}"
+
+
+@pytest.mark.parametrize("c,hw", [(64, 40 * 40), (256, 20 * 20)])
+def test_variance_of_covariance_covstat(c, hw):
+    """cal_covstat on an (image, augmented image) pair, models/ISW/__init__.py:93-104."""
+    from dgvcc_b200.models.ISW import variance_of_covariance
+    g = torch.Generator().manual_seed(c)
+    h = int(hw ** 0.5)
+    x = torch.randn((2, c, h, h), generator=g)
+    eye, rev = torch.eye(c), torch.ones(c, c).triu(diagonal=1)
+    ref = isw_oracle.covstat_variance(isw_oracle.instance_standardize(x), eye, rev)
+    got = variance_of_covariance(isw_oracle.instance_standardize(x).to(DEV), eye.to(DEV), rev.to(DEV))
+    assert_close(got.cpu(), ref, 1e-4, 1e-6 * amax(ref), "variance of covariance")  # a difference of two close covariances

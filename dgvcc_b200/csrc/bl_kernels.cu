@@ -76,6 +76,39 @@ __device__ __forceinline__ float pair_exp(float dis, float k2, const Scale& k) {
     return ex2_ftz(__fmaf_rn(neg_div<false>(dis, k), LOG2E, k2));
 }
 
+// Two fp32 values in one 64-bit register: Blackwell's packed add/mul/fma.f32x2 (SASS FADD2 / FMUL2 / FFMA2)
+// do the work of two scalar instructions in one issue slot; each lane is an ordinary IEEE round-to-nearest op.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Broadcast copies of the Scale constants for the packed path.
+struct Scale2 {
+    f2 k1, neg_s, r, neg_l;
+    __device__ __forceinline__ explicit Scale2(const Scale& k)
+        : k1(pack2(k.k1, k.k1)), neg_s(pack2(-k.s, -k.s)), r(pack2(k.r, k.r)), neg_l(pack2(-LOG2E, -LOG2E)) {}
+};
+
+// pair_exp for two pixels at once (same arithmetic per lane as the scalar version).
+template <bool POW2>
+__device__ __forceinline__ f2 pair_exp2(f2 dis, f2 k2, const Scale2& k) {
+    f2 t;
+    if (POW2) {
+        t = fma2(dis, k.k1, k2);
+    } else {
+        // dis / s correctly rounded (Markstein), then t = (-dis/s) * log2e + k2 in one fma
+        const f2 q = mul2(dis, k.r);
+        const f2 rem = fma2(q, k.neg_s, dis);
+        t = fma2(fma2(rem, k.r, q), k.neg_l, k2);
+    }
+    float t0, t1;
+    unpack2(t, t0, t1);
+    return pack2(ex2_ftz(t0), ex2_ftz(t1));
+}
+
 // ((-2 * fl(p*c)) + fl(p*p)) + fl(c*c)   bl.py:27-28;  cm2 = -2c (scaling by 2 commutes with rounding)
 __device__ __forceinline__ float axis_sqdist(float p, float pp, float cm2, float cc) {
     return __fadd_rn(__fadd_rn(__fmul_rn(p, cm2), pp), cc);
@@ -228,6 +261,20 @@ __device__ __forceinline__ void load_yd(const WarpTile<R>& tile, int i, float (&
         for (int q = 0; q < R / 4; ++q) {
             const float4 v = *reinterpret_cast<const float4*>(&tile.yd[i][4 * q]);
             yd[4 * q + 0] = v.x; yd[4 * q + 1] = v.y; yd[4 * q + 2] = v.z; yd[4 * q + 3] = v.w;
+        }
+    }
+}
+
+// The R y-distances of staged point i as R/2 packed pairs (rows 2q, 2q+1).
+template <int R>
+__device__ __forceinline__ void load_yd2(const WarpTile<R>& tile, int i, f2 (&yd)[R / 2]) {
+    if (R == 2) {
+        yd[0] = *reinterpret_cast<const f2*>(&tile.yd[i][0]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile.yd[i][4 * q]);
+            yd[2 * q] = v.x; yd[2 * q + 1] = v.y;
         }
     }
 }
@@ -430,6 +477,15 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
 #pragma unroll
         for (int c = 0; c < C; ++c) z[r][c] = 0.f;
     const ExpCull cull{exact_cull != 0, tile_max<R, C>(neg_amax), k.k1, px.box};
+    const Scale2 k2s(k);
+    f2 zp[R / 2][C], k2p[R / 2][C];
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            zp[q][c] = pack2(0.f, 0.f);
+            k2p[q][c] = pack2(neg_amax[2 * q][c], neg_amax[2 * q + 1][c]);
+        }
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
         int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
@@ -442,16 +498,21 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
 #pragma unroll 2
         for (int i = 0; i < cnt; ++i) {
             const float2 xs = tile.xs[i];
-            float yd[R];
-            load_yd<R>(tile, i, yd);
+            f2 yd[R / 2];
+            load_yd2<R>(tile, i, yd);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+                const f2 xd2 = pack2(xd, xd);
 #pragma unroll
-                for (int r = 0; r < R; ++r) z[r][c] += pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r][c], k);
+                for (int q = 0; q < R / 2; ++q) zp[q][c] = add2(zp[q][c], pair_exp2<POW2>(add2(yd[q], xd2), k2p[q][c], k2s));
             }
         }
     }
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) unpack2(zp[q][c], z[2 * q][c], z[2 * q + 1][c]);
     const bool first = t.chunk == t.first_chunk;
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -523,6 +584,15 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
     const float2* pts = pts_all + t.pt_base;
     part += t.p_start;
     const ExpCull cull{exact_cull != 0, tile_max<R, C>(neg_amax), k.k1, px.box};
+    const Scale2 k2s(k);
+    f2 k2p[R / 2][C], wdp[R / 2][C];
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            k2p[q][c] = pack2(neg_amax[2 * q][c], neg_amax[2 * q + 1][c]);
+            wdp[q][c] = pack2(wd[2 * q][c], wd[2 * q + 1][c]);
+        }
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, t.p_cnt - n0);
         int kept = cnt;
@@ -549,17 +619,20 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float2 xs = tile.xs[i0 + u];
-                float yd[R];
-                load_yd<R>(tile, i0 + u, yd);
-                float s = 0.f;
+                f2 yd[R / 2];
+                load_yd2<R>(tile, i0 + u, yd);
+                f2 s2 = pack2(0.f, 0.f);  // even / odd rows accumulate side by side
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+                    const f2 xd2 = pack2(xd, xd);
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        s = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r][c], k), wd[r][c], s);
+                    for (int q = 0; q < R / 2; ++q)
+                        s2 = fma2(pair_exp2<POW2>(add2(yd[q], xd2), k2p[q][c], k2s), wdp[q][c], s2);
                 }
-                v[u] = s;
+                float s_even, s_odd;
+                unpack2(s2, s_even, s_odd);
+                v[u] = s_even + s_odd;
             }
             // transpose-reduce: 8 per-lane partials -> lane quad q holds the warp total of point i0+q
 #pragma unroll
@@ -768,6 +841,15 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
     const float2* pts = pts_all + t.pt_base;
     const float* w_pts = wsel + t.row0 + t.p_start;
     const ExpCull cull{exact_cull != 0, tile_max<R, C>(neg_amax), k.k1, px.box};
+    const Scale2 k2s(k);
+    f2 accp[R / 2][C], k2p[R / 2][C];
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            accp[q][c] = pack2(0.f, 0.f);
+            k2p[q][c] = pack2(neg_amax[2 * q][c], neg_amax[2 * q + 1][c]);
+        }
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
@@ -778,18 +860,24 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
 #pragma unroll 2
         for (int i = 0; i < kept; ++i) {
             const float w = tile.aux[i];
+            const f2 w2 = pack2(w, w);
             const float2 xs = tile.xs[i];
-            float yd[R];
-            load_yd<R>(tile, i, yd);
+            f2 yd[R / 2];
+            load_yd2<R>(tile, i, yd);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+                const f2 xd2 = pack2(xd, xd);
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    acc[r][c] = fmaf(pair_exp<POW2>(__fadd_rn(yd[r], xd), neg_amax[r][c], k), w, acc[r][c]);
+                for (int q = 0; q < R / 2; ++q)
+                    accp[q][c] = fma2(pair_exp2<POW2>(add2(yd[q], xd2), k2p[q][c], k2s), w2, accp[q][c]);
             }
         }
     }
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q)
+#pragma unroll
+        for (int c = 0; c < C; ++c) unpack2(accp[q][c], acc[2 * q][c], acc[2 * q + 1][c]);
 
     if (t.n_chunks == 1) {
         const float gscale = grad_loss[0] * inv_batch;

@@ -41,7 +41,8 @@ SIGNATURES = {
                                          c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_bl_bayloss_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_void_p,
                                           c_void_p, c_size_t, c_void_p, c_void_p]),
-    "dgvcc_dmap_knn_sigma": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgvcc_dmap_knn_workspace_bytes": (c_size_t, [c_int]),
+    "dgvcc_dmap_knn_sigma": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dgvcc_dmap_workspace_bytes": (c_size_t, [c_int]),
     "dgvcc_dmap_splat": (c_int, [c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_void_p, c_size_t,
                                  c_void_p, c_void_p]),

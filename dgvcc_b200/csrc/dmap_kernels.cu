@@ -3,7 +3,8 @@
 // Replaces utils/dmap_gen.py:14-81 of the reference (scipy KDTree k=4 query + one full-image
 // scipy.ndimage.gaussian_filter per head) by
 //   dmap_knn_kernel     : brute-force tiled 4-nearest search in fp64 (self included, like
-//                         KDTree.query(points, k=4)), sigma = 0.1*(d1+d2+d3)        dmap_gen.py:34-48
+//   + dmap_knn_merge      KDTree.query(points, k=4)), candidates split into slices across CTAs and merged;
+//                         sigma = 0.1*(d1+d2+d3)                                     dmap_gen.py:34-48
 //   dmap_prepare_kernel : per head: truncated pixel index, in-bounds test, kernel radius
 //                         int(truncate*sigma+0.5) and the normaliser of scipy's 1-D Gaussian kernel,
 //                         summed in numpy's pairwise order                             dmap_gen.py:41-49
@@ -24,9 +25,23 @@ namespace dmap {
 constexpr int KNN_THREADS = 256;
 
 // ---------------------------------------------------------------------------------- kNN + sigma
+// Each CTA finds, for its 256 query heads, the 4 nearest candidates inside one slice of the head list
+// (grid.y slices, so that small and large N both fill the chip); dmap_knn_merge_kernel then merges the
+// per-slice lists.  Order is (squared distance, index) everywhere, so ties keep the lower index.
+__device__ __forceinline__ void knn_insert(double (&best)[4], int (&bidx)[4], double d2, int j) {
+    best[3] = d2; bidx[3] = j;
+#pragma unroll
+    for (int k = 3; k > 0; --k) {
+        if (best[k] < best[k - 1] || (best[k] == best[k - 1] && bidx[k] < bidx[k - 1])) {
+            const double tb = best[k]; best[k] = best[k - 1]; best[k - 1] = tb;
+            const int ti = bidx[k]; bidx[k] = bidx[k - 1]; bidx[k - 1] = ti;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(KNN_THREADS)
-dmap_knn_kernel(const double2* __restrict__ pts, int n, int32_t* __restrict__ nn_idx,
-                double* __restrict__ nn_dist, double* __restrict__ sigma) {
+dmap_knn_kernel(const double2* __restrict__ pts, int n, int slice_len, double* __restrict__ part_d2,
+                int32_t* __restrict__ part_idx) {
     __shared__ double2 cand[KNN_THREADS];
     const int i = blockIdx.x * KNN_THREADS + threadIdx.x;
     const double2 q = pts[min(i, n - 1)];
@@ -34,29 +49,44 @@ dmap_knn_kernel(const double2* __restrict__ pts, int n, int32_t* __restrict__ nn
     int bidx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { best[k] = INFINITY; bidx[k] = n; }  // scipy: missing neighbour = (inf, N)
-
-    for (int j0 = 0; j0 < n; j0 += KNN_THREADS) {
+    const int j_begin = blockIdx.y * slice_len, j_end = min(n, j_begin + slice_len);
+    for (int j0 = j_begin; j0 < j_end; j0 += KNN_THREADS) {
         __syncthreads();
-        if (j0 + threadIdx.x < n) cand[threadIdx.x] = pts[j0 + threadIdx.x];
+        if (j0 + threadIdx.x < j_end) cand[threadIdx.x] = pts[j0 + threadIdx.x];
         __syncthreads();
-        const int lim = min(KNN_THREADS, n - j0);
+        const int lim = min(KNN_THREADS, j_end - j0);
+#pragma unroll 4
         for (int t = 0; t < lim; ++t) {
             const double dx = __dsub_rn(q.x, cand[t].x);
             const double dy = __dsub_rn(q.y, cand[t].y);
             const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (d2 < best[3]) {  // candidates arrive in index order, so ties keep the lower index
-                best[3] = d2; bidx[3] = j0 + t;
-#pragma unroll
-                for (int k = 3; k > 0; --k) {
-                    if (best[k] < best[k - 1]) {
-                        const double tb = best[k]; best[k] = best[k - 1]; best[k - 1] = tb;
-                        const int ti = bidx[k]; bidx[k] = bidx[k - 1]; bidx[k - 1] = ti;
-                    }
-                }
-            }
+            // candidates arrive in index order, so on ties the earlier (lower) index stays in front
+            if (d2 < best[3]) knn_insert(best, bidx, d2, j0 + t);
         }
     }
     if (i >= n) return;
+    const size_t o = ((size_t)blockIdx.y * n + i) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { part_d2[o + k] = best[k]; part_idx[o + k] = bidx[k]; }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+dmap_knn_merge_kernel(const double* __restrict__ part_d2, const int32_t* __restrict__ part_idx, int n, int slices,
+                      int32_t* __restrict__ nn_idx, double* __restrict__ nn_dist, double* __restrict__ sigma) {
+    const int i = blockIdx.x * KNN_THREADS + threadIdx.x;
+    if (i >= n) return;
+    double best[4];
+    int bidx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best[k] = INFINITY; bidx[k] = n; }
+    for (int s = 0; s < slices; ++s) {
+        const size_t o = ((size_t)s * n + i) * 4;
+        for (int k = 0; k < 4; ++k) {
+            const double d2 = part_d2[o + k];
+            const int j = part_idx[o + k];
+            if (j < n && (d2 < best[3] || (d2 == best[3] && j < bidx[3]))) knn_insert(best, bidx, d2, j);
+        }
+    }
     double d[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -235,13 +265,35 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, int n, int height, int width
 using namespace dgvcc;
 using namespace dgvcc::dmap;
 
+static int knn_slices(int n) {
+    const int query_ctas = ceil_div(n, KNN_THREADS);
+    int s = ceil_div(4 * 148, query_ctas);       // ~4 CTAs per SM in flight
+    const int max_s = ceil_div(n, KNN_THREADS);  // a slice is at least one candidate tile
+    if (s > max_s) s = max_s;
+    return s < 1 ? 1 : s;
+}
+
+extern "C" size_t dgvcc_dmap_knn_workspace_bytes(int n) {
+    if (n <= 0) return 16;
+    return (size_t)knn_slices(n) * n * 4 * (sizeof(double) + sizeof(int32_t));
+}
+
 extern "C" int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx, double* nn_dist, double* sigma,
-                                    void* stream) {
+                                    void* workspace, size_t workspace_bytes, void* stream) {
     if (n < 0) return DGVCC_ERR_ARG;
     if (n == 0) return DGVCC_OK;
-    if (!pts_xy || !nn_idx || !nn_dist || !sigma) return DGVCC_ERR_ARG;
-    dmap_knn_kernel<<<ceil_div(n, KNN_THREADS), KNN_THREADS, 0, (cudaStream_t)stream>>>(
-        (const double2*)pts_xy, n, nn_idx, nn_dist, sigma);
+    if (!pts_xy || !nn_idx || !nn_dist || !sigma || !workspace) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_dmap_knn_workspace_bytes(n)) return DGVCC_ERR_WORKSPACE;
+    const int slices = knn_slices(n);
+    const int slice_len = ceil_div(ceil_div(n, slices), KNN_THREADS) * KNN_THREADS;
+    const int used = ceil_div(n, slice_len);
+    double* part_d2 = (double*)workspace;
+    int32_t* part_idx = (int32_t*)(part_d2 + (size_t)slices * n * 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    dmap_knn_kernel<<<dim3(ceil_div(n, KNN_THREADS), used), KNN_THREADS, 0, st>>>((const double2*)pts_xy, n, slice_len,
+                                                                                 part_d2, part_idx);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    dmap_knn_merge_kernel<<<ceil_div(n, KNN_THREADS), KNN_THREADS, 0, st>>>(part_d2, part_idx, n, used, nn_idx, nn_dist, sigma);
     return (int)cudaGetLastError();
 }
 

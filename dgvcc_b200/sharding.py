@@ -47,3 +47,10 @@ class ShardedLoss(torch.nn.Module):
 
     def forward(self, *args, **kwargs):
         return all_reduce_loss(self.loss_module(*args, **kwargs), self.group)
+
+
+def sharded_mean_over_batch(local_mean, local_batch, global_batch, group=None):
+    """All-reduced value of a loss that is a MEAN over samples, given each rank's mean over its own samples
+    (e.g. ``instance_whitening_loss``, which divides by the local B, instance_whitening.py:25):
+    ``sum_ranks(local_mean * B_local) / B_global``.  Gradients stay local and are scaled by B_local / B_global."""
+    return all_reduce_loss(local_mean * (float(local_batch) / float(global_batch)), group)

@@ -52,8 +52,11 @@ def knn_sigma(points, device=None):
     idx = torch.empty((n, 4), dtype=torch.int32, device=dev)
     dist = torch.empty((n, 4), dtype=torch.float64, device=dev)
     sigma = torch.empty((n,), dtype=torch.float64, device=dev)
+    kws_bytes = _native.lib().dgvcc_dmap_knn_workspace_bytes(n)
+    kws = torch.empty((kws_bytes,), dtype=torch.uint8, device=dev)
     _native.check(_native.lib().dgvcc_dmap_knn_sigma(_native.ptr(d_pts), n, _native.ptr(idx), _native.ptr(dist),
-                                                     _native.ptr(sigma), _native.stream_ptr(dev)), "dgvcc_dmap_knn_sigma")
+                                                     _native.ptr(sigma), _native.ptr(kws), kws_bytes,
+                                                     _native.stream_ptr(dev)), "dgvcc_dmap_knn_sigma")
     return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64), sigma.cpu().numpy()
 
 
@@ -75,8 +78,11 @@ def _density_device(height, width, pts, adaptive, dev):
             idx = torch.empty((n, 4), dtype=torch.int32, device=dev)
             dist = torch.empty((n, 4), dtype=torch.float64, device=dev)
             sigma = torch.empty((n,), dtype=torch.float64, device=dev)
+            kws_bytes = lib.dgvcc_dmap_knn_workspace_bytes(n)
+            kws = torch.empty((kws_bytes,), dtype=torch.uint8, device=dev)
             _native.check(lib.dgvcc_dmap_knn_sigma(_native.ptr(d_pts), n, _native.ptr(idx), _native.ptr(dist),
-                                                   _native.ptr(sigma), stream), "dgvcc_dmap_knn_sigma")
+                                                   _native.ptr(sigma), _native.ptr(kws), kws_bytes, stream),
+                          "dgvcc_dmap_knn_sigma")
     _native.check(lib.dgvcc_dmap_splat(
         _native.ptr(d_pts), _native.ptr(sigma), FIXED_SIGMA, ADAPTIVE_TRUNCATE if adaptive else FIXED_TRUNCATE, n,
         height, width, _native.ptr(ws), ws_bytes, _native.ptr(out), stream), "dgvcc_dmap_splat")

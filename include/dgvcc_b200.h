@@ -142,8 +142,9 @@ int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta, int batch,
  * sigma (dmap_gen.py:45-48): nn_idx [n,4] i32 / nn_dist [n,4] f64, column 0 the
  * point itself, missing neighbours (n < 4) = (inf, n) like scipy;
  * sigma[i] = 0.1*(d1+d2+d3) when n > 3, else 15. */
+size_t dgvcc_dmap_knn_workspace_bytes(int n);
 int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx, double* nn_dist, double* sigma,
-                         void* stream);
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 size_t dgvcc_dmap_workspace_bytes(int n);
 

@@ -57,12 +57,15 @@ def bench_dmap(cpu):
                 idx = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
                 dist = torch.empty((max(n, 1), 4), dtype=torch.float64, device=dev)
                 sig = torch.empty((max(n, 1),), dtype=torch.float64, device=dev)
+                kws_bytes = lib.dgvcc_dmap_knn_workspace_bytes(n)
+                kws = torch.empty(kws_bytes, dtype=torch.uint8, device=dev)
                 flush.zero_()
                 e0, e1, e2 = ev(), ev(), ev()
                 st = _native.stream_ptr(dev)
                 e0.record()
                 if adaptive and n:
-                    lib.dgvcc_dmap_knn_sigma(_native.ptr(d_pts), n, _native.ptr(idx), _native.ptr(dist), _native.ptr(sig), st)
+                    lib.dgvcc_dmap_knn_sigma(_native.ptr(d_pts), n, _native.ptr(idx), _native.ptr(dist), _native.ptr(sig),
+                                             _native.ptr(kws), kws_bytes, st)
                 e1.record()
                 lib.dgvcc_dmap_splat(_native.ptr(d_pts), _native.ptr(sig) if (adaptive and n) else None, 4.0,
                                      4.0 if adaptive else 1.75, n, h, w, _native.ptr(ws), ws_bytes, _native.ptr(out), st)

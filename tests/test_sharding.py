@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dgvcc_b200.sharding import ShardedLoss, all_reduce_loss, snake_partition
+from dgvcc_b200.sharding import ShardedLoss, all_reduce_loss, sharded_mean_over_batch, snake_partition
 
 
 def test_snake_partition_balances_and_covers():
@@ -44,6 +44,13 @@ def _worker(rank, world, port, out):
     tot = all_reduce_loss(part * 2)
     tot.backward()
     ok = ok and float(tot) == 6.0 and float(part.grad) == 2.0
+    # a per-sample mean loss (ISW style) on unequal shards: rank 0 holds 3 samples, rank 1 holds 5
+    samples = torch.arange(1, 9, dtype=torch.float32)
+    mine2 = (samples[:3] if rank == 0 else samples[3:]).clone().requires_grad_(True)
+    glob = sharded_mean_over_batch((mine2 ** 2).mean(), len(mine2), 8)
+    glob.backward()
+    ok = ok and abs(float(glob) - float((samples ** 2).mean())) < 1e-5
+    ok = ok and torch.allclose(mine2.grad, 2 * mine2.detach() / 8)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

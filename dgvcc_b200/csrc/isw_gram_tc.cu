@@ -11,11 +11,12 @@
 // One CTA computes one upper-triangular 128x128 tile of one sample over one split of the K = HW range
 // and stores the partial tile; isw_cov_finish_kernel (isw_kernels.cu) adds the splits in order.
 //
-// Warp roles (192 threads):
+// Warp roles (320 threads):
 //   warp 0   : TMA producer -- cp.async.bulk.tensor of the 128 x 32 fp32 operand tiles (128B swizzle)
 //   warp 1   : TMEM allocation; one lane issues tcgen05.mma.kind::tf32 (12 per 32-wide k block)
-//   warps 2-5: converters -- rewrite each landed tile as hi in place, lo beside it, then signal the
-//              MMA warp; after the k loop they are the epilogue (tcgen05.ld -> global partial tile)
+//   warps 2-9: converters -- rewrite each landed tile as hi in place, lo beside it, then signal the
+//              MMA warp; after the k loop they are the epilogue (tcgen05.ld -> global partial tile; warp w
+//              reads TMEM lane quarter w % 4, warps 2-5 the left 64 columns, warps 6-9 the right 64)
 // Pipeline: full[s] (TMA -> converters), ready[s] (converters -> MMA), empty[s] (MMA -> TMA) over
 // STAGES shared-memory stages; accum (MMA -> epilogue).
 #include "tc_common.cuh"
@@ -30,8 +31,8 @@ constexpr int UMMA_K = 8;                   // tf32 MMA k extent (32 bytes)
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = TILE_M * BLOCK_K * 4;  // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, B_hi, A_lo, B_lo
-constexpr int THREADS = 192;
-constexpr int CONVERTER_WARPS = 4;
+constexpr int CONVERTER_WARPS = 8;                  // two per SM sub-partition
+constexpr int THREADS = 64 + 32 * CONVERTER_WARPS;
 constexpr int TMEM_COLS = 256;  // two fp32 accumulators: hi*hi^T, and the small cross terms
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -131,7 +132,7 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
         }
     } else {
         // ===== converters: hi in place, lo beside =====
-        const int ctid = threadIdx.x - 64;  // 0..127
+        const int ctid = threadIdx.x - 64;  // 0..255
         for (int kb = 0; kb < n_kb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
@@ -141,7 +142,7 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
             float4* hi = reinterpret_cast<float4*>(stage);
             float4* lo = reinterpret_cast<float4*>(stage + 2 * TILE_BYTES);
 #pragma unroll 4
-            for (int i = ctid; i < n_vec; i += 128) {
+            for (int i = ctid; i < n_vec; i += 32 * CONVERTER_WARPS) {
                 const float4 v = hi[i];
                 float4 h, l;
                 h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
@@ -162,8 +163,9 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
         const int row = lane_base + lane;
         float* out = a.part + ((((size_t)b * a.splits + split) * a.n_tiles + blockIdx.x) * TILE_M + row) * TILE_M;
         const bool row_ok = ti * TILE_M + row < a.c;
+        const int col_begin = (warp - 2) / 4 * (TILE_M / 2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TILE_M; c0 += 32) {
+        for (int c0 = col_begin; c0 < col_begin + TILE_M / 2; c0 += 32) {
             uint32_t r[32], x[32];
             const uint32_t taddr = tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)c0;
             tmem_ld32(taddr, r);           // hi hi^T

@@ -164,11 +164,105 @@ __device__ double pairwise_phi_sum(double coef, int first, int n) {
     return ret;
 }
 
-__global__ void __launch_bounds__(128)
+// ---- the same sum, one warp per head -------------------------------------------------------------
+// Groups of 8 lanes evaluate one leaf each: lane j of a group owns numpy's accumulator r[j] (elements
+// j, j+8, ... of the leaf), the group leader combines them in numpy's order and adds the tail.  The tree above
+// the leaves is then combined by lane 0 in numpy's recursion order.  Bit-identical to pairwise_phi_sum.
+constexpr int MAX_LEAVES = 256;
+
+struct LeafList {
+    int first[MAX_LEAVES];
+    int len[MAX_LEAVES];
+    double sum[MAX_LEAVES];
+};
+
+// DFS enumeration of the leaves of numpy's recursion over [first, first + n); returns their number
+// (or -1 when there are more than MAX_LEAVES).  Pure integer work, done redundantly by every lane.
+__device__ int enumerate_leaves(int first, int n, LeafList& ll, bool write) {
+    constexpr int DEPTH = 26;
+    int s_first[DEPTH], s_n[DEPTH], s_stage[DEPTH];
+    int sp = 0, count = 0;
+    s_first[0] = first; s_n[0] = n; s_stage[0] = 0;
+    while (sp >= 0) {
+        const int cn = s_n[sp];
+        int n2 = cn / 2;
+        n2 -= n2 % 8;
+        if (s_stage[sp] == 0) {
+            if (cn <= 128) {
+                if (count >= MAX_LEAVES) return -1;
+                if (write) { ll.first[count] = s_first[sp]; ll.len[count] = cn; }
+                ++count; --sp;
+                continue;
+            }
+            s_stage[sp] = 1;
+            s_first[sp + 1] = s_first[sp]; s_n[sp + 1] = n2; s_stage[sp + 1] = 0;
+            ++sp;
+        } else if (s_stage[sp] == 1) {
+            s_stage[sp] = 2;
+            s_first[sp + 1] = s_first[sp] + n2; s_n[sp + 1] = cn - n2; s_stage[sp + 1] = 0;
+            ++sp;
+        } else {
+            --sp;
+        }
+    }
+    return count;
+}
+
+// One leaf (n <= 128) by a group of 8 lanes; the result is valid on the group's lane 0.
+__device__ __forceinline__ double leaf_by_group(double coef, int first, int n, int sub /*0..7*/, unsigned group_mask) {
+    if (n < 8) {  // numpy's plain loop: nothing to parallelise
+        double res = 0.0;
+        if (sub == 0)
+            for (int i = 0; i < n; ++i) res = __dadd_rn(res, phi(coef, first + i));
+        return res;
+    }
+    const int body = n - (n % 8);
+    double r = phi(coef, first + sub);
+    for (int i = 8; i < body; i += 8) r = __dadd_rn(r, phi(coef, first + i + sub));
+    // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)): a butterfly over the 8 lanes is exactly this tree
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 4));
+    if (sub == 0)
+        for (int i = body; i < n; ++i) r = __dadd_rn(r, phi(coef, first + i));
+    return r;
+}
+
+// Combine the leaf sums in numpy's recursion order (lane 0 only).
+__device__ double combine_leaves(int first, int n, const LeafList& ll) {
+    constexpr int DEPTH = 26;
+    int s_n[DEPTH], s_stage[DEPTH];
+    double s_left[DEPTH];
+    int sp = 0, next = 0;
+    s_n[0] = n; s_stage[0] = 0;
+    double ret = 0.0;
+    (void)first;
+    while (sp >= 0) {
+        const int cn = s_n[sp];
+        int n2 = cn / 2;
+        n2 -= n2 % 8;
+        if (s_stage[sp] == 0) {
+            if (cn <= 128) { ret = ll.sum[next++]; --sp; continue; }
+            s_stage[sp] = 1; s_n[sp + 1] = n2; s_stage[sp + 1] = 0; ++sp;
+        } else if (s_stage[sp] == 1) {
+            s_left[sp] = ret; s_stage[sp] = 2; s_n[sp + 1] = cn - n2; s_stage[sp + 1] = 0; ++sp;
+        } else {
+            ret = __dadd_rn(s_left[sp], ret); --sp;
+        }
+    }
+    return ret;
+}
+
+constexpr int PREP_WARPS = 4;
+
+__global__ void __launch_bounds__(PREP_WARPS * 32)
 dmap_prepare_kernel(const double2* __restrict__ pts, const double* __restrict__ sigma, double fixed_sigma,
                     double truncate, int n, int height, int width, Stamp* __restrict__ stamps) {
-    const int i = blockIdx.x * 128 + threadIdx.x;
+    __shared__ LeafList leaves[PREP_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * PREP_WARPS + warp;
     if (i >= n) return;
+    LeafList& ll = leaves[warp];
     const double2 p = pts[i];
     Stamp s;
     s.pad_ = 0;
@@ -185,9 +279,26 @@ dmap_prepare_kernel(const double2* __restrict__ pts, const double* __restrict__ 
     } else {
         s.radius = (int)__dadd_rn(__dmul_rn(truncate, sd), 0.5);
         s.coef = -0.5 / __dmul_rn(sd, sd);
-        s.norm = pairwise_phi_sum(s.coef, -s.radius, 2 * s.radius + 1);
+        const int n_el = 2 * s.radius + 1;
+        const int n_leaves = enumerate_leaves(-s.radius, n_el, ll, lane == 0);
+        if (n_leaves < 0) {
+            s.norm = (lane == 0) ? pairwise_phi_sum(s.coef, -s.radius, n_el) : 0.0;  // absurdly wide kernel
+        } else {
+            __syncwarp();
+            const int group = lane >> 3, sub = lane & 7;
+            const unsigned group_mask = 0xffu << (8 * group);
+            for (int l0 = 0; l0 < n_leaves; l0 += 4) {
+                const int l = l0 + group;
+                if (l < n_leaves) {  // uniform inside a group of 8 lanes
+                    const double v = leaf_by_group(s.coef, ll.first[l], ll.len[l], sub, group_mask);
+                    if (sub == 0) ll.sum[l] = v;
+                }
+            }
+            __syncwarp();
+            s.norm = (lane == 0) ? combine_leaves(-s.radius, n_el, ll) : 0.0;
+        }
     }
-    stamps[i] = s;
+    if (lane == 0) stamps[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------ splat
@@ -309,7 +420,7 @@ extern "C" int dgvcc_dmap_splat(const double* pts_xy, const double* sigma, doubl
     cudaStream_t st = (cudaStream_t)stream;
     Stamp* stamps = (Stamp*)workspace;
     if (n > 0) {
-        dmap_prepare_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const double2*)pts_xy, sigma, fixed_sigma, truncate, n,
+        dmap_prepare_kernel<<<ceil_div(n, PREP_WARPS), PREP_WARPS * 32, 0, st>>>((const double2*)pts_xy, sigma, fixed_sigma, truncate, n,
                                                               height, width, stamps);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }

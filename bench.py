@@ -299,6 +299,17 @@ def run_gpu(args, emit=print):
         grad_h.copy_(d.grad, non_blocking=True)
         return float(loss.detach())  # D2H of the loss: synchronises the step
 
+    # the same with the batch packed by the data pipeline (pack_batch in the collate function): one pinned buffer
+    from dgvcc_b200.losses.bl import pack_batch
+    packed_h = pack_batch(wl["points"], wl["targets"], use_background=USE_BG).pin_memory()
+
+    def step_host_packed():
+        d = dens_h.to(dev, non_blocking=True).requires_grad_(True)
+        loss = loss_fn(packed_h, st_h.to(dev, non_blocking=True), None, d)
+        loss.backward()
+        grad_h.copy_(d.grad, non_blocking=True)
+        return float(loss.detach())
+
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -353,12 +364,20 @@ def run_gpu(args, emit=print):
         step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
+    for _ in range(3):
+        step_host_packed()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host_packed()
+    barrier()
+    e2e_packed_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s, cull_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_s, cull_ms, e2e_packed_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, cull_ms = float(t[0]), float(t[1]), float(t[2])
+        total_ms, e2e_s, cull_ms, e2e_packed_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -382,6 +401,11 @@ def run_gpu(args, emit=print):
             "e2e": {"value": global_batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": args.steps * (7 if packed.multi_chunk else 5),
+            "e2e_packed_collate": {"value": global_batch * args.steps / e2e_packed_s, "unit": "images/s",
+                                   "note": ("informational: same end-to-end step, but the ragged lists were packed once by "
+                                            "pack_batch (what a collate_fn does in the DataLoader workers) instead of inside "
+                                            "every timed step; H2D of the packed buffer / density and D2H of loss / gradient "
+                                            "are still inside the timed region")},
             "exact_cull": {"value": global_batch / (cull_ms / args.steps * 1e-3), "unit": "images/s",
                            "ms_per_step": cull_ms / args.steps,
                            "note": ("informational, NOT the graded number: BL.exact_cull=True skips (point, pixel-tile) "

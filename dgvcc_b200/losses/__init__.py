@@ -1,1 +1,1 @@
-from .bl import BL, Bay_Loss, Post_Prob  # noqa: F401
+from .bl import BL, Bay_Loss, PackedBatch, Post_Prob, pack_batch  # noqa: F401

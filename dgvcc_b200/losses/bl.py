@@ -110,6 +110,52 @@ def _align16(n):
     return (n + 15) // 16 * 16
 
 
+class PackedBatch:
+    """A ragged batch already packed on the host (table + points + targets in ONE buffer), built by
+    ``pack_batch`` -- e.g. inside a DataLoader ``collate_fn`` in place of bay_dataset.py:13-19's tuples -- so that
+    the training step only has to upload it.  Pass it to ``BL.forward`` as ``points`` (``target_list=None``).
+    ``pin_memory()`` is what ``DataLoader(pin_memory=True)`` calls on custom batch types."""
+
+    def __init__(self, buf, meta_bytes, o_pts, o_tgt, total, counts, rows, total_chunks, multi_chunk, use_bg):
+        self.buf, self.meta_bytes, self.o_pts, self.o_tgt, self.total = buf, meta_bytes, o_pts, o_tgt, total
+        self.counts, self.rows, self.total_chunks, self.multi_chunk, self.use_bg = counts, rows, total_chunks, multi_chunk, use_bg
+
+    def pin_memory(self):
+        self.buf = self.buf.pin_memory()
+        return self
+
+    def __len__(self):
+        return len(self.counts)
+
+
+def pack_batch(points, targets, use_background=True, chunk=None):
+    """Host-side CSR packing of lists of [N_i,2] points and [N_i] targets (CPU tensors) into a ``PackedBatch``."""
+    points = _as_point_list(points)
+    if len(points) == 0:
+        raise ValueError("empty batch")
+    counts = np.asarray([int(p.shape[0]) for p in points], dtype=np.int64)
+    rows = np.where(counts == 0, 1, counts + (1 if use_background else 0))
+    targets = [t.reshape(-1) for t in targets]
+    for t, n in zip(targets, counts):
+        if t.shape[0] != n:
+            raise ValueError(f"target length {t.shape[0]} does not match its {n} points")
+    meta, total_chunks, multi_chunk = build_meta(counts, rows, chunk or chunk_points())
+    total_points = int(counts.sum())
+    n_pts = max(total_points, 1)
+    o_pts = _align16(meta.nbytes)
+    o_tgt = o_pts + _align16(8 * n_pts)
+    total = o_tgt + _align16(4 * n_pts)
+    buf = torch.zeros((total,), dtype=torch.uint8)
+    view = buf.numpy()
+    view[:meta.nbytes].view(np.int32)[:] = meta
+    if total_points:
+        np.concatenate([_host_f32(p) for p in points if p.shape[0]], axis=0,
+                       out=view[o_pts:o_pts + 8 * total_points].view(np.float32).reshape(-1, 2))
+        np.concatenate([_host_f32(t) for t in targets if t.shape[0]],
+                       out=view[o_tgt:o_tgt + 4 * total_points].view(np.float32))
+    return PackedBatch(buf, meta.nbytes, o_pts, o_tgt, total, counts, rows, total_chunks, multi_chunk, bool(use_background))
+
+
 class _Packed:
     """CSR packing of one ragged batch + the small int32 table the kernels read (include/dgvcc_b200.h).
 
@@ -119,6 +165,9 @@ class _Packed:
     """
 
     def __init__(self, points, use_bg, device, targets=None):
+        if isinstance(points, PackedBatch):
+            self._from_packed_batch(points, use_bg, device)
+            return
         points = _as_point_list(points)
         self.batch = len(points)
         if self.batch == 0:
@@ -176,6 +225,24 @@ class _Packed:
                     self.targets = torch.zeros((1,), dtype=torch.float32, device=device)
                 else:
                     self.targets = torch.cat([t.to(device=device, dtype=torch.float32) for t in targets]).contiguous()
+
+
+    def _from_packed_batch(self, pb, use_bg, device):
+        if pb.use_bg != bool(use_bg):
+            raise ValueError("PackedBatch was packed for a different use_background setting")
+        self.batch = len(pb.counts)
+        self.counts, self.rows = pb.counts, pb.rows
+        self.total_points, self.total_rows = int(pb.counts.sum()), int(pb.rows.sum())
+        self.total_chunks, self.multi_chunk = pb.total_chunks, pb.multi_chunk
+        b = self.batch
+        meta = pb.buf[:pb.meta_bytes].numpy().view(np.int32)
+        self.pt_off, self.row_off = meta[:b + 1].copy(), meta[b + 1:2 * b + 2].copy()
+        self.on_host = True
+        dev_buf = pb.buf.to(device, non_blocking=True)  # one copy; asynchronous when the batch is pinned
+        n_pts = max(self.total_points, 1)
+        self.meta = dev_buf[:pb.meta_bytes].view(torch.int32)
+        self.pts = dev_buf[pb.o_pts:pb.o_pts + 8 * n_pts].view(torch.float32).view(-1, 2)
+        self.targets = dev_buf[pb.o_tgt:pb.o_tgt + 4 * n_pts].view(torch.float32)
 
 
 def _pack_targets(target_list, packed, device):
@@ -371,6 +438,8 @@ class BL(Module):
         _native.require_cuda(pre_density, "BL.forward")
         if len(points) != pre_density.shape[0]:
             raise ValueError(f"{len(points)} point sets for a batch of {pre_density.shape[0]} density maps")
+        if isinstance(points, PackedBatch) and target_list is not None:
+            raise ValueError("a PackedBatch already carries its targets; pass target_list=None")
         packed = _Packed(points, pp.use_bg, dev, targets=target_list)
         targets = packed.targets
         st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()

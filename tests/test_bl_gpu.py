@@ -190,6 +190,25 @@ def test_host_lists_take_the_packed_upload_path():
     assert_close(ref[0].cpu(), c["ref_loss"], RTOL, 0, "loss")
 
 
+def test_packed_batch_from_collate_matches_lists():
+    """pack_batch (the collate-side packing) + one upload == passing the lists, bit for bit."""
+    from dgvcc_b200.losses.bl import BL, pack_batch
+    dev = torch.device("cuda:0")
+    for name in ("mixed", "nobg"):
+        c = load_bl_golden(name)
+        mod = BL(c["sigma"], c["width"], c["stride"], c["bg_ratio"], c["use_bg"], dev)
+        d1 = c["density"].to(dev).clone().requires_grad_(True)
+        l1 = mod([p.to(dev) for p in c["points"]], c["st_sizes"].to(dev), [t.to(dev) for t in c["targets"]], d1)
+        l1.backward()
+        pb = pack_batch(c["points"], c["targets"], use_background=c["use_bg"]).pin_memory()
+        d2 = c["density"].to(dev).clone().requires_grad_(True)
+        l2 = mod(pb, c["st_sizes"].to(dev), None, d2)
+        l2.backward()
+        assert torch.equal(l1.detach(), l2.detach()) and torch.equal(d1.grad, d2.grad)
+    with pytest.raises(ValueError):
+        mod(pb, c["st_sizes"].to(dev), c["targets"], d2)
+
+
 def test_topk_ties_are_index_ordered():
     """Equal residuals straddling the 90 % cut: the kept set is deterministic (first in index order)."""
     from dgvcc_b200.losses.bl import BL

@@ -93,6 +93,29 @@ def test_fused_bl_matches_oracle_small(counts, w, h, sigma, use_bg):
     check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_against_oracle(seed, monkeypatch):
+    """Randomised geometry: batch size, grid (incl. widths that are no multiple of 32), stride, sigma, background
+    on/off, point counts around the tile / chunk boundaries, chunk size, culling on/off."""
+    rng = np.random.default_rng(900 + seed)
+    stride = int(rng.choice([4, 8, 16]))
+    hp, wp = int(rng.integers(3, 70)), int(rng.integers(3, 100))
+    h, w = hp * stride, wp * stride
+    b = int(rng.integers(1, 6))
+    counts = [int(rng.choice([0, 1, 2, 3, 7, 8, 9, 31, 33, 127, 128, 129, 300])) for _ in range(b)]
+    sigma = float(rng.choice([4.0, 8.0, 5.5, 12.0]))
+    use_bg = bool(rng.integers(0, 2))
+    bg_ratio = float(rng.choice([1.0, 0.15, 0.5]))
+    monkeypatch.setenv("DGVCC_BL_CHUNK", str(int(rng.choice([17, 64, 1024]))))
+    pts, tgt, dens, st = synthetic.bl_batch(40 + seed, counts, w, h, stride)
+    pts = [torch.from_numpy(p) for p in pts]
+    tgt = [torch.from_numpy(t) for t in tgt]
+    dens, st = torch.from_numpy(dens), torch.from_numpy(st)
+    ref = bl_oracle.bl_forward_backward(pts, st, tgt, dens, stride, sigma, bg_ratio, use_bg)
+    got = run_cuda(pts, st, tgt, dens, stride, sigma, bg_ratio, use_bg, exact_cull=bool(seed % 2))
+    check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
+
+
 def test_config2_sha_batch_matches_oracle():
     """BASELINE config 2: 8 ShanghaiTech-A-shaped images, 50..3000 points, 128x128 grid."""
     counts = synthetic.config_counts(2)

@@ -341,44 +341,55 @@ extern "C" int dgvcc_isw_instnorm_backward(const float* dy, const float* y, cons
     return (int)cudaGetLastError();
 }
 
-// Split-K plan shared by both Gram kernels: enough CTAs to cover the chip ~2x, k ranges a multiple of 32.
-static void gram_plan(int batch, int c, int hw, int tile, int* splits, int* k_per_split, int* n_tiles) {
-    const int t1 = ceil_div(c, tile);
+// Split-K plans.  SIMT Gram: 64x64 tiles, enough CTAs to cover the chip about twice.  Tensor-core Gram: one CTA
+// per SM and one wave (the kernel bounds its in-TMEM accumulation chains itself, so K per CTA may be long);
+// C <= 64 packs two samples into one 128-row tile and stores 64x64 partial tiles.
+static void gram_plan_simt(int batch, int c, int hw, int* splits, int* k_per_split, int* n_tiles) {
+    const int t1 = ceil_div(c, 64);
     *n_tiles = t1 * (t1 + 1) / 2;
-    // at most two full waves of CTAs (one CTA per SM), but accumulation chains of at most 768: the tensor
-    // core truncates when it adds into TMEM (-4e-8 relative per K=8 step, scripts/probe_tc_accuracy.py)
-    int s = (2 * 148) / (batch * *n_tiles);
+    int s = ceil_div(296, batch * *n_tiles);
     const int max_s = ceil_div(hw, 256);
-    const int min_s = ceil_div(hw, 768);
     if (s > max_s) s = max_s;
-    if (s < min_s) s = min_s;
     if (s < 1) s = 1;
-    int kps = ceil_div(ceil_div(hw, s), 32) * 32;
+    const int kps = ceil_div(ceil_div(hw, s), 32) * 32;
     *splits = ceil_div(hw, kps);
     *k_per_split = kps;
 }
 
+static void gram_plan_tc(int batch, int c, int hw, int* splits, int* k_per_split, int* n_tiles, int* tile) {
+    const bool pair = c <= 64;
+    *tile = pair ? 64 : 128;
+    const int t1 = pair ? 1 : ceil_div(c, 128);
+    *n_tiles = t1 * (t1 + 1) / 2;
+    const int units = (pair ? ceil_div(batch, 2) : batch) * *n_tiles;
+    int s = 148 / units;
+    const int max_s = ceil_div(hw, 256);
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    const int kps = ceil_div(ceil_div(hw, s), 32) * 32;
+    *splits = ceil_div(hw, kps);
+    *k_per_split = kps;
+}
+
+static size_t gram_partial_floats(int batch, int c, int hw) {
+    int s, k, n, tile;
+    gram_plan_simt(batch, c, hw, &s, &k, &n);
+    const size_t p_simt = (size_t)batch * s * n * 64 * 64;
+    gram_plan_tc(batch, c, hw, &s, &k, &n, &tile);
+    const size_t p_tc = (size_t)batch * s * n * tile * tile;
+    return p_simt > p_tc ? p_simt : p_tc;
+}
+
 extern "C" size_t dgvcc_isw_workspace_bytes(int batch, int c, int hw) {
-    int s64, k64, n64, s128, k128, n128;
-    gram_plan(batch, c, hw, 64, &s64, &k64, &n64);
-    gram_plan(batch, c, hw, 128, &s128, &k128, &n128);
-    const size_t p64 = (size_t)batch * s64 * n64 * 64 * 64;
-    const size_t p128 = (size_t)batch * s128 * n128 * 128 * 128;
-    const size_t part = (p64 > p128 ? p64 : p128) * sizeof(float);
     // partials | off[B] | ticket (256 B) | S [B,C,C]
-    return align_up(part, 256) + align_up((size_t)batch * sizeof(float), 256) + 256 +
-           align_up((size_t)batch * c * c * sizeof(float), 256);
+    return align_up(gram_partial_floats(batch, c, hw) * sizeof(float), 256) + align_up((size_t)batch * sizeof(float), 256) +
+           256 + align_up((size_t)batch * c * c * sizeof(float), 256);
 }
 
 namespace {
 struct IswWs { float* part; float* off; unsigned int* ticket; float* s; };
 IswWs carve(void* ws, int batch, int c, int hw) {
-    int s64, k64, n64, s128, k128, n128;
-    gram_plan(batch, c, hw, 64, &s64, &k64, &n64);
-    gram_plan(batch, c, hw, 128, &s128, &k128, &n128);
-    const size_t p64 = (size_t)batch * s64 * n64 * 64 * 64;
-    const size_t p128 = (size_t)batch * s128 * n128 * 128 * 128;
-    const size_t part = align_up((p64 > p128 ? p64 : p128) * sizeof(float), 256);
+    const size_t part = align_up(gram_partial_floats(batch, c, hw) * sizeof(float), 256);
     IswWs w;
     char* p = (char*)ws;
     w.part = (float*)p; p += part;
@@ -402,13 +413,14 @@ extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int ba
     int splits, kps, n_tiles, tile = 64;
     bool done = false;
     if (use_tensor_cores) {
-        gram_plan(batch, c, hw, 128, &splits, &kps, &n_tiles);
+        gram_plan_tc(batch, c, hw, &splits, &kps, &n_tiles, &tile);
         const int rc = dgvcc_isw_gram_tc_partials(f_map, batch, c, hw, splits, kps, w.part, stream);
-        if (rc == DGVCC_OK) { done = true; tile = 128; }
+        if (rc == DGVCC_OK) done = true;
         else if (rc != DGVCC_ERR_UNSUPPORTED) return rc;
     }
     if (!done) {
-        gram_plan(batch, c, hw, 64, &splits, &kps, &n_tiles);
+        tile = 64;
+        gram_plan_simt(batch, c, hw, &splits, &kps, &n_tiles);
         isw_gram_simt_kernel<<<dim3(n_tiles, splits, batch), GEMM_THREADS, 0, st>>>(f_map, c, hw, splits, kps, w.part);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }

@@ -114,14 +114,15 @@ inline EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// fp32 3-D tensor map {inner, rows, batch} with a {box_inner (= 32 floats, one 128-byte swizzle row), box_rows, 1} box.
+// fp32 3-D tensor map {inner, rows, batch} with a {32 floats (one 128-byte swizzle row), box_rows, box_batch} box.
 inline bool make_tmap_f32_3d(CUtensorMap* map, const float* base, uint64_t inner, uint64_t rows, uint64_t batch,
-                             uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                             uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+                             uint32_t box_batch = 1) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
     const cuuint64_t dims[3] = {inner, rows, batch};
     const cuuint64_t strides[2] = {inner * 4, inner * rows * 4};
-    const cuuint32_t box[3] = {32, box_rows, 1};
+    const cuuint32_t box[3] = {32, box_rows, box_batch};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

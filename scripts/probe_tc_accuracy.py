@@ -10,7 +10,7 @@ for hw, kps in [(256, 256), (1024, 1024), (4096, 4096), (16384, 16384), (16384, 
     x = torch.randn((b, c, hw), generator=g)
     xd = x.to(DEV)
     splits = (hw + kps - 1) // kps
-    part = torch.zeros((b, splits, 1, 128, 128), device=DEV)
+    part = torch.zeros((b, splits, 1, 128, 128), device=DEV)  # c = 128: one 128x128 tile
     rc = _native.lib().dgvcc_isw_gram_tc_partials(_native.ptr(xd), b, c, hw, splits, kps, _native.ptr(part), _native.stream_ptr(torch.device(DEV)))
     assert rc == 0
     torch.cuda.synchronize()

@@ -23,6 +23,16 @@ class BLLayout(ctypes.Structure):
                [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("reserved_", c_int32)]
 
 
+class DmapPlan(ctypes.Structure):
+    """Mirror of struct dgvcc_dmap_plan."""
+    _fields_ = [(n, c_int64) for n in
+                ("total_heads", "total_pixels", "fine_tiles", "coarse_tasks", "knn_tasks",
+                 "off_stamps", "off_boxes", "off_wtab", "off_fmask", "off_tmpl", "off_desc", "off_ccount", "off_ctotal", "off_clist", "splat_workspace_bytes",
+                 "off_knn_d2", "off_knn_idx", "knn_workspace_bytes")]
+
+
+DMAP_META_COLS = 12  # DGVCC_DMAP_META_COLS
+
 # name -> (restype, argtypes); every symbol include/dgvcc_b200.h declares must appear here
 SIGNATURES = {
     "dgvcc_abi_version": (c_int, []),
@@ -43,9 +53,11 @@ SIGNATURES = {
                                           c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_dmap_knn_workspace_bytes": (c_size_t, [c_int]),
     "dgvcc_dmap_knn_sigma": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "dgvcc_dmap_workspace_bytes": (c_size_t, [c_int]),
-    "dgvcc_dmap_splat": (c_int, [c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_int, c_void_p, c_size_t,
-                                 c_void_p, c_void_p]),
+    "dgvcc_dmap_batch_plan": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmapPlan)]),
+    "dgvcc_dmap_knn_sigma_batch": (c_int, [c_void_p, c_int, c_void_p, POINTER(DmapPlan), c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_size_t, c_void_p]),
+    "dgvcc_dmap_splat_batch": (c_int, [c_void_p, c_void_p, c_double, c_double, c_int, c_void_p, POINTER(DmapPlan),
+                                       c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_isw_instnorm_forward": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgvcc_isw_instnorm_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_isw_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -253,119 +253,504 @@ __device__ double combine_leaves(int first, int n, const LeafList& ll) {
     return ret;
 }
 
+// ------------------------------------------------------------------------------ batch bookkeeping
+// One launch handles a whole list of images.  The host plan (dgvcc_dmap_batch_plan) writes one row of
+// META_COLS int64 per image plus a final row of totals; kernels find the image of a CTA / head by binary
+// search over the cumulative columns (L1-resident after the first touch).
+enum MetaCol {
+    M_PT_OFF = 0,    // first head of the image in the packed head arrays
+    M_N = 1,         // heads
+    M_H = 2,
+    M_W = 3,
+    M_OUT_OFF = 4,   // first float of the image in the packed output
+    M_FTILE_OFF = 5, // first fine-tile CTA
+    M_CTASK_OFF = 6, // first coarse task (coarse tile x head chunk)
+    M_CLIST_OFF = 7, // first entry of the image's coarse lists (coarse tiles x n entries)
+    M_CTILE_OFF = 8, // first coarse tile (index into ctotal / ccount rows)
+    M_KTASK_OFF = 9, // first kNN task (query block x candidate slice)
+    M_KPART_OFF = 10,// first entry of the image's kNN partial lists (slices x n x 4)
+    M_CCOUNT_OFF = 11,
+    META_COLS = DGVCC_DMAP_META_COLS
+};
+static_assert(META_COLS == 12, "header and kernels disagree on the meta row width");
+
+constexpr int FINE_W = 32;        // fine tile: 32 columns (one warp row) x FINE_H rows
+constexpr int SPLAT_RPT = 8;      // rows per thread
+constexpr int SPLAT_WARPS = 4;
+constexpr int SPLAT_THREADS = SPLAT_WARPS * 32;
+constexpr int FINE_H = SPLAT_WARPS * SPLAT_RPT;  // 32
+constexpr int COARSE_THREADS = 256;
+constexpr int COARSE = 256;       // coarse tile side, a multiple of both fine sides
+constexpr int CHUNK = 2048;       // heads per coarse task
+constexpr int KNN_SLICE = 2048;   // candidates per batched kNN task
+constexpr int TAB = 32;           // stamps of radius < TAB read their weights from the per-head table
+constexpr int GROUP = 32;         // heads staged together by a fine tile (<= 64: masks are 64-bit)
+constexpr int GEN_MAX = 8;        // of which at most this many wide ones (radius >= TAB: weights evaluated per tile)
+
+// last row r < rows with meta[r][col] <= v (cumulative column, meta[0][col] = 0; callers pass the image rows
+// plus the row of totals, which is never selected because v < total; images that own nothing are skipped)
+__device__ __forceinline__ int find_image(const int64_t* __restrict__ meta, int rows, int col, int64_t v) {
+    int lo = 0, hi = rows;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(meta + (size_t)mid * META_COLS + col) <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------- batched kNN
+// Task = (image, block of 256 query heads, slice of KNN_SLICE candidates); the merge kernel combines the
+// per-slice lists.  Same arithmetic and (distance, index) order as the single-image kernels above.
+__global__ void __launch_bounds__(KNN_THREADS)
+dmap_knn_batch_kernel(const double2* __restrict__ pts, const int64_t* __restrict__ meta, int n_images,
+                      double* __restrict__ part_d2, int32_t* __restrict__ part_idx) {
+    __shared__ double2 cand[KNN_THREADS];
+    const int img = find_image(meta, n_images + 1, M_KTASK_OFF, blockIdx.x);
+    const int64_t* m = meta + (size_t)img * META_COLS;
+    const int n = (int)m[M_N];
+    const int slices = ceil_div(n, KNN_SLICE);
+    const int local = blockIdx.x - (int)m[M_KTASK_OFF];
+    const int slice = local % slices, qb = local / slices;
+    const double2* p = pts + m[M_PT_OFF];
+    const int i = qb * KNN_THREADS + threadIdx.x;
+    const double2 q = p[min(i, n - 1)];
+    double best[4];
+    int bidx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best[k] = INFINITY; bidx[k] = n; }
+    const int j_begin = slice * KNN_SLICE, j_end = min(n, j_begin + KNN_SLICE);
+    for (int j0 = j_begin; j0 < j_end; j0 += KNN_THREADS) {
+        __syncthreads();
+        if (j0 + threadIdx.x < j_end) cand[threadIdx.x] = p[j0 + threadIdx.x];
+        __syncthreads();
+        const int lim = min(KNN_THREADS, j_end - j0);
+#pragma unroll 4
+        for (int t = 0; t < lim; ++t) {
+            const double dx = __dsub_rn(q.x, cand[t].x);
+            const double dy = __dsub_rn(q.y, cand[t].y);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 < best[3]) knn_insert(best, bidx, d2, j0 + t);
+        }
+    }
+    if (i >= n) return;
+    const size_t o = (size_t)m[M_KPART_OFF] + ((size_t)slice * n + i) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { part_d2[o + k] = best[k]; part_idx[o + k] = bidx[k]; }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+dmap_knn_merge_batch_kernel(const double* __restrict__ part_d2, const int32_t* __restrict__ part_idx,
+                            const int64_t* __restrict__ meta, int n_images, int total_heads,
+                            int32_t* __restrict__ nn_idx, double* __restrict__ nn_dist, double* __restrict__ sigma) {
+    const int g = blockIdx.x * KNN_THREADS + threadIdx.x;
+    if (g >= total_heads) return;
+    const int img = find_image(meta, n_images + 1, M_PT_OFF, g);
+    const int64_t* m = meta + (size_t)img * META_COLS;
+    const int n = (int)m[M_N], i = g - (int)m[M_PT_OFF];
+    const int slices = ceil_div(n, KNN_SLICE);
+    double best[4];
+    int bidx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { best[k] = INFINITY; bidx[k] = n; }
+    for (int s = 0; s < slices; ++s) {
+        const size_t o = (size_t)m[M_KPART_OFF] + ((size_t)s * n + i) * 4;
+        for (int k = 0; k < 4; ++k) {
+            const double d2 = part_d2[o + k];
+            const int j = part_idx[o + k];
+            if (j < n && (d2 < best[3] || (d2 == best[3] && j < bidx[3]))) knn_insert(best, bidx, d2, j);
+        }
+    }
+    double d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        d[k] = __dsqrt_rn(best[k]);
+        if (nn_idx) nn_idx[4 * (size_t)g + k] = bidx[k];
+        if (nn_dist) nn_dist[4 * (size_t)g + k] = d[k];
+    }
+    sigma[g] = (n > 3) ? __dmul_rn(__dadd_rn(__dadd_rn(d[1], d[2]), d[3]), 0.1) : 15.0;
+}
+
+// ---------------------------------------------------------------------------------- prepare
 constexpr int PREP_WARPS = 4;
 
+// Shape of scipy's 1-D kernel for one sigma, evaluated by a whole warp (all lanes return the same values):
+// radius int(truncate*sigma + 0.5), coef -0.5/sigma^2 and the normaliser in numpy's pairwise order.
+__device__ void stamp_shape(double sd, double truncate, LeafList& ll, int lane, int& radius, double& coef, double& norm) {
+    if (!(sd > 1e-15)) {  // scipy: sigma <= 1e-15 copies the input (identity filter)
+        radius = 0; coef = 0.0; norm = 1.0;
+        return;
+    }
+    // scipy: int(truncate * float(sigma) + 0.5); clamped far beyond any image so that box arithmetic cannot
+    // overflow (a radius that large covers every pixel anyway, the weights use coef / norm)
+    const double rd = __dadd_rn(__dmul_rn(truncate, sd), 0.5);
+    radius = rd < 1.0e9 ? (int)rd : 1000000000;
+    coef = -0.5 / __dmul_rn(sd, sd);
+    const int n_el = 2 * radius + 1;
+    const int n_leaves = enumerate_leaves(-radius, n_el, ll, lane == 0);
+    double v;
+    if (n_leaves < 0) {
+        v = (lane == 0) ? pairwise_phi_sum(coef, -radius, n_el) : 0.0;  // absurdly wide kernel
+    } else {
+        __syncwarp();
+        const int group = lane >> 3, sub = lane & 7;
+        const unsigned group_mask = 0xffu << (8 * group);
+        for (int l0 = 0; l0 < n_leaves; l0 += 4) {
+            const int l = l0 + group;
+            if (l < n_leaves) {  // uniform inside a group of 8 lanes
+                const double lv = leaf_by_group(coef, ll.first[l], ll.len[l], sub, group_mask);
+                if (sub == 0) ll.sum[l] = lv;
+            }
+        }
+        __syncwarp();
+        v = (lane == 0) ? combine_leaves(-radius, n_el, ll) : 0.0;
+    }
+    norm = __shfl_sync(FULL_MASK, v, 0);
+}
+
+// Pixel of the one-hot write and the skip test of dmap_gen.py:41-44; false = the head is skipped.
+__device__ __forceinline__ bool stamp_pixel(double2 p, int height, int width, int& ix, int& iy) {
+    ix = (int)p.x;  // Python int(): truncation toward zero
+    iy = (int)p.y;
+    const bool keep = iy < height && ix < width;
+    if (iy < 0) iy += height;  // numpy wraps negative indices; the host wrapper rejects < -size like numpy
+    if (ix < 0) ix += width;
+    return keep && iy >= 0 && ix >= 0;
+}
+
+__device__ __forceinline__ int4 stamp_box(int ix, int iy, int radius) {
+    return radius < 0 ? make_int4(1, 0, 1, 0)
+                      : make_int4(max(ix - radius, -(1 << 30)), min(ix + radius, 1 << 30),
+                                  max(iy - radius, -(1 << 30)), min(iy + radius, 1 << 30));
+}
+
+// Occupancy bitmap, one bit per fine tile of the batch: set for every tile the stamp's box touches.  Tiles whose
+// bit stays clear are written as zeros by the splat kernel without looking at any list.  `step` lanes share the loop.
+__device__ __forceinline__ void mark_tiles(const int4 b, int height, int width, int64_t ftile_off,
+                                           unsigned* __restrict__ fmask, int first, int step) {
+    if (b.x > b.y) return;
+    const int tx0 = max(b.x, 0) / FINE_W, tx1 = min(b.y, width - 1) / FINE_W;
+    const int ty0 = max(b.z, 0) / FINE_H, ty1 = min(b.w, height - 1) / FINE_H;
+    if (tx1 < tx0 || ty1 < ty0) return;
+    const int nx = tx1 - tx0 + 1, total = nx * (ty1 - ty0 + 1), ftx = ceil_div(width, FINE_W);
+    for (int k = first; k < total; k += step) {
+        const int64_t g = ftile_off + (int64_t)(ty0 + k / nx) * ftx + tx0 + k % nx;
+        const unsigned bit = 1u << (g & 31);
+        if (!(fmask[g >> 5] & bit)) atomicOr(fmask + (g >> 5), bit);  // mostly already set in a crowd
+    }
+}
+
+// Adaptive sigma: one warp per head of the whole batch.  Writes the Stamp (weights), the Box (bounding box of
+// the stamp, the only thing the culling passes read; an empty box marks a skipped head), the weight table of
+// narrow stamps (radius < TAB, every head of a dense crowd: the normalised 1-D weights w[|d|] are tabulated
+// once here instead of being re-evaluated -- fp64 exp + division -- by every tile the stamp touches) and the
+// tile occupancy bits.
 __global__ void __launch_bounds__(PREP_WARPS * 32)
-dmap_prepare_kernel(const double2* __restrict__ pts, const double* __restrict__ sigma, double fixed_sigma,
-                    double truncate, int n, int height, int width, Stamp* __restrict__ stamps) {
+dmap_prepare_kernel(const double2* __restrict__ pts, const double* __restrict__ sigma, double truncate,
+                    const int64_t* __restrict__ meta, int n_images, int total_heads, Stamp* __restrict__ stamps,
+                    int4* __restrict__ boxes, double* __restrict__ wtab, unsigned* __restrict__ fmask) {
     __shared__ LeafList leaves[PREP_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * PREP_WARPS + warp;
-    if (i >= n) return;
-    LeafList& ll = leaves[warp];
-    const double2 p = pts[i];
+    if (i >= total_heads) return;
+    const int img = find_image(meta, n_images + 1, M_PT_OFF, i);
+    const int64_t* m = meta + (size_t)img * META_COLS;
+    const int height = (int)__ldg(m + M_H), width = (int)__ldg(m + M_W);
     Stamp s;
     s.pad_ = 0;
-    s.ix = (int)p.x;  // Python int(): truncation toward zero
-    s.iy = (int)p.y;
-    const bool keep = s.iy < height && s.ix < width;
-    if (s.iy < 0) s.iy += height;  // numpy wraps negative indices; the host wrapper rejects < -size like numpy
-    if (s.ix < 0) s.ix += width;
-    const double sd = sigma ? sigma[i] : fixed_sigma;
-    if (!keep || s.iy < 0 || s.ix < 0) {
+    if (!stamp_pixel(pts[i], height, width, s.ix, s.iy)) {
         s.radius = -1; s.coef = 0.0; s.norm = 1.0;
-    } else if (!(sd > 1e-15)) {  // scipy: sigma <= 1e-15 copies the input (identity filter)
-        s.radius = 0; s.coef = 0.0; s.norm = 1.0;
     } else {
-        s.radius = (int)__dadd_rn(__dmul_rn(truncate, sd), 0.5);
-        s.coef = -0.5 / __dmul_rn(sd, sd);
-        const int n_el = 2 * s.radius + 1;
-        const int n_leaves = enumerate_leaves(-s.radius, n_el, ll, lane == 0);
-        if (n_leaves < 0) {
-            s.norm = (lane == 0) ? pairwise_phi_sum(s.coef, -s.radius, n_el) : 0.0;  // absurdly wide kernel
-        } else {
-            __syncwarp();
-            const int group = lane >> 3, sub = lane & 7;
-            const unsigned group_mask = 0xffu << (8 * group);
-            for (int l0 = 0; l0 < n_leaves; l0 += 4) {
-                const int l = l0 + group;
-                if (l < n_leaves) {  // uniform inside a group of 8 lanes
-                    const double v = leaf_by_group(s.coef, ll.first[l], ll.len[l], sub, group_mask);
-                    if (sub == 0) ll.sum[l] = v;
-                }
-            }
-            __syncwarp();
-            s.norm = (lane == 0) ? combine_leaves(-s.radius, n_el, ll) : 0.0;
-        }
+        stamp_shape(sigma[i], truncate, leaves[warp], lane, s.radius, s.coef, s.norm);
     }
-    if (lane == 0) stamps[i] = s;
+    if (s.radius >= 0 && s.radius < TAB && lane <= s.radius)
+        wtab[(size_t)i * TAB + lane] = __ddiv_rn(phi(s.coef, lane), s.norm);
+    const int4 box = stamp_box(s.ix, s.iy, s.radius);
+    if (lane == 0) {
+        stamps[i] = s;
+        boxes[i] = box;
+    }
+    mark_tiles(box, height, width, __ldg(m + M_FTILE_OFF), fmask, lane, 32);
 }
 
-// ------------------------------------------------------------------------------------------ splat
-constexpr int TILE = 32;
-constexpr int SPLAT_THREADS = 256;
-constexpr int GROUP = 8;  // heads whose tile weights are staged together
+// Fixed sigma: every stamp has the same shape, so one warp evaluates it once (template Stamp + weight table) ...
+__global__ void __launch_bounds__(32)
+dmap_fixed_template_kernel(double fixed_sigma, double truncate, Stamp* __restrict__ tmpl, double* __restrict__ tmpl_tab) {
+    __shared__ LeafList ll;
+    const int lane = threadIdx.x;
+    Stamp s;
+    s.ix = s.iy = 0; s.pad_ = 0;
+    stamp_shape(fixed_sigma, truncate, ll, lane, s.radius, s.coef, s.norm);
+    tmpl_tab[lane] = (lane <= s.radius && s.radius < TAB) ? __ddiv_rn(phi(s.coef, lane), s.norm) : 0.0;
+    if (lane == 0) *tmpl = s;
+}
 
-__global__ void __launch_bounds__(SPLAT_THREADS)
-dmap_splat_kernel(const Stamp* __restrict__ stamps, int n, int height, int width, float* __restrict__ density) {
+// ... and one thread per head fills in the position.
+__global__ void __launch_bounds__(256)
+dmap_prepare_fixed_kernel(const double2* __restrict__ pts, const Stamp* __restrict__ tmpl,
+                          const double* __restrict__ tmpl_tab, const int64_t* __restrict__ meta, int n_images,
+                          int total_heads, Stamp* __restrict__ stamps, int4* __restrict__ boxes,
+                          double* __restrict__ wtab, unsigned* __restrict__ fmask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_heads) return;
+    const int img = find_image(meta, n_images + 1, M_PT_OFF, i);
+    const int64_t* m = meta + (size_t)img * META_COLS;
+    const int height = (int)__ldg(m + M_H), width = (int)__ldg(m + M_W);
+    Stamp s = *tmpl;
+    const int radius = s.radius;
+    if (!stamp_pixel(pts[i], height, width, s.ix, s.iy)) {
+        s.radius = -1; s.coef = 0.0; s.norm = 1.0;
+    } else if (radius < TAB) {
+        for (int d = 0; d <= radius; ++d) wtab[(size_t)i * TAB + d] = __ldg(tmpl_tab + d);
+    }
+    const int4 box = stamp_box(s.ix, s.iy, s.radius);
+    stamps[i] = s;
+    boxes[i] = box;
+    mark_tiles(box, height, width, __ldg(m + M_FTILE_OFF), fmask, 0, 1);
+}
+
+// --------------------------------------------------------------------- two-level culling + splat
+__device__ __forceinline__ bool box_hits(const int4 b, int x0, int y0, int w, int h) {
+    return b.x <= b.y && b.y >= x0 && b.x < x0 + w && b.w >= y0 && b.z < y0 + h;
+}
+
+// Ordered compaction of one flag per thread across a CTA of THREADS; returns the slot of a set flag
+// and the CTA total.  Two __syncthreads; warp_cnt is reused by the next call only after a later barrier.
+template <int THREADS>
+__device__ __forceinline__ int cta_compact(bool hit, int* warp_cnt, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned ballot = __ballot_sync(FULL_MASK, hit);
+    __syncthreads();  // previous readers of warp_cnt are done
+    if (lane == 0) warp_cnt[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) {
+        const int c = warp_cnt[w];
+        if (w < warp) before += c;
+        total += c;
+    }
+    return before + __popc(ballot & ((1u << lane) - 1u));
+}
+
+// Coarse pass.  Task = (image, coarse tile, chunk of CHUNK heads).  WRITE = false counts the chunk's heads
+// whose box touches the coarse tile; WRITE = true repeats the scan and writes their indices, in index order,
+// behind the heads of the lower chunks (counts summed on the fly), so that every coarse tile ends up with one
+// contiguous ordered list; the last chunk also stores the list's length.
+template <bool WRITE>
+__global__ void __launch_bounds__(COARSE_THREADS)
+dmap_coarse_kernel(const int4* __restrict__ boxes, const int64_t* __restrict__ meta, int n_images,
+                   int32_t* __restrict__ ccount, int32_t* __restrict__ ctotal, int32_t* __restrict__ clist) {
+    __shared__ int warp_cnt[COARSE_THREADS / 32];
+    const int img = find_image(meta, n_images + 1, M_CTASK_OFF, blockIdx.x);
+    const int64_t* m = meta + (size_t)img * META_COLS;
+    const int n = (int)m[M_N], width = (int)m[M_W];
+    const int nchunks = ceil_div(n, CHUNK), ctx = ceil_div(width, COARSE);
+    const int local = blockIdx.x - (int)m[M_CTASK_OFF];
+    const int chunk = local % nchunks, ct = local / nchunks;
+    const int x0 = (ct % ctx) * COARSE, y0 = (ct / ctx) * COARSE;
+    const int4* b = boxes + m[M_PT_OFF];
+    int32_t* cnt_row = ccount + m[M_CCOUNT_OFF] + (size_t)ct * nchunks;
+    int pos = 0;
+    int32_t* out = nullptr;
+    if (WRITE) {
+        for (int c = 0; c < chunk; ++c) pos += cnt_row[c];
+        out = clist + m[M_CLIST_OFF] + (size_t)ct * n;
+    }
+    const int i_end = min(n, (chunk + 1) * CHUNK);
+    int count = 0;
+    for (int base = chunk * CHUNK; base < i_end; base += COARSE_THREADS) {
+        const int i = base + threadIdx.x;
+        const bool hit = i < i_end && box_hits(__ldg(b + i), x0, y0, COARSE, COARSE);
+        int total;
+        const int slot = cta_compact<COARSE_THREADS>(hit, warp_cnt, total);
+        if (WRITE && hit) out[pos + count + slot] = i;
+        count += total;
+    }
+    if (threadIdx.x == 0) {
+        if (!WRITE) cnt_row[chunk] = count;
+        else if (chunk == nchunks - 1) ctotal[m[M_CTILE_OFF] + ct] = pos + count;
+    }
+}
+
+// Fine pass: one CTA (4 warps) per 32 x 32 output tile; warp w owns the band of rows [8w, 8w + 8), lane = column.
+// Warp 0 decodes the tile (image, position, length of the coarse list) once for the CTA.  A tile whose
+// occupancy bit is clear stores zeros at once.  Otherwise the CTA walks the ordered list of its coarse tile and
+// keeps the heads whose stamp touches the fine tile (ordered compaction again).  Heads are staged GROUP at a
+// time: narrow stamps copy their weight table w[|d|] (and its fl32-rounded twin), wide ones (at most GEN_MAX
+// per group) get their 32 row and 32 column weights evaluated for this tile.  Each warp then picks, by ballot,
+// the staged heads that reach its band and accumulates fl32(f64(fl32(wy)) * wx) per pixel in fp32, in head
+// order.  Rows and columns a stamp does not reach add (float)(0 * w) = +0, which changes nothing (the sums are
+// never -0), so they are skipped.  Every pixel of the packed output is written exactly once, coalesced; zero
+// fill fused.
+struct __align__(16) TileDesc {  // 64 bytes, written by dmap_tile_setup_kernel, read whole by every thread of the tile's CTA
+    int x0, y0, width, height;
+    int cnt, n, pad0_, pad1_;      // cnt: length of the coarse tile's list, 0 when no stamp touches the fine tile
+    long long out_off, clist_off;
+    long long pt_off, pad2_;
+};
+static_assert(sizeof(TileDesc) == 64, "TileDesc is read as four 16-byte words");
+
+// One thread per fine tile of the batch: image lookup, tile position, occupancy bit, coarse-list length.
+__global__ void __launch_bounds__(256)
+dmap_tile_setup_kernel(const int64_t* __restrict__ meta, int n_images, int fine_tiles, const unsigned* __restrict__ fmask,
+                       const int32_t* __restrict__ ctotal, int have_heads, TileDesc* __restrict__ desc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= fine_tiles) return;
+    const int img = find_image(meta, n_images + 1, M_FTILE_OFF, t);
+    const int64_t* m = meta + (size_t)img * META_COLS;
+    TileDesc d;
+    d.n = (int)m[M_N]; d.height = (int)m[M_H]; d.width = (int)m[M_W];
+    const int ftx = ceil_div(d.width, FINE_W);
+    const int local = t - (int)m[M_FTILE_OFF];
+    d.x0 = (local % ftx) * FINE_W; d.y0 = (local / ftx) * FINE_H;
+    d.pt_off = m[M_PT_OFF]; d.out_off = m[M_OUT_OFF];
+    d.cnt = 0; d.clist_off = 0; d.pad0_ = d.pad1_ = 0; d.pad2_ = 0;
+    if (have_heads && d.n > 0 && ((fmask[t >> 5] >> (t & 31)) & 1u)) {
+        const int ct = (d.y0 / COARSE) * ceil_div(d.width, COARSE) + d.x0 / COARSE;
+        d.cnt = ctotal[m[M_CTILE_OFF] + ct];
+        d.clist_off = m[M_CLIST_OFF] + (long long)ct * d.n;
+    }
+    desc[t] = d;
+}
+
+__global__ void __launch_bounds__(SPLAT_THREADS, 9)
+dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ wtab, const int4* __restrict__ boxes,
+                  const TileDesc* __restrict__ desc, const int32_t* __restrict__ clist, float* __restrict__ density) {
     __shared__ int list[SPLAT_THREADS];
+    __shared__ int4 lbox[SPLAT_THREADS];     // boxes of the listed heads
     __shared__ int warp_cnt[SPLAT_THREADS / 32];
-    __shared__ double wy[GROUP][TILE];  // fl32-rounded row weights, widened again (exact)
-    __shared__ double wx[GROUP][TILE];
+    __shared__ double tab[GROUP][TAB];       // w[|d|]
+    __shared__ double tabf[GROUP][TAB];      // (double)(float)w[|d|]: the first filter pass stores float32
+    __shared__ double gwy[GEN_MAX][FINE_H];  // wide stamps: fl32-rounded row weights, widened again (exact)
+    __shared__ double gwx[GEN_MAX][FINE_W];
+    __shared__ int gen_head[GEN_MAX];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // pixels (y0 + warp + 8k, x0 + lane)
-
-    for (int base = 0; base < n; base += SPLAT_THREADS) {
-        // heads of this batch whose stamp overlaps the tile, compacted in index order
-        const int i = base + tid;
-        bool hit = false;
-        if (i < n) {
-            const Stamp s = stamps[i];
-            hit = s.radius >= 0 && s.ix + s.radius >= x0 && s.ix - s.radius < x0 + TILE &&
-                  s.iy + s.radius >= y0 && s.iy - s.radius < y0 + TILE;
-        }
-        const unsigned int ballot = __ballot_sync(FULL_MASK, hit);
-        if (lane == 0) warp_cnt[warp] = __popc(ballot);
-        __syncthreads();
-        int before = 0, total = 0;
+    const int4* dp = reinterpret_cast<const int4*>(desc + blockIdx.x);
+    const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+    const longlong2 d2 = __ldg(reinterpret_cast<const longlong2*>(dp + 2));
+    const int x0 = d0.x, y0 = d0.y, width = d0.z, height = d0.w, cnt = d1.x;
+    const int yb = y0 + SPLAT_RPT * warp;  // first row of this warp's band
+    const int x = x0 + lane;
+    float acc[SPLAT_RPT];  // pixels (yb + k, x)
 #pragma unroll
-        for (int w = 0; w < SPLAT_THREADS / 32; ++w) {
-            if (w < warp) before += warp_cnt[w];
-            total += warp_cnt[w];
-        }
-        if (hit) list[before + __popc(ballot & ((1u << lane) - 1u))] = i;
-        __syncthreads();
+    for (int k = 0; k < SPLAT_RPT; ++k) acc[k] = 0.f;
 
-        for (int g0 = 0; g0 < total; g0 += GROUP) {
-            const int gcnt = min(GROUP, total - g0);
-            // stage the tile's 32 row and 32 column weights of each head of the group
-            for (int k = tid; k < gcnt * 2 * TILE; k += SPLAT_THREADS) {
-                const int h = k / (2 * TILE), which = (k / TILE) & 1, off = k % TILE;
-                const Stamp s = stamps[list[g0 + h]];
-                const int d = which ? (x0 + off - s.ix) : (y0 + off - s.iy);
-                double w = 0.0;
-                if (d >= -s.radius && d <= s.radius) w = __ddiv_rn(phi(s.coef, d), s.norm);
-                if (which) wx[h][off] = w;
-                else wy[h][off] = (double)(float)w;  // first filter pass stores float32 (output dtype)
+    if (cnt > 0) {
+        const long long pt_off = __ldg(reinterpret_cast<const long long*>(dp + 3));
+        const int32_t* cl = clist + d2.y;
+        const int4* bx = boxes + pt_off;
+        const Stamp* st = stamps + pt_off;
+        const double* wt = wtab + (size_t)pt_off * TAB;
+        for (int base = 0; base < cnt; base += SPLAT_THREADS) {
+            int i = -1;
+            int4 b = make_int4(1, 0, 1, 0);
+            bool hit = false;
+            if (base + tid < cnt) {
+                i = __ldg(cl + base + tid);
+                b = __ldg(bx + i);
+                hit = box_hits(b, x0, y0, FINE_W, FINE_H);
             }
+            int total;
+            const int slot = cta_compact<SPLAT_THREADS>(hit, warp_cnt, total);
+            if (hit) { list[slot] = i; lbox[slot] = b; }
             __syncthreads();
-            for (int h = 0; h < gcnt; ++h) {
-                const double cx = wx[h][lane];
+            for (int c0 = 0; c0 < total; c0 += GROUP) {
+                const int ccnt = min(GROUP, total - c0);
+                // which heads of the chunk are wide (a box narrower than 2*TAB cannot be a clamped one, so centre
+                // and radius of narrow stamps follow from the box)
+                unsigned long long wide_mask = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    acc[k] = __fadd_rn(acc[k], (float)__dmul_rn(wy[h][warp + 8 * k], cx));
+                for (int w = 0; w < GROUP / 32; ++w) {
+                    const int t = 32 * w + lane;
+                    const bool wide = t < ccnt && (lbox[c0 + t].y - lbox[c0 + t].x) >= 2 * TAB;
+                    wide_mask |= (unsigned long long)__ballot_sync(FULL_MASK, wide) << (32 * w);
+                }
+                // a chunk with few wide heads is one group; otherwise groups of GEN_MAX heads
+                const int gs = __popcll(wide_mask) <= GEN_MAX ? GROUP : GEN_MAX;
+                for (int g0 = 0; g0 < ccnt; g0 += gs) {
+                    const int g1 = min(ccnt, g0 + gs);
+                    const unsigned long long range = (g1 - g0 == 64) ? ~0ull : (((1ull << (g1 - g0)) - 1ull) << g0);
+                    const unsigned long long wide_here = wide_mask & range;
+                    const int n_wide = __popcll(wide_here);
+                    // narrow heads: copy the weight tables (a warp reads one head's table per step, 8 heads in flight)
+#pragma unroll 2
+                    for (int t = g0 + warp; t < g1; t += SPLAT_WARPS) {
+                        const int r = (lbox[c0 + t].y - lbox[c0 + t].x) >> 1;
+                        if (lane <= r && r < TAB) {
+                            const double w = __ldg(wt + (size_t)list[c0 + t] * TAB + lane);
+                            tab[t][lane] = w;
+                            tabf[t][lane] = (double)(float)w;
+                        }
+                    }
+                    if (tid >= g0 && tid < g1 && ((wide_mask >> tid) & 1ull))
+                        gen_head[__popcll(wide_here & ((1ull << tid) - 1ull))] = tid;
+                    if (n_wide) {
+                        __syncthreads();
+                        for (int k = tid; k < n_wide * (FINE_H + FINE_W); k += SPLAT_THREADS) {
+                            const int gsl = k / (FINE_H + FINE_W), off = k % (FINE_H + FINE_W);
+                            const Stamp s = st[list[c0 + gen_head[gsl]]];
+                            const bool is_x = off >= FINE_H;
+                            const int d = is_x ? (x0 + off - FINE_H - s.ix) : (y0 + off - s.iy);
+                            double w = 0.0;
+                            if (d >= -s.radius && d <= s.radius) w = __ddiv_rn(phi(s.coef, d), s.norm);
+                            if (is_x) gwx[gsl][off - FINE_H] = w;
+                            else gwy[gsl][off] = (double)(float)w;
+                        }
+                    }
+                    __syncthreads();
+                    // accumulate, in head order, the staged heads that reach this warp's band
+                    for (int j0 = g0; j0 < g1; j0 += 32) {
+                        const int t = j0 + lane;
+                        bool reach = false;
+                        if (t < g1) {
+                            const int4 b = lbox[c0 + t];
+                            reach = b.w >= yb && b.z < yb + SPLAT_RPT;
+                        }
+                        unsigned todo = __ballot_sync(FULL_MASK, reach);
+                        while (todo) {
+                            const int hd = j0 + __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const int4 b = lbox[c0 + hd];
+                            const int r = (b.y - b.x) >> 1;
+                            if (r < TAB) {
+                                const int dx = abs(x - ((b.x + b.y) >> 1));
+                                if (__any_sync(FULL_MASK, dx <= r)) {
+                                    const double cx = dx <= r ? tab[hd][dx] : 0.0;
+                                    const int dy0 = yb - ((b.z + b.w) >> 1);
+#pragma unroll
+                                    for (int k = 0; k < SPLAT_RPT; ++k) {
+                                        const int dy = abs(dy0 + k);
+                                        if (dy <= r)  // warp-uniform
+                                            acc[k] = __fadd_rn(acc[k], (float)__dmul_rn(tabf[hd][dy], cx));
+                                    }
+                                }
+                            } else {
+                                const int gsl = __popcll(wide_here & ((1ull << hd) - 1ull));
+                                const double cx = gwx[gsl][lane];
+#pragma unroll
+                                for (int k = 0; k < SPLAT_RPT; ++k) {
+                                    const double ry = gwy[gsl][SPLAT_RPT * warp + k];
+                                    if (ry != 0.0) acc[k] = __fadd_rn(acc[k], (float)__dmul_rn(ry, cx));  // warp-uniform
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
             }
-            __syncthreads();
         }
     }
-    const int x = x0 + lane;
-    if (x < width) {
+    if (x < width && yb < height) {
+        float* out = density + d2.x + (size_t)yb * width + x;
+        if (yb + SPLAT_RPT <= height) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int y = y0 + warp + 8 * k;
-            if (y < height) density[(size_t)y * width + x] = acc[k];
+            for (int k = 0; k < SPLAT_RPT; ++k) out[(size_t)k * width] = acc[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < SPLAT_RPT; ++k)
+                if (yb + k < height) out[(size_t)k * width] = acc[k];
         }
     }
 }
@@ -408,23 +793,118 @@ extern "C" int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx
     return (int)cudaGetLastError();
 }
 
-extern "C" size_t dgvcc_dmap_workspace_bytes(int n) { return (size_t)(n > 0 ? n : 1) * sizeof(Stamp); }
+// ---- batch plan (host only) ---------------------------------------------------------------------
+extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const int32_t* widths, const int32_t* counts,
+                                     int64_t* meta, dgvcc_dmap_plan* plan) {
+    if (n_images <= 0 || !heights || !widths || !counts || !meta || !plan) return DGVCC_ERR_ARG;
+    int64_t acc[META_COLS] = {0};
+    for (int i = 0; i <= n_images; ++i) {
+        int64_t* m = meta + (size_t)i * META_COLS;
+        m[M_PT_OFF] = acc[M_PT_OFF]; m[M_OUT_OFF] = acc[M_OUT_OFF]; m[M_FTILE_OFF] = acc[M_FTILE_OFF];
+        m[M_CTASK_OFF] = acc[M_CTASK_OFF]; m[M_CLIST_OFF] = acc[M_CLIST_OFF]; m[M_CTILE_OFF] = acc[M_CTILE_OFF];
+        m[M_KTASK_OFF] = acc[M_KTASK_OFF]; m[M_KPART_OFF] = acc[M_KPART_OFF]; m[M_CCOUNT_OFF] = acc[M_CCOUNT_OFF];
+        if (i == n_images) { m[M_N] = m[M_H] = m[M_W] = 0; break; }
+        const int64_t n = counts[i], h = heights[i], w = widths[i];
+        if (n < 0 || h <= 0 || w <= 0) return DGVCC_ERR_ARG;
+        m[M_N] = n; m[M_H] = h; m[M_W] = w;
+        const int64_t ctiles = (int64_t)ceil_div((int)w, COARSE) * ceil_div((int)h, COARSE);
+        const int64_t nchunks = ceil_div((int)n, CHUNK), slices = ceil_div((int)n, KNN_SLICE);
+        acc[M_PT_OFF] += n;
+        acc[M_OUT_OFF] += h * w;
+        acc[M_FTILE_OFF] += (int64_t)ceil_div((int)w, FINE_W) * ceil_div((int)h, FINE_H);
+        acc[M_CTASK_OFF] += ctiles * nchunks;
+        acc[M_CCOUNT_OFF] += ctiles * nchunks;
+        acc[M_CLIST_OFF] += ctiles * n;
+        acc[M_CTILE_OFF] += ctiles;
+        acc[M_KTASK_OFF] += (int64_t)ceil_div((int)n, KNN_THREADS) * slices;
+        acc[M_KPART_OFF] += slices * n * 4;
+    }
+    if (acc[M_FTILE_OFF] > 0x7fffffffLL || acc[M_CTASK_OFF] > 0x7fffffffLL || acc[M_KTASK_OFF] > 0x7fffffffLL ||
+        acc[M_PT_OFF] > 0x7fffffffLL)
+        return DGVCC_ERR_UNSUPPORTED;
+    plan->total_heads = acc[M_PT_OFF];
+    plan->total_pixels = acc[M_OUT_OFF];
+    plan->fine_tiles = acc[M_FTILE_OFF];
+    plan->coarse_tasks = acc[M_CTASK_OFF];
+    plan->knn_tasks = acc[M_KTASK_OFF];
+    size_t off = 0;
+    const int64_t heads = acc[M_PT_OFF] > 0 ? acc[M_PT_OFF] : 1;
+    plan->off_stamps = (int64_t)off; off = align_up(off + (size_t)heads * sizeof(Stamp), 256);
+    plan->off_boxes = (int64_t)off;  off = align_up(off + (size_t)heads * sizeof(int4), 256);
+    plan->off_wtab = (int64_t)off;   off = align_up(off + (size_t)heads * TAB * sizeof(double), 256);
+    plan->off_fmask = (int64_t)off;  off = align_up(off + (size_t)(acc[M_FTILE_OFF] / 32 + 1) * 4, 256);
+    plan->off_tmpl = (int64_t)off;   off = align_up(off + sizeof(Stamp) + TAB * sizeof(double), 256);
+    plan->off_desc = (int64_t)off;   off = align_up(off + (size_t)acc[M_FTILE_OFF] * sizeof(TileDesc), 256);
+    plan->off_ccount = (int64_t)off; off = align_up(off + (size_t)(acc[M_CCOUNT_OFF] + 1) * 4, 256);
+    plan->off_ctotal = (int64_t)off; off = align_up(off + (size_t)(acc[M_CTILE_OFF] + 1) * 4, 256);
+    plan->off_clist = (int64_t)off;  off = align_up(off + (size_t)(acc[M_CLIST_OFF] + 1) * 4, 256);
+    plan->splat_workspace_bytes = (int64_t)off;
+    off = 0;
+    plan->off_knn_d2 = 0;            off = align_up((size_t)(acc[M_KPART_OFF] + 1) * 8, 256);
+    plan->off_knn_idx = (int64_t)off; off = align_up(off + (size_t)(acc[M_KPART_OFF] + 1) * 4, 256);
+    plan->knn_workspace_bytes = (int64_t)off;
+    return DGVCC_OK;
+}
 
-extern "C" int dgvcc_dmap_splat(const double* pts_xy, const double* sigma, double fixed_sigma, double truncate, int n,
-                                int height, int width, void* workspace, size_t workspace_bytes, float* density,
-                                void* stream) {
-    if (n < 0 || height <= 0 || width <= 0 || !density) return DGVCC_ERR_ARG;
-    if (n > 0 && (!pts_xy || !workspace)) return DGVCC_ERR_ARG;
-    if (workspace_bytes < dgvcc_dmap_workspace_bytes(n)) return DGVCC_ERR_WORKSPACE;
+extern "C" int dgvcc_dmap_knn_sigma_batch(const double* pts_xy, int n_images, const int64_t* meta,
+                                          const dgvcc_dmap_plan* plan, int32_t* nn_idx, double* nn_dist, double* sigma,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_images <= 0 || !meta || !plan) return DGVCC_ERR_ARG;
+    if (plan->total_heads == 0) return DGVCC_OK;
+    if (!pts_xy || !sigma || !workspace) return DGVCC_ERR_ARG;
+    if (workspace_bytes < (size_t)plan->knn_workspace_bytes) return DGVCC_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* part_d2 = (double*)((char*)workspace + plan->off_knn_d2);
+    int32_t* part_idx = (int32_t*)((char*)workspace + plan->off_knn_idx);
+    dmap_knn_batch_kernel<<<(unsigned)plan->knn_tasks, KNN_THREADS, 0, st>>>((const double2*)pts_xy, meta, n_images,
+                                                                             part_d2, part_idx);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    dmap_knn_merge_batch_kernel<<<ceil_div((int)plan->total_heads, KNN_THREADS), KNN_THREADS, 0, st>>>(
+        part_d2, part_idx, meta, n_images, (int)plan->total_heads, nn_idx, nn_dist, sigma);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma, double fixed_sigma, double truncate,
+                                      int n_images, const int64_t* meta, const dgvcc_dmap_plan* plan, void* workspace,
+                                      size_t workspace_bytes, float* density, void* stream) {
+    if (n_images <= 0 || !meta || !plan || !density || !workspace) return DGVCC_ERR_ARG;
+    if (plan->total_heads > 0 && !pts_xy) return DGVCC_ERR_ARG;
+    if (workspace_bytes < (size_t)plan->splat_workspace_bytes) return DGVCC_ERR_WORKSPACE;
     if (!sigma && !(fixed_sigma >= 0.0)) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    Stamp* stamps = (Stamp*)workspace;
-    if (n > 0) {
-        dmap_prepare_kernel<<<ceil_div(n, PREP_WARPS), PREP_WARPS * 32, 0, st>>>((const double2*)pts_xy, sigma, fixed_sigma, truncate, n,
-                                                              height, width, stamps);
+    char* ws = (char*)workspace;
+    Stamp* stamps = (Stamp*)(ws + plan->off_stamps);
+    int4* boxes = (int4*)(ws + plan->off_boxes);
+    double* wtab = (double*)(ws + plan->off_wtab);
+    unsigned* fmask = (unsigned*)(ws + plan->off_fmask);
+    Stamp* tmpl = (Stamp*)(ws + plan->off_tmpl);
+    double* tmpl_tab = (double*)(ws + plan->off_tmpl + sizeof(Stamp));
+    int32_t* ccount = (int32_t*)(ws + plan->off_ccount);
+    int32_t* ctotal = (int32_t*)(ws + plan->off_ctotal);
+    int32_t* clist = (int32_t*)(ws + plan->off_clist);
+    const int heads = (int)plan->total_heads;
+    if (heads > 0) {
+        DGVCC_RETURN_IF_CUDA(cudaMemsetAsync(fmask, 0, (size_t)(plan->fine_tiles / 32 + 1) * 4, st));
+        if (sigma) {
+            dmap_prepare_kernel<<<ceil_div(heads, PREP_WARPS), PREP_WARPS * 32, 0, st>>>(
+                (const double2*)pts_xy, sigma, truncate, meta, n_images, heads, stamps, boxes, wtab, fmask);
+        } else {
+            dmap_fixed_template_kernel<<<1, 32, 0, st>>>(fixed_sigma, truncate, tmpl, tmpl_tab);
+            dmap_prepare_fixed_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, tmpl, tmpl_tab, meta,
+                                                                            n_images, heads, stamps, boxes, wtab, fmask);
+        }
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+        dmap_coarse_kernel<false><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
+                                                                                          ctotal, clist);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+        dmap_coarse_kernel<true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
+                                                                                         ctotal, clist);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
-    dmap_splat_kernel<<<dim3(ceil_div(width, TILE), ceil_div(height, TILE)), SPLAT_THREADS, 0, st>>>(
-        stamps, n, height, width, density);
+    TileDesc* desc = (TileDesc*)(ws + plan->off_desc);
+    dmap_tile_setup_kernel<<<ceil_div((int)plan->fine_tiles, 256), 256, 0, st>>>(meta, n_images, (int)plan->fine_tiles, fmask,
+                                                                                 ctotal, heads > 0, desc);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    dmap_splat_kernel<<<(unsigned)plan->fine_tiles, SPLAT_THREADS, 0, st>>>(stamps, wtab, boxes, desc, clist, density);
     return (int)cudaGetLastError();
 }

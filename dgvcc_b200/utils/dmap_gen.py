@@ -12,6 +12,7 @@ Host numpy in / host numpy out like the reference; the work runs in csrc/dmap_ke
 CUDA is initialised lazily on first call, so the functions are safe to import before a fork.
 """
 import argparse
+import ctypes
 import os
 from glob import glob
 
@@ -60,33 +61,62 @@ def knn_sigma(points, device=None):
     return dist.cpu().numpy(), idx.cpu().numpy().astype(np.int64), sigma.cpu().numpy()
 
 
+class _Plan:
+    """Host plan of one batched launch set (include/dgvcc_b200.h: dgvcc_dmap_batch_plan)."""
+
+    def __init__(self, shapes, counts):
+        lib = _native.lib()
+        b = len(shapes)
+        heights = np.ascontiguousarray([int(s[0]) for s in shapes], dtype=np.int32)
+        widths = np.ascontiguousarray([int(s[1]) for s in shapes], dtype=np.int32)
+        cnts = np.ascontiguousarray(counts, dtype=np.int32)
+        self.meta = np.zeros((b + 1, _native.DMAP_META_COLS), dtype=np.int64)
+        self.plan = _native.DmapPlan()
+        _native.check(lib.dgvcc_dmap_batch_plan(b, heights.ctypes.data, widths.ctypes.data, cnts.ctypes.data,
+                                                self.meta.ctypes.data, ctypes.byref(self.plan)),
+                      "dgvcc_dmap_batch_plan")
+        self.n_images = b
+        self.out_off = self.meta[:, 4]
+        self.pt_off = self.meta[:, 0]
+
+
+def _density_batch_device(shapes, pts_list, adaptive, dev):
+    """(packed device tensor [sum H*W] f32, per-image offsets into it) for a list of images; ``pts_list`` holds
+    host float64 [N,2] arrays.  Images are launched in order of falling head count -- the crowded ones, whose
+    tiles take longest, start first -- so the packed layout follows that order, not the caller's."""
+    lib = _native.lib()
+    counts = np.array([len(p) for p in pts_list], dtype=np.int64)
+    order = np.argsort(-counts, kind="stable")
+    plan = _Plan([shapes[i] for i in order], counts[order])
+    pl = plan.plan
+    stream = _native.stream_ptr(dev)
+    meta = torch.from_numpy(plan.meta).pin_memory().to(dev, non_blocking=True)
+    out = torch.empty((pl.total_pixels,), dtype=torch.float32, device=dev)
+    ws = torch.empty((pl.splat_workspace_bytes,), dtype=torch.uint8, device=dev)
+    d_pts = sigma = None
+    if pl.total_heads:
+        packed = np.concatenate([pts_list[i] for i in order if counts[i]], axis=0)
+        d_pts = torch.from_numpy(np.ascontiguousarray(packed)).pin_memory().to(dev, non_blocking=True)
+        if adaptive:
+            sigma = torch.empty((pl.total_heads,), dtype=torch.float64, device=dev)
+            kws = torch.empty((pl.knn_workspace_bytes,), dtype=torch.uint8, device=dev)
+            _native.check(lib.dgvcc_dmap_knn_sigma_batch(_native.ptr(d_pts), plan.n_images, _native.ptr(meta),
+                                                         ctypes.byref(pl), None, None, _native.ptr(sigma),
+                                                         _native.ptr(kws), pl.knn_workspace_bytes, stream),
+                          "dgvcc_dmap_knn_sigma_batch")
+    _native.check(lib.dgvcc_dmap_splat_batch(
+        _native.ptr(d_pts), _native.ptr(sigma), FIXED_SIGMA, ADAPTIVE_TRUNCATE if adaptive else FIXED_TRUNCATE,
+        plan.n_images, _native.ptr(meta), ctypes.byref(pl), _native.ptr(ws), pl.splat_workspace_bytes,
+        _native.ptr(out), stream), "dgvcc_dmap_splat_batch")
+    offsets = np.empty(len(shapes), dtype=np.int64)
+    offsets[order] = plan.out_off[:-1]
+    return out, offsets
+
+
 def _density_device(height, width, pts, adaptive, dev):
     """Device tensor [H,W] f32 for one image; ``pts`` is a host float64 [N,2] array."""
-    lib = _native.lib()
-    n = len(pts)
-    out = torch.empty((height, width), dtype=torch.float32, device=dev)
-    stream = _native.stream_ptr(dev)
-    if n == 0:
-        d_pts = sigma = ws = None
-        ws_bytes = lib.dgvcc_dmap_workspace_bytes(0)
-    else:
-        d_pts = torch.from_numpy(pts).pin_memory().to(dev, non_blocking=True)
-        ws_bytes = lib.dgvcc_dmap_workspace_bytes(n)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        sigma = None
-        if adaptive:
-            idx = torch.empty((n, 4), dtype=torch.int32, device=dev)
-            dist = torch.empty((n, 4), dtype=torch.float64, device=dev)
-            sigma = torch.empty((n,), dtype=torch.float64, device=dev)
-            kws_bytes = lib.dgvcc_dmap_knn_workspace_bytes(n)
-            kws = torch.empty((kws_bytes,), dtype=torch.uint8, device=dev)
-            _native.check(lib.dgvcc_dmap_knn_sigma(_native.ptr(d_pts), n, _native.ptr(idx), _native.ptr(dist),
-                                                   _native.ptr(sigma), _native.ptr(kws), kws_bytes, stream),
-                          "dgvcc_dmap_knn_sigma")
-    _native.check(lib.dgvcc_dmap_splat(
-        _native.ptr(d_pts), _native.ptr(sigma), FIXED_SIGMA, ADAPTIVE_TRUNCATE if adaptive else FIXED_TRUNCATE, n,
-        height, width, _native.ptr(ws), ws_bytes, _native.ptr(out), stream), "dgvcc_dmap_splat")
-    return out
+    out, _ = _density_batch_device([(height, width)], [pts], adaptive, dev)
+    return out.view(height, width)
 
 
 def _density(img, points, adaptive, device=None):
@@ -112,17 +142,19 @@ def gaussian_filter_density_fixed(img, points, device=None):
 
 
 def gaussian_filter_density_batch(shapes, points_list, fixed=False, device=None):
-    """Many images back to back on one stream, one synchronisation at the end; returns a list of [H,W] arrays."""
+    """A list of images through ONE set of launches (kNN, prepare, two culling passes, splat), one packed
+    device-to-host copy and one synchronisation; returns a list of [H,W] float32 arrays (views of one buffer)."""
     dev = _device(device)
-    outs = []
-    for (h, w), pts in zip(shapes, points_list):
-        h, w = int(h), int(w)
-        host = torch.empty((h, w), dtype=torch.float32).pin_memory()
-        p = _check_points(pts, h, w) if len(pts) else np.zeros((0, 2))
-        host.copy_(_density_device(h, w, p, not fixed, dev), non_blocking=True)
-        outs.append(host)
+    shapes = [(int(h), int(w)) for h, w in shapes]
+    if not shapes:
+        return []
+    pts = [_check_points(p, h, w) if len(p) else np.zeros((0, 2)) for (h, w), p in zip(shapes, points_list)]
+    out, offsets = _density_batch_device(shapes, pts, not fixed, dev)
+    host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+    host.copy_(out, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
-    return [o.numpy() for o in outs]
+    flat = host.numpy()
+    return [flat[o:o + h * w].reshape(h, w) for o, (h, w) in zip(offsets, shapes)]
 
 
 def _image_shape(img_fn):

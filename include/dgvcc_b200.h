@@ -146,16 +146,44 @@ size_t dgvcc_dmap_knn_workspace_bytes(int n);
 int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx, double* nn_dist, double* sigma,
                          void* workspace, size_t workspace_bytes, void* stream);
 
-size_t dgvcc_dmap_workspace_bytes(int n);
+/* ---- batched entry points: a list of images per launch --------------------------------
+ * The reference generates one map per call inside a Pool(8) (dmap_gen.py:97-117); here a whole list
+ * of images (a single one included) goes through one set of launches.  Heads of all images are packed
+ * back to back (pts_xy [total_heads,2] f64, sigma [total_heads] f64), the maps likewise
+ * (density: image i occupies [out_off_i, out_off_i + H_i*W_i) floats, row-major [H_i,W_i]).
+ *
+ * dgvcc_dmap_batch_plan (host only, no CUDA call) fills
+ *   meta  [(n_images+1) x DGVCC_DMAP_META_COLS] int64, one row per image + a row of totals:
+ *         head offset, heads, H, W, output offset, and the launch bookkeeping of the kernels
+ *         (first fine tile / coarse task / coarse-list entry / coarse tile / kNN task / kNN partial);
+ *         the caller copies it to the device and passes that DEVICE pointer to the launchers;
+ *   plan  totals and the workspace layouts (host struct, passed back by pointer).            */
+#define DGVCC_DMAP_META_COLS 12
+typedef struct dgvcc_dmap_plan {
+    int64_t total_heads, total_pixels, fine_tiles, coarse_tasks, knn_tasks;
+    int64_t off_stamps, off_boxes, off_wtab, off_fmask, off_tmpl, off_desc, off_ccount, off_ctotal, off_clist, splat_workspace_bytes;
+    int64_t off_knn_d2, off_knn_idx, knn_workspace_bytes;
+} dgvcc_dmap_plan;
 
-/* density [height,width] f32 = sum over heads, in index order, of
+int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const int32_t* widths, const int32_t* counts,
+                          int64_t* meta, dgvcc_dmap_plan* plan);
+
+/* dgvcc_dmap_knn_sigma for every image of the batch (neighbours are searched inside each image only).
+ * nn_idx [total_heads,4] / nn_dist [total_heads,4] may be NULL when only sigma is wanted. */
+int dgvcc_dmap_knn_sigma_batch(const double* pts_xy, int n_images, const int64_t* meta, const dgvcc_dmap_plan* plan,
+                               int32_t* nn_idx, double* nn_dist, double* sigma, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* density map of every image = sum over its heads, in index order, of
  * scipy.ndimage.gaussian_filter(one_hot, sigma_i, truncate=truncate, mode='constant')
  * (dmap_gen.py:38-49 / 71-79).  sigma == NULL uses fixed_sigma for every head
  * (the fixed variant: sigma 4, truncate 7/4).  Heads with int(y) >= height or
- * int(x) >= width are skipped (dmap_gen.py:41-44).  Every pixel is written. */
-int dgvcc_dmap_splat(const double* pts_xy, const double* sigma, double fixed_sigma, double truncate, int n,
-                     int height, int width, void* workspace, size_t workspace_bytes, float* density,
-                     void* stream);
+ * int(x) >= width are skipped (dmap_gen.py:41-44) but still count as neighbours.
+ * Every pixel of the packed output is written exactly once (zero fill fused):
+ * algorithmic HBM traffic 4*H*W + 16*N bytes per image. */
+int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma, double fixed_sigma, double truncate,
+                           int n_images, const int64_t* meta, const dgvcc_dmap_plan* plan, void* workspace,
+                           size_t workspace_bytes, float* density, void* stream);
 
 /* ---------------------------------------------------------------------------
  * ISW instance-whitening covariance loss -- replaces

@@ -37,57 +37,63 @@ def config4_images():
 
 
 def bench_dmap(cpu):
+    import ctypes
     from dgvcc_b200.utils import dmap_gen
     lib = _native.lib()
     images = config4_images()
+    shapes = [s for s, _ in images]
+    order = np.argsort([-len(p) for _, p in images], kind="stable")  # launch order of the public batch API
+    pts_list = [np.ascontiguousarray(images[i][1], dtype=np.float64) for i in order]
+    plan = dmap_gen._Plan([shapes[i] for i in order], [len(p) for p in pts_list])
+    pl = plan.plan
+    meta = torch.from_numpy(plan.meta).to(dev)
+    d_pts = torch.from_numpy(np.concatenate([p for p in pts_list if len(p)], axis=0)).to(dev)
+    out = torch.empty((pl.total_pixels,), dtype=torch.float32, device=dev)
+    ws = torch.empty((pl.splat_workspace_bytes,), dtype=torch.uint8, device=dev)
+    sig = torch.empty((pl.total_heads,), dtype=torch.float64, device=dev)
+    kws = torch.empty((pl.knn_workspace_bytes,), dtype=torch.uint8, device=dev)
+    bytes_alg = 4 * int(pl.total_pixels) + 16 * int(pl.total_heads)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = _native.stream_ptr(dev)
     for adaptive in (True, False):
-        t_dev = t_splat = 0.0
-        bytes_alg = 0
-        for rep in range(2):
-            t_dev = t_splat = 0.0
-            bytes_alg = 0
-            for (h, w), pts in images:
-                n = len(pts)
-                p64 = np.ascontiguousarray(pts, dtype=np.float64)
-                d_pts = torch.from_numpy(p64).to(dev) if n else None
-                out = torch.empty((h, w), dtype=torch.float32, device=dev)
-                ws_bytes = lib.dgvcc_dmap_workspace_bytes(n)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                idx = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
-                dist = torch.empty((max(n, 1), 4), dtype=torch.float64, device=dev)
-                sig = torch.empty((max(n, 1),), dtype=torch.float64, device=dev)
-                kws_bytes = lib.dgvcc_dmap_knn_workspace_bytes(n)
-                kws = torch.empty(kws_bytes, dtype=torch.uint8, device=dev)
-                flush.zero_()
-                e0, e1, e2 = ev(), ev(), ev()
-                st = _native.stream_ptr(dev)
-                e0.record()
-                if adaptive and n:
-                    lib.dgvcc_dmap_knn_sigma(_native.ptr(d_pts), n, _native.ptr(idx), _native.ptr(dist), _native.ptr(sig),
-                                             _native.ptr(kws), kws_bytes, st)
-                e1.record()
-                lib.dgvcc_dmap_splat(_native.ptr(d_pts), _native.ptr(sig) if (adaptive and n) else None, 4.0,
-                                     4.0 if adaptive else 1.75, n, h, w, _native.ptr(ws), ws_bytes, _native.ptr(out), st)
-                e2.record()
-                torch.cuda.synchronize()
-                t_dev += e0.elapsed_time(e2)
-                t_splat += e1.elapsed_time(e2)
-                bytes_alg += 4 * h * w + 16 * n
+        t_dev, t_splat = [], []
+        for rep in range(6):  # the whole set is ONE batched launch set (inputs resident, L2 flushed before each)
+            flush.zero_()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            if adaptive:
+                _native.check(lib.dgvcc_dmap_knn_sigma_batch(_native.ptr(d_pts), len(images), _native.ptr(meta), ctypes.byref(pl),
+                                                             None, None, _native.ptr(sig), _native.ptr(kws),
+                                                             pl.knn_workspace_bytes, st), "knn")
+            e1.record()
+            _native.check(lib.dgvcc_dmap_splat_batch(_native.ptr(d_pts), _native.ptr(sig) if adaptive else None, 4.0,
+                                                     4.0 if adaptive else 1.75, len(images), _native.ptr(meta), ctypes.byref(pl),
+                                                     _native.ptr(ws), pl.splat_workspace_bytes, _native.ptr(out), st), "splat")
+            e2.record()
+            torch.cuda.synchronize()
+            if rep >= 2:
+                t_dev.append(e0.elapsed_time(e2))
+                t_splat.append(e1.elapsed_time(e2))
+        t_dev, t_splat = float(np.mean(t_dev)), float(np.mean(t_splat))
         # end to end through the public API: host numpy in, host numpy out
         fn = dmap_gen.gaussian_filter_density if adaptive else dmap_gen.gaussian_filter_density_fixed
         t0 = time.perf_counter()
         for (h, w), pts in images:
             fn(np.empty((h, w, 0)), pts)
         e2e_s = time.perf_counter() - t0
+        dmap_gen.gaussian_filter_density_batch(shapes, [p for _, p in images], fixed=not adaptive)  # warm the pinned pool
+        t0 = time.perf_counter()
+        dmap_gen.gaussian_filter_density_batch(shapes, [p for _, p in images], fixed=not adaptive)
+        e2e_batch_s = time.perf_counter() - t0
         line = {
             "workload": f"BASELINE config 4: 64 JHU-shaped images (512..2048 px sides, 0..25000 heads), "
                         f"{'adaptive kNN sigma' if adaptive else 'fixed sigma 4'}",
             "metric": "density maps/s", "value_device": 64 / (t_dev * 1e-3), "value_e2e_host_numpy": 64 / e2e_s,
+            "value_e2e_host_numpy_batch_api": 64 / e2e_batch_s,
             "ms_total_device": t_dev, "ms_splat": t_splat,
             "roofline": {"bound": "hbm", "achieved": bytes_alg / (t_splat * 1e-3) / 1e9, "peak": HBM_GBS, "unit": "GB/s",
                          "frac": bytes_alg / (t_splat * 1e-3) / 1e9 / HBM_GBS,
-                         "note": "algorithmic bytes 4*H*W + 16*N per image / time of prepare+splat kernels"},
+                         "note": "algorithmic bytes 4*H*W + 16*N per image / time of the prepare + culling + splat kernels of the batch"},
         }
         if cpu:
             from oracle import dmap_oracle

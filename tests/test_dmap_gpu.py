@@ -120,6 +120,59 @@ def test_batch_api_and_file_protocol(tmp_path):
     assert os.path.getmtime(tmp_path / "img_7_dmap.npy") == mtime
 
 
+def test_batched_launch_matches_oracle_on_a_ragged_list():
+    """One launch set for a ragged list (empty image, < 4 heads, > CHUNK heads, sides that are no multiple of the
+    fine / coarse tile): every map bit-identical to the closed-form oracle and to the single-image call."""
+    from dgvcc_b200.utils import dmap_gen
+    rng = np.random.default_rng(77)
+    spec = [(300, 520, 0), (257, 513, 3), (700, 333, 2500), (64, 32, 1), (1030, 1290, 5000), (40, 700, 60), (512, 512, 4)]
+    shapes = [(h, w) for h, w, _ in spec]
+    plist = [synthetic.crowd_points(np.random.default_rng(100 + i), n, w, h, dtype=np.float64)
+             for i, (h, w, n) in enumerate(spec)]
+    for fixed in (False, True):
+        outs = dmap_gen.gaussian_filter_density_batch(shapes, plist, fixed=fixed)
+        assert len(outs) == len(spec)
+        for (h, w), p, o in zip(shapes, plist, outs):
+            assert o.shape == (h, w) and o.dtype == np.float32
+            if len(p) == 0:
+                assert not o.any()
+                continue
+            ref = dmap_oracle.density_closed_form((h, w), p, fixed=fixed)
+            assert_map_close(o, ref, f"batch {h}x{w} n={len(p)} fixed={fixed}")
+            fn = dmap_gen.gaussian_filter_density_fixed if fixed else dmap_gen.gaussian_filter_density
+            assert np.array_equal(o, fn(np.empty((h, w, 0)), p)), "batched and single-image launches differ"
+
+
+def test_batched_knn_bit_exact():
+    import ctypes
+    import torch
+    from dgvcc_b200 import _native
+    from dgvcc_b200.utils import dmap_gen
+    counts = [0, 1, 3, 4, 257, 2048, 2049, 5000]
+    plist = [synthetic.crowd_points(np.random.default_rng(200 + i), n, 1500, 1100, dtype=np.float64) for i, n in enumerate(counts)]
+    plan = dmap_gen._Plan([(1100, 1500)] * len(counts), counts)
+    pl = plan.plan
+    dev = torch.device("cuda")
+    meta = torch.from_numpy(plan.meta).to(dev)
+    d_pts = torch.from_numpy(np.concatenate([p for p in plist if len(p)])).to(dev)
+    idx = torch.empty((pl.total_heads, 4), dtype=torch.int32, device=dev)
+    dist = torch.empty((pl.total_heads, 4), dtype=torch.float64, device=dev)
+    sigma = torch.empty((pl.total_heads,), dtype=torch.float64, device=dev)
+    kws = torch.empty((pl.knn_workspace_bytes,), dtype=torch.uint8, device=dev)
+    _native.check(_native.lib().dgvcc_dmap_knn_sigma_batch(
+        _native.ptr(d_pts), len(counts), _native.ptr(meta), ctypes.byref(pl), _native.ptr(idx), _native.ptr(dist),
+        _native.ptr(sigma), _native.ptr(kws), pl.knn_workspace_bytes, _native.stream_ptr(dev)), "knn batch")
+    idx, dist, sigma = idx.cpu().numpy(), dist.cpu().numpy(), sigma.cpu().numpy()
+    for i, p in enumerate(plist):
+        if not len(p):
+            continue
+        lo, hi = plan.pt_off[i], plan.pt_off[i + 1]
+        rd, rl = dmap_oracle.knn4(p)
+        assert np.array_equal(idx[lo:hi], rl) and np.array_equal(dist[lo:hi], rd), f"image {i} (n={len(p)})"
+        ref_sigma = (rd[:, 1] + rd[:, 2] + rd[:, 3]) * 0.1 if len(p) > 3 else np.full(len(p), 15.0)
+        assert np.array_equal(sigma[lo:hi], ref_sigma)
+
+
 def test_negative_beyond_size_raises_like_numpy():
     from dgvcc_b200.utils import dmap_gen
     with pytest.raises(IndexError):

@@ -32,6 +32,7 @@ class DmapPlan(ctypes.Structure):
 
 
 DMAP_META_COLS = 12  # DGVCC_DMAP_META_COLS
+DEN_META_COLS = 8    # DGVCC_DEN_META_COLS
 
 # name -> (restype, argtypes); every symbol include/dgvcc_b200.h declares must appear here
 SIGNATURES = {
@@ -71,10 +72,12 @@ SIGNATURES = {
                                         c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_isw_sx_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_isw_covstat_var": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dgvcc_isw_topk_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dgvcc_isw_gram_tc_partials": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_bay_knn_mean": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_bay_crop_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
+    "dgvcc_den_train_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dgvcc_probe_ex2": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
     "dgvcc_probe_ffma": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
 }

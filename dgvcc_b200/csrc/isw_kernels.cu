@@ -262,6 +262,80 @@ isw_covstat_var_kernel(const float* __restrict__ f_cor, const float* __restrict_
     var_out[e] = ss / (float)(batch - 1);  // batch == 1 -> 0/0 = nan, like torch.var
 }
 
+// ------------------------------------------------------------------------ top-k mask (CovMatrix_ISW)
+// set_mask_matrix (models/ISW/cov_settings.py:52-72): mask = 1 at the k largest entries of the averaged
+// variance matrix, 0 elsewhere, AND-ed with the previous mask.  The statistics are accumulated and averaged
+// here too: values[i] = sum_s stats[s][i] / count, summed in arrival order like the reference's
+// `var_matrix + var_cov` chain.  One CTA: MSB-first radix select of the k-th largest key (4 passes of 8 bits),
+// then one ordered pass; ties at the threshold are taken in index order (torch.topk leaves tie order open).
+constexpr int TOPK_THREADS = 1024;
+
+__device__ __forceinline__ unsigned ordered_key(float v) {  // larger float <=> larger unsigned key
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+isw_topk_mask_kernel(const float* __restrict__ stats, int n_stats, float count, int n, int k,
+                     const float* __restrict__ prev_mask, float* __restrict__ values, float* __restrict__ mask) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix;
+    __shared__ int s_remaining;
+    __shared__ int warp_cnt[TOPK_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += TOPK_THREADS) {
+        float v = stats[i];
+        for (int s = 1; s < n_stats; ++s) v = __fadd_rn(v, stats[(size_t)s * n + i]);
+        values[i] = __fdiv_rn(v, count);
+    }
+    __syncthreads();
+    unsigned prefix = 0, known = 0;
+    int remaining = min(k, n);
+    if (remaining > 0) {
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += TOPK_THREADS) {
+                const unsigned key = ordered_key(values[i]);
+                if ((key & known) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0, digit = 0;
+                for (int b = 255; b >= 0; --b) {
+                    if (cum + (int)hist[b] >= remaining) { digit = b; break; }
+                    cum += (int)hist[b];
+                }
+                s_prefix = prefix | ((unsigned)digit << shift);
+                s_remaining = remaining - cum;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            remaining = s_remaining;
+            known |= 0xffu << shift;
+        }
+    }
+    // prefix = key of the k-th largest; `remaining` of the entries equal to it are still to be taken
+    int taken = 0;
+    for (int base = 0; base < n; base += TOPK_THREADS) {
+        const int i = base + tid;
+        const unsigned key = i < n ? ordered_key(values[i]) : 0u;
+        const bool gt = k > 0 && i < n && key > prefix, eq = k > 0 && i < n && key == prefix;
+        const unsigned bal = __ballot_sync(FULL_MASK, eq);
+        __syncthreads();
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < TOPK_THREADS / 32; ++w) {
+            if (w < warp) before += warp_cnt[w];
+            total += warp_cnt[w];
+        }
+        const bool sel = gt || (eq && taken + before + __popc(bal & ((1u << lane) - 1u)) < remaining);
+        if (i < n) mask[i] = (sel && (!prev_mask || prev_mask[i] != 0.f)) ? 1.f : 0.f;
+        taken += total;
+    }
+}
+
 // ------------------------------------------------------------------------------- dX = S X (SIMT)
 __global__ void __launch_bounds__(GEMM_THREADS)
 isw_sx_simt_kernel(const float* __restrict__ s, const float* __restrict__ x, int c, int hw, float* __restrict__ dx) {
@@ -485,5 +559,13 @@ extern "C" int dgvcc_isw_covstat_var(const float* f_cor, const float* reverse_ey
                                      void* stream) {
     if (!f_cor || !reverse_eye || !var_out || batch <= 0 || c <= 0) return DGVCC_ERR_ARG;
     isw_covstat_var_kernel<<<ceil_div(c * c, 256), 256, 0, (cudaStream_t)stream>>>(f_cor, reverse_eye, batch, c * c, var_out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_topk_mask(const float* stats, int n_stats, int count, int n, int k, const float* prev_mask,
+                                   float* values, float* mask, void* stream) {
+    if (!stats || !values || !mask || n_stats <= 0 || count <= 0 || n <= 0 || k < 0) return DGVCC_ERR_ARG;
+    isw_topk_mask_kernel<<<1, TOPK_THREADS, 0, (cudaStream_t)stream>>>(stats, n_stats, (float)count, n, k, prev_mask,
+                                                                       values, mask);
     return (int)cudaGetLastError();
 }

@@ -186,6 +186,25 @@ int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma, double fix
                            size_t workspace_bytes, float* density, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Dataset-side density handling -- replaces the density part of
+ * DenClsDataset._train_transform (datasets/den_cls_dataset.py:109-150; same block in
+ * datasets/den_dataset.py:86-127) and the occupancy map of DenClsDataset.__getitem__
+ * (den_cls_dataset.py:60-61) for a whole batch in one launch:
+ *   zero padding F.pad(dmap, (left, top, ..)), F.crop(dmap, i, j, crop_h, crop_w),
+ *   sum-pool reshape([1, h/d, d, w/d, d]).sum((2, 4)), optional F.hflip, and
+ *   bmap = (16 x 16 block sums of the pooled map > 0).
+ * maps: packed full-resolution maps f32 (e.g. the output of dgvcc_dmap_splat_batch);
+ * meta [batch][DGVCC_DEN_META_COLS] int64 DEVICE table: first float of the map, H, W,
+ *   pad_left, pad_top, crop_i (row), crop_j (column), flip (0/1);
+ * out_dmap [batch, crop_h/d, crop_w/d] f32; out_bmap [batch, crop_h/d/16, crop_w/d/16] f32
+ *   in {0,1}, or NULL (den_dataset.py has no occupancy map).
+ * crop_h, crop_w must be multiples of d (the reference's reshape raises otherwise) and,
+ * with out_bmap, of 16*d. */
+#define DGVCC_DEN_META_COLS 8
+int dgvcc_den_train_targets(const float* maps, const int64_t* meta, int batch, int crop_h, int crop_w,
+                            int downsample, float* out_dmap, float* out_bmap, void* stream);
+
+/* ---------------------------------------------------------------------------
  * ISW instance-whitening covariance loss -- replaces
  * models/ISW/instance_whitening.py:5-16 (InstanceWhitening = InstanceNorm2d, affine=False),
  * :30-39 (get_covariance_matrix) and :19-27 (instance_whitening_loss) + their autograd.
@@ -226,6 +245,14 @@ int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float*
  * batch of f_cor * reverse_eye. */
 int dgvcc_isw_covstat_var(const float* f_cor, const float* reverse_eye, int batch, int c, float* var_out,
                           void* stream);
+
+/* CovMatrix_ISW.set_mask_matrix (models/ISW/cov_settings.py:52-72), relax_denom != 0 branch:
+ * values[i] = (stats[0][i] + stats[1][i] + ...) / count   (the accumulated variance statistics, :84-89, :54)
+ * mask[i]   = 1 at the k largest values, else 0; AND-ed with prev_mask when it is not NULL (:70-71).
+ * stats [n_stats, n] f32, values / mask / prev_mask [n] f32, n = C*C.  Ties at the k-th value are taken in
+ * index order (torch.topk leaves that open).  k = int(num_off_diagonal - margin) is the caller's (:63-65). */
+int dgvcc_isw_topk_mask(const float* stats, int n_stats, int count, int n, int k, const float* prev_mask,
+                        float* values, float* mask, void* stream);
 
 /* The tensor-core Gram on its own (split-K partial tiles, tests / profiling):
  * part [batch][splits][upper-triangular 128x128 tiles][128][128]. */

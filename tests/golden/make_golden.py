@@ -225,8 +225,112 @@ def make_bay():
     np.savez_compressed(os.path.join(HERE, "bay_cases.npz"), **out)
 
 
+# -------------------------------------------------------------------------- den
+def make_den():
+    """Density side of DenClsDataset.__getitem__ / _train_transform (pad, crop, sum-pool, flip, 16x16 block
+    occupancy), run on the unmodified class with its three file loaders stubbed."""
+    import importlib
+    import random
+    import types
+    from PIL import Image
+    pkg = types.ModuleType("datasets")        # the HuggingFace `datasets` package shadows the reference's
+    pkg.__path__ = [os.path.join(REF, "datasets")]
+    saved = sys.modules.get("datasets")
+    sys.modules["datasets"] = pkg
+    sys.path.insert(0, REF)
+    try:
+        dc = importlib.import_module("datasets.den_cls_dataset")
+        from utils.misc import get_padding
+    finally:
+        sys.path.remove(REF)
+    rec = {}
+    real_crop = dc.random_crop
+    def recording_crop(im_h, im_w, ch, cw):
+        rec["ij"] = real_crop(im_h, im_w, ch, cw)
+        return rec["ij"]
+    dc.random_crop = recording_crop
+    out = {}
+    cases = [  # (w, h, crop, downsample, heads, seed)
+        (640, 480, (256, 256), 1, 300, 1), (640, 480, (256, 256), 8, 300, 2), (300, 200, (256, 256), 4, 80, 3),
+        (900, 700, (512, 256), 2, 40, 4), (1100, 800, (320, 320), 4, 2000, 5), (400, 400, (256, 256), 8, 0, 6),
+    ]
+    for k, (w, h, crop, down, n, seed) in enumerate(cases):
+        rng = np.random.default_rng(8300 + k)
+        pts = synthetic.crowd_points(rng, n, w, h, dtype=np.float64)
+        dmap = np.zeros((h, w), dtype=np.float32)
+        for x, y in pts:  # small positive stamps: what a *_dmap.npy holds (non-negative, mostly zero)
+            x0, y0 = int(x), int(y)
+            dmap[max(0, y0 - 2):y0 + 3, max(0, x0 - 2):x0 + 3] += rng.random(dmap[max(0, y0 - 2):y0 + 3, max(0, x0 - 2):x0 + 3].shape, dtype=np.float32) / 25
+        ds = dc.DenClsDataset.__new__(dc.DenClsDataset)
+        ds.img_fns, ds.root, ds.method, ds.gt_dir = ["/data/train/img_1.jpg"], "/data", "train", None
+        ds.crop_size, ds.downsample, ds.pre_resize = crop, down, 1
+        ds.transform = ds.more_transform = (lambda im: torch.zeros(1))
+        img = Image.fromarray(np.zeros((h, w, 3), dtype=np.uint8))
+        ds._load_img = lambda fn, img=img: (img, ".jpg")
+        ds._load_gt = lambda fn, pts=pts: pts.copy()
+        ds._load_dmap = lambda fn, dmap=dmap: dmap.copy()
+        random.seed(seed)
+        state = random.getstate()
+        _, _, _, d_out, b_out = ds[0]
+        # replay the draws: grey-scale, crop (recorded), flip
+        random.setstate(state)
+        random.random()
+        ph, pw = h, w
+        left = top = 0
+        if 1.0 * min(w, h) < min(crop):
+            (left, top, _, _), ph, pw = get_padding(h, w, crop[0], crop[1])
+        i, j = dc.random_crop.__wrapped__(ph, pw, crop[0], crop[1]) if hasattr(dc.random_crop, "__wrapped__") else real_crop(ph, pw, crop[0], crop[1])
+        assert (i, j) == rec["ij"]
+        flip = int(random.random() > 0.5)
+        out[f"den_{k}_dmap"] = dmap
+        out[f"den_{k}_geom"] = np.asarray([left, top, i, j, crop[0], crop[1], down, flip])
+        out[f"den_{k}_ref_dmap"], out[f"den_{k}_ref_bmap"] = d_out.numpy(), b_out.numpy()
+        print("den", k, "geom", out[f"den_{k}_geom"].tolist(), "sum", float(d_out.sum()), "occupied", int(b_out.sum()), "of", b_out.numel())
+    if saved is not None:
+        sys.modules["datasets"] = saved
+    np.savez_compressed(os.path.join(HERE, "den_cases.npz"), **out)
+
+
+# -------------------------------------------------------------------------- cov
+def make_cov():
+    """CovMatrix_ISW (models/ISW/cov_settings.py:16-89), unmodified, on CPU: `.cuda()` made a no-op, the absent
+    `kmeans1d` stubbed (only the relax_denom == 0 branch uses it; the shipped default is 2.0,
+    models/ISW/__init__.py:23)."""
+    import importlib
+    import types
+    pkg = types.ModuleType("refisw")
+    pkg.__path__ = [os.path.join(REF, "models", "ISW")]
+    sys.modules["refisw"] = pkg
+    sys.modules.setdefault("kmeans1d", types.ModuleType("kmeans1d"))
+    saved_cuda, saved_dev = torch.Tensor.cuda, torch.cuda.current_device
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cuda.current_device = lambda: 0
+    try:
+        cs = importlib.import_module("refisw.cov_settings")
+        out = {}
+        for name, dim, relax, rounds, batches in (("c16", 16, 2.0, 1, 3), ("c64", 64, 2.0, 2, 4), ("c64r3", 64, 3.0, 2, 2),
+                                                  ("c256", 256, 2.0, 1, 2)):
+            g = torch.Generator().manual_seed(8400 + dim + int(relax))
+            cm = cs.CovMatrix_ISW(dim=dim, relax_denom=relax)
+            out[f"{name}_cfg"] = np.asarray([dim, relax, rounds, batches])
+            for r in range(rounds):
+                for b in range(batches):
+                    var = (torch.rand(dim, dim, generator=g) ** 3).triu(1)  # what var(f_cor * reverse_eye, dim=0) looks like
+                    out[f"{name}_var_{r}_{b}"] = var.numpy()
+                    cm.set_variance_of_covariance(var)
+                cm.set_mask_matrix()   # the second round ANDs with the first mask (cov_settings.py:70-71)
+                eye, mask, margin, num = cm.get_mask_matrix()
+                out[f"{name}_mask_{r}"] = mask.numpy().copy()
+                out[f"{name}_num_{r}"] = np.asarray([float(num), float(margin), float(cm.margin), float(cm.num_off_diagonal)])
+            cm.reset_mask_matrix()
+            assert cm.mask_matrix is None
+    finally:
+        torch.Tensor.cuda, torch.cuda.current_device = saved_cuda, saved_dev
+    np.savez_compressed(os.path.join(HERE, "cov_cases.npz"), **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["bl", "dmap", "isw", "bay"]
+    what = sys.argv[1:] or ["bl", "dmap", "isw", "bay", "den", "cov"]
     torch.manual_seed(0)
     for w in what:
         globals()[f"make_{w}"]()

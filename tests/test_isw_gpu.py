@@ -185,3 +185,81 @@ def test_variance_of_covariance_covstat(c, hw):
     ref = isw_oracle.covstat_variance(isw_oracle.instance_standardize(x), eye, rev)
     got = variance_of_covariance(isw_oracle.instance_standardize(x).to(DEV), eye.to(DEV), rev.to(DEV))
     assert_close(got.cpu(), ref, 1e-4, 1e-6 * amax(ref), "variance of covariance")  # a difference of two close covariances
+
+
+# ------------------------------------------------------------------ CovMatrix_ISW
+COV_CASES = ["c16", "c64", "c64r3", "c256"]
+
+
+@pytest.mark.parametrize("name", COV_CASES)
+def test_cov_matrix_isw_matches_reference_fixture(name):
+    """The drop-in class replays the statistics the unmodified reference class saw: masks bit-exact."""
+    from dgvcc_b200.models.ISW import CovMatrix_ISW
+    fx = np.load(os.path.join(GOLDEN, "cov_cases.npz"))
+    dim, relax, rounds, batches = fx[f"{name}_cfg"]
+    cm = CovMatrix_ISW(dim=int(dim), relax_denom=float(relax))
+    eye, rev = cm.get_eye_matrix()
+    assert eye.is_cuda and torch.equal(eye.cpu(), torch.eye(int(dim))) and torch.equal(rev.cpu(), torch.ones(int(dim), int(dim)).triu(1))
+    for r in range(int(rounds)):
+        for b in range(int(batches)):
+            cm.set_variance_of_covariance(torch.from_numpy(fx[f"{name}_var_{r}_{b}"]).cuda())
+        cm.set_mask_matrix()
+        eye, mask, margin, num = cm.get_mask_matrix()
+        assert np.array_equal(mask.cpu().numpy(), fx[f"{name}_mask_{r}"])
+        ref_num, ref_margin_ret, ref_margin, ref_off = fx[f"{name}_num_{r}"]
+        assert float(num) == ref_num and margin == ref_margin_ret == 0
+        assert float(cm.margin) == ref_margin and float(cm.num_off_diagonal) == ref_off
+    cm.reset_mask_matrix()
+    assert cm.mask_matrix is None
+
+
+def test_topk_mask_ties_and_edges():
+    from dgvcc_b200.models.ISW.cov_settings import topk_mask
+    g = torch.Generator().manual_seed(3)
+    v = torch.rand(3, 5000, generator=g).cuda()
+    vals, mask = topk_mask(v, 3, 1234)
+    vc = v.cpu()
+    ref_vals = ((vc[0] + vc[1]) + vc[2]) / 3   # on the CPU like the reference: IEEE division (torch's CUDA
+    assert torch.equal(vals.cpu(), ref_vals)   # division by a scalar multiplies by the reciprocal instead)
+    ref = torch.zeros(5000)
+    ref[torch.topk(ref_vals, 1234).indices] = 1
+    assert torch.equal(mask.cpu(), ref)
+    # ties at the threshold (a half-empty variance matrix): exactly k ones, taken in index order
+    t = torch.tensor([[0.0, 2.0, 0.0, 1.0, 0.0, 1.0, 1.0, 0.0, -1.0]]).cuda()
+    for k, want in ((0, [0] * 9), (1, [0, 1, 0, 0, 0, 0, 0, 0, 0]), (3, [0, 1, 0, 1, 0, 1, 0, 0, 0]),
+                    (5, [1, 1, 0, 1, 0, 1, 1, 0, 0]), (9, [1] * 9), (20, [1] * 9)):
+        _, m = topk_mask(t, 1, k)
+        assert m.cpu().tolist() == [float(x) for x in want], k
+    _, m = topk_mask(t, 1, 5, prev_mask=torch.tensor([1.0, 0, 1, 1, 1, 0, 1, 1, 1]).cuda())
+    assert m.cpu().tolist() == [1.0, 0, 0, 1, 0, 0, 1, 0, 0]
+
+
+def test_cal_covstat_to_mask_end_to_end():
+    """cal_covstat statistic (variance_of_covariance) -> CovMatrix_ISW -> mask -> loss, all on the device,
+    against the oracle restatements on the same inputs."""
+    from dgvcc_b200.models.ISW import CovMatrix_ISW, InstanceWhitening, instance_whitening_loss, variance_of_covariance
+    from oracle import isw_oracle
+    from oracle.cov_settings_oracle import CovMatrixISW
+    c = 64
+    cm, ocm = CovMatrix_ISW(dim=c, relax_denom=2.0), CovMatrixISW(c, 2.0)
+    eye, rev = cm.get_eye_matrix()
+    for s in range(3):
+        x = torch.randn(2, c, 24, 20, generator=torch.Generator().manual_seed(50 + s))
+        w = isw_oracle.instance_standardize(x)
+        stat = variance_of_covariance(w.cuda(), eye, rev)
+        ostat = isw_oracle.covstat_variance(w, torch.eye(c), torch.ones(c, c).triu(1))
+        torch.testing.assert_close(stat.cpu(), ostat, rtol=1e-4, atol=1e-7)
+        cm.set_variance_of_covariance(stat)
+        ocm.set_variance_of_covariance(stat.cpu())   # same statistic: the selection itself must then agree exactly
+    _, mask, margin, num = cm.get_mask_matrix()
+    ocm.set_mask_matrix()
+    assert torch.equal(mask.cpu(), ocm.mask_matrix) and float(num) == float(ocm.num_sensitive)
+    xin = torch.randn(4, c, 24, 20, generator=torch.Generator().manual_seed(99)).cuda().requires_grad_(True)
+    _, wt = InstanceWhitening(c)(xin)
+    loss = instance_whitening_loss(wt, eye, mask, margin, num)
+    loss.backward()
+    xo = xin.detach().cpu().requires_grad_(True)
+    lo = isw_oracle.whitening_loss(isw_oracle.instance_standardize(xo), torch.eye(c), ocm.mask_matrix, 0, ocm.num_sensitive)
+    lo.backward()
+    torch.testing.assert_close(loss.cpu(), lo, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(xin.grad.cpu(), xo.grad, rtol=1e-4, atol=1e-6 * float(xo.grad.abs().max()))

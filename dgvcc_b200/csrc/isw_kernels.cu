@@ -142,94 +142,142 @@ isw_gram_simt_kernel(const float* __restrict__ x, int c, int hw, int splits, int
 
 // f_cor[b][i][j] = sum_split part / (hw-1) + eps*eye[i][j], written to both (i,j) and (j,i).
 // `tile` is the edge of the partial tiles (64 for the SIMT kernel, 128 for the tensor-core kernel).
-// One thread sums four consecutive columns of one row over the splits (float4 loads, fixed order).
+// One CTA (32 x 8 threads) owns a 32 x 32 block of a partial tile: it adds the splits in order (coalesced rows),
+// stores the block, and stores its mirror image through a shared-memory transpose, so both stores are coalesced.
+// One writer per entry: on diagonal tiles the upper triangle is what gets mirrored.
 __global__ void __launch_bounds__(256)
 isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits, int tile, const float* __restrict__ eye,
                       float eps, float* __restrict__ f_cor) {
+    __shared__ float tr[32][33];
     const int tiles_1d = (c + tile - 1) / tile;
     const int n_tiles = tiles_1d * (tiles_1d + 1) / 2;
     int ti = 0, rem = blockIdx.x;
     while (rem >= tiles_1d - ti) { rem -= tiles_1d - ti; ++ti; }
     const int tj = ti + rem;
     const int b = blockIdx.z;
+    const int sub = tile / 32, sy = blockIdx.y / sub, sx = blockIdx.y % sub;
+    if (ti == tj && sx < sy) return;  // below the diagonal of a diagonal tile: written by the mirror of (sx, sy)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const size_t tile_elems = (size_t)tile * tile;
-    const int quads = tile * tile / 4;
+    const float* p0 = part + ((size_t)b * splits * n_tiles + blockIdx.x) * tile_elems;
     float* fc = f_cor + (size_t)b * c * c;
-    for (int q = blockIdx.y * 256 + threadIdx.x; q < quads; q += gridDim.y * 256) {
-        const int e = 4 * q, li = e / tile, lj = e % tile;
-        const int i = ti * tile + li, j0 = tj * tile + lj;
-        if (i >= c || j0 >= c) continue;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sp = 0; sp < splits; ++sp) {
-            const float4 v = *reinterpret_cast<const float4*>(part + (((size_t)b * splits + sp) * n_tiles + blockIdx.x) * tile_elems + e);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        const float sv[4] = {s.x, s.y, s.z, s.w};
+    const int i0 = ti * tile + 32 * sy, j0 = tj * tile + 32 * sx;
+    const bool diag_block = ti == tj && sx == sy;
+    const float denom = (float)(hw - 1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = j0 + k;
-            if (j >= c) break;
-            if (ti == tj && j < i) continue;  // diagonal tiles: the upper triangle is mirrored (one writer per entry)
-            // torch: bmm(...).div(HW-1) is a true division; + (eps * eye)
-            const float v = sv[k] / (float)(hw - 1);
-            fc[(size_t)i * c + j] = v + eps * eye[(size_t)i * c + j];
-            if (ti != tj || li != lj + k) fc[(size_t)j * c + i] = v + eps * eye[(size_t)j * c + i];
-        }
+    for (int r = 0; r < 4; ++r) {
+        const int li = ty + 8 * r, i = i0 + li, j = j0 + tx;
+        float s = 0.f;
+        const float* p = p0 + (size_t)(32 * sy + li) * tile + 32 * sx + tx;
+#pragma unroll 8
+        for (int sp = 0; sp < splits; ++sp) s += p[(size_t)sp * n_tiles * tile_elems];  // loads batched, adds in split order
+        // torch: bmm(...).div(HW-1) is a true division; + (eps * eye)
+        const float v = s / denom;
+        tr[li][tx] = v;
+        if (i < c && j < c && (!diag_block || tx >= li)) fc[(size_t)i * c + j] = v + eps * eye[(size_t)i * c + j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int lj = ty + 8 * r, j = j0 + lj, i = i0 + tx;  // entry (j, i) = mirror of (i, j) = tr[tx][lj]
+        if (i < c && j < c && (!diag_block || lj > tx)) fc[(size_t)j * c + i] = tr[tx][lj] + eps * eye[(size_t)j * c + i];
     }
 }
 
 // ------------------------------------------------------------------------------- loss
 // off[b] = sum_ij |f_cor[b,i,j] * mask[i,j]| - margin; loss = sum_b max(off[b] / num_remove, 0) / B.
-// One CTA per sample (fixed-order block sums), the last CTA adds the samples in order.
+// Each sample is cut into up to LOSS_CHUNKS slices (one CTA each, fixed-order block sums); the last CTA to
+// finish adds the slices of every sample in slice order and then the samples in order: deterministic, no
+// float atomics.  off_out holds off[B] followed by the [B][LOSS_CHUNKS] partial sums.
+constexpr int LOSS_CHUNKS = 32;
+
 __global__ void __launch_bounds__(256)
 isw_loss_kernel(const float* __restrict__ f_cor, const float* __restrict__ mask, int c, int batch,
                 const float* __restrict__ margin, const float* __restrict__ num_remove, float* __restrict__ off_out,
                 float* __restrict__ loss_out, unsigned int* __restrict__ ticket) {
     __shared__ float scratch[8];
-    const int b = blockIdx.x;
-    const float* fc = f_cor + (size_t)b * c * c;
-    float s = 0.f;
-    for (int e = threadIdx.x; e < c * c; e += 256) s += fabsf(fc[e] * mask[e]);
-    s = warp_sum(s);
+    __shared__ bool s_last;
+    const int b = blockIdx.y, chunks = gridDim.x;
+    const int cc = c * c;
+    const int per = ceil_div(ceil_div(cc, chunks), 4) * 4;  // float4-aligned slices (cc is a multiple of 4 or handled below)
+    const int e0 = blockIdx.x * per, e1 = min(cc, e0 + per);
+    const float* fc = f_cor + (size_t)b * cc;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if ((cc & 3) == 0 && (((uintptr_t)fc | (uintptr_t)mask) & 15u) == 0) {
+        for (int e = e0 + 4 * threadIdx.x; e < e1; e += 4 * 256) {
+            const float4 f = *reinterpret_cast<const float4*>(fc + e);
+            const float4 m = *reinterpret_cast<const float4*>(mask + e);
+            s0 += fabsf(f.x * m.x); s1 += fabsf(f.y * m.y); s2 += fabsf(f.z * m.z); s3 += fabsf(f.w * m.w);
+        }
+    } else {
+        for (int e = e0 + threadIdx.x; e < e1; e += 256) s0 += fabsf(fc[e] * mask[e]);
+    }
+    float s = warp_sum((s0 + s1) + (s2 + s3));
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += scratch[w];
-        off_out[b] = t - margin[0];
+        float* part = off_out + batch;
+        part[b * LOSS_CHUNKS + blockIdx.x] = t;
         __threadfence();
-        if (atomicAdd(ticket, 1u) == (unsigned)batch - 1u) {
-            __threadfence();
-            const volatile float* ov = off_out;
-            float total = 0.f;
-            for (int i = 0; i < batch; ++i) total += fmaxf(ov[i] / num_remove[0], 0.f);
-            loss_out[0] = total / (float)batch;
-            *ticket = 0u;
-        }
+        s_last = atomicAdd(ticket, 1u) == (unsigned)(batch * chunks) - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last CTA: one thread per sample adds its slices in slice order, thread 0 then adds the samples in order
+    __threadfence();
+    const volatile float* pv = off_out + batch;
+    for (int i = threadIdx.x; i < batch; i += 256) {
+        float o = 0.f;
+        for (int k = 0; k < chunks; ++k) o += pv[i * LOSS_CHUNKS + k];
+        off_out[i] = o - margin[0];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float total = 0.f;
+        for (int i = 0; i < batch; ++i) total += fmaxf(off_out[i] / num_remove[0], 0.f);
+        loss_out[0] = total / (float)batch;
+        *ticket = 0u;
     }
 }
 
 // S_b[i][j] = g * gate_b * (sgn(fc_ij * m_ij) * m_ij + sgn(fc_ji * m_ji) * m_ji) / (num_remove * B * (hw-1))
 // with gate_b = [off_b / num_remove >= 0]  (torch clamp passes the gradient at the boundary).
+// One CTA (32 x 8 threads) per 32 x 32 block: the (j,i) terms come from the mirrored block through a
+// shared-memory transpose, so every global access is coalesced.
 __global__ void __launch_bounds__(256)
 isw_loss_grad_kernel(const float* __restrict__ f_cor, const float* __restrict__ mask, const float* __restrict__ off,
                      const float* __restrict__ num_remove, const float* __restrict__ grad_loss, int c, int hw,
-                     int batch, float* __restrict__ s_out) {
-    const int b = blockIdx.y;
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    if (e >= c * c) return;
-    const int i = e / c, j = e % c;
+                     int batch, float* __restrict__ s_out, float* __restrict__ alpha_out) {
+    __shared__ float tr[32][33];
+    const int b = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     const float* fc = f_cor + (size_t)b * c * c;
     const float nr = num_remove[0];
     const float gate = (off[b] / nr >= 0.f) ? 1.f : 0.f;
     auto term = [&](int r, int q) {
+        if (r >= c || q >= c) return 0.f;
         const float m = mask[(size_t)r * c + q];
         const float v = fc[(size_t)r * c + q] * m;
         const float sg = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
         return sg * m;
     };
+#pragma unroll
+    for (int r = 0; r < 4; ++r) tr[ty + 8 * r][tx] = term(j0 + ty + 8 * r, i0 + tx);  // mirrored block, row-wise
+    __syncthreads();
     const float scale = grad_loss[0] * gate / (nr * (float)batch) / (float)(hw - 1);
-    s_out[(size_t)b * c * c + e] = scale * (term(i, j) + term(j, i));
+    if (alpha_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) alpha_out[b] = scale;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r, j = j0 + tx;
+        if (i >= c || j >= c) continue;
+        const float t = term(i, j) + tr[tx][ty + 8 * r];
+        // alpha_out: factored form S_b = alpha_b * T_b for the tensor-core GEMM -- T is in {0, +-1, +-2} for a 0/1
+        // mask, exact in TF32, which lets isw_sx_tc_kernel<EXACT> skip the hi/lo split of A
+        s_out[(size_t)b * c * c + (size_t)i * c + j] = alpha_out ? t : scale * t;
+    }
 }
 
 // S_b = (dF_b + dF_b^T) / (hw-1): backward of get_covariance_matrix for an arbitrary upstream gradient.
@@ -455,19 +503,21 @@ static size_t gram_partial_floats(int batch, int c, int hw) {
 }
 
 extern "C" size_t dgvcc_isw_workspace_bytes(int batch, int c, int hw) {
-    // partials | off[B] | ticket (256 B) | S [B,C,C]
-    return align_up(gram_partial_floats(batch, c, hw) * sizeof(float), 256) + align_up((size_t)batch * sizeof(float), 256) +
+    // partials | off[B] + loss partials [B][LOSS_CHUNKS] + alpha[B] | ticket (256 B) | S [B,C,C]
+    return align_up(gram_partial_floats(batch, c, hw) * sizeof(float), 256) +
+           align_up((size_t)batch * (2 + LOSS_CHUNKS) * sizeof(float), 256) +
            256 + align_up((size_t)batch * c * c * sizeof(float), 256);
 }
 
 namespace {
-struct IswWs { float* part; float* off; unsigned int* ticket; float* s; };
+struct IswWs { float* part; float* off; float* alpha; unsigned int* ticket; float* s; };
 IswWs carve(void* ws, int batch, int c, int hw) {
     const size_t part = align_up(gram_partial_floats(batch, c, hw) * sizeof(float), 256);
     IswWs w;
     char* p = (char*)ws;
     w.part = (float*)p; p += part;
-    w.off = (float*)p; p += align_up((size_t)batch * sizeof(float), 256);
+    w.off = (float*)p; p += align_up((size_t)batch * (2 + LOSS_CHUNKS) * sizeof(float), 256);
+    w.alpha = w.off + (size_t)batch * (1 + LOSS_CHUNKS);
     w.ticket = (unsigned int*)p; p += 256;
     w.s = (float*)p;
     return w;
@@ -498,7 +548,7 @@ extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int ba
         isw_gram_simt_kernel<<<dim3(n_tiles, splits, batch), GEMM_THREADS, 0, st>>>(f_map, c, hw, splits, kps, w.part);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
-    const int yblocks = tile == 128 ? 16 : 4;
+    const int yblocks = (tile / 32) * (tile / 32);
     isw_cov_finish_kernel<<<dim3(n_tiles, yblocks, batch), 256, 0, st>>>(w.part, c, hw, splits, tile, eye, 1e-5f, f_cor);
     return (int)cudaGetLastError();
 }
@@ -511,18 +561,28 @@ extern "C" int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, con
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
     DGVCC_RETURN_IF_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
-    isw_loss_kernel<<<batch, 256, 0, st>>>(f_cor, mask, c, batch, margin, num_remove_cov, w.off, loss_out, w.ticket);
+    const int chunks = max(1, min(LOSS_CHUNKS, c * c / 4096));
+    isw_loss_kernel<<<dim3(chunks, batch), 256, 0, st>>>(f_cor, mask, c, batch, margin, num_remove_cov, w.off, loss_out,
+                                                        w.ticket);
     return (int)cudaGetLastError();
 }
 
 // implemented in isw_sx_tc.cu; returns DGVCC_ERR_UNSUPPORTED for shapes it does not tile
-extern "C" int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c, int hw, float* dx, void* stream);
+namespace dgvcc { namespace isw_sx {
+int launch(const float* s, const float* x, int batch, int c, int hw, float* dx, const float* scale, bool a_is_tf32_exact,
+           void* stream);
+} }
+
+// the shapes / alignments dgvcc::isw_sx::launch accepts
+static bool sx_tc_tiles(const float* s, const float* x, const float* dx, int c, int hw) {
+    return hw % 4 == 0 && c % 4 == 0 && c >= 32 && !(((uintptr_t)s | (uintptr_t)x | (uintptr_t)dx) & 15u);
+}
 
 // dX = S X on the tensor cores where the shape tiles, else exact fp32 on CUDA cores
 static int launch_sx(const float* s, const float* x, int batch, int c, int hw, int use_tensor_cores, float* dx,
                      cudaStream_t st) {
     if (use_tensor_cores) {
-        const int rc = dgvcc_isw_sx_tc(s, x, batch, c, hw, dx, (void*)st);
+        const int rc = dgvcc::isw_sx::launch(s, x, batch, c, hw, dx, nullptr, false, (void*)st);
         if (rc != DGVCC_ERR_UNSUPPORTED) return rc;
     }
     isw_sx_simt_kernel<<<dim3(ceil_div(hw, GT), ceil_div(c, GT), batch), GEMM_THREADS, 0, st>>>(s, x, c, hw, dx);
@@ -531,14 +591,22 @@ static int launch_sx(const float* s, const float* x, int batch, int c, int hw, i
 
 extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float* mask,
                                        const float* num_remove_cov, const float* grad_loss, int batch, int c, int hw,
-                                       int use_tensor_cores, void* workspace, size_t workspace_bytes,
-                                       float* grad_f_map, void* stream) {
+                                       int use_tensor_cores, int mask_is_binary, void* workspace,
+                                       size_t workspace_bytes, float* grad_f_map, void* stream) {
     if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
-    isw_loss_grad_kernel<<<dim3(ceil_div(c * c, 256), batch), 256, 0, st>>>(f_cor, mask, w.off, num_remove_cov, grad_loss,
-                                                                            c, hw, batch, w.s);
+    if (use_tensor_cores && mask_is_binary && sx_tc_tiles(w.s, f_map, grad_f_map, c, hw)) {
+        // factored S = alpha * T: the GEMM runs on T (TF32-exact for a 0/1 mask) and scales in its epilogue
+        isw_loss_grad_kernel<<<dim3(ceil_div(c, 32), ceil_div(c, 32), batch), 256, 0, st>>>(f_cor, mask, w.off, num_remove_cov, grad_loss,
+                                                                                c, hw, batch, w.s, w.alpha);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+        const int rc = dgvcc::isw_sx::launch(w.s, f_map, batch, c, hw, grad_f_map, w.alpha, true, (void*)st);
+        if (rc != DGVCC_ERR_UNSUPPORTED) return rc;
+    }
+    isw_loss_grad_kernel<<<dim3(ceil_div(c, 32), ceil_div(c, 32), batch), 256, 0, st>>>(f_cor, mask, w.off, num_remove_cov, grad_loss,
+                                                                            c, hw, batch, w.s, nullptr);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     return launch_sx(w.s, f_map, batch, c, hw, use_tensor_cores, grad_f_map, st);
 }

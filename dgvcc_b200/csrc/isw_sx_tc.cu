@@ -10,6 +10,13 @@
 // fp32 accuracy as in the Gram: 3xTF32, A and B both split into hi + lo, cross terms in their own TMEM
 // accumulator.  The accumulation chain is only C/8 steps, so no split-K is needed.
 // One CTA = one 128 x 128 tile of dX of one sample; warp roles as in isw_gram_tc.cu.
+//
+// EXACT variant (the backward of instance_whitening_loss): there S_b = alpha_b * T_b with T_b = sgn(.)*mask
+// in {0, +-1, +-2} for a 0/1 mask -- exactly representable in TF32.  The caller passes T and alpha; A then
+// needs neither conversion nor a lo part (2 MMAs per k step instead of 3, a third less shared-memory traffic),
+// the stage shrinks to 48 KB so two CTAs share an SM (one's epilogue under the other's main loop), and the
+// epilogue multiplies by alpha_b.  The caller promises exactness (`a_is_tf32_exact`: the Python side checks the
+// mask once per mask tensor and caches the answer).
 #include "tc_common.cuh"
 #include "../../include/dgvcc_b200.h"
 
@@ -21,24 +28,33 @@ using namespace dgvcc::tc;
 constexpr int TILE = 128;                  // M and N of the output tile
 constexpr int BLOCK_K = 32;
 constexpr int UMMA_K = 8;
-constexpr int STAGES = 3;
 constexpr int TILE_BYTES = TILE * BLOCK_K * 4;  // 16 KB for either operand
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi, B_hi, A_lo, B_lo
 constexpr int THREADS = 192;
 constexpr int CONVERTER_WARPS = 4;
 constexpr int TMEM_COLS = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+template <bool EXACT> struct Cfg {
+    static constexpr int STAGES = EXACT ? 2 : 3;
+    static constexpr int STAGE_BYTES = (EXACT ? 3 : 4) * TILE_BYTES;  // EXACT: A, B_hi, B_lo; else A_hi, B_hi, A_lo, B_lo
+    static constexpr int B_LO = (EXACT ? 2 : 3) * TILE_BYTES;         // offset of B_lo inside a stage
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 constexpr int B_BOX_BYTES = 32 * BLOCK_K * 4;   // one 32(n) x 32(k) box = 4 KB
 
 constexpr uint32_t IDESC = umma_idesc_tf32(TILE, TILE, /*b_mn_major=*/true);
 
+int launch(const float* s, const float* x, int batch, int c, int hw, float* dx, const float* scale, bool a_is_tf32_exact,
+           void* stream);
+
 struct Args {
     int c, hw;
     float* dx;
+    const float* scale;    // [batch] factor applied in the epilogue, or NULL (= 1)
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool EXACT>
+__global__ void __launch_bounds__(THREADS, EXACT ? 2 : 1)
 isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_x, const Args a) {
+    constexpr int STAGES = Cfg<EXACT>::STAGES, STAGE_BYTES = Cfg<EXACT>::STAGE_BYTES, B_LO = Cfg<EXACT>::B_LO;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -96,6 +112,7 @@ isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constan
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
+                if (EXACT) mbar_wait(full_bar(s), ph);  // A goes from TMA straight to the tensor core: observe its arrival here too
                 mbar_wait(ready_bar(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t stage = base + s * STAGE_BYTES;
@@ -103,29 +120,32 @@ isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constan
                 for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
                     // A (K-major): +32 B inside the swizzle row per k step; B (MN-major): next 8-row k group
                     const uint64_t a_hi = umma_desc_sw128(stage + ks * UMMA_K * 4, 16, 1024);
-                    const uint64_t a_lo = umma_desc_sw128(stage + 2 * TILE_BYTES + ks * UMMA_K * 4, 16, 1024);
                     const uint64_t b_hi = umma_desc(stage + TILE_BYTES + ks * 1024, B_BOX_BYTES, 512, 1);
-                    const uint64_t b_lo = umma_desc(stage + 3 * TILE_BYTES + ks * 1024, B_BOX_BYTES, 512, 1);
+                    const uint64_t b_lo = umma_desc(stage + B_LO + ks * 1024, B_BOX_BYTES, 512, 1);
                     umma_tf32(tmem_d, a_hi, b_hi, IDESC, (kb | ks) != 0);
                     umma_tf32(tmem_d + TILE, a_hi, b_lo, IDESC, (kb | ks) != 0);
-                    umma_tf32(tmem_d + TILE, a_lo, b_hi, IDESC, 1u);
+                    if (!EXACT) {
+                        const uint64_t a_lo = umma_desc_sw128(stage + 2 * TILE_BYTES + ks * UMMA_K * 4, 16, 1024);
+                        umma_tf32(tmem_d + TILE, a_lo, b_hi, IDESC, 1u);
+                    }
                 }
                 umma_commit(empty_bar(s));
             }
             umma_commit(accum_bar);
         }
     } else {
-        // ===== converters: both operand tiles -> hi in place, lo beside =====
+        // ===== converters: operand tiles -> hi in place, lo beside (EXACT: only B, A is exact as it is) =====
         const int ctid = threadIdx.x - 64;
         for (int kb = 0; kb < n_kb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
             mbar_wait(full_bar(s), ph);
             uint8_t* stage = base_ptr + s * STAGE_BYTES;
-            float4* hi = reinterpret_cast<float4*>(stage);                   // A_hi then B_hi, contiguous
-            float4* lo = reinterpret_cast<float4*>(stage + 2 * TILE_BYTES);  // A_lo then B_lo
+            // general: [A_hi, B_hi] contiguous -> [A_lo, B_lo] two tiles further; EXACT: B_hi -> B_lo one tile further
+            float4* hi = reinterpret_cast<float4*>(stage + (EXACT ? TILE_BYTES : 0));
+            float4* lo = reinterpret_cast<float4*>(stage + 2 * TILE_BYTES);
 #pragma unroll 4
-            for (int i = ctid; i < 2 * TILE_BYTES / 16; i += 128) {
+            for (int i = ctid; i < (EXACT ? 1 : 2) * TILE_BYTES / 16; i += 128) {
                 const float4 v = hi[i];
                 float4 h, l;
                 h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
@@ -145,6 +165,7 @@ isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constan
         const int lane_base = 32 * (warp & 3);
         const int row = m0 + lane_base + lane;
         float* out = a.dx + ((size_t)b * a.c + row) * a.hw + n0;
+        const float sc = a.scale ? a.scale[b] : 1.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < TILE; c0 += 32) {
             uint32_t r[32], x[32];
@@ -158,10 +179,10 @@ isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constan
                     const int n = n0 + c0 + 4 * q;
                     if (n < a.hw)  // hw % 4 == 0, so a float4 is either fully inside or fully outside
                         *reinterpret_cast<float4*>(out + c0 + 4 * q) =
-                            make_float4(__uint_as_float(r[4 * q]) + __uint_as_float(x[4 * q]),
-                                        __uint_as_float(r[4 * q + 1]) + __uint_as_float(x[4 * q + 1]),
-                                        __uint_as_float(r[4 * q + 2]) + __uint_as_float(x[4 * q + 2]),
-                                        __uint_as_float(r[4 * q + 3]) + __uint_as_float(x[4 * q + 3]));
+                            make_float4(sc * (__uint_as_float(r[4 * q]) + __uint_as_float(x[4 * q])),
+                                        sc * (__uint_as_float(r[4 * q + 1]) + __uint_as_float(x[4 * q + 1])),
+                                        sc * (__uint_as_float(r[4 * q + 2]) + __uint_as_float(x[4 * q + 2])),
+                                        sc * (__uint_as_float(r[4 * q + 3]) + __uint_as_float(x[4 * q + 3])));
                 }
             }
         }
@@ -181,7 +202,10 @@ isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constan
 using namespace dgvcc;
 using namespace dgvcc::isw_sx;
 
-extern "C" int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c, int hw, float* dx, void* stream) {
+// dX_b = scale_b * (S_b X_b); a_is_tf32_exact selects the EXACT variant.  Returns DGVCC_ERR_UNSUPPORTED for shapes
+// TMA cannot tile.
+int dgvcc::isw_sx::launch(const float* s, const float* x, int batch, int c, int hw, float* dx, const float* scale,
+                          bool a_is_tf32_exact, void* stream) {
     if (!s || !x || !dx || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     // TMA: 16-byte global strides and bases; tiny channel counts waste the 128-wide tile
     if (hw % 4 != 0 || c % 4 != 0 || c < 32 || ((uintptr_t)s & 15u) || ((uintptr_t)x & 15u) || ((uintptr_t)dx & 15u))
@@ -192,12 +216,22 @@ extern "C" int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c,
         return DGVCC_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
-        DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_sx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_sx_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  Cfg<false>::SMEM_BYTES));
+        DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_sx_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  Cfg<true>::SMEM_BYTES));
         attr_set = true;
     }
     Args a;
-    a.c = c; a.hw = hw; a.dx = dx;
-    isw_sx_tc_kernel<<<dim3(ceil_div(hw, TILE), ceil_div(c, TILE), batch), THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
-        map_s, map_x, a);
+    a.c = c; a.hw = hw; a.dx = dx; a.scale = scale;
+    const dim3 grid(ceil_div(hw, TILE), ceil_div(c, TILE), batch);
+    if (a_is_tf32_exact)
+        isw_sx_tc_kernel<true><<<grid, THREADS, Cfg<true>::SMEM_BYTES, (cudaStream_t)stream>>>(map_s, map_x, a);
+    else
+        isw_sx_tc_kernel<false><<<grid, THREADS, Cfg<false>::SMEM_BYTES, (cudaStream_t)stream>>>(map_s, map_x, a);
     return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c, int hw, float* dx, void* stream) {
+    return dgvcc::isw_sx::launch(s, x, batch, c, hw, dx, nullptr, false, stream);
 }

@@ -14,6 +14,8 @@ Python numbers or 0-dim tensors, as in the reference (cov_settings.py:47,73).
 """
 import os
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -112,6 +114,21 @@ class _Covariance(torch.autograd.Function):
         return dx.view(shape).to(dtype), None
 
 
+_binary_masks = {}  # id(mask tensor) -> (version, bool); dropped when the tensor dies
+
+
+def _mask_is_binary(mask):
+    """True when every entry is 0 or 1: one device read-back per mask tensor (they live for an epoch,
+    cov_settings.py:52-73), cached until the tensor is modified in place or freed."""
+    key = id(mask)
+    hit = _binary_masks.get(key)
+    if hit is None or hit[0] != mask._version:
+        if hit is None:
+            weakref.finalize(mask, _binary_masks.pop, key, None)
+        hit = _binary_masks[key] = (mask._version, bool(((mask == 0) | (mask == 1)).all()))
+    return hit[1]
+
+
 class _WhiteningLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f_map, eye, mask_matrix, margin, num_remove_cov):
@@ -133,20 +150,20 @@ class _WhiteningLoss(torch.autograd.Function):
                                                  b, c, hw, _native.ptr(ws), n, _native.ptr(loss), stream),
                       "dgvcc_isw_loss_forward")
         ctx.save_for_backward(x, f_cor, mask, nr, ws)
-        ctx.meta = (f_map.shape, f_map.dtype, n)
+        ctx.meta = (f_map.shape, f_map.dtype, n, _mask_is_binary(mask_matrix))
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_loss):
         x, f_cor, mask, nr, ws = ctx.saved_tensors
-        shape, dtype, n = ctx.meta
+        shape, dtype, n, binary = ctx.meta
         b, c, hw = x.shape
         dev = x.device
         g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         dx = torch.empty_like(x)
         _native.check(_native.lib().dgvcc_isw_loss_backward(
             _native.ptr(x), _native.ptr(f_cor), _native.ptr(mask), _native.ptr(nr), _native.ptr(g), b, c, hw, _use_tc(),
-            _native.ptr(ws), n, _native.ptr(dx), _native.stream_ptr(dev)), "dgvcc_isw_loss_backward")
+            int(binary), _native.ptr(ws), n, _native.ptr(dx), _native.stream_ptr(dev)), "dgvcc_isw_loss_backward")
         return dx.view(shape).to(dtype), None, None, None, None
 
 

@@ -236,10 +236,13 @@ int dgvcc_isw_covariance_backward(const float* f_map, const float* grad_f_cor, i
 int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, const float* margin, const float* num_remove_cov,
                            int batch, int c, int hw, void* workspace, size_t workspace_bytes, float* loss_out,
                            void* stream);
-/* grad_f_map for grad_loss[0]; re-uses the workspace written by dgvcc_isw_loss_forward. */
+/* grad_f_map for grad_loss[0]; re-uses the workspace written by dgvcc_isw_loss_forward.
+ * mask_is_binary != 0 is the caller's promise that every mask entry is 0 or 1 (what CovMatrix_ISW and
+ * CovMatrix_IRW produce, cov_settings.py:66-73,103): the upstream matrix is then alpha_b * {0,+-1,+-2}, exact in
+ * TF32, and the tensor-core GEMM skips the hi/lo split of that operand.  0 is always correct. */
 int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, const float* mask, const float* num_remove_cov,
-                            const float* grad_loss, int batch, int c, int hw, int use_tensor_cores, void* workspace,
-                            size_t workspace_bytes, float* grad_f_map, void* stream);
+                            const float* grad_loss, int batch, int c, int hw, int use_tensor_cores, int mask_is_binary,
+                            void* workspace, size_t workspace_bytes, float* grad_f_map, void* stream);
 
 /* cal_covstat (models/ISW/__init__.py:93-104): var_out [c,c] = unbiased variance over the
  * batch of f_cor * reverse_eye. */

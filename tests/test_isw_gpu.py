@@ -263,3 +263,27 @@ def test_cal_covstat_to_mask_end_to_end():
     lo.backward()
     torch.testing.assert_close(loss.cpu(), lo, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(xin.grad.cpu(), xo.grad, rtol=1e-4, atol=1e-6 * float(xo.grad.abs().max()))
+
+
+def test_non_binary_mask_takes_the_general_backward():
+    """A mask with fractional weights is legal input; the factored (sign-matrix) tensor-core backward is only
+    promised for 0/1 masks, so this goes through the general 3xTF32 GEMM.  Both against the oracle."""
+    from dgvcc_b200.models.ISW import InstanceWhitening, instance_whitening_loss
+    c, h, w = 128, 32, 40
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(4, c, h, w, generator=g)
+    eye = torch.eye(c)
+    for binary in (True, False):
+        mask = isw_oracle.upper_mask(c, 0.5, 5)
+        if not binary:
+            mask = mask * (0.25 + torch.rand(c, c, generator=g))
+        num = mask.sum()
+        xin = x.clone().cuda().requires_grad_(True)
+        _, wt = InstanceWhitening(c)(xin)
+        loss = instance_whitening_loss(wt, eye.cuda(), mask.cuda(), 0, num.cuda())
+        loss.backward()
+        xo = x.clone().requires_grad_(True)
+        lo = isw_oracle.whitening_loss(isw_oracle.instance_standardize(xo), eye, mask, 0, num)
+        lo.backward()
+        torch.testing.assert_close(loss.cpu(), lo, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(xin.grad.cpu(), xo.grad, rtol=1e-4, atol=2e-6 * float(xo.grad.abs().max()))

@@ -487,9 +487,9 @@ dmap_fixed_template_kernel(double fixed_sigma, double truncate, Stamp* __restric
 // ... and one thread per head fills in the position.
 __global__ void __launch_bounds__(256)
 dmap_prepare_fixed_kernel(const double2* __restrict__ pts, const Stamp* __restrict__ tmpl,
-                          const double* __restrict__ tmpl_tab, const int64_t* __restrict__ meta, int n_images,
+                          const int64_t* __restrict__ meta, int n_images,
                           int total_heads, Stamp* __restrict__ stamps, int4* __restrict__ boxes,
-                          double* __restrict__ wtab, unsigned* __restrict__ fmask) {
+                          unsigned* __restrict__ fmask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_heads) return;
     const int img = find_image(meta, n_images + 1, M_PT_OFF, i);
@@ -499,9 +499,7 @@ dmap_prepare_fixed_kernel(const double2* __restrict__ pts, const Stamp* __restri
     const int radius = s.radius;
     if (!stamp_pixel(pts[i], height, width, s.ix, s.iy)) {
         s.radius = -1; s.coef = 0.0; s.norm = 1.0;
-    } else if (radius < TAB) {
-        for (int d = 0; d <= radius; ++d) wtab[(size_t)i * TAB + d] = __ldg(tmpl_tab + d);
-    }
+    }  // no per-head weight table: the splat reads the template's (shared_tab)
     const int4 box = stamp_box(s.ix, s.iy, s.radius);
     stamps[i] = s;
     boxes[i] = box;
@@ -616,7 +614,8 @@ dmap_tile_setup_kernel(const int64_t* __restrict__ meta, int n_images, int fine_
 
 __global__ void __launch_bounds__(SPLAT_THREADS, 9)
 dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ wtab, const int4* __restrict__ boxes,
-                  const TileDesc* __restrict__ desc, const int32_t* __restrict__ clist, float* __restrict__ density) {
+                  const TileDesc* __restrict__ desc, const int32_t* __restrict__ clist,
+                  const double* __restrict__ shared_tab, float* __restrict__ density) {
     __shared__ int list[SPLAT_THREADS];
     __shared__ int4 lbox[SPLAT_THREADS];     // boxes of the listed heads
     __shared__ int warp_cnt[SPLAT_THREADS / 32];
@@ -625,8 +624,14 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
     __shared__ double gwy[GEN_MAX][FINE_H];  // wide stamps: fl32-rounded row weights, widened again (exact)
     __shared__ double gwx[GEN_MAX][FINE_W];
     __shared__ int gen_head[GEN_MAX];
+    __shared__ double stab[2][TAB];          // fixed sigma: the one table every narrow stamp shares, and its fl32 twin
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (shared_tab && tid < TAB) {
+        const double w = __ldg(shared_tab + tid);
+        stab[0][tid] = w;
+        stab[1][tid] = (double)(float)w;
+    }  // ordered before its first use by the barriers of the list scan
     const int4* dp = reinterpret_cast<const int4*>(desc + blockIdx.x);
     const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
     const longlong2 d2 = __ldg(reinterpret_cast<const longlong2*>(dp + 2));
@@ -674,14 +679,26 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
                     const unsigned long long range = (g1 - g0 == 64) ? ~0ull : (((1ull << (g1 - g0)) - 1ull) << g0);
                     const unsigned long long wide_here = wide_mask & range;
                     const int n_wide = __popcll(wide_here);
-                    // narrow heads: copy the weight tables (a warp reads one head's table per step, 8 heads in flight)
-#pragma unroll 2
-                    for (int t = g0 + warp; t < g1; t += SPLAT_WARPS) {
-                        const int r = (lbox[c0 + t].y - lbox[c0 + t].x) >> 1;
-                        if (lane <= r && r < TAB) {
-                            const double w = __ldg(wt + (size_t)list[c0 + t] * TAB + lane);
-                            tab[t][lane] = w;
-                            tabf[t][lane] = (double)(float)w;
+                    // narrow heads: copy the weight tables (a warp reads one head's table per step, all of its
+                    // steps in flight together); with a shared table (fixed sigma) there is nothing to copy
+                    if (!shared_tab) {
+                        double wv[GROUP / SPLAT_WARPS];
+#pragma unroll
+                        for (int u = 0; u < GROUP / SPLAT_WARPS; ++u) {
+                            const int t = g0 + warp + u * SPLAT_WARPS;
+                            wv[u] = 0.0;
+                            if (t < g1) {
+                                const int r = (lbox[c0 + t].y - lbox[c0 + t].x) >> 1;
+                                if (lane <= r && r < TAB) wv[u] = __ldg(wt + (size_t)list[c0 + t] * TAB + lane);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < GROUP / SPLAT_WARPS; ++u) {
+                            const int t = g0 + warp + u * SPLAT_WARPS;
+                            if (t < g1) {  // entries past the radius are never read
+                                tab[t][lane] = wv[u];
+                                tabf[t][lane] = (double)(float)wv[u];
+                            }
                         }
                     }
                     if (tid >= g0 && tid < g1 && ((wide_mask >> tid) & 1ull))
@@ -717,13 +734,15 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
                             if (r < TAB) {
                                 const int dx = abs(x - ((b.x + b.y) >> 1));
                                 if (__any_sync(FULL_MASK, dx <= r)) {
-                                    const double cx = dx <= r ? tab[hd][dx] : 0.0;
+                                    const double* tb = shared_tab ? stab[0] : tab[hd];
+                                    const double* tbf = shared_tab ? stab[1] : tabf[hd];
+                                    const double cx = dx <= r ? tb[dx] : 0.0;
                                     const int dy0 = yb - ((b.z + b.w) >> 1);
 #pragma unroll
                                     for (int k = 0; k < SPLAT_RPT; ++k) {
                                         const int dy = abs(dy0 + k);
                                         if (dy <= r)  // warp-uniform
-                                            acc[k] = __fadd_rn(acc[k], (float)__dmul_rn(tabf[hd][dy], cx));
+                                            acc[k] = __fadd_rn(acc[k], (float)__dmul_rn(tbf[dy], cx));
                                     }
                                 }
                             } else {
@@ -890,8 +909,8 @@ extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma,
                 (const double2*)pts_xy, sigma, truncate, meta, n_images, heads, stamps, boxes, wtab, fmask);
         } else {
             dmap_fixed_template_kernel<<<1, 32, 0, st>>>(fixed_sigma, truncate, tmpl, tmpl_tab);
-            dmap_prepare_fixed_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, tmpl, tmpl_tab, meta,
-                                                                            n_images, heads, stamps, boxes, wtab, fmask);
+            dmap_prepare_fixed_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, tmpl, meta, n_images,
+                                                                            heads, stamps, boxes, fmask);
         }
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
         dmap_coarse_kernel<false><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
@@ -905,6 +924,8 @@ extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma,
     dmap_tile_setup_kernel<<<ceil_div((int)plan->fine_tiles, 256), 256, 0, st>>>(meta, n_images, (int)plan->fine_tiles, fmask,
                                                                                  ctotal, heads > 0, desc);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    dmap_splat_kernel<<<(unsigned)plan->fine_tiles, SPLAT_THREADS, 0, st>>>(stamps, wtab, boxes, desc, clist, density);
+    // fixed sigma with a narrow stamp: every head shares the template table (wide stamps never use tables)
+    dmap_splat_kernel<<<(unsigned)plan->fine_tiles, SPLAT_THREADS, 0, st>>>(stamps, wtab, boxes, desc, clist,
+                                                                            sigma ? nullptr : tmpl_tab, density);
     return (int)cudaGetLastError();
 }

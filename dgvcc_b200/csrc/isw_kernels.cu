@@ -164,15 +164,21 @@ isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits,
     const int i0 = ti * tile + 32 * sy, j0 = tj * tile + 32 * sx;
     const bool diag_block = ti == tj && sx == sy;
     const float denom = (float)(hw - 1);
+    // the thread's four rows are summed side by side (independent chains, loads of several splits in flight);
+    // each entry still adds its splits in split order
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* p = p0 + (size_t)(32 * sy + ty) * tile + 32 * sx + tx;
+    const size_t split_stride = (size_t)n_tiles * tile_elems;
+#pragma unroll 4
+    for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] += p[(size_t)sp * split_stride + (size_t)(8 * r) * tile];
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int li = ty + 8 * r, i = i0 + li, j = j0 + tx;
-        float s = 0.f;
-        const float* p = p0 + (size_t)(32 * sy + li) * tile + 32 * sx + tx;
-#pragma unroll 8
-        for (int sp = 0; sp < splits; ++sp) s += p[(size_t)sp * n_tiles * tile_elems];  // loads batched, adds in split order
         // torch: bmm(...).div(HW-1) is a true division; + (eps * eye)
-        const float v = s / denom;
+        const float v = acc[r] / denom;
         tr[li][tx] = v;
         if (i < c && j < c && (!diag_block || tx >= li)) fc[(size_t)i * c + j] = v + eps * eye[(size_t)i * c + j];
     }

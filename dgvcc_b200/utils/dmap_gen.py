@@ -164,12 +164,16 @@ def _image_shape(img_fn):
     return np.empty((h, w, 0))
 
 
-def run(img_fn):
-    """File protocol of dmap_gen.py:83-95: <name>.<ext> + <name>.npy -> <name>_dmap.npy, skipped when present."""
+def _paths(img_fn):
     img_ext = os.path.splitext(img_fn)[1]
     basename = os.path.basename(img_fn).replace(img_ext, '')
     gt_fn = img_fn.replace(img_ext, '.npy')
-    dmap_fn = gt_fn.replace(basename, basename + '_dmap')
+    return gt_fn, gt_fn.replace(basename, basename + '_dmap')
+
+
+def run(img_fn):
+    """File protocol of dmap_gen.py:83-95: <name>.<ext> + <name>.npy -> <name>_dmap.npy, skipped when present."""
+    gt_fn, dmap_fn = _paths(img_fn)
 
     if os.path.exists(dmap_fn):
         return
@@ -178,6 +182,19 @@ def run(img_fn):
     gt = np.load(gt_fn)
     dmap = gaussian_filter_density_fixed(img, gt)
     np.save(dmap_fn, dmap)
+
+
+def run_many(img_fns, batch=32):
+    """``run`` for a list of images, ``batch`` at a time through the batched launch set (what replaces the
+    reference's ``Pool(8)``, dmap_gen.py:116-117)."""
+    todo = [fn for fn in img_fns if not os.path.exists(_paths(fn)[1])]
+    for k in range(0, len(todo), batch):
+        chunk = todo[k:k + batch]
+        shapes = [_image_shape(fn).shape[:2] for fn in chunk]
+        gts = [np.load(_paths(fn)[0]) for fn in chunk]
+        gts = [g if len(g) else np.zeros((0, 2)) for g in gts]
+        for fn, dmap in zip(chunk, gaussian_filter_density_batch(shapes, gts, fixed=True)):
+            np.save(_paths(fn)[1], dmap)
 
 
 if __name__ == '__main__':
@@ -194,6 +211,5 @@ if __name__ == '__main__':
         img_fns += glob(os.path.join(path, phase, '*.jpg'))
     img_fns = [fn for fn in img_fns if 'aug' not in fn]
 
-    # the reference fans out over Pool(8); one GPU stream is faster than that and needs no fork
-    for fn in img_fns:
-        run(fn)
+    # the reference fans out over Pool(8); batched launches on one GPU stream are faster and need no fork
+    run_many(img_fns)

@@ -210,6 +210,90 @@ def bench_bay(cpu):
     print(json.dumps(line), flush=True)
 
 
+def bench_den(cpu):
+    """Row f3: dataset-side density targets (crop + 8x8 sum-pool + flip + 16x16 occupancy) for a batch of maps."""
+    from dgvcc_b200.datasets import den_targets
+    rng = np.random.default_rng(8600)
+    b, h, w, crop, down = 64, 1536, 2048, (1024, 1024), 8
+    maps = [torch.from_numpy(np.where(rng.random((h, w)) < 0.01, rng.random((h, w)), 0).astype(np.float32)).to(dev) for _ in range(b)]
+    geoms = [(0, 0, int(rng.integers(0, h - crop[0] + 1)), int(rng.integers(0, w - crop[1] + 1)), k % 2) for k in range(b)]
+    lib = _native.lib()
+    flat = torch.cat([m.reshape(-1) for m in maps])
+    meta = np.zeros((b, _native.DEN_META_COLS), dtype=np.int64)
+    for k, g in enumerate(geoms):
+        meta[k] = (k * h * w, h, w, g[0], g[1], g[2], g[3], g[4])
+    d_meta = torch.from_numpy(meta).to(dev)
+    dh, dw = crop[0] // down, crop[1] // down
+    out = torch.empty((b, 1, dh, dw), dtype=torch.float32, device=dev)
+    bm = torch.empty((b, dh // 16, dw // 16), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for rep in range(6):
+        flush.zero_()
+        e0, e1 = ev(), ev()
+        e0.record()
+        _native.check(lib.dgvcc_den_train_targets(_native.ptr(flat), _native.ptr(d_meta), b, crop[0], crop[1], down, _native.ptr(out),
+                                                  _native.ptr(bm), _native.stream_ptr(dev)), "den")
+        e1.record()
+        torch.cuda.synchronize()
+        if rep:
+            ts.append(e0.elapsed_time(e1))
+    t0 = time.perf_counter()
+    den_targets.train_density_targets(maps, geoms, crop, down)
+    torch.cuda.synchronize()
+    api_s = time.perf_counter() - t0
+    bytes_alg = b * (crop[0] * crop[1] * 4 + dh * dw * 4 + (dh // 16) * (dw // 16) * 4)
+    line = {"workload": f"SURVEY 8f rank 3: density targets of {b} maps {h}x{w}: crop {crop[0]}x{crop[1]}, {down}x{down} sum-pool, flip, 16x16 occupancy",
+            "metric": "maps/s", "value_device": b / (min(ts) * 1e-3), "ms": min(ts), "value_public_api_device_maps": b / api_s,
+            "roofline": {"bound": "hbm", "achieved": bytes_alg / (min(ts) * 1e-3) / 1e9, "peak": HBM_GBS, "unit": "GB/s",
+                         "frac": bytes_alg / (min(ts) * 1e-3) / 1e9 / HBM_GBS,
+                         "note": "algorithmic bytes: every source pixel of the crops read once, targets written once"}}
+    if cpu:
+        from oracle import den_targets_oracle as do
+        host = [m.cpu().numpy() for m in maps[:8]]
+        t0 = time.perf_counter()
+        for m, g in zip(host, geoms[:8]):
+            do.block_occupancy(do.train_density(m, g[0], g[1], g[2], g[3], crop[0], crop[1], down, g[4]))
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 8 / dt, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "oracle port of den_cls_dataset.py:109-150 + :60-61 (torch CPU ops) on 8 of the maps"}
+    print(json.dumps(line), flush=True)
+
+
+def bench_cov(cpu):
+    """Row f2: CovMatrix_ISW.set_mask_matrix (average of the statistics, top-k mask, AND with the previous mask)."""
+    from dgvcc_b200.models.ISW.cov_settings import topk_mask
+    c, n_stats = 512, 4
+    g = torch.Generator().manual_seed(8700)
+    stats = (torch.rand(n_stats, c * c, generator=g) ** 3).to(dev)
+    prev = (torch.rand(c * c, generator=g) < 0.7).float().to(dev)
+    k = (c * c - c) // 2 - (c * c - c) // 4
+    ts = []
+    for rep in range(6):
+        e0, e1 = ev(), ev()
+        e0.record()
+        topk_mask(stats, n_stats, k, prev)
+        e1.record()
+        torch.cuda.synchronize()
+        if rep:
+            ts.append(e0.elapsed_time(e1))
+    line = {"workload": f"SURVEY 8f rank 2: CovMatrix_ISW mask construction, C={c} ({c * c} entries, {n_stats} statistics, k={k})",
+            "metric": "masks/s", "value": 1e3 / min(ts), "ms": min(ts)}
+    if cpu:
+        from oracle.cov_settings_oracle import CovMatrixISW
+        cm = CovMatrixISW(c, 2.0)
+        cm.mask_matrix = prev.cpu().view(c, c)
+        sc = stats.cpu()
+        t0 = time.perf_counter()
+        for s_ in sc:
+            cm.set_variance_of_covariance(s_.view(c, c))
+        cm.set_mask_matrix()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1 / dt, "unit": "masks/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "oracle port of cov_settings.py:52-89 (torch CPU topk), same statistics"}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
@@ -221,3 +305,7 @@ if __name__ == "__main__":
         bench_isw(a.cpu)
     if a.only in ("", "bay"):
         bench_bay(a.cpu)
+    if a.only in ("", "den"):
+        bench_den(a.cpu)
+    if a.only in ("", "cov"):
+        bench_cov(a.cpu)

@@ -118,6 +118,19 @@ def test_batch_api_and_file_protocol(tmp_path):
     mtime = os.path.getmtime(tmp_path / "img_7_dmap.npy")
     dmap_gen.run(str(fn))
     assert os.path.getmtime(tmp_path / "img_7_dmap.npy") == mtime
+    # run_many(): what the CLI does for a directory -- batched, existing outputs skipped
+    fns = [str(fn)]
+    for k, (s, p) in enumerate(zip(shapes, plist)):
+        f2 = tmp_path / f"img_b{k}.jpg"
+        Image.fromarray(np.zeros(s + (3,), dtype=np.uint8)).save(f2)
+        np.save(tmp_path / f"img_b{k}.npy", p)
+        fns.append(str(f2))
+    dmap_gen.run_many(fns, batch=2)
+    assert os.path.getmtime(tmp_path / "img_7_dmap.npy") == mtime
+    for k, (s, p) in enumerate(zip(shapes, plist)):
+        saved = np.load(tmp_path / f"img_b{k}_dmap.npy")
+        assert saved.shape == s and saved.dtype == np.float32
+        assert_map_close(saved, dmap_oracle.density_closed_form(s, p, fixed=True), "run_many()")
 
 
 def test_batched_launch_matches_oracle_on_a_ragged_list():

@@ -97,6 +97,34 @@ def cpu_step(wl, picked):
     return time.perf_counter() - t0
 
 
+def profiled_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the three sweep kernels (per launch each, summed: they are
+    the path's exponential-carrying kernels), from the newest committed `ncu --set full` capture of this workload
+    (profiles/r*_bl_ncu_raw.csv); None when no capture is in the tree."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_bl_ncu_raw.csv")))
+    if not files:
+        return None, "no ncu capture under profiles/"
+    rows = list(csv.reader(open(files[-1])))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, per = 0.0, {}
+    for r in data:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0]
+        if name not in ("bl_z_kernel", "bl_counts_kernel", "bl_grad_kernel"):
+            continue
+        b = 0.0
+        for col in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            k = hdr.index(col)
+            b += float(r[k].replace(",", "")) * scale.get(units[k], 1.0)
+        per[name] = b
+        total += b
+    note = (f"{os.path.basename(files[-1])}: " + ", ".join(f"{k} {v / 1e6:.1f} MB" for k, v in per.items()) +
+            "; against ~6 MB of algorithmic inputs/outputs per step the sweeps are nowhere near HBM-bound (MUFU-bound)")
+    return total, note
+
+
 def cpu_baseline(wl, budget_s, repeats=2):
     use_all_host_threads()
     picked = cpu_sample(wl, budget_s / repeats)
@@ -389,6 +417,7 @@ def run_gpu(args, emit=print):
         algorithmic = 3.0 * pairs                       # 3 exponentials per pair, dense
         executed = (2.0 + kept_frac) * pairs            # backward skips the 10 % of rows the top-k trims
         achieved = executed / (path_ms * 1e-3)
+        traffic, traffic_note = profiled_dram_traffic()
         out = {
             "metric": "Bayesian-loss fwd+bwd images/s (QNRF shape)", "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -413,7 +442,7 @@ def run_gpu(args, emit=print):
                                     "dense path that value / e2e / roofline measure")},
             "roofline": {
                 "bound": "sfu", "achieved": achieved / 1e9, "peak": peak_ex2 / 1e9, "unit": "Gexp/s",
-                "frac": achieved / peak_ex2, "traffic": None,
+                "frac": achieved / peak_ex2, "traffic": traffic, "traffic_note": traffic_note,
                 "note": ("fused BL path (bl_min+bl_z+bl_counts+bl_reduce_counts+bl_select+bl_grad+bl_grad_reduce), MUFU.EX2-bound; achieved = executed "
                          "exponentials / sum of kernel times; peak = dgvcc_probe_ex2 measured in this run "
                          "(MEASURED_PEAKS.json carries no SFU peak)"),

@@ -269,7 +269,7 @@ enum MetaCol {
     M_CTILE_OFF = 8, // first coarse tile (index into ctotal / ccount rows)
     M_KTASK_OFF = 9, // first kNN task (query block x candidate slice)
     M_KPART_OFF = 10,// first entry of the image's kNN partial lists (slices x n x 4)
-    M_CCOUNT_OFF = 11,
+    M_KQB_OFF = 11,  // first kNN query block (256 heads)
     META_COLS = DGVCC_DMAP_META_COLS
 };
 static_assert(META_COLS == 12, "header and kernels disagree on the meta row width");
@@ -282,7 +282,30 @@ constexpr int FINE_H = SPLAT_WARPS * SPLAT_RPT;  // 32
 constexpr int COARSE_THREADS = 256;
 constexpr int COARSE = 256;       // coarse tile side, a multiple of both fine sides
 constexpr int CHUNK = 2048;       // heads per coarse task
-constexpr int KNN_SLICE = 2048;   // candidates per batched kNN task
+constexpr int KNN_SLICE = 2048;   // fewest candidates per batched kNN task
+
+// Candidate slices of an image with n heads: at most max_slices equal slices of at least KNN_SLICE candidates.
+// Every slice restarts its neighbour list, which costs insertions, so a batch that already fills the chip with
+// query blocks uses few slices and a single big image uses many.  Slice 0 is scanned first (phase 0) and gives
+// the others (phase 1) their bound.  (Measured on the 64-image set: a short bound-only slice 0 plus long phase-1
+// slices is slower -- 1.39 vs 1.26 ms -- than equal halves: the bound of a longer scan is tighter.)
+struct KnnSlicing {
+    int first_len, rest, rest_len;
+    __host__ __device__ int slices() const { return 1 + rest; }
+    __host__ __device__ int begin(int s) const { return s == 0 ? 0 : first_len + (s - 1) * rest_len; }
+    __host__ __device__ int len(int s) const { return s == 0 ? first_len : rest_len; }
+};
+__host__ __device__ __forceinline__ KnnSlicing knn_slicing(int n, int max_slices) {
+    KnnSlicing k;
+    int s = (n + KNN_SLICE - 1) / KNN_SLICE;
+    if (s > max_slices) s = max_slices;
+    if (s < 1) s = 1;
+    const int len = ((n + s - 1) / s + 255) / 256 * 256;
+    k.first_len = n < len ? n : len;
+    k.rest_len = len;
+    k.rest = (n - k.first_len + len - 1) / len;
+    return k;
+}
 constexpr int TAB = 32;           // stamps of radius < TAB read their weights from the per-head table
 constexpr int GROUP = 32;         // heads staged together by a fine tile (<= 64: masks are 64-bit)
 constexpr int GEN_MAX = 8;        // of which at most this many wide ones (radius >= TAB: weights evaluated per tile)
@@ -299,37 +322,137 @@ __device__ __forceinline__ int find_image(const int64_t* __restrict__ meta, int 
 }
 
 // ------------------------------------------------------------------------------- batched kNN
+// fp32 copies of the heads + the largest |coordinate| of every image (for the error bound of the fp32 filter).
+__global__ void __launch_bounds__(256)
+dmap_knn_prep_kernel(const double2* __restrict__ pts, const int64_t* __restrict__ meta, int n_images, int total_heads,
+                     float2* __restrict__ pts32, int* __restrict__ img_max_bits) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_heads) return;
+    const double2 p = pts[g];
+    pts32[g] = make_float2(__double2float_rn(p.x), __double2float_rn(p.y));
+    const float m = __double2float_ru(fmax(fabs(p.x), fabs(p.y)));  // non-negative floats order like their bit patterns
+    const int img = find_image(meta, n_images + 1, M_PT_OFF, g);
+    // one atomic per (warp, image): lanes of the same image reduce among themselves first
+    const unsigned peers = __match_any_sync(__activemask(), img);
+    const int warp_max = __reduce_max_sync(peers, __float_as_int(m));
+    if ((threadIdx.x & 31) == __ffs(peers) - 1 && warp_max > img_max_bits[img]) atomicMax(img_max_bits + img, warp_max);
+}
+
+// Two fp32 values in one 64-bit register for Blackwell's packed add / mul / fma.f32x2 (SASS FADD2 / FMUL2 / FFMA2).
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Upper bound, in fp32, of what the fp32 evaluation of a squared distance can return when the exact fp64 value is
+// below `thr`.  With u = 2^-24, M >= every |coordinate| of the image and d2 the exact value, the fp32 result is within
+//     E(d2) <= 5.7 u M sqrt(d2) + 4.2 u d2 + 16 u^2 M^2
+// of d2 (inputs rounded to fp32: <= u M each; the difference, the two squares and the sum: relative u each); E grows
+// with d2, so d2 < thr implies fp32(d2) <= thr + E(thr).  The constants below are more than twice the derived ones and
+// every step rounds up.  Candidates above the bound are skipped, all others are evaluated exactly in fp64.
+__device__ __forceinline__ float knn_bound32(double thr, float big_m) {
+    if (!(thr < 1.0e30) || !(big_m < 1.0e15f)) return INFINITY;  // nothing to filter with / out of the bound's range
+    constexpr float U = 5.9604645e-8f;
+    const float t = __double2float_ru(thr);
+    const float um = __fmul_ru(U, big_m);
+    float e = __fmul_ru(__fmul_ru(12.f, um), __fmul_ru(__fsqrt_ru(t), 1.000001f));
+    e = __fadd_ru(e, __fmul_ru(__fmul_ru(16.f, U), t));
+    e = __fadd_ru(e, __fmul_ru(32.f, __fmul_ru(um, um)));
+    return __fadd_ru(t, e);
+}
+
 // Task = (image, block of 256 query heads, slice of KNN_SLICE candidates); the merge kernel combines the
-// per-slice lists.  Same arithmetic and (distance, index) order as the single-image kernels above.
+// per-slice lists.  Same fp64 arithmetic and (distance, index) order as the single-image kernels above.
+// Two things keep the FP64 pipe (the bound of the plain brute-force loop) out of the inner loop:
+// * an fp32 filter: the squared distance is first evaluated in fp32 (4 instructions on the FP32 pipe) and compared
+//   with knn_bound32 of the current threshold; only candidates that pass are evaluated in fp64, exactly as before,
+//   so the result is unchanged bit for bit;
+// * two phases: a slice that starts from an empty list inserts all the time, and one inserting lane drags its whole
+//   warp through the insertion network.  Phase 0 runs slice 0 of every query block, phase 1 (all other slices)
+//   starts each query with the 4th-best distance of its slice 0 as an upper bound: a later candidate at that
+//   distance or beyond cannot enter the final list (later slices hold higher indices, which lose ties).
 __global__ void __launch_bounds__(KNN_THREADS)
-dmap_knn_batch_kernel(const double2* __restrict__ pts, const int64_t* __restrict__ meta, int n_images,
+dmap_knn_batch_kernel(const double2* __restrict__ pts, const float2* __restrict__ pts32, const int* __restrict__ img_max_bits,
+                      const int64_t* __restrict__ meta, int n_images, int max_slices, int phase,
                       double* __restrict__ part_d2, int32_t* __restrict__ part_idx) {
     __shared__ double2 cand[KNN_THREADS];
-    const int img = find_image(meta, n_images + 1, M_KTASK_OFF, blockIdx.x);
+    __shared__ float4 cand32[KNN_THREADS / 2];  // fp32 candidates, negated, in pairs: (-x0, -x1, -y0, -y1)
+    int img, slice, qb;
+    if (phase == 0) {
+        img = find_image(meta, n_images + 1, M_KQB_OFF, blockIdx.x);
+        slice = 0;
+        qb = blockIdx.x - (int)meta[(size_t)img * META_COLS + M_KQB_OFF];
+    } else {
+        // cumulative count of phase-1 tasks = all tasks - query blocks
+        int lo = 0, hi = n_images + 1;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            const int64_t* mm = meta + (size_t)mid * META_COLS;
+            if (__ldg(mm + M_KTASK_OFF) - __ldg(mm + M_KQB_OFF) <= (int64_t)blockIdx.x) lo = mid; else hi = mid;
+        }
+        img = lo;
+        const int64_t* mm = meta + (size_t)img * META_COLS;
+        const int rest = knn_slicing((int)mm[M_N], max_slices).rest;
+        const int local = blockIdx.x - (int)(mm[M_KTASK_OFF] - mm[M_KQB_OFF]);
+        slice = 1 + local % rest;
+        qb = local / rest;
+    }
     const int64_t* m = meta + (size_t)img * META_COLS;
     const int n = (int)m[M_N];
-    const int slices = ceil_div(n, KNN_SLICE);
-    const int local = blockIdx.x - (int)m[M_KTASK_OFF];
-    const int slice = local % slices, qb = local / slices;
     const double2* p = pts + m[M_PT_OFF];
+    const float2* p32 = pts32 + m[M_PT_OFF];
+    const float big_m = __int_as_float(img_max_bits[img]);
     const int i = qb * KNN_THREADS + threadIdx.x;
     const double2 q = p[min(i, n - 1)];
+    const float2 qf = p32[min(i, n - 1)];
     double best[4];
     int bidx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { best[k] = INFINITY; bidx[k] = n; }
-    const int j_begin = slice * KNN_SLICE, j_end = min(n, j_begin + KNN_SLICE);
+    const double bound = phase == 0 ? INFINITY : part_d2[(size_t)m[M_KPART_OFF] + (size_t)min(i, n - 1) * 4 + 3];
+    double thr = bound;  // = min(best[3], bound)
+    float thr32 = knn_bound32(thr, big_m);
+    const f2 qx2 = pack2(qf.x, qf.x), qy2 = pack2(qf.y, qf.y);
+    const KnnSlicing ks = knn_slicing(n, max_slices);
+    const int j_begin = ks.begin(slice), j_end = min(n, j_begin + ks.len(slice));
     for (int j0 = j_begin; j0 < j_end; j0 += KNN_THREADS) {
         __syncthreads();
-        if (j0 + threadIdx.x < j_end) cand[threadIdx.x] = p[j0 + threadIdx.x];
+        {
+            // candidates past the end of the slice become +inf: their fp32 distance is inf and never passes
+            float2 c = make_float2(-INFINITY, -INFINITY);
+            if (j0 + threadIdx.x < j_end) {
+                cand[threadIdx.x] = p[j0 + threadIdx.x];
+                c = p32[j0 + threadIdx.x];
+            }
+            float* c32 = reinterpret_cast<float*>(cand32) + 4 * (threadIdx.x >> 1) + (threadIdx.x & 1);
+            c32[0] = -c.x;
+            c32[2] = -c.y;
+        }
         __syncthreads();
         const int lim = min(KNN_THREADS, j_end - j0);
-#pragma unroll 4
-        for (int t = 0; t < lim; ++t) {
+        auto exact = [&](int t) {  // the reference's fp64 evaluation, for a candidate the fp32 filter let through
             const double dx = __dsub_rn(q.x, cand[t].x);
             const double dy = __dsub_rn(q.y, cand[t].y);
             const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (d2 < best[3]) knn_insert(best, bidx, d2, j0 + t);
+            if (d2 < thr) {
+                knn_insert(best, bidx, d2, j0 + t);
+                thr = fmin(best[3], bound);
+                thr32 = knn_bound32(thr, big_m);
+            }
+        };
+        // two candidates per step with Blackwell's packed fp32x2 add / mul / fma (each half an ordinary IEEE op)
+#pragma unroll 4
+        for (int t = 0; t < lim; t += 2) {
+            const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(&cand32[t >> 1]);  // {(-x0,-x1), (-y0,-y1)}
+            const f2 fx = add2(qx2, c.x), fy = add2(qy2, c.y);
+            float a0, a1;
+            unpack2(fma2(fx, fx, mul2(fy, fy)), a0, a1);
+            if (fminf(a0, a1) <= thr32) {
+                if (a0 <= thr32) exact(t);
+                if (a1 <= thr32 && t + 1 < lim) exact(t + 1);
+            }
         }
     }
     if (i >= n) return;
@@ -340,14 +463,14 @@ dmap_knn_batch_kernel(const double2* __restrict__ pts, const int64_t* __restrict
 
 __global__ void __launch_bounds__(KNN_THREADS)
 dmap_knn_merge_batch_kernel(const double* __restrict__ part_d2, const int32_t* __restrict__ part_idx,
-                            const int64_t* __restrict__ meta, int n_images, int total_heads,
+                            const int64_t* __restrict__ meta, int n_images, int total_heads, int max_slices,
                             int32_t* __restrict__ nn_idx, double* __restrict__ nn_dist, double* __restrict__ sigma) {
     const int g = blockIdx.x * KNN_THREADS + threadIdx.x;
     if (g >= total_heads) return;
     const int img = find_image(meta, n_images + 1, M_PT_OFF, g);
     const int64_t* m = meta + (size_t)img * META_COLS;
     const int n = (int)m[M_N], i = g - (int)m[M_PT_OFF];
-    const int slices = ceil_div(n, KNN_SLICE);
+    const int slices = knn_slicing(n, max_slices).slices();
     double best[4];
     int bidx[4];
 #pragma unroll
@@ -548,7 +671,7 @@ dmap_coarse_kernel(const int4* __restrict__ boxes, const int64_t* __restrict__ m
     const int chunk = local % nchunks, ct = local / nchunks;
     const int x0 = (ct % ctx) * COARSE, y0 = (ct / ctx) * COARSE;
     const int4* b = boxes + m[M_PT_OFF];
-    int32_t* cnt_row = ccount + m[M_CCOUNT_OFF] + (size_t)ct * nchunks;
+    int32_t* cnt_row = ccount + m[M_CTASK_OFF] + (size_t)ct * nchunks;
     int pos = 0;
     int32_t* out = nullptr;
     if (WRITE) {
@@ -817,25 +940,31 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
                                      int64_t* meta, dgvcc_dmap_plan* plan) {
     if (n_images <= 0 || !heights || !widths || !counts || !meta || !plan) return DGVCC_ERR_ARG;
     int64_t acc[META_COLS] = {0};
+    // kNN: as many candidate slices per image as it takes to fill the chip with tasks, no more
+    int64_t query_blocks = 0;
+    for (int i = 0; i < n_images; ++i) query_blocks += counts[i] > 0 ? ceil_div(counts[i], KNN_THREADS) : 0;
+    int max_slices = query_blocks > 0 ? (int)((148 * 8 + query_blocks - 1) / query_blocks) : 1;
+    if (max_slices > 64) max_slices = 64;
+    plan->knn_max_slices = max_slices;
     for (int i = 0; i <= n_images; ++i) {
         int64_t* m = meta + (size_t)i * META_COLS;
         m[M_PT_OFF] = acc[M_PT_OFF]; m[M_OUT_OFF] = acc[M_OUT_OFF]; m[M_FTILE_OFF] = acc[M_FTILE_OFF];
         m[M_CTASK_OFF] = acc[M_CTASK_OFF]; m[M_CLIST_OFF] = acc[M_CLIST_OFF]; m[M_CTILE_OFF] = acc[M_CTILE_OFF];
-        m[M_KTASK_OFF] = acc[M_KTASK_OFF]; m[M_KPART_OFF] = acc[M_KPART_OFF]; m[M_CCOUNT_OFF] = acc[M_CCOUNT_OFF];
+        m[M_KTASK_OFF] = acc[M_KTASK_OFF]; m[M_KPART_OFF] = acc[M_KPART_OFF]; m[M_KQB_OFF] = acc[M_KQB_OFF];
         if (i == n_images) { m[M_N] = m[M_H] = m[M_W] = 0; break; }
         const int64_t n = counts[i], h = heights[i], w = widths[i];
         if (n < 0 || h <= 0 || w <= 0) return DGVCC_ERR_ARG;
         m[M_N] = n; m[M_H] = h; m[M_W] = w;
         const int64_t ctiles = (int64_t)ceil_div((int)w, COARSE) * ceil_div((int)h, COARSE);
-        const int64_t nchunks = ceil_div((int)n, CHUNK), slices = ceil_div((int)n, KNN_SLICE);
+        const int64_t nchunks = ceil_div((int)n, CHUNK), slices = n > 0 ? knn_slicing((int)n, max_slices).slices() : 0;
         acc[M_PT_OFF] += n;
         acc[M_OUT_OFF] += h * w;
         acc[M_FTILE_OFF] += (int64_t)ceil_div((int)w, FINE_W) * ceil_div((int)h, FINE_H);
         acc[M_CTASK_OFF] += ctiles * nchunks;
-        acc[M_CCOUNT_OFF] += ctiles * nchunks;
         acc[M_CLIST_OFF] += ctiles * n;
         acc[M_CTILE_OFF] += ctiles;
         acc[M_KTASK_OFF] += (int64_t)ceil_div((int)n, KNN_THREADS) * slices;
+        acc[M_KQB_OFF] += ceil_div((int)n, KNN_THREADS);
         acc[M_KPART_OFF] += slices * n * 4;
     }
     if (acc[M_FTILE_OFF] > 0x7fffffffLL || acc[M_CTASK_OFF] > 0x7fffffffLL || acc[M_KTASK_OFF] > 0x7fffffffLL ||
@@ -846,6 +975,7 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
     plan->fine_tiles = acc[M_FTILE_OFF];
     plan->coarse_tasks = acc[M_CTASK_OFF];
     plan->knn_tasks = acc[M_KTASK_OFF];
+    plan->knn_query_blocks = acc[M_KQB_OFF];
     size_t off = 0;
     const int64_t heads = acc[M_PT_OFF] > 0 ? acc[M_PT_OFF] : 1;
     plan->off_stamps = (int64_t)off; off = align_up(off + (size_t)heads * sizeof(Stamp), 256);
@@ -854,13 +984,15 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
     plan->off_fmask = (int64_t)off;  off = align_up(off + (size_t)(acc[M_FTILE_OFF] / 32 + 1) * 4, 256);
     plan->off_tmpl = (int64_t)off;   off = align_up(off + sizeof(Stamp) + TAB * sizeof(double), 256);
     plan->off_desc = (int64_t)off;   off = align_up(off + (size_t)acc[M_FTILE_OFF] * sizeof(TileDesc), 256);
-    plan->off_ccount = (int64_t)off; off = align_up(off + (size_t)(acc[M_CCOUNT_OFF] + 1) * 4, 256);
+    plan->off_ccount = (int64_t)off; off = align_up(off + (size_t)(acc[M_CTASK_OFF] + 1) * 4, 256);
     plan->off_ctotal = (int64_t)off; off = align_up(off + (size_t)(acc[M_CTILE_OFF] + 1) * 4, 256);
     plan->off_clist = (int64_t)off;  off = align_up(off + (size_t)(acc[M_CLIST_OFF] + 1) * 4, 256);
     plan->splat_workspace_bytes = (int64_t)off;
     off = 0;
     plan->off_knn_d2 = 0;            off = align_up((size_t)(acc[M_KPART_OFF] + 1) * 8, 256);
     plan->off_knn_idx = (int64_t)off; off = align_up(off + (size_t)(acc[M_KPART_OFF] + 1) * 4, 256);
+    plan->off_knn_pts32 = (int64_t)off; off = align_up(off + (size_t)heads * sizeof(float2), 256);
+    plan->off_knn_max = (int64_t)off; off = align_up(off + (size_t)n_images * sizeof(int), 256);
     plan->knn_workspace_bytes = (int64_t)off;
     return DGVCC_OK;
 }
@@ -875,11 +1007,23 @@ extern "C" int dgvcc_dmap_knn_sigma_batch(const double* pts_xy, int n_images, co
     cudaStream_t st = (cudaStream_t)stream;
     double* part_d2 = (double*)((char*)workspace + plan->off_knn_d2);
     int32_t* part_idx = (int32_t*)((char*)workspace + plan->off_knn_idx);
-    dmap_knn_batch_kernel<<<(unsigned)plan->knn_tasks, KNN_THREADS, 0, st>>>((const double2*)pts_xy, meta, n_images,
-                                                                             part_d2, part_idx);
+    float2* pts32 = (float2*)((char*)workspace + plan->off_knn_pts32);
+    int* img_max = (int*)((char*)workspace + plan->off_knn_max);
+    const int heads = (int)plan->total_heads;
+    DGVCC_RETURN_IF_CUDA(cudaMemsetAsync(img_max, 0, (size_t)n_images * sizeof(int), st));
+    dmap_knn_prep_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, meta, n_images, heads, pts32, img_max);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    dmap_knn_batch_kernel<<<(unsigned)plan->knn_query_blocks, KNN_THREADS, 0, st>>>((const double2*)pts_xy, pts32, img_max, meta,
+                                                                                    n_images, (int)plan->knn_max_slices, 0, part_d2,
+                                                                                    part_idx);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    if (plan->knn_tasks > plan->knn_query_blocks) {
+        dmap_knn_batch_kernel<<<(unsigned)(plan->knn_tasks - plan->knn_query_blocks), KNN_THREADS, 0, st>>>(
+            (const double2*)pts_xy, pts32, img_max, meta, n_images, (int)plan->knn_max_slices, 1, part_d2, part_idx);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
     dmap_knn_merge_batch_kernel<<<ceil_div((int)plan->total_heads, KNN_THREADS), KNN_THREADS, 0, st>>>(
-        part_d2, part_idx, meta, n_images, (int)plan->total_heads, nn_idx, nn_dist, sigma);
+        part_d2, part_idx, meta, n_images, (int)plan->total_heads, (int)plan->knn_max_slices, nn_idx, nn_dist, sigma);
     return (int)cudaGetLastError();
 }
 

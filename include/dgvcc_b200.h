@@ -160,9 +160,9 @@ int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx, double* n
  *   plan  totals and the workspace layouts (host struct, passed back by pointer).            */
 #define DGVCC_DMAP_META_COLS 12
 typedef struct dgvcc_dmap_plan {
-    int64_t total_heads, total_pixels, fine_tiles, coarse_tasks, knn_tasks;
+    int64_t total_heads, total_pixels, fine_tiles, coarse_tasks, knn_tasks, knn_query_blocks, knn_max_slices;
     int64_t off_stamps, off_boxes, off_wtab, off_fmask, off_tmpl, off_desc, off_ccount, off_ctotal, off_clist, splat_workspace_bytes;
-    int64_t off_knn_d2, off_knn_idx, knn_workspace_bytes;
+    int64_t off_knn_d2, off_knn_idx, off_knn_pts32, off_knn_max, knn_workspace_bytes;
 } dgvcc_dmap_plan;
 
 int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const int32_t* widths, const int32_t* counts,

@@ -186,6 +186,43 @@ def test_batched_knn_bit_exact():
         assert np.array_equal(sigma[lo:hi], ref_sigma)
 
 
+def test_batched_knn_fp32_filter_stays_exact_far_from_the_origin():
+    """The batched search skips candidates through an fp32 bound; crowds far from the origin (large |coordinates|,
+    small separations: the worst case for fp32) and near-coincident heads must still give KDTree's answer bit for bit."""
+    import ctypes
+    import torch
+    from dgvcc_b200 import _native
+    from dgvcc_b200.utils import dmap_gen
+    rng = np.random.default_rng(321)
+    clouds = [
+        1.0e6 + rng.uniform(0, 300, size=(3000, 2)),                       # far from the origin
+        np.concatenate([rng.uniform(0, 2000, size=(2500, 2)),              # tight pairs: separations ~1e-4 px
+                        rng.uniform(0, 2000, size=(2500, 2))]) ,
+        rng.uniform(-5.0e4, 5.0e4, size=(2600, 2)),                        # both signs, wide range
+        (rng.uniform(0, 1500, size=(4100, 2))).astype(np.float32).astype(np.float64),
+    ]
+    clouds[1][2500:] = clouds[1][:2500] + rng.uniform(1e-5, 1e-4, size=(2500, 2))
+    counts = [len(c) for c in clouds]
+    plan = dmap_gen._Plan([(2048, 2048)] * len(clouds), counts)
+    pl = plan.plan
+    dev = torch.device("cuda")
+    meta = torch.from_numpy(plan.meta).to(dev)
+    d_pts = torch.from_numpy(np.concatenate(clouds)).to(dev)
+    idx = torch.empty((pl.total_heads, 4), dtype=torch.int32, device=dev)
+    dist = torch.empty((pl.total_heads, 4), dtype=torch.float64, device=dev)
+    sigma = torch.empty((pl.total_heads,), dtype=torch.float64, device=dev)
+    kws = torch.empty((pl.knn_workspace_bytes,), dtype=torch.uint8, device=dev)
+    _native.check(_native.lib().dgvcc_dmap_knn_sigma_batch(
+        _native.ptr(d_pts), len(counts), _native.ptr(meta), ctypes.byref(pl), _native.ptr(idx), _native.ptr(dist),
+        _native.ptr(sigma), _native.ptr(kws), pl.knn_workspace_bytes, _native.stream_ptr(dev)), "knn batch")
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    for i, c in enumerate(clouds):
+        lo, hi = plan.pt_off[i], plan.pt_off[i + 1]
+        rd, rl = dmap_oracle.knn4(c)
+        assert np.array_equal(dist[lo:hi], rd), f"cloud {i}: distances"
+        assert np.array_equal(idx[lo:hi], rl), f"cloud {i}: indices"
+
+
 def test_negative_beyond_size_raises_like_numpy():
     from dgvcc_b200.utils import dmap_gen
     with pytest.raises(IndexError):

@@ -73,6 +73,17 @@ SIGNATURES = {
     "dgvcc_isw_sx_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_isw_covstat_var": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_isw_topk_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dgvcc_lw_standardize_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                             c_void_p]),
+    "dgvcc_lw_standardize_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                              c_void_p]),
+    "dgvcc_isw_gram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_lw_loss_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_lw_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                                       c_void_p, c_void_p]),
+    "dgvcc_ortho_loss_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_ortho_loss_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
+                                          c_void_p, c_void_p, c_void_p]),
     "dgvcc_isw_gram_tc_partials": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_bay_knn_mean": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_bay_crop_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_void_p,
@@ -121,5 +132,9 @@ def ptr(t):
 
 
 def stream_ptr(device):
+    """cudaStream_t of torch's current stream on ``device`` (raw handle; ~20x cheaper than building a Stream object)."""
     import torch
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    return c_void_p(torch._C._cuda_getCurrentRawStream(idx))

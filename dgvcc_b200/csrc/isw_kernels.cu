@@ -146,7 +146,7 @@ isw_gram_simt_kernel(const float* __restrict__ x, int c, int hw, int splits, int
 // stores the block, and stores its mirror image through a shared-memory transpose, so both stores are coalesced.
 // One writer per entry: on diagonal tiles the upper triangle is what gets mirrored.
 __global__ void __launch_bounds__(256)
-isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits, int tile, const float* __restrict__ eye,
+isw_cov_finish_kernel(const float* __restrict__ part, int c, float denom, int splits, int tile, const float* __restrict__ eye,
                       float eps, float* __restrict__ f_cor) {
     __shared__ float tr[32][33];
     const int tiles_1d = (c + tile - 1) / tile;
@@ -163,7 +163,7 @@ isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits,
     float* fc = f_cor + (size_t)b * c * c;
     const int i0 = ti * tile + 32 * sy, j0 = tj * tile + 32 * sx;
     const bool diag_block = ti == tj && sx == sy;
-    const float denom = (float)(hw - 1);
+    // denom = HW - 1 for the covariance (instance_whitening.py:37), 1 for a raw Gram; eye == NULL: no eps * eye term
     // the thread's four rows are summed side by side (independent chains, loads of several splits in flight);
     // each entry still adds its splits in split order
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -180,13 +180,14 @@ isw_cov_finish_kernel(const float* __restrict__ part, int c, int hw, int splits,
         // torch: bmm(...).div(HW-1) is a true division; + (eps * eye)
         const float v = acc[r] / denom;
         tr[li][tx] = v;
-        if (i < c && j < c && (!diag_block || tx >= li)) fc[(size_t)i * c + j] = v + eps * eye[(size_t)i * c + j];
+        if (i < c && j < c && (!diag_block || tx >= li)) fc[(size_t)i * c + j] = eye ? v + eps * eye[(size_t)i * c + j] : v;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int lj = ty + 8 * r, j = j0 + lj, i = i0 + tx;  // entry (j, i) = mirror of (i, j) = tr[tx][lj]
-        if (i < c && j < c && (!diag_block || lj > tx)) fc[(size_t)j * c + i] = tr[tx][lj] + eps * eye[(size_t)j * c + i];
+        if (i < c && j < c && (!diag_block || lj > tx))
+            fc[(size_t)j * c + i] = eye ? tr[tx][lj] + eps * eye[(size_t)j * c + i] : tr[tx][lj];
     }
 }
 
@@ -314,6 +315,123 @@ isw_covstat_var_kernel(const float* __restrict__ f_cor, const float* __restrict_
         ss = fmaf(d, d, ss);
     }
     var_out[e] = ss / (float)(batch - 1);  // batch == 1 -> 0/0 = nan, like torch.var
+}
+
+// ------------------------------------------------------------- auxiliary Gram losses
+// lw_loss (losses/lw.py:5-18): per-(n,c) standardisation with the UNBIASED variance and a true division by
+// sqrt(var + 1e-5), optional spatial mask, Gram, sum of the squared strictly-upper-triangular entries.
+// ortho_loss (losses/ortho.py:5-11): mean over C*C of triu(x y^T, 1)^2.  Both reuse the Gram / dX = S X kernels.
+
+// One CTA per (n, c) plane.  yhat = standardised plane (kept for the backward), ym = yhat * mask (the Gram input;
+// not written when there is no mask: ym == yhat).
+__global__ void __launch_bounds__(NORM_THREADS)
+lw_standardize_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mask, int channels, int hw, float eps,
+                          float* __restrict__ yhat, float* __restrict__ ym, float* __restrict__ invstd_out) {
+    __shared__ float scratch[NORM_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * hw;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) s += x[base + i];
+    const float mean = block_sum(s, scratch) / (float)hw;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) {
+        const float d = x[base + i] - mean;
+        q = fmaf(d, d, q);
+    }
+    const float var = block_sum(q, scratch) / (float)(hw - 1);  // torch.var: unbiased; hw == 1 -> nan like torch
+    const float sd = sqrtf(var + eps);
+    const float* mrow = mask ? mask + (size_t)(blockIdx.x / channels) * hw : nullptr;
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) {
+        const float v = (x[base + i] - mean) / sd;
+        yhat[base + i] = v;
+        if (mrow) ym[base + i] = v * mrow[i];
+    }
+    if (threadIdx.x == 0) invstd_out[blockIdx.x] = 1.0f / sd;
+}
+
+// g = dy * mask; dx = (g - mean(g) - yhat * sum(g * yhat) / (hw - 1)) / sd
+__global__ void __launch_bounds__(NORM_THREADS)
+lw_standardize_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yhat, const float* __restrict__ invstd,
+                          const float* __restrict__ mask, int channels, int hw, float* __restrict__ dx) {
+    __shared__ float scratch[NORM_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * hw;
+    const float* mrow = mask ? mask + (size_t)(blockIdx.x / channels) * hw : nullptr;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) {
+        const float g = mrow ? dy[base + i] * mrow[i] : dy[base + i];
+        s1 += g;
+        s2 = fmaf(g, yhat[base + i], s2);
+    }
+    const float m1 = block_sum(s1, scratch) / (float)hw;
+    const float m2 = block_sum(s2, scratch) / (float)(hw - 1);
+    const float is = invstd[blockIdx.x];
+    for (int i = threadIdx.x; i < hw; i += NORM_THREADS) {
+        const float g = mrow ? dy[base + i] * mrow[i] : dy[base + i];
+        dx[base + i] = is * (g - m1 - yhat[base + i] * m2);
+    }
+}
+
+// Sum over the strictly-upper-triangular entries of g[rows 0..c) x cols col0..col0+c) (leading dimension ld) of
+// every sample, squared; sliced like isw_loss_kernel, ordered final sum; loss = scale * total.
+__global__ void __launch_bounds__(256)
+triu_sq_loss_kernel(const float* __restrict__ g, int c, int ld, int col0, size_t sample_stride, int batch, float scale,
+                    float* __restrict__ part, float* __restrict__ loss_out, unsigned int* __restrict__ ticket) {
+    __shared__ float scratch[8];
+    __shared__ bool s_last;
+    const int b = blockIdx.y, chunks = gridDim.x;
+    const float* gb = g + (size_t)b * sample_stride;
+    const int rows_per = ceil_div(c, chunks);
+    const int r0 = blockIdx.x * rows_per, r1 = min(c, r0 + rows_per);
+    float s = 0.f;
+    for (int i = r0; i < r1; ++i)
+        for (int j = i + 1 + threadIdx.x; j < c; j += 256) {
+            const float v = gb[(size_t)i * ld + col0 + j];
+            s = fmaf(v, v, s);
+        }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += scratch[w];
+        part[b * LOSS_CHUNKS + blockIdx.x] = t;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == (unsigned)(batch * chunks) - 1u;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    const volatile float* pv = part;
+    float total = 0.f;
+    for (int i = 0; i < batch; ++i)
+        for (int k = 0; k < chunks; ++k) total += pv[i * LOSS_CHUNKS + k];
+    loss_out[0] = scale * total;
+    *ticket = 0u;
+}
+
+// lw backward: S_b = dG_b + dG_b^T with dG_b = 2 g triu(G_b, 1): symmetric, zero diagonal; the upper entry is used
+// on both sides.
+__global__ void __launch_bounds__(256)
+lw_grad_s_kernel(const float* __restrict__ gram, const float* __restrict__ grad_loss, int c, float* __restrict__ s_out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= c * c) return;
+    const int i = e / c, j = e % c;
+    const float* gb = gram + (size_t)b * c * c;
+    const float v = i == j ? 0.f : gb[(size_t)min(i, j) * c + max(i, j)];
+    s_out[(size_t)b * c * c + e] = 2.f * grad_loss[0] * v;
+}
+
+// ortho backward: Sx = (2 g / C^2) triu(G, 1) (dL/dx = Sx y) and Sy = Sx^T (dL/dy = Sy x); G is the block
+// rows 0..c x cols c..2c of the stacked Gram (leading dimension 2c).
+__global__ void __launch_bounds__(256)
+ortho_grad_s_kernel(const float* __restrict__ gram_zz, const float* __restrict__ grad_loss, int c, float* __restrict__ sx,
+                    float* __restrict__ sy) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= c * c) return;
+    const int i = e / c, j = e % c;
+    const float k = 2.f * grad_loss[0] / ((float)c * (float)c);
+    sx[e] = j > i ? k * gram_zz[(size_t)i * 2 * c + c + j] : 0.f;
+    sy[e] = i > j ? k * gram_zz[(size_t)j * 2 * c + c + i] : 0.f;
 }
 
 // ------------------------------------------------------------------------ top-k mask (CovMatrix_ISW)
@@ -534,17 +652,15 @@ IswWs carve(void* ws, int batch, int c, int hw) {
 extern "C" int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int hw, int splits, int k_per_split,
                                           float* part, void* stream);
 
-extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int batch, int c, int hw, int use_tensor_cores,
-                                    void* workspace, size_t workspace_bytes, float* f_cor, void* stream) {
-    if (!f_map || !eye || !workspace || !f_cor || batch <= 0 || c <= 0 || hw <= 1) return DGVCC_ERR_ARG;
-    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
-    const IswWs w = carve(workspace, batch, c, hw);
+// Gram of every sample on the tensor cores where the shape tiles (else exact fp32 on CUDA cores), finished as
+// out = X X^T / denom (+ eps * eye when eye is given).
+static int launch_gram(const float* f_map, const float* eye, float denom, float eps, int batch, int c, int hw,
+                       int use_tensor_cores, const IswWs& w, float* out, cudaStream_t st) {
     int splits, kps, n_tiles, tile = 64;
     bool done = false;
     if (use_tensor_cores) {
         gram_plan_tc(batch, c, hw, &splits, &kps, &n_tiles, &tile);
-        const int rc = dgvcc_isw_gram_tc_partials(f_map, batch, c, hw, splits, kps, w.part, stream);
+        const int rc = dgvcc_isw_gram_tc_partials(f_map, batch, c, hw, splits, kps, w.part, (void*)st);
         if (rc == DGVCC_OK) done = true;
         else if (rc != DGVCC_ERR_UNSUPPORTED) return rc;
     }
@@ -555,8 +671,16 @@ extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int ba
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     const int yblocks = (tile / 32) * (tile / 32);
-    isw_cov_finish_kernel<<<dim3(n_tiles, yblocks, batch), 256, 0, st>>>(w.part, c, hw, splits, tile, eye, 1e-5f, f_cor);
+    isw_cov_finish_kernel<<<dim3(n_tiles, yblocks, batch), 256, 0, st>>>(w.part, c, denom, splits, tile, eye, eps, out);
     return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int batch, int c, int hw, int use_tensor_cores,
+                                    void* workspace, size_t workspace_bytes, float* f_cor, void* stream) {
+    if (!f_map || !eye || !workspace || !f_cor || batch <= 0 || c <= 0 || hw <= 1) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, batch, c, hw);
+    return launch_gram(f_map, eye, (float)(hw - 1), 1e-5f, batch, c, hw, use_tensor_cores, w, f_cor, (cudaStream_t)stream);
 }
 
 extern "C" int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, const float* margin,
@@ -642,4 +766,81 @@ extern "C" int dgvcc_isw_topk_mask(const float* stats, int n_stats, int count, i
     isw_topk_mask_kernel<<<1, TOPK_THREADS, 0, (cudaStream_t)stream>>>(stats, n_stats, (float)count, n, k, prev_mask,
                                                                        values, mask);
     return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ auxiliary Gram losses: entry points
+extern "C" int dgvcc_lw_standardize_forward(const float* x, const float* mask, int batch, int c, int hw, float eps,
+                                            float* yhat, float* y_masked, float* invstd, void* stream) {
+    if (!x || !yhat || !invstd || batch <= 0 || c <= 0 || hw <= 0 || (mask && !y_masked)) return DGVCC_ERR_ARG;
+    lw_standardize_fwd_kernel<<<batch * c, NORM_THREADS, 0, (cudaStream_t)stream>>>(x, mask, c, hw, eps, yhat, y_masked, invstd);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_lw_standardize_backward(const float* dy, const float* yhat, const float* invstd, const float* mask,
+                                             int batch, int c, int hw, float* dx, void* stream) {
+    if (!dy || !yhat || !invstd || !dx || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    lw_standardize_bwd_kernel<<<batch * c, NORM_THREADS, 0, (cudaStream_t)stream>>>(dy, yhat, invstd, mask, c, hw, dx);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_isw_gram(const float* f_map, int batch, int c, int hw, int use_tensor_cores, void* workspace,
+                              size_t workspace_bytes, float* gram, void* stream) {
+    if (!f_map || !workspace || !gram || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, batch, c, hw);
+    return launch_gram(f_map, nullptr, 1.0f, 0.f, batch, c, hw, use_tensor_cores, w, gram, (cudaStream_t)stream);
+}
+
+static int launch_triu_sq(const float* g, int c, int ld, int col0, size_t sample_stride, int batch, float scale,
+                          const IswWs& w, float* loss_out, cudaStream_t st) {
+    DGVCC_RETURN_IF_CUDA(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+    const int chunks = max(1, min(LOSS_CHUNKS, c / 16));
+    triu_sq_loss_kernel<<<dim3(chunks, batch), 256, 0, st>>>(g, c, ld, col0, sample_stride, batch, scale, w.off + batch,
+                                                             loss_out, w.ticket);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_lw_loss_forward(const float* gram, int batch, int c, int hw, void* workspace, size_t workspace_bytes,
+                                     float* loss_out, void* stream) {
+    if (!gram || !workspace || !loss_out || batch <= 0 || c <= 0) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, batch, c, hw);
+    return launch_triu_sq(gram, c, c, 0, (size_t)c * c, batch, 1.0f, w, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int dgvcc_lw_loss_backward(const float* y, const float* gram, const float* grad_loss, int batch, int c, int hw,
+                                      int use_tensor_cores, void* workspace, size_t workspace_bytes, float* grad_y,
+                                      void* stream) {
+    if (!y || !gram || !grad_loss || !workspace || !grad_y || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, batch, c, hw);
+    cudaStream_t st = (cudaStream_t)stream;
+    lw_grad_s_kernel<<<dim3(ceil_div(c * c, 256), batch), 256, 0, st>>>(gram, grad_loss, c, w.s);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    return launch_sx(w.s, y, batch, c, hw, use_tensor_cores, grad_y, st);
+}
+
+// z = [x; y] stacked [2c, p]; gram_zz [2c, 2c] = z z^T from dgvcc_isw_gram(z, 1, 2c, p, ...).
+extern "C" int dgvcc_ortho_loss_forward(const float* gram_zz, int c, int p, void* workspace, size_t workspace_bytes,
+                                        float* loss_out, void* stream) {
+    if (!gram_zz || !workspace || !loss_out || c <= 0 || p <= 0) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(1, 2 * c, p)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, 1, 2 * c, p);
+    return launch_triu_sq(gram_zz, c, 2 * c, c, 0, 1, 1.0f / ((float)c * (float)c), w, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int dgvcc_ortho_loss_backward(const float* x, const float* y, const float* gram_zz, const float* grad_loss, int c,
+                                         int p, int use_tensor_cores, void* workspace, size_t workspace_bytes,
+                                         float* grad_x, float* grad_y, void* stream) {
+    if (!x || !y || !gram_zz || !grad_loss || !workspace || !grad_x || !grad_y || c <= 0 || p <= 0) return DGVCC_ERR_ARG;
+    if (workspace_bytes < dgvcc_isw_workspace_bytes(1, 2 * c, p)) return DGVCC_ERR_WORKSPACE;
+    const IswWs w = carve(workspace, 1, 2 * c, p);  // S region holds (2c)^2 floats: Sx and Sy fit
+    cudaStream_t st = (cudaStream_t)stream;
+    float* sx = w.s;
+    float* sy = w.s + (size_t)c * c;
+    ortho_grad_s_kernel<<<ceil_div(c * c, 256), 256, 0, st>>>(gram_zz, grad_loss, c, sx, sy);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    const int rc = launch_sx(sx, y, 1, c, p, use_tensor_cores, grad_x, st);
+    if (rc != DGVCC_OK) return rc;
+    return launch_sx(sy, x, 1, c, p, use_tensor_cores, grad_y, st);
 }

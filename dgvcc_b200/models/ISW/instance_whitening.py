@@ -37,10 +37,19 @@ def _workspace(b, c, hw, dev):
     return torch.empty((n,), dtype=torch.uint8, device=dev), n
 
 
+_scalars = {}  # (device, value) -> 1-element device tensor for Python-number margins / counts (read-only)
+
+
 def _scalar(v, dev):
     if torch.is_tensor(v):
         return v.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-    return torch.full((1,), float(v), dtype=torch.float32, device=dev)
+    key = (dev, float(v))
+    t = _scalars.get(key)
+    if t is None:
+        if len(_scalars) > 256:
+            _scalars.clear()
+        t = _scalars[key] = torch.full((1,), float(v), dtype=torch.float32, device=dev)
+    return t
 
 
 class _InstanceNorm(torch.autograd.Function):

@@ -290,6 +290,42 @@ int dgvcc_bay_crop_targets(const void* gt_xy, const void* dists, int n, int is_d
 int dgvcc_probe_ex2(float* sink, int iters, int64_t* ops_out, void* stream);
 int dgvcc_probe_ffma(float* sink, int iters, int64_t* ops_out, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Auxiliary Gram-type losses -- replace losses/lw.py:5-18 (lw_loss) and
+ * losses/ortho.py:5-11 (ortho_loss); they reuse the Gram and dX = S X kernels of the ISW path and its
+ * workspace (dgvcc_isw_workspace_bytes(batch, c, hw)).
+ * ------------------------------------------------------------------------- */
+
+/* lw.py:11-15: yhat = (x - mean) / sqrt(var_unbiased + eps) per (n, c) plane; with a mask [batch, hw]
+ * (lw.py:14-15) y_masked = yhat * mask is the Gram input (y_masked may be NULL when mask is NULL).
+ * invstd [batch*c] = 1 / sqrt(var + eps), kept for the backward. */
+int dgvcc_lw_standardize_forward(const float* x, const float* mask, int batch, int c, int hw, float eps,
+                                 float* yhat, float* y_masked, float* invstd, void* stream);
+/* dx for an upstream gradient dy of the (masked) standardised map. */
+int dgvcc_lw_standardize_backward(const float* dy, const float* yhat, const float* invstd, const float* mask,
+                                  int batch, int c, int hw, float* dx, void* stream);
+
+/* gram [batch, c, c] = X X^T (no scaling, no eps): lw.py:16, and the stacked form of ortho.py:9. */
+int dgvcc_isw_gram(const float* f_map, int batch, int c, int hw, int use_tensor_cores, void* workspace,
+                   size_t workspace_bytes, float* gram, void* stream);
+
+/* lw.py:17-18: loss[0] = sum over samples of sum_{i<j} gram[i][j]^2; backward: grad_y = (dG + dG^T) Y with
+ * dG = 2 * grad_loss * triu(gram, 1). */
+int dgvcc_lw_loss_forward(const float* gram, int batch, int c, int hw, void* workspace, size_t workspace_bytes,
+                          float* loss_out, void* stream);
+int dgvcc_lw_loss_backward(const float* y, const float* gram, const float* grad_loss, int batch, int c, int hw,
+                           int use_tensor_cores, void* workspace, size_t workspace_bytes, float* grad_y, void* stream);
+
+/* ortho.py:9-11 on the stacked operand z = [x; y] ([2c, p]): gram_zz = dgvcc_isw_gram(z, 1, 2c, p); the block
+ * rows 0..c x columns c..2c is x y^T.  loss[0] = mean over c*c of triu(x y^T, 1)^2; backward:
+ * grad_x = Sx y, grad_y = Sx^T x with Sx = (2 grad_loss / c^2) triu(x y^T, 1).
+ * workspace: dgvcc_isw_workspace_bytes(1, 2c, p). */
+int dgvcc_ortho_loss_forward(const float* gram_zz, int c, int p, void* workspace, size_t workspace_bytes,
+                             float* loss_out, void* stream);
+int dgvcc_ortho_loss_backward(const float* x, const float* y, const float* gram_zz, const float* grad_loss, int c, int p,
+                              int use_tensor_cores, void* workspace, size_t workspace_bytes, float* grad_x,
+                              float* grad_y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

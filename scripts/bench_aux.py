@@ -294,6 +294,39 @@ def bench_cov(cpu):
     print(json.dumps(line), flush=True)
 
 
+def bench_auxloss(cpu):
+    """Row f4: lw_loss / ortho_loss forward + backward (the Gram and dX = S X kernels of the ISW path)."""
+    from dgvcc_b200.losses.lw import lw_loss
+    from dgvcc_b200.losses.ortho import ortho_loss
+    g = torch.Generator().manual_seed(8800)
+    x = torch.randn(8, 256, 80, 80, generator=g)
+    mask = (torch.rand(8, 1, 80, 80, generator=g) < 0.5).float()
+    a, b_ = torch.randn(256, 16384, generator=g), torch.randn(256, 16384, generator=g)
+    for name, fn, args in (("lw_loss (8,256,80,80) + mask", lw_loss, (x, mask)), ("ortho_loss (256,16384) x2", ortho_loss, (a, b_))):
+        dargs = [t.to(dev).requires_grad_(t.dim() != 4 or t.shape[1] != 1) for t in args]
+        ts = []
+        for rep in range(6):
+            for t in dargs:
+                t.grad = None
+            e0, e1 = ev(), ev()
+            e0.record()
+            fn(*dargs).backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                ts.append(e0.elapsed_time(e1))
+        line = {"workload": f"SURVEY 8f rank 4: {name}, forward + backward", "metric": "steps/s", "value": 1e3 / min(ts), "ms": min(ts)}
+        if cpu:
+            from oracle import aux_losses_oracle as ao
+            cargs = [t.clone().requires_grad_(t.dim() != 4 or t.shape[1] != 1) for t in args]
+            t0 = time.perf_counter()
+            (ao.lw_loss if fn is lw_loss else ao.ortho_loss)(*cargs).backward()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "oracle port (torch CPU), same tensors, one forward + backward"}
+        print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
@@ -309,3 +342,5 @@ if __name__ == "__main__":
         bench_den(a.cpu)
     if a.only in ("", "cov"):
         bench_cov(a.cpu)
+    if a.only in ("", "auxloss"):
+        bench_auxloss(a.cpu)

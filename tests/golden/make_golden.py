@@ -329,8 +329,39 @@ def make_cov():
     np.savez_compressed(os.path.join(HERE, "cov_cases.npz"), **out)
 
 
+# -------------------------------------------------------------------------- aux (lw / ortho losses)
+def make_aux():
+    """losses/lw.py:5-18 and losses/ortho.py:5-11, the unmodified files loaded by path: values and gradients."""
+    lw = load_ref("losses/lw.py", "ref_lw").lw_loss
+    ortho = load_ref("losses/ortho.py", "ref_ortho").ortho_loss
+    out = {}
+    g = torch.Generator().manual_seed(8500)
+    for name, (n, c, h, w), masked in (("lw_a", (2, 32, 12, 10), 0), ("lw_b", (3, 64, 16, 16), 1), ("lw_c", (2, 128, 16, 16), 2),
+                                        ("lw_d", (1, 48, 9, 7), 0)):
+        x = (torch.randn(n, c, h, w, generator=g) * (1 + torch.rand(1, c, 1, 1, generator=g)) + torch.randn(1, c, 1, 1, generator=g))
+        x.requires_grad_(True)
+        mask = None
+        if masked == 1:
+            mask = (torch.rand(n, 1, h, w, generator=g) < 0.6).float()
+        elif masked == 2:
+            mask = torch.rand(n, 1, h, w, generator=g)
+        loss = lw(x, mask)
+        loss.backward()
+        out[f"{name}_x"], out[f"{name}_loss"], out[f"{name}_grad"] = x.detach().numpy(), loss.detach().numpy(), x.grad.numpy()
+        if mask is not None:
+            out[f"{name}_mask"] = mask.numpy()
+    for name, (c, p_) in (("or_a", (32, 200)), ("or_b", (64, 500)), ("or_c", (100, 333)), ("or_d", (128, 512))):
+        x = torch.randn(c, p_, generator=g, requires_grad=True)
+        y = (0.3 * x.detach() + torch.randn(c, p_, generator=g)).requires_grad_(True)
+        loss = ortho(x, y)
+        loss.backward()
+        out[f"{name}_x"], out[f"{name}_y"], out[f"{name}_loss"] = x.detach().numpy(), y.detach().numpy(), loss.detach().numpy()
+        out[f"{name}_gx"], out[f"{name}_gy"] = x.grad.numpy(), y.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "aux_cases.npz"), **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["bl", "dmap", "isw", "bay", "den", "cov"]
+    what = sys.argv[1:] or ["bl", "dmap", "isw", "bay", "den", "cov", "aux"]
     torch.manual_seed(0)
     for w in what:
         globals()[f"make_{w}"]()

@@ -104,7 +104,7 @@ if os.path.exists(rep):
     aux = os.path.join(ROOT, "gpurun_out", f"aux_{tag}.ncu-rep")
     if os.path.exists(aux):
         summarize(aux, f"ncu --set full, ISW module fwd+bwd (B=8, C=256, HW=6400) and one density map (2048x2048, 25 000 heads; adaptive, then fixed sigma) ({tag})",
-                  "ncu --set full --clock-control none --import-source on -k 'regex:isw_|dmap_' -s 20 -c 20 python scripts/profile_aux.py",
+                  "ncu --set full --clock-control none --import-source on -k 'regex:isw_|dmap_' -s 22 -c 22 python scripts/profile_aux.py",
                   os.path.join(out_dir, f"{tag}_aux_ncu_summary.md"), os.path.join(out_dir, f"{tag}_aux_ncu_raw.csv"))
     with open(os.path.join(out_dir, f"{tag}_bl_ncu_summary.md"), "w") as f:
         f.write(f"# ncu --set full, fused Bayesian loss, BASELINE config 3 ({tag})\n\n"

@@ -210,10 +210,14 @@ __device__ int enumerate_leaves(int first, int n, LeafList& ll, bool write) {
 
 // One leaf (n <= 128) by a group of 8 lanes; the result is valid on the group's lane 0.
 __device__ __forceinline__ double leaf_by_group(double coef, int first, int n, int sub /*0..7*/, unsigned group_mask) {
-    if (n < 8) {  // numpy's plain loop: nothing to parallelise
+    const int group_lane0 = __ffs(group_mask) - 1;  // first lane of this group of 8
+    if (n < 8) {  // numpy's plain loop: the lanes evaluate the elements side by side, the leader adds them in order
+        const double ev = sub < n ? phi(coef, first + sub) : 0.0;
         double res = 0.0;
-        if (sub == 0)
-            for (int i = 0; i < n; ++i) res = __dadd_rn(res, phi(coef, first + i));
+        for (int j = 0; j < n; ++j) {
+            const double v = __shfl_sync(group_mask, ev, (group_lane0 + j) & 31);
+            if (sub == 0) res = __dadd_rn(res, v);
+        }
         return res;
     }
     const int body = n - (n % 8);
@@ -223,8 +227,14 @@ __device__ __forceinline__ double leaf_by_group(double coef, int first, int n, i
     r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 1));
     r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 2));
     r = __dadd_rn(r, __shfl_xor_sync(group_mask, r, 4));
-    if (sub == 0)
-        for (int i = body; i < n; ++i) r = __dadd_rn(r, phi(coef, first + i));
+    // numpy adds the n % 8 tail elements one by one: the lanes evaluate them side by side (sub-lane j holds tail
+    // element j), the leader then adds them in order
+    const int tail = n - body;
+    const double tv = sub < tail ? phi(coef, first + body + sub) : 0.0;
+    for (int j = 0; j < tail; ++j) {
+        const double v = __shfl_sync(group_mask, tv, (group_lane0 + j) & 31);
+        if (sub == 0) r = __dadd_rn(r, v);
+    }
     return r;
 }
 

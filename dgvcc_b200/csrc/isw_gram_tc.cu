@@ -18,7 +18,7 @@
 // Warp roles (320 threads):
 //   warp 0   : TMA producer -- cp.async.bulk.tensor of the 128 x 32 fp32 operand tiles (128B swizzle)
 //   warp 1   : TMEM allocation; one lane issues tcgen05.mma.kind::tf32 (12 per 32-wide k block)
-//   warps 2-9: converters -- rewrite each landed tile as hi in place, lo beside it, then signal the
+//   warps 2-9: converters -- write lo beside each landed tile (the tile itself serves as hi), then signal the
 //              MMA warp; they also drain finished accumulator sets (tcgen05.ld; warp w reads TMEM lane
 //              quarter w % 4, warps 2-5 the left 64 columns, warps 6-9 the right 64) and store the tile
 // Pipeline: full[s] (TMA -> converters), ready[s] (converters -> MMA), empty[s] (MMA -> TMA) over
@@ -33,6 +33,7 @@ constexpr int TILE_M = 128;                 // rows of X per operand tile (= UMM
 constexpr int BLOCK_K = 32;                 // fp32 per k block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                   // tf32 MMA k extent (32 bytes)
 constexpr int STAGES = 3;
+constexpr bool HI_BY_TRUNCATION = true;     // hi = what the tensor core reads of the raw tile (see the converter loop)
 constexpr int SEG_KB = 16;                  // k blocks accumulated in TMEM before a drain (512 k = 64 steps)
 constexpr int TILE_BYTES = TILE_M * BLOCK_K * 4;  // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi, B_hi, A_lo, B_lo
@@ -150,7 +151,7 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
             }
         }
     } else {
-        // ===== converters (hi in place, lo beside) and, lagging two k blocks behind, the segment drains =====
+        // ===== converters (lo beside the tile; hi = the tile as delivered) and, lagging two k blocks behind, the segment drains =====
         const int ctid = threadIdx.x - 64;      // 0..255
         const int lane_base = 32 * (warp & 3);  // a warp may only touch its own quarter of the TMEM lanes
         const int row = lane_base + lane;       // row of the 128 x 128 tile held by this thread
@@ -195,12 +196,22 @@ isw_gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
 #pragma unroll 4
             for (int i = ctid; i < n_vec; i += 32 * CONVERTER_WARPS) {
                 const float4 v = hi[i];
-                float4 h, l;
-                h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
-                h.y = tf32_round(v.y); l.y = tf32_round(v.y - h.y);
-                h.z = tf32_round(v.z); l.z = tf32_round(v.z - h.z);
-                h.w = tf32_round(v.w); l.w = tf32_round(v.w - h.w);
-                hi[i] = h;
+                float4 l;
+                if (HI_BY_TRUNCATION) {
+                    // the tensor core reads only the top 19 bits of a TF32 operand, so the raw tile IS hi = trunc(x);
+                    // only lo = RN_tf32(x - trunc(x)) has to be written
+                    l.x = tf32_round(v.x - tf32_trunc(v.x));
+                    l.y = tf32_round(v.y - tf32_trunc(v.y));
+                    l.z = tf32_round(v.z - tf32_trunc(v.z));
+                    l.w = tf32_round(v.w - tf32_trunc(v.w));
+                } else {
+                    float4 h;
+                    h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
+                    h.y = tf32_round(v.y); l.y = tf32_round(v.y - h.y);
+                    h.z = tf32_round(v.z); l.z = tf32_round(v.z - h.z);
+                    h.w = tf32_round(v.w); l.w = tf32_round(v.w - h.w);
+                    hi[i] = h;
+                }
                 lo[i] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads

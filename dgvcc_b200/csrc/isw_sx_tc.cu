@@ -146,13 +146,14 @@ isw_sx_tc_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constan
             float4* lo = reinterpret_cast<float4*>(stage + 2 * TILE_BYTES);
 #pragma unroll 4
             for (int i = ctid; i < (EXACT ? 1 : 2) * TILE_BYTES / 16; i += 128) {
+                // the tensor core reads only the top 19 bits of a TF32 operand: the raw tile already is hi = trunc(x),
+                // only lo = RN_tf32(x - trunc(x)) is written (isw_gram_tc.cu)
                 const float4 v = hi[i];
-                float4 h, l;
-                h.x = tf32_round(v.x); l.x = tf32_round(v.x - h.x);
-                h.y = tf32_round(v.y); l.y = tf32_round(v.y - h.y);
-                h.z = tf32_round(v.z); l.z = tf32_round(v.z - h.z);
-                h.w = tf32_round(v.w); l.w = tf32_round(v.w - h.w);
-                hi[i] = h;
+                float4 l;
+                l.x = tf32_round(v.x - tf32_trunc(v.x));
+                l.y = tf32_round(v.y - tf32_trunc(v.y));
+                l.z = tf32_round(v.z - tf32_trunc(v.z));
+                l.w = tf32_round(v.w - tf32_trunc(v.w));
                 lo[i] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -23,6 +23,13 @@ class BLLayout(ctypes.Structure):
                [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("reserved_", c_int32)]
 
 
+class BLPacked(ctypes.Structure):
+    """Mirror of struct dgvcc_bl_packed."""
+    _fields_ = [(n, c_int64) for n in
+                ("total_points", "total_rows", "total_chunks", "multi_chunk", "meta_bytes", "off_points", "off_targets",
+                 "total_bytes")]
+
+
 class DmapPlan(ctypes.Structure):
     """Mirror of struct dgvcc_dmap_plan."""
     _fields_ = [(n, c_int64) for n in
@@ -38,6 +45,7 @@ DEN_META_COLS = 8    # DGVCC_DEN_META_COLS
 SIGNATURES = {
     "dgvcc_abi_version": (c_int, []),
     "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
+    "dgvcc_bl_pack_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, POINTER(BLPacked)]),
     "dgvcc_bl_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                  c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, c_void_p, c_size_t,
                                  c_void_p, c_void_p]),

@@ -156,6 +156,25 @@ def pack_batch(points, targets, use_background=True, chunk=None):
     return PackedBatch(buf, meta.nbytes, o_pts, o_tgt, total, counts, rows, total_chunks, multi_chunk, bool(use_background))
 
 
+def _plain_f32(tensors):
+    return all(t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad for t in tensors)
+
+
+def pack_host_native(points, targets, use_bg, chunk, dst_ptr, dst_bytes, args=None):
+    """dgvcc_bl_pack_host on lists of contiguous fp32 CPU tensors; ``dst_ptr=None`` only sizes the buffer.
+    Returns (BLPacked info, the ctypes argument arrays for a second call)."""
+    import ctypes
+    if args is None:
+        b = len(points)
+        args = ((ctypes.c_void_p * b)(*[p.data_ptr() for p in points]),
+                (ctypes.c_void_p * b)(*[t.data_ptr() for t in targets]) if targets is not None else None,
+                (ctypes.c_int32 * b)(*[p.shape[0] for p in points]), b)
+    info = _native.BLPacked()
+    _native.check(_native.lib().dgvcc_bl_pack_host(args[0], args[1], args[2], args[3], int(bool(use_bg)), int(chunk),
+                                                   dst_ptr, dst_bytes, ctypes.byref(info)), "dgvcc_bl_pack_host")
+    return info, args
+
+
 class _Packed:
     """CSR packing of one ragged batch + the small int32 table the kernels read (include/dgvcc_b200.h).
 
@@ -179,9 +198,6 @@ class _Packed:
         self.total_points = int(counts.sum())
         self.total_rows = int(rows.sum())
         b = self.batch
-        meta, self.total_chunks, self.multi_chunk = build_meta(counts, rows, chunk_points())
-        self.pt_off = meta[:b + 1].copy()
-        self.row_off = meta[b + 1:2 * b + 2].copy()
         self.targets = None
         if targets is not None:
             targets = [t.reshape(-1) for t in targets]
@@ -191,6 +207,24 @@ class _Packed:
         self.on_host = device.type == "cuda" and all(p.device.type == "cpu" for p in points) and \
             (targets is None or all(t.device.type == "cpu" for t in targets))
         n_pts = max(self.total_points, 1)
+        self.pt_off = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
+        self.row_off = np.concatenate(([0], np.cumsum(rows))).astype(np.int32)
+        if self.on_host and _plain_f32(points) and (targets is None or _plain_f32(targets)):
+            # fp32 host tensors (what the DataLoader delivers): table + points + targets written into the pinned
+            # staging buffer by one native pass (csrc/bl_pack_host.cu), then ONE asynchronous upload
+            ring = _staging.setdefault(device, _Staging())
+            info, args = pack_host_native(points, targets, use_bg, chunk_points(), None, 0)
+            slot, host = ring.take(info.total_bytes)
+            pack_host_native(points, targets, use_bg, chunk_points(), host.data_ptr(), host.numel(), args)
+            dev_buf = host[:info.total_bytes].to(device, non_blocking=True)
+            ring.sent(slot, device)
+            self.total_chunks, self.multi_chunk = int(info.total_chunks), int(info.multi_chunk)
+            self.meta = dev_buf[:info.meta_bytes].view(torch.int32)
+            self.pts = dev_buf[info.off_points:info.off_points + 8 * n_pts].view(torch.float32).view(-1, 2)
+            if targets is not None:
+                self.targets = dev_buf[info.off_targets:info.off_targets + 4 * n_pts].view(torch.float32)
+            return
+        meta, self.total_chunks, self.multi_chunk = build_meta(counts, rows, chunk_points())
         if self.on_host:
             o_pts = _align16(meta.nbytes)
             o_tgt = o_pts + _align16(8 * n_pts)

@@ -57,6 +57,19 @@ int dgvcc_abi_version(void);
  * (flush-to-zero MUFU.EX2 below 2^-126): bit-identical results, far fewer pairs.  0 = dense.
  * ------------------------------------------------------------------------- */
 
+/* Host-side packing (no CUDA call): the CSR concatenation of bl.py:21-22 plus the int32 table above, written in
+ * one pass into the caller's staging buffer (pinned, so that the step uploads ONE buffer).
+ *   points[i]  [counts[i], 2] f32 host, targets[i] [counts[i]] f32 host (targets may be NULL: points only);
+ *   chunk      points per chunk (big images are cut into near-equal slices of at most this many points);
+ *   dst == NULL: only fill `info` (sizes, offsets); otherwise dst must hold info->total_bytes.
+ * Layout of dst: table at 0, points at off_points, targets at off_targets (16-byte aligned regions). */
+typedef struct dgvcc_bl_packed {
+    int64_t total_points, total_rows, total_chunks, multi_chunk;
+    int64_t meta_bytes, off_points, off_targets, total_bytes;
+} dgvcc_bl_packed;
+int dgvcc_bl_pack_host(const float* const* points, const float* const* targets, const int32_t* counts, int batch,
+                       int use_background, int chunk, void* dst, size_t dst_bytes, dgvcc_bl_packed* info);
+
 /* Named regions inside the caller-owned workspace (byte offsets), for tests and
  * for the autograd wrapper that keeps the workspace alive until backward. */
 typedef struct dgvcc_bl_layout {

@@ -51,3 +51,23 @@ def test_meta_table_layout():
         mine = table[table[:, 0] == i]
         assert mine[:, 2].sum() == counts[i] and mine[0, 1] == 0
     assert sorted(table[:, 3].tolist()) == list(range(c))
+
+
+def test_native_host_packing_matches_the_python_packing():
+    """dgvcc_bl_pack_host (host-only C) writes byte for byte what build_meta + numpy concatenate write."""
+    import numpy as np
+    import torch
+    from dgvcc_b200.losses import bl
+    rng = np.random.default_rng(5)
+    for counts, use_bg, chunk in (([2500, 0, 3, 1024, 1025], True, 1024), ([7], False, 4), ([0, 0], True, 1024),
+                                  ([300, 12000, 5, 4097], True, 1024)):
+        pts = [torch.from_numpy(rng.random((n, 2), dtype=np.float32)) for n in counts]
+        tgt = [torch.from_numpy(rng.random(n, dtype=np.float32)) for n in counts]
+        ref = bl.pack_batch(pts, tgt, use_background=use_bg, chunk=chunk)
+        info, args = bl.pack_host_native(pts, tgt, use_bg, chunk, None, 0)
+        assert (info.meta_bytes, info.off_points, info.off_targets, info.total_bytes) == \
+            (ref.meta_bytes, ref.o_pts, ref.o_tgt, ref.total)
+        assert (info.total_chunks, info.multi_chunk) == (ref.total_chunks, ref.multi_chunk)
+        buf = torch.zeros((info.total_bytes,), dtype=torch.uint8)
+        bl.pack_host_native(pts, tgt, use_bg, chunk, buf.data_ptr(), buf.numel(), args)
+        assert torch.equal(buf, ref.buf), counts

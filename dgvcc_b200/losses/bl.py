@@ -187,6 +187,8 @@ class _Packed:
         if isinstance(points, PackedBatch):
             self._from_packed_batch(points, use_bg, device)
             return
+        if device.type == "cuda" and self._init_from_host_lists(points, targets, use_bg, device):
+            return
         points = _as_point_list(points)
         self.batch = len(points)
         if self.batch == 0:
@@ -209,21 +211,6 @@ class _Packed:
         n_pts = max(self.total_points, 1)
         self.pt_off = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
         self.row_off = np.concatenate(([0], np.cumsum(rows))).astype(np.int32)
-        if self.on_host and _plain_f32(points) and (targets is None or _plain_f32(targets)):
-            # fp32 host tensors (what the DataLoader delivers): table + points + targets written into the pinned
-            # staging buffer by one native pass (csrc/bl_pack_host.cu), then ONE asynchronous upload
-            ring = _staging.setdefault(device, _Staging())
-            info, args = pack_host_native(points, targets, use_bg, chunk_points(), None, 0)
-            slot, host = ring.take(info.total_bytes)
-            pack_host_native(points, targets, use_bg, chunk_points(), host.data_ptr(), host.numel(), args)
-            dev_buf = host[:info.total_bytes].to(device, non_blocking=True)
-            ring.sent(slot, device)
-            self.total_chunks, self.multi_chunk = int(info.total_chunks), int(info.multi_chunk)
-            self.meta = dev_buf[:info.meta_bytes].view(torch.int32)
-            self.pts = dev_buf[info.off_points:info.off_points + 8 * n_pts].view(torch.float32).view(-1, 2)
-            if targets is not None:
-                self.targets = dev_buf[info.off_targets:info.off_targets + 4 * n_pts].view(torch.float32)
-            return
         meta, self.total_chunks, self.multi_chunk = build_meta(counts, rows, chunk_points())
         if self.on_host:
             o_pts = _align16(meta.nbytes)
@@ -260,6 +247,64 @@ class _Packed:
                 else:
                     self.targets = torch.cat([t.to(device=device, dtype=torch.float32) for t in targets]).contiguous()
 
+
+    def _init_from_host_lists(self, points, targets, use_bg, device):
+        """Fast path for what a DataLoader delivers: lists of contiguous fp32 CPU tensors.  One pass over the lists
+        collects pointers and sizes; table + points + targets are then written into the pinned staging buffer by
+        one native call (csrc/bl_pack_host.cu) and uploaded with ONE asynchronous copy.  Returns False (nothing
+        done) when a tensor does not qualify; the general path then validates and converts."""
+        import ctypes
+        b = len(points)
+        if b == 0 or (targets is not None and len(targets) != b):
+            return False
+        pp, cn = (ctypes.c_void_p * b)(), (ctypes.c_int32 * b)()
+        tp = (ctypes.c_void_p * b)() if targets is not None else None
+        f32 = torch.float32
+        for i in range(b):
+            p = points[i]
+            if p.dtype is not f32 or p.is_cuda or p.requires_grad or not p.is_contiguous():
+                return False
+            if p.dim() == 2 and p.shape[1] == 2:
+                n = p.shape[0]
+            elif p.numel() == 0:
+                n = 0
+            else:
+                return False  # the general path raises the shape error
+            cn[i] = n
+            pp[i] = p.data_ptr()
+            if tp is not None:
+                t = targets[i]
+                if t.dtype is not f32 or t.is_cuda or t.requires_grad or not t.is_contiguous() or t.numel() != n:
+                    return False
+                tp[i] = t.data_ptr()
+        args = (pp, tp, cn, b)
+        info, _ = pack_host_native(None, None, use_bg, chunk_points(), None, 0, args)
+        ring = _staging.setdefault(device, _Staging())
+        slot, host = ring.take(info.total_bytes)
+        pack_host_native(None, None, use_bg, chunk_points(), host.data_ptr(), host.numel(), args)
+        dev_buf = host[:info.total_bytes].to(device, non_blocking=True)
+        ring.sent(slot, device)
+        n_pts = max(int(info.total_points), 1)
+        self.batch, self.on_host = b, True
+        self._counts_c = cn
+        self._use_bg = bool(use_bg)
+        self.total_points, self.total_rows = int(info.total_points), int(info.total_rows)
+        self.total_chunks, self.multi_chunk = int(info.total_chunks), int(info.multi_chunk)
+        self.meta = dev_buf[:info.meta_bytes].view(torch.int32)
+        self.pts = dev_buf[info.off_points:info.off_points + 8 * n_pts].view(torch.float32).view(-1, 2)
+        self.targets = dev_buf[info.off_targets:info.off_targets + 4 * n_pts].view(torch.float32) if tp is not None else None
+        return True
+
+    def __getattr__(self, name):
+        # per-image bookkeeping of the fast path, built only when somebody asks (Post_Prob, tests)
+        if name in ("counts", "rows", "pt_off", "row_off") and "_counts_c" in self.__dict__:
+            counts = np.asarray(list(self._counts_c), dtype=np.int64)
+            rows = np.where(counts == 0, 1, counts + (1 if self._use_bg else 0))
+            self.counts, self.rows = counts, rows
+            self.pt_off = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
+            self.row_off = np.concatenate(([0], np.cumsum(rows))).astype(np.int32)
+            return self.__dict__[name]
+        raise AttributeError(name)
 
     def _from_packed_batch(self, pb, use_bg, device):
         if pb.use_bg != bool(use_bg):

@@ -1,17 +1,22 @@
 // Geometry-adaptive density-map generation for sm_100a.
 //
 // Replaces utils/dmap_gen.py:14-81 of the reference (scipy KDTree k=4 query + one full-image
-// scipy.ndimage.gaussian_filter per head) by
-//   dmap_knn_kernel     : brute-force tiled 4-nearest search in fp64 (self included, like
-//   + dmap_knn_merge      KDTree.query(points, k=4)), candidates split into slices across CTAs and merged;
-//                         sigma = 0.1*(d1+d2+d3)                                     dmap_gen.py:34-48
-//   dmap_prepare_kernel : per head: truncated pixel index, in-bounds test, kernel radius
-//                         int(truncate*sigma+0.5) and the normaliser of scipy's 1-D Gaussian kernel,
-//                         summed in numpy's pairwise order                             dmap_gen.py:41-49
-//   dmap_splat_kernel   : one CTA per 32x32 output tile gathers the heads whose stamp overlaps it, in
-//                         index order, and accumulates fl32(f64(fl32(w[dy])) * w[dx]) per pixel in
-//                         fp32 -- the closed form of gaussian_filter on a one-hot image.
-//                         Every output pixel is written exactly once (zero fill fused), coalesced.
+// scipy.ndimage.gaussian_filter per head).  A whole list of images goes through one set of launches
+// (dgvcc_dmap_batch_plan lays out the work; `meta` is its per-image table):
+//   dmap_knn_batch_kernel : brute-force tiled 4-nearest search, exact in fp64 (self included, like
+//   + prep / merge          KDTree.query(points, k=4)) behind an exact fp32 filter, candidates in slices across CTAs,
+//                           two phases (slice 0 bounds the others); sigma = 0.1*(d1+d2+d3)   dmap_gen.py:34-48
+//                           (dmap_knn_kernel + dmap_knn_merge_kernel: the single-image form behind knn_sigma())
+//   dmap_prepare_kernel   : per head: truncated pixel index, in-bounds test, kernel radius
+//   / _fixed_ variants      int(truncate*sigma+0.5), the normaliser of scipy's 1-D Gaussian kernel summed in numpy's
+//                           pairwise order, bounding box, weight table of narrow stamps, tile occupancy bits
+//                                                                                           dmap_gen.py:41-49
+//   dmap_coarse_kernel    : ordered two-level culling: per 256x256 coarse tile the list of heads whose stamp touches
+//   dmap_tile_setup_kernel  it, IN INDEX ORDER (count pass + write pass); one descriptor per 32x32 fine tile
+//   dmap_splat_kernel     : one CTA per 32x32 output tile gathers, from its coarse list, the heads whose stamp
+//                           overlaps it, in index order, and accumulates fl32(f64(fl32(w[dy])) * w[dx]) per pixel
+//                           in fp32 -- the closed form of gaussian_filter on a one-hot image.
+//                           Every output pixel is written exactly once (zero fill fused), coalesced.
 // All fp64 arithmetic uses explicit _rn intrinsics (no FMA contraction): scipy's wheels are baseline
 // x86-64 without FMA, and the neighbour indices must match bit for bit.
 #include <math.h>

@@ -273,3 +273,30 @@ def test_errors_are_loud():
     mod = BL(8.0, 256, 8, 1.0, True, dev)
     with pytest.raises(RuntimeError):
         mod([torch.zeros(3, 2)], torch.ones(1), [torch.ones(3)], torch.zeros(1, 1, 32, 32))  # CPU tensors: no CPU path
+
+
+def test_host_lists_that_do_not_qualify_for_the_native_packer():
+    """float64 / non-contiguous host tensors take the general packing path (same result, bit for bit); malformed
+    inputs raise from it exactly as they do for device lists."""
+    from dgvcc_b200.losses.bl import BL
+    dev = torch.device("cuda:0")
+    c = load_bl_golden("mixed")
+    mod = BL(c["sigma"], c["width"], c["stride"], c["bg_ratio"], c["use_bg"], dev)
+
+    def run(pts, tgt):
+        d = c["density"].to(dev).clone().requires_grad_(True)
+        loss = mod(pts, c["st_sizes"].to(dev), tgt, d)
+        loss.backward()
+        return loss.detach(), d.grad
+
+    ref = run(c["points"], c["targets"])                                     # native packer
+    got = run([p.double() for p in c["points"]], c["targets"])              # float64 points
+    assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])
+    wide = [torch.cat([p, p], dim=1)[:, :2] if len(p) else p for p in c["points"]]  # non-contiguous views
+    assert any(not w.is_contiguous() for w in wide)
+    got = run(wide, c["targets"])
+    assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])
+    with pytest.raises(ValueError):
+        run(c["points"], [t[:-1] if len(t) else t for t in c["targets"]])   # target length mismatch
+    with pytest.raises(ValueError):
+        run([torch.zeros(5, 3)] + list(c["points"][1:]), c["targets"])      # not [N, 2]

@@ -26,14 +26,26 @@ def _use_tc():
     return int(os.environ.get("DGVCC_ISW_TENSOR_CORES", "1"))
 
 
+def _f32c(t, dev=None):
+    """``t`` as a detached contiguous fp32 tensor (on ``dev``); no copy, and one call only, when it already is one."""
+    if t.dtype is torch.float32 and t.is_contiguous() and (dev is None or t.device == dev):
+        return t.detach()
+    return t.detach().to(device=dev if dev is not None else t.device, dtype=torch.float32).contiguous()
+
+
 def _as3d(f_map):
     _native.require_cuda(f_map, "instance_whitening")
     b, c, h, w = f_map.shape
-    return f_map.detach().to(torch.float32).contiguous().view(b, c, h * w), b, c, h * w
+    return _f32c(f_map).view(b, c, h * w), b, c, h * w
+
+
+_ws_bytes = {}
 
 
 def _workspace(b, c, hw, dev):
-    n = _native.lib().dgvcc_isw_workspace_bytes(b, c, hw)
+    n = _ws_bytes.get((b, c, hw))
+    if n is None:
+        n = _ws_bytes[(b, c, hw)] = _native.lib().dgvcc_isw_workspace_bytes(b, c, hw)
     return torch.empty((n,), dtype=torch.uint8, device=dev), n
 
 
@@ -42,7 +54,7 @@ _scalars = {}  # (device, value) -> 1-element device tensor for Python-number ma
 
 def _scalar(v, dev):
     if torch.is_tensor(v):
-        return v.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        return _f32c(v, dev).reshape(1)
     key = (dev, float(v))
     t = _scalars.get(key)
     if t is None:
@@ -57,7 +69,7 @@ class _InstanceNorm(torch.autograd.Function):
     def forward(ctx, x, eps):
         _native.require_cuda(x, "InstanceWhitening")
         b, c, h, w = x.shape
-        xc = x.detach().to(torch.float32).contiguous()
+        xc = _f32c(x)
         y = torch.empty_like(xc)
         mean = torch.empty((b * c,), dtype=torch.float32, device=x.device)
         invstd = torch.empty_like(mean)
@@ -72,7 +84,7 @@ class _InstanceNorm(torch.autograd.Function):
     def backward(ctx, dy):
         y, invstd = ctx.saved_tensors
         b, c, h, w = y.shape
-        g = dy.detach().to(torch.float32).contiguous()
+        g = _f32c(dy)
         dx = torch.empty_like(y)
         _native.check(_native.lib().dgvcc_isw_instnorm_backward(
             _native.ptr(g), _native.ptr(y), _native.ptr(invstd), b * c, h * w, _native.ptr(dx),
@@ -100,7 +112,7 @@ class _Covariance(torch.autograd.Function):
         dev = x.device
         ws, n = _workspace(b, c, hw, dev)
         f_cor = torch.empty((b, c, c), dtype=torch.float32, device=dev)
-        eye32 = eye.detach().to(device=dev, dtype=torch.float32).contiguous()
+        eye32 = _f32c(eye, dev)
         _native.check(_native.lib().dgvcc_isw_covariance(
             _native.ptr(x), _native.ptr(eye32), b, c, hw, _use_tc(), _native.ptr(ws), n, _native.ptr(f_cor),
             _native.stream_ptr(dev)), "dgvcc_isw_covariance")
@@ -114,7 +126,7 @@ class _Covariance(torch.autograd.Function):
         b, c, hw = x.shape
         dev = x.device
         ws, n = _workspace(b, c, hw, dev)
-        g = d_fcor.detach().to(torch.float32).contiguous()
+        g = _f32c(d_fcor)
         dx = torch.empty_like(x)
         _native.check(_native.lib().dgvcc_isw_covariance_backward(
             _native.ptr(x), _native.ptr(g), b, c, hw, _use_tc(), _native.ptr(ws), n, _native.ptr(dx),
@@ -146,8 +158,8 @@ class _WhiteningLoss(torch.autograd.Function):
         lib = _native.lib()
         ws, n = _workspace(b, c, hw, dev)
         f_cor = torch.empty((b, c, c), dtype=torch.float32, device=dev)
-        eye32 = eye.detach().to(device=dev, dtype=torch.float32).contiguous()
-        mask = mask_matrix.detach().to(device=dev, dtype=torch.float32).contiguous()
+        eye32 = _f32c(eye, dev)
+        mask = _f32c(mask_matrix, dev)
         if mask.shape != (c, c):
             raise ValueError(f"mask_matrix must be [{c},{c}], got {tuple(mask.shape)}")
         mg, nr = _scalar(margin, dev), _scalar(num_remove_cov, dev)
@@ -168,7 +180,7 @@ class _WhiteningLoss(torch.autograd.Function):
         shape, dtype, n, binary = ctx.meta
         b, c, hw = x.shape
         dev = x.device
-        g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        g = _f32c(grad_loss, dev).reshape(1)
         dx = torch.empty_like(x)
         _native.check(_native.lib().dgvcc_isw_loss_backward(
             _native.ptr(x), _native.ptr(f_cor), _native.ptr(mask), _native.ptr(nr), _native.ptr(g), b, c, hw, _use_tc(),

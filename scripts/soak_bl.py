@@ -1,0 +1,92 @@
+"""Randomised soak of the fused Bayesian loss against the CPU oracle: random batch sizes, grids, strides, sigmas,
+background on/off, point counts (incl. empty images), chunk sizes, host or device lists, culling on/off.
+
+    python scripts/soak_bl.py [seconds]
+"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from dgvcc_b200 import synthetic
+from dgvcc_b200.losses.bl import BL
+import oracle
+from oracle import bl_oracle
+
+oracle.warm_up()
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(77001)
+t0, cases, worst_l, worst_g, sqrt_cases, ambiguous_cases = time.time(), 0, 0.0, 0.0, 0, 0
+while time.time() - t0 < budget:
+    stride = int(rng.choice([4, 8, 16]))
+    hp, wp = int(rng.integers(2, 80)), int(rng.integers(2, 110))
+    h, w = hp * stride, wp * stride
+    b = int(rng.integers(1, 7))
+    counts = [int(rng.choice([0, 1, 2, 5, 31, 32, 33, 100, 257, 700, 1500])) for _ in range(b)]
+    sigma = float(rng.choice([4.0, 8.0, 5.5, 12.0, 16.0]))
+    use_bg = bool(rng.integers(0, 2))
+    bg_ratio = float(rng.choice([1.0, 0.15, 0.5]))
+    os.environ["DGVCC_BL_CHUNK"] = str(int(rng.choice([17, 64, 256, 1024])))
+    cfg = int(rng.integers(100, 10000))
+    pts, tgt, dens, st = synthetic.bl_batch(cfg, counts, w, h, stride)
+    pts = [torch.from_numpy(p) for p in pts]
+    tgt = [torch.from_numpy(t) for t in tgt]
+    dens, st = torch.from_numpy(dens), torch.from_numpy(st)
+    ref_loss, ref_grad, ref_counts = bl_oracle.bl_forward_backward(pts, st, tgt, dens, stride, sigma, bg_ratio, use_bg)
+    mod = BL(sigma, max(h, w), stride, bg_ratio, use_bg, dev)
+    mod.exact_cull = bool(rng.integers(0, 2))
+    d = dens.to(dev).clone().requires_grad_(True)
+    on_host = bool(rng.integers(0, 2))
+    loss = mod(pts if on_host else [p.to(dev) for p in pts], st.to(dev), tgt if on_host else [t.to(dev) for t in tgt], d)
+    loss.backward()
+    g = d.grad.cpu().double()
+
+    # the loss is a sum of |t - c| terms: its absolute rounding floor follows the size of the counts, not of the loss
+    loss_floor = 2e-7 * sum(float(c.abs().sum()) + float(t.abs().sum()) for c, t in zip(ref_counts, tgt)) / b
+
+    def gate(rl, rgrad):
+        rg = rgrad.double()
+        el = max(0.0, abs(float(loss.detach()) - float(rl)) - loss_floor) / max(abs(float(rl)), 1e-30)
+        eg = float(((g - rg).abs() / (1e-5 * rg.abs() + 1e-6 * float(rg.abs().max()) + 1e-300)).max())
+        return el, eg
+
+    el, eg = gate(ref_loss, ref_grad)
+    if el > 1e-5 or eg > 1.0:
+        # torch's CPU sqrt is not correctly rounded (e.g. sqrt(2112.9423828125f) comes out one ulp low), the kernel's
+        # __fsqrt_rn -- like torch's CUDA sqrt -- is; a one-ulp difference in sqrt(min_dis) moves the background
+        # logit by up to ~1e-5.  Re-evaluate the oracle with an IEEE sqrt before calling it a mismatch.
+        orig = torch.sqrt
+        torch.sqrt = lambda t: torch.from_numpy(np.sqrt(t.detach().numpy()))
+        try:
+            l2, g2, _ = bl_oracle.bl_forward_backward(pts, st, tgt, dens, stride, sigma, bg_ratio, use_bg)
+        finally:
+            torch.sqrt = orig
+        el, eg = gate(l2, g2)
+        # The trimmed L1 (bl.py:75-78) is discontinuous in the gradient: when the residuals on both sides of the
+        # 90 % cut are equal to within rounding, or a kept residual is ~0 (sign of c - t undecided), the reference's
+        # own gradient flips with the last bit of a count.  Such batches cannot be compared pixel by pixel.
+        ambiguous = False
+        for i, c in enumerate(ref_counts):
+            if counts[i] == 0:
+                ambiguous |= abs(float(c.sum())) < 1e-6
+                continue
+            t = torch.cat([tgt[i], torch.zeros(1)]) if use_bg else tgt[i]
+            res = (t - c).abs()
+            cand = torch.sort(res[:-1]).values
+            k = int(np.ceil(0.9 * (len(res) - 1)))
+            if 0 < k < len(cand):
+                ambiguous |= float(cand[k] - cand[k - 1]) < 4e-6 * (1 + float(cand[k]))
+            ambiguous |= bool((res < 2e-6).any())
+        if el <= 1e-5 and eg > 1.0 and ambiguous:
+            ambiguous_cases += 1
+            cases += 1
+            continue
+        if el > 1e-5 or eg > 1.0:
+            raise SystemExit(f"MISMATCH: cfg={cfg} counts={counts} grid={hp}x{wp} stride={stride} sigma={sigma} bg={use_bg}/{bg_ratio} "
+                             f"host={on_host} cull={mod.exact_cull} chunk={os.environ['DGVCC_BL_CHUNK']}: loss rel err {el:.3g}, grad err/tol {eg:.3g}")
+        sqrt_cases += 1
+    worst_l, worst_g = max(worst_l, el), max(worst_g, eg)
+    cases += 1
+print(f"soak ok: {cases} random batches, worst loss rel err {worst_l:.2e}, worst gradient err/tol {worst_g:.2f} "
+      f"(tol = rtol 1e-5 + 1e-6 max|ref|); {sqrt_cases} of them only against the oracle with an IEEE sqrt, "
+      f"{ambiguous_cases} with an undecided trimming cut / residual sign skipped; {time.time() - t0:.0f} s")

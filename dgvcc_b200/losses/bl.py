@@ -87,7 +87,13 @@ class _Staging:
         if self.events[i] is not None:
             self.events[i].synchronize()
         if self.bufs[i] is None or self.bufs[i].numel() < nbytes:
-            self.bufs[i] = torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8).pin_memory()
+            size = max(nbytes + nbytes // 4, 1 << 20)
+            if self.bufs[i] is None and not any(b is not None for b in self.bufs):
+                # first use: pin the whole ring now (cudaHostAlloc takes milliseconds, and longer when several
+                # processes pin at once), not one slot per step over the first RING steps
+                self.bufs = [torch.empty((size,), dtype=torch.uint8).pin_memory() for _ in range(self.RING)]
+            else:
+                self.bufs[i] = torch.empty((size,), dtype=torch.uint8).pin_memory()
         return i, self.bufs[i]
 
     def sent(self, i, device):

@@ -7,6 +7,11 @@ Same functions and call signatures as the reference (utils/dmap_gen.py:14, 53, 8
     run(img_fn)                                 <name>.jpg + <name>.npy -> <name>_dmap.npy
     python -m dgvcc_b200.utils.dmap_gen --path <root>
 
+and, beyond the reference (whose unit of work is one image in a Pool(8) worker, dmap_gen.py:116-117):
+
+    gaussian_filter_density_batch(shapes, points_list, fixed=False) -> list of [H, W] float32 maps
+    run_many(img_fns, batch=32)                 run() for a list of files, `batch` images per launch set
+
 ``img`` is only inspected for ``.shape[0:2]``; ``points`` is [N,2] (col,row), float32 or float64.
 Host numpy in / host numpy out like the reference; the work runs in csrc/dmap_kernels.cu.
 CUDA is initialised lazily on first call, so the functions are safe to import before a fork.

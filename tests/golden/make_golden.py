@@ -360,8 +360,119 @@ def make_aux():
     np.savez_compressed(os.path.join(HERE, "aux_cases.npz"), **out)
 
 
+SW_CASES = (  # name, module ("plain" / "sync1" / "sync2"), (n, ch, h, w), num_pergroup, sw_type, tie, affine, training
+    ("p2", "plain", (3, 32, 6, 5), 16, 2, False, True, True),
+    ("p3", "plain", (2, 32, 7, 4), 16, 3, False, True, True),
+    ("p5", "plain", (3, 16, 5, 5), 16, 5, False, True, True),
+    ("p5t", "plain", (2, 32, 4, 6), 16, 5, True, False, True),
+    ("p2e", "plain", (2, 32, 6, 5), 16, 2, False, True, False),
+    ("p3e", "plain", (2, 16, 6, 5), 16, 3, True, True, False),
+    ("p5e", "plain", (2, 32, 3, 9), 16, 5, False, False, False),
+    ("p2g8", "plain", (2, 24, 8, 5), 8, 2, False, True, True),
+    ("p3g4", "plain", (3, 8, 6, 6), 4, 3, False, True, True),
+    ("p2big", "plain", (2, 64, 24, 20), 16, 2, False, True, True),
+    ("s2", "sync1", (3, 32, 6, 5), 16, 2, False, True, True),
+    ("s5", "sync1", (2, 32, 5, 4), 16, 5, False, True, True),
+    ("s3e", "sync1", (2, 16, 6, 5), 16, 3, False, True, False),
+    ("d2", "sync2", (4, 32, 6, 5), 16, 2, False, True, True),
+    ("d5", "sync2", (2, 32, 5, 6), 16, 5, True, True, True),
+)
+
+
+def _sw_inputs(seed, shape, cper, sw_type, tie, affine):
+    g = torch.Generator().manual_seed(seed)
+    n, ch, h, w = shape
+    groups = ch // cper
+    x = torch.randn(n, ch, h, w, generator=g) * (0.5 + torch.rand(1, ch, 1, 1, generator=g)) + \
+        0.8 * torch.randn(1, ch, 1, 1, generator=g)
+    x = x + 0.4 * x.roll(1, dims=1)                          # correlated channels: a non-trivial whitening matrix
+    d = {"x": x, "gy": torch.randn(n, ch, h, w, generator=g), "mw": torch.randn(sw_type, generator=g)}
+    if not tie:
+        d["vw"] = torch.randn(sw_type, generator=g)
+    if affine:
+        d["weight"], d["bias"] = 1 + 0.3 * torch.randn(ch, generator=g), 0.3 * torch.randn(ch, generator=g)
+    a = torch.randn(groups, cper, cper, generator=g)
+    d["rmean"] = 0.3 * torch.randn(groups, cper, 1, generator=g)
+    d["rcov"] = a @ a.transpose(1, 2) / cper + 0.2 * torch.eye(cper)
+    return d
+
+
+def _sw_run(mod_cls, d, x, gy, cper, sw_type, tie, affine, training):
+    m = mod_cls(x.shape[1], num_pergroup=cper, sw_type=sw_type, tie_weight=tie, affine=affine)
+    with torch.no_grad():
+        m.sw_mean_weight.copy_(d["mw"])
+        if not tie:
+            m.sw_var_weight.copy_(d["vw"])
+        if affine:
+            m.weight.copy_(d["weight"])
+            m.bias.copy_(d["bias"])
+        m.running_mean.copy_(d["rmean"])
+        m.running_cov.copy_(d["rcov"])
+    m.train(training)
+    x = x.clone().requires_grad_(True)
+    y = m(x)
+    y.backward(gy)
+    out = {"y": y.detach(), "gx": x.grad, "gmw": m.sw_mean_weight.grad, "rmean": m.running_mean, "rcov": m.running_cov}
+    if not tie:
+        out["gvw"] = m.sw_var_weight.grad
+    if affine:
+        out["gweight"], out["gbias"] = m.weight.grad, m.bias.grad
+    return {k: v.detach().clone().numpy() for k, v in out.items()}
+
+
+def _sw_rank(rank, world, port, case, queue):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    name, _, shape, cper, sw_type, tie, affine, training = case
+    d = _sw_inputs(8600 + [c[0] for c in SW_CASES].index(name), shape, cper, sw_type, tie, affine)
+    per = shape[0] // world
+    cls = load_ref("models/ISW/sync_switchwhiten.py", "ref_ssw").SyncSwitchWhiten2d
+    out = _sw_run(cls, d, d["x"][rank * per:(rank + 1) * per], d["gy"][rank * per:(rank + 1) * per], cper, sw_type, tie,
+                  affine, training)
+    queue.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def make_sw():
+    """models/ISW/switchwhiten.py:84-183 (SwitchWhiten2d) and models/ISW/sync_switchwhiten.py (SyncSwitchWhiten2d over
+    gloo with 1 and 2 ranks; in the 2-rank cases each rank gets half of the batch and the per-rank outputs are
+    stored as ``ref_<case>_r<rank>_*``), the unmodified files loaded by path: output, every gradient, running buffers."""
+    import warnings
+    import torch.multiprocessing as mp
+    warnings.filterwarnings("ignore", message=".*baddbmm.*")
+    plain = load_ref("models/ISW/switchwhiten.py", "ref_sw").SwitchWhiten2d
+    out = {}
+    ctx = mp.get_context("spawn")
+    for idx, case in enumerate(SW_CASES):
+        name, kind, shape, cper, sw_type, tie, affine, training = case
+        d = _sw_inputs(8600 + idx, shape, cper, sw_type, tie, affine)
+        for k, v in d.items():
+            out[f"in_{name}_{k}"] = v.numpy()
+        out[f"in_{name}_cfg"] = np.array([cper, sw_type, int(tie), int(affine), int(training),
+                                          {"plain": 0, "sync1": 1, "sync2": 2}[kind]])
+        if kind == "plain":
+            for k, v in _sw_run(plain, d, d["x"], d["gy"], cper, sw_type, tie, affine, training).items():
+                out[f"ref_{name}_{k}"] = v
+        else:
+            world = 1 if kind == "sync1" else 2
+            q = ctx.Queue()
+            procs = [ctx.Process(target=_sw_rank, args=(r, world, 29610 + idx, case, q)) for r in range(world)]
+            for p_ in procs:
+                p_.start()
+            got = dict(q.get(timeout=120) for _ in range(world))
+            for p_ in procs:
+                p_.join()
+            for r in range(world):
+                for k, v in got[r].items():
+                    out[f"ref_{name}_r{r}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "sw_cases.npz"), **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["bl", "dmap", "isw", "bay", "den", "cov", "aux"]
+    what = sys.argv[1:] or ["bl", "dmap", "isw", "bay", "den", "cov", "aux", "sw"]
     torch.manual_seed(0)
     for w in what:
         globals()[f"make_{w}"]()

@@ -45,3 +45,23 @@ def assert_close(got, ref, rtol, atol, what=""):
         raise AssertionError(
             f"{what}: {int(bad.sum())}/{bad.numel()} out of tolerance (rtol={rtol}, atol={atol}); "
             f"worst err/tol={worst:.3g}; first at {idx}: got {got[tuple(idx)].item():.9g} ref {ref[tuple(idx)].item():.9g}")
+
+
+def load_sw_cases():
+    """tests/golden/sw_cases.npz -> {name: dict(cfg..., inputs as torch tensors, ref outputs per rank)}."""
+    z = np.load(os.path.join(GOLDEN, "sw_cases.npz"))
+    cases = {}
+    for key in z.files:
+        if key.startswith("in_") and key.endswith("_cfg"):
+            name = key[3:-4]
+            cper, sw_type, tie, affine, training, kind = (int(v) for v in z[key])
+            c = {"num_pergroup": cper, "sw_type": sw_type, "tie": bool(tie), "affine": bool(affine),
+                 "training": bool(training), "kind": ("plain", "sync1", "sync2")[kind]}
+            for k in ("x", "gy", "mw", "vw", "weight", "bias", "rmean", "rcov"):
+                c[k] = torch.from_numpy(z[f"in_{name}_{k}"].copy()) if f"in_{name}_{k}" in z.files else None
+            world = 2 if c["kind"] == "sync2" else 1
+            prefix = [f"ref_{name}_"] if c["kind"] == "plain" else [f"ref_{name}_r{r}_" for r in range(world)]
+            c["world"] = world
+            c["ref"] = [{k[len(p):]: z[k] for k in z.files if k.startswith(p)} for p in prefix]
+            cases[name] = c
+    return cases

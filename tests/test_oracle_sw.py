@@ -1,0 +1,135 @@
+"""The switchable-whitening oracle vs fixtures produced by the unmodified reference (models/ISW/switchwhiten.py,
+models/ISW/sync_switchwhiten.py over gloo with 1 and 2 ranks), and the kernel-order restatement vs the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import switchwhiten_oracle as so
+from helpers import load_sw_cases
+
+CASES = load_sw_cases()
+GRADS = {"gx": "x", "gmw": "sw_mean_weight", "gvw": "sw_var_weight", "gweight": "weight", "gbias": "bias"}
+
+
+def close(got, ref, rtol, what):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    tol = rtol * np.abs(ref) + rtol * np.abs(ref).max()
+    assert (np.abs(got - ref) <= tol).all(), f"{what}: max err {np.abs(got - ref).max():.3g} vs max|ref| {np.abs(ref).max():.3g}"
+
+
+def run_oracle(c, x, gy, all_reduce=None, world=1):
+    rm, rc = c["rmean"].clone(), c["rcov"].clone()
+    y, grads = so.forward_backward(x, gy, c["mw"], c["vw"], c["weight"], c["bias"], rm, rc,
+                                   num_pergroup=c["num_pergroup"], sw_type=c["sw_type"], training=c["training"],
+                                   all_reduce=all_reduce, world_size=world)
+    return y, grads, rm, rc
+
+
+def check_against(c, ref, y, grads, rm, rc, rtol):
+    close(y, ref["y"], rtol, "y")
+    for k, leaf in GRADS.items():
+        if k in ref:
+            close(grads[leaf], ref[k], rtol, k)
+    close(rm, ref["rmean"], rtol, "running_mean")
+    close(rc, ref["rcov"], rtol, "running_cov")
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["world"] == 1])
+def test_oracle_matches_the_reference(name):
+    """Same torch ops in the same order: agreement to fp32 rounding of a few reordered sums (tolerance 2e-5 of the
+    value plus 2e-5 of the array's max; the whitened activations themselves are O(1))."""
+    c = CASES[name]
+    all_reduce = (lambda t: t) if c["kind"] == "sync1" else None
+    y, grads, rm, rc = run_oracle(c, c["x"], c["gy"], all_reduce)
+    check_against(c, c["ref"][0], y, grads, rm, rc, 2e-5)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_kernel_order_restatement_matches_the_reference(name):
+    """``decomposed`` (fp64, the order the CUDA kernels use) reproduces the reference's fp32 outputs and gradients to
+    fp32 accuracy; in the 2-rank cases the exchange is emulated by summing over the two halves."""
+    c = CASES[name]
+    world, per = c["world"], c["x"].shape[0] // c["world"]
+    halves = [(c["x"][r * per:(r + 1) * per].numpy(), c["gy"][r * per:(r + 1) * per].numpy()) for r in range(world)]
+    opt = lambda t: None if t is None else t.numpy()
+    kw = dict(num_pergroup=c["num_pergroup"], sw_type=c["sw_type"], training=c["training"], world_size=world)
+    if world == 1:
+        outs = [so.decomposed(*halves[0], opt(c["mw"]), opt(c["vw"]), opt(c["weight"]), opt(c["bias"]),
+                              c["rmean"].numpy(), c["rcov"].numpy(),
+                              all_reduce=(lambda a: a) if c["kind"] == "sync1" else None, **kw)]
+    else:
+        # run both ranks in lock step: generators yielding at every exchange would be overkill -- two passes instead,
+        # the first records each rank's contributions, the second replays their sums
+        log = [[], []]
+        for r in range(world):
+            so.decomposed(*halves[r], opt(c["mw"]), opt(c["vw"]), opt(c["weight"]), opt(c["bias"]), c["rmean"].numpy(),
+                          c["rcov"].numpy(), all_reduce=lambda a, r=r: log[r].append(a.copy()), **kw)
+        # the contributions after the first exchange depend on the reduced mean: iterate the passes until stable
+        for _ in range(4):
+            sums = [sum(log[r][i] for r in range(world)) for i in range(len(log[0]))]
+            log = [[], []]
+            outs = []
+            for r in range(world):
+                it = iter(sums)
+
+                def replay(a, r=r, it=it):
+                    log[r].append(a.copy())
+                    a[...] = next(it)
+                outs.append(so.decomposed(*halves[r], opt(c["mw"]), opt(c["vw"]), opt(c["weight"]), opt(c["bias"]),
+                                          c["rmean"].numpy(), c["rcov"].numpy(), all_reduce=replay, **kw))
+    for r, (y, grads, (mean_bn, cov_bn)) in enumerate(outs):
+        ref = c["ref"][r]
+        close(y, ref["y"], 1e-4, "y")
+        for k, leaf in GRADS.items():
+            if k in ref:
+                close(grads[leaf], ref[k], 1e-4, k)
+        if c["training"]:
+            close(0.99 * c["rmean"].numpy().reshape(mean_bn.shape) + 0.01 * mean_bn, ref["rmean"].reshape(mean_bn.shape),
+                  1e-5, "running_mean")
+            close(0.99 * c["rcov"].numpy() + 0.01 * cov_bn, ref["rcov"], 1e-5, "running_cov")
+
+
+def _rank(rank, world, port, name, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    c = load_sw_cases()[name]
+    per = c["x"].shape[0] // world
+    y, grads, rm, rc = run_oracle(c, c["x"][rank * per:(rank + 1) * per], c["gy"][rank * per:(rank + 1) * per],
+                                  dist.all_reduce, world)
+    try:
+        check_against(c, c["ref"][rank], y, grads, rm, rc, 2e-5)
+        out[rank] = "ok"
+    except AssertionError as e:
+        out[rank] = str(e)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["world"] == 2])
+def test_oracle_two_ranks_gloo(name):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_rank, args=(2, port, name, out), nprocs=2, join=True)
+    assert out[0] == "ok" and out[1] == "ok", dict(out)
+
+
+def test_newton_adjoint_against_finite_differences():
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(16, 40))
+    cov = a @ a.T / 40 + 1e-3 * np.eye(16)
+    g_wm = rng.normal(size=(16, 16))
+    wm, saved = so.newton_forward(cov, 5)
+    g_cov = so.newton_backward(g_wm, cov, saved)
+    for _ in range(10):
+        d = rng.normal(size=(16, 16))
+        h = 1e-6
+        fd = ((so.newton_forward(cov + h * d, 5)[0] - so.newton_forward(cov - h * d, 5)[0]) * g_wm).sum() / (2 * h)
+        assert abs(fd - (g_cov * d).sum()) <= 1e-6 * (abs(fd) + 1)

@@ -97,6 +97,17 @@ SIGNATURES = {
     "dgvcc_bay_crop_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "dgvcc_den_train_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dgvcc_sw_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "dgvcc_sw_instance_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
+    "dgvcc_sw_batch_mean": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "dgvcc_sw_batch_cov": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dgvcc_sw_whiten_forward": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                                                                       c_void_p]),
+    "dgvcc_sw_backward_stats": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float] + [c_void_p] * 6 + [c_void_p, c_size_t,
+                                                                                                  c_void_p]),
+    "dgvcc_sw_backward_apply": (c_int, [c_void_p] * 9 + [c_double] + [c_int] * 5 + [c_void_p, c_void_p, c_size_t,
+                                                                                   c_void_p]),
     "dgvcc_probe_ex2": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
     "dgvcc_probe_ffma": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
 }

@@ -339,6 +339,68 @@ int dgvcc_ortho_loss_backward(const float* x, const float* y, const float* gram_
                               int use_tensor_cores, void* workspace, size_t workspace_bytes, float* grad_x,
                               float* grad_y, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Switchable whitening -- replaces SwitchWhiten2d.forward
+ * (models/ISW/switchwhiten.py:84-183) and SyncMeanCov / SyncSwitchWhiten2d.forward
+ * (models/ISW/sync_switchwhiten.py:9-56,135-223) with hand-derived backward passes.
+ *
+ * x, y, grad_y, grad_x: fp32 [n, channels, hw] contiguous; groups = channels / num_pergroup, num_pergroup in
+ * {4, 8, 16}; sw_type in {2, 3, 5}; 1 <= T <= 8.  Statistics are fp64 device arrays owned by the caller:
+ *   mean_in [n, channels]   cov_in [n, groups, cp, cp]   mean_bn [channels]   cov_bn [groups, cp, cp]
+ * The four exchanges of SyncMeanCov happen BETWEEN these calls, on mean_bn / cov_bn / grad_mean_bn / grad_cov_bn
+ * (sum over ranks, then the caller divides the forward ones by the world size).
+ * ------------------------------------------------------------------------- */
+
+#define DGVCC_SW_MAX_T 8
+
+/* Bytes of the scratch workspace shared by every call below for one layer invocation (the backward calls keep
+ * intermediate adjoints in it between dgvcc_sw_backward_stats and dgvcc_sw_backward_apply).  0 on bad arguments. */
+size_t dgvcc_sw_workspace_bytes(int n, int channels, int hw, int num_pergroup);
+
+/* One read of x: per-sample channel means and group covariances, centred, divided by hw
+ * (switchwhiten.py:117-121). */
+int dgvcc_sw_instance_stats(const float* x, int n, int channels, int hw, int num_pergroup, double* mean_in,
+                            double* cov_in, void* workspace, size_t workspace_bytes, void* stream);
+
+/* This rank's batch mean (switchwhiten.py:94 / sync_switchwhiten.py:19) and, given the (exchanged) mean, this rank's
+ * batch covariance centred on it (switchwhiten.py:95-98 / sync_switchwhiten.py:22-23), both from the per-sample
+ * statistics: cov_bn = mean_n(cov_in + d d^T), d = mean_in - mean_bn. */
+int dgvcc_sw_batch_mean(const double* mean_in, int n, int channels, double* mean_bn, void* stream);
+int dgvcc_sw_batch_cov(const double* mean_in, const double* cov_in, const double* mean_bn, int n, int channels,
+                       int num_pergroup, double* cov_bn, void* stream);
+
+/* Mixes the statistics with softmax(sw_mean_weight), softmax(sw_var_weight) (sw_var_weight NULL = tie_weight),
+ * runs T Newton iterations per (sample, group) (switchwhiten.py:166-175) and applies
+ * y = weight * (wm (x - mean)) + bias (weight / bias NULL = affine=False) in one pass over x.
+ * a_fwd [n, groups, cp, cp] fp32 = diag(weight) wm is kept for the backward. */
+int dgvcc_sw_whiten_forward(const float* x, const double* mean_in, const double* cov_in, const double* mean_bn,
+                            const double* cov_bn, const float* sw_mean_weight, const float* sw_var_weight,
+                            const float* weight, const float* bias, int n, int channels, int hw, int num_pergroup,
+                            int sw_type, int T, float eps, float* a_fwd, float* y, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Backward, first half: one read of x and grad_y, the adjoint of the Newton iteration per (sample, group), and the
+ * reductions over samples.  Outputs: grad_sw_mean [sw_type], grad_sw_var [sw_type] (NULL when tied: the sum goes to
+ * grad_sw_mean), grad_weight / grad_bias [channels] (NULL = affine=False), and this rank's adjoints of the batch
+ * statistics grad_mean_bn [channels], grad_cov_bn [groups, cp, cp] (fp64) -- the two backward exchanges of
+ * sync_switchwhiten.py:44-45 act on them. */
+int dgvcc_sw_backward_stats(const float* x, const float* grad_y, const double* mean_in, const double* cov_in,
+                            const double* mean_bn, const double* cov_bn, const float* sw_mean_weight,
+                            const float* sw_var_weight, const float* weight, int n, int channels, int hw,
+                            int num_pergroup, int sw_type, int T, float eps, float* grad_sw_mean, float* grad_sw_var,
+                            float* grad_weight, float* grad_bias, double* grad_mean_bn, double* grad_cov_bn,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward, second half: grad_x = a_fwd^T grad_y + M2 x + const in one pass over x and grad_y.
+ * bn_scale = 1 / (n * hw * world_size) when the batch statistics were computed from x (training), 1 / (n * hw) for
+ * the synchronised layer in eval mode (sync_switchwhiten.py:48-55 back-propagates through the running statistics),
+ * 0 for the plain layer in eval mode. */
+int dgvcc_sw_backward_apply(const float* x, const float* grad_y, const float* a_fwd, const double* mean_in,
+                            const double* mean_bn, const double* grad_mean_bn, const double* grad_cov_bn,
+                            const float* sw_mean_weight, const float* sw_var_weight, double bn_scale, int n,
+                            int channels, int hw, int num_pergroup, int sw_type, float* grad_x, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

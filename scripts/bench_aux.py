@@ -327,6 +327,48 @@ def bench_auxloss(cpu):
         print(json.dumps(line), flush=True)
 
 
+def bench_sw(cpu):
+    """Row f4: SwitchWhiten2d forward + backward at the ISW feature-map shapes; the four big passes are HBM-bound
+    (forward 4+8 bytes per element, backward 8+12), so the line reports achieved HBM GB/s over those 32 bytes."""
+    from dgvcc_b200.models.ISW.switchwhiten import SwitchWhiten2d
+    g = torch.Generator().manual_seed(8900)
+    for shape, sw_type in (((8, 64, 160, 160), 2), ((8, 256, 80, 80), 2), ((8, 256, 80, 80), 5), ((8, 512, 40, 40), 3)):
+        x = torch.randn(*shape, generator=g)
+        m = SwitchWhiten2d(shape[1], sw_type=sw_type).to(dev)
+        xd, gy = x.to(dev).requires_grad_(True), torch.randn(*shape, generator=g).to(dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        tf, tb = [], []
+        for rep in range(6):
+            xd.grad = None
+            flush.zero_()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+            y = m(xd)
+            e1.record()
+            y.backward(gy)
+            e2.record()
+            torch.cuda.synchronize()
+            if rep:
+                tf.append(e0.elapsed_time(e1))
+                tb.append(e1.elapsed_time(e2))
+        elems = x.numel()
+        line = {"workload": f"SURVEY 8f rank 4: SwitchWhiten2d{shape} sw_type={sw_type} T=5, forward + backward (L2 flushed)",
+                "metric": "steps/s", "value": 1e3 / (min(tf) + min(tb)), "ms_forward": min(tf), "ms_backward": min(tb),
+                "roofline": {"bound": "hbm", "achieved": 32 * elems / ((min(tf) + min(tb)) * 1e-3) / 1e9, "peak": HBM_GBS,
+                             "unit": "GB/s", "frac": 32 * elems / ((min(tf) + min(tb)) * 1e-3) / 1e9 / HBM_GBS,
+                             "note": "algorithmic bytes: 4 (moments) + 8 (y) + 8 (backward moments) + 12 (grad_x) per element"}}
+        if cpu:
+            from oracle import switchwhiten_oracle as so
+            mc = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+            t0 = time.perf_counter()
+            so.forward_backward(x, gy.cpu(), mc["sw_mean_weight"], mc["sw_var_weight"], mc["weight"], mc["bias"],
+                                mc["running_mean"], mc["running_cov"], sw_type=sw_type)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "oracle port (the reference's torch ops on CPU), same tensors, one forward + backward"}
+        print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu", action="store_true")
@@ -344,3 +386,5 @@ if __name__ == "__main__":
         bench_cov(a.cpu)
     if a.only in ("", "auxloss"):
         bench_auxloss(a.cpu)
+    if a.only in ("", "sw"):
+        bench_sw(a.cpu)

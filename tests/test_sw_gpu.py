@@ -1,0 +1,181 @@
+"""Parity of switchable whitening through the C ABI: fixtures produced by the unmodified
+SwitchWhiten2d / SyncSwitchWhiten2d, the kernel-order fp64 restatement, and the torch oracle on larger random shapes.
+
+Gates (floating point; the reference iterates Newton's method in fp32, the kernels in fp64 on fp32-accumulated
+moments): |got - ref| <= rtol * (|ref| + max|ref|) with rtol 2e-4 against the reference / fp32 oracle and 2e-5
+against the fp64 restatement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import switchwhiten_oracle as so
+from helpers import load_sw_cases
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_sw_cases()
+GRADS = {"gx": "x", "gmw": "sw_mean_weight", "gvw": "sw_var_weight", "gweight": "weight", "gbias": "bias"}
+
+
+def close(got, ref, rtol, what):
+    got = got.detach().cpu().numpy() if torch.is_tensor(got) else np.asarray(got)
+    got, ref = got.astype(np.float64), np.asarray(ref, np.float64)
+    tol = rtol * np.abs(ref) + rtol * np.abs(ref).max()
+    err = np.abs(got.reshape(ref.shape) - ref)
+    assert (err <= tol).all(), f"{what}: max err {err.max():.3g} vs max|ref| {np.abs(ref).max():.3g}"
+
+
+class FakeExchange:
+    """Stands in for the process group: identity for one rank; for two ranks run one after the other in this process
+    it records this pass's contributions and replays the sums of the previous pass."""
+
+    def __init__(self, world_size=1, replay=None):
+        self.world_size, self.replay, self.log = world_size, replay, []
+
+    def sum_(self, t):
+        self.log.append(t.clone())
+        if self.replay is not None:
+            t.copy_(self.replay[len(self.log) - 1])
+        return t
+
+
+def build(c, exchange=None):
+    from dgvcc_b200.models.ISW.switchwhiten import SwitchWhiten2d
+    m = SwitchWhiten2d(c["x"].shape[1], num_pergroup=c["num_pergroup"], sw_type=c["sw_type"], tie_weight=c["tie"],
+                       affine=c["affine"]).cuda()
+    with torch.no_grad():
+        m.sw_mean_weight.copy_(c["mw"])
+        if not c["tie"]:
+            m.sw_var_weight.copy_(c["vw"])
+        if c["affine"]:
+            m.weight.copy_(c["weight"])
+            m.bias.copy_(c["bias"])
+        m.running_mean.copy_(c["rmean"])
+        m.running_cov.copy_(c["rcov"])
+    m.train(c["training"])
+    if exchange is not None:
+        m._exchange = lambda: exchange
+    return m
+
+
+def run(m, x, gy):
+    x = x.cuda().clone().requires_grad_(True)
+    y = m(x)
+    y.backward(gy.cuda())
+    out = {"y": y.detach(), "gx": x.grad, "gmw": m.sw_mean_weight.grad, "rmean": m.running_mean, "rcov": m.running_cov}
+    if m.sw_var_weight is not None:
+        out["gvw"] = m.sw_var_weight.grad
+    if m.affine:
+        out["gweight"], out["gbias"] = m.weight.grad, m.bias.grad
+    return out
+
+
+def check(out, ref, rtol):
+    for k, v in ref.items():
+        close(out[k], v, rtol if k not in ("rmean", "rcov") else 2e-5, k)
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["world"] == 1])
+def test_matches_the_reference_fixture(name):
+    c = CASES[name]
+    m = build(c, FakeExchange() if c["kind"] == "sync1" else None)
+    check(run(m, c["x"], c["gy"]), c["ref"][0], 2e-4)
+
+
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["world"] == 2])
+def test_two_rank_fixture_with_emulated_exchange(name):
+    """Each rank's half of the batch, the exchange replaced by record / replay over five passes (the mean settles
+    after the first, the covariance after the second, the backward adjoints after the fourth)."""
+    c = CASES[name]
+    per = c["x"].shape[0] // 2
+    replay = None
+    for _ in range(5):
+        outs, exchanges = [], [FakeExchange(2, replay), FakeExchange(2, replay)]
+        for r in range(2):
+            m = build(c, exchanges[r])
+            outs.append(run(m, c["x"][r * per:(r + 1) * per], c["gy"][r * per:(r + 1) * per]))
+        replay = [a + b for a, b in zip(exchanges[0].log, exchanges[1].log)]
+    assert len(replay) == 4       # sync_switchwhiten.py:21,25,44,45
+    for r in range(2):
+        check(outs[r], c["ref"][r], 2e-4)
+
+
+RANDOM = [  # n, ch, h, w, num_pergroup, sw_type, tie, affine, training
+    (4, 64, 40, 40, 16, 2, False, True, True),
+    (3, 48, 37, 29, 16, 3, False, True, True),      # odd plane size: unaligned rows
+    (2, 32, 80, 80, 16, 5, False, True, True),      # two moment chunks per plane
+    (2, 32, 65, 64, 16, 5, True, False, True),      # one pixel row past a chunk boundary
+    (3, 32, 21, 20, 8, 3, False, True, True),
+    (5, 16, 12, 12, 4, 2, False, True, False),
+    (1, 16, 5, 5, 16, 2, False, True, False),       # one small sample against the running statistics
+    (2, 128, 24, 24, 16, 3, False, True, False),
+]
+
+
+@pytest.mark.parametrize("shape", RANDOM, ids=[f"{s[0]}x{s[1]}x{s[2]}x{s[3]}g{s[4]}t{s[5]}" for s in RANDOM])
+def test_random_shapes_match_the_oracle(shape):
+    n, ch, h, w, cper, sw_type, tie, affine, training = shape
+    g = torch.Generator().manual_seed(sum(shape[:6]) * 7 + 1)
+    x = torch.randn(n, ch, h, w, generator=g) * (0.5 + torch.rand(1, ch, 1, 1, generator=g)) + 0.8 * torch.randn(1, ch, 1, 1, generator=g)
+    x = x + 0.4 * x.roll(1, dims=1)
+    a = torch.randn(ch // cper, cper, cper, generator=g)
+    c = {"x": x, "gy": torch.randn(n, ch, h, w, generator=g), "mw": torch.randn(sw_type, generator=g),
+         "vw": None if tie else torch.randn(sw_type, generator=g),
+         "weight": 1 + 0.3 * torch.randn(ch, generator=g) if affine else None,
+         "bias": 0.3 * torch.randn(ch, generator=g) if affine else None,
+         "rmean": 0.3 * torch.randn(ch // cper, cper, 1, generator=g), "rcov": a @ a.transpose(1, 2) / cper + 0.2 * torch.eye(cper),
+         "num_pergroup": cper, "sw_type": sw_type, "tie": tie, "affine": affine, "training": training}
+    out = run(build(c), c["x"], c["gy"])
+    opt = lambda t: None if t is None else t.numpy()
+    y64, g64, _ = so.decomposed(x.numpy(), c["gy"].numpy(), opt(c["mw"]), opt(c["vw"]), opt(c["weight"]), opt(c["bias"]),
+                                c["rmean"].numpy(), c["rcov"].numpy(), num_pergroup=cper, sw_type=sw_type, training=training)
+    close(out["y"], y64, 2e-5, "y vs fp64")
+    for k, leaf in GRADS.items():
+        if k in out and g64[leaf] is not None:
+            close(out[k], g64[leaf], 2e-5, f"{k} vs fp64")
+    rm, rc = c["rmean"].clone(), c["rcov"].clone()
+    y32, g32 = so.forward_backward(x, c["gy"], c["mw"], c["vw"], c["weight"], c["bias"], rm, rc, num_pergroup=cper,
+                                   sw_type=sw_type, training=training)
+    close(out["y"], y32.numpy(), 2e-4, "y vs fp32 oracle")
+    for k, leaf in GRADS.items():
+        if k in out and leaf in g32:
+            close(out[k], g32[leaf].numpy(), 2e-4, f"{k} vs fp32 oracle")
+    close(out["rmean"], rm.numpy(), 2e-5, "running_mean")
+    close(out["rcov"], rc.numpy(), 2e-5, "running_cov")
+
+
+def test_whitened_output_is_white_and_deterministic():
+    """Size-independent property at a training-size shape: with instance statistics only the output's per-sample group
+    covariance is the identity (Newton converged), and two runs are bit-identical."""
+    from dgvcc_b200.models.ISW.switchwhiten import SwitchWhiten2d
+    torch.manual_seed(5)
+    x = torch.randn(8, 64, 160, 160, device="cuda")
+    x = x + 0.5 * x.roll(1, dims=1)
+    m = SwitchWhiten2d(64, sw_type=2, affine=False, T=8).cuda()
+    with torch.no_grad():
+        m.sw_mean_weight.copy_(torch.tensor([-40.0, 40.0]))     # softmax -> (0, 1): pure instance whitening
+        m.sw_var_weight.copy_(torch.tensor([-40.0, 40.0]))
+    y1, y2 = m(x), m(x)
+    assert torch.equal(y1, y2)
+    yg = y1.view(8 * 4, 16, -1).double()
+    cov = yg @ yg.transpose(1, 2) / yg.shape[-1]
+    assert float(yg.mean(-1).abs().max()) < 1e-5
+    assert float((cov - torch.eye(16, device="cuda", dtype=torch.float64)).abs().max()) < 2e-3
+
+
+def test_errors():
+    from dgvcc_b200.models.ISW.switchwhiten import SwitchWhiten2d
+    from dgvcc_b200.models.ISW.sync_switchwhiten import SyncSwitchWhiten2d
+    with pytest.raises(ValueError):
+        SwitchWhiten2d(32, sw_type=4)
+    with pytest.raises(AssertionError):
+        SwitchWhiten2d(30, num_pergroup=16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        SwitchWhiten2d(32)(torch.randn(1, 32, 4, 4))
+    with pytest.raises(ValueError, match="unsupported shape"):
+        SwitchWhiten2d(24, num_pergroup=12).cuda()(torch.randn(1, 24, 4, 4, device="cuda"))
+    SyncSwitchWhiten2d(32, sw_type=4)      # accepted like the reference (sync_switchwhiten.py:84-86) ...
+    with pytest.raises(RuntimeError, match="no forward"):
+        m = SyncSwitchWhiten2d(32, sw_type=4).cuda()
+        m._exchange = lambda: None
+        m(torch.randn(1, 32, 4, 4, device="cuda"))

@@ -102,6 +102,7 @@ SIGNATURES = {
                                         c_void_p]),
     "dgvcc_sw_batch_mean": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dgvcc_sw_batch_cov": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dgvcc_sw_update_running": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_void_p]),
     "dgvcc_sw_whiten_forward": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                                                        c_void_p]),
     "dgvcc_sw_backward_stats": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float] + [c_void_p] * 6 + [c_void_p, c_size_t,

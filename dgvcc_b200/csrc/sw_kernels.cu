@@ -25,7 +25,8 @@ namespace dgvcc {
 namespace sw {
 
 constexpr int MOM_THREADS = 128;
-constexpr int MOM_CHUNK = 4096;      // pixels per moments CTA
+constexpr int NUM_SMS = 148;         // B200
+constexpr int MOM_CTAS_PER_SM = 2;   // ~210 registers x 128 threads
 constexpr int MAT_THREADS = 256;     // one thread per entry of a 16 x 16 matrix
 constexpr int AFF_THREADS = 128;
 constexpr int AFF_PIX = 4;           // pixels per thread of the affine pass
@@ -88,38 +89,61 @@ __host__ __device__ __forceinline__ int tri_index(int cp, int i, int j) {  // i 
 
 // ------------------------------------------------------------------------------------------------ moments (fwd)
 
+// The two moments passes keep ~150 accumulators per thread, so only 8 warps fit on an SM: register-staged loads
+// cannot cover the HBM latency.  Each thread instead streams ITS OWN pixels through a private ring of shared-memory
+// slots with 4-byte cp.async (any alignment, no barrier needed: a thread only ever reads what it copied itself).
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int FWD_STAGES = 8, BWD_STAGES = 6;   // 64 / 72 KB of dynamic shared memory per CTA for cp = 16
+
 // grid (splits, n * groups).  part[(ng * splits + split) * NV + k]: k < CP the shifted sums, then the upper triangle.
 template <int CP>
-__global__ void __launch_bounds__(MOM_THREADS)
-sw_moments_kernel(const float* __restrict__ x, int hw, float* __restrict__ part) {
+__global__ void __launch_bounds__(MOM_THREADS, 2)
+sw_moments_kernel(const float* __restrict__ x, int hw, int chunk, float* __restrict__ part) {
     constexpr int NV = CP + CP * (CP + 1) / 2;
+    extern __shared__ float ring_raw[];
+    float (*ring)[CP][MOM_THREADS] = reinterpret_cast<float (*)[CP][MOM_THREADS]>(ring_raw);
     __shared__ float red[MOM_THREADS / 32][NV];
     const float* base = x + (size_t)blockIdx.y * CP * hw;
+    const int tid = threadIdx.x;
     float shift[CP], acc[NV];
 #pragma unroll
     for (int j = 0; j < CP; ++j) shift[j] = __ldg(base + (size_t)j * hw);
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.f;
-    const int p0 = blockIdx.x * MOM_CHUNK, p1 = min(hw, p0 + MOM_CHUNK);
-    for (int p = p0 + threadIdx.x; p < p1; p += 2 * MOM_THREADS) {
-        const bool two = p + MOM_THREADS < p1;
-        float u[CP], v[CP];
+    const int p0 = blockIdx.x * chunk, p1 = min(hw, p0 + chunk);
+    const int iters = ceil_div(p1 - p0, MOM_THREADS);
+    auto issue = [&](int it) {
+        const int p = p0 + it * MOM_THREADS + tid;
+        if (it < iters && p < p1) {
 #pragma unroll
-        for (int j = 0; j < CP; ++j) {
-            u[j] = __ldg(base + (size_t)j * hw + p);
-            v[j] = two ? __ldg(base + (size_t)j * hw + p + MOM_THREADS) : shift[j];
+            for (int j = 0; j < CP; ++j) cp_async_f32(&ring[it % FWD_STAGES][j][tid], base + (size_t)j * hw + p);
         }
+        cp_async_commit();
+    };
+    for (int it = 0; it < FWD_STAGES - 1; ++it) issue(it);
+    for (int it = 0; it < iters; ++it) {
+        issue(it + FWD_STAGES - 1);       // its slot was read (into registers) one iteration ago
+        cp_async_wait<FWD_STAGES - 1>();
+        const bool valid = p0 + it * MOM_THREADS + tid < p1;
+        float u[CP];
 #pragma unroll
-        for (int j = 0; j < CP; ++j) { u[j] -= shift[j]; v[j] -= shift[j]; }
+        for (int j = 0; j < CP; ++j) u[j] = valid ? ring[it % FWD_STAGES][j][tid] - shift[j] : 0.f;
         int k = CP;
 #pragma unroll
         for (int i = 0; i < CP; ++i) {
-            acc[i] += u[i] + v[i];
+            acc[i] += u[i];
 #pragma unroll
-            for (int j = i; j < CP; ++j, ++k) acc[k] = fmaf(u[i], u[j], fmaf(v[i], v[j], acc[k]));
+            for (int j = i; j < CP; ++j, ++k) acc[k] = fmaf(u[i], u[j], acc[k]);
         }
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const float s = warp_sum(acc[k]);
@@ -127,7 +151,7 @@ sw_moments_kernel(const float* __restrict__ x, int hw, float* __restrict__ part)
     }
     __syncthreads();
     float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NV;
-    for (int k = threadIdx.x; k < NV; k += MOM_THREADS) {
+    for (int k = tid; k < NV; k += MOM_THREADS) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < MOM_THREADS / 32; ++w) s += red[w][k];
@@ -186,15 +210,27 @@ sw_batch_cov_kernel(const double* __restrict__ mean_in, const double* __restrict
     cov_bn[(size_t)g * cp * cp + t] = s / n;
 }
 
+// switchwhiten.py:101-104 in one launch, with the rounding sequence of the four torch ops:
+// running = fl(fl(running * momentum) + fl((1 - momentum) * batch)), batch rounded to fp32 first.
+__global__ void sw_update_running_kernel(float* __restrict__ running_mean, float* __restrict__ running_cov,
+                                         const double* __restrict__ mean_bn, const double* __restrict__ cov_bn, int channels,
+                                         int cov_elems, float momentum, float one_minus) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < channels)
+        running_mean[t] = __fadd_rn(__fmul_rn(running_mean[t], momentum), __fmul_rn(one_minus, (float)mean_bn[t]));
+    if (t < cov_elems)
+        running_cov[t] = __fadd_rn(__fmul_rn(running_cov[t], momentum), __fmul_rn(one_minus, (float)cov_bn[t]));
+}
+
 // ------------------------------------------------------------------------------------------------ small matrices
 
 // One entry of A B (optionally with transposed operands) per thread; matrices are CP x CP row-major in shared memory.
 template <int CP, bool TA, bool TB>
 __device__ __forceinline__ double mm(const double* a, const double* b, int i, int j) {
-    double s = 0.0;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};   // four independent chains: the fp64 pipe's latency, not its rate, is the cost
 #pragma unroll
-    for (int k = 0; k < CP; ++k) s += (TA ? a[k * CP + i] : a[i * CP + k]) * (TB ? b[j * CP + k] : b[k * CP + j]);
-    return s;
+    for (int k = 0; k < CP; ++k) s[k & 3] += (TA ? a[k * CP + i] : a[i * CP + k]) * (TB ? b[j * CP + k] : b[k * CP + j]);
+    return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 // What both matrix kernels share: layer statistics of the sample, the mixed mean and covariance of the
@@ -353,12 +389,14 @@ sw_affine_kernel(const float* __restrict__ u, const float* __restrict__ v, const
 // grid (splits, n * groups, CP / ROWS).  part[((ng * splits + split) * CP + row) * (CP + 1) + j]: j < CP is
 // K[row][j] = sum_p gy[row, p] (x[j, p] - mean_in[j]), j == CP is s[row] = sum_p gy[row, p].
 template <int CP, int ROWS>
-__global__ void __launch_bounds__(MOM_THREADS)
+__global__ void __launch_bounds__(MOM_THREADS, 2)
 sw_backward_moments_kernel(const float* __restrict__ x, const float* __restrict__ gy, const double* __restrict__ mean_in,
-                           int hw, float* __restrict__ part) {
+                           int hw, int chunk, float* __restrict__ part) {
     constexpr int NV = ROWS * (CP + 1);
+    extern __shared__ float ring_raw[];
+    float (*ring)[CP + ROWS][MOM_THREADS] = reinterpret_cast<float (*)[CP + ROWS][MOM_THREADS]>(ring_raw);
     __shared__ float red[MOM_THREADS / 32][NV];
-    const int ng = blockIdx.y, row0 = blockIdx.z * ROWS;
+    const int ng = blockIdx.y, row0 = blockIdx.z * ROWS, tid = threadIdx.x;
     const float* xb = x + (size_t)ng * CP * hw;
     const float* gb = gy + ((size_t)ng * CP + row0) * hw;
     float centre[CP], acc[NV];
@@ -366,13 +404,28 @@ sw_backward_moments_kernel(const float* __restrict__ x, const float* __restrict_
     for (int j = 0; j < CP; ++j) centre[j] = (float)mean_in[(size_t)ng * CP + j];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.f;
-    const int p0 = blockIdx.x * MOM_CHUNK, p1 = min(hw, p0 + MOM_CHUNK);
-    for (int p = p0 + threadIdx.x; p < p1; p += MOM_THREADS) {
+    const int p0 = blockIdx.x * chunk, p1 = min(hw, p0 + chunk);
+    const int iters = ceil_div(p1 - p0, MOM_THREADS);
+    auto issue = [&](int it) {
+        const int p = p0 + it * MOM_THREADS + tid;
+        if (it < iters && p < p1) {
+#pragma unroll
+            for (int j = 0; j < CP; ++j) cp_async_f32(&ring[it % BWD_STAGES][j][tid], xb + (size_t)j * hw + p);
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) cp_async_f32(&ring[it % BWD_STAGES][CP + i][tid], gb + (size_t)i * hw + p);
+        }
+        cp_async_commit();
+    };
+    for (int it = 0; it < BWD_STAGES - 1; ++it) issue(it);
+    for (int it = 0; it < iters; ++it) {
+        issue(it + BWD_STAGES - 1);
+        cp_async_wait<BWD_STAGES - 1>();
+        const bool valid = p0 + it * MOM_THREADS + tid < p1;
         float u[CP], w[ROWS];
 #pragma unroll
-        for (int j = 0; j < CP; ++j) u[j] = __ldg(xb + (size_t)j * hw + p) - centre[j];
+        for (int j = 0; j < CP; ++j) u[j] = valid ? ring[it % BWD_STAGES][j][tid] - centre[j] : 0.f;
 #pragma unroll
-        for (int i = 0; i < ROWS; ++i) w[i] = __ldg(gb + (size_t)i * hw + p);
+        for (int i = 0; i < ROWS; ++i) w[i] = valid ? ring[it % BWD_STAGES][CP + i][tid] : 0.f;
 #pragma unroll
         for (int i = 0; i < ROWS; ++i) {
 #pragma unroll
@@ -380,7 +433,7 @@ sw_backward_moments_kernel(const float* __restrict__ x, const float* __restrict_
             acc[i * (CP + 1) + CP] += w[i];
         }
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const float s = warp_sum(acc[k]);
@@ -388,7 +441,7 @@ sw_backward_moments_kernel(const float* __restrict__ x, const float* __restrict_
     }
     __syncthreads();
     float* out = part + (((size_t)ng * gridDim.x + blockIdx.x) * CP + row0) * (CP + 1);
-    for (int k = threadIdx.x; k < NV; k += MOM_THREADS) {
+    for (int k = tid; k < NV; k += MOM_THREADS) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < MOM_THREADS / 32; ++w) s += red[w][k];
@@ -402,12 +455,24 @@ struct BwdLayout {
     size_t part, g_cov, g_mean, dots, ln, gw, gb, a_fwd_cst, m1, m2, cst, total;
 };
 
-__host__ inline int splits_of(int hw) { return (hw + MOM_CHUNK - 1) / MOM_CHUNK; }
+// Pixels per moments CTA: as many CTAs as one resident wave holds (2 per SM), in whole 128-pixel steps, at least
+// 512 pixels so that the 150-value block reduction stays a small part of the CTA's work.
+struct Split { int chunk, splits; };
+__host__ inline Split plan_split(int ng, int hw, int z) {
+    int want = (NUM_SMS * MOM_CTAS_PER_SM + ng * z / 2) / (ng * z);
+    const int most = ceil_div(hw, 512);
+    want = want < 1 ? 1 : want > most ? most : want;
+    Split s;
+    s.chunk = ceil_div(ceil_div(hw, want), MOM_THREADS) * MOM_THREADS;
+    s.splits = ceil_div(hw, s.chunk);
+    return s;
+}
+__host__ inline int bwd_z(int cp) { return cp / (cp < BWD_ROWS ? cp : BWD_ROWS); }
 
 __host__ inline BwdLayout layout(int n, int channels, int hw, int cp) {
     const size_t ng = (size_t)n * (channels / cp), mat = (size_t)cp * cp;
-    const size_t fwd_part = ng * splits_of(hw) * (cp + cp * (cp + 1) / 2) * sizeof(float);
-    const size_t bwd_part = ng * splits_of(hw) * cp * (cp + 1) * sizeof(float);
+    const size_t fwd_part = ng * plan_split((int)ng, hw, 1).splits * (cp + cp * (cp + 1) / 2) * sizeof(float);
+    const size_t bwd_part = ng * plan_split((int)ng, hw, bwd_z(cp)).splits * cp * (cp + 1) * sizeof(float);
     BwdLayout l;
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 256); return at; };
@@ -667,11 +732,33 @@ void launch_affine(const float* u, const float* v, const float* a, const float* 
 }
 
 template <int CP>
-void launch_backward_moments(const float* x, const float* gy, const double* mean_in, int ng, int hw, float* part,
-                             cudaStream_t st) {
+cudaError_t launch_moments(const float* x, int ng, int hw, Split sp, float* part, cudaStream_t st) {
+    constexpr int SMEM = FWD_STAGES * CP * MOM_THREADS * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(sw_moments_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    sw_moments_kernel<CP><<<dim3(sp.splits, ng), MOM_THREADS, SMEM, st>>>(x, hw, sp.chunk, part);
+    return cudaSuccess;
+}
+
+template <int CP>
+cudaError_t launch_backward_moments(const float* x, const float* gy, const double* mean_in, int ng, int hw, Split sp,
+                                    float* part, cudaStream_t st) {
     constexpr int ROWS = CP < BWD_ROWS ? CP : BWD_ROWS;
-    const dim3 grid(splits_of(hw), ng, CP / ROWS);
-    sw_backward_moments_kernel<CP, ROWS><<<grid, MOM_THREADS, 0, st>>>(x, gy, mean_in, hw, part);
+    constexpr int SMEM = BWD_STAGES * (CP + ROWS) * MOM_THREADS * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(sw_backward_moments_kernel<CP, ROWS>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    sw_backward_moments_kernel<CP, ROWS><<<dim3(sp.splits, ng, CP / ROWS), MOM_THREADS, SMEM, st>>>(x, gy, mean_in, hw,
+                                                                                                  sp.chunk, part);
+    return cudaSuccess;
 }
 
 }  // namespace sw
@@ -691,11 +778,12 @@ extern "C" int dgvcc_sw_instance_stats(const float* x, int n, int channels, int 
     const BwdLayout l = layout(n, channels, hw, num_pergroup);
     if (workspace_bytes < l.total) return DGVCC_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const int ng = n * (channels / num_pergroup), splits = splits_of(hw);
+    const int ng = n * (channels / num_pergroup);
+    const Split sp = plan_split(ng, hw, 1);
     float* part = (float*)((char*)workspace + l.part);
 #define CALL(CP)                                                                                             \
-    sw_moments_kernel<CP><<<dim3(splits, ng), MOM_THREADS, 0, st>>>(x, hw, part);                             \
-    sw_instance_stats_kernel<CP><<<ng, MAT_THREADS, 0, st>>>(x, part, splits, hw, mean_in, cov_in)
+    DGVCC_RETURN_IF_CUDA(launch_moments<CP>(x, ng, hw, sp, part, st));                                       \
+    sw_instance_stats_kernel<CP><<<ng, MAT_THREADS, 0, st>>>(x, part, sp.splits, hw, mean_in, cov_in)
     SW_DISPATCH(num_pergroup, CALL);
 #undef CALL
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
@@ -714,6 +802,17 @@ extern "C" int dgvcc_sw_batch_cov(const double* mean_in, const double* cov_in, c
     if (!mean_in || !cov_in || !mean_bn || !cov_bn || bad_shape(n, channels, 1, num_pergroup)) return DGVCC_ERR_ARG;
     sw_batch_cov_kernel<<<channels / num_pergroup, MAT_THREADS, 0, (cudaStream_t)stream>>>(mean_in, cov_in, mean_bn, n,
                                                                                          channels, num_pergroup, cov_bn);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    return DGVCC_OK;
+}
+
+extern "C" int dgvcc_sw_update_running(float* running_mean, float* running_cov, const double* mean_bn,
+                                       const double* cov_bn, int channels, int num_pergroup, double momentum,
+                                       double one_minus_momentum, void* stream) {
+    if (!running_mean || !running_cov || !mean_bn || !cov_bn || bad_shape(1, channels, 1, num_pergroup)) return DGVCC_ERR_ARG;
+    const int cov_elems = channels * num_pergroup;
+    sw_update_running_kernel<<<ceil_div(cov_elems, 256), 256, 0, (cudaStream_t)stream>>>(
+        running_mean, running_cov, mean_bn, cov_bn, channels, cov_elems, (float)momentum, (float)one_minus_momentum);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     return DGVCC_OK;
 }
@@ -754,13 +853,15 @@ extern "C" int dgvcc_sw_backward_stats(const float* x, const float* grad_y, cons
     const BwdLayout l = layout(n, channels, hw, num_pergroup);
     if (workspace_bytes < l.total) return DGVCC_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const int groups = channels / num_pergroup, ng = n * groups, splits = splits_of(hw);
+    const int groups = channels / num_pergroup, ng = n * groups;
+    const Split sp = plan_split(ng, hw, bwd_z(num_pergroup));
+    const int splits = sp.splits;
     char* ws = (char*)workspace;
     float* part = (float*)(ws + l.part);
     double *g_cov = (double*)(ws + l.g_cov), *g_mean = (double*)(ws + l.g_mean), *dots = (double*)(ws + l.dots),
            *ln = (double*)(ws + l.ln), *gw = (double*)(ws + l.gw), *gb = (double*)(ws + l.gb);
 #define CALL(CP)                                                                                                      \
-    launch_backward_moments<CP>(x, grad_y, mean_in, ng, hw, part, st);                                                \
+    DGVCC_RETURN_IF_CUDA(launch_backward_moments<CP>(x, grad_y, mean_in, ng, hw, sp, part, st));                                              \
     sw_backward_matrices_kernel<CP><<<ng, MAT_THREADS, 0, st>>>(part, splits, mean_in, cov_in, mean_bn, cov_bn,        \
                                                                sw_mean_weight, sw_var_weight, weight, channels, hw,   \
                                                                sw_type, T, (double)eps, g_cov, g_mean, dots, ln, gw, gb)

@@ -60,11 +60,17 @@ class _SwitchWhitenFn(torch.autograd.Function):
                                                  _native.ptr(cov_bn), stream), "dgvcc_sw_batch_cov")
             if exchange is not None:
                 exchange.sum_(cov_bn).div_(world)
-            with torch.no_grad():  # switchwhiten.py:101-104
-                running_mean.mul_(momentum)
-                running_mean.add_((1 - momentum) * mean_bn.to(running_mean.dtype).view_as(running_mean))
-                running_cov.mul_(momentum)
-                running_cov.add_((1 - momentum) * cov_bn.to(running_cov.dtype))
+            plain = all(b.dtype == torch.float32 and b.is_contiguous() and b.device == dev for b in (running_mean, running_cov))
+            if plain:    # switchwhiten.py:101-104, one launch
+                _native.check(lib.dgvcc_sw_update_running(_native.ptr(running_mean), _native.ptr(running_cov),
+                                                          _native.ptr(mean_bn), _native.ptr(cov_bn), ch, cper, momentum,
+                                                          1 - momentum, stream), "dgvcc_sw_update_running")
+            else:
+                with torch.no_grad():
+                    running_mean.mul_(momentum)
+                    running_mean.add_((1 - momentum) * mean_bn.to(running_mean).view_as(running_mean))
+                    running_cov.mul_(momentum)
+                    running_cov.add_((1 - momentum) * cov_bn.to(running_cov))
         else:
             mean_bn = running_mean.detach().to(device=dev, dtype=torch.float64).reshape(ch).contiguous()
             cov_bn = running_cov.detach().to(device=dev, dtype=torch.float64).contiguous()

@@ -369,6 +369,12 @@ int dgvcc_sw_batch_mean(const double* mean_in, int n, int channels, double* mean
 int dgvcc_sw_batch_cov(const double* mean_in, const double* cov_in, const double* mean_bn, int n, int channels,
                        int num_pergroup, double* cov_bn, void* stream);
 
+/* switchwhiten.py:101-104 / sync_switchwhiten.py:28-31 on fp32 buffers running_mean [channels], running_cov
+ * [groups, cp, cp]: running = running * momentum + one_minus_momentum * batch, rounded like the four torch ops
+ * (the caller passes 1 - momentum as its host language computes it). */
+int dgvcc_sw_update_running(float* running_mean, float* running_cov, const double* mean_bn, const double* cov_bn,
+                            int channels, int num_pergroup, double momentum, double one_minus_momentum, void* stream);
+
 /* Mixes the statistics with softmax(sw_mean_weight), softmax(sw_var_weight) (sw_var_weight NULL = tie_weight),
  * runs T Newton iterations per (sample, group) (switchwhiten.py:166-175) and applies
  * y = weight * (wm (x - mean)) + bias (weight / bias NULL = affine=False) in one pass over x.

@@ -41,12 +41,12 @@ def check_against(c, ref, y, grads, rm, rc, rtol):
 
 @pytest.mark.parametrize("name", [n for n, c in CASES.items() if c["world"] == 1])
 def test_oracle_matches_the_reference(name):
-    """Same torch ops in the same order: agreement to fp32 rounding of a few reordered sums (tolerance 2e-5 of the
-    value plus 2e-5 of the array's max; the whitened activations themselves are O(1))."""
+    """Same torch ops in the same order: bit-identical in the authoring container; the gate leaves 1e-6 (of the value
+    plus of the array's max) for a host whose BLAS orders the bmm sums differently."""
     c = CASES[name]
     all_reduce = (lambda t: t) if c["kind"] == "sync1" else None
     y, grads, rm, rc = run_oracle(c, c["x"], c["gy"], all_reduce)
-    check_against(c, c["ref"][0], y, grads, rm, rc, 2e-5)
+    check_against(c, c["ref"][0], y, grads, rm, rc, 1e-6)
 
 
 @pytest.mark.parametrize("name", list(CASES))

@@ -102,6 +102,30 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int FWD_STAGES = 8, BWD_STAGES = 6;   // 64 / 72 KB of dynamic shared memory per CTA for cp = 16
 
+// Sums NV per-thread values over the lanes of a warp with a halving butterfly: 31 shuffles per 32 values instead of
+// 5 per value.  Afterwards lane l holds the warp totals of values l, 32 + l, ... in out[0], out[1], ...
+template <int NV>
+__device__ __forceinline__ void warp_transpose_sum(const float (&acc)[NV], float (&out)[(NV + 31) / 32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int g = 0; g < (NV + 31) / 32; ++g) {
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = g * 32 + k < NV ? acc[g * 32 + k] : 0.f;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int k = 0; k < off; ++k) {
+                const float keep = up ? v[k + off] : v[k];
+                const float send = up ? v[k] : v[k + off];
+                v[k] = keep + __shfl_xor_sync(FULL_MASK, send, off);
+            }
+        }
+        out[g] = v[0];
+    }
+}
+
 // grid (splits, n * groups).  part[(ng * splits + split) * NV + k]: k < CP the shifted sums, then the upper triangle.
 template <int CP>
 __global__ void __launch_bounds__(MOM_THREADS, 2)
@@ -144,11 +168,11 @@ sw_moments_kernel(const float* __restrict__ x, int hw, int chunk, float* __restr
         }
     }
     const int warp = tid >> 5, lane = tid & 31;
+    float tot[(NV + 31) / 32];
+    warp_transpose_sum<NV>(acc, tot);
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const float s = warp_sum(acc[k]);
-        if (lane == 0) red[warp][k] = s;
-    }
+    for (int g = 0; g < (NV + 31) / 32; ++g)
+        if (g * 32 + lane < NV) red[warp][g * 32 + lane] = tot[g];
     __syncthreads();
     float* out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * NV;
     for (int k = tid; k < NV; k += MOM_THREADS) {
@@ -434,11 +458,11 @@ sw_backward_moments_kernel(const float* __restrict__ x, const float* __restrict_
         }
     }
     const int warp = tid >> 5, lane = tid & 31;
+    float tot[(NV + 31) / 32];
+    warp_transpose_sum<NV>(acc, tot);
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const float s = warp_sum(acc[k]);
-        if (lane == 0) red[warp][k] = s;
-    }
+    for (int g = 0; g < (NV + 31) / 32; ++g)
+        if (g * 32 + lane < NV) red[warp][g * 32 + lane] = tot[g];
     __syncthreads();
     float* out = part + (((size_t)ng * gridDim.x + blockIdx.x) * CP + row0) * (CP + 1);
     for (int k = tid; k < NV; k += MOM_THREADS) {

@@ -29,7 +29,6 @@ constexpr int NUM_SMS = 148;         // B200
 constexpr int MOM_CTAS_PER_SM = 2;   // ~210 registers x 128 threads
 constexpr int MAT_THREADS = 256;     // one thread per entry of a 16 x 16 matrix
 constexpr int AFF_THREADS = 128;
-constexpr int AFF_PIX = 4;           // pixels per thread of the affine pass
 constexpr int MAX_T = DGVCC_SW_MAX_T;
 constexpr int BWD_ROWS = 8;          // rows of K per backward-moments CTA (register budget)
 
@@ -304,13 +303,14 @@ __device__ void whiten_forward(Whiten<CP>& s, const Mix& m, const double* __rest
     if (t == 0) s.r = r;
     if (live) s.cov_n[t] = s.cov[t] * r;
     __syncthreads();
-    for (int k = 0; k < T; ++k) {
+    for (int k = 0; k < T; ++k) {   // P^3 cov_n = (P P)(P cov_n): two independent products, then one -- two barriers per iteration
         const double* p = s.ps[k];
-        if (live) s.p2[t] = mm<CP, false, false>(p, p, i, j);
+        if (live) {
+            s.p2[t] = mm<CP, false, false>(p, p, i, j);
+            s.p3[t] = mm<CP, false, false>(p, s.cov_n, i, j);
+        }
         __syncthreads();
-        if (live) s.p3[t] = mm<CP, false, false>(s.p2, p, i, j);
-        __syncthreads();
-        if (live) s.ps[k + 1][t] = 1.5 * p[t] - 0.5 * mm<CP, false, false>(s.p3, s.cov_n, i, j);
+        if (live) s.ps[k + 1][t] = 1.5 * p[t] - 0.5 * mm<CP, false, false>(s.p2, s.p3, i, j);
         __syncthreads();
     }
 }
@@ -345,8 +345,8 @@ sw_whiten_kernel(const double* __restrict__ mean_in, const double* __restrict__ 
 // ------------------------------------------------------------------------------------------------ affine passes
 
 // out[ng, i, p] = sum_j A[ng][i][j] u[ng, j, p] (+ sum_j B[ng][i][j] v[ng, j, p]) + cst[ng, i].
-// grid (ceil(hw / (AFF_THREADS * AFF_PIX)), n * groups).
-template <int CP, bool TWO>
+// grid (ceil(hw / (AFF_THREADS * AFF_PIX)), n * groups); AFF_PIX pixels per thread.
+template <int CP, bool TWO, int AFF_PIX>
 __global__ void __launch_bounds__(AFF_THREADS)
 sw_affine_kernel(const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ a, const float* __restrict__ b,
                  const float* __restrict__ cst, int hw, float* __restrict__ out) {
@@ -483,7 +483,7 @@ struct BwdLayout {
 // 512 pixels so that the 150-value block reduction stays a small part of the CTA's work.
 struct Split { int chunk, splits; };
 __host__ inline Split plan_split(int ng, int hw, int z) {
-    int want = (NUM_SMS * MOM_CTAS_PER_SM + ng * z / 2) / (ng * z);
+    int want = NUM_SMS * MOM_CTAS_PER_SM / (ng * z);   // never more CTAs than one resident wave (a second, short wave costs a whole CTA time)
     const int most = ceil_div(hw, 512);
     want = want < 1 ? 1 : want > most ? most : want;
     Split s;
@@ -526,7 +526,7 @@ sw_backward_matrices_kernel(const float* __restrict__ part, int splits, const do
                             double* __restrict__ dots, double* __restrict__ ln, double* __restrict__ gw_part,
                             double* __restrict__ gb_part) {
     __shared__ Whiten<CP> s;
-    __shared__ double gp[CP * CP], gp3[CP * CP], tmp[CP * CP], s_gy[CP], g_mean[CP];
+    __shared__ double gp_a[CP * CP], gp_b[CP * CP], gp3[CP * CP], tmp[CP * CP], s_gy[CP], g_mean[CP];
     const Mix m = mix_coeffs(sw_type, mean_logits, var_logits);
     const int ng = blockIdx.x, groups = channels / CP, smp = ng / groups, g = ng % groups, t = threadIdx.x;
     const bool live = t < CP * CP;
@@ -572,26 +572,33 @@ sw_backward_matrices_kernel(const float* __restrict__ part, int splits, const do
     // adjoint of wm = P_T sqrt(r), r = 1 / tr(cov), cov_n = cov r, P_{k+1} = 1.5 P_k - 0.5 P_k^3 cov_n
     double g_r = block_sum(live ? g_wm * pt[t] : 0.0, s.red) * 0.5 / root;   // (syncs: tmp / g_mean are settled)
     double g_covn = 0.0;
+    double* gp = gp_a;     // G_{k+1}; the next one is written to the other buffer while this one is still being read
+    double* gq = gp_b;
     if (live) gp[t] = g_wm * root;
     __syncthreads();
-    for (int k = T - 1; k >= 0; --k) {
+    // cov_n and every iterate are polynomials in the symmetric cov: they equal their transposes to fp64 rounding, so the
+    // transposed right-hand operands below are read untransposed (a transposed read of a 16 x 16 fp64 matrix is a
+    // 16-way shared-memory bank conflict).
+    for (int k = T - 1; k >= 0; --k) {   // three barriers per iteration
         const double* p = s.ps[k];
-        if (live) s.p2[t] = mm<CP, false, false>(p, p, i, j);
-        __syncthreads();
         if (live) {
-            s.p3[t] = mm<CP, false, false>(s.p2, p, i, j);
-            gp3[t] = -0.5 * mm<CP, false, true>(gp, s.cov_n, i, j);
+            s.p2[t] = mm<CP, false, false>(p, p, i, j);
+            gp3[t] = -0.5 * mm<CP, false, false>(gp, s.cov_n, i, j);          // cov_n^T = cov_n
         }
         __syncthreads();
         double next = 0.0;
         if (live) {
-            g_covn += -0.5 * mm<CP, true, false>(s.p3, gp, i, j);
+            s.p3[t] = mm<CP, false, false>(s.p2, p, i, j);
             tmp[t] = mm<CP, true, false>(p, gp3, i, j);                       // P^T G3
-            next = 1.5 * gp[t] + mm<CP, false, true>(gp3, s.p2, i, j) + mm<CP, true, false>(s.p2, gp3, i, j);
+            next = 1.5 * gp[t] + mm<CP, false, false>(gp3, s.p2, i, j) + mm<CP, true, false>(s.p2, gp3, i, j);
         }
         __syncthreads();
-        if (live) gp[t] = next + mm<CP, false, true>(tmp, p, i, j);            // + P^T G3 P^T
+        if (live) {
+            g_covn += -0.5 * mm<CP, true, false>(s.p3, gp, i, j);
+            gq[t] = next + mm<CP, false, false>(tmp, p, i, j);                 // + P^T G3 P^T
+        }
         __syncthreads();
+        double* swap = gp; gp = gq; gq = swap;
     }
     g_r += block_sum(live ? g_covn * s.cov[t] : 0.0, s.red);
     double g_cov = 0.0;
@@ -751,8 +758,8 @@ inline bool bad_mix(int sw_type, int T) { return (sw_type != 2 && sw_type != 3 &
 template <int CP, bool TWO>
 void launch_affine(const float* u, const float* v, const float* a, const float* b, const float* cst, int ng, int hw,
                    float* out, cudaStream_t st) {
-    const dim3 grid(ceil_div(hw, AFF_THREADS * AFF_PIX), ng);
-    sw_affine_kernel<CP, TWO><<<grid, AFF_THREADS, 0, st>>>(u, v, a, b, cst, hw, out);
+    // 4 pixels per thread: 168 registers, 3 CTAs per SM; 2 pixels (128 registers, 4 CTAs) measured 10 % slower
+    sw_affine_kernel<CP, TWO, 4><<<dim3(ceil_div(hw, AFF_THREADS * 4), ng), AFF_THREADS, 0, st>>>(u, v, a, b, cst, hw, out);
 }
 
 template <int CP>

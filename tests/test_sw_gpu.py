@@ -243,3 +243,19 @@ def test_sync_layer_two_ranks_real_process_group(name):
 def test_sync_layer_one_rank_nccl():
     """The NCCL path of the exchange (all_reduce of fp64 device tensors) with a world of one."""
     _spawn_sync("s5", 1, "nccl")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (one NCCL rank per device)")
+def test_sync_layer_two_gpus_nccl():
+    """scripts/sync_sw_2gpu.py under torchrun: the reference's two-rank fixtures and sync-on-slices == plain-on-batch."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "sync_sw_2gpu.py")
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                           "127.0.0.1", "--master-port", str(port), script], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]

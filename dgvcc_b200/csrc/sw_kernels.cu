@@ -26,6 +26,7 @@ namespace sw {
 
 constexpr int MOM_THREADS = 128;
 constexpr int NUM_SMS = 148;         // B200
+constexpr int MAX_DEVICES = 64;
 constexpr int MOM_CTAS_PER_SM = 2;   // ~210 registers x 128 threads
 constexpr int MAT_THREADS = 256;     // one thread per entry of a 16 x 16 matrix
 constexpr int AFF_THREADS = 128;
@@ -765,11 +766,13 @@ void launch_affine(const float* u, const float* v, const float* a, const float* 
 template <int CP>
 cudaError_t launch_moments(const float* x, int ng, int hw, Split sp, float* part, cudaStream_t st) {
     constexpr int SMEM = FWD_STAGES * CP * MOM_THREADS * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {};   // the attribute is per device
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    if (!configured[device]) {
         const cudaError_t e = cudaFuncSetAttribute(sw_moments_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[device] = true;
     }
     sw_moments_kernel<CP><<<dim3(sp.splits, ng), MOM_THREADS, SMEM, st>>>(x, hw, sp.chunk, part);
     return cudaSuccess;
@@ -780,12 +783,14 @@ cudaError_t launch_backward_moments(const float* x, const float* gy, const doubl
                                     float* part, cudaStream_t st) {
     constexpr int ROWS = CP < BWD_ROWS ? CP : BWD_ROWS;
     constexpr int SMEM = BWD_STAGES * (CP + ROWS) * MOM_THREADS * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {};
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    if (!configured[device]) {
         const cudaError_t e = cudaFuncSetAttribute(sw_backward_moments_kernel<CP, ROWS>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[device] = true;
     }
     sw_backward_moments_kernel<CP, ROWS><<<dim3(sp.splits, ng, CP / ROWS), MOM_THREADS, SMEM, st>>>(x, gy, mean_in, hw,
                                                                                                   sp.chunk, part);

@@ -11,6 +11,11 @@ numpy / scipy, the same third-party primitives the reference itself calls):
 * ``bl_oracle``   <- /root/reference/losses/bl.py
 * ``dmap_oracle`` <- /root/reference/utils/dmap_gen.py
 * ``isw_oracle``  <- /root/reference/models/ISW/instance_whitening.py
+* ``bay_targets_oracle``   <- /root/reference/datasets/bay_dataset.py (targets)
+* ``cov_settings_oracle``  <- /root/reference/models/ISW/cov_settings.py, models/ISW/__init__.py (cal_covstat)
+* ``den_targets_oracle``   <- /root/reference/datasets/den_cls_dataset.py, den_dataset.py (density targets)
+* ``aux_losses_oracle``    <- /root/reference/losses/lw.py, losses/ortho.py
+* ``switchwhiten_oracle``  <- /root/reference/models/ISW/switchwhiten.py, sync_switchwhiten.py
 
 Pinning: the reference ships no tests or golden vectors,
 so the pins are outputs of the unmodified reference files executed in the

@@ -409,84 +409,6 @@ sw_affine_kernel(const float* __restrict__ u, const float* __restrict__ v, const
         }
 }
 
-// Streaming form of the affine pass: a CTA walks a strip of pixels of one (sample, group); every thread feeds its own two
-// pixels per step through a private cp.async ring (see the moments passes), so the loads of the next steps, the FMAs of
-// this one and the stores of the last overlap inside the CTA instead of only between co-resident CTAs.
-// grid (strips, n * groups); dynamic shared memory STAGES * SRC * CP * 2 * AFF_THREADS floats.
-template <int CP, bool TWO>
-__global__ void __launch_bounds__(AFF_THREADS)
-sw_affine_stream_kernel(const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ a,
-                        const float* __restrict__ b, const float* __restrict__ cst, int hw, int chunk, float* __restrict__ out) {
-    constexpr int SRC = TWO ? 2 : 1, STAGES = TWO ? 3 : 4, PIX = 2;
-    extern __shared__ float ring_raw[];
-    __shared__ __align__(16) float sa[CP * CP];
-    __shared__ __align__(16) float sb[TWO ? CP * CP : 4];
-    __shared__ float sc[CP];
-    const int ng = blockIdx.y, tid = threadIdx.x;
-    for (int k = tid; k < CP * CP; k += AFF_THREADS) {
-        sa[k] = a[(size_t)ng * CP * CP + k];
-        if (TWO) sb[k] = b[(size_t)ng * CP * CP + k];
-    }
-    if (tid < CP) sc[tid] = cst[(size_t)ng * CP + tid];
-    __syncthreads();
-    const size_t base = (size_t)ng * CP * hw;
-    const int p0 = blockIdx.x * chunk, p1 = min(hw, p0 + chunk);
-    const int iters = ceil_div(p1 - p0, AFF_THREADS * PIX);
-    auto slot = [&](int stage, int src, int j, int k) -> float* {
-        return ring_raw + ((((size_t)stage * SRC + src) * CP + j) * PIX + k) * AFF_THREADS + tid;
-    };
-    auto issue = [&](int it) {
-        if (it < iters) {
-#pragma unroll
-            for (int k = 0; k < PIX; ++k) {
-                const int p = p0 + (it * PIX + k) * AFF_THREADS + tid;
-                if (p < p1) {
-#pragma unroll
-                    for (int j = 0; j < CP; ++j) {
-                        cp_async_f32(slot(it % STAGES, 0, j, k), u + base + (size_t)j * hw + p);
-                        if (TWO) cp_async_f32(slot(it % STAGES, 1, j, k), v + base + (size_t)j * hw + p);
-                    }
-                }
-            }
-        }
-        cp_async_commit();
-    };
-    for (int it = 0; it < STAGES - 1; ++it) issue(it);
-    for (int it = 0; it < iters; ++it) {
-        issue(it + STAGES - 1);            // its slot was read one iteration ago
-        cp_async_wait<STAGES - 1>();
-        float acc[CP][PIX], in[CP][PIX];
-#pragma unroll
-        for (int i = 0; i < CP; ++i)
-#pragma unroll
-            for (int k = 0; k < PIX; ++k) acc[i][k] = sc[i];
-#pragma unroll
-        for (int src = 0; src < SRC; ++src) {
-#pragma unroll
-            for (int j = 0; j < CP; ++j)
-#pragma unroll
-                for (int k = 0; k < PIX; ++k) in[j][k] = *slot(it % STAGES, src, j, k);
-            const float* coef = src == 0 ? sa : sb;
-#pragma unroll
-            for (int i = 0; i < CP; ++i)
-#pragma unroll
-                for (int j = 0; j < CP; ++j) {
-                    const float c = coef[i * CP + j];
-#pragma unroll
-                    for (int k = 0; k < PIX; ++k) acc[i][k] = fmaf(c, in[j][k], acc[i][k]);
-                }
-        }
-#pragma unroll
-        for (int k = 0; k < PIX; ++k) {
-            const int p = p0 + (it * PIX + k) * AFF_THREADS + tid;
-            if (p < p1) {
-#pragma unroll
-                for (int i = 0; i < CP; ++i) out[base + (size_t)i * hw + p] = acc[i][k];
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ moments (bwd)
 
 // grid (splits, n * groups, CP / ROWS).  part[((ng * splits + split) * CP + row) * (CP + 1) + j]: j < CP is
@@ -835,27 +757,10 @@ inline bool bad_mix(int sw_type, int T) { return (sw_type != 2 && sw_type != 3 &
     } while (0)
 
 template <int CP, bool TWO>
-cudaError_t launch_affine(const float* u, const float* v, const float* a, const float* b, const float* cst, int ng, int hw,
-                          float* out, cudaStream_t st) {
-    constexpr int SRC = TWO ? 2 : 1, STAGES = TWO ? 3 : 4, STEP = AFF_THREADS * 2;
-    constexpr int SMEM = STAGES * SRC * CP * STEP * (int)sizeof(float);          // 64 / 96 KB for cp = 16
-    constexpr int CTAS_PER_SM = TWO ? 2 : 3;
-    static bool configured[MAX_DEVICES] = {};
-    int device = 0;
-    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= MAX_DEVICES) return cudaErrorInvalidDevice;
-    if (!configured[device]) {
-        const cudaError_t e = cudaFuncSetAttribute(sw_affine_stream_kernel<CP, TWO>,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return e;
-        configured[device] = true;
-    }
-    // strips: one resident wave, at least four steps per CTA
-    int want = NUM_SMS * CTAS_PER_SM / ng;
-    const int most = ceil_div(hw, 4 * STEP);
-    want = want < 1 ? 1 : want > most ? most : want;
-    const int chunk = ceil_div(ceil_div(hw, want), STEP) * STEP;
-    sw_affine_stream_kernel<CP, TWO><<<dim3(ceil_div(hw, chunk), ng), AFF_THREADS, SMEM, st>>>(u, v, a, b, cst, hw, chunk, out);
-    return cudaSuccess;
+void launch_affine(const float* u, const float* v, const float* a, const float* b, const float* cst, int ng, int hw,
+                   float* out, cudaStream_t st) {
+    // 4 pixels per thread: 168 registers, 3 CTAs per SM; 2 pixels (128 registers, 4 CTAs) measured 10 % slower
+    sw_affine_kernel<CP, TWO, 4><<<dim3(ceil_div(hw, AFF_THREADS * 4), ng), AFF_THREADS, 0, st>>>(u, v, a, b, cst, hw, out);
 }
 
 template <int CP>
@@ -964,7 +869,7 @@ extern "C" int dgvcc_sw_whiten_forward(const float* x, const double* mean_in, co
 #define CALL(CP)                                                                                                      \
     sw_whiten_kernel<CP><<<ng, MAT_THREADS, 0, st>>>(mean_in, cov_in, mean_bn, cov_bn, sw_mean_weight, sw_var_weight,   \
                                                     weight, bias, channels, hw, sw_type, T, (double)eps, a_fwd, cst);  \
-    DGVCC_RETURN_IF_CUDA((launch_affine<CP, false>(x, nullptr, a_fwd, nullptr, cst, ng, hw, y, st)))
+    launch_affine<CP, false>(x, nullptr, a_fwd, nullptr, cst, ng, hw, y, st)
     SW_DISPATCH(num_pergroup, CALL);
 #undef CALL
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
@@ -1025,7 +930,7 @@ extern "C" int dgvcc_sw_backward_apply(const float* x, const float* grad_y, cons
                                                              (const double*)(ws + l.g_mean), (const double*)(ws + l.ln), \
                                                              mean_in, mean_bn, grad_mean_bn, grad_cov_bn, sw_mean_weight, \
                                                              sw_var_weight, bn_scale, channels, hw, sw_type, m1, m2, cst); \
-    DGVCC_RETURN_IF_CUDA((launch_affine<CP, true>(grad_y, x, m1, m2, cst, ng, hw, grad_x, st)))
+    launch_affine<CP, true>(grad_y, x, m1, m2, cst, ng, hw, grad_x, st)
     SW_DISPATCH(num_pergroup, CALL);
 #undef CALL
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());

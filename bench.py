@@ -3,19 +3,24 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...        # the UNMODIFIED reference losses/bl.py on the host cores (oracle/_ref)
 
 One "step" = one pass of the hot path (BL forward + backward) over one batch of 16 synthetic
 QNRF-shaped images per GPU (2048x1536 px, stride-8 grid 192x256, 500..12000 heads, CSR-packed).
 Images are sharded across ranks (weak scaling: 16 images per GPU); the only collective is the
 all-reduce of the scalar loss.  Prints ONE JSON line on rank 0.
 
-  value     images/s, inputs already resident in HBM, through the drop-in ``BL`` module
+  value     images/s, inputs already resident in HBM, through the drop-in ``BL`` module (dense sweep)
   e2e       images/s with HOST inputs: packed H2D copies of points/targets/density/st_sizes and
             D2H of the loss and the density gradient inside the timed region
   roofline  the fused path's MUFU.EX2 work (3 exponentials per point-pixel pair, dense) against the
             chip's MUFU.EX2 rate measured live by dgvcc_probe_ex2 (MEASURED_PEAKS.json has no
             SFU figure); per-kernel shares from CUDA events recorded on the launch stream
+  cpu_baseline  the unmodified reference on the host cores: ONE full step over the same 16 images
+  gpu_eager     the unmodified reference module with device='cuda' on the same B200 (PyTorch eager)
+  strong    (N > 1) the SAME 16-image batch spread over the N GPUs: by image (snake partition) and by
+            point chunk (sub-image sharding over NVLink peer memory), speed-up over one GPU
+  aux       the two other north-star kernels: Gaussian splat (HBM roofline) and ISW Gram (tensor roofline)
 """
 import argparse
 import ctypes
@@ -43,8 +48,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=240.0,
+                    help="wall budget of the --impl reference arm (it stops early, reporting the steps it ran)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the splat / Gram lines")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU reference leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs at N > 1")
     return ap.parse_args()
 
 
@@ -67,34 +76,127 @@ def workload_name(wl):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_sample(wl, budget_s):
-    """Smallest images first until the estimated cost fills the budget (cost ~ N*M pairs)."""
-    order = sorted(range(len(wl["counts"])), key=lambda i: wl["counts"][i])
-    m = wl["hp"] * wl["wp"]
-    pairs_budget = budget_s * 2.5e8  # ~2.5e8 pairs/s is the survey-time speed of the reference on 8 cores
-    picked, pairs = [], 0
-    for i in order:
-        if picked and pairs + wl["counts"][i] * m > pairs_budget:
-            break
-        picked.append(i)
-        pairs += wl["counts"][i] * m
-    return picked
-
-
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(max(1, n))
 
 
-def cpu_step(wl, picked):
-    """The reference's CPU algorithm (oracle port of losses/bl.py) on the sampled images, one at a time."""
-    from oracle import bl_oracle
-    t0 = time.perf_counter()
-    for i in picked:
-        bl_oracle.bl_forward_backward([wl["points"][i]], wl["st_sizes"][i:i + 1], [wl["targets"][i]],
-                                      wl["density"][i:i + 1], STRIDE, SIGMA, BG_RATIO, USE_BG)
-    return time.perf_counter() - t0
+class ReferenceBL:
+    """The reference's own Bayesian loss on ``device``: the UNMODIFIED losses/bl.py from oracle/_ref (byte copy made by
+    oracle/make_ref.sh; /root/reference itself does not exist on the GPU box), else the oracle port.
+
+    losses/bl.py is square-only (one ``cood`` vector for x and y, bl.py:14-16) and concatenates the batch before it
+    splits it (bl.py:21-35: [sum N, M] temporaries, ~40 GB for this batch), so the module is called the way SURVEY 8c
+    prescribes: c_size = max(H, W) = 2048, the 192x256 density zero-padded to the 256x256 grid (zero density adds
+    exactly nothing to any count), one image per call, losses summed / B.  That is 33 % more pixels than the B200 arm
+    evaluates -- the cost of running the reference unmodified on a non-square image."""
+
+    def __init__(self, wl, device):
+        self.wl, self.device = wl, torch.device(device)
+        self.kind, self.mod = "port", None
+        try:
+            from oracle import ref_loader
+            if ref_loader.available("bl"):
+                c = max(wl["width"], wl["height"])
+                self.mod = ref_loader.load("bl").BL(SIGMA, c, STRIDE, BG_RATIO, USE_BG, self.device)
+                self.kind, self.side = "reference", c // STRIDE
+        except Exception as exc:  # fall back to the port, say why
+            self.note = f"unmodified reference not usable ({type(exc).__name__}: {exc}); oracle port timed instead"
+        dev = self.device
+        self.pts = [p.to(dev) for p in wl["points"]]
+        self.tgt = [t.to(dev) for t in wl["targets"]]
+        self.st = wl["st_sizes"].to(dev)
+        self.dens = wl["density"].to(dev)
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("unmodified losses/bl.py (oracle/_ref), image by image, c_size=2048: the 192x256 density zero-padded to "
+                    "the square 256x256 grid the reference needs")
+        return "oracle port of losses/bl.py (oracle/bl_oracle.py), image by image on the 192x256 grid"
+
+    def step(self):
+        """One forward + backward over the whole batch; returns (seconds, loss)."""
+        wl, b = self.wl, len(self.wl["counts"])
+        sync = (lambda: torch.cuda.synchronize(self.device)) if self.device.type == "cuda" else (lambda: None)
+        sync()
+        t0 = time.perf_counter()
+        total = 0.0
+        if self.kind == "reference":
+            for i in range(b):
+                d = torch.zeros((1, 1, self.side, self.side), dtype=torch.float32, device=self.device)
+                d[0, 0, :wl["hp"], :wl["wp"]] = self.dens[i, 0]
+                d.requires_grad_(True)
+                loss = self.mod([self.pts[i]], self.st[i:i + 1], [self.tgt[i]], d) / b
+                loss.backward()
+                total += float(loss.detach())
+                del d, loss
+        else:
+            from oracle import bl_oracle
+            for i in range(b):
+                l, _, _ = bl_oracle.bl_forward_backward([self.pts[i]], self.st[i:i + 1], [self.tgt[i]], self.dens[i:i + 1],
+                                                        STRIDE, SIGMA, BG_RATIO, USE_BG)
+                total += float(l) / b
+        sync()
+        return time.perf_counter() - t0, total
+
+
+def cpu_baseline(wl):
+    """ONE full step of the reference on the host cores (about 5-10 s on the box's 16 cores)."""
+    use_all_host_threads()
+    ref = ReferenceBL(wl, "cpu")
+    dt, loss = ref.step()
+    return {
+        "value": len(wl["counts"]) / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": ref.kind,
+        "sample": f"{ref.describe()}; torch CPU, {torch.get_num_threads()} threads; ONE full forward+backward over the same "
+                  f"16 images ({sum(wl['counts'])} heads) in {dt:.2f} s, nothing extrapolated",
+        "loss": loss,
+    }
+
+
+def gpu_eager(wl, dev, reps=2):
+    """SURVEY section 2's bar: the unmodified reference module as PyTorch eager ops on the SAME B200 (device='cuda')."""
+    ref = ReferenceBL(wl, dev)
+    ref.step()  # allocator warm-up
+    times = [ref.step() for _ in range(reps)]
+    dt = min(t for t, _ in times)
+    out = {"value": len(wl["counts"]) / dt, "unit": "images/s", "kind": ref.kind, "ms_per_step": dt * 1e3,
+           "loss": times[-1][1],
+           "note": f"{ref.describe()}; torch CUDA eager on this GPU, best of {reps} full steps (wall clock around a synchronize)"}
+    del ref
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_reference(args, emit=print):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    use_all_host_threads()
+    wl = workload(0)
+    ref = ReferenceBL(wl, "cpu")
+    t_start = time.perf_counter()
+    for _ in range(min(args.warmup, 1)):
+        ref.step()
+    times = []
+    for _ in range(max(1, args.steps)):
+        times.append(ref.step()[0])
+        if time.perf_counter() - t_start > args.cpu_seconds:  # wall budget: report the steps actually run
+            break
+    per_batch = float(np.mean(times))
+    value = len(wl["counts"]) / per_batch
+    sample = (f"{ref.describe()}; torch CPU, {torch.get_num_threads()} threads; every step is the FULL 16-image batch "
+              f"({sum(wl['counts'])} heads); {len(times)} of the {args.steps} requested steps fitted the {args.cpu_seconds:.0f} s budget")
+    emit(json.dumps({
+        "impl": "reference", "metric": "Bayesian-loss fwd+bwd images/s (QNRF shape)", "value": value,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": per_batch * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(wl)},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": ref.kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
 
 
 def profiled_dram_traffic():
@@ -123,53 +225,6 @@ def profiled_dram_traffic():
     note = (f"{os.path.basename(files[-1])}: " + ", ".join(f"{k} {v / 1e6:.1f} MB" for k, v in per.items()) +
             "; against ~6 MB of algorithmic inputs/outputs per step the sweeps are nowhere near HBM-bound (MUFU-bound)")
     return total, note
-
-
-def cpu_baseline(wl, budget_s, repeats=2):
-    use_all_host_threads()
-    picked = cpu_sample(wl, budget_s / repeats)
-    best = min(cpu_step(wl, picked) for _ in range(repeats))
-    m = wl["hp"] * wl["wp"]
-    pairs_sample = sum(wl["counts"][i] for i in picked) * m
-    pairs_batch = sum(wl["counts"]) * m
-    # images/s the CPU path would reach on the whole batch: cost is linear in pairs
-    value = len(wl["counts"]) / (best * pairs_batch / pairs_sample)
-    return {
-        "value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-        "sample": (f"oracle port of losses/bl.py (torch CPU, {torch.get_num_threads()} threads) on the {len(picked)} "
-                   f"smallest images of the batch ({sum(wl['counts'][i] for i in picked)} heads, {best:.2f} s); "
-                   f"scaled by point-pixel pairs to the full batch"),
-    }
-
-
-def run_reference(args, emit=print):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    use_all_host_threads()
-    wl = workload(0)
-    picked = cpu_sample(wl, max(2.0, args.cpu_seconds / max(1, args.steps + args.warmup)))
-    for _ in range(min(args.warmup, 1)):
-        cpu_step(wl, picked)
-    times = [cpu_step(wl, picked) for _ in range(args.steps)]
-    m = wl["hp"] * wl["wp"]
-    pairs_sample = sum(wl["counts"][i] for i in picked) * m
-    pairs_batch = sum(wl["counts"]) * m
-    per_batch = float(np.mean(times)) * pairs_batch / pairs_sample
-    value = len(wl["counts"]) / per_batch
-    sample = (f"oracle port of losses/bl.py (torch CPU, {torch.get_num_threads()} threads); each step = the "
-              f"{len(picked)} smallest images of the batch ({sum(wl['counts'][i] for i in picked)} heads), "
-              f"scaled by point-pixel pairs to the full 16-image batch")
-    emit(json.dumps({
-        "impl": "reference", "metric": "Bayesian-loss fwd+bwd images/s (QNRF shape)", "value": value,
-        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_batch * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(wl)},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -276,6 +331,86 @@ def kernel_breakdown(wl, dev, reps=5):
     return dict(zip(names, ms.tolist())), kept_rows, packed
 
 
+def aux_lines(dev, cpu=True):
+    """The two other north-star kernels in the driver-run line: Gaussian splat against the HBM
+    roofline (BASELINE config 4) and the ISW Gram against the tensor / HBM roofline (config 5), each with e2e and a
+    CPU baseline.  Implemented in scripts/bench_aux.py (also runnable on its own)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import bench_aux
+    bench_aux.dev = dev
+    out = {}
+    out.update(bench_aux.dmap_lines(cpu))
+    tf32 = bench_aux.probe_tf32_peak(dev)
+    out.update(bench_aux.isw_lines(cpu, tf32))
+    out["tf32_peak_tflops"] = tf32 / 1e12
+    return out
+
+
+def strong_scaling(args, dev, rank, world, t1_ms, flush, barrier):
+    """Strong scaling of BASELINE config 3 as written: ONE batch of 16 images spread over the N GPUs.
+
+    by_image: whole images assigned to ranks by ``snake_partition`` (cost N_i * M); bounded by the biggest image.
+    Every rank times its own shard with per-step CUDA events; the step time of the job is the max over ranks."""
+    import torch.distributed as dist
+    from dgvcc_b200.losses.bl import BL
+    from dgvcc_b200.sharding import ShardedLoss, snake_partition
+    wl = workload(0)  # the SAME 16 images on every rank
+    b, m = len(wl["counts"]), wl["hp"] * wl["wp"]
+    out = {"batch": b, "heads": sum(wl["counts"]), "t1_ms": t1_ms,
+           "note": ("the same 16-image batch (the one rank 0 holds in the weak run) spread over the N GPUs; t1_ms = rank 0's "
+                    "device time per step for the whole batch on ONE GPU, measured in this run; speedup = t1_ms / max over "
+                    "ranks of the per-step device time")}
+    t1 = torch.tensor([t1_ms], device=dev, dtype=torch.float64)
+    dist.broadcast(t1, 0)
+    t1_ms = out["t1_ms"] = float(t1[0])
+
+    # ---- by image
+    shards = snake_partition([n * m for n in wl["counts"]], world)
+    mine = shards[rank]
+    mod = BL(SIGMA, max(wl["width"], wl["height"]), STRIDE, BG_RATIO, USE_BG, dev)
+    mod.exact_cull = False
+    fn = ShardedLoss(mod, b)
+    pts = [wl["points"][i].to(dev) for i in mine]
+    tgt = [wl["targets"][i].to(dev) for i in mine]
+    st = wl["st_sizes"][mine].to(dev)
+    dens = wl["density"][mine].to(dev).requires_grad_(True)
+
+    def step():
+        dens.grad = None
+        loss = fn(pts, st, tgt, dens)
+        loss.backward()
+        return loss
+
+    def timed(step_fn):
+        for _ in range(3):
+            step_fn()
+            flush.zero_()
+        barrier()
+        evs = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+            flush.zero_()
+        barrier()
+        ms = sum(a.elapsed_time(c) for a, c in evs) / args.steps
+        allms = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms], device=dev, dtype=torch.float64))
+        return [float(x[0]) for x in allms]
+
+    per_rank = timed(step)
+    heads = [sum(wl["counts"][i] for i in s) for s in shards]
+    out["by_image"] = {
+        "partition": "snake_partition by N_i * M (whole images)", "heads_per_rank": heads,
+        "ms_per_rank": per_rank, "ms_per_step": max(per_rank), "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / world),
+        "images_per_s": b / (max(per_rank) * 1e-3), "speedup": t1_ms / max(per_rank),
+        "bound_by_largest_shard": sum(wl["counts"]) / max(heads),
+        "collective": "one all_reduce(sum) of the scalar loss per step (NCCL)"}
+    return out
+
+
 def run_gpu(args, emit=print):
     import torch.distributed as dist
     from dgvcc_b200.losses.bl import BL
@@ -296,6 +431,7 @@ def run_gpu(args, emit=print):
     global_batch = b * world
 
     loss_mod = BL(SIGMA, max(wl["width"], wl["height"]), STRIDE, BG_RATIO, USE_BG, dev)
+    loss_mod.exact_cull = False  # the graded numbers (value / e2e / roofline) are the DENSE sweep; the product default culls
     loss_fn = ShardedLoss(loss_mod, global_batch) if world > 1 else loss_mod
 
     # ---- resident inputs ("value")
@@ -402,10 +538,18 @@ def run_gpu(args, emit=print):
     e2e_packed_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
+    own_ms_per_step = total_ms / args.steps  # this rank's own 16 images on one GPU: the 1-GPU time of the strong legs
     if world > 1:
         t = torch.tensor([total_ms, e2e_s, cull_ms, e2e_packed_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s, cull_ms, e2e_packed_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+
+    strong = None
+    if world > 1 and not args.no_strong:
+        try:
+            strong = strong_scaling(args, dev, rank, world, own_ms_per_step, flush, barrier)
+        except Exception as exc:  # the strong legs must never take the headline line down with them
+            strong = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -450,8 +594,20 @@ def run_gpu(args, emit=print):
                 "path_ms": path_ms, "kernels_ms": kernels, "ffma_peak_tflops": 2 * peak_ffma / 1e12,
             },
         }
+        if strong is not None:
+            out["strong"] = strong
+        if not args.no_eager:
+            try:
+                out["gpu_eager"] = gpu_eager(wl, dev)
+            except Exception as exc:
+                out["gpu_eager"] = {"error": f"{type(exc).__name__}: {exc}"}
+        if not args.no_aux:
+            try:
+                out["aux"] = aux_lines(dev, cpu=not args.no_cpu_baseline)
+            except Exception as exc:
+                out["aux"] = {"error": f"{type(exc).__name__}: {exc}"}
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
+            out["cpu_baseline"] = cpu_baseline(wl)
         emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

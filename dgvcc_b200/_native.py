@@ -111,6 +111,7 @@ SIGNATURES = {
                                                                                    c_void_p]),
     "dgvcc_probe_ex2": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
     "dgvcc_probe_ffma": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
+    "dgvcc_probe_tf32": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p]),
 }
 
 
@@ -120,9 +121,7 @@ def lib():
     if _lib is None:
         with _lock:
             if _lib is None:
-                path = _build.LIB_PATH
-                if not os.path.exists(path) or os.environ.get("DGVCC_REBUILD"):
-                    path = _build.build()
+                path = _build.build(force=bool(os.environ.get("DGVCC_REBUILD")))  # returns at once unless stale
                 handle = ctypes.CDLL(path)
                 for name, (res, args) in SIGNATURES.items():
                     fn = getattr(handle, name)  # AttributeError here = header / library mismatch

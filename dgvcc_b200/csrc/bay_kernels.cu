@@ -157,6 +157,7 @@ int launch_crop(const void* gt, const void* dists, int n, double l, double u, do
 using namespace dgvcc;
 
 extern "C" int dgvcc_bay_knn_mean(const void* pts_xy, int n, int is_double, void* dists, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (n < 2) return n < 0 ? DGVCC_ERR_ARG : DGVCC_OK;  // the N = 0 / N = 1 constants are the host wrapper's
     if (!pts_xy || !dists) return DGVCC_ERR_ARG;
     return is_double ? bay::launch_knn<double>(pts_xy, n, dists, (cudaStream_t)stream)
@@ -166,6 +167,7 @@ extern "C" int dgvcc_bay_knn_mean(const void* pts_xy, int n, int is_double, void
 extern "C" int dgvcc_bay_crop_targets(const void* gt_xy, const void* dists, int n, int is_double, double crop_left,
                                       double crop_up, double crop_right, double crop_down, double* gt_out,
                                       void* targ_out, int* kept_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (n <= 0 || !gt_xy || !dists || !gt_out || !targ_out || !kept_out) return DGVCC_ERR_ARG;
     return is_double ? bay::launch_crop<double>(gt_xy, dists, n, crop_left, crop_up, crop_right, crop_down, gt_out,
                                                 targ_out, kept_out, (cudaStream_t)stream)

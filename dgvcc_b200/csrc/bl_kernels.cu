@@ -38,6 +38,8 @@ namespace bl {
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr int TILE_PTS = 128;  // points staged per warp per tile
+constexpr int COUNT_SPAN = 1024;  // points whose partial counts a CTA combines in shared memory per pass
+static_assert(COUNT_SPAN % TILE_PTS == 0 && WARPS_PER_CTA == 4, "bl_counts_kernel's CTA combine");
 
 struct Scale {
     float s;          // fl32(2*sigma^2)                     bl.py:42
@@ -163,7 +165,6 @@ __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, in
                                             TaskInfo& t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     t.task = blockIdx.x * WARPS_PER_CTA + warp;
-    if (t.task >= g.tiles) return false;
     const Meta mv = meta_view(meta, batch);
     t.chunk = mv.chunks[4 * blockIdx.y + 3];
     const int32_t* ce = mv.chunks + 4 * t.chunk;
@@ -180,7 +181,7 @@ __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, in
     const int jb = t.task % g.col_blocks, kb = t.task / g.col_blocks;
     t.col0 = jb * 32 * C + lane;
     t.row_base = kb * R;
-    return true;
+    return t.task < g.tiles;  // the chunk fields are valid either way (all warps of a CTA share the chunk)
 }
 
 // Stage `padded` points starting at pts[n0] (lane-strided, coalesced float2 loads); entries at or
@@ -406,8 +407,9 @@ __global__ void __launch_bounds__(CTA_THREADS)
 bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
             int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
-            float* __restrict__ amax_out, float* __restrict__ ebg_out) {
+            float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
     TaskInfo t;
     if (!decode_task<R, C>(meta, batch, g, t)) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
@@ -545,17 +547,24 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
                  const float* __restrict__ amax_in, const float* __restrict__ ebg_in,
                  const float* __restrict__ zpart, float* __restrict__ rz_out, float* __restrict__ pbg_out,
                  int64_t total_rows, float* __restrict__ cpart) {
+    // The four warps of a CTA sweep the same point chunk over four pixel tiles; their per-point partial counts
+    // meet in shared memory and leave the CTA as ONE partial row (a quarter of the cpart traffic, and a quarter
+    // of what bl_reduce_counts_kernel has to read).  Warps past the last pixel tile contribute zeros.
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
+    __shared__ float cta_acc[WARPS_PER_CTA][COUNT_SPAN];
+    __shared__ float cta_bg[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return;
-    WarpTile<R>& tile = tiles[threadIdx.x >> 5];
+    const bool live = decode_task<R, C>(meta, batch, g, t);
+    const int warp = threadIdx.x >> 5;
+    WarpTile<R>& tile = tiles[warp];
     const int lane = threadIdx.x & 31;
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
     PixelTile<R, C> px;
     px.init(t, g);
-    float* part = cpart + (size_t)t.task * total_rows + t.row0;
+    float* part = cpart + (size_t)blockIdx.x * total_rows + t.row0;
     const bool first = t.chunk == t.first_chunk;
+    const bool bg_row = first && (use_bg || t.n_img_pts == 0);
 
     // per-pixel weights D[m]/Z[m]; pixels outside the grid get weight 0
     float neg_amax[R][C], wd[R][C], bg_part = 0.f;
@@ -565,7 +574,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
         for (int c = 0; c < C; ++c) {
             const int p = px.pix(r, c);
             const size_t m = img_base + p;
-            const bool ok = px.ok(r, c);
+            const bool ok = live && px.ok(r, c);
             const float d = ok ? density[m] : 0.f;
             const float ebg = ebg_in[m];
             const float rz = softmax_rz(zpart, M, t.first_chunk, t.n_chunks, p, ebg);
@@ -575,11 +584,12 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
             bg_part = fmaf(d, pbg, bg_part);
             if (first && ok) { rz_out[m] = rz; pbg_out[m] = pbg; }
         }
-    if (first && (use_bg || t.n_img_pts == 0)) {  // background row / sum-of-density row of an empty image
+    if (bg_row) {  // background row / sum-of-density row of an empty image
         bg_part = warp_sum(bg_part);
-        if (lane == 0) part[t.n_rows - 1] = bg_part;
+        if (lane == 0) cta_bg[warp] = bg_part;
     }
-    if (t.p_cnt == 0) return;
+    __syncthreads();
+    if (bg_row && threadIdx.x == 0) part[t.n_rows - 1] = ((cta_bg[0] + cta_bg[1]) + cta_bg[2]) + cta_bg[3];
 
     const float2* pts = pts_all + t.pt_base;
     part += t.p_start;
@@ -593,68 +603,76 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
             k2p[q][c] = pack2(neg_amax[2 * q][c], neg_amax[2 * q + 1][c]);
             wdp[q][c] = pack2(wd[2 * q][c], wd[2 * q + 1][c]);
         }
-    for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
-        const int cnt = min(TILE_PTS, t.p_cnt - n0);
-        int kept = cnt;
-        __syncwarp();
-        if (exact_cull) {
-            for (int i = lane; i < cnt; i += 32) tile.aux[i] = 0.f;  // culled points: partial count exactly 0
-            kept = stage_points_if<R, false, true>(tile, pts, nullptr, n0, cnt, px.cym2, px.cyy,
-                                                   [&](float x, float y, float) { return cull.keep(x, y); });
+    for (int span0 = 0; span0 < t.p_cnt; span0 += COUNT_SPAN) {
+        const int span_cnt = min(COUNT_SPAN, t.p_cnt - span0);
+        if (!live)
+            for (int i = lane; i < span_cnt; i += 32) cta_acc[warp][i] = 0.f;
+        for (int n0 = span0; live && n0 < span0 + span_cnt; n0 += TILE_PTS) {
+            const int cnt = min(TILE_PTS, t.p_cnt - n0);
+            float* acc_w = &cta_acc[warp][n0 - span0];
+            int kept = cnt;
             __syncwarp();
-            // pad the compacted list to a multiple of 8 with copies of its last point (results discarded)
-            for (int i = kept + lane; i < ((kept + 7) & ~7); i += 32) {
-                tile.xs[i] = tile.xs[kept - 1];
+            if (exact_cull) {
+                for (int i = lane; i < cnt; i += 32) acc_w[i] = 0.f;  // culled points: partial count exactly 0
+                kept = stage_points_if<R, false, true>(tile, pts, nullptr, n0, cnt, px.cym2, px.cyy,
+                                                       [&](float x, float y, float) { return cull.keep(x, y); });
+                __syncwarp();
+                // pad the compacted list to a multiple of 8 with copies of its last point (results discarded)
+                for (int i = kept + lane; i < ((kept + 7) & ~7); i += 32) {
+                    tile.xs[i] = tile.xs[kept - 1];
 #pragma unroll
-                for (int r = 0; r < R; ++r) tile.yd[i][r] = tile.yd[kept - 1][r];
+                    for (int r = 0; r < R; ++r) tile.yd[i][r] = tile.yd[kept - 1][r];
+                }
+            } else {
+                stage_points<R>(tile, pts, n0, t.p_cnt, (cnt + 7) & ~7, px.cym2, px.cyy);
             }
-        } else {
-            stage_points<R>(tile, pts, n0, t.p_cnt, (cnt + 7) & ~7, px.cym2, px.cyy);
-        }
-        const int padded = (kept + 7) & ~7;
-        __syncwarp();
+            const int padded = (kept + 7) & ~7;
+            __syncwarp();
 #pragma unroll 1
-        for (int i0 = 0; i0 < padded; i0 += 8) {
-            float v[8];
+            for (int i0 = 0; i0 < padded; i0 += 8) {
+                float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float2 xs = tile.xs[i0 + u];
-                f2 yd[R / 2];
-                load_yd2<R>(tile, i0 + u, yd);
-                f2 s2 = pack2(0.f, 0.f);  // even / odd rows accumulate side by side
+                for (int u = 0; u < 8; ++u) {
+                    const float2 xs = tile.xs[i0 + u];
+                    f2 yd[R / 2];
+                    load_yd2<R>(tile, i0 + u, yd);
+                    f2 s2 = pack2(0.f, 0.f);  // even / odd rows accumulate side by side
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
-                    const f2 xd2 = pack2(xd, xd);
+                    for (int c = 0; c < C; ++c) {
+                        const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+                        const f2 xd2 = pack2(xd, xd);
 #pragma unroll
-                    for (int q = 0; q < R / 2; ++q)
-                        s2 = fma2(pair_exp2<POW2>(add2(yd[q], xd2), k2p[q][c], k2s), wdp[q][c], s2);
+                        for (int q = 0; q < R / 2; ++q)
+                            s2 = fma2(pair_exp2<POW2>(add2(yd[q], xd2), k2p[q][c], k2s), wdp[q][c], s2);
+                    }
+                    float s_even, s_odd;
+                    unpack2(s2, s_even, s_odd);
+                    v[u] = s_even + s_odd;
                 }
-                float s_even, s_odd;
-                unpack2(s2, s_even, s_odd);
-                v[u] = s_even + s_odd;
-            }
-            // transpose-reduce: 8 per-lane partials -> lane quad q holds the warp total of point i0+q
+                // transpose-reduce: 8 per-lane partials -> lane quad q holds the warp total of point i0+q
 #pragma unroll
-            for (int h = 4, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
-                const bool up = (lane & bit) != 0;
+                for (int h = 4, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+                    const bool up = (lane & bit) != 0;
 #pragma unroll
-                for (int u = 0; u < h; ++u) {
-                    const float send = up ? v[u] : v[u + h];
-                    const float keep = up ? v[u + h] : v[u];
-                    v[u] = keep + __shfl_xor_sync(FULL_MASK, send, bit);
+                    for (int u = 0; u < h; ++u) {
+                        const float send = up ? v[u] : v[u + h];
+                        const float keep = up ? v[u + h] : v[u];
+                        v[u] = keep + __shfl_xor_sync(FULL_MASK, send, bit);
+                    }
                 }
-            }
-            v[0] += __shfl_xor_sync(FULL_MASK, v[0], 2);
-            v[0] += __shfl_xor_sync(FULL_MASK, v[0], 1);
-            if ((lane & 3) == 0) {
-                const int q = i0 + (lane >> 2);
-                if (!exact_cull) tile.aux[q] = v[0];
-                else if (q < kept) tile.aux[tile.idx[q]] = v[0];
+                v[0] += __shfl_xor_sync(FULL_MASK, v[0], 2);
+                v[0] += __shfl_xor_sync(FULL_MASK, v[0], 1);
+                if ((lane & 3) == 0) {
+                    const int q = i0 + (lane >> 2);
+                    if (!exact_cull) { if (q < cnt) acc_w[q] = v[0]; }
+                    else if (q < kept) acc_w[tile.idx[q]] = v[0];
+                }
             }
         }
-        __syncwarp();
-        for (int i = lane; i < cnt; i += 32) part[n0 + i] = tile.aux[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < span_cnt; i += CTA_THREADS)
+            part[span0 + i] = ((cta_acc[0][i] + cta_acc[1][i]) + cta_acc[2][i]) + cta_acc[3][i];
+        __syncthreads();
     }
 }
 
@@ -732,16 +750,28 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
                 if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned int rank = sh_rank, cum = 0u;
-                int b = 0;
-                for (; b < 255; ++b) {
-                    if (cum + hist[b] >= rank) break;
-                    cum += hist[b];
+            if (tid < 32) {  // first bin whose running count reaches the rank: 8 bins per lane + a warp scan
+                const unsigned int rank = sh_rank;
+                unsigned int h[8], mine = 0u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { h[u] = hist[8 * tid + u]; mine += h[u]; }
+                unsigned int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int up = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (tid >= o) incl += up;
                 }
-                sh_rank = rank - cum;
-                sh_prefix = prefix | ((unsigned)b << shift);
-                sh_equal = hist[b];
+                unsigned int cum = incl - mine;
+                if (cum < rank && rank <= incl) {  // exactly one lane (the matching elements number >= rank)
+                    int u = 0;
+                    for (; u < 7; ++u) {
+                        if (cum + h[u] >= rank) break;
+                        cum += h[u];
+                    }
+                    sh_rank = rank - cum;
+                    sh_prefix = prefix | ((unsigned)(8 * tid + u) << shift);
+                    sh_equal = h[u];
+                }
             }
             mask |= 255u << shift;
             __syncthreads();
@@ -993,7 +1023,8 @@ bl_posterior_kernel(const float2* __restrict__ pts_all, const int32_t* __restric
 __global__ void __launch_bounds__(256)
 bl_prob_counts_kernel(const float* __restrict__ prob, const float* __restrict__ density,
                       const int32_t* __restrict__ meta, int batch, int M, int64_t total_rows,
-                      float* __restrict__ cpart) {
+                      float* __restrict__ cpart, unsigned int* __restrict__ ticket) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= total_rows) return;
     const int lane = threadIdx.x & 31;
@@ -1051,11 +1082,6 @@ static long variant_tasks(const Variant& v, int total_chunks, int hp, int wp) {
 }
 
 static Variant pick_variant(int total_chunks, int hp, int wp) {
-    // tuning override for experiments (scripts/sweep_bl.sh): DGVCC_BL_VARIANT = index into kVariants
-    if (const char* e = getenv("DGVCC_BL_VARIANT")) {
-        const int i = atoi(e);
-        if (i >= 0 && i < 4) return kVariants[i];
-    }
     const long want = 148L * 16;
     for (const Variant& v : kVariants)
         if (variant_tasks(v, total_chunks, hp, wp) >= want) return v;
@@ -1086,12 +1112,13 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     L->counts = take(rows); L->wsel = take(rows); L->residual = take(rows);
     L->loss_img = take((size_t)batch * sizeof(float));
     L->ticket = take(sizeof(unsigned int));
-    L->cpart = take((size_t)tiles * rows);
+    const int count_rows = ceil_div(tiles, WARPS_PER_CTA);  // one partial row per CTA of bl_counts_kernel
+    L->cpart = take((size_t)count_rows * rows);
     L->zpart = take(chunk_pix);
     L->minpart = take(chunk_pix);
     L->gpart = L->minpart;  // minima are dead once the denominators exist; backward re-uses the region
     L->total = (int64_t)off;
-    L->tiles = tiles;
+    L->tiles = count_rows;
     L->rows_per_thread = v.rows;
     L->cols_per_thread = v.cols;
     return DGVCC_OK;
@@ -1173,7 +1200,8 @@ int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const floa
     }
     mark(events, 1, st);
     BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
-                exact_cull, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg));
+                exact_cull, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg),
+                at<unsigned int>(ws, p.L.ticket));
     mark(events, 2, st);
     return (int)cudaGetLastError();
 }
@@ -1198,6 +1226,7 @@ extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targe
                                          float sigma, float bg_ratio, int use_bg, int exact_cull, float inv_batch,
                                          void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
                                          void** events) {
+    DGVCC_DEVICE_GUARD(stream);
     Plan p;
     int rc = make_plan(meta, density, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
                        sigma, &p);
@@ -1221,6 +1250,7 @@ extern "C" int dgvcc_bl_forward(const float* pts_xy, const float* targets, const
                                 int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
                                 float bg_ratio, int use_bg, int exact_cull, float inv_batch, void* workspace,
                                 size_t workspace_bytes, float* loss_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     return dgvcc_bl_forward_profiled(pts_xy, targets, meta, st_sizes, density, batch, hp, wp, total_rows,
                                      total_chunks, multi_chunk, stride, sigma, bg_ratio, use_bg, exact_cull,
                                      inv_batch, workspace, workspace_bytes, loss_out, stream, nullptr);
@@ -1230,6 +1260,7 @@ extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int b
                                  int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
                                  int use_bg, int exact_cull, float inv_batch, const float* grad_loss,
                                  void* workspace, size_t workspace_bytes, float* grad_density, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     Plan p;
     int rc = make_plan(meta, grad_loss, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
                        sigma, &p);
@@ -1255,6 +1286,7 @@ extern "C" int dgvcc_bl_posterior(const float* pts_xy, const int32_t* meta, cons
                                   int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,
                                   float stride, float sigma, float bg_ratio, int use_bg, void* workspace,
                                   size_t workspace_bytes, float* prob_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     Plan p;
     int rc = make_plan(meta, st_sizes, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride,
                        sigma, &p);
@@ -1276,6 +1308,7 @@ extern "C" int dgvcc_bl_bayloss_forward(const float* prob, const float* targets,
                                         const float* density, int batch, int hp, int wp, int64_t total_rows,
                                         float inv_batch, void* workspace, size_t workspace_bytes,
                                         float* loss_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!prob || !targets || !meta || !density || !workspace || !loss_out) return DGVCC_ERR_ARG;
     dgvcc_bl_layout L;
     int rc;
@@ -1284,7 +1317,8 @@ extern "C" int dgvcc_bl_bayloss_forward(const float* prob, const float* targets,
     cudaStream_t st = (cudaStream_t)stream;
     const int M = hp * wp;
     bl_prob_counts_kernel<<<(unsigned)((total_rows + 7) / 8), 256, 0, st>>>(prob, density, meta, batch, M, total_rows,
-                                                                            at<float>(workspace, L.cpart));
+                                                                            at<float>(workspace, L.cpart),
+                                                                            at<unsigned int>(workspace, L.ticket));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     return launch_select(L, targets, meta, batch, total_rows, inv_batch, /*tiles=*/1, workspace, loss_out, st);
 }
@@ -1293,6 +1327,7 @@ extern "C" int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta,
                                          int64_t total_rows, float inv_batch, const float* grad_loss,
                                          const void* workspace, size_t workspace_bytes, float* grad_density,
                                          void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!prob || !meta || !grad_loss || !workspace || !grad_density) return DGVCC_ERR_ARG;
     dgvcc_bl_layout L;
     int rc;

@@ -16,6 +16,36 @@
 
 namespace dgvcc {
 
+// Every launcher runs on the device that owns the caller's stream, whatever the calling thread's current
+// device is (the reference's configs pass device='cuda:1' etc. without ever calling set_device); the
+// previous current device is restored on return.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(void* stream) {
+        int cur = 0, want = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) return;
+        if (cudaStreamGetDevice((cudaStream_t)stream, &want) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        if (want != cur && cudaSetDevice(want) == cudaSuccess) prev = cur;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DGVCC_DEVICE_GUARD(stream) ::dgvcc::DeviceGuard dgvcc_device_guard_(stream)
+
+// Function attributes (opt-in dynamic shared memory) are per device: `static PerDeviceOnce once;`
+// `if (once.first()) cudaFuncSetAttribute(...)` configures a kernel the first time each device launches it.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;  // a race only repeats the same idempotent call
+        return true;
+    }
+};
+
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr float LOG2E = 1.4426950408889634f;
 

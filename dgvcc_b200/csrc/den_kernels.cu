@@ -65,6 +65,7 @@ using namespace dgvcc::den;
 
 extern "C" int dgvcc_den_train_targets(const float* maps, const int64_t* meta, int batch, int crop_h, int crop_w,
                                        int downsample, float* out_dmap, float* out_bmap, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!maps || !meta || !out_dmap || batch <= 0 || crop_h <= 0 || crop_w <= 0 || downsample <= 0) return DGVCC_ERR_ARG;
     // the reference's reshape needs exact divisibility (den_cls_dataset.py:138, :60)
     if (crop_h % downsample || crop_w % downsample) return DGVCC_ERR_ARG;

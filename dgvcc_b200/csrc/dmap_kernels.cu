@@ -933,6 +933,7 @@ extern "C" size_t dgvcc_dmap_knn_workspace_bytes(int n) {
 
 extern "C" int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx, double* nn_dist, double* sigma,
                                     void* workspace, size_t workspace_bytes, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (n < 0) return DGVCC_ERR_ARG;
     if (n == 0) return DGVCC_OK;
     if (!pts_xy || !nn_idx || !nn_dist || !sigma || !workspace) return DGVCC_ERR_ARG;
@@ -1015,6 +1016,7 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
 extern "C" int dgvcc_dmap_knn_sigma_batch(const double* pts_xy, int n_images, const int64_t* meta,
                                           const dgvcc_dmap_plan* plan, int32_t* nn_idx, double* nn_dist, double* sigma,
                                           void* workspace, size_t workspace_bytes, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (n_images <= 0 || !meta || !plan) return DGVCC_ERR_ARG;
     if (plan->total_heads == 0) return DGVCC_OK;
     if (!pts_xy || !sigma || !workspace) return DGVCC_ERR_ARG;
@@ -1045,6 +1047,7 @@ extern "C" int dgvcc_dmap_knn_sigma_batch(const double* pts_xy, int n_images, co
 extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma, double fixed_sigma, double truncate,
                                       int n_images, const int64_t* meta, const dgvcc_dmap_plan* plan, void* workspace,
                                       size_t workspace_bytes, float* density, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (n_images <= 0 || !meta || !plan || !density || !workspace) return DGVCC_ERR_ARG;
     if (plan->total_heads > 0 && !pts_xy) return DGVCC_ERR_ARG;
     if (workspace_bytes < (size_t)plan->splat_workspace_bytes) return DGVCC_ERR_WORKSPACE;

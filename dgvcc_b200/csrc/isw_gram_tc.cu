@@ -263,6 +263,7 @@ using namespace dgvcc::isw_tc;
 
 extern "C" int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int hw, int splits, int k_per_split,
                                           float* part, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !part || batch <= 0 || c <= 0 || hw <= 0 || splits <= 0 || k_per_split <= 0) return DGVCC_ERR_ARG;
     // TMA needs 16-byte global strides and a 16-byte aligned base; rows past C are zero-filled by the
     // tensor map, so any C works, but tiny channel counts waste the 128-wide tile
@@ -274,11 +275,9 @@ extern "C" int dgvcc_isw_gram_tc_partials(const float* x, int batch, int c, int 
                           pair ? 2 : 1))
         return DGVCC_ERR_UNSUPPORTED;
 
-    static bool attr_set = false;  // idempotent; a race only repeats the same call
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.first())
         DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
     Args a;
     a.c = c; a.hw = hw; a.batch = batch; a.splits = splits; a.k_per_split = k_per_split;
     a.pair = pair;

@@ -567,6 +567,7 @@ using namespace dgvcc::isw;
 
 extern "C" int dgvcc_isw_instnorm_forward(const float* x, int planes, int hw, float eps, float* y, float* mean,
                                           float* invstd, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !y || !mean || !invstd || planes <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     const size_t smem = (size_t)hw * sizeof(float);
     const bool fits = smem <= 200 * 1024;
@@ -582,6 +583,7 @@ extern "C" int dgvcc_isw_instnorm_forward(const float* x, int planes, int hw, fl
 
 extern "C" int dgvcc_isw_instnorm_backward(const float* dy, const float* y, const float* invstd, int planes, int hw,
                                            float* dx, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!dy || !y || !invstd || !dx || planes <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     isw_instnorm_bwd_kernel<<<planes, NORM_THREADS, 0, (cudaStream_t)stream>>>(dy, y, invstd, hw, dx);
     return (int)cudaGetLastError();
@@ -677,6 +679,7 @@ static int launch_gram(const float* f_map, const float* eye, float denom, float 
 
 extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int batch, int c, int hw, int use_tensor_cores,
                                     void* workspace, size_t workspace_bytes, float* f_cor, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!f_map || !eye || !workspace || !f_cor || batch <= 0 || c <= 0 || hw <= 1) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -686,6 +689,7 @@ extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int ba
 extern "C" int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, const float* margin,
                                       const float* num_remove_cov, int batch, int c, int hw, void* workspace,
                                       size_t workspace_bytes, float* loss_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!f_cor || !mask || !margin || !num_remove_cov || !workspace || !loss_out) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -723,6 +727,7 @@ extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, c
                                        const float* num_remove_cov, const float* grad_loss, int batch, int c, int hw,
                                        int use_tensor_cores, int mask_is_binary, void* workspace,
                                        size_t workspace_bytes, float* grad_f_map, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -744,6 +749,7 @@ extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, c
 extern "C" int dgvcc_isw_covariance_backward(const float* f_map, const float* grad_f_cor, int batch, int c, int hw,
                                              int use_tensor_cores, void* workspace, size_t workspace_bytes,
                                              float* grad_f_map, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!f_map || !grad_f_cor || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -755,6 +761,7 @@ extern "C" int dgvcc_isw_covariance_backward(const float* f_map, const float* gr
 
 extern "C" int dgvcc_isw_covstat_var(const float* f_cor, const float* reverse_eye, int batch, int c, float* var_out,
                                      void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!f_cor || !reverse_eye || !var_out || batch <= 0 || c <= 0) return DGVCC_ERR_ARG;
     isw_covstat_var_kernel<<<ceil_div(c * c, 256), 256, 0, (cudaStream_t)stream>>>(f_cor, reverse_eye, batch, c * c, var_out);
     return (int)cudaGetLastError();
@@ -762,6 +769,7 @@ extern "C" int dgvcc_isw_covstat_var(const float* f_cor, const float* reverse_ey
 
 extern "C" int dgvcc_isw_topk_mask(const float* stats, int n_stats, int count, int n, int k, const float* prev_mask,
                                    float* values, float* mask, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!stats || !values || !mask || n_stats <= 0 || count <= 0 || n <= 0 || k < 0) return DGVCC_ERR_ARG;
     isw_topk_mask_kernel<<<1, TOPK_THREADS, 0, (cudaStream_t)stream>>>(stats, n_stats, (float)count, n, k, prev_mask,
                                                                        values, mask);
@@ -771,6 +779,7 @@ extern "C" int dgvcc_isw_topk_mask(const float* stats, int n_stats, int count, i
 // ------------------------------------------------------------------ auxiliary Gram losses: entry points
 extern "C" int dgvcc_lw_standardize_forward(const float* x, const float* mask, int batch, int c, int hw, float eps,
                                             float* yhat, float* y_masked, float* invstd, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !yhat || !invstd || batch <= 0 || c <= 0 || hw <= 0 || (mask && !y_masked)) return DGVCC_ERR_ARG;
     lw_standardize_fwd_kernel<<<batch * c, NORM_THREADS, 0, (cudaStream_t)stream>>>(x, mask, c, hw, eps, yhat, y_masked, invstd);
     return (int)cudaGetLastError();
@@ -778,6 +787,7 @@ extern "C" int dgvcc_lw_standardize_forward(const float* x, const float* mask, i
 
 extern "C" int dgvcc_lw_standardize_backward(const float* dy, const float* yhat, const float* invstd, const float* mask,
                                              int batch, int c, int hw, float* dx, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!dy || !yhat || !invstd || !dx || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     lw_standardize_bwd_kernel<<<batch * c, NORM_THREADS, 0, (cudaStream_t)stream>>>(dy, yhat, invstd, mask, c, hw, dx);
     return (int)cudaGetLastError();
@@ -785,6 +795,7 @@ extern "C" int dgvcc_lw_standardize_backward(const float* dy, const float* yhat,
 
 extern "C" int dgvcc_isw_gram(const float* f_map, int batch, int c, int hw, int use_tensor_cores, void* workspace,
                               size_t workspace_bytes, float* gram, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!f_map || !workspace || !gram || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -802,6 +813,7 @@ static int launch_triu_sq(const float* g, int c, int ld, int col0, size_t sample
 
 extern "C" int dgvcc_lw_loss_forward(const float* gram, int batch, int c, int hw, void* workspace, size_t workspace_bytes,
                                      float* loss_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!gram || !workspace || !loss_out || batch <= 0 || c <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -811,6 +823,7 @@ extern "C" int dgvcc_lw_loss_forward(const float* gram, int batch, int c, int hw
 extern "C" int dgvcc_lw_loss_backward(const float* y, const float* gram, const float* grad_loss, int batch, int c, int hw,
                                       int use_tensor_cores, void* workspace, size_t workspace_bytes, float* grad_y,
                                       void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!y || !gram || !grad_loss || !workspace || !grad_y || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
@@ -823,6 +836,7 @@ extern "C" int dgvcc_lw_loss_backward(const float* y, const float* gram, const f
 // z = [x; y] stacked [2c, p]; gram_zz [2c, 2c] = z z^T from dgvcc_isw_gram(z, 1, 2c, p, ...).
 extern "C" int dgvcc_ortho_loss_forward(const float* gram_zz, int c, int p, void* workspace, size_t workspace_bytes,
                                         float* loss_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!gram_zz || !workspace || !loss_out || c <= 0 || p <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(1, 2 * c, p)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, 1, 2 * c, p);
@@ -832,6 +846,7 @@ extern "C" int dgvcc_ortho_loss_forward(const float* gram_zz, int c, int p, void
 extern "C" int dgvcc_ortho_loss_backward(const float* x, const float* y, const float* gram_zz, const float* grad_loss, int c,
                                          int p, int use_tensor_cores, void* workspace, size_t workspace_bytes,
                                          float* grad_x, float* grad_y, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !y || !gram_zz || !grad_loss || !workspace || !grad_x || !grad_y || c <= 0 || p <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(1, 2 * c, p)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, 1, 2 * c, p);  // S region holds (2c)^2 floats: Sx and Sy fit

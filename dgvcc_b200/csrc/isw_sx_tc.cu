@@ -215,13 +215,12 @@ int dgvcc::isw_sx::launch(const float* s, const float* x, int batch, int c, int 
     if (!make_tmap_f32_3d(&map_s, s, (uint64_t)c, (uint64_t)c, (uint64_t)batch, TILE)) return DGVCC_ERR_UNSUPPORTED;
     if (!make_tmap_f32_3d(&map_x, x, (uint64_t)hw, (uint64_t)c, (uint64_t)batch, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
         return DGVCC_ERR_UNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_sx_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   Cfg<false>::SMEM_BYTES));
         DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_sx_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   Cfg<true>::SMEM_BYTES));
-        attr_set = true;
     }
     Args a;
     a.c = c; a.hw = hw; a.dx = dx; a.scale = scale;
@@ -234,5 +233,6 @@ int dgvcc::isw_sx::launch(const float* s, const float* x, int batch, int c, int 
 }
 
 extern "C" int dgvcc_isw_sx_tc(const float* s, const float* x, int batch, int c, int hw, float* dx, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     return dgvcc::isw_sx::launch(s, x, batch, c, hw, dx, nullptr, false, stream);
 }

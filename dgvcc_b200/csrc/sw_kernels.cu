@@ -810,6 +810,7 @@ extern "C" size_t dgvcc_sw_workspace_bytes(int n, int channels, int hw, int num_
 
 extern "C" int dgvcc_sw_instance_stats(const float* x, int n, int channels, int hw, int num_pergroup, double* mean_in,
                                        double* cov_in, void* workspace, size_t workspace_bytes, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !mean_in || !cov_in || !workspace || bad_shape(n, channels, hw, num_pergroup)) return DGVCC_ERR_ARG;
     const BwdLayout l = layout(n, channels, hw, num_pergroup);
     if (workspace_bytes < l.total) return DGVCC_ERR_WORKSPACE;
@@ -827,6 +828,7 @@ extern "C" int dgvcc_sw_instance_stats(const float* x, int n, int channels, int 
 }
 
 extern "C" int dgvcc_sw_batch_mean(const double* mean_in, int n, int channels, double* mean_bn, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!mean_in || !mean_bn || n <= 0 || channels <= 0) return DGVCC_ERR_ARG;
     sw_batch_mean_kernel<<<ceil_div(channels, 128), 128, 0, (cudaStream_t)stream>>>(mean_in, n, channels, mean_bn);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
@@ -835,6 +837,7 @@ extern "C" int dgvcc_sw_batch_mean(const double* mean_in, int n, int channels, d
 
 extern "C" int dgvcc_sw_batch_cov(const double* mean_in, const double* cov_in, const double* mean_bn, int n, int channels,
                                   int num_pergroup, double* cov_bn, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!mean_in || !cov_in || !mean_bn || !cov_bn || bad_shape(n, channels, 1, num_pergroup)) return DGVCC_ERR_ARG;
     sw_batch_cov_kernel<<<channels / num_pergroup, MAT_THREADS, 0, (cudaStream_t)stream>>>(mean_in, cov_in, mean_bn, n,
                                                                                          channels, num_pergroup, cov_bn);
@@ -845,6 +848,7 @@ extern "C" int dgvcc_sw_batch_cov(const double* mean_in, const double* cov_in, c
 extern "C" int dgvcc_sw_update_running(float* running_mean, float* running_cov, const double* mean_bn,
                                        const double* cov_bn, int channels, int num_pergroup, double momentum,
                                        double one_minus_momentum, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!running_mean || !running_cov || !mean_bn || !cov_bn || bad_shape(1, channels, 1, num_pergroup)) return DGVCC_ERR_ARG;
     const int cov_elems = channels * num_pergroup;
     sw_update_running_kernel<<<ceil_div(cov_elems, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -858,6 +862,7 @@ extern "C" int dgvcc_sw_whiten_forward(const float* x, const double* mean_in, co
                                        const float* weight, const float* bias, int n, int channels, int hw,
                                        int num_pergroup, int sw_type, int T, float eps, float* a_fwd, float* y,
                                        void* workspace, size_t workspace_bytes, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !mean_in || !cov_in || !mean_bn || !cov_bn || !sw_mean_weight || !a_fwd || !y || !workspace ||
         (weight == nullptr) != (bias == nullptr) || bad_shape(n, channels, hw, num_pergroup) || bad_mix(sw_type, T))
         return DGVCC_ERR_ARG;
@@ -882,6 +887,7 @@ extern "C" int dgvcc_sw_backward_stats(const float* x, const float* grad_y, cons
                                        int num_pergroup, int sw_type, int T, float eps, float* grad_sw_mean,
                                        float* grad_sw_var, float* grad_weight, float* grad_bias, double* grad_mean_bn,
                                        double* grad_cov_bn, void* workspace, size_t workspace_bytes, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !grad_y || !mean_in || !cov_in || !mean_bn || !cov_bn || !sw_mean_weight || !grad_sw_mean || !grad_mean_bn ||
         !grad_cov_bn || !workspace || (sw_var_weight == nullptr) != (grad_sw_var == nullptr) ||
         bad_shape(n, channels, hw, num_pergroup) || bad_mix(sw_type, T))
@@ -916,6 +922,7 @@ extern "C" int dgvcc_sw_backward_apply(const float* x, const float* grad_y, cons
                                        const float* sw_mean_weight, const float* sw_var_weight, double bn_scale, int n,
                                        int channels, int hw, int num_pergroup, int sw_type, float* grad_x,
                                        void* workspace, size_t workspace_bytes, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
     if (!x || !grad_y || !a_fwd || !mean_in || !mean_bn || !grad_mean_bn || !grad_cov_bn || !sw_mean_weight || !grad_x ||
         !workspace || bad_shape(n, channels, hw, num_pergroup) || bad_mix(sw_type, 1))
         return DGVCC_ERR_ARG;

@@ -49,7 +49,7 @@ class CovMatrix_ISW:
         self.reversal_i = torch.ones(dim, dim, device=dev).triu(diagonal=1)
         self.num_off_diagonal = torch.sum(self.reversal_i)
         self.num_sensitive = 0
-        self.var_matrix = None          # list of the statistics handed in since the last set_mask_matrix
+        self.var_matrix = None          # running fp32 sum of the statistics since the last set_mask_matrix
         self.count_var_cov = 0
         self.mask_matrix = None
         self.clusters = clusters
@@ -70,7 +70,7 @@ class CovMatrix_ISW:
         self.mask_matrix = None
 
     def set_mask_matrix(self):
-        stats = torch.stack([v.reshape(-1).to(torch.float32) for v in self.var_matrix])
+        stats = self.var_matrix.reshape(1, -1)  # the sum; the kernel divides by count (cov_settings.py:53)
         if self.margin == 0:    # cov_settings.py:57-61
             import kmeans1d  # third-party, like the reference; not part of this package
             var_flatten = stats.sum(0) / self.count_var_cov
@@ -85,9 +85,10 @@ class CovMatrix_ISW:
         self.count_var_cov = 0
 
     def set_variance_of_covariance(self, var_cov):
-        if self.var_matrix is None:
-            self.var_matrix = []
-        self.var_matrix.append(var_cov.detach())
+        # one running sum like cov_settings.py:84-88 (same fp32 summation order), not a list that grows with every
+        # validation patch
+        var_cov = var_cov.detach().to(torch.float32)
+        self.var_matrix = var_cov.clone() if self.var_matrix is None else self.var_matrix + var_cov
         self.count_var_cov += 1
 
 

@@ -33,7 +33,7 @@ class _SwitchWhitenFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, sw_mean_weight, sw_var_weight, weight, bias, running_mean, running_cov, cfg):
         _native.require_cuda(x, "SwitchWhiten2d")
-        cper, sw_type, T, eps, momentum, training, exchange = cfg
+        cper, sw_type, T, eps, momentum, training, exchange, sync = cfg
         n, ch, h, w = x.shape
         hw, groups, dev = h * w, ch // cper, x.device
         lib, stream = _native.lib(), _native.stream_ptr(dev)
@@ -83,7 +83,7 @@ class _SwitchWhitenFn(torch.autograd.Function):
                       "dgvcc_sw_whiten_forward")
         ctx.save_for_backward(xc, mean_in, cov_in, mean_bn, cov_bn, mw, vw, wt, a_fwd)
         if not training:
-            bn_scale = 0.0 if exchange is None else 1.0 / (n * hw)   # sync_switchwhiten.py:48-55, see the C header
+            bn_scale = 1.0 / (n * hw) if sync else 0.0   # sync_switchwhiten.py:48-55, see the C header
         else:
             bn_scale = 1.0 / (n * hw * world)
         ctx.cfg = (cper, sw_type, T, eps, training, exchange, bn_scale, x.dtype, nbytes)
@@ -129,6 +129,7 @@ class SwitchWhiten2d(nn.Module):
     """Switchable whitening (BW + IW [+ LN [+ BN + IN]]); constructor and state of switchwhiten.py:7-77."""
 
     _sw_types = (2, 3, 5)
+    _sync = False
 
     def __init__(self, num_features, num_pergroup=16, sw_type=2, T=5, tie_weight=False, eps=1e-5, momentum=0.99,
                  affine=True):
@@ -176,6 +177,6 @@ class SwitchWhiten2d(nn.Module):
         if self.sw_type not in (2, 3, 5):
             # the synchronised reference class accepts sw_type 4 but has no branch for it (sync_switchwhiten.py:176-195)
             raise RuntimeError(f"sw_type={self.sw_type} has no forward in the reference either")
-        cfg = (self.num_pergroup, self.sw_type, self.T, self.eps, self.momentum, self.training, self._exchange())
+        cfg = (self.num_pergroup, self.sw_type, self.T, self.eps, self.momentum, self.training, self._exchange(), self._sync)
         return _SwitchWhitenFn.apply(x, self.sw_mean_weight, self.sw_var_weight, self.weight, self.bias, self.running_mean,
                                      self.running_cov, cfg)

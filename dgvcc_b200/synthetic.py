@@ -77,3 +77,20 @@ def config_counts(config, batch=None):
 
 
 CONFIG_SHAPES = {1: (1024, 768), 2: (1024, 1024), 3: (2048, 1536)}  # (W, H) image pixels
+
+
+def config4_images(n_images=64, seed=4000):
+    """BASELINE config 4: ``n_images`` JHU-Crowd-shaped images as ((H, W), points [N,2]) -- sides U{512..2048}
+    (utils/preprocess_data.py:536-539 bounds), head counts exp(U[ln 1, ln 25000]) plus one empty and one 3-head image,
+    float64 points (the JHU path, preprocess_data.py:54-55) with every eighth image float32 (the QNRF path, :70)."""
+    rng = np.random.default_rng(seed)
+    images = []
+    for i in range(n_images):
+        h, w = int(rng.integers(512, 2049)), int(rng.integers(512, 2049))
+        n = 0 if i == 0 else 3 if i == 1 else log_uniform_count(rng, 1, 25000)
+        dtype = np.float32 if i % 8 == 7 else np.float64
+        images.append(((h, w), crowd_points(np.random.default_rng(seed + i), n, w, h, dtype=dtype)))
+    return images
+
+
+CONFIG5_SHAPES = [(8, 64, 160, 160), (8, 256, 80, 80), (8, 512, 40, 40)]  # (B, C, H, W) of the three whitened layers

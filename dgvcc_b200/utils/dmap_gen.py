@@ -37,6 +37,21 @@ def _device(device):
     return torch.device(device if device is not None else "cuda")
 
 
+def _pinned(shape, dtype):
+    """Page-locked host tensor from torch's caching host allocator: after the first call of a given size this is a
+    free-list pop (no cudaHostAlloc, which costs milliseconds), and a block is only handed out again once every
+    copy that used it has completed.  Results returned to the caller are numpy views of such tensors -- the view keeps
+    the block alive, dropping it returns the block to the cache -- so no staging copy follows the device-to-host copy."""
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def _to_device(array, dev):
+    """Host numpy array -> device tensor through a pinned staging block, asynchronous on the current stream."""
+    host = _pinned(array.shape, torch.from_numpy(array[:0] if array.ndim else array).dtype)
+    host.numpy()[...] = array
+    return host.to(dev, non_blocking=True)
+
+
 def _check_points(points, height, width):
     pts = np.ascontiguousarray(np.asarray(points), dtype=np.float64)  # KDTree(points.copy()) works in float64
     if pts.ndim != 2 or pts.shape[1] != 2:
@@ -54,7 +69,7 @@ def knn_sigma(points, device=None):
     n = len(pts)
     if n == 0:
         return np.zeros((0, 4)), np.zeros((0, 4), dtype=np.int64), np.zeros((0,))
-    d_pts = torch.from_numpy(pts).pin_memory().to(dev, non_blocking=True)
+    d_pts = _to_device(pts, dev)
     idx = torch.empty((n, 4), dtype=torch.int32, device=dev)
     dist = torch.empty((n, 4), dtype=torch.float64, device=dev)
     sigma = torch.empty((n,), dtype=torch.float64, device=dev)
@@ -95,13 +110,14 @@ def _density_batch_device(shapes, pts_list, adaptive, dev):
     plan = _Plan([shapes[i] for i in order], counts[order])
     pl = plan.plan
     stream = _native.stream_ptr(dev)
-    meta = torch.from_numpy(plan.meta).pin_memory().to(dev, non_blocking=True)
+    meta = _to_device(plan.meta, dev)
     out = torch.empty((pl.total_pixels,), dtype=torch.float32, device=dev)
     ws = torch.empty((pl.splat_workspace_bytes,), dtype=torch.uint8, device=dev)
     d_pts = sigma = None
     if pl.total_heads:
-        packed = np.concatenate([pts_list[i] for i in order if counts[i]], axis=0)
-        d_pts = torch.from_numpy(np.ascontiguousarray(packed)).pin_memory().to(dev, non_blocking=True)
+        host_pts = _pinned((int(pl.total_heads), 2), torch.float64)
+        np.concatenate([pts_list[i] for i in order if counts[i]], axis=0, out=host_pts.numpy())
+        d_pts = host_pts.to(dev, non_blocking=True)
         if adaptive:
             sigma = torch.empty((pl.total_heads,), dtype=torch.float64, device=dev)
             kws = torch.empty((pl.knn_workspace_bytes,), dtype=torch.uint8, device=dev)
@@ -130,10 +146,10 @@ def _density(img, points, adaptive, device=None):
         return np.zeros((height, width), dtype=np.float32)
     dev = _device(device)
     pts = _check_points(points, height, width)
-    host = torch.empty((height, width), dtype=torch.float32).pin_memory()
+    host = _pinned((height, width), torch.float32)
     host.copy_(_density_device(height, width, pts, adaptive, dev), non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
-    return host.numpy().copy()
+    return host.numpy()
 
 
 def gaussian_filter_density(img, points, device=None):
@@ -155,7 +171,7 @@ def gaussian_filter_density_batch(shapes, points_list, fixed=False, device=None)
         return []
     pts = [_check_points(p, h, w) if len(p) else np.zeros((0, 2)) for (h, w), p in zip(shapes, points_list)]
     out, offsets = _density_batch_device(shapes, pts, not fixed, dev)
-    host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+    host = _pinned(out.shape, torch.float32)
     host.copy_(out, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
     flat = host.numpy()

@@ -82,12 +82,12 @@ typedef struct dgvcc_bl_layout {
     int64_t residual;  /* [rows]    f32  |t - c|                                     */
     int64_t loss_img;  /* [B]       f32  per-image trimmed L1                        */
     int64_t ticket;    /* [1]       u32  must be zero on entry (memset once)         */
-    int64_t cpart;     /* [tiles*rows] f32 per-pixel-tile partial counts             */
+    int64_t cpart;     /* [tiles*rows] f32 partial counts, one row per CTA of the sweep */
     int64_t zpart;     /* [C*hp*wp] f32  per-chunk share of the softmax denominator  */
     int64_t minpart;   /* [C*hp*wp] f32  per-chunk min squared distance              */
     int64_t gpart;     /* [C*hp*wp] f32  per-chunk gradient sums (aliases minpart)   */
     int64_t total;     /* bytes needed                                               */
-    int32_t tiles;     /* pixel tiles per image                                      */
+    int32_t tiles;     /* partial-count rows (CTAs of 4 pixel tiles) per point chunk */
     int32_t rows_per_thread; /* kernel variant chosen for this shape: grid rows ...   */
     int32_t cols_per_thread; /* ... and columns owned by one thread                  */
     int32_t reserved_;
@@ -302,6 +302,10 @@ int dgvcc_bay_crop_targets(const void* gt_xy, const void* dists, int n, int is_d
  * ------------------------------------------------------------------------- */
 int dgvcc_probe_ex2(float* sink, int iters, int64_t* ops_out, void* stream);
 int dgvcc_probe_ffma(float* sink, int iters, int64_t* ops_out, void* stream);
+/* Tensor-pipe probe: every SM issues `iters` x 4 back-to-back tcgen05.mma.kind::tf32 (M=128, N=256, K=8, operands
+ * in shared memory, accumulators in TMEM); *flops_out = TF32 flops executed.  The Gram's roofline denominator
+ * ("Tensor peak for TF32 must also be measured on the box"). */
+int dgvcc_probe_tf32(float* sink, int iters, int64_t* flops_out, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Auxiliary Gram-type losses -- replace losses/lw.py:5-18 (lw_loss) and

@@ -23,6 +23,23 @@ authoring container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).
 ``tests/test_oracle_*.py`` check every restatement against those fixtures.
 """
 
+CHECKER_THREADS = 8   # the thread count tests/golden/make_golden.py ran the unmodified reference with
+
+
+def pin_threads():
+    """Make the CPU checker's arithmetic a function of its inputs only.
+
+    torch's CPU reductions and GEMMs split their work by the size of the intra-op thread pool, so the last bits of
+    a reference value depend on the thread count (an 8-thread and a 1-thread evaluation of losses/ortho.py differ in
+    the last bit; the bit-exact fixture pins in tests/test_oracle_*.py were produced with 8 threads).  Checkers
+    (tests/conftest.py, __graft_entry__.smoke) therefore fix the pool at CHECKER_THREADS before they take any
+    reference value, whatever the host offers.  ``scripts/oracle_repro.py`` measures, on the GPU box's host, how many
+    distinct results fresh processes produce with the default pool, with 8 threads and with 1."""
+    import torch
+    if torch.get_num_threads() != CHECKER_THREADS:
+        torch.set_num_threads(CHECKER_THREADS)
+
+
 _warm = False
 
 
@@ -37,6 +54,7 @@ def warm_up():
     global _warm
     if _warm:
         return
+    pin_threads()
     import numpy as np
     import torch
     from . import bl_oracle

@@ -25,18 +25,39 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def config4_images():
-    rng = np.random.default_rng(4000)
-    images = []
-    for i in range(64):
-        h, w = int(rng.integers(512, 2049)), int(rng.integers(512, 2049))
-        n = 0 if i == 0 else 3 if i == 1 else synthetic.log_uniform_count(rng, 1, 25000)
-        dtype = np.float32 if i % 8 == 7 else np.float64
-        images.append(((h, w), synthetic.crowd_points(np.random.default_rng(4000 + i), n, w, h, dtype=dtype)))
-    return images
+config4_images = synthetic.config4_images
 
 
-def bench_dmap(cpu):
+def probe_tf32_peak(device=None, iters=20000):
+    """TF32 flop/s of the tensor pipe (tcgen05.mma.kind::tf32 issued back to back on every SM), best of 3."""
+    import ctypes
+    d = device or dev
+    lib = _native.lib()
+    sink = torch.zeros(4, device=d)
+    flops = ctypes.c_int64(0)
+    best = 0.0
+    for rep in range(4):
+        e0, e1 = ev(), ev()
+        e0.record()
+        _native.check(lib.dgvcc_probe_tf32(_native.ptr(sink), iters, ctypes.byref(flops), _native.stream_ptr(d)), "dgvcc_probe_tf32")
+        e1.record()
+        torch.cuda.synchronize(d)
+        if rep:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3))
+    return best
+
+
+def _reference_module(name):
+    """The unmodified reference file from oracle/_ref (oracle/make_ref.sh) or None when it did not travel."""
+    try:
+        from oracle import ref_loader
+        return ref_loader.load(name) if ref_loader.available(name) else None
+    except Exception:
+        return None
+
+
+def dmap_lines(cpu, cpu_seconds=10.0):
+    """BASELINE config 4 (64 JHU-shaped images): {splat_adaptive, splat_fixed} lines with roofline / e2e / cpu_baseline."""
     import ctypes
     from dgvcc_b200.utils import dmap_gen
     lib = _native.lib()
@@ -55,9 +76,10 @@ def bench_dmap(cpu):
     bytes_alg = 4 * int(pl.total_pixels) + 16 * int(pl.total_heads)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     st = _native.stream_ptr(dev)
+    lines = {}
     for adaptive in (True, False):
         t_dev, t_splat = [], []
-        for rep in range(6):  # the whole set is ONE batched launch set (inputs resident, L2 flushed before each)
+        for rep in range(8):  # the whole set is ONE batched launch set (inputs resident, L2 flushed before each)
             flush.zero_()
             e0, e1, e2 = ev(), ev(), ev()
             e0.record()
@@ -71,107 +93,181 @@ def bench_dmap(cpu):
                                                      _native.ptr(ws), pl.splat_workspace_bytes, _native.ptr(out), st), "splat")
             e2.record()
             torch.cuda.synchronize()
-            if rep >= 2:
+            if rep >= 3:
                 t_dev.append(e0.elapsed_time(e2))
                 t_splat.append(e1.elapsed_time(e2))
         t_dev, t_splat = float(np.mean(t_dev)), float(np.mean(t_splat))
-        # end to end through the public API: host numpy in, host numpy out
+        # end to end through the public API: host numpy in, host numpy out (H2D of heads + plan, D2H of the maps inside)
         fn = dmap_gen.gaussian_filter_density if adaptive else dmap_gen.gaussian_filter_density_fixed
+        for (h, w), pts in images[:8]:
+            fn(np.empty((h, w, 0)), pts)  # warm the pinned-block cache
         t0 = time.perf_counter()
         for (h, w), pts in images:
             fn(np.empty((h, w, 0)), pts)
         e2e_s = time.perf_counter() - t0
-        dmap_gen.gaussian_filter_density_batch(shapes, [p for _, p in images], fixed=not adaptive)  # warm the pinned pool
-        t0 = time.perf_counter()
-        dmap_gen.gaussian_filter_density_batch(shapes, [p for _, p in images], fixed=not adaptive)
-        e2e_batch_s = time.perf_counter() - t0
+        pts_in = [p for _, p in images]
+        for _ in range(2):
+            maps = dmap_gen.gaussian_filter_density_batch(shapes, pts_in, fixed=not adaptive)
+            del maps
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            maps = dmap_gen.gaussian_filter_density_batch(shapes, pts_in, fixed=not adaptive)
+            times.append(time.perf_counter() - t0)
+            del maps
+        e2e_batch_s = float(np.mean(times))
+        achieved = bytes_alg / (t_splat * 1e-3) / 1e9
         line = {
-            "workload": f"BASELINE config 4: 64 JHU-shaped images (512..2048 px sides, 0..25000 heads), "
-                        f"{'adaptive kNN sigma' if adaptive else 'fixed sigma 4'}",
-            "metric": "density maps/s", "value_device": 64 / (t_dev * 1e-3), "value_e2e_host_numpy": 64 / e2e_s,
-            "value_e2e_host_numpy_batch_api": 64 / e2e_batch_s,
-            "ms_total_device": t_dev, "ms_splat": t_splat,
-            "roofline": {"bound": "hbm", "achieved": bytes_alg / (t_splat * 1e-3) / 1e9, "peak": HBM_GBS, "unit": "GB/s",
-                         "frac": bytes_alg / (t_splat * 1e-3) / 1e9 / HBM_GBS,
-                         "note": "algorithmic bytes 4*H*W + 16*N per image / time of the prepare + culling + splat kernels of the batch"},
+            "workload": f"BASELINE config 4: 64 JHU-shaped images (512..2048 px sides, 0..25000 heads, {int(pl.total_heads)} in all, "
+                        f"{int(pl.total_pixels) * 4 / 1e6:.0f} MB of maps), {'adaptive kNN sigma' if adaptive else 'fixed sigma 4'}",
+            "metric": "density maps/s", "unit": "maps/s", "value": 64 / (t_dev * 1e-3), "ms_total_device": t_dev,
+            "ms_splat": t_splat, "ms_knn": t_dev - t_splat,
+            "e2e": {"value": 64 / e2e_batch_s, "unit": "maps/s", "h2d_bytes_per_step": 16 * int(pl.total_heads) + plan.meta.nbytes,
+                    "d2h_bytes_per_step": 4 * int(pl.total_pixels),
+                    "note": "gaussian_filter_density_batch: host numpy heads in, host numpy maps out (one launch set, one packed D2H)",
+                    "per_image_api_maps_per_s": 64 / e2e_s},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": HBM_GBS, "unit": "GB/s", "frac": achieved / HBM_GBS,
+                         "traffic": None,
+                         "note": "algorithmic bytes 4*H*W + 16*N per image over the time of the prepare + culling + splat kernels "
+                                 "of the batch (kNN time reported separately: N^2 fp64 distance evaluations, compute only)"},
         }
         if cpu:
-            from oracle import dmap_oracle
+            ref = _reference_module("dmap_gen")
             cand = sorted([im for im in images if 15 <= len(im[1]) <= 400], key=lambda im: len(im[1]) * im[0][0] * im[0][1])
-            small = cand[:2]  # the two cheapest images with a non-trivial crowd (cost ~ heads x pixels)
-            t0 = time.perf_counter()
-            heads = 0
-            for (h, w), pts in small:
-                dmap_oracle.density_reference_like((h, w), pts, fixed=not adaptive)
+            heads, done, t0 = 0, 0, time.perf_counter()
+            for (h, w), pts in cand:  # cheapest images with a non-trivial crowd first, until the budget is spent
+                if done and time.perf_counter() - t0 > cpu_seconds / 2:
+                    break
+                if ref is not None:
+                    (ref.gaussian_filter_density if adaptive else ref.gaussian_filter_density_fixed)(np.empty((h, w, 3)), pts)
+                else:
+                    from oracle import dmap_oracle
+                    dmap_oracle.density_reference_like((h, w), pts, fixed=not adaptive)
                 heads += len(pts)
+                done += 1
             dt = time.perf_counter() - t0
             total_heads = sum(len(p) for _, p in images)
-            line["cpu_baseline"] = {"value": 64 / (dt / max(heads, 1) * total_heads), "unit": "density maps/s", "cores": 1,
-                                    "kind": "port", "sample": f"reference algorithm (scipy gaussian_filter per head) on {len(small)} small images, "
-                                    f"{heads} heads in {dt:.1f} s; extrapolated per head to the {total_heads} heads of the set"}
+            line["cpu_baseline"] = {
+                "value": 64 / (dt / max(heads, 1) * total_heads), "unit": "maps/s", "cores": 1,
+                "kind": "reference" if ref is not None else "port",
+                "sample": (f"{'unmodified utils/dmap_gen.py' if ref is not None else 'oracle port of utils/dmap_gen.py'} "
+                           f"(scipy gaussian_filter per head, one process) on the {done} cheapest non-trivial images, {heads} heads in "
+                           f"{dt:.1f} s; per-head cost extrapolated to the {total_heads} heads of the set (SURVEY 8d: the full "
+                           f"set would take hours)")}
+        lines["splat_adaptive" if adaptive else "splat_fixed"] = line
+    return lines
+
+
+def bench_dmap(cpu):
+    for line in dmap_lines(cpu).values():
         print(json.dumps(line), flush=True)
 
 
-def bench_isw(cpu):
+def isw_lines(cpu, tf32_peak=None):
+    """BASELINE config 5: {gram_c64, gram_c256, gram_c512} lines (covariance kernel roofline, module step, e2e, cpu_baseline)."""
     from dgvcc_b200.models.ISW import InstanceWhitening, instance_whitening_loss
-    from oracle import isw_oracle
     lib = _native.lib()
+    tf32_peak = tf32_peak or probe_tf32_peak()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for (b, c, h, w) in [(8, 64, 160, 160), (8, 256, 80, 80), (8, 512, 40, 40)]:
+    lines = {}
+    for (b, c, h, w) in synthetic.CONFIG5_SHAPES:
         hw = h * w
-        x = torch.randn(b, c, hw, device=dev)
+        gen = torch.Generator().manual_seed(5000 + c)
+        x_host = torch.randn(b, c, h, w, generator=gen)
+        mask_host = (torch.rand(c, c, generator=gen) < 0.5).float().triu(1)   # relax_denom = 2 branch: half of the upper triangle
+        x = x_host.to(dev).view(b, c, hw)
         eye = torch.eye(c, device=dev)
         n = lib.dgvcc_isw_workspace_bytes(b, c, hw)
         ws = torch.empty(n, dtype=torch.uint8, device=dev)
         fc = torch.empty(b, c, c, device=dev)
         ts = []
-        for rep in range(6):
+        for rep in range(8):
             flush.zero_()
             e0, e1 = ev(), ev()
             e0.record()
             lib.dgvcc_isw_covariance(_native.ptr(x), _native.ptr(eye), b, c, hw, 1, _native.ptr(ws), n, _native.ptr(fc), _native.stream_ptr(dev))
             e1.record()
             torch.cuda.synchronize()
-            if rep:
+            if rep >= 2:
                 ts.append(e0.elapsed_time(e1))
-        t_cov = min(ts)
-        xin = torch.randn(b, c, h, w, device=dev, requires_grad=True)
-        mask = isw_oracle.upper_mask(c, 0.5, 1).to(dev)
+        t_cov = float(np.mean(ts))
+        xin = x_host.to(dev).requires_grad_(True)
+        mask = mask_host.to(dev)
+        nrm = mask.sum()
         iw = InstanceWhitening(c)
         tm = []
-        for rep in range(6):
+        for rep in range(8):
             flush.zero_()
             xin.grad = None
             e0, e1 = ev(), ev()
             e0.record()
             y, wt = iw(xin)
-            loss = instance_whitening_loss(wt, eye, mask, 0, mask.sum())
+            loss = instance_whitening_loss(wt, eye, mask, 0, nrm)
             loss.backward()
             e1.record()
             torch.cuda.synchronize()
-            if rep:
+            if rep >= 2:
                 tm.append(e0.elapsed_time(e1))
+        t_mod = float(np.mean(tm))
+        # end to end: pinned host feature map in, loss + gradient out
+        x_pin, g_pin = x_host.pin_memory(), torch.empty_like(x_host).pin_memory()
+
+        def host_step():
+            xd = x_pin.to(dev, non_blocking=True).requires_grad_(True)
+            _, wt_ = iw(xd)
+            l_ = instance_whitening_loss(wt_, eye, mask, 0, nrm)
+            l_.backward()
+            g_pin.copy_(xd.grad, non_blocking=True)
+            return float(l_.detach())
+        for _ in range(3):
+            host_step()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            host_step()
+        e2e_s = (time.perf_counter() - t0) / 10
+        flops_alg = 3.0 * b * c * c * hw        # 2 B C^2 HW x 3 TF32 MMAs per product / 2 (upper-triangular tiles)
+        bytes_alg = 4.0 * b * c * hw            # the feature map read once
+        t_tensor, t_hbm = flops_alg / tf32_peak, bytes_alg / (HBM_GBS * 1e9)
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
         t1 = (c + 127) // 128
         tiles = t1 * (t1 + 1) // 2
-        mma_flops = 3 * 2.0 * b * tiles * 128 * 128 * hw  # executed: 3 TF32 MMAs per logical product, 128x128 tiles
-        line = {
-            "workload": f"BASELINE config 5: ISW covariance loss, B={b} C={c} HW={hw}",
-            "metric": "steps/s (InstanceWhitening + instance_whitening_loss fwd+bwd)", "value": 1e3 / min(tm),
-            "ms_fwd_bwd": min(tm), "us_covariance": t_cov * 1e3,
-            "roofline": {"bound": "hbm" if c <= 64 else "tensor",
-                         "hbm_gbs": 4.0 * b * c * hw / (t_cov * 1e-3) / 1e9, "hbm_frac": 4.0 * b * c * hw / (t_cov * 1e-3) / 1e9 / HBM_GBS,
-                         "tf32_tflops_executed": mma_flops / (t_cov * 1e-3) / 1e12,
-                         "useful_tflops": 2.0 * b * c * c * hw / (t_cov * 1e-3) / 1e12,
-                         "note": "covariance = tcgen05 Gram partials + finish kernel; hbm = 4*B*C*HW bytes read once"},
-        }
+        executed = 3 * 2.0 * (b if c > 64 else (b + 1) // 2) * tiles * 128 * 128 * hw
+        roof = {"bound": bound, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                "achieved": (flops_alg / (t_cov * 1e-3) / 1e12) if bound == "tensor" else (bytes_alg / (t_cov * 1e-3) / 1e9),
+                "peak": (tf32_peak / 1e12) if bound == "tensor" else HBM_GBS,
+                "frac": max(t_tensor, t_hbm) / (t_cov * 1e-3), "traffic": None,
+                "tf32_peak_tflops_probed": tf32_peak / 1e12, "executed_mma_tflops": executed / (t_cov * 1e-3) / 1e12,
+                "hbm_gbs": bytes_alg / (t_cov * 1e-3) / 1e9,
+                "note": ("dgvcc_isw_covariance (tcgen05 3xTF32 Gram partials + split-K finish); roofline time = max(3 B C^2 HW / "
+                         "TF32 peak probed in this run by dgvcc_probe_tf32, 4 B C HW / measured HBM copy peak); frac = roofline "
+                         "time / measured time")}
+        line = {"workload": f"BASELINE config 5: ISW covariance loss, B={b} C={c} HW={hw} (fp32 in, 3xTF32 tensor cores)",
+                "metric": "steps/s (InstanceWhitening + instance_whitening_loss fwd+bwd)", "unit": "steps/s",
+                "value": 1e3 / t_mod, "ms_fwd_bwd": t_mod, "us_covariance": t_cov * 1e3, "roofline": roof,
+                "e2e": {"value": 1 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                        "d2h_bytes_per_step": x_host.numel() * 4 + 4}}
         if cpu:
-            xc = xin.detach().cpu().requires_grad_(True)
+            ref = _reference_module("instance_whitening")
+            xc = x_host.clone().requires_grad_(True)
             t0 = time.perf_counter()
-            wr = isw_oracle.instance_standardize(xc)
-            isw_oracle.whitening_loss(wr, eye.cpu(), mask.cpu(), 0, mask.sum().cpu()).backward()
+            if ref is not None:
+                _, wr = ref.InstanceWhitening(c)(xc)
+                ref.instance_whitening_loss(wr, torch.eye(c), mask_host, 0, mask_host.sum()).backward()
+            else:
+                from oracle import isw_oracle
+                wr = isw_oracle.instance_standardize(xc)
+                isw_oracle.whitening_loss(wr, torch.eye(c), mask_host, 0, mask_host.sum()).backward()
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": 1 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "oracle port of instance_whitening.py, same tensors, one fwd+bwd"}
+            line["cpu_baseline"] = {"value": 1 / dt, "unit": "steps/s", "cores": torch.get_num_threads(),
+                                    "kind": "reference" if ref is not None else "port",
+                                    "sample": ("unmodified models/ISW/instance_whitening.py" if ref is not None else "oracle port of "
+                                               "instance_whitening.py") + " on torch CPU, same tensors, one forward + backward"}
+        lines[f"gram_c{c}"] = line
+    return lines
+
+
+def bench_isw(cpu):
+    for line in isw_lines(cpu).values():
         print(json.dumps(line), flush=True)
 
 

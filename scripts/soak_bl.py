@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from dgvcc_b200 import synthetic
 from dgvcc_b200.losses.bl import BL
+from dgvcc_b200.losses import bl as blmod
 import oracle
 from oracle import bl_oracle
 
@@ -26,7 +27,7 @@ while time.time() - t0 < budget:
     sigma = float(rng.choice([4.0, 8.0, 5.5, 12.0, 16.0]))
     use_bg = bool(rng.integers(0, 2))
     bg_ratio = float(rng.choice([1.0, 0.15, 0.5]))
-    os.environ["DGVCC_BL_CHUNK"] = str(int(rng.choice([17, 64, 256, 1024])))
+    blmod._CHUNK_POINTS = int(rng.choice([17, 64, 256, 1024]))
     cfg = int(rng.integers(100, 10000))
     pts, tgt, dens, st = synthetic.bl_batch(cfg, counts, w, h, stride)
     pts = [torch.from_numpy(p) for p in pts]
@@ -83,7 +84,7 @@ while time.time() - t0 < budget:
             continue
         if el > 1e-5 or eg > 1.0:
             raise SystemExit(f"MISMATCH: cfg={cfg} counts={counts} grid={hp}x{wp} stride={stride} sigma={sigma} bg={use_bg}/{bg_ratio} "
-                             f"host={on_host} cull={mod.exact_cull} chunk={os.environ['DGVCC_BL_CHUNK']}: loss rel err {el:.3g}, grad err/tol {eg:.3g}")
+                             f"host={on_host} cull={mod.exact_cull} chunk={blmod._CHUNK_POINTS}: loss rel err {el:.3g}, grad err/tol {eg:.3g}")
         sqrt_cases += 1
     worst_l, worst_g = max(worst_l, el), max(worst_g, eg)
     cases += 1

@@ -33,11 +33,26 @@ def load_bl_golden(name):
 BL_GOLDEN_CASES = ["c1", "mixed", "nobg", "empty", "sigma10", "outside"]
 
 
+# (test id, what, worst err / gate, rtol, atol) of every tolerance check that ran: conftest.py prints the worst one
+# per test at the end of the session, so the log shows how far inside its gate each parity test sits.
+MARGINS = []
+
+
+def record_margin(what, err, tol, rtol, atol):
+    """err, tol: float64 tensors of equal shape (|got - ref| and atol + rtol |ref|)."""
+    if err.numel() == 0:
+        return
+    ratio = torch.where(tol > 0, err / tol.clamp_min(1e-300), torch.where(err > 0, torch.inf, 0.0).to(err.dtype))
+    test = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" (")[0]
+    MARGINS.append((test, what, float(ratio.max()), float(rtol), float(atol)))
+
+
 def assert_close(got, ref, rtol, atol, what=""):
     got = torch.as_tensor(got).double()
     ref = torch.as_tensor(ref).double()
     err = (got - ref).abs()
     tol = atol + rtol * ref.abs()
+    record_margin(what, err, tol, rtol, atol)
     bad = err > tol
     if bad.any():
         idx = torch.nonzero(bad)[0].tolist()

@@ -48,7 +48,7 @@ def check_against(loss, grad, counts, ref_loss, ref_grad, ref_counts):
 @pytest.mark.parametrize("chunk", [1024, 37])
 @pytest.mark.parametrize("name", BL_GOLDEN_CASES)
 def test_fused_bl_matches_reference_fixture(name, chunk, monkeypatch):
-    monkeypatch.setenv("DGVCC_BL_CHUNK", str(chunk))  # 37: every image is cut into several point chunks
+    monkeypatch.setattr("dgvcc_b200.losses.bl._CHUNK_POINTS", int(chunk))  # 37: every image is cut into several point chunks
     c = load_bl_golden(name)
     loss, grad, counts = run_cuda(c["points"], c["st_sizes"], c["targets"], c["density"], c["stride"], c["sigma"], c["bg_ratio"], c["use_bg"])
     check_against(loss, grad, counts, c["ref_loss"], c["ref_grad"], c["ref_count"])
@@ -58,7 +58,7 @@ def test_fused_bl_matches_reference_fixture(name, chunk, monkeypatch):
 @pytest.mark.parametrize("name", ["c1", "mixed", "nobg", "sigma10", "outside"])
 def test_posteriors_match_reference_fixture(name, chunk, monkeypatch):
     from dgvcc_b200.losses.bl import Post_Prob
-    monkeypatch.setenv("DGVCC_BL_CHUNK", str(chunk))
+    monkeypatch.setattr("dgvcc_b200.losses.bl._CHUNK_POINTS", int(chunk))
     c = load_bl_golden(name)
     dev = torch.device("cuda:0")
     hp, wp = c["height"] // c["stride"], c["width"] // c["stride"]
@@ -106,7 +106,7 @@ def test_random_shapes_against_oracle(seed, monkeypatch):
     sigma = float(rng.choice([4.0, 8.0, 5.5, 12.0]))
     use_bg = bool(rng.integers(0, 2))
     bg_ratio = float(rng.choice([1.0, 0.15, 0.5]))
-    monkeypatch.setenv("DGVCC_BL_CHUNK", str(int(rng.choice([17, 64, 1024]))))
+    monkeypatch.setattr("dgvcc_b200.losses.bl._CHUNK_POINTS", int(int(rng.choice([17, 64, 1024]))))
     pts, tgt, dens, st = synthetic.bl_batch(40 + seed, counts, w, h, stride)
     pts = [torch.from_numpy(p) for p in pts]
     tgt = [torch.from_numpy(t) for t in tgt]
@@ -131,6 +131,49 @@ def test_config3_qnrf_image_matches_oracle():
     ref = bl_oracle.bl_forward_backward_chunked(pts, st, tgt, dens, 8, 8.0, 1.0, True, chunk_rows=8)
     got = run_cuda(pts, st, tgt, dens, 8, 8.0, 1.0, True)
     check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
+
+
+def test_config3_full_batch_matches_oracle():
+    """The FULL BASELINE config-3 batch (16 images, 49 697 heads, 192x256 grid) -- the workload bench.py times --
+    against the chunked oracle: loss, every expected count and the whole density gradient, dense and culled."""
+    counts = synthetic.config_counts(3)
+    pts, st, tgt, dens = _batch(3, counts, 2048, 1536)
+    ref = bl_oracle.bl_forward_backward_chunked(pts, st, tgt, dens, 8, 8.0, 1.0, True, chunk_rows=8)
+    for cull in (False, True):
+        got = run_cuda(pts, st, tgt, dens, 8, 8.0, 1.0, True, exact_cull=cull)
+        check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs a second GPU")
+def test_tensors_on_another_device_than_the_current_one():
+    """The reference's configs pass device='cuda:1' .. 'cuda:3' and never call set_device: every launcher must run
+    on the device that owns the tensors (the stream's device), and leave the current device alone."""
+    from dgvcc_b200.losses.bl import BL
+    c = load_bl_golden("mixed")
+    assert torch.cuda.current_device() == 0
+    dev = torch.device("cuda:1")
+    mod = BL(c["sigma"], max(c["density"].shape[-2:]) * c["stride"], c["stride"], c["bg_ratio"], c["use_bg"], dev)
+    d = c["density"].to(dev).clone().requires_grad_(True)
+    loss = mod([p.to(dev) for p in c["points"]], c["st_sizes"].to(dev), [t.to(dev) for t in c["targets"]], d)
+    loss.backward()
+    torch.cuda.synchronize(dev)
+    assert torch.cuda.current_device() == 0
+    assert_close(loss.cpu(), c["ref_loss"], RTOL, 0, "loss on cuda:1")
+    assert_close(d.grad.cpu(), c["ref_grad"], RTOL, 1e-6 * float(c["ref_grad"].abs().max()), "gradient on cuda:1")
+    # the ISW Gram (tensor maps, per-device kernel attributes) on the second device as well
+    from dgvcc_b200.models.ISW import InstanceWhitening, instance_whitening_loss
+    from oracle import isw_oracle
+    x = torch.randn(2, 64, 24, 24, generator=torch.Generator().manual_seed(3))
+    mask = isw_oracle.upper_mask(64, 0.5, 1)
+    xd = x.to(dev).requires_grad_(True)
+    _, w = InstanceWhitening(64)(xd)
+    l = instance_whitening_loss(w, torch.eye(64, device=dev), mask.to(dev), 0, mask.sum().to(dev))
+    l.backward()
+    xr = x.clone().requires_grad_(True)
+    lr = isw_oracle.whitening_loss(isw_oracle.instance_standardize(xr), torch.eye(64), mask, 0, mask.sum())
+    lr.backward()
+    assert torch.cuda.current_device() == 0
+    assert_close(l.cpu(), lr.detach(), 1e-5, 1e-7, "ISW loss on cuda:1")
 
 
 def test_config3_full_batch_properties():

@@ -156,6 +156,38 @@ def test_batched_launch_matches_oracle_on_a_ragged_list():
             assert np.array_equal(o, fn(np.empty((h, w, 0)), p)), "batched and single-image launches differ"
 
 
+def test_config4_full_set_matches_oracle():
+    """The FULL BASELINE config-4 set (64 JHU-shaped images, sides 512..2048, 0..25 000 heads, float64 and float32
+    points) through the batched API, adaptive and fixed: kNN neighbours bit-exact against scipy's KDTree, every map
+    against the closed-form oracle (bit-identical up to the few pixels assert_map_close allows)."""
+    from dgvcc_b200.utils import dmap_gen
+    images = synthetic.config4_images()
+    shapes = [s for s, _ in images]
+    plist = [p for _, p in images]
+    assert len(images) == 64 and any(len(p) == 0 for p in plist) and max(len(p) for p in plist) > 15000
+    sig = {}
+    for i, p in enumerate(plist):
+        if len(p) > 3:
+            p64 = np.ascontiguousarray(p, dtype=np.float64)
+            rd, rl = dmap_oracle.knn4(p64)
+            if i % 8 == 0:  # the device kNN on its own for every eighth image (all of them feed the maps below)
+                dist, loc, sigma = dmap_gen.knn_sigma(p64)
+                assert np.array_equal(loc, rl) and np.array_equal(dist, rd), f"kNN image {i}"
+            sig[i] = (rd[:, 1] + rd[:, 2] + rd[:, 3]) * 0.1
+    for fixed in (False, True):
+        outs = dmap_gen.gaussian_filter_density_batch(shapes, plist, fixed=fixed)
+        bad = 0
+        for i, ((h, w), p, o) in enumerate(zip(shapes, plist, outs)):
+            assert o.shape == (h, w) and o.dtype == np.float32
+            if len(p) == 0:
+                assert not o.any()
+                continue
+            p64 = np.ascontiguousarray(p, dtype=np.float64)
+            ref = dmap_oracle.density_closed_form((h, w), p64, fixed=fixed, sigmas=None if fixed else sig.get(i))
+            bad += assert_map_close(o, ref, f"config 4 image {i} ({h}x{w}, {len(p)} heads, fixed={fixed})")
+        print(f"config 4, fixed={fixed}: {bad} pixels of {sum(h * w for h, w in shapes)} not bit-identical")
+
+
 def test_batched_knn_bit_exact():
     import ctypes
     import torch

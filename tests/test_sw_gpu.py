@@ -41,7 +41,9 @@ class FakeExchange:
 
 def build(c, exchange=None):
     from dgvcc_b200.models.ISW.switchwhiten import SwitchWhiten2d
-    m = SwitchWhiten2d(c["x"].shape[1], num_pergroup=c["num_pergroup"], sw_type=c["sw_type"], tie_weight=c["tie"],
+    from dgvcc_b200.models.ISW.sync_switchwhiten import SyncSwitchWhiten2d
+    cls = SwitchWhiten2d if c["kind"] == "plain" else SyncSwitchWhiten2d
+    m = cls(c["x"].shape[1], num_pergroup=c["num_pergroup"], sw_type=c["sw_type"], tie_weight=c["tie"],
                        affine=c["affine"]).cuda()
     with torch.no_grad():
         m.sw_mean_weight.copy_(c["mw"])
@@ -238,6 +240,21 @@ def test_sync_layer_two_ranks_real_process_group(name):
     refuses two ranks on one device; with one GPU per rank the same code runs over NCCL), against the fixtures the
     reference's SyncSwitchWhiten2d produced with two gloo ranks."""
     _spawn_sync(name, 2, "gloo")
+
+
+def test_sync_layer_eval_needs_no_process_group():
+    """SyncMeanCov makes no dist call in eval mode (sync_switchwhiten.py:27-28, 48-55): single-process validation
+    with SyncSwitchWhiten2d (models/ISW/Resnet.py, iw=5) must work without init_process_group, forward and backward;
+    the backward keeps the synchronised layer's 1 / (n hw) scaling of the running-statistics adjoints."""
+    import torch.distributed as dist
+    assert not dist.is_initialized()
+    c = CASES["s3e"]
+    assert c["kind"] == "sync1" and not c["training"]
+    m = build(c)          # the real SyncSwitchWhiten2d, its own _exchange()
+    check(run(m, c["x"], c["gy"]), c["ref"][0], 2e-4)
+    m.train()
+    with pytest.raises((RuntimeError, ValueError)):   # training DOES need the group, like the reference
+        m(c["x"].cuda())
 
 
 def test_sync_layer_one_rank_nccl():

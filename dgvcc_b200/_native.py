@@ -19,7 +19,7 @@ class BLLayout(ctypes.Structure):
     """Mirror of struct dgvcc_bl_layout."""
     _fields_ = [(n, c_int64) for n in
                 ("amax", "rz", "pbg", "ebg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "zpart",
-                 "minpart", "gpart", "total")] + \
+                 "minpart", "gpart", "total", "dens", "gfinal", "flags", "err", "push_ticket")] + \
                [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("reserved_", c_int32)]
 
 
@@ -28,6 +28,17 @@ class BLPacked(ctypes.Structure):
     _fields_ = [(n, c_int64) for n in
                 ("total_points", "total_rows", "total_chunks", "multi_chunk", "meta_bytes", "off_points", "off_targets",
                  "total_bytes")]
+
+
+BL_PHASES = 8  # DGVCC_BL_PHASES
+BL_PH_DENS, BL_PH_MIN, BL_PH_Z, BL_PH_CNT, BL_PH_LOSS, BL_PH_GPART, BL_PH_GRAD, BL_PH_OUT = range(BL_PHASES)
+
+
+class BLShard(ctypes.Structure):
+    """Mirror of struct dgvcc_bl_shard."""
+    _fields_ = [(n, c_int32) for n in ("rank", "world", "chunk_lo", "chunk_hi", "pt_lo", "pt_hi", "img_lo", "img_hi")] + \
+               [("push_first", c_int32 * (BL_PHASES + 1)), ("wait_mask", ctypes.c_uint32 * BL_PHASES),
+                ("signal_mask", ctypes.c_uint32 * BL_PHASES), ("epoch", ctypes.c_uint32), ("reserved_", c_int32)]
 
 
 class DmapPlan(ctypes.Structure):
@@ -60,6 +71,18 @@ SIGNATURES = {
                                          c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dgvcc_bl_bayloss_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_float, c_void_p,
                                           c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_bl_shard_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
+    "dgvcc_bl_shard_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
+                                       c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, POINTER(BLShard),
+                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dgvcc_bl_shard_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_float, c_float, c_int,
+                                        c_int, c_float, c_void_p, POINTER(BLShard), c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p, c_void_p]),
+    "dgvcc_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "dgvcc_peer_free": (c_int, [c_void_p]),
+    "dgvcc_peer_export": (c_int, [c_void_p, c_void_p]),
+    "dgvcc_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "dgvcc_peer_close": (c_int, [c_void_p]),
     "dgvcc_dmap_knn_workspace_bytes": (c_size_t, [c_int]),
     "dgvcc_dmap_knn_sigma": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dgvcc_dmap_batch_plan": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmapPlan)]),

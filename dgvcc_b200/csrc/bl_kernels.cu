@@ -28,6 +28,7 @@
 // rounded).  Only exp (one MUFU.EX2 fed by one fused multiply-add, see pair_exp) and the summation order
 // differ, ~1e-6.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "../../include/dgvcc_b200.h"
@@ -147,6 +148,14 @@ __host__ __device__ __forceinline__ Meta meta_view(const int32_t* m, int batch) 
     v.chunks = m + 4 * batch + 3;
     return v;
 }
+
+// Point-chunk sharding across GPUs (dgvcc_bl_shard_*): this rank owns the chunk ids [chunk_lo, chunk_hi), i.e. the
+// points [pt_lo, pt_hi) of the packed sequence, and touches the images [img_lo, img_hi).  One GPU: on = 0.
+struct Shard {
+    int on;
+    int chunk_lo, chunk_hi, pt_lo, pt_hi, img_lo, img_hi;
+};
+__host__ __device__ __forceinline__ Shard no_shard() { return Shard{0, 0, 0x7fffffff, 0, 0x7fffffff, 0, 0x7fffffff}; }
 
 struct TaskInfo {
     int img, row0, n_rows;    // image, its first posterior row, number of rows
@@ -407,7 +416,7 @@ __global__ void __launch_bounds__(CTA_THREADS)
 bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
             int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
-            float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket) {
+            float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, Shard sh) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
     TaskInfo t;
@@ -515,7 +524,7 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
     for (int q = 0; q < R / 2; ++q)
 #pragma unroll
         for (int c = 0; c < C; ++c) unpack2(zp[q][c], z[2 * q][c], z[2 * q + 1][c]);
-    const bool first = t.chunk == t.first_chunk;
+    const bool first = t.chunk == max(t.first_chunk, sh.chunk_lo);  // the image's first chunk ON THIS RANK
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -546,7 +555,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
                  const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg, int exact_cull,
                  const float* __restrict__ amax_in, const float* __restrict__ ebg_in,
                  const float* __restrict__ zpart, float* __restrict__ rz_out, float* __restrict__ pbg_out,
-                 int64_t total_rows, float* __restrict__ cpart) {
+                 int64_t total_rows, float* __restrict__ cpart, Shard sh) {
     // The four warps of a CTA sweep the same point chunk over four pixel tiles; their per-point partial counts
     // meet in shared memory and leave the CTA as ONE partial row (a quarter of the cpart traffic, and a quarter
     // of what bl_reduce_counts_kernel has to read).  Warps past the last pixel tile contribute zeros.
@@ -563,8 +572,8 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
     PixelTile<R, C> px;
     px.init(t, g);
     float* part = cpart + (size_t)blockIdx.x * total_rows + t.row0;
-    const bool first = t.chunk == t.first_chunk;
-    const bool bg_row = first && (use_bg || t.n_img_pts == 0);
+    const bool first = t.chunk == max(t.first_chunk, sh.chunk_lo);  // first chunk of the image on this rank: rz / pbg
+    const bool bg_row = t.chunk == t.first_chunk && (use_bg || t.n_img_pts == 0);  // the image's first chunk anywhere
 
     // per-pixel weights D[m]/Z[m]; pixels outside the grid get weight 0
     float neg_amax[R][C], wd[R][C], bg_part = 0.f;
@@ -696,7 +705,7 @@ __device__ __forceinline__ float block_sum_ordered(float v, float* scratch) {
 __global__ void __launch_bounds__(256)
 bl_reduce_counts_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
-                        float* __restrict__ counts, float* __restrict__ residual) {
+                        float* __restrict__ counts, float* __restrict__ residual, Shard sh) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (j >= total_rows) return;
     const Meta mv = meta_view(meta, batch);
@@ -707,6 +716,12 @@ bl_reduce_counts_kernel(const float* __restrict__ cpart, int tiles, int64_t tota
     }
     const int local = (int)(j - mv.row_off[lo]);
     const int n_pts = mv.pt_off[lo + 1] - mv.pt_off[lo];
+    if (sh.on) {  // only rows whose partials this rank computed: its own points; the last row with the image's first chunk
+        const int gp = mv.pt_off[lo] + local;
+        const bool mine = local < n_pts ? (gp >= sh.pt_lo && gp < sh.pt_hi)
+                                        : (mv.icb[lo] >= sh.chunk_lo && mv.icb[lo] < sh.chunk_hi);
+        if (!mine) return;
+    }
     const float* p = cpart + j;
     float c = 0.f;
 #pragma unroll 8
@@ -720,13 +735,13 @@ __global__ void __launch_bounds__(SELECT_THREADS)
 bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
                  float inv_batch, const float* __restrict__ counts, const float* __restrict__ residual,
                  float* __restrict__ wsel, float* __restrict__ loss_img, float* __restrict__ loss_out,
-                 unsigned int* __restrict__ ticket) {
+                 unsigned int* __restrict__ ticket, int img_first, int finish) {
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sh_prefix, sh_rank, sh_equal;
     __shared__ unsigned int warp_cnt[SELECT_THREADS / 32];
     __shared__ float scratch[SELECT_THREADS / 32];
 
-    const int img = blockIdx.x, tid = threadIdx.x;
+    const int img = img_first + blockIdx.x, tid = threadIdx.x;
     const Meta mv = meta_view(meta, batch);
     const int pt0 = mv.pt_off[img], n_pts = mv.pt_off[img + 1] - pt0;
     const int row0 = mv.row_off[img], n_rows = mv.row_off[img + 1] - row0;
@@ -824,7 +839,8 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
     const float l_img = block_sum_ordered(lsum, scratch);
 
     // last CTA to finish adds the per-image losses in image order (deterministic), bl.py:79
-    if (tid == 0) {
+    if (tid == 0 && !finish) loss_img[img] = l_img;  // sharded: bl_loss_finish_kernel adds them once every rank's arrived
+    if (tid == 0 && finish) {
         loss_img[img] = l_img;
         __threadfence();
         const unsigned int done = atomicAdd(ticket, 1u);
@@ -849,7 +865,7 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
                Scale k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
-               float* __restrict__ gpart, float* __restrict__ grad_density) {
+               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
     if (!decode_task<R, C>(meta, batch, g, t)) return;
@@ -909,7 +925,7 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
 #pragma unroll
         for (int c = 0; c < C; ++c) unpack2(accp[q][c], acc[2 * q][c], acc[2 * q + 1][c]);
 
-    if (t.n_chunks == 1) {
+    if (t.n_chunks == 1 && !always_partial) {
         const float gscale = grad_loss[0] * inv_batch;
         const bool has_bg_row = use_bg || t.n_img_pts == 0;
         const float w_bg = has_bg_row ? wsel[t.row0 + t.n_rows - 1] : 0.f;
@@ -936,17 +952,22 @@ __global__ void __launch_bounds__(256)
 bl_grad_reduce_kernel(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
                       const float* __restrict__ grad_loss, const float* __restrict__ gpart,
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
-                      const float* __restrict__ wsel, float* __restrict__ grad_density) {
-    const int img = blockIdx.y;
+                      const float* __restrict__ wsel, float* __restrict__ grad_density, Shard sh) {
+    const int img = sh.img_lo + blockIdx.y;
     const Meta mv = meta_view(meta, batch);
     const int first = mv.icb[img], n_chunks = mv.icb[img + 1] - first;
-    if (n_chunks <= 1) return;
+    if (sh.on) {  // every image is finished by the rank that owns its first chunk, single-chunk images included
+        if (first < sh.chunk_lo || first >= sh.chunk_hi) return;
+    } else if (n_chunks <= 1) {
+        return;
+    }
     const int pix = blockIdx.x * 256 + threadIdx.x;
     if (pix >= M) return;
     float acc = 0.f;
     for (int c = 0; c < n_chunks; ++c) acc += gpart[(size_t)(first + c) * M + pix];
     const int n_rows = mv.row_off[img + 1] - mv.row_off[img];
-    const float w_bg = use_bg ? wsel[mv.row_off[img] + n_rows - 1] : 0.f;
+    const bool has_bg_row = use_bg || mv.pt_off[img + 1] == mv.pt_off[img];
+    const float w_bg = has_bg_row ? wsel[mv.row_off[img] + n_rows - 1] : 0.f;
     const size_t m = (size_t)img * M + pix;
     grad_density[m] = grad_loss[0] * inv_batch * fmaf(acc, rz_in[m], w_bg * pbg_in[m]);
 }
@@ -1057,6 +1078,111 @@ bl_prob_grad_kernel(const float* __restrict__ prob, const int32_t* __restrict__ 
     grad_density[(size_t)img * M + m] = grad_loss[0] * inv_batch * acc;
 }
 
+// ------------------------------------------------------------------- point-chunk sharding across GPUs
+// One batch spread over the GPUs of a box by POINT CHUNKS (dgvcc_bl_shard_*): every rank sweeps its own chunks over
+// all pixels of the images they belong to; the per-chunk partials an image's other ranks need (minima, denominator
+// shares, gradient sums), the counts / residuals of its rows, the density and the finished gradient travel as plain
+// stores into the peers' workspaces over NVLink (peer pointers from dgvcc_peer_open), followed by a flag per
+// (phase, source rank).  Receivers combine the partials in chunk order, exactly like one GPU does, so the sharded
+// result is bit-identical to the single-GPU one.  No NCCL on the data path.
+constexpr int PUSH_THREADS = 256;
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One CTA per slice: copy `bytes` from src_base + src_off to peers[dst_rank] + dst_off.  The last CTA to finish
+// raises this rank's flag of `phase` on every rank in signal_mask (release at system scope, after every CTA's
+// stores were fenced), so a receiver that sees the flag sees the data.
+__global__ void __launch_bounds__(PUSH_THREADS)
+bl_push_kernel(const dgvcc_bl_push* __restrict__ slices, int n_slices, const char* __restrict__ src_base,
+               char* const* __restrict__ peers, int64_t flags_off, int phase, int rank, int world,
+               unsigned int signal_mask, unsigned int epoch, unsigned int* __restrict__ ticket) {
+    __shared__ bool last;
+    if ((int)blockIdx.x < n_slices) {
+        const dgvcc_bl_push sl = slices[blockIdx.x];
+        const char* src = src_base + sl.src_off;
+        char* dst = peers[sl.dst_rank] + sl.dst_off;
+        if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)sl.bytes) & 15u) == 0) {
+            const int n = sl.bytes >> 4;
+            for (int i = threadIdx.x; i < n; i += PUSH_THREADS)
+                reinterpret_cast<int4*>(dst)[i] = __ldcg(reinterpret_cast<const int4*>(src) + i);
+        } else {
+            const int n = sl.bytes >> 2;  // every region is made of 4-byte elements
+            for (int i = threadIdx.x; i < n; i += PUSH_THREADS)
+                reinterpret_cast<int*>(dst)[i] = __ldcg(reinterpret_cast<const int*>(src) + i);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < world && ((signal_mask >> threadIdx.x) & 1u)) {
+        unsigned int* flag = reinterpret_cast<unsigned int*>(peers[threadIdx.x] + flags_off) + phase * world + rank;
+        st_release_sys(flag, epoch);
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// Local variant: the same slices with one destination base and no flags (gathers a rank's own finished gradients).
+__global__ void __launch_bounds__(PUSH_THREADS)
+bl_copy_kernel(const dgvcc_bl_push* __restrict__ slices, int n_slices, const char* __restrict__ src_base,
+               char* __restrict__ dst_base) {
+    if ((int)blockIdx.x >= n_slices) return;
+    const dgvcc_bl_push sl = slices[blockIdx.x];
+    const char* src = src_base + sl.src_off;
+    char* dst = dst_base + sl.dst_off;
+    if ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)sl.bytes) & 15u) == 0) {
+        for (int i = threadIdx.x; i < (sl.bytes >> 4); i += PUSH_THREADS)
+            reinterpret_cast<int4*>(dst)[i] = __ldcg(reinterpret_cast<const int4*>(src) + i);
+    } else {
+        for (int i = threadIdx.x; i < (sl.bytes >> 2); i += PUSH_THREADS)
+            reinterpret_cast<int*>(dst)[i] = __ldcg(reinterpret_cast<const int*>(src) + i);
+    }
+}
+
+// Wait until every rank in wait_mask has raised its flag of this phase to `epoch` (lane = source rank).  Bounded:
+// after `timeout_ns` the kernel records the phase in err[0] and returns, so a lost peer cannot hang the GPU.
+__global__ void __launch_bounds__(32)
+bl_wait_kernel(const unsigned int* __restrict__ flags, int phase, int world, unsigned int wait_mask,
+               unsigned int epoch, unsigned long long timeout_ns, int* __restrict__ err) {
+    const int src = threadIdx.x;
+    if (src < world && ((wait_mask >> src) & 1u)) {
+        const unsigned int* flag = flags + phase * world + src;
+        const unsigned long long t0 = global_ns();
+        while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+            if (global_ns() - t0 > timeout_ns) {
+                atomicExch(err, 1 + phase + 16 * src);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+
+// Sum of the per-image losses in image order (every rank received the values of the images it does not hold).
+__global__ void bl_loss_finish_kernel(const float* __restrict__ loss_img, int batch, float inv_batch,
+                                      float* __restrict__ loss_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float total = 0.f;
+        for (int i = 0; i < batch; ++i) total += loss_img[i];
+        loss_out[0] = total * inv_batch;
+    }
+}
+
 // ------------------------------------------------------------------------------- host side
 static bool is_pow2(float s) {
     int e;
@@ -1098,9 +1224,12 @@ static Geom make_geom(int hp, int wp, const Variant& v, float stride) {
     return g;
 }
 
-static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, dgvcc_bl_layout* L) {
-    if (!L || total_rows < batch || total_chunks < batch || batch <= 0 || hp <= 0 || wp <= 0) return DGVCC_ERR_ARG;
-    const Variant v = pick_variant(total_chunks, hp, wp);
+static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, dgvcc_bl_layout* L, int world = 0) {
+    if (!L || total_rows < batch || total_chunks < batch || batch <= 0 || hp <= 0 || wp <= 0 || world < 0 || world > 32)
+        return DGVCC_ERR_ARG;
+    // world > 0: the symmetric layout of dgvcc_bl_shard_* (identical on every rank); the pixel tile is chosen for the
+    // chunks ONE rank sweeps
+    const Variant v = pick_variant(world > 0 ? ceil_div(total_chunks, world) : total_chunks, hp, wp);
     const int tiles = make_geom(hp, wp, v, 1.f).tiles;
     const size_t M = (size_t)hp * wp;
     const size_t pix = (size_t)batch * M * sizeof(float);
@@ -1108,6 +1237,12 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     const size_t chunk_pix = (size_t)total_chunks * M * sizeof(float);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (int64_t)o; };
+    L->dens = L->gfinal = L->flags = L->err = L->push_ticket = 0;
+    if (world > 0) {  // fixed offsets, whatever the batch: the flags outlive a step (they are compared with the epoch)
+        L->flags = take((size_t)DGVCC_BL_PHASES * 32 * sizeof(unsigned int));
+        L->err = take(sizeof(int));
+        L->push_ticket = take(sizeof(unsigned int));
+    }
     L->amax = take(pix); L->rz = take(pix); L->pbg = take(pix); L->ebg = take(pix);
     L->counts = take(rows); L->wsel = take(rows); L->residual = take(rows);
     L->loss_img = take((size_t)batch * sizeof(float));
@@ -1117,6 +1252,11 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     L->zpart = take(chunk_pix);
     L->minpart = take(chunk_pix);
     L->gpart = L->minpart;  // minima are dead once the denominators exist; backward re-uses the region
+    if (world > 0) {
+        L->gpart = take(chunk_pix);  // a fast peer may already push the next step's minima while this rank still adds gradient sums
+        L->dens = take(pix);         // density of every image this rank sweeps, delivered by the image's owner
+        L->gfinal = take(pix);       // finished gradients, delivered to the image's owner
+    }
     L->total = (int64_t)off;
     L->tiles = count_rows;
     L->rows_per_thread = v.rows;
@@ -1133,7 +1273,7 @@ static T* at(const void* ws, int64_t off) { return reinterpret_cast<T*>((char*)w
 using namespace dgvcc;
 using namespace dgvcc::bl;
 
-extern "C" int dgvcc_abi_version(void) { return 7; }
+extern "C" int dgvcc_abi_version(void) { return 8; }
 
 extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                                          dgvcc_bl_layout* out) {
@@ -1162,21 +1302,33 @@ struct Plan {
     Scale k;
     Variant v;
     bool pow2;
-    dim3 grid;
+    dim3 grid;   // (CTAs per chunk, chunks this launch sweeps)
+    Shard sh;
 };
 
 int make_plan(const void* a, const void* b, const void* ws, size_t ws_bytes, int batch, int hp, int wp,
-              int64_t total_rows, int total_chunks, float stride, float sigma, Plan* p) {
+              int64_t total_rows, int total_chunks, float stride, float sigma, Plan* p,
+              const dgvcc_bl_shard* shard = nullptr) {
     if (!a || !b || !ws) return DGVCC_ERR_ARG;
     if (!(stride > 0.f) || !(sigma > 0.f)) return DGVCC_ERR_ARG;
-    int rc = layout(total_rows, total_chunks, batch, hp, wp, &p->L);
+    int rc = layout(total_rows, total_chunks, batch, hp, wp, &p->L, shard ? shard->world : 0);
     if (rc) return rc;
     if (ws_bytes < (size_t)p->L.total) return DGVCC_ERR_WORKSPACE;
     p->v = Variant{p->L.rows_per_thread, p->L.cols_per_thread};
     p->g = make_geom(hp, wp, p->v, stride);
     p->k = make_scale(sigma);
     p->pow2 = is_pow2(p->k.s);
-    p->grid = dim3(ceil_div(p->g.tiles, WARPS_PER_CTA), total_chunks);
+    p->sh = no_shard();
+    int slots = total_chunks;
+    if (shard) {
+        if (shard->world < 1 || shard->rank < 0 || shard->rank >= shard->world || shard->chunk_lo < 0 ||
+            shard->chunk_hi < shard->chunk_lo || shard->chunk_hi > total_chunks || shard->img_lo < 0 ||
+            shard->img_hi < shard->img_lo || shard->img_hi > batch)
+            return DGVCC_ERR_ARG;
+        p->sh = Shard{1, shard->chunk_lo, shard->chunk_hi, shard->pt_lo, shard->pt_hi, shard->img_lo, shard->img_hi};
+        slots = shard->chunk_hi - shard->chunk_lo;
+    }
+    p->grid = dim3(ceil_div(p->g.tiles, WARPS_PER_CTA), slots);
     return DGVCC_OK;
 }
 
@@ -1201,20 +1353,26 @@ int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const floa
     mark(events, 1, st);
     BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
                 exact_cull, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg),
-                at<unsigned int>(ws, p.L.ticket));
+                at<unsigned int>(ws, p.L.ticket), p.sh);
     mark(events, 2, st);
+    return (int)cudaGetLastError();
+}
+
+int launch_reduce_counts(const dgvcc_bl_layout& L, const float* targets, const int32_t* meta, int batch,
+                         int64_t total_rows, int tiles, void* ws, const Shard& sh, cudaStream_t st) {
+    bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
+        at<float>(ws, L.cpart), tiles, total_rows, meta, targets, batch, at<float>(ws, L.counts),
+        at<float>(ws, L.residual), sh);
     return (int)cudaGetLastError();
 }
 
 int launch_select(const dgvcc_bl_layout& L, const float* targets, const int32_t* meta, int batch,
                   int64_t total_rows, float inv_batch, int tiles, void* ws, float* loss_out, cudaStream_t st) {
-    bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
-        at<float>(ws, L.cpart), tiles, total_rows, meta, targets, batch, at<float>(ws, L.counts),
-        at<float>(ws, L.residual));
-    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    int rc = launch_reduce_counts(L, targets, meta, batch, total_rows, tiles, ws, no_shard(), st);
+    if (rc) return rc;
     bl_select_kernel<<<batch, SELECT_THREADS, 0, st>>>(
         meta, targets, batch, inv_batch, at<float>(ws, L.counts), at<float>(ws, L.residual), at<float>(ws, L.wsel),
-        at<float>(ws, L.loss_img), loss_out, at<unsigned int>(ws, L.ticket));
+        at<float>(ws, L.loss_img), loss_out, at<unsigned int>(ws, L.ticket), 0, 1);
     return (int)cudaGetLastError();
 }
 
@@ -1237,7 +1395,7 @@ extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targe
     BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
                 use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.zpart),
                 at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
-                at<float>(workspace, p.L.cpart));
+                at<float>(workspace, p.L.cpart), p.sh);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 3, st);
     rc = launch_select(p.L, targets, meta, batch, total_rows, inv_batch, p.L.tiles, workspace, loss_out, st);
@@ -1270,17 +1428,189 @@ extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int b
     BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
                 exact_cull, inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                 at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                grad_density);
+                grad_density, 0);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     if (multi_chunk) {
         const int M = hp * wp;
         bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, st>>>(
             meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart),
-            at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), grad_density);
+            at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), grad_density,
+            no_shard());
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     return DGVCC_OK;
 }
+
+// ------------------------------------------------------------------- point-chunk sharding: launch sequences
+namespace {
+
+struct ShardCtx {
+    const dgvcc_bl_shard* sh;
+    const dgvcc_bl_push* slices;  // device
+    char* const* peers;           // device array [world]
+    void* ws;
+    const dgvcc_bl_layout* L;
+    cudaStream_t st;
+};
+
+constexpr unsigned long long SHARD_WAIT_TIMEOUT_NS = 2000000000ull;  // 2 s
+
+// Phase `ph`: copy this rank's slices (sources relative to src_base, destinations relative to the peers' workspaces or
+// to dst_override) and raise the flags.
+int shard_push(const ShardCtx& c, int ph, const void* src_base, void* dst_override = nullptr) {
+    const int first = c.sh->push_first[ph], n = c.sh->push_first[ph + 1] - first;
+    if (n <= 0) return DGVCC_OK;
+    if (!dst_override) {
+        bl_push_kernel<<<n, PUSH_THREADS, 0, c.st>>>(c.slices + first, n, (const char*)src_base, c.peers, c.L->flags, ph,
+                                                     c.sh->rank, c.sh->world, c.sh->signal_mask[ph], c.sh->epoch,
+                                                     at<unsigned int>(c.ws, c.L->push_ticket));
+    } else {
+        bl_copy_kernel<<<n, PUSH_THREADS, 0, c.st>>>(c.slices + first, n, (const char*)src_base, (char*)dst_override);
+    }
+    return (int)cudaGetLastError();
+}
+
+int shard_wait(const ShardCtx& c, int ph) {
+    if (!c.sh->wait_mask[ph]) return DGVCC_OK;
+    bl_wait_kernel<<<1, 32, 0, c.st>>>(at<unsigned int>(c.ws, c.L->flags), ph, c.sh->world, c.sh->wait_mask[ph],
+                                       c.sh->epoch, SHARD_WAIT_TIMEOUT_NS, at<int>(c.ws, c.L->err));
+    return (int)cudaGetLastError();
+}
+
+bool shard_args_ok(const dgvcc_bl_shard* sh, const dgvcc_bl_push* slices, void* const* peers) {
+    if (!sh || !peers) return false;
+    for (int ph = 0; ph < DGVCC_BL_PHASES; ++ph)
+        if (sh->push_first[ph + 1] < sh->push_first[ph]) return false;
+    return sh->push_first[DGVCC_BL_PHASES] == 0 || slices != nullptr;
+}
+
+}  // namespace
+
+extern "C" int dgvcc_bl_shard_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, int world,
+                                               dgvcc_bl_layout* out) {
+    if (world < 1) return DGVCC_ERR_ARG;
+    return layout(total_rows, total_chunks, batch, hp, wp, out, world);
+}
+
+extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets, const int32_t* meta,
+                                      const float* st_sizes, const float* density_local, int batch, int hp, int wp,
+                                      int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
+                                      float bg_ratio, int use_bg, int exact_cull, float inv_batch,
+                                      const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
+                                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
+    if (!shard_args_ok(shard, slices, peers)) return DGVCC_ERR_ARG;
+    Plan p;
+    int rc = make_plan(meta, st_sizes, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride, sigma,
+                       &p, shard);
+    if (rc) return rc;
+    if (!loss_out || !pts_xy || !targets) return DGVCC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ShardCtx c{shard, slices, (char* const*)peers, workspace, &p.L, st};
+    const float2* pts = (const float2*)pts_xy;
+    const bool sweeps = p.grid.y > 0;
+    // density of the images this rank owns -> every rank that sweeps them (needed from bl_counts on)
+    if ((rc = shard_push(c, DGVCC_BL_PH_DENS, density_local))) return rc;
+    // per-chunk minima of the images cut into several chunks
+    if (sweeps && multi_chunk) {
+        float* minpart = at<float>(workspace, p.L.minpart);
+        if (p.v.rows == 8 && p.v.cols == 2) bl_min_kernel<8, 2><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
+        else if (p.v.rows == 8) bl_min_kernel<8, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
+        else if (p.v.rows == 4) bl_min_kernel<4, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
+        else bl_min_kernel<2, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    if ((rc = shard_push(c, DGVCC_BL_PH_MIN, workspace))) return rc;
+    if ((rc = shard_wait(c, DGVCC_BL_PH_MIN))) return rc;
+    if (sweeps) {
+        BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
+                    at<float>(workspace, p.L.minpart), at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
+                    at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    if ((rc = shard_push(c, DGVCC_BL_PH_Z, workspace))) return rc;
+    if ((rc = shard_wait(c, DGVCC_BL_PH_Z))) return rc;
+    if ((rc = shard_wait(c, DGVCC_BL_PH_DENS))) return rc;
+    if (sweeps) {
+        BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
+                    use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
+                    at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
+                    at<float>(workspace, p.L.cpart), p.sh);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+        if ((rc = launch_reduce_counts(p.L, targets, meta, batch, total_rows, p.L.tiles, workspace, p.sh, st))) return rc;
+    }
+    if ((rc = shard_push(c, DGVCC_BL_PH_CNT, workspace))) return rc;
+    if ((rc = shard_wait(c, DGVCC_BL_PH_CNT))) return rc;
+    if (p.sh.img_hi > p.sh.img_lo) {
+        bl_select_kernel<<<p.sh.img_hi - p.sh.img_lo, SELECT_THREADS, 0, st>>>(
+            meta, targets, batch, inv_batch, at<float>(workspace, p.L.counts), at<float>(workspace, p.L.residual),
+            at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.loss_img), loss_out,
+            at<unsigned int>(workspace, p.L.ticket), p.sh.img_lo, 0);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    if ((rc = shard_push(c, DGVCC_BL_PH_LOSS, workspace))) return rc;
+    if ((rc = shard_wait(c, DGVCC_BL_PH_LOSS))) return rc;
+    bl_loss_finish_kernel<<<1, 32, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp,
+                                       int64_t total_rows, int total_chunks, float stride, float sigma, int use_bg,
+                                       int exact_cull, float inv_batch, const float* grad_loss,
+                                       const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
+                                       void* workspace, size_t workspace_bytes, float* grad_local, void* stream) {
+    DGVCC_DEVICE_GUARD(stream);
+    if (!shard_args_ok(shard, slices, peers)) return DGVCC_ERR_ARG;
+    Plan p;
+    int rc = make_plan(meta, grad_loss, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride, sigma,
+                       &p, shard);
+    if (rc) return rc;
+    if (!pts_xy) return DGVCC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ShardCtx c{shard, slices, (char* const*)peers, workspace, &p.L, st};
+    const int M = hp * wp;
+    if (p.grid.y > 0) {  // raw per-chunk gradient sums, every image (the rank with an image's first chunk finishes it)
+        BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
+                    inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
+                    at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
+                    at<float>(workspace, p.L.gfinal), 1);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    if ((rc = shard_push(c, DGVCC_BL_PH_GPART, workspace))) return rc;
+    if ((rc = shard_wait(c, DGVCC_BL_PH_GPART))) return rc;
+    if (p.sh.img_hi > p.sh.img_lo) {
+        bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), p.sh.img_hi - p.sh.img_lo), 256, 0, st>>>(
+            meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart), at<float>(workspace, p.L.rz),
+            at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gfinal), p.sh);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    if ((rc = shard_push(c, DGVCC_BL_PH_GRAD, workspace))) return rc;
+    if ((rc = shard_wait(c, DGVCC_BL_PH_GRAD))) return rc;
+    // the finished gradients of this rank's own images, gathered into the caller's tensor
+    if (shard->push_first[DGVCC_BL_PH_OUT + 1] > shard->push_first[DGVCC_BL_PH_OUT] && !grad_local) return DGVCC_ERR_ARG;
+    return shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local);
+}
+
+// ------------------------------------------------------------------- peer memory (CUDA IPC) for the sharded path
+extern "C" int dgvcc_peer_alloc(size_t bytes, void** ptr) {
+    if (!ptr || bytes == 0) return DGVCC_ERR_ARG;
+    DGVCC_RETURN_IF_CUDA(cudaMalloc(ptr, bytes));
+    DGVCC_RETURN_IF_CUDA(cudaMemset(*ptr, 0, bytes));
+    return (int)cudaDeviceSynchronize();
+}
+extern "C" int dgvcc_peer_free(void* ptr) { return ptr ? (int)cudaFree(ptr) : DGVCC_OK; }
+extern "C" int dgvcc_peer_export(void* ptr, unsigned char* handle64) {
+    if (!ptr || !handle64) return DGVCC_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    return (int)cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), ptr);
+}
+extern "C" int dgvcc_peer_open(const unsigned char* handle64, void** ptr) {
+    if (!ptr || !handle64) return DGVCC_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+extern "C" int dgvcc_peer_close(void* ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : DGVCC_OK; }
 
 extern "C" int dgvcc_bl_posterior(const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
                                   int hp, int wp, int64_t total_rows, int total_chunks, int multi_chunk,

@@ -87,6 +87,12 @@ typedef struct dgvcc_bl_layout {
     int64_t minpart;   /* [C*hp*wp] f32  per-chunk min squared distance              */
     int64_t gpart;     /* [C*hp*wp] f32  per-chunk gradient sums (aliases minpart)   */
     int64_t total;     /* bytes needed                                               */
+    /* regions of the symmetric (sharded) layout only, 0 otherwise -- dgvcc_bl_shard_workspace_layout */
+    int64_t dens;      /* [B*hp*wp] f32  density of the images this rank sweeps      */
+    int64_t gfinal;    /* [B*hp*wp] f32  finished gradients, at the image's owner    */
+    int64_t flags;     /* [PHASES*world] u32 arrival flags (phase, source rank)      */
+    int64_t err;       /* [1] i32        non-zero: a wait timed out (1 + phase + 16*source) */
+    int64_t push_ticket; /* [1] u32                                                  */
     int32_t tiles;     /* partial-count rows (CTAs of 4 pixel tiles) per point chunk */
     int32_t rows_per_thread; /* kernel variant chosen for this shape: grid rows ...   */
     int32_t cols_per_thread; /* ... and columns owned by one thread                  */
@@ -144,6 +150,70 @@ int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta, int batch,
                               int64_t total_rows, float inv_batch, const float* grad_loss,
                               const void* workspace, size_t workspace_bytes,
                               float* grad_density, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Bayesian loss, ONE batch spread over the GPUs of a box by point chunks (strong scaling of BASELINE config 3;
+ * SURVEY.md 8e).  The reference's unit of independence is the image (losses/bl.py:36,62); an image with 12 000 heads
+ * is a quarter of the 16-image batch, so whole-image partitioning stops at 4x on 8 GPUs.  Here the packed point
+ * sequence of the batch (bl.py:21-22) is cut into `world` equal contiguous spans; rank r sweeps the chunks of its
+ * span over all pixels of the images they belong to, and what an image's other ranks need travels as plain stores
+ * into their workspaces over NVLink (peer pointers from dgvcc_peer_open), one arrival flag per (phase, source):
+ *   DENS   density of an image, owner -> every rank that sweeps it          (before the expected counts)
+ *   MIN    per-chunk minima (bl.py:39), Z per-chunk denominator shares (bl.py:44)   among the image's ranks
+ *   CNT    expected counts + residuals of a rank's rows (bl.py:73-75)        among the image's ranks (top-k needs all)
+ *   LOSS   per-image loss, from the rank with the image's first chunk to everybody (summed in image order, bl.py:79)
+ *   GPART  per-chunk gradient sums -> the rank with the image's first chunk, which finishes the gradient
+ *   GRAD   finished gradient -> the image's owner;  OUT: local gather into the caller's tensor
+ * Receivers combine partials in chunk order exactly like dgvcc_bl_forward / _backward, so loss and gradients are
+ * bit-identical to the single-GPU call.  No NCCL on the data path.
+ *
+ * All ranks pass the SAME packed points / targets / st_sizes and the same chunk table (the schedule column lists
+ * the rank's own chunk ids in its first chunk_hi - chunk_lo slots); density_local / grad_local hold only the
+ * images the rank owns, in the order of the DENS / OUT slices.  `slices` is a DEVICE array, `peers` a DEVICE array of
+ * `world` workspace base pointers (own pointer at [rank]); every workspace has dgvcc_bl_shard_workspace_layout.
+ * `epoch` must grow by one per forward/backward pair (flags are compared against it); workspaces start zeroed.
+ * A wait that sees no flag within 2 s records 1 + phase + 16 * source in the workspace's `err` word and moves on.
+ * ------------------------------------------------------------------------- */
+#define DGVCC_BL_PHASES 8
+enum { DGVCC_BL_PH_DENS = 0, DGVCC_BL_PH_MIN, DGVCC_BL_PH_Z, DGVCC_BL_PH_CNT, DGVCC_BL_PH_LOSS, DGVCC_BL_PH_GPART,
+       DGVCC_BL_PH_GRAD, DGVCC_BL_PH_OUT };
+typedef struct dgvcc_bl_push {
+    int64_t src_off;   /* bytes from the phase's source base (own workspace; density_local for DENS) */
+    int64_t dst_off;   /* bytes from the destination rank's workspace (grad_local for OUT)            */
+    int32_t bytes;     /* multiple of 4                                                              */
+    int32_t dst_rank;
+} dgvcc_bl_push;
+typedef struct dgvcc_bl_shard {
+    int32_t rank, world;
+    int32_t chunk_lo, chunk_hi;   /* chunk ids this rank sweeps                         */
+    int32_t pt_lo, pt_hi;         /* = packed points [pt_lo, pt_hi)                     */
+    int32_t img_lo, img_hi;       /* images it touches                                  */
+    int32_t push_first[DGVCC_BL_PHASES + 1];   /* slices of phase p: [push_first[p], push_first[p+1]) */
+    uint32_t wait_mask[DGVCC_BL_PHASES];       /* ranks whose flag of phase p this rank waits for     */
+    uint32_t signal_mask[DGVCC_BL_PHASES];     /* ranks this rank signals after its slices of phase p */
+    uint32_t epoch;
+    int32_t reserved_;
+} dgvcc_bl_shard;
+int dgvcc_bl_shard_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, int world,
+                                    dgvcc_bl_layout* out);
+int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets, const int32_t* meta, const float* st_sizes,
+                           const float* density_local, int batch, int hp, int wp, int64_t total_rows, int total_chunks,
+                           int multi_chunk, float stride, float sigma, float bg_ratio, int use_bg, int exact_cull,
+                           float inv_batch, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
+                           void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
+int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp, int64_t total_rows,
+                            int total_chunks, float stride, float sigma, int use_bg, int exact_cull, float inv_batch,
+                            const float* grad_loss, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices,
+                            void* const* peers, void* workspace, size_t workspace_bytes, float* grad_local, void* stream);
+
+/* Peer-visible device memory for the sharded workspaces (CUDA IPC between the ranks' processes of one box):
+ * alloc = cudaMalloc + zero fill; export writes the 64-byte handle a peer process passes to open, which maps the
+ * memory into the calling process and enables peer access to the owning GPU. */
+int dgvcc_peer_alloc(size_t bytes, void** ptr);
+int dgvcc_peer_free(void* ptr);
+int dgvcc_peer_export(void* ptr, unsigned char* handle64);
+int dgvcc_peer_open(const unsigned char* handle64, void** ptr);
+int dgvcc_peer_close(void* ptr);
 
 /* ---------------------------------------------------------------------------
  * Density-map generation -- replaces utils/dmap_gen.py:14-51 (gaussian_filter_density)

@@ -1,0 +1,115 @@
+"""Point-chunk sharding of the Bayesian loss (dgvcc_b200/losses/bl_sharded.py) on ONE GPU: `world` ranks run inside
+this process, one CUDA stream each, exchanging partials through the same kernels, flags and phase order as one process
+per GPU does over NVLink (LocalComm: plain pointers instead of CUDA IPC mappings).
+
+Gates: loss and every owner's gradient BIT-IDENTICAL to one GPU running the same chunk table through
+dgvcc_bl_forward / _backward (the exchange must not change a bit), and within the usual rtol 1e-5 of the CPU oracle.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from dgvcc_b200 import synthetic
+from oracle import bl_oracle
+from helpers import assert_close, load_bl_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def single_gpu_with_table(plan, points, targets, st, dens, stride, sigma, bg_ratio, use_bg, cull):
+    """One GPU, the plan's chunk table, the ordinary fused path."""
+    from dgvcc_b200.losses import bl as blmod
+    dev = torch.device("cuda:0")
+    packed = types.SimpleNamespace(
+        pts=torch.cat([p.reshape(-1, 2) for p in points]).to(dev) if plan.total_points else torch.zeros((1, 2), device=dev),
+        meta=torch.from_numpy(plan.meta_all()).to(dev), total_rows=plan.total_rows, total_chunks=plan.total_chunks,
+        multi_chunk=plan.multi_chunk, batch=plan.batch)
+    tg = torch.cat([t.reshape(-1) for t in targets]).to(dev) if plan.total_points else torch.zeros((1,), device=dev)
+    d = dens.to(dev).clone().requires_grad_(True)
+    loss = blmod._FusedBL.apply(d, packed, tg, st.to(dev), float(stride), float(sigma), float(bg_ratio), bool(use_bg),
+                                1.0 / plan.batch, None, cull)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), d.grad.cpu()
+
+
+def run_sharded(world, points, targets, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners=None, steps=1):
+    from dgvcc_b200.losses.bl_sharded import ChunkShardedBL, LocalComm, plan_shards
+    dev = torch.device("cuda:0")
+    b, _, hp, wp = dens.shape
+    comms = LocalComm.make(world, dev, nbytes=192 << 20)
+    plan = plan_shards([len(p) for p in points], use_bg, world, owners, hp, wp)
+    mods = [ChunkShardedBL(sigma, max(hp, wp) * stride, stride, bg_ratio, use_bg, dev, c) for c in comms]
+    for m in mods:
+        m.exact_cull = cull
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    st_d = st.to(dev)
+    locals_ = [dens[plan.owned[r]].to(dev).clone().requires_grad_(True) for r in range(world)]
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        losses = []
+        for r in range(world):
+            locals_[r].grad = None
+            with torch.cuda.stream(streams[r]):
+                losses.append(mods[r](points, st_d, targets, locals_[r], owners))
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                losses[r].backward()
+        for m in mods:
+            m.check()
+    grad = torch.zeros_like(dens)
+    for r in range(world):
+        if len(plan.owned[r]):
+            grad[plan.owned[r]] = locals_[r].grad.cpu()
+    return [l.detach().cpu() for l in losses], grad, plan
+
+
+def _case(name):
+    if name.startswith("config"):
+        cfg = int(name[-1])
+        w, h = synthetic.CONFIG_SHAPES[cfg]
+        counts = synthetic.config_counts(cfg)
+        pts, tgt, dens, st = synthetic.bl_batch(cfg, counts, w, h, 8)
+        return ([torch.from_numpy(p) for p in pts], [torch.from_numpy(t) for t in tgt], torch.from_numpy(st),
+                torch.from_numpy(dens), 8, 8.0, 1.0, True)
+    c = load_bl_golden(name)
+    return c["points"], c["targets"], c["st_sizes"], c["density"], c["stride"], c["sigma"], c["bg_ratio"], c["use_bg"]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("name", ["mixed", "nobg", "empty", "outside", "config2"])
+def test_sharded_ranks_reproduce_one_gpu_bit_for_bit(name, world, monkeypatch):
+    monkeypatch.setattr("dgvcc_b200.losses.bl._CHUNK_POINTS", 1024 if name == "config2" else 29)
+    pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = _case(name)
+    owners = [(3 * i + 1) % world for i in range(len(pts))]          # density owners unrelated to where the points fall
+    for cull in (False, True):
+        losses, grad, plan = run_sharded(world, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners, steps=2)
+        ref_loss, ref_grad = single_gpu_with_table(plan, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull)
+        for r, l in enumerate(losses):
+            assert torch.equal(l, ref_loss), f"loss on rank {r}: {float(l)!r} vs {float(ref_loss)!r}"
+        assert torch.equal(grad, ref_grad), f"gradient differs in {int((grad != ref_grad).sum())} pixels"
+    o_loss, o_grad, _ = bl_oracle.bl_forward_backward(pts, st, tgt, dens, stride, sigma, bg_ratio, use_bg)
+    assert_close(losses[0], o_loss, 1e-5, 0, "sharded loss vs oracle")
+    assert_close(grad, o_grad, 1e-5, 1e-6 * float(o_grad.abs().max()), "sharded gradient vs oracle")
+
+
+def test_config3_batch_on_four_emulated_ranks():
+    """BASELINE config 3 (16 images, 49 697 heads): the 12 000-head image is spread over several ranks."""
+    pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = _case("config3")
+    losses, grad, plan = run_sharded(4, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, False)
+    assert max(len(g) for g in plan.groups) >= 2
+    per_rank = [int(plan.c_cnt[plan.chunk_lo[r]:plan.chunk_hi[r]].sum()) for r in range(4)]
+    assert max(per_rank) - min(per_rank) <= 1
+    ref_loss, ref_grad = single_gpu_with_table(plan, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, False)
+    assert all(torch.equal(l, ref_loss) for l in losses) and torch.equal(grad, ref_grad)
+    from dgvcc_b200.losses.bl import BL
+    dev = torch.device("cuda:0")
+    d = dens.to(dev).requires_grad_(True)
+    mod = BL(sigma, 2048, stride, bg_ratio, use_bg, dev)
+    l1 = mod([p.to(dev) for p in pts], st.to(dev), [t.to(dev) for t in tgt], d)
+    l1.backward()
+    # against the ordinary single-GPU module (another chunk table: other summation order of the chunk partials)
+    assert_close(losses[0], l1.detach().cpu(), 2e-6, 0, "sharded vs BL loss")
+    assert_close(grad, d.grad.cpu(), 1e-5, 1e-6 * float(d.grad.abs().max()), "sharded vs BL gradient")

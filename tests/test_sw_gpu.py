@@ -42,7 +42,7 @@ class FakeExchange:
 def build(c, exchange=None):
     from dgvcc_b200.models.ISW.switchwhiten import SwitchWhiten2d
     from dgvcc_b200.models.ISW.sync_switchwhiten import SyncSwitchWhiten2d
-    cls = SwitchWhiten2d if c["kind"] == "plain" else SyncSwitchWhiten2d
+    cls = SwitchWhiten2d if c.get("kind", "plain") == "plain" else SyncSwitchWhiten2d
     m = cls(c["x"].shape[1], num_pergroup=c["num_pergroup"], sw_type=c["sw_type"], tie_weight=c["tie"],
                        affine=c["affine"]).cuda()
     with torch.no_grad():

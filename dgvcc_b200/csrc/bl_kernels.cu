@@ -1486,6 +1486,36 @@ bool shard_args_ok(const dgvcc_bl_shard* sh, const dgvcc_bl_push* slices, void* 
 
 }  // namespace
 
+// CUDA loads kernels lazily, and loading one can wait for the kernels already running in the context: a rank's wait
+// kernel spinning on a flag while the kernel that would raise it is still being loaded is a deadlock when several
+// ranks share one context (LocalComm), and a stall of the first step otherwise.  Called once per communicator.
+extern "C" int dgvcc_bl_shard_preload(void) {
+    cudaFuncAttributes a;
+#define BL_PRELOAD(K) DGVCC_RETURN_IF_CUDA(cudaFuncGetAttributes(&a, K))
+#define BL_PRELOAD_RC(R_, C_)                     \
+    BL_PRELOAD((bl_min_kernel<R_, C_>));          \
+    BL_PRELOAD((bl_z_kernel<R_, C_, true>));      \
+    BL_PRELOAD((bl_z_kernel<R_, C_, false>));     \
+    BL_PRELOAD((bl_counts_kernel<R_, C_, true>)); \
+    BL_PRELOAD((bl_counts_kernel<R_, C_, false>));\
+    BL_PRELOAD((bl_grad_kernel<R_, C_, true>));   \
+    BL_PRELOAD((bl_grad_kernel<R_, C_, false>))
+    BL_PRELOAD_RC(8, 2);
+    BL_PRELOAD_RC(8, 1);
+    BL_PRELOAD_RC(4, 1);
+    BL_PRELOAD_RC(2, 1);
+    BL_PRELOAD(bl_reduce_counts_kernel);
+    BL_PRELOAD(bl_select_kernel);
+    BL_PRELOAD(bl_grad_reduce_kernel);
+    BL_PRELOAD(bl_push_kernel);
+    BL_PRELOAD(bl_copy_kernel);
+    BL_PRELOAD(bl_wait_kernel);
+    BL_PRELOAD(bl_loss_finish_kernel);
+#undef BL_PRELOAD_RC
+#undef BL_PRELOAD
+    return DGVCC_OK;
+}
+
 extern "C" int dgvcc_bl_shard_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, int world,
                                                dgvcc_bl_layout* out) {
     if (world < 1) return DGVCC_ERR_ARG;

@@ -256,6 +256,8 @@ class IpcComm:
         self._finish()
 
     def _finish(self):
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().dgvcc_bl_shard_preload(), "dgvcc_bl_shard_preload")
         self.workspace = _as_tensor(self.ptrs[self.rank], self.nbytes, self.device)
         self.peer_table = torch.tensor(self.ptrs, dtype=torch.int64, device=self.device)
         self.epoch = 0

@@ -196,6 +196,9 @@ typedef struct dgvcc_bl_shard {
 } dgvcc_bl_shard;
 int dgvcc_bl_shard_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, int world,
                                     dgvcc_bl_layout* out);
+/* Loads every kernel of the sharded path into the current context (cudaFuncGetAttributes): CUDA loads kernels lazily
+ * and a load can wait for running kernels -- such as a peer's wait kernel.  Call once per process / communicator. */
+int dgvcc_bl_shard_preload(void);
 int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets, const int32_t* meta, const float* st_sizes,
                            const float* density_local, int batch, int hp, int wp, int64_t total_rows, int total_chunks,
                            int multi_chunk, float stride, float sigma, float bg_ratio, int use_bg, int exact_cull,

@@ -45,6 +45,10 @@ def run_sharded(world, points, targets, st, dens, stride, sigma, bg_ratio, use_b
     for m in mods:
         m.exact_cull = cull
     streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    # torch's own kernels are loaded lazily too: run the ones a step uses once before any wait kernel can be spinning
+    warm = torch.zeros((2, 1, hp, wp), device=dev, requires_grad=True)
+    (warm * 2.0).sum().backward()
+    warm.grad.clone().to(torch.float32).contiguous()
     st_d = st.to(dev)
     locals_ = [dens[plan.owned[r]].to(dev).clone().requires_grad_(True) for r in range(world)]
     torch.cuda.synchronize()

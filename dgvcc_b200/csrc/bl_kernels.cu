@@ -1527,7 +1527,8 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
                                       int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
                                       float bg_ratio, int use_bg, int exact_cull, float inv_batch,
                                       const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
-                                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream) {
+                                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
+                                      void** events) {
     DGVCC_DEVICE_GUARD(stream);
     if (!shard_args_ok(shard, slices, peers)) return DGVCC_ERR_ARG;
     Plan p;
@@ -1539,6 +1540,7 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
     const ShardCtx c{shard, slices, (char* const*)peers, workspace, &p.L, st};
     const float2* pts = (const float2*)pts_xy;
     const bool sweeps = p.grid.y > 0;
+    mark(events, 0, st);
     // density of the images this rank owns -> every rank that sweeps them (needed from bl_counts on)
     if ((rc = shard_push(c, DGVCC_BL_PH_DENS, density_local))) return rc;
     // per-chunk minima of the images cut into several chunks
@@ -1550,17 +1552,21 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         else bl_min_kernel<2, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    mark(events, 1, st);
     if ((rc = shard_push(c, DGVCC_BL_PH_MIN, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_MIN))) return rc;
+    mark(events, 2, st);
     if (sweeps) {
         BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
                     at<float>(workspace, p.L.minpart), at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
                     at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    mark(events, 3, st);
     if ((rc = shard_push(c, DGVCC_BL_PH_Z, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_Z))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_DENS))) return rc;
+    mark(events, 4, st);
     if (sweeps) {
         BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
                     use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
@@ -1569,8 +1575,10 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
         if ((rc = launch_reduce_counts(p.L, targets, meta, batch, total_rows, p.L.tiles, workspace, p.sh, st))) return rc;
     }
+    mark(events, 5, st);
     if ((rc = shard_push(c, DGVCC_BL_PH_CNT, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_CNT))) return rc;
+    mark(events, 6, st);
     if (p.sh.img_hi > p.sh.img_lo) {
         bl_select_kernel<<<p.sh.img_hi - p.sh.img_lo, SELECT_THREADS, 0, st>>>(
             meta, targets, batch, inv_batch, at<float>(workspace, p.L.counts), at<float>(workspace, p.L.residual),
@@ -1578,9 +1586,11 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
             at<unsigned int>(workspace, p.L.ticket), p.sh.img_lo, 0);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    mark(events, 7, st);
     if ((rc = shard_push(c, DGVCC_BL_PH_LOSS, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_LOSS))) return rc;
     bl_loss_finish_kernel<<<1, 32, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out);
+    mark(events, 8, st);
     return (int)cudaGetLastError();
 }
 
@@ -1588,7 +1598,8 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
                                        int64_t total_rows, int total_chunks, float stride, float sigma, int use_bg,
                                        int exact_cull, float inv_batch, const float* grad_loss,
                                        const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
-                                       void* workspace, size_t workspace_bytes, float* grad_local, void* stream) {
+                                       void* workspace, size_t workspace_bytes, float* grad_local, void* stream,
+                                       void** events) {
     DGVCC_DEVICE_GUARD(stream);
     if (!shard_args_ok(shard, slices, peers)) return DGVCC_ERR_ARG;
     Plan p;
@@ -1599,6 +1610,7 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
     cudaStream_t st = (cudaStream_t)stream;
     const ShardCtx c{shard, slices, (char* const*)peers, workspace, &p.L, st};
     const int M = hp * wp;
+    mark(events, 0, st);
     if (p.grid.y > 0) {  // raw per-chunk gradient sums, every image (the rank with an image's first chunk finishes it)
         BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
                     inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
@@ -1606,19 +1618,25 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
                     at<float>(workspace, p.L.gfinal), 1);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    mark(events, 1, st);
     if ((rc = shard_push(c, DGVCC_BL_PH_GPART, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_GPART))) return rc;
+    mark(events, 2, st);
     if (p.sh.img_hi > p.sh.img_lo) {
         bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), p.sh.img_hi - p.sh.img_lo), 256, 0, st>>>(
             meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart), at<float>(workspace, p.L.rz),
             at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gfinal), p.sh);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    mark(events, 3, st);
     if ((rc = shard_push(c, DGVCC_BL_PH_GRAD, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_GRAD))) return rc;
     // the finished gradients of this rank's own images, gathered into the caller's tensor
     if (shard->push_first[DGVCC_BL_PH_OUT + 1] > shard->push_first[DGVCC_BL_PH_OUT] && !grad_local) return DGVCC_ERR_ARG;
-    return shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local);
+    mark(events, 4, st);
+    rc = shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local);
+    mark(events, 5, st);
+    return rc;
 }
 
 // ------------------------------------------------------------------- peer memory (CUDA IPC) for the sharded path

@@ -199,11 +199,19 @@ class ShardPlan:
 _plan_cache = {}
 
 
+def shard_chunk_points(total_points, world):
+    """Points per chunk for a batch spread over ``world`` ranks: small enough that ONE rank still has ~28 chunks x 96
+    pixel tiles = enough warp tasks to fill its 148 SMs with the large (8 x 2) pixel tile, never above the single-GPU
+    chunk size, a multiple of 32."""
+    want = max(1, total_points // (max(world, 1) * 30))
+    return int(min(_bl.chunk_points(), max(128, -(-want // 32) * 32)))
+
+
 def plan_shards(counts, use_bg, world, owners, hp, wp, chunk=None):
     """Cached ``ShardPlan`` (a training loop sees few distinct count tuples per epoch only in benchmarks, but the
     plan of the previous step is the common hit: forward and backward of one step share it)."""
     key = (tuple(int(c) for c in counts), bool(use_bg), int(world), None if owners is None else tuple(int(o) for o in owners),
-           int(hp), int(wp), int(chunk or _bl.chunk_points()))
+           int(hp), int(wp), int(chunk or shard_chunk_points(sum(int(c) for c in counts), world)))
     plan = _plan_cache.get(key)
     if plan is None:
         if len(_plan_cache) > 64:
@@ -302,7 +310,8 @@ class _ShardedFn(torch.autograd.Function):
             _native.ptr(packed.pts), _native.ptr(packed.targets), _native.ptr(packed.meta), _native.ptr(st), _native.ptr(dens),
             plan.batch, hp, wp, plan.total_rows, plan.total_chunks, plan.multi_chunk, float(pp.stride), float(pp.sigma),
             float(pp.bg_ratio), int(pp.use_bg), int(mod.exact_cull), inv_batch, ctypes.byref(shard), _native.ptr(slices),
-            _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), _native.stream_ptr(dev))
+            _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), _native.stream_ptr(dev),
+            mod._event_handles("fwd", 9))
         _native.check(rc, "dgvcc_bl_shard_forward")
         ctx.saved = (mod, plan, packed, slices, inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own)
         return loss.reshape(())
@@ -323,7 +332,8 @@ class _ShardedFn(torch.autograd.Function):
             _native.ptr(packed.pts), _native.ptr(packed.meta), plan.batch, plan.hp, plan.wp, plan.total_rows,
             plan.total_chunks, float(pp.stride), float(pp.sigma), int(pp.use_bg), int(mod.exact_cull), inv_batch,
             _native.ptr(g), ctypes.byref(shard), _native.ptr(slices), _native.ptr(comm.peer_table),
-            _native.ptr(comm.workspace), comm.nbytes, _native.ptr(grad), _native.stream_ptr(dev))
+            _native.ptr(comm.workspace), comm.nbytes, _native.ptr(grad), _native.stream_ptr(dev),
+            mod._event_handles("bwd", 6))
         _native.check(rc, "dgvcc_bl_shard_backward")
         return (grad[:n_own].reshape(shape).to(dtype),) + (None,) * 5
 
@@ -380,6 +390,31 @@ class ChunkShardedBL(Module):
             self._last = (key, packed, points, target_list)   # the lists are kept alive so that the ids stay meaningful
         st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()
         return _ShardedFn.apply(pre_density_local, self, plan, packed, st, 1.0 / plan.batch)
+
+    FWD_PHASES = ["min", "push+wait MIN", "z", "push+wait Z, wait DENS", "counts+reduce", "push+wait CNT", "select",
+                  "push+wait LOSS + loss"]
+    BWD_PHASES = ["grad", "push+wait GPART", "reduce", "push+wait GRAD", "gather"]
+
+    def _event_handles(self, which, n):
+        """None, or ctypes array of cudaEvent_t for the per-phase timing (``profile = True``)."""
+        if not getattr(self, "profile", False):
+            return None
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        for e in evs:
+            e.record()  # materialises the handle
+        self._events = getattr(self, "_events", {})
+        self._events[which] = evs
+        return (ctypes.c_void_p * n)(*[e.cuda_event for e in evs])
+
+    def phase_ms(self):
+        """{phase: ms} of the last profiled step (synchronises)."""
+        torch.cuda.synchronize(self.comm.device)
+        out = {}
+        for which, names in (("fwd", self.FWD_PHASES), ("bwd", self.BWD_PHASES)):
+            evs = self._events[which]
+            for k, name in enumerate(names):
+                out[f"{which}: {name}"] = evs[k].elapsed_time(evs[k + 1])
+        return out
 
     def check(self):
         """Synchronise and raise if a wait of the exchange protocol timed out (a peer died or fell out of step)."""

@@ -203,11 +203,17 @@ int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets, const int3
                            const float* density_local, int batch, int hp, int wp, int64_t total_rows, int total_chunks,
                            int multi_chunk, float stride, float sigma, float bg_ratio, int use_bg, int exact_cull,
                            float inv_batch, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
-                           void* workspace, size_t workspace_bytes, float* loss_out, void* stream);
+                           void* workspace, size_t workspace_bytes, float* loss_out, void* stream, void** events);
 int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp, int64_t total_rows,
                             int total_chunks, float stride, float sigma, int use_bg, int exact_cull, float inv_batch,
                             const float* grad_loss, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices,
-                            void* const* peers, void* workspace, size_t workspace_bytes, float* grad_local, void* stream);
+                            void* const* peers, void* workspace, size_t workspace_bytes, float* grad_local, void* stream,
+                            void** events);
+/* `events` (NULL, or caller-created cudaEvent_t handles; NULL entries skipped) are recorded on the stream between the
+ * phases, for per-phase timing.  forward: [0] start, [1] after the minima, [2] after push+wait MIN, [3] after bl_z,
+ * [4] after push+wait Z and wait DENS, [5] after counts + reduce, [6] after push+wait CNT, [7] after the selection,
+ * [8] after push+wait LOSS and the loss.  backward: [0] start, [1] after bl_grad, [2] after push+wait GPART,
+ * [3] after the reduction, [4] after push+wait GRAD, [5] after the gather. */
 
 /* Peer-visible device memory for the sharded workspaces (CUDA IPC between the ranks' processes of one box):
  * alloc = cudaMalloc + zero fill; export writes the 64-byte handle a peer process passes to open, which maps the

@@ -60,7 +60,7 @@ def main():
 
     ok_all = True
     for name, chunk in (("mixed", 29), ("config2", 1024), ("config3", 1024)):
-        blmod._CHUNK_POINTS = chunk
+        blmod._CHUNK_POINTS = chunk   # upper bound; the sharded plan picks smaller chunks for larger worlds
         pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = case(name)
         b, _, hp, wp = dens.shape
         plan = plan_shards([len(p) for p in pts], use_bg, world, None, hp, wp)
@@ -118,9 +118,23 @@ def main():
     allms = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(allms, torch.tensor([ms], device=dev, dtype=torch.float64))
     allms = [float(x[0]) for x in allms]
+    # per-phase device times (CUDA events recorded between the launches), averaged over a few steps
+    mod.profile = True
+    acc = {}
+    for _ in range(5):
+        step()
+        for k, v in mod.phase_ms().items():
+            acc[k] = acc.get(k, 0.0) + v / 5
+        flush.zero_()
+    mod.profile = False
+    phases = [None] * world
+    dist.all_gather_object(phases, acc)
     if rank == 0:
+        out["phase_ms_rank0"] = {k: round(v, 4) for k, v in phases[0].items()}
+        out["phase_ms_max_over_ranks"] = {k: round(max(p[k] for p in phases), 4) for k in phases[0]}
+        out["phase_sum_ms_per_rank"] = [round(sum(p.values()), 4) for p in phases]
         out.update({"config3_ms_per_rank": allms, "config3_ms_per_step": max(allms), "images_per_s": b / (max(allms) * 1e-3),
-                    "chunks": plan.total_chunks, "groups": [len(g) for g in plan.groups], "ok": ok_all})
+                    "chunks": plan.total_chunks, "chunk_points": int(plan.c_cnt.max()), "groups": [len(g) for g in plan.groups], "ok": ok_all})
         print(json.dumps(out), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)

@@ -200,10 +200,13 @@ _plan_cache = {}
 
 
 def shard_chunk_points(total_points, world):
-    """Points per chunk for a batch spread over ``world`` ranks: small enough that ONE rank still has ~28 chunks x 96
-    pixel tiles = enough warp tasks to fill its 148 SMs with the large (8 x 2) pixel tile, never above the single-GPU
-    chunk size, a multiple of 32."""
-    want = max(1, total_points // (max(world, 1) * 30))
+    """Points per chunk for a batch spread over ``world`` ranks.  One rank sweeps total / world points; cutting them into
+    ~64 chunks (x 24 CTAs of four pixel tiles each) gives every SM several rounds of short CTAs, so the ragged last
+    round of each sweep is a small fraction of it -- with 1024-point chunks a rank of an 8-GPU run would hold 7 chunks,
+    a third of one round.  Small chunks are affordable because the sharded path reduces the per-chunk partials in
+    separate kernels (bl_min_combine / bl_finish_z) and bounds the min sweep of later chunks by the first one.  Never
+    above the single-GPU chunk size, never below 128 (the sweeps stage 128 points at a time), a multiple of 32."""
+    want = max(1, total_points // (max(world, 1) * 64))
     return int(min(_bl.chunk_points(), max(128, -(-want // 32) * 32)))
 
 

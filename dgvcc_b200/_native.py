@@ -38,7 +38,7 @@ class BLShard(ctypes.Structure):
     """Mirror of struct dgvcc_bl_shard."""
     _fields_ = [(n, c_int32) for n in ("rank", "world", "chunk_lo", "chunk_hi", "pt_lo", "pt_hi", "img_lo", "img_hi")] + \
                [("push_first", c_int32 * (BL_PHASES + 1)), ("wait_mask", ctypes.c_uint32 * BL_PHASES),
-                ("signal_mask", ctypes.c_uint32 * BL_PHASES), ("epoch", ctypes.c_uint32), ("reserved_", c_int32)]
+                ("signal_mask", ctypes.c_uint32 * BL_PHASES), ("epoch", ctypes.c_uint32), ("fuse_waits", c_int32)]
 
 
 class DmapPlan(ctypes.Structure):
@@ -74,10 +74,10 @@ SIGNATURES = {
     "dgvcc_bl_shard_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
     "dgvcc_bl_shard_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                        c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, POINTER(BLShard),
-                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
     "dgvcc_bl_shard_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_float, c_float, c_int,
-                                        c_int, c_float, c_void_p, POINTER(BLShard), c_void_p, c_void_p, c_void_p, c_size_t,
-                                        c_void_p, c_void_p, POINTER(c_void_p)]),
+                                        c_int, c_float, c_void_p, POINTER(BLShard), c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
     "dgvcc_bl_shard_preload": (c_int, []),
     "dgvcc_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "dgvcc_peer_free": (c_int, [c_void_p]),

@@ -157,6 +157,94 @@ struct Shard {
 };
 __host__ __device__ __forceinline__ Shard no_shard() { return Shard{0, 0, 0x7fffffff, 0, 0x7fffffff, 0, 0x7fffffff}; }
 
+// Peer exchange of the sharded path, fused into the kernels that produce / consume the data.  A producing kernel
+// stores its results into its own workspace AND, with plain stores over NVLink, into the workspaces of the ranks in
+// the destination mask of its chunk / image; when its last CTA is done (every CTA fences its remote stores at system
+// scope before it takes a ticket) it raises this rank's flag of the phase on the ranks in signal_mask.  A consuming
+// kernel first waits for the flags of the ranks in wait_mask (bounded: a lost peer leaves a code in err[0], not a hung
+// GPU).  peers == nullptr and wait_mask == 0 (the value-initialised struct): one GPU, nothing happens.
+struct Xchg {
+    char* const* peers;         // [world] workspace bases as mapped into this process (own one included)
+    const unsigned int* mask;   // destination ranks per chunk (sweeps) or per image (row / image kernels)
+    unsigned int* ticket;       // CTA arrival counter of the producing kernel (zero between kernels)
+    const unsigned int* flags;  // this rank's own flag array [phase][source]
+    int* err;
+    long long flags_off;        // byte offset of the flag array in every workspace
+    long long region_off, region_off2;  // byte offsets of the exchanged arrays in every workspace
+    int phase, rank, world;     // producing side: phase raised
+    unsigned int signal_mask, epoch;
+    unsigned int wait_mask, wait_mask2;  // consuming side: up to two phases to wait for
+    int wait_phase, wait_phase2;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long XCHG_TIMEOUT_NS = 2000000000ull;  // 2 s
+
+__device__ __forceinline__ void xchg_spin(const unsigned int* flag, unsigned int epoch, int code, int* err) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (global_ns() - t0 > XCHG_TIMEOUT_NS) {
+            atomicExch(err, code);
+            break;
+        }
+        __nanosleep(32);
+    }
+}
+
+// Consumer prologue, called by every thread of the CTA: lane = source rank, warp 0 / 1 = first / second phase.
+__device__ __forceinline__ void xchg_wait(const Xchg& x) {
+    if ((x.wait_mask | x.wait_mask2) == 0u) return;
+    const int src = threadIdx.x & 31, which = threadIdx.x >> 5;
+    if (which < 2 && src < x.world) {
+        const unsigned int m = which ? x.wait_mask2 : x.wait_mask;
+        const int ph = which ? x.wait_phase2 : x.wait_phase;
+        if ((m >> src) & 1u) xchg_spin(x.flags + ph * x.world + src, x.epoch, 1 + ph + 16 * src, x.err);
+    }
+    __threadfence_system();
+    __syncthreads();
+}
+
+// One value into the same array of every rank in `mask`.
+__device__ __forceinline__ void xchg_store(const Xchg& x, unsigned int mask, long long region_off, size_t elem, float v) {
+    while (mask) {
+        const int q = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        reinterpret_cast<float*>(x.peers[q] + region_off)[elem] = v;
+    }
+}
+
+// Producer epilogue, called by every thread of every CTA of the grid (no early returns before it).
+__device__ __forceinline__ void xchg_signal(const Xchg& x) {
+    if (!x.peers) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(x.ticket, 1u) == total - 1u) {
+            __threadfence_system();
+            unsigned int m = x.signal_mask;
+            while (m) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1u;
+                st_release_sys(reinterpret_cast<unsigned int*>(x.peers[q] + x.flags_off) + x.phase * x.world + x.rank, x.epoch);
+            }
+            *x.ticket = 0u;
+        }
+    }
+}
+
 struct TaskInfo {
     int img, row0, n_rows;    // image, its first posterior row, number of rows
     int n_img_pts;            // points in the whole image
@@ -393,9 +481,9 @@ struct ExpCull {
 // minimum over the image's chunks is unchanged, and min is exact, so nothing depends on the order.  (Measured on one
 // GPU: two stages 97 us against 83 us for the single launch -- stage 0 alone leaves most SMs idle.)
 template <int R, int C>
-__global__ void __launch_bounds__(CTA_THREADS)
-bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
-              float* __restrict__ minpart, int stage, int chunk_lo) {
+__device__ __forceinline__ void bl_min_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch,
+                                            const Geom& g, float* __restrict__ minpart, int stage, int chunk_lo,
+                                            const Xchg& x) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
     if (!decode_task<R, C>(meta, batch, g, t)) return;
@@ -414,18 +502,33 @@ bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ me
             mind[r][c] = stage <= 0 ? __int_as_float(0x7f800000) : minpart[(size_t)lead * M + px.pix(r, c)];
     sweep_min<R, C>(tile, px, pts_all + t.pt_base, t.p_cnt, mind);
     float* out = minpart + (size_t)t.chunk * M;
+    const unsigned int dst = x.peers ? x.mask[t.chunk] : 0u;
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < C; ++c)
-            if (px.ok(r, c)) out[px.pix(r, c)] = mind[r][c];
+            if (px.ok(r, c)) {
+                out[px.pix(r, c)] = mind[r][c];
+                if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + px.pix(r, c), mind[r][c]);
+            }
+}
+
+template <int R, int C>
+__global__ void __launch_bounds__(CTA_THREADS)
+bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
+              float* __restrict__ minpart, int stage, int chunk_lo, Xchg x) {
+    bl_min_body<R, C>(pts_all, meta, batch, g, minpart, stage, chunk_lo, x);
+    if (stage != 0) xchg_signal(x);  // stage 0's stores are fenced below; the flag goes up after the last launch
+    else if (x.peers) __threadfence_system();
 }
 
 // Sharded path: min over the chunks of an image once they have all arrived, so that bl_z_kernel reads one value per
 // pixel instead of one per chunk (small chunks, many of them).
 __global__ void __launch_bounds__(256)
 bl_min_combine_kernel(const int32_t* __restrict__ meta, int batch, int M, int img_first, const float* __restrict__ minpart,
-                      float* __restrict__ min_img) {
+                      float* __restrict__ min_img, Xchg x, int n_img) {
+    xchg_wait(x);
+    if ((int)blockIdx.y >= n_img) return;
     const int img = img_first + blockIdx.y;
     const Meta mv = meta_view(meta, batch);
     const int first = mv.icb[img], n_chunks = mv.icb[img + 1] - first;
@@ -439,12 +542,11 @@ bl_min_combine_kernel(const int32_t* __restrict__ meta, int batch, int M, int im
 // ------------------------------------------------------------------------------------------ K1
 // Softmax max (incl. the background row, bl.py:39-43) and this chunk's share of the denominator.
 template <int R, int C, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS)
-bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
-            const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
+__device__ __forceinline__ void bl_z_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
+            const float* __restrict__ st_sizes, int batch, const Geom& g, const Scale& k, float bg_ratio, int use_bg,
             int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
-            float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, Shard sh,
-            const float* __restrict__ min_img) {
+            float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, const Shard& sh,
+            const float* __restrict__ min_img, const Xchg& x) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
     TaskInfo t;
@@ -555,6 +657,7 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
 #pragma unroll
         for (int c = 0; c < C; ++c) unpack2(zp[q][c], z[2 * q][c], z[2 * q + 1][c]);
     const bool first = t.chunk == max(t.first_chunk, sh.chunk_lo);  // the image's first chunk ON THIS RANK
+    const unsigned int dst = x.peers ? x.mask[t.chunk] : 0u;
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -562,11 +665,24 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
             if (!px.ok(r, c)) continue;
             const int p = px.pix(r, c);
             zout[p] = z[r][c];
+            if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + p, z[r][c]);
             if (first) {
                 amax_img[p] = amax_v[r][c];
                 ebg_img[p] = use_bg ? ex2_ftz(ebg_arg[r][c]) : 0.f;
             }
         }
+}
+
+template <int R, int C, bool POW2>
+__global__ void __launch_bounds__(CTA_THREADS)
+bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
+            const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
+            int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
+            float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, Shard sh,
+            const float* __restrict__ min_img, Xchg x) {
+    bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull, minpart, zpart, amax_out,
+                          ebg_out, ticket, sh, min_img, x);
+    xchg_signal(x);
 }
 
 // 1 / (sum of the chunk shares in chunk order + background term last), the reference's row order.
@@ -738,10 +854,21 @@ __device__ __forceinline__ float block_sum_ordered(float v, float* scratch) {
 
 // Expected counts: fixed-order sum of the per-tile partials (one thread per posterior row, coalesced
 // across rows), and the residual |t - c|  (bl.py:73-75).
+__device__ __forceinline__ void bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
+                        const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
+                        float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x);
+
 __global__ void __launch_bounds__(256)
 bl_reduce_counts_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
-                        float* __restrict__ counts, float* __restrict__ residual, Shard sh) {
+                        float* __restrict__ counts, float* __restrict__ residual, Shard sh, Xchg x) {
+    bl_reduce_counts_body(cpart, tiles, total_rows, meta, targets, batch, counts, residual, sh, x);
+    xchg_signal(x);
+}
+
+__device__ __forceinline__ void bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
+                        const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
+                        float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (j >= total_rows) return;
     const Meta mv = meta_view(meta, batch);
@@ -763,15 +890,26 @@ bl_reduce_counts_kernel(const float* __restrict__ cpart, int tiles, int64_t tota
 #pragma unroll 8
     for (int tl = 0; tl < tiles; ++tl) c += p[(size_t)tl * total_rows];
     const float tgt = (local < n_pts) ? targets[mv.pt_off[lo] + local] : 0.f;
+    const float res = fabsf(__fadd_rn(tgt, -c));
     counts[j] = c;
-    residual[j] = fabsf(__fadd_rn(tgt, -c));
+    residual[j] = res;
+    if (x.peers) {  // the image's other ranks need every row for the top-k cut (bl.py:77)
+        const unsigned int dst = x.mask[lo];
+        xchg_store(x, dst, x.region_off, (size_t)j, c);
+        xchg_store(x, dst, x.region_off2, (size_t)j, res);
+    }
 }
 
 __global__ void __launch_bounds__(SELECT_THREADS)
 bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
                  float inv_batch, const float* __restrict__ counts, const float* __restrict__ residual,
                  float* __restrict__ wsel, float* __restrict__ loss_img, float* __restrict__ loss_out,
-                 unsigned int* __restrict__ ticket, int img_first, int finish) {
+                 unsigned int* __restrict__ ticket, int img_first, int finish, Shard sh, Xchg x, int n_img) {
+    xchg_wait(x);  // sharded: the counts / residuals of the rows other ranks computed
+    if ((int)blockIdx.x >= n_img) {  // a rank that touches no image still takes part in the exchange
+        xchg_signal(x);
+        return;
+    }
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sh_prefix, sh_rank, sh_equal;
     __shared__ unsigned int warp_cnt[SELECT_THREADS / 32];
@@ -875,7 +1013,13 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
     const float l_img = block_sum_ordered(lsum, scratch);
 
     // last CTA to finish adds the per-image losses in image order (deterministic), bl.py:79
-    if (tid == 0 && !finish) loss_img[img] = l_img;  // sharded: bl_loss_finish_kernel adds them once every rank's arrived
+    if (tid == 0 && !finish) {  // sharded: bl_loss_finish_kernel adds the images' losses once every rank's have arrived
+        loss_img[img] = l_img;
+        const int first_chunk = mv.icb[img];
+        if (x.peers && first_chunk >= sh.chunk_lo && first_chunk < sh.chunk_hi)  // from the rank with the image's first chunk
+            xchg_store(x, ((1u << x.world) - 1u) & ~(1u << x.rank), x.region_off, (size_t)img, l_img);
+    }
+    if (!finish) xchg_signal(x);
     if (tid == 0 && finish) {
         loss_img[img] = l_img;
         __threadfence();
@@ -896,12 +1040,11 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
 // compacted away while staging.  Single-chunk images store the final gradient; otherwise the raw
 // chunk sum goes to gpart and bl_grad_reduce_kernel finishes.
 template <int R, int C, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS)
-bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
-               Scale k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
+__device__ __forceinline__ void bl_grad_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch,
+               const Geom& g, const Scale& k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
-               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial) {
+               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, const Xchg& x) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
     if (!decode_task<R, C>(meta, batch, g, t)) return;
@@ -974,21 +1117,53 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
                 grad_density[m] = gscale * fmaf(acc[r][c], rz_in[m], w_bg * pbg_in[m]);
             }
     } else {
+        // sharded: chunks of an image finished by another rank go straight (and only) into that rank's workspace
+        const unsigned int dst = x.peers ? x.mask[t.chunk] : 0u;
         float* out = gpart + (size_t)t.chunk * M;
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int c = 0; c < C; ++c)
-                if (px.ok(r, c)) out[px.pix(r, c)] = acc[r][c];
+                if (px.ok(r, c)) {
+                    if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + px.pix(r, c), acc[r][c]);
+                    else out[px.pix(r, c)] = acc[r][c];
+                }
     }
 }
 
+template <int R, int C, bool POW2>
+__global__ void __launch_bounds__(CTA_THREADS)
+bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
+               Scale k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
+               const float* __restrict__ amax_in, const float* __restrict__ rz_in,
+               const float* __restrict__ pbg_in, const float* __restrict__ wsel,
+               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, Xchg x) {
+    bl_grad_body<R, C, POW2>(pts_all, meta, batch, g, k, use_bg, exact_cull, inv_batch, grad_loss, amax_in, rz_in, pbg_in,
+                             wsel, gpart, grad_density, always_partial, x);
+    xchg_signal(x);
+}
+
 // Multi-chunk images: add the chunk sums in chunk order and apply the per-pixel factors.
+__device__ __forceinline__ void bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
+                      const float* __restrict__ grad_loss, const float* __restrict__ gpart,
+                      const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
+                      const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x);
+
 __global__ void __launch_bounds__(256)
 bl_grad_reduce_kernel(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
                       const float* __restrict__ grad_loss, const float* __restrict__ gpart,
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
-                      const float* __restrict__ wsel, float* __restrict__ grad_density, Shard sh) {
+                      const float* __restrict__ wsel, float* __restrict__ grad_density, Shard sh, Xchg x, int n_img) {
+    xchg_wait(x);  // sharded: the gradient sums of the chunks other ranks swept
+    if ((int)blockIdx.y < n_img)
+        bl_grad_reduce_body(meta, batch, M, use_bg, inv_batch, grad_loss, gpart, rz_in, pbg_in, wsel, grad_density, sh, x);
+    xchg_signal(x);
+}
+
+__device__ __forceinline__ void bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
+                      const float* __restrict__ grad_loss, const float* __restrict__ gpart,
+                      const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
+                      const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x) {
     const int img = sh.img_lo + blockIdx.y;
     const Meta mv = meta_view(meta, batch);
     const int first = mv.icb[img], n_chunks = mv.icb[img + 1] - first;
@@ -1005,7 +1180,10 @@ bl_grad_reduce_kernel(const int32_t* __restrict__ meta, int batch, int M, int us
     const bool has_bg_row = use_bg || mv.pt_off[img + 1] == mv.pt_off[img];
     const float w_bg = has_bg_row ? wsel[mv.row_off[img] + n_rows - 1] : 0.f;
     const size_t m = (size_t)img * M + pix;
-    grad_density[m] = grad_loss[0] * inv_batch * fmaf(acc, rz_in[m], w_bg * pbg_in[m]);
+    const float gv = grad_loss[0] * inv_batch * fmaf(acc, rz_in[m], w_bg * pbg_in[m]);
+    const unsigned int dst = x.peers ? x.mask[img] : 0u;  // the image's owner, when that is another rank
+    if (dst) xchg_store(x, dst, x.region_off, m, gv);
+    else grad_density[m] = gv;
 }
 
 // ------------------------------------------------------------------------- posterior (API parity)
@@ -1013,7 +1191,9 @@ bl_grad_reduce_kernel(const int32_t* __restrict__ meta, int batch, int M, int us
 __global__ void __launch_bounds__(256)
 bl_finish_z_kernel(const int32_t* __restrict__ meta, int batch, int M, const float* __restrict__ zpart,
                    const float* __restrict__ ebg_in, float* __restrict__ rz_out, float* __restrict__ pbg_out,
-                   int img_first) {
+                   int img_first, Xchg x, int n_img) {
+    xchg_wait(x);  // sharded: the other ranks' denominator shares (and the density, for the kernel that follows)
+    if ((int)blockIdx.y >= n_img) return;
     const int img = img_first + blockIdx.y;
     const Meta mv = meta_view(meta, batch);
     const int pix = blockIdx.x * 256 + threadIdx.x;
@@ -1124,20 +1304,6 @@ bl_prob_grad_kernel(const float* __restrict__ prob, const int32_t* __restrict__ 
 // result is bit-identical to the single-GPU one.  No NCCL on the data path.
 constexpr int PUSH_THREADS = 256;
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 // One CTA per slice: copy `bytes` from src_base + src_off to peers[dst_rank] + dst_off.  The last CTA to finish
 // raises this rank's flag of `phase` on every rank in signal_mask (release at system scope, after every CTA's
 // stores were fenced), so a receiver that sees the flag sees the data.
@@ -1173,10 +1339,14 @@ bl_push_kernel(const dgvcc_bl_push* __restrict__ slices, int n_slices, const cha
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// A rank without work in a phase still raises its flag.
+__global__ void bl_signal_kernel(Xchg x) { xchg_signal(x); }
+
 // Local variant: the same slices with one destination base and no flags (gathers a rank's own finished gradients).
 __global__ void __launch_bounds__(PUSH_THREADS)
 bl_copy_kernel(const dgvcc_bl_push* __restrict__ slices, int n_slices, const char* __restrict__ src_base,
-               char* __restrict__ dst_base) {
+               char* __restrict__ dst_base, Xchg x) {
+    xchg_wait(x);  // the finished gradients other ranks delivered
     if ((int)blockIdx.x >= n_slices) return;
     const dgvcc_bl_push sl = slices[blockIdx.x];
     const char* src = src_base + sl.src_off;
@@ -1212,10 +1382,12 @@ bl_wait_kernel(const unsigned int* __restrict__ flags, int phase, int world, uns
 
 // Sum of the per-image losses in image order (every rank received the values of the images it does not hold).
 __global__ void bl_loss_finish_kernel(const float* __restrict__ loss_img, int batch, float inv_batch,
-                                      float* __restrict__ loss_out) {
+                                      float* __restrict__ loss_out, Xchg x) {
+    xchg_wait(x);
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         float total = 0.f;
-        for (int i = 0; i < batch; ++i) total += loss_img[i];
+        const volatile float* li = loss_img;  // written by the peers
+        for (int i = 0; i < batch; ++i) total += li[i];
         loss_out[0] = total * inv_batch;
     }
 }
@@ -1376,10 +1548,10 @@ inline void mark(void** events, int i, cudaStream_t st) {
 // per-chunk partial minima of the images cut into several chunks: first chunks, then the others bounded by them
 int launch_min(const Plan& p, const float2* pts, const int32_t* meta, int batch, float* minpart, cudaStream_t st) {
     for (int stage = p.sh.on ? 0 : -1; stage < (p.sh.on ? 2 : 0); ++stage) {
-        if (p.v.rows == 8 && p.v.cols == 2) bl_min_kernel<8, 2><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo);
-        else if (p.v.rows == 8) bl_min_kernel<8, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo);
-        else if (p.v.rows == 4) bl_min_kernel<4, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo);
-        else bl_min_kernel<2, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo);
+        if (p.v.rows == 8 && p.v.cols == 2) bl_min_kernel<8, 2><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
+        else if (p.v.rows == 8) bl_min_kernel<8, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
+        else if (p.v.rows == 4) bl_min_kernel<4, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
+        else bl_min_kernel<2, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
         if (cudaError_t e = cudaGetLastError()) return (int)e;
     }
     return DGVCC_OK;
@@ -1396,7 +1568,7 @@ int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const floa
     mark(events, 1, st);
     BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
                 exact_cull, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg),
-                at<unsigned int>(ws, p.L.ticket), p.sh, (const float*)nullptr);
+                at<unsigned int>(ws, p.L.ticket), p.sh, (const float*)nullptr, Xchg{});
     mark(events, 2, st);
     return (int)cudaGetLastError();
 }
@@ -1405,7 +1577,7 @@ int launch_reduce_counts(const dgvcc_bl_layout& L, const float* targets, const i
                          int64_t total_rows, int tiles, void* ws, const Shard& sh, cudaStream_t st) {
     bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
         at<float>(ws, L.cpart), tiles, total_rows, meta, targets, batch, at<float>(ws, L.counts),
-        at<float>(ws, L.residual), sh);
+        at<float>(ws, L.residual), sh, Xchg{});
     return (int)cudaGetLastError();
 }
 
@@ -1415,7 +1587,7 @@ int launch_select(const dgvcc_bl_layout& L, const float* targets, const int32_t*
     if (rc) return rc;
     bl_select_kernel<<<batch, SELECT_THREADS, 0, st>>>(
         meta, targets, batch, inv_batch, at<float>(ws, L.counts), at<float>(ws, L.residual), at<float>(ws, L.wsel),
-        at<float>(ws, L.loss_img), loss_out, at<unsigned int>(ws, L.ticket), 0, 1);
+        at<float>(ws, L.loss_img), loss_out, at<unsigned int>(ws, L.ticket), 0, 1, no_shard(), Xchg{}, batch);
     return (int)cudaGetLastError();
 }
 
@@ -1471,14 +1643,14 @@ extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int b
     BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
                 exact_cull, inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                 at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                grad_density, 0);
+                grad_density, 0, Xchg{});
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     if (multi_chunk) {
         const int M = hp * wp;
         bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, st>>>(
             meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart),
             at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), grad_density,
-            no_shard());
+            no_shard(), Xchg{}, batch);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     return DGVCC_OK;
@@ -1489,39 +1661,67 @@ namespace {
 
 struct ShardCtx {
     const dgvcc_bl_shard* sh;
-    const dgvcc_bl_push* slices;  // device
+    const dgvcc_bl_push* slices;  // device: DENS and OUT slices
+    const unsigned int* aux;      // device: zmask[C] | gmask[C] | img_mask[B] | owner_mask[B]
     char* const* peers;           // device array [world]
     void* ws;
     const dgvcc_bl_layout* L;
     cudaStream_t st;
+    int total_chunks, batch;
+
+    const unsigned int* zmask() const { return aux; }
+    const unsigned int* gmask() const { return aux + total_chunks; }
+    const unsigned int* img_mask() const { return aux + 2 * total_chunks; }
+    const unsigned int* owner_mask() const { return aux + 2 * total_chunks + batch; }
+
+    // Xchg of a kernel that produces phase `ph` (mask: per chunk / image destinations; region: exchanged array) and / or
+    // waits for `w1`, `w2` first (-1: none).  With separate wait kernels (sh->fuse_waits == 0) the wait part stays empty.
+    Xchg make(int ph, const unsigned int* mask, int64_t region, int64_t region2, int w1, int w2) const {
+        Xchg x{};
+        x.flags = at<unsigned int>(ws, L->flags);
+        x.err = at<int>(ws, L->err);
+        x.world = sh->world; x.rank = sh->rank; x.epoch = sh->epoch;
+        if (ph >= 0) {
+            x.peers = peers; x.mask = mask; x.ticket = at<unsigned int>(ws, L->push_ticket);
+            x.flags_off = L->flags; x.region_off = region; x.region_off2 = region2;
+            x.phase = ph; x.signal_mask = sh->signal_mask[ph];
+        }
+        if (sh->fuse_waits) {
+            if (w1 >= 0) { x.wait_phase = w1; x.wait_mask = sh->wait_mask[w1]; }
+            if (w2 >= 0) { x.wait_phase2 = w2; x.wait_mask2 = sh->wait_mask[w2]; }
+        }
+        return x;
+    }
 };
 
-constexpr unsigned long long SHARD_WAIT_TIMEOUT_NS = 2000000000ull;  // 2 s
-
-// Phase `ph`: copy this rank's slices (sources relative to src_base, destinations relative to the peers' workspaces or
-// to dst_override) and raise the flags.
-int shard_push(const ShardCtx& c, int ph, const void* src_base, void* dst_override = nullptr) {
+// Phase DENS / OUT: copy this rank's slices (sources relative to src_base, destinations relative to the peers' workspaces
+// or to dst_override) and, for DENS, raise the flags.
+int shard_push(const ShardCtx& c, int ph, const void* src_base, void* dst_override = nullptr, int wait_ph = -1) {
     const int first = c.sh->push_first[ph], n = c.sh->push_first[ph + 1] - first;
-    if (n <= 0) return DGVCC_OK;
     if (!dst_override) {
+        if (n <= 0) return DGVCC_OK;
         bl_push_kernel<<<n, PUSH_THREADS, 0, c.st>>>(c.slices + first, n, (const char*)src_base, c.peers, c.L->flags, ph,
                                                      c.sh->rank, c.sh->world, c.sh->signal_mask[ph], c.sh->epoch,
                                                      at<unsigned int>(c.ws, c.L->push_ticket));
     } else {
-        bl_copy_kernel<<<n, PUSH_THREADS, 0, c.st>>>(c.slices + first, n, (const char*)src_base, (char*)dst_override);
+        const Xchg x = c.make(-1, nullptr, 0, 0, wait_ph, -1);
+        if (n <= 0 && !x.wait_mask) return DGVCC_OK;
+        bl_copy_kernel<<<n > 0 ? n : 1, PUSH_THREADS, 0, c.st>>>(c.slices + first, n, (const char*)src_base, (char*)dst_override, x);
     }
     return (int)cudaGetLastError();
 }
 
+// Separate wait kernel (sh->fuse_waits == 0: several ranks inside one process / on one GPU, where a whole grid of
+// spinning CTAs could keep a co-resident "peer" from ever running).
 int shard_wait(const ShardCtx& c, int ph) {
-    if (!c.sh->wait_mask[ph]) return DGVCC_OK;
+    if (c.sh->fuse_waits || !c.sh->wait_mask[ph]) return DGVCC_OK;
     bl_wait_kernel<<<1, 32, 0, c.st>>>(at<unsigned int>(c.ws, c.L->flags), ph, c.sh->world, c.sh->wait_mask[ph],
-                                       c.sh->epoch, SHARD_WAIT_TIMEOUT_NS, at<int>(c.ws, c.L->err));
+                                       c.sh->epoch, XCHG_TIMEOUT_NS, at<int>(c.ws, c.L->err));
     return (int)cudaGetLastError();
 }
 
-bool shard_args_ok(const dgvcc_bl_shard* sh, const dgvcc_bl_push* slices, void* const* peers) {
-    if (!sh || !peers) return false;
+bool shard_args_ok(const dgvcc_bl_shard* sh, const dgvcc_bl_push* slices, const void* aux, void* const* peers) {
+    if (!sh || !peers || !aux) return false;
     for (int ph = 0; ph < DGVCC_BL_PHASES; ++ph)
         if (sh->push_first[ph + 1] < sh->push_first[ph]) return false;
     return sh->push_first[DGVCC_BL_PHASES] == 0 || slices != nullptr;
@@ -1553,6 +1753,7 @@ extern "C" int dgvcc_bl_shard_preload(void) {
     BL_PRELOAD(bl_push_kernel);
     BL_PRELOAD(bl_copy_kernel);
     BL_PRELOAD(bl_wait_kernel);
+    BL_PRELOAD(bl_signal_kernel);
     BL_PRELOAD(bl_loss_finish_kernel);
     BL_PRELOAD(bl_min_combine_kernel);
     BL_PRELOAD(bl_finish_z_kernel);
@@ -1571,76 +1772,97 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
                                       const float* st_sizes, const float* density_local, int batch, int hp, int wp,
                                       int64_t total_rows, int total_chunks, int multi_chunk, float stride, float sigma,
                                       float bg_ratio, int use_bg, int exact_cull, float inv_batch,
-                                      const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
-                                      void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
-                                      void** events) {
+                                      const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, const uint32_t* aux,
+                                      void* const* peers, void* workspace, size_t workspace_bytes, float* loss_out,
+                                      void* stream, void** events) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!shard_args_ok(shard, slices, peers)) return DGVCC_ERR_ARG;
+    if (!shard_args_ok(shard, slices, aux, peers)) return DGVCC_ERR_ARG;
     Plan p;
     int rc = make_plan(meta, st_sizes, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride, sigma,
                        &p, shard);
     if (rc) return rc;
     if (!loss_out || !pts_xy || !targets) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const ShardCtx c{shard, slices, (char* const*)peers, workspace, &p.L, st};
+    const ShardCtx c{shard, slices, aux, (char* const*)peers, workspace, &p.L, st, total_chunks, batch};
     const float2* pts = (const float2*)pts_xy;
     const bool sweeps = p.grid.y > 0;
+    const int n_img = p.sh.img_hi - p.sh.img_lo;
+    const int M = hp * wp;
+    const dim3 pix_grid(ceil_div(M, 256), n_img > 0 ? n_img : 1);
     mark(events, 0, st);
     // density of the images this rank owns -> every rank that sweeps them (needed from bl_counts on)
     if ((rc = shard_push(c, DGVCC_BL_PH_DENS, density_local))) return rc;
-    // per-chunk minima of the images cut into several chunks
-    if (sweeps && multi_chunk)
-        if ((rc = launch_min(p, pts, meta, batch, at<float>(workspace, p.L.minpart), st))) return rc;
-    mark(events, 1, st);
-    if ((rc = shard_push(c, DGVCC_BL_PH_MIN, workspace))) return rc;
-    if ((rc = shard_wait(c, DGVCC_BL_PH_MIN))) return rc;
-    mark(events, 2, st);
-    const int n_img = p.sh.img_hi - p.sh.img_lo;
-    const int M = hp * wp;
-    if (sweeps) {
-        float* min_img = at<float>(workspace, p.L.pbg);  // the region is free until bl_finish_z_kernel fills it
-        if (multi_chunk) {
-            bl_min_combine_kernel<<<dim3(ceil_div(M, 256), n_img), 256, 0, st>>>(meta, batch, M, p.sh.img_lo,
-                                                                               at<float>(workspace, p.L.minpart), min_img);
+    // per-chunk minima of the images cut into several chunks, stored at home and on the image's other ranks; the flag
+    // goes up with the second stage
+    if (multi_chunk) {
+        float* minpart = at<float>(workspace, p.L.minpart);
+        const Xchg x = c.make(DGVCC_BL_PH_MIN, c.zmask(), p.L.minpart, 0, -1, -1);
+        const dim3 grid = sweeps ? p.grid : dim3(1, 1);  // a rank without chunks still raises its flag
+        for (int stage = 0; stage < 2; ++stage) {
+            const int slots_meta = sweeps ? 0 : -1;
+            (void)slots_meta;
+            if (!sweeps) {
+                if (stage == 1) bl_signal_kernel<<<1, 32, 0, st>>>(x);
+            } else if (p.v.rows == 8 && p.v.cols == 2) bl_min_kernel<8, 2><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
+            else if (p.v.rows == 8) bl_min_kernel<8, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
+            else if (p.v.rows == 4) bl_min_kernel<4, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
+            else bl_min_kernel<2, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
             DGVCC_RETURN_IF_CUDA(cudaGetLastError());
         }
-        BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
-                    at<float>(workspace, p.L.minpart), at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
-                    at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img);
+    }
+    mark(events, 1, st);
+    if (multi_chunk && (rc = shard_wait(c, DGVCC_BL_PH_MIN))) return rc;
+    mark(events, 2, st);
+    float* min_img = at<float>(workspace, p.L.pbg);  // the region is free until bl_finish_z_kernel fills it
+    if (multi_chunk && (n_img > 0 || (shard->fuse_waits && shard->wait_mask[DGVCC_BL_PH_MIN]))) {
+        bl_min_combine_kernel<<<pix_grid, 256, 0, st>>>(meta, batch, M, p.sh.img_lo, at<float>(workspace, p.L.minpart), min_img,
+                                                       c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_MIN, -1), n_img);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    }
+    {
+        const Xchg x = c.make(DGVCC_BL_PH_Z, c.zmask(), p.L.zpart, 0, -1, -1);
+        if (sweeps) {
+            BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
+                        at<float>(workspace, p.L.minpart), at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
+                        at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img, x);
+        } else {
+            bl_signal_kernel<<<1, 32, 0, st>>>(x);
+        }
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     mark(events, 3, st);
-    if ((rc = shard_push(c, DGVCC_BL_PH_Z, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_Z))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_DENS))) return rc;
     mark(events, 4, st);
+    bl_finish_z_kernel<<<pix_grid, 256, 0, st>>>(meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg),
+                                                 at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), p.sh.img_lo,
+                                                 c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_Z, DGVCC_BL_PH_DENS), n_img);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     if (sweeps) {
-        bl_finish_z_kernel<<<dim3(ceil_div(M, 256), n_img), 256, 0, st>>>(
-            meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.rz),
-            at<float>(workspace, p.L.pbg), p.sh.img_lo);
-        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
         BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
                     use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
                     at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
                     at<float>(workspace, p.L.cpart), p.sh, 1);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-        if ((rc = launch_reduce_counts(p.L, targets, meta, batch, total_rows, p.L.tiles, workspace, p.sh, st))) return rc;
     }
+    // fixed-order sums of the tile partials of this rank's rows, delivered to the image's other ranks as they are written
+    bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
+        at<float>(workspace, p.L.cpart), p.L.tiles, total_rows, meta, targets, batch, at<float>(workspace, p.L.counts),
+        at<float>(workspace, p.L.residual), p.sh, c.make(DGVCC_BL_PH_CNT, c.img_mask(), p.L.counts, p.L.residual, -1, -1));
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 5, st);
-    if ((rc = shard_push(c, DGVCC_BL_PH_CNT, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_CNT))) return rc;
     mark(events, 6, st);
-    if (p.sh.img_hi > p.sh.img_lo) {
-        bl_select_kernel<<<p.sh.img_hi - p.sh.img_lo, SELECT_THREADS, 0, st>>>(
-            meta, targets, batch, inv_batch, at<float>(workspace, p.L.counts), at<float>(workspace, p.L.residual),
-            at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.loss_img), loss_out,
-            at<unsigned int>(workspace, p.L.ticket), p.sh.img_lo, 0);
-        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    }
+    // top-k cut and per-image loss of every image this rank touches; the rank with an image's first chunk tells everybody
+    bl_select_kernel<<<n_img > 0 ? n_img : 1, SELECT_THREADS, 0, st>>>(
+        meta, targets, batch, inv_batch, at<float>(workspace, p.L.counts), at<float>(workspace, p.L.residual),
+        at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.loss_img), loss_out, at<unsigned int>(workspace, p.L.ticket),
+        p.sh.img_lo, 0, p.sh, c.make(DGVCC_BL_PH_LOSS, nullptr, p.L.loss_img, 0, DGVCC_BL_PH_CNT, -1), n_img);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 7, st);
-    if ((rc = shard_push(c, DGVCC_BL_PH_LOSS, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_LOSS))) return rc;
-    bl_loss_finish_kernel<<<1, 32, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out);
+    bl_loss_finish_kernel<<<1, 64, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out,
+                                            c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_LOSS, -1));
     mark(events, 8, st);
     return (int)cudaGetLastError();
 }
@@ -1648,44 +1870,48 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
 extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp,
                                        int64_t total_rows, int total_chunks, float stride, float sigma, int use_bg,
                                        int exact_cull, float inv_batch, const float* grad_loss,
-                                       const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
-                                       void* workspace, size_t workspace_bytes, float* grad_local, void* stream,
-                                       void** events) {
+                                       const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, const uint32_t* aux,
+                                       void* const* peers, void* workspace, size_t workspace_bytes, float* grad_local,
+                                       void* stream, void** events) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!shard_args_ok(shard, slices, peers)) return DGVCC_ERR_ARG;
+    if (!shard_args_ok(shard, slices, aux, peers)) return DGVCC_ERR_ARG;
     Plan p;
     int rc = make_plan(meta, grad_loss, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride, sigma,
                        &p, shard);
     if (rc) return rc;
     if (!pts_xy) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const ShardCtx c{shard, slices, (char* const*)peers, workspace, &p.L, st};
+    const ShardCtx c{shard, slices, aux, (char* const*)peers, workspace, &p.L, st, total_chunks, batch};
     const int M = hp * wp;
+    const int n_img = p.sh.img_hi - p.sh.img_lo;
     mark(events, 0, st);
-    if (p.grid.y > 0) {  // raw per-chunk gradient sums, every image (the rank with an image's first chunk finishes it)
-        BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
-                    inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
-                    at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                    at<float>(workspace, p.L.gfinal), 1);
+    {   // raw per-chunk gradient sums of every image, written where the rank with the image's first chunk will add them
+        const Xchg x = c.make(DGVCC_BL_PH_GPART, c.gmask(), p.L.gpart, 0, -1, -1);
+        if (p.grid.y > 0) {
+            BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
+                        inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
+                        at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
+                        at<float>(workspace, p.L.gfinal), 1, x);
+        } else {
+            bl_signal_kernel<<<1, 32, 0, st>>>(x);
+        }
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     mark(events, 1, st);
-    if ((rc = shard_push(c, DGVCC_BL_PH_GPART, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_GPART))) return rc;
     mark(events, 2, st);
-    if (p.sh.img_hi > p.sh.img_lo) {
-        bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), p.sh.img_hi - p.sh.img_lo), 256, 0, st>>>(
-            meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart), at<float>(workspace, p.L.rz),
-            at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gfinal), p.sh);
-        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    }
+    // chunk sums added in chunk order, per-pixel factors applied, the result written at the image's owner
+    bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), n_img > 0 ? n_img : 1), 256, 0, st>>>(
+        meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart), at<float>(workspace, p.L.rz),
+        at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gfinal), p.sh,
+        c.make(DGVCC_BL_PH_GRAD, c.owner_mask(), p.L.gfinal, 0, DGVCC_BL_PH_GPART, -1), n_img);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 3, st);
-    if ((rc = shard_push(c, DGVCC_BL_PH_GRAD, workspace))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_GRAD))) return rc;
+    mark(events, 4, st);
     // the finished gradients of this rank's own images, gathered into the caller's tensor
     if (shard->push_first[DGVCC_BL_PH_OUT + 1] > shard->push_first[DGVCC_BL_PH_OUT] && !grad_local) return DGVCC_ERR_ARG;
-    mark(events, 4, st);
-    rc = shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local);
+    rc = shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local ? (void*)grad_local : workspace, DGVCC_BL_PH_GRAD);
     mark(events, 5, st);
     return rc;
 }
@@ -1726,7 +1952,7 @@ extern "C" int dgvcc_bl_posterior(const float* pts_xy, const int32_t* meta, cons
     const int M = hp * wp;
     bl_finish_z_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, st>>>(
         meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.rz),
-        at<float>(workspace, p.L.pbg), 0);
+        at<float>(workspace, p.L.pbg), 0, Xchg{}, batch);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     BL_DISPATCH(p.v, p.pow2, bl_posterior_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
                 at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), prob_out);

@@ -111,71 +111,64 @@ class ShardPlan:
         produce the bits the sharded ranks must reproduce (tests)."""
         return self.meta_for(None)
 
-    def slices_on(self, rank, device):
-        key = (rank, str(device))
-        t = self._slices_dev.get(key)
-        if t is None:
-            t = self._slices_dev[key] = torch.from_numpy(self.slices[rank]).to(device)
-        return t
-
     # ------------------------------------------------------------------------------------------------ exchange plan
     def _build_slices(self):
+        """Who sends what to whom.  DENS and OUT are copy launches described by slices; the other phases are fused into
+        the kernels, which only need destination masks (``aux``) -- and every phase needs its wait / signal masks."""
         w, L, m4 = self.world, self.layout, 4 * self.hp * self.wp
-        per = [[[] for _ in range(_native.BL_PHASES)] for _ in range(w)]        # per[src][phase] = [(src_off, dst_off, bytes, dst)]
-        wait = np.zeros((w, _native.BL_PHASES), dtype=np.uint32)
-        signal = np.zeros((w, _native.BL_PHASES), dtype=np.uint32)
+        P = _native
+        per = [[[] for _ in range(P.BL_PHASES)] for _ in range(w)]        # per[src][phase] = [(src_off, dst_off, bytes, dst)]
+        wait = np.zeros((w, P.BL_PHASES), dtype=np.uint32)
+        signal = np.zeros((w, P.BL_PHASES), dtype=np.uint32)
+        c, b = self.total_chunks, self.batch
+        zmask = np.zeros((w, c), dtype=np.uint32)      # per rank: destinations of a chunk's minima / denominator share
+        gmask = np.zeros((w, c), dtype=np.uint32)      # rank that finishes the chunk's image (0: this rank itself)
+        img_mask = np.zeros((w, b), dtype=np.uint32)   # the image's other ranks
+        owner_mask = np.zeros((w, b), dtype=np.uint32)  # owner of the image's gradient (0: the finishing rank itself)
+
+        def flag(phase, src, dst):
+            if dst != src:
+                wait[dst, phase] |= np.uint32(1 << src)
+                signal[src, phase] |= np.uint32(1 << dst)
 
         def add(phase, src, src_off, dst, dst_off, nbytes, flagged=True):
             step = SLICE_BYTES if (src_off | dst_off | nbytes) % 16 == 0 else 1 << 30
             for o in range(0, nbytes, step):
                 per[src][phase].append((src_off + o, dst_off + o, min(step, nbytes - o), dst))
-            if flagged and dst != src:
-                wait[dst, phase] |= np.uint32(1 << src)
-                signal[src, phase] |= np.uint32(1 << dst)
+            if flagged:
+                flag(phase, src, dst)
 
-        P = _native
-        for i in range(self.batch):
+        for i in range(b):
             g, lead, own = self.groups[i], int(self.lead[i]), int(self.owners[i])
             k_local = int(np.searchsorted(self.owned[own], i))
             for q in g:                                   # density: owner -> every rank that sweeps the image
                 add(P.BL_PH_DENS, own, k_local * m4, q, L.dens + i * m4, m4)
             c0, c1 = int(self.icb[i]), int(self.icb[i + 1])
-            if len(g) > 1:
-                for c in range(c0, c1):
-                    r = int(self.c_owner[c])
-                    for q in g:
-                        if q == r:
-                            continue
-                        if c1 - c0 > 1:
-                            add(P.BL_PH_MIN, r, L.minpart + c * m4, q, L.minpart + c * m4, m4)
-                        add(P.BL_PH_Z, r, L.zpart + c * m4, q, L.zpart + c * m4, m4)
-                for r in g:                               # expected counts + residuals of the rows a rank computed
-                    cs = [c for c in range(c0, c1) if self.c_owner[c] == r]
-                    first_row = int(self.row_off[i] + self.c_start[cs[0]])
-                    n_rows = int(sum(self.c_cnt[c] for c in cs))
-                    spans = [(first_row, n_rows)] if n_rows else []
-                    if r == lead and (self.use_bg or self.counts[i] == 0):
-                        spans.append((int(self.row_off[i + 1]) - 1, 1))
-                    for q in g:
-                        if q == r:
-                            continue
-                        for row, n in spans:
-                            add(P.BL_PH_CNT, r, L.counts + 4 * row, q, L.counts + 4 * row, 4 * n)
-                            add(P.BL_PH_CNT, r, L.residual + 4 * row, q, L.residual + 4 * row, 4 * n)
+            for ch in range(c0, c1):
+                r = int(self.c_owner[ch])
+                for q in g:
+                    if q != r:                            # minima and denominator shares: among the image's ranks
+                        zmask[r, ch] |= np.uint32(1 << q)
+                        flag(P.BL_PH_MIN, r, q)
+                        flag(P.BL_PH_Z, r, q)
+                if r != lead:                             # gradient sums -> the rank with the image's first chunk
+                    gmask[r, ch] = np.uint32(1 << lead)
+                    flag(P.BL_PH_GPART, r, lead)
+            for r in g:                                   # expected counts + residuals of a rank's rows: among the image's ranks
+                for q in g:
+                    if q != r:
+                        img_mask[r, i] |= np.uint32(1 << q)
+                        flag(P.BL_PH_CNT, r, q)
             for q in range(w):                            # the image's loss: lead -> everybody
-                if q != lead:
-                    add(P.BL_PH_LOSS, lead, L.loss_img + 4 * i, q, L.loss_img + 4 * i, 4)
-            for c in range(c0, c1):                       # gradient sums -> lead, which finishes the image
-                r = int(self.c_owner[c])
-                if r != lead:
-                    add(P.BL_PH_GPART, r, L.gpart + c * m4, lead, L.gpart + c * m4, m4)
+                flag(P.BL_PH_LOSS, lead, q)
             if own != lead:                               # finished gradient -> owner
-                add(P.BL_PH_GRAD, lead, L.gfinal + i * m4, own, L.gfinal + i * m4, m4)
+                owner_mask[lead, i] = np.uint32(1 << own)
+                flag(P.BL_PH_GRAD, lead, own)
             add(P.BL_PH_OUT, own, L.gfinal + i * m4, own, k_local * m4, m4, flagged=False)
-        self.slices, self.shards, self._slices_dev = [], [], {}
+        self.slices, self.shards, self.aux, self._dev = [], [], [], {}
         for r in range(w):
             rows, first = [], [0]
-            for ph in range(_native.BL_PHASES):
+            for ph in range(P.BL_PHASES):
                 rows += per[r][ph]
                 first.append(len(rows))
             arr = np.zeros((max(len(rows), 1), 3), dtype=np.int64)   # (src_off, dst_off, bytes | dst_rank << 32): 24-byte records
@@ -184,16 +177,26 @@ class ShardPlan:
                 arr[:len(rows), 0], arr[:len(rows), 1] = t[:, 0], t[:, 1]
                 arr[:len(rows), 2] = t[:, 2] | (t[:, 3] << 32)
             self.slices.append(arr)
+            self.aux.append(np.concatenate([zmask[r], gmask[r], img_mask[r], owner_mask[r]]).astype(np.uint32))
             sh = _native.BLShard()
             sh.rank, sh.world = r, w
             sh.chunk_lo, sh.chunk_hi = int(self.chunk_lo[r]), int(self.chunk_hi[r])
             sh.pt_lo, sh.pt_hi = int(self.bounds[r]), int(self.bounds[r + 1])
             sh.img_lo, sh.img_hi = int(self.img_lo[r]), int(self.img_hi[r])
-            for ph in range(_native.BL_PHASES + 1):
+            for ph in range(P.BL_PHASES + 1):
                 sh.push_first[ph] = first[ph]
-            for ph in range(_native.BL_PHASES):
+            for ph in range(P.BL_PHASES):
                 sh.wait_mask[ph], sh.signal_mask[ph] = int(wait[r, ph]), int(signal[r, ph])
             self.shards.append(sh)
+
+    def tables_on(self, rank, device):
+        """(slices, aux) of ``rank`` as device tensors (uploaded once per plan)."""
+        key = (rank, str(device))
+        t = self._dev.get(key)
+        if t is None:
+            t = self._dev[key] = (torch.from_numpy(self.slices[rank]).to(device),
+                                  torch.from_numpy(self.aux[rank].view(np.int32)).to(device))
+        return t
 
 
 _plan_cache = {}
@@ -272,7 +275,7 @@ class IpcComm:
         self.workspace = _as_tensor(self.ptrs[self.rank], self.nbytes, self.device)
         self.peer_table = torch.tensor(self.ptrs, dtype=torch.int64, device=self.device)
         self.epoch = 0
-        self.stream = None
+        self.fuse_waits = not isinstance(self, LocalComm)   # ranks that share one GPU need the one-warp wait kernels
 
 
 class LocalComm(IpcComm):
@@ -307,21 +310,22 @@ class _ShardedFn(torch.autograd.Function):
         comm.epoch += 1
         shard = plan.shards[r]
         shard.epoch = comm.epoch
-        slices = plan.slices_on(r, dev)
+        slices, aux = plan.tables_on(r, dev)
+        shard.fuse_waits = int(comm.fuse_waits)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         rc = _native.lib().dgvcc_bl_shard_forward(
             _native.ptr(packed.pts), _native.ptr(packed.targets), _native.ptr(packed.meta), _native.ptr(st), _native.ptr(dens),
             plan.batch, hp, wp, plan.total_rows, plan.total_chunks, plan.multi_chunk, float(pp.stride), float(pp.sigma),
             float(pp.bg_ratio), int(pp.use_bg), int(mod.exact_cull), inv_batch, ctypes.byref(shard), _native.ptr(slices),
-            _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), _native.stream_ptr(dev),
+            _native.ptr(aux), _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), _native.stream_ptr(dev),
             mod._event_handles("fwd", 9))
         _native.check(rc, "dgvcc_bl_shard_forward")
-        ctx.saved = (mod, plan, packed, slices, inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own)
+        ctx.saved = (mod, plan, packed, (slices, aux), inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_loss):
-        mod, plan, packed, slices, inv_batch, epoch, shape, dtype, n_own = ctx.saved
+        mod, plan, packed, (slices, aux), inv_batch, epoch, shape, dtype, n_own = ctx.saved
         comm, pp = mod.comm, mod.post_prob
         dev, r = comm.device, comm.rank
         if epoch != comm.epoch:
@@ -329,12 +333,13 @@ class _ShardedFn(torch.autograd.Function):
                                "forward (one forward/backward pair at a time per communicator)")
         shard = plan.shards[r]
         shard.epoch = epoch
+        shard.fuse_waits = int(comm.fuse_waits)
         g = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         grad = torch.empty((max(n_own, 1), plan.hp, plan.wp), dtype=torch.float32, device=dev)
         rc = _native.lib().dgvcc_bl_shard_backward(
             _native.ptr(packed.pts), _native.ptr(packed.meta), plan.batch, plan.hp, plan.wp, plan.total_rows,
             plan.total_chunks, float(pp.stride), float(pp.sigma), int(pp.use_bg), int(mod.exact_cull), inv_batch,
-            _native.ptr(g), ctypes.byref(shard), _native.ptr(slices), _native.ptr(comm.peer_table),
+            _native.ptr(g), ctypes.byref(shard), _native.ptr(slices), _native.ptr(aux), _native.ptr(comm.peer_table),
             _native.ptr(comm.workspace), comm.nbytes, _native.ptr(grad), _native.stream_ptr(dev),
             mod._event_handles("bwd", 6))
         _native.check(rc, "dgvcc_bl_shard_backward")

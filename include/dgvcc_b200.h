@@ -166,6 +166,13 @@ int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta, int batch,
  *   GRAD   finished gradient -> the image's owner;  OUT: local gather into the caller's tensor
  * Receivers combine partials in chunk order exactly like dgvcc_bl_forward / _backward, so loss and gradients are
  * bit-identical to the single-GPU call.  No NCCL on the data path.
+ * The transfers are fused into the kernels: the sweeps (bl_min / bl_z / bl_grad), the row reduction, the selection
+ * and the gradient reduction store their results at home AND on the ranks in the destination mask of the chunk /
+ * image as they produce them, and their last CTA raises the flag; the small consumer kernels wait for the flags in
+ * their own prologue.  Only DENS (caller's tensor -> workspaces) and OUT are separate copy launches, described by
+ * `slices`.  `aux` (DEVICE, uint32): zmask[total_chunks] (ranks that need a chunk's minima / denominator share) |
+ * gmask[total_chunks] (rank that finishes the chunk's image, 0 when this rank does) | img_mask[batch] (other ranks
+ * of an image) | owner_mask[batch] (owner of an image's gradient, 0 when it is the finishing rank itself).
  *
  * All ranks pass the SAME packed points / targets / st_sizes and the same chunk table (the schedule column lists
  * the rank's own chunk ids in its first chunk_hi - chunk_lo slots); density_local / grad_local hold only the
@@ -192,7 +199,8 @@ typedef struct dgvcc_bl_shard {
     uint32_t wait_mask[DGVCC_BL_PHASES];       /* ranks whose flag of phase p this rank waits for     */
     uint32_t signal_mask[DGVCC_BL_PHASES];     /* ranks this rank signals after its slices of phase p */
     uint32_t epoch;
-    int32_t reserved_;
+    int32_t fuse_waits;           /* 1: consumers spin on the flags in their own prologue (one process per GPU);
+                                     0: separate one-warp wait kernels (several ranks sharing one GPU / context)   */
 } dgvcc_bl_shard;
 int dgvcc_bl_shard_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, int world,
                                     dgvcc_bl_layout* out);
@@ -202,13 +210,14 @@ int dgvcc_bl_shard_preload(void);
 int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets, const int32_t* meta, const float* st_sizes,
                            const float* density_local, int batch, int hp, int wp, int64_t total_rows, int total_chunks,
                            int multi_chunk, float stride, float sigma, float bg_ratio, int use_bg, int exact_cull,
-                           float inv_batch, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, void* const* peers,
-                           void* workspace, size_t workspace_bytes, float* loss_out, void* stream, void** events);
+                           float inv_batch, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, const uint32_t* aux,
+                           void* const* peers, void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
+                           void** events);
 int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp, int64_t total_rows,
                             int total_chunks, float stride, float sigma, int use_bg, int exact_cull, float inv_batch,
                             const float* grad_loss, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices,
-                            void* const* peers, void* workspace, size_t workspace_bytes, float* grad_local, void* stream,
-                            void** events);
+                            const uint32_t* aux, void* const* peers, void* workspace, size_t workspace_bytes,
+                            float* grad_local, void* stream, void** events);
 /* `events` (NULL, or caller-created cudaEvent_t handles; NULL entries skipped) are recorded on the stream between the
  * phases, for per-phase timing.  forward: [0] start, [1] after the minima, [2] after push+wait MIN, [3] after bl_z,
  * [4] after push+wait Z and wait DENS, [5] after counts + reduce, [6] after push+wait CNT, [7] after the selection,

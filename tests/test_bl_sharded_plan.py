@@ -58,32 +58,63 @@ def test_exchange_plan_is_consistent(counts, world):
     owners = (np.arange(len(counts)) * 7 + 3) % world     # owners unrelated to where the points fall
     p = ShardPlan(counts, True, world, owners, 24, 32, 1024)
     L, m4 = p.layout, 4 * 24 * 32
+    P = _native
+    b, c = len(counts), p.total_chunks
     assert 0 == L.flags < L.err < L.push_ticket < L.amax and L.gpart != L.minpart and L.total > L.gfinal > 0
-    recv = np.zeros((world, _native.BL_PHASES), dtype=np.uint32)
+    recv = np.zeros((world, P.BL_PHASES), dtype=np.uint32)
     for r in range(world):
         sh, sl = p.shards[r], p.slices[r]
-        assert sh.push_first[0] == 0 and all(sh.push_first[k] <= sh.push_first[k + 1] for k in range(_native.BL_PHASES))
-        for ph in range(_native.BL_PHASES):
+        assert sh.push_first[0] == 0 and all(sh.push_first[k] <= sh.push_first[k + 1] for k in range(P.BL_PHASES))
+        for ph in range(P.BL_PHASES):
+            n = sh.push_first[ph + 1] - sh.push_first[ph]
+            assert n == 0 or ph in (P.BL_PH_DENS, P.BL_PH_OUT)        # every other phase travels inside the kernels
             sent = 0
             for k in range(sh.push_first[ph], sh.push_first[ph + 1]):
                 src_off, dst_off, packed = (int(v) for v in sl[k])
                 nbytes, dst = packed & 0xffffffff, packed >> 32
                 assert 0 < nbytes <= 1 << 30 and nbytes % 4 == 0 and 0 <= dst < world
-                assert dst_off + nbytes <= (L.total if ph != _native.BL_PH_OUT else len(p.owned[r]) * m4)
-                if ph not in (_native.BL_PH_OUT,) and dst != r:
+                assert dst_off + nbytes <= (L.total if ph != P.BL_PH_OUT else len(p.owned[r]) * m4)
+                if ph == P.BL_PH_DENS and dst != r:
                     sent |= 1 << dst
-                    recv[dst, ph] |= np.uint32(1 << r)
-            assert sent == sh.signal_mask[ph]
+            if ph == P.BL_PH_DENS:
+                assert sent == sh.signal_mask[ph]
+            for q in range(world):
+                if sh.signal_mask[ph] >> q & 1:
+                    assert q != r
+                    recv[q, ph] |= np.uint32(1 << r)
         # every image this rank owns is gathered exactly once, into consecutive slots of its gradient tensor
-        out = sl[sh.push_first[_native.BL_PH_OUT]:sh.push_first[_native.BL_PH_OUT + 1]]
+        out = sl[sh.push_first[P.BL_PH_OUT]:sh.push_first[P.BL_PH_OUT + 1]]
         assert sum(int(v[2]) & 0xffffffff for v in out) == len(p.owned[r]) * m4
     for r in range(world):
-        for ph in range(_native.BL_PHASES):
-            assert int(recv[r, ph]) == p.shards[r].wait_mask[ph]      # I wait exactly for those who send to me
-    # density reaches every rank that sweeps an image; gradient sums reach the lead; the finished gradient its owner
-    for i in range(len(counts)):
+        for ph in range(P.BL_PHASES):
+            assert int(recv[r, ph]) == p.shards[r].wait_mask[ph]      # I wait exactly for those who signal me
+    # the destination masks the kernels use agree with the flags
+    for r in range(world):
+        aux = p.aux[r]
+        assert aux.shape == (2 * c + 2 * b,) and aux.dtype == np.uint32
+        zmask, gmask, img_mask, owner_mask = aux[:c], aux[c:2 * c], aux[2 * c:2 * c + b], aux[2 * c + b:]
+        sh = p.shards[r]
+        for ch in range(c):
+            g = set(p.groups[p.c_img[ch]])
+            if p.c_owner[ch] == r:
+                assert zmask[ch] == sum(1 << q for q in g if q != r)
+                lead = int(p.lead[p.c_img[ch]])
+                assert gmask[ch] == (0 if lead == r else 1 << lead)
+            else:
+                assert zmask[ch] == 0 and gmask[ch] == 0
+        z_dst = int(np.bitwise_or.reduce(zmask)) if c else 0
+        assert z_dst == sh.signal_mask[P.BL_PH_Z] == sh.signal_mask[P.BL_PH_MIN]
+        assert (int(np.bitwise_or.reduce(gmask)) if c else 0) == sh.signal_mask[P.BL_PH_GPART]
+        assert int(np.bitwise_or.reduce(img_mask)) == sh.signal_mask[P.BL_PH_CNT]
+        assert int(np.bitwise_or.reduce(owner_mask)) == sh.signal_mask[P.BL_PH_GRAD]
+        for i in range(b):
+            g = p.groups[i]
+            assert img_mask[i] == (sum(1 << q for q in g if q != r) if r in g else 0)
+            assert owner_mask[i] == ((1 << int(owners[i])) if (p.lead[i] == r and owners[i] != r) else 0)
+        leads = sorted(set(int(x) for x in p.lead))
+        assert sh.wait_mask[P.BL_PH_LOSS] == sum(1 << q for q in leads if q != r)
+    # density reaches every rank that sweeps an image
+    for i in range(b):
         for q in p.groups[i]:
             if q != owners[i]:
-                assert p.shards[q].wait_mask[_native.BL_PH_DENS] >> int(owners[i]) & 1
-        if owners[i] != p.lead[i]:
-            assert p.shards[int(owners[i])].wait_mask[_native.BL_PH_GRAD] >> int(p.lead[i]) & 1
+                assert p.shards[q].wait_mask[P.BL_PH_DENS] >> int(owners[i]) & 1

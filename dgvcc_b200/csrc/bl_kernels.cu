@@ -226,9 +226,11 @@ __device__ __forceinline__ void xchg_store(const Xchg& x, unsigned int mask, lon
 }
 
 // Producer epilogue, called by every thread of every CTA of the grid (no early returns before it).
-__device__ __forceinline__ void xchg_signal(const Xchg& x) {
+// `stored`: this thread wrote to a peer (only then does it pay for the system-scope fence; a CTA that kept everything
+// at home just takes its ticket).
+__device__ __forceinline__ void xchg_signal(const Xchg& x, bool stored = true) {
     if (!x.peers) return;
-    __threadfence_system();
+    if (stored) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
@@ -481,15 +483,15 @@ struct ExpCull {
 // minimum over the image's chunks is unchanged, and min is exact, so nothing depends on the order.  (Measured on one
 // GPU: two stages 97 us against 83 us for the single launch -- stage 0 alone leaves most SMs idle.)
 template <int R, int C>
-__device__ __forceinline__ void bl_min_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch,
+__device__ __forceinline__ bool bl_min_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch,
                                             const Geom& g, float* __restrict__ minpart, int stage, int chunk_lo,
                                             const Xchg& x) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return;
-    if (t.n_chunks <= 1) return;  // single-chunk images take the fused path inside bl_z_kernel
+    if (!decode_task<R, C>(meta, batch, g, t)) return false;
+    if (t.n_chunks <= 1) return false;  // single-chunk images take the fused path inside bl_z_kernel
     const int lead = max(t.first_chunk, chunk_lo);   // the image's first chunk on this rank
-    if (stage >= 0 && (t.chunk == lead) != (stage == 0)) return;  // stage < 0: one launch, every chunk on its own
+    if (stage >= 0 && (t.chunk == lead) != (stage == 0)) return false;  // stage < 0: one launch, every chunk on its own
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     PixelTile<R, C> px;
     px.init(t, g);
@@ -511,15 +513,16 @@ __device__ __forceinline__ void bl_min_body(const float2* __restrict__ pts_all, 
                 out[px.pix(r, c)] = mind[r][c];
                 if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + px.pix(r, c), mind[r][c]);
             }
+    return dst != 0u;
 }
 
 template <int R, int C>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
               float* __restrict__ minpart, int stage, int chunk_lo, Xchg x) {
-    bl_min_body<R, C>(pts_all, meta, batch, g, minpart, stage, chunk_lo, x);
-    if (stage != 0) xchg_signal(x);  // stage 0's stores are fenced below; the flag goes up after the last launch
-    else if (x.peers) __threadfence_system();
+    const bool stored = bl_min_body<R, C>(pts_all, meta, batch, g, minpart, stage, chunk_lo, x);
+    if (stage != 0) xchg_signal(x, stored);  // the flag goes up after the last launch; stage 0 only fences its stores
+    else if (stored) __threadfence_system();
 }
 
 // Sharded path: min over the chunks of an image once they have all arrived, so that bl_z_kernel reads one value per
@@ -542,7 +545,7 @@ bl_min_combine_kernel(const int32_t* __restrict__ meta, int batch, int M, int im
 // ------------------------------------------------------------------------------------------ K1
 // Softmax max (incl. the background row, bl.py:39-43) and this chunk's share of the denominator.
 template <int R, int C, bool POW2>
-__device__ __forceinline__ void bl_z_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
+__device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, const Geom& g, const Scale& k, float bg_ratio, int use_bg,
             int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, const Shard& sh,
@@ -550,7 +553,7 @@ __device__ __forceinline__ void bl_z_body(const float2* __restrict__ pts_all, co
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t)) return false;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     PixelTile<R, C> px;
@@ -568,7 +571,7 @@ __device__ __forceinline__ void bl_z_body(const float2* __restrict__ pts_all, co
                     const int p = px.pix(r, c);
                     zout[p] = 0.f; amax_img[p] = 0.f; ebg_img[p] = 1.f;
                 }
-        return;
+        return false;
     }
     const float2* pts = pts_all + t.pt_base;
 
@@ -671,6 +674,7 @@ __device__ __forceinline__ void bl_z_body(const float2* __restrict__ pts_all, co
                 ebg_img[p] = use_bg ? ex2_ftz(ebg_arg[r][c]) : 0.f;
             }
         }
+    return dst != 0u;
 }
 
 template <int R, int C, bool POW2>
@@ -680,9 +684,9 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
             int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, Shard sh,
             const float* __restrict__ min_img, Xchg x) {
-    bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull, minpart, zpart, amax_out,
-                          ebg_out, ticket, sh, min_img, x);
-    xchg_signal(x);
+    const bool stored = bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull, minpart,
+                                              zpart, amax_out, ebg_out, ticket, sh, min_img, x);
+    xchg_signal(x, stored);
 }
 
 // 1 / (sum of the chunk shares in chunk order + background term last), the reference's row order.
@@ -854,7 +858,7 @@ __device__ __forceinline__ float block_sum_ordered(float v, float* scratch) {
 
 // Expected counts: fixed-order sum of the per-tile partials (one thread per posterior row, coalesced
 // across rows), and the residual |t - c|  (bl.py:73-75).
-__device__ __forceinline__ void bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
+__device__ __forceinline__ bool bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
                         float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x);
 
@@ -862,15 +866,15 @@ __global__ void __launch_bounds__(256)
 bl_reduce_counts_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
                         float* __restrict__ counts, float* __restrict__ residual, Shard sh, Xchg x) {
-    bl_reduce_counts_body(cpart, tiles, total_rows, meta, targets, batch, counts, residual, sh, x);
-    xchg_signal(x);
+    const bool stored = bl_reduce_counts_body(cpart, tiles, total_rows, meta, targets, batch, counts, residual, sh, x);
+    xchg_signal(x, stored);
 }
 
-__device__ __forceinline__ void bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
+__device__ __forceinline__ bool bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
                         float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (j >= total_rows) return;
+    if (j >= total_rows) return false;
     const Meta mv = meta_view(meta, batch);
     int lo = 0, hi = batch;  // image of row j: row_off[lo] <= j < row_off[lo+1]
     while (hi - lo > 1) {
@@ -883,7 +887,7 @@ __device__ __forceinline__ void bl_reduce_counts_body(const float* __restrict__ 
         const int gp = mv.pt_off[lo] + local;
         const bool mine = local < n_pts ? (gp >= sh.pt_lo && gp < sh.pt_hi)
                                         : (mv.icb[lo] >= sh.chunk_lo && mv.icb[lo] < sh.chunk_hi);
-        if (!mine) return;
+        if (!mine) return false;
     }
     const float* p = cpart + j;
     float c = 0.f;
@@ -897,7 +901,9 @@ __device__ __forceinline__ void bl_reduce_counts_body(const float* __restrict__ 
         const unsigned int dst = x.mask[lo];
         xchg_store(x, dst, x.region_off, (size_t)j, c);
         xchg_store(x, dst, x.region_off2, (size_t)j, res);
+        return dst != 0u;
     }
+    return false;
 }
 
 __global__ void __launch_bounds__(SELECT_THREADS)
@@ -1040,14 +1046,14 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
 // compacted away while staging.  Single-chunk images store the final gradient; otherwise the raw
 // chunk sum goes to gpart and bl_grad_reduce_kernel finishes.
 template <int R, int C, bool POW2>
-__device__ __forceinline__ void bl_grad_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch,
+__device__ __forceinline__ bool bl_grad_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch,
                const Geom& g, const Scale& k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
                float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, const Xchg& x) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t)) return false;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
@@ -1116,6 +1122,7 @@ __device__ __forceinline__ void bl_grad_body(const float2* __restrict__ pts_all,
                 const size_t m = img_base + px.pix(r, c);
                 grad_density[m] = gscale * fmaf(acc[r][c], rz_in[m], w_bg * pbg_in[m]);
             }
+        return false;
     } else {
         // sharded: chunks of an image finished by another rank go straight (and only) into that rank's workspace
         const unsigned int dst = x.peers ? x.mask[t.chunk] : 0u;
@@ -1128,6 +1135,7 @@ __device__ __forceinline__ void bl_grad_body(const float2* __restrict__ pts_all,
                     if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + px.pix(r, c), acc[r][c]);
                     else out[px.pix(r, c)] = acc[r][c];
                 }
+        return dst != 0u;
     }
 }
 
@@ -1138,13 +1146,13 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
                float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, Xchg x) {
-    bl_grad_body<R, C, POW2>(pts_all, meta, batch, g, k, use_bg, exact_cull, inv_batch, grad_loss, amax_in, rz_in, pbg_in,
-                             wsel, gpart, grad_density, always_partial, x);
-    xchg_signal(x);
+    const bool stored = bl_grad_body<R, C, POW2>(pts_all, meta, batch, g, k, use_bg, exact_cull, inv_batch, grad_loss, amax_in,
+                                                 rz_in, pbg_in, wsel, gpart, grad_density, always_partial, x);
+    xchg_signal(x, stored);
 }
 
 // Multi-chunk images: add the chunk sums in chunk order and apply the per-pixel factors.
-__device__ __forceinline__ void bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
+__device__ __forceinline__ bool bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
                       const float* __restrict__ grad_loss, const float* __restrict__ gpart,
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
                       const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x);
@@ -1155,12 +1163,13 @@ bl_grad_reduce_kernel(const int32_t* __restrict__ meta, int batch, int M, int us
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
                       const float* __restrict__ wsel, float* __restrict__ grad_density, Shard sh, Xchg x, int n_img) {
     xchg_wait(x);  // sharded: the gradient sums of the chunks other ranks swept
+    bool stored = false;
     if ((int)blockIdx.y < n_img)
-        bl_grad_reduce_body(meta, batch, M, use_bg, inv_batch, grad_loss, gpart, rz_in, pbg_in, wsel, grad_density, sh, x);
-    xchg_signal(x);
+        stored = bl_grad_reduce_body(meta, batch, M, use_bg, inv_batch, grad_loss, gpart, rz_in, pbg_in, wsel, grad_density, sh, x);
+    xchg_signal(x, stored);
 }
 
-__device__ __forceinline__ void bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
+__device__ __forceinline__ bool bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
                       const float* __restrict__ grad_loss, const float* __restrict__ gpart,
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
                       const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x) {
@@ -1168,12 +1177,12 @@ __device__ __forceinline__ void bl_grad_reduce_body(const int32_t* __restrict__ 
     const Meta mv = meta_view(meta, batch);
     const int first = mv.icb[img], n_chunks = mv.icb[img + 1] - first;
     if (sh.on) {  // every image is finished by the rank that owns its first chunk, single-chunk images included
-        if (first < sh.chunk_lo || first >= sh.chunk_hi) return;
+        if (first < sh.chunk_lo || first >= sh.chunk_hi) return false;
     } else if (n_chunks <= 1) {
-        return;
+        return false;
     }
     const int pix = blockIdx.x * 256 + threadIdx.x;
-    if (pix >= M) return;
+    if (pix >= M) return false;
     float acc = 0.f;
     for (int c = 0; c < n_chunks; ++c) acc += gpart[(size_t)(first + c) * M + pix];
     const int n_rows = mv.row_off[img + 1] - mv.row_off[img];
@@ -1184,6 +1193,7 @@ __device__ __forceinline__ void bl_grad_reduce_body(const int32_t* __restrict__ 
     const unsigned int dst = x.peers ? x.mask[img] : 0u;  // the image's owner, when that is another rank
     if (dst) xchg_store(x, dst, x.region_off, m, gv);
     else grad_density[m] = gv;
+    return dst != 0u;
 }
 
 // ------------------------------------------------------------------------- posterior (API parity)

@@ -216,6 +216,11 @@ __device__ __forceinline__ void xchg_wait(const Xchg& x) {
     __syncthreads();
 }
 
+// Base of an exchanged array on rank q.
+__device__ __forceinline__ float* xchg_ptr(const Xchg& x, int q, long long region_off) {
+    return reinterpret_cast<float*>(x.peers[q] + region_off);
+}
+
 // One value into the same array of every rank in `mask`.
 __device__ __forceinline__ void xchg_store(const Xchg& x, unsigned int mask, long long region_off, size_t elem, float v) {
     while (mask) {
@@ -509,10 +514,15 @@ __device__ __forceinline__ bool bl_min_body(const float2* __restrict__ pts_all, 
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < C; ++c)
-            if (px.ok(r, c)) {
-                out[px.pix(r, c)] = mind[r][c];
-                if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + px.pix(r, c), mind[r][c]);
-            }
+            if (px.ok(r, c)) out[px.pix(r, c)] = mind[r][c];
+    for (unsigned int m = dst; m; m &= m - 1u) {  // the same tile into the workspaces of the image's other ranks
+        float* rp = xchg_ptr(x, __ffs(m) - 1, x.region_off) + (size_t)t.chunk * M;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (px.ok(r, c)) rp[px.pix(r, c)] = mind[r][c];
+    }
     return dst != 0u;
 }
 
@@ -668,12 +678,19 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
             if (!px.ok(r, c)) continue;
             const int p = px.pix(r, c);
             zout[p] = z[r][c];
-            if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + p, z[r][c]);
             if (first) {
                 amax_img[p] = amax_v[r][c];
                 ebg_img[p] = use_bg ? ex2_ftz(ebg_arg[r][c]) : 0.f;
             }
         }
+    for (unsigned int m = dst; m; m &= m - 1u) {  // the same tile into the workspaces of the image's other ranks
+        float* rp = xchg_ptr(x, __ffs(m) - 1, x.region_off) + (size_t)t.chunk * M;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (px.ok(r, c)) rp[px.pix(r, c)] = z[r][c];
+    }
     return dst != 0u;
 }
 
@@ -1126,15 +1143,12 @@ __device__ __forceinline__ bool bl_grad_body(const float2* __restrict__ pts_all,
     } else {
         // sharded: chunks of an image finished by another rank go straight (and only) into that rank's workspace
         const unsigned int dst = x.peers ? x.mask[t.chunk] : 0u;
-        float* out = gpart + (size_t)t.chunk * M;
+        float* out = (dst ? xchg_ptr(x, __ffs(dst) - 1, x.region_off) : gpart) + (size_t)t.chunk * M;
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int c = 0; c < C; ++c)
-                if (px.ok(r, c)) {
-                    if (dst) xchg_store(x, dst, x.region_off, (size_t)t.chunk * M + px.pix(r, c), acc[r][c]);
-                    else out[px.pix(r, c)] = acc[r][c];
-                }
+                if (px.ok(r, c)) out[px.pix(r, c)] = acc[r][c];
         return dst != 0u;
     }
 }
@@ -1802,6 +1816,7 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
     mark(events, 0, st);
     // density of the images this rank owns -> every rank that sweeps them (needed from bl_counts on)
     if ((rc = shard_push(c, DGVCC_BL_PH_DENS, density_local))) return rc;
+    mark(events, 1, st);
     // per-chunk minima of the images cut into several chunks, stored at home and on the image's other ranks; the flag
     // goes up with the second stage
     if (multi_chunk) {
@@ -1818,17 +1833,17 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
             else if (p.v.rows == 4) bl_min_kernel<4, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
             else bl_min_kernel<2, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
             DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+            mark(events, 2 + stage, st);
         }
     }
-    mark(events, 1, st);
     if (multi_chunk && (rc = shard_wait(c, DGVCC_BL_PH_MIN))) return rc;
-    mark(events, 2, st);
     float* min_img = at<float>(workspace, p.L.pbg);  // the region is free until bl_finish_z_kernel fills it
     if (multi_chunk && (n_img > 0 || (shard->fuse_waits && shard->wait_mask[DGVCC_BL_PH_MIN]))) {
         bl_min_combine_kernel<<<pix_grid, 256, 0, st>>>(meta, batch, M, p.sh.img_lo, at<float>(workspace, p.L.minpart), min_img,
                                                        c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_MIN, -1), n_img);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    mark(events, 4, st);
     {
         const Xchg x = c.make(DGVCC_BL_PH_Z, c.zmask(), p.L.zpart, 0, -1, -1);
         if (sweeps) {
@@ -1840,14 +1855,14 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         }
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
-    mark(events, 3, st);
+    mark(events, 5, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_Z))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_DENS))) return rc;
-    mark(events, 4, st);
     bl_finish_z_kernel<<<pix_grid, 256, 0, st>>>(meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg),
                                                  at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), p.sh.img_lo,
                                                  c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_Z, DGVCC_BL_PH_DENS), n_img);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    mark(events, 6, st);
     if (sweeps) {
         BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
                     use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
@@ -1855,25 +1870,25 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
                     at<float>(workspace, p.L.cpart), p.sh, 1);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    mark(events, 7, st);
     // fixed-order sums of the tile partials of this rank's rows, delivered to the image's other ranks as they are written
     bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
         at<float>(workspace, p.L.cpart), p.L.tiles, total_rows, meta, targets, batch, at<float>(workspace, p.L.counts),
         at<float>(workspace, p.L.residual), p.sh, c.make(DGVCC_BL_PH_CNT, c.img_mask(), p.L.counts, p.L.residual, -1, -1));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    mark(events, 5, st);
+    mark(events, 8, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_CNT))) return rc;
-    mark(events, 6, st);
     // top-k cut and per-image loss of every image this rank touches; the rank with an image's first chunk tells everybody
     bl_select_kernel<<<n_img > 0 ? n_img : 1, SELECT_THREADS, 0, st>>>(
         meta, targets, batch, inv_batch, at<float>(workspace, p.L.counts), at<float>(workspace, p.L.residual),
         at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.loss_img), loss_out, at<unsigned int>(workspace, p.L.ticket),
         p.sh.img_lo, 0, p.sh, c.make(DGVCC_BL_PH_LOSS, nullptr, p.L.loss_img, 0, DGVCC_BL_PH_CNT, -1), n_img);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    mark(events, 7, st);
+    mark(events, 9, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_LOSS))) return rc;
     bl_loss_finish_kernel<<<1, 64, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out,
                                             c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_LOSS, -1));
-    mark(events, 8, st);
+    mark(events, 10, st);
     return (int)cudaGetLastError();
 }
 
@@ -1909,20 +1924,18 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
     }
     mark(events, 1, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_GPART))) return rc;
-    mark(events, 2, st);
     // chunk sums added in chunk order, per-pixel factors applied, the result written at the image's owner
     bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), n_img > 0 ? n_img : 1), 256, 0, st>>>(
         meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart), at<float>(workspace, p.L.rz),
         at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gfinal), p.sh,
         c.make(DGVCC_BL_PH_GRAD, c.owner_mask(), p.L.gfinal, 0, DGVCC_BL_PH_GPART, -1), n_img);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    mark(events, 3, st);
+    mark(events, 2, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_GRAD))) return rc;
-    mark(events, 4, st);
     // the finished gradients of this rank's own images, gathered into the caller's tensor
     if (shard->push_first[DGVCC_BL_PH_OUT + 1] > shard->push_first[DGVCC_BL_PH_OUT] && !grad_local) return DGVCC_ERR_ARG;
     rc = shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local ? (void*)grad_local : workspace, DGVCC_BL_PH_GRAD);
-    mark(events, 5, st);
+    mark(events, 3, st);
     return rc;
 }
 

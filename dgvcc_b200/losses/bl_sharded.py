@@ -202,6 +202,9 @@ class ShardPlan:
 _plan_cache = {}
 
 
+FORCE_CHUNK = None   # experiments: points per chunk of the sharded plan, whatever the world size
+
+
 def shard_chunk_points(total_points, world):
     """Points per chunk for a batch spread over ``world`` ranks.  One rank sweeps total / world points; cutting them into
     ~64 chunks (x 24 CTAs of four pixel tiles each) gives every SM several rounds of short CTAs, so the ragged last
@@ -209,6 +212,8 @@ def shard_chunk_points(total_points, world):
     a third of one round.  Small chunks are affordable because the sharded path reduces the per-chunk partials in
     separate kernels (bl_min_combine / bl_finish_z) and bounds the min sweep of later chunks by the first one.  Never
     above the single-GPU chunk size, never below 128 (the sweeps stage 128 points at a time), a multiple of 32."""
+    if FORCE_CHUNK:
+        return int(FORCE_CHUNK)
     want = max(1, total_points // (max(world, 1) * 64))
     return int(min(_bl.chunk_points(), max(128, -(-want // 32) * 32)))
 
@@ -318,7 +323,7 @@ class _ShardedFn(torch.autograd.Function):
             plan.batch, hp, wp, plan.total_rows, plan.total_chunks, plan.multi_chunk, float(pp.stride), float(pp.sigma),
             float(pp.bg_ratio), int(pp.use_bg), int(mod.exact_cull), inv_batch, ctypes.byref(shard), _native.ptr(slices),
             _native.ptr(aux), _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), _native.stream_ptr(dev),
-            mod._event_handles("fwd", 9))
+            mod._event_handles("fwd", 11))
         _native.check(rc, "dgvcc_bl_shard_forward")
         ctx.saved = (mod, plan, packed, (slices, aux), inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own)
         return loss.reshape(())
@@ -341,7 +346,7 @@ class _ShardedFn(torch.autograd.Function):
             plan.total_chunks, float(pp.stride), float(pp.sigma), int(pp.use_bg), int(mod.exact_cull), inv_batch,
             _native.ptr(g), ctypes.byref(shard), _native.ptr(slices), _native.ptr(aux), _native.ptr(comm.peer_table),
             _native.ptr(comm.workspace), comm.nbytes, _native.ptr(grad), _native.stream_ptr(dev),
-            mod._event_handles("bwd", 6))
+            mod._event_handles("bwd", 4))
         _native.check(rc, "dgvcc_bl_shard_backward")
         return (grad[:n_own].reshape(shape).to(dtype),) + (None,) * 5
 
@@ -399,9 +404,10 @@ class ChunkShardedBL(Module):
         st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()
         return _ShardedFn.apply(pre_density_local, self, plan, packed, st, 1.0 / plan.batch)
 
-    FWD_PHASES = ["min", "push+wait MIN", "z", "push+wait Z, wait DENS", "counts+reduce", "push+wait CNT", "select",
-                  "push+wait LOSS + loss"]
-    BWD_PHASES = ["grad", "push+wait GPART", "reduce", "push+wait GRAD", "gather"]
+    FWD_PHASES = ["push DENS", "min stage 0", "min stage 1 (+MIN out)", "[wait MIN] combine", "z (+Z out)",
+                  "[wait Z, DENS] finish_z", "counts", "reduce_counts (+CNT out)", "[wait CNT] select (+LOSS out)",
+                  "[wait LOSS] loss"]
+    BWD_PHASES = ["grad (+GPART out)", "[wait GPART] reduce (+GRAD out)", "[wait GRAD] gather"]
 
     def _event_handles(self, which, n):
         """None, or ctypes array of cudaEvent_t for the per-phase timing (``profile = True``)."""

@@ -219,10 +219,9 @@ int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch,
                             const uint32_t* aux, void* const* peers, void* workspace, size_t workspace_bytes,
                             float* grad_local, void* stream, void** events);
 /* `events` (NULL, or caller-created cudaEvent_t handles; NULL entries skipped) are recorded on the stream between the
- * phases, for per-phase timing.  forward: [0] start, [1] after the minima, [2] after push+wait MIN, [3] after bl_z,
- * [4] after push+wait Z and wait DENS, [5] after counts + reduce, [6] after push+wait CNT, [7] after the selection,
- * [8] after push+wait LOSS and the loss.  backward: [0] start, [1] after bl_grad, [2] after push+wait GPART,
- * [3] after the reduction, [4] after push+wait GRAD, [5] after the gather. */
+ * launches, for per-kernel timing.  forward (11): start, after the DENS copy, min stage 0, min stage 1, [wait MIN] combine,
+ * bl_z, [wait Z, DENS] finish_z, bl_counts, the row reduction, [wait CNT] selection, [wait LOSS] loss.
+ * backward (4): start, bl_grad, [wait GPART] reduction, [wait GRAD] gather. */
 
 /* Peer-visible device memory for the sharded workspaces (CUDA IPC between the ranks' processes of one box):
  * alloc = cudaMalloc + zero fill; export writes the 64-byte handle a peer process passes to open, which maps the

@@ -24,6 +24,8 @@ import torch.distributed as dist  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--chunks", default="", help="comma-separated chunk sizes to time on config 3 (default: the plan's own choice)")
+    ap.add_argument("--no-checks", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -35,7 +37,7 @@ def main():
     from helpers import load_bl_golden
 
     comm = IpcComm(device=dev)
-    out = {"world": world, "checks": {}}
+    out = out_checks = {"world": world, "checks": {}}
 
     def case(name):
         if name.startswith("config"):
@@ -59,7 +61,7 @@ def main():
         return loss.detach(), d.grad
 
     ok_all = True
-    for name, chunk in (("mixed", 29), ("config2", 1024), ("config3", 1024)):
+    for name, chunk in (() if args.no_checks else (("mixed", 29), ("config2", 1024), ("config3", 1024))):
         blmod._CHUNK_POINTS = chunk   # upper bound; the sharded plan picks smaller chunks for larger worlds
         pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = case(name)
         b, _, hp, wp = dens.shape
@@ -82,60 +84,66 @@ def main():
             out["checks"][f"{name}_cull{int(cull)}"] = bool(flag.item())
             ok_all = ok_all and bool(flag.item())
 
-    # ---- timing: config 3, dense
-    blmod._CHUNK_POINTS = 1024
-    pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = case("config3")
-    b, _, hp, wp = dens.shape
-    plan = plan_shards([len(p) for p in pts], use_bg, world, None, hp, wp)
-    mod = ChunkShardedBL(sigma, 2048, stride, bg_ratio, use_bg, dev, comm)
-    mod.exact_cull = False
-    local_d = dens[plan.owned[rank]].to(dev).clone().requires_grad_(True)
-    st_d = st.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    results = {}
+    for forced in ([int(c) for c in args.chunks.split(",")] if args.chunks else [None]):
+        # ---- timing: config 3, dense
+        blmod._CHUNK_POINTS = 1024
+        from dgvcc_b200.losses import bl_sharded
+        bl_sharded.FORCE_CHUNK = forced
+        pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = case("config3")
+        b, _, hp, wp = dens.shape
+        plan = plan_shards([len(p) for p in pts], use_bg, world, None, hp, wp)
+        mod = ChunkShardedBL(sigma, 2048, stride, bg_ratio, use_bg, dev, comm)
+        mod.exact_cull = False
+        local_d = dens[plan.owned[rank]].to(dev).clone().requires_grad_(True)
+        st_d = st.to(dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step():
-        local_d.grad = None
-        loss = mod(pts, st_d, tgt, local_d)
-        loss.backward()
+        def step():
+            local_d.grad = None
+            loss = mod(pts, st_d, tgt, local_d)
+            loss.backward()
 
-    for _ in range(5):
-        step()
-        flush.zero_()
-    torch.cuda.synchronize()
-    dist.barrier()
-    evs = []
-    for _ in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        evs.append((e0, e1))
-        flush.zero_()
-    torch.cuda.synchronize()
-    dist.barrier()
-    mod.check()
-    ms = sum(a.elapsed_time(c) for a, c in evs) / args.steps
-    allms = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
-    dist.all_gather(allms, torch.tensor([ms], device=dev, dtype=torch.float64))
-    allms = [float(x[0]) for x in allms]
-    # per-phase device times (CUDA events recorded between the launches), averaged over a few steps
-    mod.profile = True
-    acc = {}
-    for _ in range(5):
-        step()
-        for k, v in mod.phase_ms().items():
-            acc[k] = acc.get(k, 0.0) + v / 5
-        flush.zero_()
-    mod.profile = False
-    phases = [None] * world
-    dist.all_gather_object(phases, acc)
+        for _ in range(5):
+            step()
+            flush.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        evs = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            evs.append((e0, e1))
+            flush.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        mod.check()
+        ms = sum(a.elapsed_time(c) for a, c in evs) / args.steps
+        allms = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms], device=dev, dtype=torch.float64))
+        allms = [float(x[0]) for x in allms]
+        # per-phase device times (CUDA events recorded between the launches), averaged over a few steps
+        mod.profile = True
+        acc = {}
+        for _ in range(5):
+            step()
+            for k, v in mod.phase_ms().items():
+                acc[k] = acc.get(k, 0.0) + v / 5
+            flush.zero_()
+        mod.profile = False
+        phases = [None] * world
+        dist.all_gather_object(phases, acc)
+        if rank == 0:
+            out = results.setdefault(str(forced or "auto"), {})
+            out["phase_ms_rank0"] = {k: round(v, 4) for k, v in phases[0].items()}
+            out["phase_ms_max_over_ranks"] = {k: round(max(p[k] for p in phases), 4) for k in phases[0]}
+            out["phase_sum_ms_per_rank"] = [round(sum(p.values()), 4) for p in phases]
+            out.update({"config3_ms_per_rank": allms, "config3_ms_per_step": max(allms), "images_per_s": b / (max(allms) * 1e-3),
+                        "chunks": plan.total_chunks, "chunk_points": int(plan.c_cnt.max()), "groups": [len(g) for g in plan.groups]})
     if rank == 0:
-        out["phase_ms_rank0"] = {k: round(v, 4) for k, v in phases[0].items()}
-        out["phase_ms_max_over_ranks"] = {k: round(max(p[k] for p in phases), 4) for k in phases[0]}
-        out["phase_sum_ms_per_rank"] = [round(sum(p.values()), 4) for p in phases]
-        out.update({"config3_ms_per_rank": allms, "config3_ms_per_step": max(allms), "images_per_s": b / (max(allms) * 1e-3),
-                    "chunks": plan.total_chunks, "chunk_points": int(plan.c_cnt.max()), "groups": [len(g) for g in plan.groups], "ok": ok_all})
-        print(json.dumps(out), flush=True)
+        print(json.dumps({"world": world, "checks": out_checks["checks"], "ok": ok_all, "timing": results}), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)
 

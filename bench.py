@@ -415,6 +415,7 @@ def strong_scaling(args, dev, rank, world, t1_ms, flush, barrier):
     comm = IpcComm(device=dev)
     cmod = ChunkShardedBL(SIGMA, max(wl["width"], wl["height"]), STRIDE, BG_RATIO, USE_BG, dev, comm)
     cmod.exact_cull = False
+    cmod.defer_loss = True   # a training step calls loss.backward() before it reads the value
     plan = plan_shards(wl["counts"], USE_BG, world, None, wl["hp"], wl["wp"])
     local_d = wl["density"][plan.owned[rank]].to(dev).requires_grad_(True)
     st_all = wl["st_sizes"].to(dev)

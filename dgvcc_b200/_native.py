@@ -74,10 +74,11 @@ SIGNATURES = {
     "dgvcc_bl_shard_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
     "dgvcc_bl_shard_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                        c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, POINTER(BLShard),
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p,
+                                       POINTER(c_void_p)]),
     "dgvcc_bl_shard_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_float, c_float, c_int,
                                         c_int, c_float, c_void_p, POINTER(BLShard), c_void_p, c_void_p, c_void_p, c_void_p,
-                                        c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
+                                        c_size_t, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
     "dgvcc_bl_shard_preload": (c_int, []),
     "dgvcc_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "dgvcc_peer_free": (c_int, [c_void_p]),

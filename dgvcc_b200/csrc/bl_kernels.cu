@@ -235,7 +235,9 @@ __device__ __forceinline__ void xchg_store(const Xchg& x, unsigned int mask, lon
 // at home just takes its ticket).
 __device__ __forceinline__ void xchg_signal(const Xchg& x, bool stored = true) {
     if (!x.peers) return;
-    if (stored) __threadfence_system();
+    // device-scope fence per storing thread, ONE system-scope fence by the thread that raises the flags: the ticket
+    // (device scope) orders every CTA's stores before the last CTA's fence.sys, which is cumulative
+    if (stored) __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
@@ -532,7 +534,7 @@ bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ me
               float* __restrict__ minpart, int stage, int chunk_lo, Xchg x) {
     const bool stored = bl_min_body<R, C>(pts_all, meta, batch, g, minpart, stage, chunk_lo, x);
     if (stage != 0) xchg_signal(x, stored);  // the flag goes up after the last launch; stage 0 only fences its stores
-    else if (stored) __threadfence_system();
+    else if (stored) __threadfence();
 }
 
 // Sharded path: min over the chunks of an image once they have all arrived, so that bl_z_kernel reads one value per
@@ -1474,7 +1476,7 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     if (world > 0) {  // fixed offsets, whatever the batch: the flags outlive a step (they are compared with the epoch)
         L->flags = take((size_t)DGVCC_BL_PHASES * 32 * sizeof(unsigned int));
         L->err = take(sizeof(int));
-        L->push_ticket = take(sizeof(unsigned int));
+        L->push_ticket = take(2 * sizeof(unsigned int));  // [0] fused producers (main stream), [1] the DENS copy (side stream)
     }
     L->amax = take(pix); L->rz = take(pix); L->pbg = take(pix); L->ebg = take(pix);
     L->counts = take(rows); L->wsel = take(rows); L->residual = take(rows);
@@ -1726,7 +1728,7 @@ int shard_push(const ShardCtx& c, int ph, const void* src_base, void* dst_overri
         if (n <= 0) return DGVCC_OK;
         bl_push_kernel<<<n, PUSH_THREADS, 0, c.st>>>(c.slices + first, n, (const char*)src_base, c.peers, c.L->flags, ph,
                                                      c.sh->rank, c.sh->world, c.sh->signal_mask[ph], c.sh->epoch,
-                                                     at<unsigned int>(c.ws, c.L->push_ticket));
+                                                     at<unsigned int>(c.ws, c.L->push_ticket) + 1);  // own counter: side stream
     } else {
         const Xchg x = c.make(-1, nullptr, 0, 0, wait_ph, -1);
         if (n <= 0 && !x.wait_mask) return DGVCC_OK;
@@ -1742,6 +1744,26 @@ int shard_wait(const ShardCtx& c, int ph) {
     bl_wait_kernel<<<1, 32, 0, c.st>>>(at<unsigned int>(c.ws, c.L->flags), ph, c.sh->world, c.sh->wait_mask[ph],
                                        c.sh->epoch, XCHG_TIMEOUT_NS, at<int>(c.ws, c.L->err));
     return (int)cudaGetLastError();
+}
+
+// The density copy (owner -> sweeping ranks) is needed only by bl_counts, four kernels into the step: it runs on a
+// side stream of the library (one per device, created on first use) between two events, so it costs the step nothing.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+    static SideStream side[64];
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
+    SideStream& s = side[d];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)
+            return nullptr;
+    }
+    return &s;
 }
 
 bool shard_args_ok(const dgvcc_bl_shard* sh, const dgvcc_bl_push* slices, const void* aux, void* const* peers) {
@@ -1798,7 +1820,7 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
                                       float bg_ratio, int use_bg, int exact_cull, float inv_batch,
                                       const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, const uint32_t* aux,
                                       void* const* peers, void* workspace, size_t workspace_bytes, float* loss_out,
-                                      void* stream, void** events) {
+                                      int defer_loss, void* stream, void** events) {
     DGVCC_DEVICE_GUARD(stream);
     if (!shard_args_ok(shard, slices, aux, peers)) return DGVCC_ERR_ARG;
     Plan p;
@@ -1814,8 +1836,18 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
     const int M = hp * wp;
     const dim3 pix_grid(ceil_div(M, 256), n_img > 0 ? n_img : 1);
     mark(events, 0, st);
-    // density of the images this rank owns -> every rank that sweeps them (needed from bl_counts on)
-    if ((rc = shard_push(c, DGVCC_BL_PH_DENS, density_local))) return rc;
+    // density of the images this rank owns -> every rank that sweeps them (needed from bl_counts on): on the side stream
+    SideStream* side = shard->push_first[DGVCC_BL_PH_DENS + 1] > shard->push_first[DGVCC_BL_PH_DENS] ? side_stream() : nullptr;
+    if (side) {
+        DGVCC_RETURN_IF_CUDA(cudaEventRecord(side->fork, st));
+        DGVCC_RETURN_IF_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        ShardCtx cs = c;
+        cs.st = side->stream;
+        if ((rc = shard_push(cs, DGVCC_BL_PH_DENS, density_local))) return rc;
+        DGVCC_RETURN_IF_CUDA(cudaEventRecord(side->join, side->stream));
+    } else if ((rc = shard_push(c, DGVCC_BL_PH_DENS, density_local))) {
+        return rc;
+    }
     mark(events, 1, st);
     // per-chunk minima of the images cut into several chunks, stored at home and on the image's other ranks; the flag
     // goes up with the second stage
@@ -1856,6 +1888,7 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     mark(events, 5, st);
+    if (side) DGVCC_RETURN_IF_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // this rank's own copies are in place
     if ((rc = shard_wait(c, DGVCC_BL_PH_Z))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_DENS))) return rc;
     bl_finish_z_kernel<<<pix_grid, 256, 0, st>>>(meta, batch, M, at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.ebg),
@@ -1885,9 +1918,13 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         p.sh.img_lo, 0, p.sh, c.make(DGVCC_BL_PH_LOSS, nullptr, p.L.loss_img, 0, DGVCC_BL_PH_CNT, -1), n_img);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 9, st);
-    if ((rc = shard_wait(c, DGVCC_BL_PH_LOSS))) return rc;
-    bl_loss_finish_kernel<<<1, 64, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out,
-                                            c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_LOSS, -1));
+    // the images' losses from all ranks, summed in image order -- a barrier over the whole group, which the backward
+    // pass does not need: with defer_loss the same two launches close dgvcc_bl_shard_backward instead
+    if (!defer_loss) {
+        if ((rc = shard_wait(c, DGVCC_BL_PH_LOSS))) return rc;
+        bl_loss_finish_kernel<<<1, 64, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out,
+                                                c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_LOSS, -1));
+    }
     mark(events, 10, st);
     return (int)cudaGetLastError();
 }
@@ -1897,7 +1934,7 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
                                        int exact_cull, float inv_batch, const float* grad_loss,
                                        const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, const uint32_t* aux,
                                        void* const* peers, void* workspace, size_t workspace_bytes, float* grad_local,
-                                       void* stream, void** events) {
+                                       float* deferred_loss_out, void* stream, void** events) {
     DGVCC_DEVICE_GUARD(stream);
     if (!shard_args_ok(shard, slices, aux, peers)) return DGVCC_ERR_ARG;
     Plan p;
@@ -1936,6 +1973,13 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
     if (shard->push_first[DGVCC_BL_PH_OUT + 1] > shard->push_first[DGVCC_BL_PH_OUT] && !grad_local) return DGVCC_ERR_ARG;
     rc = shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local ? (void*)grad_local : workspace, DGVCC_BL_PH_GRAD);
     mark(events, 3, st);
+    if (rc == DGVCC_OK && deferred_loss_out) {  // the loss of a forward that ran with defer_loss
+        if ((rc = shard_wait(c, DGVCC_BL_PH_LOSS))) return rc;
+        bl_loss_finish_kernel<<<1, 64, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, deferred_loss_out,
+                                                c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_LOSS, -1));
+        rc = (int)cudaGetLastError();
+    }
+    mark(events, 4, st);
     return rc;
 }
 

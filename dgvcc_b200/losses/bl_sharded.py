@@ -318,19 +318,22 @@ class _ShardedFn(torch.autograd.Function):
         slices, aux = plan.tables_on(r, dev)
         shard.fuse_waits = int(comm.fuse_waits)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        # deferred loss: only when a backward pass will follow (it carries the closing launches)
+        defer = bool(mod.defer_loss and ctx.needs_input_grad[0])
         rc = _native.lib().dgvcc_bl_shard_forward(
             _native.ptr(packed.pts), _native.ptr(packed.targets), _native.ptr(packed.meta), _native.ptr(st), _native.ptr(dens),
             plan.batch, hp, wp, plan.total_rows, plan.total_chunks, plan.multi_chunk, float(pp.stride), float(pp.sigma),
             float(pp.bg_ratio), int(pp.use_bg), int(mod.exact_cull), inv_batch, ctypes.byref(shard), _native.ptr(slices),
-            _native.ptr(aux), _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), _native.stream_ptr(dev),
+_native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), int(defer), _native.stream_ptr(dev),
             mod._event_handles("fwd", 11))
         _native.check(rc, "dgvcc_bl_shard_forward")
-        ctx.saved = (mod, plan, packed, (slices, aux), inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own)
+        ctx.saved = (mod, plan, packed, (slices, aux), inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own,
+                     loss if defer else None)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_loss):
-        mod, plan, packed, (slices, aux), inv_batch, epoch, shape, dtype, n_own = ctx.saved
+        mod, plan, packed, (slices, aux), inv_batch, epoch, shape, dtype, n_own, deferred = ctx.saved
         comm, pp = mod.comm, mod.post_prob
         dev, r = comm.device, comm.rank
         if epoch != comm.epoch:
@@ -345,8 +348,8 @@ class _ShardedFn(torch.autograd.Function):
             _native.ptr(packed.pts), _native.ptr(packed.meta), plan.batch, plan.hp, plan.wp, plan.total_rows,
             plan.total_chunks, float(pp.stride), float(pp.sigma), int(pp.use_bg), int(mod.exact_cull), inv_batch,
             _native.ptr(g), ctypes.byref(shard), _native.ptr(slices), _native.ptr(aux), _native.ptr(comm.peer_table),
-            _native.ptr(comm.workspace), comm.nbytes, _native.ptr(grad), _native.stream_ptr(dev),
-            mod._event_handles("bwd", 4))
+            _native.ptr(comm.workspace), comm.nbytes, _native.ptr(grad), _native.ptr(deferred), _native.stream_ptr(dev),
+            mod._event_handles("bwd", 5))
         _native.check(rc, "dgvcc_bl_shard_backward")
         return (grad[:n_own].reshape(shape).to(dtype),) + (None,) * 5
 
@@ -383,6 +386,11 @@ class ChunkShardedBL(Module):
         self.bay_loss = _bl.Bay_Loss(use_background, device)
         self.comm = comm
         self.exact_cull = True
+        # The images' losses come from all ranks: waiting for them is a barrier over the whole group that the backward pass
+        # does not need.  With defer_loss (and a backward pass to follow) the forward returns at once and the backward
+        # launches close with that wait: the returned tensor holds the loss once ``backward()`` has been called --
+        # the usual order of a training step (``loss.backward(); loss.item()``).  False: complete after forward.
+        self.defer_loss = False
         self._last = None   # (key, packed): a benchmark / test that feeds the same lists again skips the re-pack
 
     def forward(self, points, st_sizes, target_list, pre_density_local, owners=None):
@@ -407,7 +415,7 @@ class ChunkShardedBL(Module):
     FWD_PHASES = ["push DENS", "min stage 0", "min stage 1 (+MIN out)", "[wait MIN] combine", "z (+Z out)",
                   "[wait Z, DENS] finish_z", "counts", "reduce_counts (+CNT out)", "[wait CNT] select (+LOSS out)",
                   "[wait LOSS] loss"]
-    BWD_PHASES = ["grad (+GPART out)", "[wait GPART] reduce (+GRAD out)", "[wait GRAD] gather"]
+    BWD_PHASES = ["grad (+GPART out)", "[wait GPART] reduce (+GRAD out)", "[wait GRAD] gather", "[wait LOSS] deferred loss"]
 
     def _event_handles(self, which, n):
         """None, or ctypes array of cudaEvent_t for the per-phase timing (``profile = True``)."""

@@ -211,17 +211,21 @@ int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets, const int3
                            const float* density_local, int batch, int hp, int wp, int64_t total_rows, int total_chunks,
                            int multi_chunk, float stride, float sigma, float bg_ratio, int use_bg, int exact_cull,
                            float inv_batch, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, const uint32_t* aux,
-                           void* const* peers, void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
-                           void** events);
+                           void* const* peers, void* workspace, size_t workspace_bytes, float* loss_out, int defer_loss,
+                           void* stream, void** events);
 int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp, int64_t total_rows,
                             int total_chunks, float stride, float sigma, int use_bg, int exact_cull, float inv_batch,
                             const float* grad_loss, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices,
                             const uint32_t* aux, void* const* peers, void* workspace, size_t workspace_bytes,
-                            float* grad_local, void* stream, void** events);
+                            float* grad_local, float* deferred_loss_out, void* stream, void** events);
+/* defer_loss != 0: the forward does not wait for the other ranks' per-image losses (a barrier over the whole group that the
+ * backward pass does not need); loss_out is then written by dgvcc_bl_shard_backward(deferred_loss_out = the same pointer),
+ * i.e. the loss value is complete once the backward launches have run.  The density copy runs on a side stream owned
+ * by the library (one per device), forked from and joined to `stream` by events. */
 /* `events` (NULL, or caller-created cudaEvent_t handles; NULL entries skipped) are recorded on the stream between the
  * launches, for per-kernel timing.  forward (11): start, after the DENS copy, min stage 0, min stage 1, [wait MIN] combine,
  * bl_z, [wait Z, DENS] finish_z, bl_counts, the row reduction, [wait CNT] selection, [wait LOSS] loss.
- * backward (4): start, bl_grad, [wait GPART] reduction, [wait GRAD] gather. */
+ * backward (5): start, bl_grad, [wait GPART] reduction, [wait GRAD] gather, [wait LOSS] deferred loss. */
 
 /* Peer-visible device memory for the sharded workspaces (CUDA IPC between the ranks' processes of one box):
  * alloc = cudaMalloc + zero fill; export writes the 64-byte handle a peer process passes to open, which maps the

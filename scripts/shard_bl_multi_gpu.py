@@ -69,6 +69,7 @@ def main():
         mod = ChunkShardedBL(sigma, max(hp, wp) * stride, stride, bg_ratio, use_bg, dev, comm)
         for cull in (False, True):
             mod.exact_cull = cull
+            mod.defer_loss = cull
             local_d = dens[plan.owned[rank]].to(dev).clone().requires_grad_(True)
             for _ in range(3):  # several steps: flags, epochs and buffer re-use
                 local_d.grad = None
@@ -95,6 +96,7 @@ def main():
         plan = plan_shards([len(p) for p in pts], use_bg, world, None, hp, wp)
         mod = ChunkShardedBL(sigma, 2048, stride, bg_ratio, use_bg, dev, comm)
         mod.exact_cull = False
+        mod.defer_loss = True   # a training step: loss.backward() first, the value is read afterwards
         local_d = dens[plan.owned[rank]].to(dev).clone().requires_grad_(True)
         st_d = st.to(dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

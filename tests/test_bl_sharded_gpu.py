@@ -35,7 +35,7 @@ def single_gpu_with_table(plan, points, targets, st, dens, stride, sigma, bg_rat
     return loss.detach().cpu(), d.grad.cpu()
 
 
-def run_sharded(world, points, targets, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners=None, steps=1):
+def run_sharded(world, points, targets, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners=None, steps=1, defer=False):
     from dgvcc_b200.losses.bl_sharded import ChunkShardedBL, LocalComm, plan_shards
     dev = torch.device("cuda:0")
     b, _, hp, wp = dens.shape
@@ -44,6 +44,7 @@ def run_sharded(world, points, targets, st, dens, stride, sigma, bg_ratio, use_b
     mods = [ChunkShardedBL(sigma, max(hp, wp) * stride, stride, bg_ratio, use_bg, dev, c) for c in comms]
     for m in mods:
         m.exact_cull = cull
+        m.defer_loss = defer   # the loss value then completes with the backward launches
     streams = [torch.cuda.Stream(dev) for _ in range(world)]
     # torch's own kernels are loaded lazily too: run the ones a step uses once before any wait kernel can be spinning
     warm = torch.zeros((2, 1, hp, wp), device=dev, requires_grad=True)
@@ -89,7 +90,8 @@ def test_sharded_ranks_reproduce_one_gpu_bit_for_bit(name, world, monkeypatch):
     pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = _case(name)
     owners = [(3 * i + 1) % world for i in range(len(pts))]          # density owners unrelated to where the points fall
     for cull in (False, True):
-        losses, grad, plan = run_sharded(world, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners, steps=2)
+        losses, grad, plan = run_sharded(world, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners, steps=2,
+                                         defer=cull)
         ref_loss, ref_grad = single_gpu_with_table(plan, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull)
         for r, l in enumerate(losses):
             assert torch.equal(l, ref_loss), f"loss on rank {r}: {float(l)!r} vs {float(ref_loss)!r}"

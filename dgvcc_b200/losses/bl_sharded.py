@@ -324,8 +324,8 @@ class _ShardedFn(torch.autograd.Function):
             _native.ptr(packed.pts), _native.ptr(packed.targets), _native.ptr(packed.meta), _native.ptr(st), _native.ptr(dens),
             plan.batch, hp, wp, plan.total_rows, plan.total_chunks, plan.multi_chunk, float(pp.stride), float(pp.sigma),
             float(pp.bg_ratio), int(pp.use_bg), int(mod.exact_cull), inv_batch, ctypes.byref(shard), _native.ptr(slices),
-_native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss), int(defer), _native.stream_ptr(dev),
-            mod._event_handles("fwd", 11))
+            _native.ptr(aux), _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss),
+            int(defer), _native.stream_ptr(dev), mod._event_handles("fwd", 11))
         _native.check(rc, "dgvcc_bl_shard_forward")
         ctx.saved = (mod, plan, packed, (slices, aux), inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own,
                      loss if defer else None)

@@ -185,6 +185,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -212,7 +213,8 @@ __device__ __forceinline__ void xchg_wait(const Xchg& x) {
         const int ph = which ? x.wait_phase2 : x.wait_phase;
         if ((m >> src) & 1u) xchg_spin(x.flags + ph * x.world + src, x.epoch, 1 + ph + 16 * src, x.err);
     }
-    __threadfence_system();
+    // the polling threads' ld.acquire.sys + the CTA barrier order every thread's later loads after the peers' stores
+    // (causality is transitive over the barrier); a system-scope fence here cost ~5 us per consumer kernel
     __syncthreads();
 }
 
@@ -235,14 +237,14 @@ __device__ __forceinline__ void xchg_store(const Xchg& x, unsigned int mask, lon
 // at home just takes its ticket).
 __device__ __forceinline__ void xchg_signal(const Xchg& x, bool stored = true) {
     if (!x.peers) return;
-    // device-scope fence per storing thread, ONE system-scope fence by the thread that raises the flags: the ticket
-    // (device scope) orders every CTA's stores before the last CTA's fence.sys, which is cumulative
-    if (stored) __threadfence();
+    // device-scope acq_rel fence per storing thread; the thread that raises the flags acquires them through the ticket
+    // and publishes everything with its st.release.sys (release is cumulative) -- no fence.sc.sys on the path
+    if (stored) fence_acq_rel_gpu();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
         if (atomicAdd(x.ticket, 1u) == total - 1u) {
-            __threadfence_system();
+            fence_acq_rel_gpu();  // acquires the other CTAs' stores; the st.release.sys below publishes them (cumulative)
             unsigned int m = x.signal_mask;
             while (m) {
                 const int q = __ffs(m) - 1;
@@ -534,7 +536,7 @@ bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ me
               float* __restrict__ minpart, int stage, int chunk_lo, Xchg x) {
     const bool stored = bl_min_body<R, C>(pts_all, meta, batch, g, minpart, stage, chunk_lo, x);
     if (stage != 0) xchg_signal(x, stored);  // the flag goes up after the last launch; stage 0 only fences its stores
-    else if (stored) __threadfence();
+    else if (stored) fence_acq_rel_gpu();
 }
 
 // Sharded path: min over the chunks of an image once they have all arrived, so that bl_z_kernel reads one value per
@@ -1352,12 +1354,12 @@ bl_push_kernel(const dgvcc_bl_push* __restrict__ slices, int n_slices, const cha
                 reinterpret_cast<int*>(dst)[i] = __ldcg(reinterpret_cast<const int*>(src) + i);
         }
     }
-    __threadfence_system();
+    fence_acq_rel_gpu();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
-    __threadfence_system();
+    fence_acq_rel_gpu();
     if ((int)threadIdx.x < world && ((signal_mask >> threadIdx.x) & 1u)) {
         unsigned int* flag = reinterpret_cast<unsigned int*>(peers[threadIdx.x] + flags_off) + phase * world + rank;
         st_release_sys(flag, epoch);
@@ -1403,7 +1405,6 @@ bl_wait_kernel(const unsigned int* __restrict__ flags, int phase, int world, uns
             __nanosleep(64);
         }
     }
-    __threadfence_system();
 }
 
 // Sum of the per-image losses in image order (every rank received the values of the images it does not hold).

@@ -206,15 +206,16 @@ FORCE_CHUNK = None   # experiments: points per chunk of the sharded plan, whatev
 
 
 def shard_chunk_points(total_points, world):
-    """Points per chunk for a batch spread over ``world`` ranks.  One rank sweeps total / world points; cutting them into
-    ~64 chunks (x 24 CTAs of four pixel tiles each) gives every SM several rounds of short CTAs, so the ragged last
-    round of each sweep is a small fraction of it -- with 1024-point chunks a rank of an 8-GPU run would hold 7 chunks,
-    a third of one round.  Small chunks are affordable because the sharded path reduces the per-chunk partials in
-    separate kernels (bl_min_combine / bl_finish_z) and bounds the min sweep of later chunks by the first one.  Never
-    above the single-GPU chunk size, never below 128 (the sweeps stage 128 points at a time), a multiple of 32."""
+    """Points per chunk for a batch spread over ``world`` ranks: about 18 chunks per rank (and per 18 x 1024 points).
+    Measured on 8 B200 with BASELINE config 3 (profiles/r2_strong_scaling.md; step time against points per chunk):
+    128 -> 0.50 ms, 192 -> 0.46, 256 -> 0.48, 352 -> 0.447, 448 -> 0.45, 704 -> 0.50.  Small chunks pay the per-task
+    prologues / epilogues and per-chunk partial arrays, large ones leave a rank with too few CTAs to fill its SMs.
+    Never above the single-GPU chunk size, never below 128, a multiple of 32."""
     if FORCE_CHUNK:
         return int(FORCE_CHUNK)
-    want = max(1, total_points // (max(world, 1) * 64))
+    per_rank = max(1, -(-total_points // max(world, 1)))
+    waves = max(1, -(-per_rank // (18 * _bl.chunk_points())))
+    want = -(-per_rank // (18 * waves))
     return int(min(_bl.chunk_points(), max(128, -(-want // 32) * 32)))
 
 

@@ -673,7 +673,7 @@ __device__ __forceinline__ int cta_compact(bool hit, int* warp_cnt, int& total) 
 // whose box touches the coarse tile; WRITE = true repeats the scan and writes their indices, in index order,
 // behind the heads of the lower chunks (counts summed on the fly), so that every coarse tile ends up with one
 // contiguous ordered list; the last chunk also stores the list's length.
-template <bool WRITE>
+template <bool WRITE, bool PACKED = false>
 __global__ void __launch_bounds__(COARSE_THREADS)
 dmap_coarse_kernel(const int4* __restrict__ boxes, const int64_t* __restrict__ meta, int n_images,
                    int32_t* __restrict__ ccount, int32_t* __restrict__ ctotal, int32_t* __restrict__ clist) {
@@ -697,10 +697,13 @@ dmap_coarse_kernel(const int4* __restrict__ boxes, const int64_t* __restrict__ m
     int count = 0;
     for (int base = chunk * CHUNK; base < i_end; base += COARSE_THREADS) {
         const int i = base + threadIdx.x;
-        const bool hit = i < i_end && box_hits(__ldg(b + i), x0, y0, COARSE, COARSE);
+        const int4 bi = i < i_end ? __ldg(b + i) : make_int4(1, 0, 1, 0);
+        const bool hit = i < i_end && box_hits(bi, x0, y0, COARSE, COARSE);
         int total;
         const int slot = cta_compact<COARSE_THREADS>(hit, warp_cnt, total);
-        if (WRITE && hit) out[pos + count + slot] = i;
+        // PACKED (fixed sigma, identical stamps): the list carries the stamp's centre pixel (row << 16 | column) instead
+        // of the head index -- the fine pass needs nothing else and saves the dependent loads through the index
+        if (WRITE && hit) out[pos + count + slot] = PACKED ? (int)(((unsigned)((bi.z + bi.w) >> 1) << 16) | (unsigned)((bi.x + bi.y) >> 1)) : i;
         count += total;
     }
     if (threadIdx.x == 0) {
@@ -912,6 +915,101 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
     }
 }
 
+// ------------------------------------------------------------------------------- fixed sigma, 15 x 15 stamps
+// gaussian_filter_density_fixed (dmap_gen.py:53-81; what run() calls): sigma 4, truncate 7/4 -> radius 7, every head
+// adds the SAME 15 x 15 table fl32(f64(fl32(w[|dy|])) * w[|dx|]), only shifted.  One WARP owns one 32 x 32 output tile:
+//   * accumulators in shared memory with an apron of 2R pixels on every side (60 x 60), so that a stamp that merely
+//     touches the tile is applied whole, without clipping tests; only the inner 32 x 32 is stored;
+//   * the 225 stamp pixels are spread over the lanes (7 full steps + one pixel): lane l step k handles stamp pixel
+//     p = 32 k + l, whose table value and offset inside the apron tile sit in registers for the life of the warp --
+//     per stamp and step: one add for the address, LDS, FADD, STS (the row pitch 79 = 15 mod 32 makes the 32 lanes
+//     of a step hit 32 different banks);
+//   * stamps are applied in list order, one after the other, by the same warp: every pixel sees its heads in index
+//     order, which is what makes the fp32 sums bit-identical to the reference's sequential accumulation;
+//   * the list of the coarse tile carries packed centre pixels (dmap_coarse_kernel<true, true>): one coalesced load
+//     per 32 entries, the next one already in flight.
+// Against dmap_splat_kernel (lane = tile column, 8 rows per thread, 105 instructions per 8-row band and stamp with
+// half the lanes idle on a 15-wide stamp) this is ~45 instructions per (tile, stamp) with every lane busy.
+constexpr int FAST_R = 7;
+constexpr int FAST_S = 2 * FAST_R + 1;             // 15
+constexpr int FAST_APRON = 32 + 4 * FAST_R;        // 60
+constexpr int FAST_PITCH = 79;                     // >= FAST_APRON, = FAST_S (mod 32)
+constexpr int FAST_TILE_FLOATS = FAST_APRON * FAST_PITCH;   // 4740 floats = 18960 bytes per warp
+constexpr int FAST_STEPS = (FAST_S * FAST_S + 31) / 32;     // 8; the last one holds a single pixel
+constexpr int FAST_SMEM = SPLAT_WARPS * FAST_TILE_FLOATS * 4;
+static_assert(FAST_TILE_FLOATS % 4 == 0 && FAST_S * FAST_S == 32 * (FAST_STEPS - 1) + 1, "layout of the 15 x 15 stamp over the lanes");
+
+__global__ void __launch_bounds__(256)
+dmap_fixed_table_kernel(const double* __restrict__ tmpl_tab, float* __restrict__ tab2d) {
+    const int p = threadIdx.x;
+    if (p >= FAST_S * FAST_S) return;
+    const int dy = abs(p / FAST_S - FAST_R), dx = abs(p % FAST_S - FAST_R);
+    // the first pass of the separable filter stores float32, the second multiplies in double and stores float32
+    tab2d[p] = (float)__dmul_rn((double)(float)tmpl_tab[dy], tmpl_tab[dx]);
+}
+
+__global__ void __launch_bounds__(SPLAT_THREADS)
+dmap_splat_fixed_kernel(const TileDesc* __restrict__ desc, int fine_tiles, const unsigned* __restrict__ clist,
+                        const float* __restrict__ tab2d, float* __restrict__ density) {
+    extern __shared__ float4 fast_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * SPLAT_WARPS + warp;
+    if (t >= fine_tiles) return;  // warps never synchronise with each other
+    float* tile = reinterpret_cast<float*>(fast_smem) + warp * FAST_TILE_FLOATS;
+    const int4* dp = reinterpret_cast<const int4*>(desc + t);
+    const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+    const longlong2 d2 = __ldg(reinterpret_cast<const longlong2*>(dp + 2));
+    const int x0 = d0.x, y0 = d0.y, width = d0.z, height = d0.w, cnt = d1.x;
+    const int x = x0 + lane;
+    float* out = density + d2.x + (size_t)y0 * width + x;
+    const int rows = min(FINE_H, height - y0);
+    if (cnt == 0) {  // no stamp touches the tile
+        if (x < width)
+            for (int r = 0; r < rows; ++r) out[(size_t)r * width] = 0.f;
+        return;
+    }
+    float tv[FAST_STEPS];
+    int off[FAST_STEPS];
+#pragma unroll
+    for (int k = 0; k < FAST_STEPS; ++k) {
+        const int p = min(32 * k + lane, FAST_S * FAST_S - 1);
+        tv[k] = __ldg(tab2d + p);
+        off[k] = (p / FAST_S) * FAST_PITCH + p % FAST_S;
+    }
+    float4* tile4 = reinterpret_cast<float4*>(tile);
+    for (int i = lane; i < FAST_TILE_FLOATS / 4; i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    const unsigned* cl = clist + d2.y;
+    unsigned nxt = lane < cnt ? __ldg(cl + lane) : 0xffffffffu;
+    for (int base = 0; base < cnt; base += 32) {
+        const unsigned e = nxt;
+        nxt = base + 32 + lane < cnt ? __ldg(cl + base + 32 + lane) : 0xffffffffu;
+        const int ix = (int)(e & 0xffffu), iy = (int)(e >> 16);
+        const bool hit = base + lane < cnt && ix + FAST_R >= x0 && ix - FAST_R < x0 + FINE_W && iy + FAST_R >= y0 &&
+                         iy - FAST_R < y0 + FINE_H;
+        unsigned todo = __ballot_sync(FULL_MASK, hit);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned s = __shfl_sync(FULL_MASK, e, src);
+            // top-left pixel of the stamp inside the apron tile (whose origin is the tile's minus 2R)
+            float* a = tile + ((int)(s >> 16) - y0 + FAST_R) * FAST_PITCH + ((int)(s & 0xffffu) - x0 + FAST_R);
+            float v[FAST_STEPS];
+#pragma unroll
+            for (int k = 0; k < FAST_STEPS - 1; ++k) v[k] = a[off[k]];   // 32 different pixels per step, all lanes
+            if (lane == 0) v[FAST_STEPS - 1] = a[off[FAST_STEPS - 1]];   // pixel 224
+#pragma unroll
+            for (int k = 0; k < FAST_STEPS - 1; ++k) a[off[k]] = __fadd_rn(v[k], tv[k]);
+            if (lane == 0) a[off[FAST_STEPS - 1]] = __fadd_rn(v[FAST_STEPS - 1], tv[FAST_STEPS - 1]);
+            __syncwarp();  // the next stamp may touch the same pixels from other lanes
+        }
+    }
+    if (x < width) {
+        const float* in = tile + 2 * FAST_R * FAST_PITCH + 2 * FAST_R + lane;
+        for (int r = 0; r < rows; ++r) out[(size_t)r * width] = in[r * FAST_PITCH];
+    }
+}
+
 }  // namespace dmap
 }  // namespace dgvcc
 
@@ -954,6 +1052,7 @@ extern "C" int dgvcc_dmap_knn_sigma(const double* pts_xy, int n, int32_t* nn_idx
 // ---- batch plan (host only) ---------------------------------------------------------------------
 extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const int32_t* widths, const int32_t* counts,
                                      int64_t* meta, dgvcc_dmap_plan* plan) {
+    int64_t max_side = 0;
     if (n_images <= 0 || !heights || !widths || !counts || !meta || !plan) return DGVCC_ERR_ARG;
     int64_t acc[META_COLS] = {0};
     // kNN: as many candidate slices per image as it takes to fill the chip with tasks, no more
@@ -971,6 +1070,8 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
         const int64_t n = counts[i], h = heights[i], w = widths[i];
         if (n < 0 || h <= 0 || w <= 0) return DGVCC_ERR_ARG;
         m[M_N] = n; m[M_H] = h; m[M_W] = w;
+        max_side = h > max_side ? h : max_side;
+        max_side = w > max_side ? w : max_side;
         const int64_t ctiles = (int64_t)ceil_div((int)w, COARSE) * ceil_div((int)h, COARSE);
         const int64_t nchunks = ceil_div((int)n, CHUNK), slices = n > 0 ? knn_slicing((int)n, max_slices).slices() : 0;
         acc[M_PT_OFF] += n;
@@ -986,6 +1087,7 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
     if (acc[M_FTILE_OFF] > 0x7fffffffLL || acc[M_CTASK_OFF] > 0x7fffffffLL || acc[M_KTASK_OFF] > 0x7fffffffLL ||
         acc[M_PT_OFF] > 0x7fffffffLL)
         return DGVCC_ERR_UNSUPPORTED;
+    plan->max_side = max_side;
     plan->total_heads = acc[M_PT_OFF];
     plan->total_pixels = acc[M_OUT_OFF];
     plan->fine_tiles = acc[M_FTILE_OFF];
@@ -998,7 +1100,7 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
     plan->off_boxes = (int64_t)off;  off = align_up(off + (size_t)heads * sizeof(int4), 256);
     plan->off_wtab = (int64_t)off;   off = align_up(off + (size_t)heads * TAB * sizeof(double), 256);
     plan->off_fmask = (int64_t)off;  off = align_up(off + (size_t)(acc[M_FTILE_OFF] / 32 + 1) * 4, 256);
-    plan->off_tmpl = (int64_t)off;   off = align_up(off + sizeof(Stamp) + TAB * sizeof(double), 256);
+    plan->off_tmpl = (int64_t)off;   off = align_up(off + sizeof(Stamp) + TAB * sizeof(double) + 256 * sizeof(float), 256);
     plan->off_desc = (int64_t)off;   off = align_up(off + (size_t)acc[M_FTILE_OFF] * sizeof(TileDesc), 256);
     plan->off_ccount = (int64_t)off; off = align_up(off + (size_t)(acc[M_CTASK_OFF] + 1) * 4, 256);
     plan->off_ctotal = (int64_t)off; off = align_up(off + (size_t)(acc[M_CTILE_OFF] + 1) * 4, 256);
@@ -1064,6 +1166,10 @@ extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma,
     int32_t* ctotal = (int32_t*)(ws + plan->off_ctotal);
     int32_t* clist = (int32_t*)(ws + plan->off_clist);
     const int heads = (int)plan->total_heads;
+    // the reference's fixed generator (sigma 4, truncate 7/4: 15 x 15 stamps) takes the warp-per-tile kernel; its lists
+    // pack the centre pixel into 16 + 16 bits
+    const bool fast = !sigma && (int)(truncate * fixed_sigma + 0.5) == FAST_R && plan->max_side > 0 && plan->max_side < 65536;
+    float* tab2d = (float*)(ws + plan->off_tmpl + sizeof(Stamp) + TAB * sizeof(double));
     if (heads > 0) {
         DGVCC_RETURN_IF_CUDA(cudaMemsetAsync(fmask, 0, (size_t)(plan->fine_tiles / 32 + 1) * 4, st));
         if (sigma) {
@@ -1078,14 +1184,27 @@ extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma,
         dmap_coarse_kernel<false><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
                                                                                           ctotal, clist);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-        dmap_coarse_kernel<true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
-                                                                                         ctotal, clist);
+        if (fast)
+            dmap_coarse_kernel<true, true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
+                                                                                                   ctotal, clist);
+        else
+            dmap_coarse_kernel<true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
+                                                                                             ctotal, clist);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     TileDesc* desc = (TileDesc*)(ws + plan->off_desc);
     dmap_tile_setup_kernel<<<ceil_div((int)plan->fine_tiles, 256), 256, 0, st>>>(meta, n_images, (int)plan->fine_tiles, fmask,
                                                                                  ctotal, heads > 0, desc);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    if (fast) {
+        static PerDeviceOnce once;
+        if (once.first())
+            DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(dmap_splat_fixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
+        if (heads > 0) dmap_fixed_table_kernel<<<1, 256, 0, st>>>(tmpl_tab, tab2d);
+        dmap_splat_fixed_kernel<<<ceil_div((int)plan->fine_tiles, SPLAT_WARPS), SPLAT_THREADS, FAST_SMEM, st>>>(
+            desc, (int)plan->fine_tiles, (const unsigned*)clist, tab2d, density);
+        return (int)cudaGetLastError();
+    }
     // fixed sigma with a narrow stamp: every head shares the template table (wide stamps never use tables)
     dmap_splat_kernel<<<(unsigned)plan->fine_tiles, SPLAT_THREADS, 0, st>>>(stamps, wtab, boxes, desc, clist,
                                                                             sigma ? nullptr : tmpl_tab, density);

@@ -1001,7 +1001,8 @@ dmap_fine_bin_kernel(const int64_t* __restrict__ meta, int n_images, const int32
 #pragma unroll
         for (int c = 0; c < COARSE / FINE_W; ++c) {
             const int tx0 = cx0 + FINE_W * c;
-            const bool hit = row && ix + FAST_R >= tx0 && ix - FAST_R < tx0 + FINE_W;
+            // c < n_cols: a stamp at the right border reaches past the image's last tile column
+            const bool hit = row && c < n_cols && ix + FAST_R >= tx0 && ix - FAST_R < tx0 + FINE_W;
             const unsigned mk = __ballot_sync(FULL_MASK, hit);
             if (mk) {
                 if (WRITE && hit) flist[dst[c] + cur[c] + __popc(mk & ((1u << lane) - 1u))] = e;

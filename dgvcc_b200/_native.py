@@ -46,8 +46,7 @@ class DmapPlan(ctypes.Structure):
     _fields_ = [(n, c_int64) for n in
                 ("total_heads", "total_pixels", "fine_tiles", "coarse_tasks", "knn_tasks", "knn_query_blocks", "knn_max_slices",
                  "off_stamps", "off_boxes", "off_wtab", "off_fmask", "off_tmpl", "off_desc", "off_ccount", "off_ctotal", "off_clist", "splat_workspace_bytes",
-                 "off_knn_d2", "off_knn_idx", "off_knn_pts32", "off_knn_max", "knn_workspace_bytes", "max_side",
-                 "coarse_tiles", "off_fcount", "off_foff", "off_flist")]
+                 "off_knn_d2", "off_knn_idx", "off_knn_pts32", "off_knn_max", "knn_workspace_bytes", "max_side")]
 
 
 DMAP_META_COLS = 12  # DGVCC_DMAP_META_COLS

@@ -733,8 +733,7 @@ static_assert(sizeof(TileDesc) == 64, "TileDesc is read as four 16-byte words");
 // One thread per fine tile of the batch: image lookup, tile position, occupancy bit, coarse-list length.
 __global__ void __launch_bounds__(256)
 dmap_tile_setup_kernel(const int64_t* __restrict__ meta, int n_images, int fine_tiles, const unsigned* __restrict__ fmask,
-                       const int32_t* __restrict__ ctotal, int have_heads, TileDesc* __restrict__ desc,
-                       const int32_t* __restrict__ fcount, const int32_t* __restrict__ foff) {
+                       const int32_t* __restrict__ ctotal, int have_heads, TileDesc* __restrict__ desc) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= fine_tiles) return;
     const int img = find_image(meta, n_images + 1, M_FTILE_OFF, t);
@@ -746,9 +745,7 @@ dmap_tile_setup_kernel(const int64_t* __restrict__ meta, int n_images, int fine_
     d.x0 = (local % ftx) * FINE_W; d.y0 = (local / ftx) * FINE_H;
     d.pt_off = m[M_PT_OFF]; d.out_off = m[M_OUT_OFF];
     d.cnt = 0; d.clist_off = 0; d.pad0_ = d.pad1_ = 0; d.pad2_ = 0;
-    if (fcount) {  // fixed-sigma fast path: the tile's own list (dmap_fine_bin_kernel)
-        if (have_heads) { d.cnt = fcount[t]; d.clist_off = foff[t]; }
-    } else if (have_heads && d.n > 0 && ((fmask[t >> 5] >> (t & 31)) & 1u)) {
+    if (have_heads && d.n > 0 && ((fmask[t >> 5] >> (t & 31)) & 1u)) {
         const int ct = (d.y0 / COARSE) * ceil_div(d.width, COARSE) + d.x0 / COARSE;
         d.cnt = ctotal[m[M_CTILE_OFF] + ct];
         d.clist_off = m[M_CLIST_OFF] + (long long)ct * d.n;
@@ -929,8 +926,8 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
 //     of a step hit 32 different banks);
 //   * stamps are applied in list order, one after the other, by the same warp: every pixel sees its heads in index
 //     order, which is what makes the fp32 sums bit-identical to the reference's sequential accumulation;
-//   * the tile has its own ordered list of packed centre pixels (dmap_coarse_kernel<true, true> -> dmap_fine_bin_kernel):
-//     one coalesced load per 32 stamps, the next one already in flight, no scanning of heads that miss the tile.
+//   * the list of the coarse tile carries packed centre pixels (dmap_coarse_kernel<true, true>): one coalesced load
+//     per 32 entries, the next one already in flight.
 // Against dmap_splat_kernel (lane = tile column, 8 rows per thread, 105 instructions per 8-row band and stamp with
 // half the lanes idle on a 15-wide stamp) this is ~45 instructions per (tile, stamp) with every lane busy.
 constexpr int FAST_R = 7;
@@ -951,103 +948,20 @@ dmap_fixed_table_kernel(const double* __restrict__ tmpl_tab, float* __restrict__
     tab2d[p] = (float)__dmul_rn((double)(float)tmpl_tab[dy], tmpl_tab[dx]);
 }
 
-// Fast-path prepare: only the box of every head (the culling passes read nothing else).
+// Fast-path prepare: the box of every head (the only thing the culling passes read) and the tile occupancy bits.
 __global__ void __launch_bounds__(256)
 dmap_prepare_fast_kernel(const double2* __restrict__ pts, const int64_t* __restrict__ meta, int n_images, int total_heads,
-                         int4* __restrict__ boxes) {
+                         int4* __restrict__ boxes, unsigned* __restrict__ fmask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_heads) return;
     const int img = find_image(meta, n_images + 1, M_PT_OFF, i);
     const int64_t* m = meta + (size_t)img * META_COLS;
+    const int height = (int)__ldg(m + M_H), width = (int)__ldg(m + M_W);
     int ix, iy;
-    const bool keep = stamp_pixel(pts[i], (int)__ldg(m + M_H), (int)__ldg(m + M_W), ix, iy);
-    boxes[i] = stamp_box(ix, iy, keep ? FAST_R : -1);
-}
-
-// Fine binning: one CTA per coarse tile, warp w = the w-th row of its 8 x 8 fine tiles.  Every warp walks the coarse
-// tile's ordered list of packed centres and appends each stamp to the lists of the fine tiles of its row that the stamp
-// touches -- ballot + popc keep the list order, every fine tile belongs to exactly one warp, so there are no atomics
-// and the result is deterministic.  WRITE = false only counts (the lengths feed an exclusive scan).
-template <bool WRITE>
-__global__ void __launch_bounds__(256)
-dmap_fine_bin_kernel(const int64_t* __restrict__ meta, int n_images, const int32_t* __restrict__ ctotal,
-                     const unsigned* __restrict__ clist, const int32_t* __restrict__ foff, int32_t* __restrict__ fcount,
-                     unsigned* __restrict__ flist) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int img = find_image(meta, n_images + 1, M_CTILE_OFF, blockIdx.x);
-    const int64_t* m = meta + (size_t)img * META_COLS;
-    const int n = (int)m[M_N], width = (int)m[M_W], height = (int)m[M_H];
-    const int ct = blockIdx.x - (int)m[M_CTILE_OFF], ctx = ceil_div(width, COARSE);
-    const int cx0 = (ct % ctx) * COARSE, ty0 = (ct / ctx) * COARSE + FINE_H * warp;
-    if (ty0 >= height) return;
-    const int ftx = ceil_div(width, FINE_W);
-    const int tile0 = (int)m[M_FTILE_OFF] + (ty0 / FINE_H) * ftx + cx0 / FINE_W;   // the row's first fine tile
-    const int n_cols = min(COARSE / FINE_W, ftx - cx0 / FINE_W);
-    const int len = n > 0 ? ctotal[blockIdx.x] : 0;
-    const unsigned* list = clist + m[M_CLIST_OFF] + (size_t)ct * n;
-    int cur[COARSE / FINE_W], dst[COARSE / FINE_W];
-#pragma unroll
-    for (int c = 0; c < COARSE / FINE_W; ++c) {
-        cur[c] = 0;
-        dst[c] = (WRITE && c < n_cols) ? foff[tile0 + c] : 0;
-    }
-    unsigned nxt = lane < len ? __ldg(list + lane) : 0u;
-    for (int base = 0; base < len; base += 32) {
-        const unsigned e = nxt;
-        nxt = base + 32 + lane < len ? __ldg(list + base + 32 + lane) : 0u;
-        const int ix = (int)(e & 0xffffu), iy = (int)(e >> 16);
-        const bool row = base + lane < len && iy + FAST_R >= ty0 && iy - FAST_R < ty0 + FINE_H;
-        if (!__any_sync(FULL_MASK, row)) continue;
-#pragma unroll
-        for (int c = 0; c < COARSE / FINE_W; ++c) {
-            const int tx0 = cx0 + FINE_W * c;
-            // c < n_cols: a stamp at the right border reaches past the image's last tile column
-            const bool hit = row && c < n_cols && ix + FAST_R >= tx0 && ix - FAST_R < tx0 + FINE_W;
-            const unsigned mk = __ballot_sync(FULL_MASK, hit);
-            if (mk) {
-                if (WRITE && hit) flist[dst[c] + cur[c] + __popc(mk & ((1u << lane) - 1u))] = e;
-                cur[c] += __popc(mk);
-            }
-        }
-    }
-    if (!WRITE) {
-#pragma unroll
-        for (int c = 0; c < COARSE / FINE_W; ++c)
-            if (lane == c && c < n_cols) fcount[tile0 + c] = cur[c];
-    }
-}
-
-// Exclusive scan of the list lengths (one CTA; ~1e5 tiles).
-__global__ void __launch_bounds__(1024)
-dmap_scan_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int n) {
-    __shared__ int warp_sum_s[32];
-    const int per = ceil_div(n, 1024), b0 = threadIdx.x * per, b1 = min(n, b0 + per);
-    int local = 0;
-    for (int i = b0; i < b1; ++i) local += in[i];
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL_MASK, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += v;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sum_s[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        int w = warp_sum_s[threadIdx.x], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL_MASK, wi, o);
-            if ((int)threadIdx.x >= o) wi += v;
-        }
-        warp_sum_s[threadIdx.x] = wi - w;
-    }
-    __syncthreads();
-    int run = warp_sum_s[threadIdx.x >> 5] + incl - local;
-    for (int i = b0; i < b1; ++i) {
-        out[i] = run;
-        run += in[i];
-    }
-    if (threadIdx.x == 1023) out[n] = run;   // b1 == n for the last thread: the grand total
+    const bool keep = stamp_pixel(pts[i], height, width, ix, iy);
+    const int4 box = stamp_box(ix, iy, keep ? FAST_R : -1);
+    boxes[i] = box;
+    mark_tiles(box, height, width, __ldg(m + M_FTILE_OFF), fmask, 0, 1);
 }
 
 __global__ void __launch_bounds__(SPLAT_THREADS)
@@ -1081,13 +995,31 @@ dmap_splat_fixed_kernel(const TileDesc* __restrict__ desc, int fine_tiles, const
     float4* tile4 = reinterpret_cast<float4*>(tile);
     for (int i = lane; i < FAST_TILE_FLOATS / 4; i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
-    const unsigned* cl = clist + d2.y;   // the tile's own list: every entry touches the tile (dmap_fine_bin_kernel)
-    unsigned nxt = lane < cnt ? __ldg(cl + lane) : 0u;
-    for (int base = 0; base < cnt; base += 32) {
-        const unsigned e = nxt;
-        nxt = base + 32 + lane < cnt ? __ldg(cl + base + 32 + lane) : 0u;
-        const int here = min(32, cnt - base);
-        for (int src = 0; src < here; ++src) {
+    const unsigned* cl = clist + d2.y;
+    // the scan of the coarse tile's list is a chain of L2 round trips: four batches of 32 entries are in flight at a time
+    constexpr int AHEAD = 4;
+    unsigned nxt[AHEAD];
+#pragma unroll
+    for (int q = 0; q < AHEAD; ++q) nxt[q] = 32 * q + lane < cnt ? __ldg(cl + 32 * q + lane) : 0xffffffffu;
+    for (int base0 = 0; base0 < cnt; base0 += 32 * AHEAD) {
+        unsigned cur[AHEAD];
+#pragma unroll
+        for (int q = 0; q < AHEAD; ++q) {
+            cur[q] = nxt[q];
+            const int j = base0 + 32 * (AHEAD + q) + lane;
+            nxt[q] = j < cnt ? __ldg(cl + j) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int q = 0; q < AHEAD; ++q) {
+        const int base = base0 + 32 * q;
+        const unsigned e = cur[q];
+        const int ix = (int)(e & 0xffffu), iy = (int)(e >> 16);
+        const bool hit = base + lane < cnt && ix + FAST_R >= x0 && ix - FAST_R < x0 + FINE_W && iy + FAST_R >= y0 &&
+                         iy - FAST_R < y0 + FINE_H;
+        unsigned todo = __ballot_sync(FULL_MASK, hit);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
             const unsigned s = __shfl_sync(FULL_MASK, e, src);
             // top-left pixel of the stamp inside the apron tile (whose origin is the tile's minus 2R)
             float* a = tile + ((int)(s >> 16) - y0 + FAST_R) * FAST_PITCH + ((int)(s & 0xffffu) - x0 + FAST_R);
@@ -1099,6 +1031,7 @@ dmap_splat_fixed_kernel(const TileDesc* __restrict__ desc, int fine_tiles, const
             for (int k = 0; k < FAST_STEPS - 1; ++k) a[off[k]] = __fadd_rn(v[k], tv[k]);
             if (lane == 0) a[off[FAST_STEPS - 1]] = __fadd_rn(v[FAST_STEPS - 1], tv[FAST_STEPS - 1]);
             __syncwarp();  // the next stamp may touch the same pixels from other lanes
+        }
         }
     }
     if (x < width) {
@@ -1202,12 +1135,6 @@ extern "C" int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const
     plan->off_ccount = (int64_t)off; off = align_up(off + (size_t)(acc[M_CTASK_OFF] + 1) * 4, 256);
     plan->off_ctotal = (int64_t)off; off = align_up(off + (size_t)(acc[M_CTILE_OFF] + 1) * 4, 256);
     plan->off_clist = (int64_t)off;  off = align_up(off + (size_t)(acc[M_CLIST_OFF] + 1) * 4, 256);
-    // fixed-sigma fast path: per fine tile the ordered list of the stamps that touch it (a 15 x 15 stamp touches at most
-    // 2 x 2 tiles), its length and its offset
-    plan->coarse_tiles = acc[M_CTILE_OFF];
-    plan->off_fcount = (int64_t)off; off = align_up(off + (size_t)(acc[M_FTILE_OFF] + 1) * 4, 256);
-    plan->off_foff = (int64_t)off;   off = align_up(off + (size_t)(acc[M_FTILE_OFF] + 1) * 4, 256);
-    plan->off_flist = (int64_t)off;  off = align_up(off + (size_t)(4 * heads + 1) * 4, 256);
     plan->splat_workspace_bytes = (int64_t)off;
     off = 0;
     plan->off_knn_d2 = 0;            off = align_up((size_t)(acc[M_KPART_OFF] + 1) * 8, 256);
@@ -1269,36 +1196,10 @@ extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma,
     int32_t* ctotal = (int32_t*)(ws + plan->off_ctotal);
     int32_t* clist = (int32_t*)(ws + plan->off_clist);
     const int heads = (int)plan->total_heads;
-    TileDesc* desc = (TileDesc*)(ws + plan->off_desc);
     // the reference's fixed generator (sigma 4, truncate 7/4: 15 x 15 stamps) takes the warp-per-tile kernel; its lists
     // pack the centre pixel into 16 + 16 bits
     const bool fast = !sigma && (int)(truncate * fixed_sigma + 0.5) == FAST_R && plan->max_side > 0 && plan->max_side < 65536;
-    if (fast) {
-        float* tab2d = (float*)(ws + plan->off_tmpl + sizeof(Stamp) + TAB * sizeof(double));
-        int32_t* fcount = (int32_t*)(ws + plan->off_fcount);
-        int32_t* foff = (int32_t*)(ws + plan->off_foff);
-        unsigned* flist = (unsigned*)(ws + plan->off_flist);
-        const int ftiles = (int)plan->fine_tiles, ctiles = (int)plan->coarse_tiles;
-        if (heads > 0) {
-            dmap_fixed_template_kernel<<<1, 32, 0, st>>>(fixed_sigma, truncate, tmpl, tmpl_tab);
-            dmap_fixed_table_kernel<<<1, 256, 0, st>>>(tmpl_tab, tab2d);
-            dmap_prepare_fast_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, meta, n_images, heads, boxes);
-            DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-            dmap_coarse_kernel<false><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount, ctotal, clist);
-            dmap_coarse_kernel<true, true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount, ctotal, clist);
-            DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-            dmap_fine_bin_kernel<false><<<ctiles, 256, 0, st>>>(meta, n_images, ctotal, (const unsigned*)clist, foff, fcount, flist);
-            dmap_scan_kernel<<<1, 1024, 0, st>>>(fcount, foff, ftiles);
-            dmap_fine_bin_kernel<true><<<ctiles, 256, 0, st>>>(meta, n_images, ctotal, (const unsigned*)clist, foff, fcount, flist);
-            DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-        }
-        dmap_tile_setup_kernel<<<ceil_div(ftiles, 256), 256, 0, st>>>(meta, n_images, ftiles, fmask, ctotal, heads > 0, desc, fcount, foff);
-        static PerDeviceOnce once;
-        if (once.first())
-            DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(dmap_splat_fixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
-        dmap_splat_fixed_kernel<<<ceil_div(ftiles, SPLAT_WARPS), SPLAT_THREADS, FAST_SMEM, st>>>(desc, ftiles, flist, tab2d, density);
-        return (int)cudaGetLastError();
-    }
+    float* tab2d = (float*)(ws + plan->off_tmpl + sizeof(Stamp) + TAB * sizeof(double));
     if (heads > 0) {
         DGVCC_RETURN_IF_CUDA(cudaMemsetAsync(fmask, 0, (size_t)(plan->fine_tiles / 32 + 1) * 4, st));
         if (sigma) {
@@ -1306,20 +1207,37 @@ extern "C" int dgvcc_dmap_splat_batch(const double* pts_xy, const double* sigma,
                 (const double2*)pts_xy, sigma, truncate, meta, n_images, heads, stamps, boxes, wtab, fmask);
         } else {
             dmap_fixed_template_kernel<<<1, 32, 0, st>>>(fixed_sigma, truncate, tmpl, tmpl_tab);
-            dmap_prepare_fixed_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, tmpl, meta, n_images,
-                                                                            heads, stamps, boxes, fmask);
+            if (fast)
+                dmap_prepare_fast_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, meta, n_images, heads, boxes, fmask);
+            else
+                dmap_prepare_fixed_kernel<<<ceil_div(heads, 256), 256, 0, st>>>((const double2*)pts_xy, tmpl, meta, n_images,
+                                                                                heads, stamps, boxes, fmask);
         }
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
         dmap_coarse_kernel<false><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
                                                                                           ctotal, clist);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-        dmap_coarse_kernel<true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
-                                                                                         ctotal, clist);
+        if (fast)
+            dmap_coarse_kernel<true, true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
+                                                                                                   ctotal, clist);
+        else
+            dmap_coarse_kernel<true><<<(unsigned)plan->coarse_tasks, COARSE_THREADS, 0, st>>>(boxes, meta, n_images, ccount,
+                                                                                             ctotal, clist);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
+    TileDesc* desc = (TileDesc*)(ws + plan->off_desc);
     dmap_tile_setup_kernel<<<ceil_div((int)plan->fine_tiles, 256), 256, 0, st>>>(meta, n_images, (int)plan->fine_tiles, fmask,
-                                                                                 ctotal, heads > 0, desc, nullptr, nullptr);
+                                                                                 ctotal, heads > 0, desc);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    if (fast) {
+        static PerDeviceOnce once;
+        if (once.first())
+            DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(dmap_splat_fixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
+        if (heads > 0) dmap_fixed_table_kernel<<<1, 256, 0, st>>>(tmpl_tab, tab2d);
+        dmap_splat_fixed_kernel<<<ceil_div((int)plan->fine_tiles, SPLAT_WARPS), SPLAT_THREADS, FAST_SMEM, st>>>(
+            desc, (int)plan->fine_tiles, (const unsigned*)clist, tab2d, density);
+        return (int)cudaGetLastError();
+    }
     // fixed sigma with a narrow stamp: every head shares the template table (wide stamps never use tables)
     dmap_splat_kernel<<<(unsigned)plan->fine_tiles, SPLAT_THREADS, 0, st>>>(stamps, wtab, boxes, desc, clist,
                                                                             sigma ? nullptr : tmpl_tab, density);

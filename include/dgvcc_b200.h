@@ -268,7 +268,6 @@ typedef struct dgvcc_dmap_plan {
     int64_t off_stamps, off_boxes, off_wtab, off_fmask, off_tmpl, off_desc, off_ccount, off_ctotal, off_clist, splat_workspace_bytes;
     int64_t off_knn_d2, off_knn_idx, off_knn_pts32, off_knn_max, knn_workspace_bytes;
     int64_t max_side;   /* largest image side of the batch (the fixed-sigma fast path packs pixel indices into 16 bits) */
-    int64_t coarse_tiles, off_fcount, off_foff, off_flist;   /* fixed-sigma fast path: per-fine-tile lists */
 } dgvcc_dmap_plan;
 
 int dgvcc_dmap_batch_plan(int n_images, const int32_t* heights, const int32_t* widths, const int32_t* counts,

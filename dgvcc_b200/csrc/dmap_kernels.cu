@@ -918,11 +918,13 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
 // ------------------------------------------------------------------------------- fixed sigma, 15 x 15 stamps
 // gaussian_filter_density_fixed (dmap_gen.py:53-81; what run() calls): sigma 4, truncate 7/4 -> radius 7, every head
 // adds the SAME 15 x 15 table fl32(f64(fl32(w[|dy|])) * w[|dx|]), only shifted.  One WARP owns one 32 x 32 output tile:
-//   * accumulators in shared memory with an apron of 2R pixels on every side (60 x 60), so that a stamp that merely
-//     touches the tile is applied whole, without clipping tests; only the inner 32 x 32 is stored;
+//   * accumulators in shared memory with an apron of R pixels on every side (46 x 46; 8.7 KB per warp, so that 24
+//     warps fit an SM -- a 2R apron needs no clipping tests at all but allows only 12, and the kernel is bound by
+//     memory latency, not by instruction issue); stamp pixels beyond the apron are predicated off; only the inner
+//     32 x 32 is stored;
 //   * the 225 stamp pixels are spread over the lanes (7 full steps + one pixel): lane l step k handles stamp pixel
 //     p = 32 k + l, whose table value and offset inside the apron tile sit in registers for the life of the warp --
-//     per stamp and step: one add for the address, LDS, FADD, STS (the row pitch 79 = 15 mod 32 makes the 32 lanes
+//     per stamp and step: the apron test, LDS, FADD, STS (the row pitch 47 = 15 mod 32 makes the 32 lanes
 //     of a step hit 32 different banks);
 //   * stamps are applied in list order, one after the other, by the same warp: every pixel sees its heads in index
 //     order, which is what makes the fp32 sums bit-identical to the reference's sequential accumulation;
@@ -932,12 +934,12 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
 // half the lanes idle on a 15-wide stamp) this is ~45 instructions per (tile, stamp) with every lane busy.
 constexpr int FAST_R = 7;
 constexpr int FAST_S = 2 * FAST_R + 1;             // 15
-constexpr int FAST_APRON = 32 + 4 * FAST_R;        // 60
-constexpr int FAST_PITCH = 79;                     // >= FAST_APRON, = FAST_S (mod 32)
-constexpr int FAST_TILE_FLOATS = FAST_APRON * FAST_PITCH;   // 4740 floats = 18960 bytes per warp
+constexpr int FAST_APRON = 32 + 2 * FAST_R;        // 46: apron of R pixels; stamp pixels beyond it are predicated off
+constexpr int FAST_PITCH = 47;                     // >= FAST_APRON, = FAST_S (mod 32)
+constexpr int FAST_TILE_FLOATS = (FAST_APRON * FAST_PITCH + 3) / 4 * 4;   // 2164 floats = 8656 bytes per warp
 constexpr int FAST_STEPS = (FAST_S * FAST_S + 31) / 32;     // 8; the last one holds a single pixel
 constexpr int FAST_SMEM = SPLAT_WARPS * FAST_TILE_FLOATS * 4;
-static_assert(FAST_TILE_FLOATS % 4 == 0 && FAST_S * FAST_S == 32 * (FAST_STEPS - 1) + 1, "layout of the 15 x 15 stamp over the lanes");
+static_assert(FAST_S * FAST_S == 32 * (FAST_STEPS - 1) + 1, "layout of the 15 x 15 stamp over the lanes");
 
 __global__ void __launch_bounds__(256)
 dmap_fixed_table_kernel(const double* __restrict__ tmpl_tab, float* __restrict__ tab2d) {
@@ -985,12 +987,13 @@ dmap_splat_fixed_kernel(const TileDesc* __restrict__ desc, int fine_tiles, const
         return;
     }
     float tv[FAST_STEPS];
-    int off[FAST_STEPS];
+    int off[FAST_STEPS], dxy[FAST_STEPS];   // dxy: (row << 8 | column) of the stamp pixel inside the stamp
 #pragma unroll
     for (int k = 0; k < FAST_STEPS; ++k) {
         const int p = min(32 * k + lane, FAST_S * FAST_S - 1);
         tv[k] = __ldg(tab2d + p);
         off[k] = (p / FAST_S) * FAST_PITCH + p % FAST_S;
+        dxy[k] = ((p / FAST_S) << 8) | (p % FAST_S);
     }
     float4* tile4 = reinterpret_cast<float4*>(tile);
     for (int i = lane; i < FAST_TILE_FLOATS / 4; i += 32) tile4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1021,22 +1024,27 @@ dmap_splat_fixed_kernel(const TileDesc* __restrict__ desc, int fine_tiles, const
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             const unsigned s = __shfl_sync(FULL_MASK, e, src);
-            // top-left pixel of the stamp inside the apron tile (whose origin is the tile's minus 2R)
-            float* a = tile + ((int)(s >> 16) - y0 + FAST_R) * FAST_PITCH + ((int)(s & 0xffffu) - x0 + FAST_R);
+            // top-left pixel of the stamp relative to the apron tile (whose origin is the tile's minus R): -R .. 31 + R
+            const int ay = (int)(s >> 16) - y0, ax = (int)(s & 0xffffu) - x0;
+            float* a = tile + ay * FAST_PITCH + ax;
             float v[FAST_STEPS];
+            bool in[FAST_STEPS];
 #pragma unroll
-            for (int k = 0; k < FAST_STEPS - 1; ++k) v[k] = a[off[k]];   // 32 different pixels per step, all lanes
-            if (lane == 0) v[FAST_STEPS - 1] = a[off[FAST_STEPS - 1]];   // pixel 224
+            for (int k = 0; k < FAST_STEPS; ++k) {   // 32 different pixels per step; those beyond the apron are nobody's
+                in[k] = (unsigned)(ay + (dxy[k] >> 8)) < (unsigned)FAST_APRON && (unsigned)(ax + (dxy[k] & 255)) < (unsigned)FAST_APRON &&
+                        (k < FAST_STEPS - 1 || lane == 0);   // the last step holds pixel 224 only
+                v[k] = in[k] ? a[off[k]] : 0.f;
+            }
 #pragma unroll
-            for (int k = 0; k < FAST_STEPS - 1; ++k) a[off[k]] = __fadd_rn(v[k], tv[k]);
-            if (lane == 0) a[off[FAST_STEPS - 1]] = __fadd_rn(v[FAST_STEPS - 1], tv[FAST_STEPS - 1]);
+            for (int k = 0; k < FAST_STEPS; ++k)
+                if (in[k]) a[off[k]] = __fadd_rn(v[k], tv[k]);
             __syncwarp();  // the next stamp may touch the same pixels from other lanes
         }
         }
     }
     if (x < width) {
-        const float* in = tile + 2 * FAST_R * FAST_PITCH + 2 * FAST_R + lane;
-        for (int r = 0; r < rows; ++r) out[(size_t)r * width] = in[r * FAST_PITCH];
+        const float* src = tile + FAST_R * FAST_PITCH + FAST_R + lane;
+        for (int r = 0; r < rows; ++r) out[(size_t)r * width] = src[r * FAST_PITCH];
     }
 }
 

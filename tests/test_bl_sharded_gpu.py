@@ -119,3 +119,39 @@ def test_config3_batch_on_four_emulated_ranks():
     # against the ordinary single-GPU module (another chunk table: other summation order of the chunk partials)
     assert_close(losses[0], l1.detach().cpu(), 2e-6, 0, "sharded vs BL loss")
     assert_close(grad, d.grad.cpu(), 1e-5, 1e-6 * float(d.grad.abs().max()), "sharded vs BL gradient")
+
+
+def _torchrun(script, nproc, *args, timeout=600):
+    import os
+    import socket
+    import subprocess
+    import sys
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", script)
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), path, *args],
+                          capture_output=True, text=True, timeout=timeout)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    return proc.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (one process per GPU, CUDA IPC peer memory)")
+def test_real_processes_over_peer_memory():
+    """scripts/shard_bl_multi_gpu.py under torchrun on every GPU of the box (at most 8): loss and gradients of the
+    golden 'mixed' case, BASELINE config 2 and config 3 bit-identical to one GPU running the same chunk table."""
+    import json
+    out = _torchrun("shard_bl_multi_gpu.py", min(8, torch.cuda.device_count()), "--steps", "3")
+    line = json.loads(out[out.index("{"):].splitlines()[0])
+    assert line["ok"] and all(line["checks"].values()), line["checks"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_isw_loss_sharded_over_processes():
+    """scripts/isw_multi_gpu.py: the ISW covariance loss with the batch split over the GPUs equals the whole batch on one
+    GPU (loss and gradients, rtol 1e-6) for the three config-5 layers."""
+    import json
+    out = _torchrun("isw_multi_gpu.py", min(8, torch.cuda.device_count()), "--steps", "2")
+    line = json.loads(out[out.index("{"):].splitlines()[0])
+    assert line["ok"], line

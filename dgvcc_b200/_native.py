@@ -19,7 +19,7 @@ class BLLayout(ctypes.Structure):
     """Mirror of struct dgvcc_bl_layout."""
     _fields_ = [(n, c_int64) for n in
                 ("amax", "rz", "pbg", "ebg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "zpart",
-                 "minpart", "gpart", "total", "dens", "gfinal", "flags", "err", "push_ticket")] + \
+                 "minpart", "gpart", "total", "dens", "gfinal", "flags", "err", "push_ticket", "goff", "gsorted")] + \
                [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("reserved_", c_int32)]
 
 

@@ -436,38 +436,6 @@ __device__ __forceinline__ float tile_max(const float (&v)[R][C]) {
     return m;
 }
 
-// min over the chunk's points of the squared distance (bl.py:39), into mind[r][c].
-// Exact pruning: a point whose distance lower bound over the tile exceeds the largest current minimum of
-// the tile cannot lower any pixel's minimum, so it is not staged (the first tile of a chunk is dense).
-template <int R, int C>
-__device__ __forceinline__ void sweep_min(WarpTile<R>& tile, const PixelTile<R, C>& px, const float2* pts,
-                                          int cnt_total, float (&mind)[R][C]) {
-    for (int n0 = 0; n0 < cnt_total; n0 += TILE_PTS) {
-        const int cnt = min(TILE_PTS, cnt_total - n0);
-        const float bound = tile_max<R, C>(mind);
-        const TileBox box = px.box;
-        __syncwarp();
-        // the four 32-point steps of a tile unrolled: their loads are in flight together (the pruned sweep is a chain of
-        // load -> test -> ballot latencies, not of arithmetic)
-        const int kept = stage_points_if<R, false, false, 4>(
-            tile, pts, nullptr, n0, cnt, px.cym2, px.cyy,
-            [&](float x, float y, float) { return box.lower_bound(x, y) <= bound; });
-        __syncwarp();
-#pragma unroll 2
-        for (int i = 0; i < kept; ++i) {
-            const float2 xs = tile.xs[i];
-            float yd[R];
-            load_yd<R>(tile, i, yd);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
-#pragma unroll
-                for (int r = 0; r < R; ++r) mind[r][c] = fminf(mind[r][c], __fadd_rn(yd[r], xd));
-            }
-        }
-    }
-}
-
 // Exact-zero culling of the exponential sweeps (opt-in): exp(a - amax) is computed as one MUFU.EX2 with
 // flush-to-zero, so it is exactly +0 whenever (a - amax) * log2(e) < -126.  With a <= -lb/s for every pixel
 // of the tile and amax >= the tile's smallest amax, a point is skipped when that bound is below -128 --
@@ -484,76 +452,183 @@ struct ExpCull {
 };
 
 // ------------------------------------------------------------------------------------------ K0
-// Only for images split into several point chunks: per-chunk partial minima.  One GPU (1024-point chunks): one launch,
-// every chunk sweeps its first 128 points densely and prunes after that.  Sharded path (chunks of 128..512 points, for
-// which "the first 128 densely" would be most of the sweep): two launches -- stage 0 sweeps the first chunk each image
-// has on this rank, stage 1 the other chunks starting from stage 0's minima, so that their pruning bites from the first
-// point on.  A partial that starts from another chunk's minima is the minimum over more points of the same image: the
-// minimum over the image's chunks is unchanged, and min is exact, so nothing depends on the order.  (Measured on one
-// GPU: two stages 97 us against 83 us for the single launch -- stage 0 alone leaves most SMs idle.)
+// min_n dis[n, pixel] over ALL points of an image (bl.py:39), through a uniform grid over the points.
+// The minimum is exact whatever the order of the points, so they may be visited by locality instead of by index:
+//   bl_grid_build_kernel : one CTA per image sorts its points by grid cell (counting sort in shared memory; the order
+//                          inside a cell is whatever the atomics give -- it cannot change a minimum);
+//   bl_gridmin_kernel    : warp task = (image, pixel tile).  The warp visits the cells around its tile ring by ring
+//                          (ring d = cells at Chebyshev cell distance d from the cells the tile's rectangle of pixel
+//                          centres overlaps): every point of a ring is tested against the exact per-point lower bound
+//                          of TileBox and, if it can still lower some pixel's minimum, swept over the tile.  Any point of
+//                          a ring beyond d lies at least d cells away from the rectangle, so the walk stops as soon as
+//                          the tile's largest current minimum is below that distance (minus the rounding slack of the
+//                          reference's cancelling expansion).
+// A QNRF image (12 000 heads, 96 tiles) costs ~2.5 k instructions per tile instead of ~80 k for the index-ordered
+// chunk sweeps this replaces (83 us of the 1.95 ms path on the config-3 batch), and there are no per-chunk minima to
+// combine -- or, in the sharded path, to exchange: every rank finds the minima of the images it touches from the
+// (replicated) points itself.
+constexpr int GRID_MAX_CELLS = 1024;
+
+struct GridGeom {
+    float cell, inv_cell;   // cell side in image pixels (a power of two: cell indices are exact), its reciprocal
+    int gx, gy;             // cells per row / column, gx * gy <= GRID_MAX_CELLS
+    float slack_m;          // magnitude term of the ring bound's rounding slack (see TileBox::lower_bound)
+};
+
+__device__ __forceinline__ int grid_cell_1d(float v, float inv_cell, int n) {
+    return min(max((int)floorf(v * inv_cell), 0), n - 1);   // points outside the grid fall into the border cells
+}
+
+__global__ void __launch_bounds__(1024)
+bl_grid_build_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, GridGeom gg,
+                     int img_first, int32_t* __restrict__ goff, float2* __restrict__ gsorted) {
+    __shared__ int hist[GRID_MAX_CELLS];
+    __shared__ int warp_tot[32];
+    const int img = img_first + blockIdx.x, tid = threadIdx.x;
+    const Meta mv = meta_view(meta, batch);
+    const int pt0 = mv.pt_off[img], n = mv.pt_off[img + 1] - pt0;
+    if (n == 0) return;
+    const float2* pts = pts_all + pt0;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const float2 p = __ldg(pts + i);
+        atomicAdd(&hist[grid_cell_1d(p.y, gg.inv_cell, gg.gy) * gg.gx + grid_cell_1d(p.x, gg.inv_cell, gg.gx)], 1);
+    }
+    __syncthreads();
+    const int mine = hist[tid];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL_MASK, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        const int w = warp_tot[tid];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, wi, o);
+            if (tid >= o) wi += v;
+        }
+        warp_tot[tid] = wi - w;
+    }
+    __syncthreads();
+    const int excl = warp_tot[tid >> 5] + incl - mine;
+    int32_t* off = goff + (size_t)img * (GRID_MAX_CELLS + 1);
+    off[tid] = excl;                       // cells past gx * gy are empty: their offsets equal n
+    if (tid == 1023) off[GRID_MAX_CELLS] = n;
+    hist[tid] = excl;                      // now the write cursor of the cell
+    __syncthreads();
+    float2* out = gsorted + pt0;
+    for (int i = tid; i < n; i += 1024) {
+        const float2 p = __ldg(pts + i);
+        out[atomicAdd(&hist[grid_cell_1d(p.y, gg.inv_cell, gg.gy) * gg.gx + grid_cell_1d(p.x, gg.inv_cell, gg.gx)], 1)] = p;
+    }
+}
+
 template <int R, int C>
-__device__ __forceinline__ bool bl_min_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch,
-                                            const Geom& g, float* __restrict__ minpart, int stage, int chunk_lo,
-                                            const Xchg& x) {
+__global__ void __launch_bounds__(CTA_THREADS)
+bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict__ goff, const int32_t* __restrict__ meta,
+                  int batch, Geom g, GridGeom gg, int img_first, float* __restrict__ min_img) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return false;
-    if (t.n_chunks <= 1) return false;  // single-chunk images take the fused path inside bl_z_kernel
-    const int lead = max(t.first_chunk, chunk_lo);   // the image's first chunk on this rank
-    if (stage >= 0 && (t.chunk == lead) != (stage == 0)) return false;  // stage < 0: one launch, every chunk on its own
-    WarpTile<R>& tile = tiles[threadIdx.x >> 5];
+    t.task = blockIdx.x * WARPS_PER_CTA + warp;
+    if (t.task >= g.tiles) return;
+    t.img = img_first + blockIdx.y;
+    const Meta mv = meta_view(meta, batch);
+    const int pt0 = mv.pt_off[t.img], n = mv.pt_off[t.img + 1] - pt0;
+    if (n == 0) return;
+    t.col0 = (t.task % g.col_blocks) * 32 * C + lane;
+    t.row_base = (t.task / g.col_blocks) * R;
+    WarpTile<R>& tile = tiles[warp];
     PixelTile<R, C> px;
     px.init(t, g);
-    const size_t M = (size_t)g.hp * g.wp;
+    const TileBox box = px.box;
+    const int32_t* off = goff + (size_t)t.img * (GRID_MAX_CELLS + 1);
+    const float2* sp = gsorted + pt0;
+    const int cx0 = grid_cell_1d(box.x0, gg.inv_cell, gg.gx), cx1 = grid_cell_1d(box.x1, gg.inv_cell, gg.gx);
+    const int cy0 = grid_cell_1d(box.y0, gg.inv_cell, gg.gy), cy1 = grid_cell_1d(box.y1, gg.inv_cell, gg.gy);
     float mind[R][C];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-            mind[r][c] = stage <= 0 ? __int_as_float(0x7f800000) : minpart[(size_t)lead * M + px.pix(r, c)];
-    sweep_min<R, C>(tile, px, pts_all + t.pt_base, t.p_cnt, mind);
-    float* out = minpart + (size_t)t.chunk * M;
-    const unsigned int dst = x.peers ? x.mask[t.chunk] : 0u;
+        for (int c = 0; c < C; ++c) mind[r][c] = __int_as_float(0x7f800000);
+    int staged = 0;
+    float bound = __int_as_float(0x7f800000);
+
+    auto sweep_staged = [&]() {   // the staged points over the tile; refreshes the pruning bound
+        __syncwarp();
+#pragma unroll 2
+        for (int i = 0; i < staged; ++i) {
+            const float2 xs = tile.xs[i];
+            float yd[R];
+            load_yd<R>(tile, i, yd);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float xd = axis_sqdist(xs.x, xs.y, px.cxm2[c], px.cxx[c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) mind[r][c] = fminf(mind[r][c], __fadd_rn(yd[r], xd));
+            }
+        }
+        staged = 0;
+        bound = tile_max<R, C>(mind);
+        __syncwarp();
+    };
+    auto feed = [&](int first, int count) {   // points [first, first + count) of the sorted list: test, stage, sweep when full
+        for (int base = 0; base < count; base += 32) {
+            const int i = base + lane;
+            float2 p = make_float2(0.f, 0.f);
+            bool keep = false;
+            if (i < count) {
+                p = __ldg(sp + first + i);
+                keep = box.lower_bound(p.x, p.y) <= bound;
+            }
+            const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+                const int pos = staged + __popc(ballot & ((1u << lane) - 1u));
+                tile.xs[pos] = make_float2(p.x, __fmul_rn(p.x, p.x));
+                const float yy = __fmul_rn(p.y, p.y);
+#pragma unroll
+                for (int r = 0; r < R; ++r) tile.yd[pos][r] = axis_sqdist(p.y, yy, px.cym2[r], px.cyy[r]);
+            }
+            staged += __popc(ballot);
+            if (staged > TILE_PTS - 32) sweep_staged();
+        }
+    };
+
+    const int max_d = max(max(cx0, gg.gx - 1 - cx1), max(cy0, gg.gy - 1 - cy1));
+    for (int d = 0; d <= max_d; ++d) {
+        for (int j = max(cy0 - d, 0); j <= min(cy1 + d, gg.gy - 1); ++j) {
+            const int i0 = max(cx0 - d, 0), i1 = min(cx1 + d, gg.gx - 1);
+            if (d == 0 || j == cy0 - d || j == cy1 + d) {   // a full row of the ring: one contiguous run of cells
+                const int a = off[j * gg.gx + i0];
+                feed(a, off[j * gg.gx + i1 + 1] - a);
+            } else {                                       // the ring's two side cells of this row
+                if (cx0 - d >= 0) {
+                    const int a = off[j * gg.gx + cx0 - d];
+                    feed(a, off[j * gg.gx + cx0 - d + 1] - a);
+                }
+                if (cx1 + d < gg.gx) {
+                    const int a = off[j * gg.gx + cx1 + d];
+                    feed(a, off[j * gg.gx + cx1 + d + 1] - a);
+                }
+            }
+        }
+        sweep_staged();
+        // every point not visited yet lies in a ring beyond d: at least d cells from the tile's rectangle
+        const float far = (float)d * gg.cell, lb = far * far;
+        if (bound <= lb - fmaf(lb, 9.5367431640625e-07f /*2^-20*/, gg.slack_m * 1.9073486328125e-06f /*2^-19*/)) break;
+    }
+    float* out = min_img + (size_t)t.img * g.hp * g.wp;
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < C; ++c)
             if (px.ok(r, c)) out[px.pix(r, c)] = mind[r][c];
-    for (unsigned int m = dst; m; m &= m - 1u) {  // the same tile into the workspaces of the image's other ranks
-        float* rp = xchg_ptr(x, __ffs(m) - 1, x.region_off) + (size_t)t.chunk * M;
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-                if (px.ok(r, c)) rp[px.pix(r, c)] = mind[r][c];
-    }
-    return dst != 0u;
-}
-
-template <int R, int C>
-__global__ void __launch_bounds__(CTA_THREADS)
-bl_min_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, Geom g,
-              float* __restrict__ minpart, int stage, int chunk_lo, Xchg x) {
-    const bool stored = bl_min_body<R, C>(pts_all, meta, batch, g, minpart, stage, chunk_lo, x);
-    if (stage != 0) xchg_signal(x, stored);  // the flag goes up after the last launch; stage 0 only fences its stores
-    else if (stored) fence_acq_rel_gpu();
-}
-
-// Sharded path: min over the chunks of an image once they have all arrived, so that bl_z_kernel reads one value per
-// pixel instead of one per chunk (small chunks, many of them).
-__global__ void __launch_bounds__(256)
-bl_min_combine_kernel(const int32_t* __restrict__ meta, int batch, int M, int img_first, const float* __restrict__ minpart,
-                      float* __restrict__ min_img, Xchg x, int n_img) {
-    xchg_wait(x);
-    if ((int)blockIdx.y >= n_img) return;
-    const int img = img_first + blockIdx.y;
-    const Meta mv = meta_view(meta, batch);
-    const int first = mv.icb[img], n_chunks = mv.icb[img + 1] - first;
-    const int pix = blockIdx.x * 256 + threadIdx.x;
-    if (n_chunks <= 1 || pix >= M) return;
-    float m = __int_as_float(0x7f800000);
-    for (int c = 0; c < n_chunks; ++c) m = fminf(m, minpart[(size_t)(first + c) * M + pix]);
-    min_img[(size_t)img * M + pix] = m;
 }
 
 // ------------------------------------------------------------------------------------------ K1
@@ -561,7 +636,7 @@ bl_min_combine_kernel(const int32_t* __restrict__ meta, int batch, int M, int im
 template <int R, int C, bool POW2>
 __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, const Geom& g, const Scale& k, float bg_ratio, int use_bg,
-            int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
+            int exact_cull, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, const Shard& sh,
             const float* __restrict__ min_img, const Xchg& x) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
@@ -590,24 +665,11 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
     const float2* pts = pts_all + t.pt_base;
 
     float neg_amax[R][C];  // first holds min dis, then k2 = -amax * log2(e)
-    if (t.n_chunks == 1) {
+    {  // bl_gridmin_kernel has been over the image
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int c = 0; c < C; ++c) neg_amax[r][c] = __int_as_float(0x7f800000);
-        sweep_min<R, C>(tile, px, pts, t.p_cnt, neg_amax);
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const int p = px.pix(r, c);
-                float m = __int_as_float(0x7f800000);
-                if (min_img) m = min_img[(size_t)t.img * M + p];  // bl_min_combine_kernel has been over the chunks
-                else
-                    for (int ch = 0; ch < t.n_chunks; ++ch) m = fminf(m, minpart[(size_t)(t.first_chunk + ch) * M + p]);
-                neg_amax[r][c] = m;
-            }
+            for (int c = 0; c < C; ++c) neg_amax[r][c] = min_img[(size_t)t.img * M + px.pix(r, c)];
     }
 
     float ebg_arg[R][C], amax_v[R][C];  // (a_bg - amax) * log2(e); amax itself (stored for the later sweeps)
@@ -702,10 +764,10 @@ template <int R, int C, bool POW2>
 __global__ void __launch_bounds__(CTA_THREADS)
 bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
-            int exact_cull, const float* __restrict__ minpart, float* __restrict__ zpart,
+            int exact_cull, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, Shard sh,
             const float* __restrict__ min_img, Xchg x) {
-    const bool stored = bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull, minpart,
+    const bool stored = bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull,
                                               zpart, amax_out, ebg_out, ticket, sh, min_img, x);
     xchg_signal(x, stored);
 }
@@ -1486,10 +1548,11 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     const int count_rows = ceil_div(tiles, WARPS_PER_CTA);  // one partial row per CTA of bl_counts_kernel
     L->cpart = take((size_t)count_rows * rows);
     L->zpart = take(chunk_pix);
-    L->minpart = take(chunk_pix);
-    L->gpart = L->minpart;  // minima are dead once the denominators exist; backward re-uses the region
+    L->gpart = take(chunk_pix);
+    L->minpart = L->gpart;       // (no per-chunk minima any more: bl_gridmin_kernel writes per-image minima into the pbg region)
+    L->goff = take((size_t)batch * (GRID_MAX_CELLS + 1) * sizeof(int32_t));   // grid cell offsets per image
+    L->gsorted = take((size_t)total_rows * sizeof(float2));                   // points sorted by grid cell (<= rows)
     if (world > 0) {
-        L->gpart = take(chunk_pix);  // a fast peer may already push the next step's minima while this rank still adds gradient sums
         L->dens = take(pix);         // density of every image this rank sweeps, delivered by the image's owner
         L->gfinal = take(pix);       // finished gradients, delivered to the image's owner
     }
@@ -1572,30 +1635,55 @@ inline void mark(void** events, int i, cudaStream_t st) {
     if (events && events[i]) cudaEventRecord((cudaEvent_t)events[i], st);
 }
 
-// per-chunk partial minima of the images cut into several chunks: first chunks, then the others bounded by them
-int launch_min(const Plan& p, const float2* pts, const int32_t* meta, int batch, float* minpart, cudaStream_t st) {
-    for (int stage = p.sh.on ? 0 : -1; stage < (p.sh.on ? 2 : 0); ++stage) {
-        if (p.v.rows == 8 && p.v.cols == 2) bl_min_kernel<8, 2><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
-        else if (p.v.rows == 8) bl_min_kernel<8, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
-        else if (p.v.rows == 4) bl_min_kernel<4, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
-        else bl_min_kernel<2, 1><<<p.grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, Xchg{});
-        if (cudaError_t e = cudaGetLastError()) return (int)e;
+GridGeom make_grid(int hp, int wp, float stride) {
+    const float ex = wp * stride, ey = hp * stride;
+    GridGeom gg;
+    gg.cell = 64.f;
+    for (;;) {
+        gg.gx = (int)ceilf(ex / gg.cell);
+        gg.gy = (int)ceilf(ey / gg.cell);
+        if ((long)gg.gx * gg.gy <= GRID_MAX_CELLS) break;
+        gg.cell *= 2.f;
     }
-    return DGVCC_OK;
+    gg.gx = gg.gx < 1 ? 1 : gg.gx;
+    gg.gy = gg.gy < 1 ? 1 : gg.gy;
+    gg.inv_cell = 1.f / gg.cell;
+    const float e = ex > ey ? ex : ey;
+    gg.slack_m = 32.f * e * e;   // covers points up to four grid extents away; farther ones are far beyond any bound
+    return gg;
+}
+
+// per-pixel minima of the images [img_first, img_first + n_img): grid build + ring walk, into min_img [B, hp*wp]
+int launch_gridmin(const Plan& p, const float2* pts, const int32_t* meta, int batch, int hp, int wp, int img_first, int n_img,
+                   void* ws, float* min_img, cudaStream_t st) {
+    if (n_img <= 0) return DGVCC_OK;
+    const GridGeom gg = make_grid(hp, wp, p.g.stride);
+    int32_t* goff = at<int32_t>(ws, p.L.goff);
+    float2* gsorted = at<float2>(ws, p.L.gsorted);
+    bl_grid_build_kernel<<<n_img, 1024, 0, st>>>(pts, meta, batch, gg, img_first, goff, gsorted);
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    const dim3 grid(ceil_div(p.g.tiles, WARPS_PER_CTA), n_img);
+    if (p.v.rows == 8 && p.v.cols == 2) bl_gridmin_kernel<8, 2><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
+    else if (p.v.rows == 8) bl_gridmin_kernel<8, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
+    else if (p.v.rows == 4) bl_gridmin_kernel<4, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
+    else bl_gridmin_kernel<2, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
+    return (int)cudaGetLastError();
 }
 
 // partial minima (multi-chunk images only) + softmax max / denominator shares
 int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
              int multi_chunk, float bg_ratio, int use_bg, int exact_cull, void* ws, cudaStream_t st,
              void** events = nullptr) {
-    float* minpart = at<float>(ws, p.L.minpart);
+    float* min_img = at<float>(ws, p.L.pbg);   // the region is free until the posteriors of the background row are written
     const float2* pts = (const float2*)pts_xy;
+    (void)multi_chunk;
     mark(events, 0, st);
-    if (multi_chunk) DGVCC_RETURN_IF_CUDA((cudaError_t)launch_min(p, pts, meta, batch, minpart, st));
+    int rc = launch_gridmin(p, pts, meta, batch, p.g.hp, p.g.wp, 0, batch, ws, min_img, st);
+    if (rc) return rc;
     mark(events, 1, st);
     BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
-                exact_cull, minpart, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg),
-                at<unsigned int>(ws, p.L.ticket), p.sh, (const float*)nullptr, Xchg{});
+                exact_cull, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg),
+                at<unsigned int>(ws, p.L.ticket), p.sh, (const float*)min_img, Xchg{});
     mark(events, 2, st);
     return (int)cudaGetLastError();
 }
@@ -1783,7 +1871,7 @@ extern "C" int dgvcc_bl_shard_preload(void) {
     cudaFuncAttributes a;
 #define BL_PRELOAD(K) DGVCC_RETURN_IF_CUDA(cudaFuncGetAttributes(&a, K))
 #define BL_PRELOAD_RC(R_, C_)                     \
-    BL_PRELOAD((bl_min_kernel<R_, C_>));          \
+    BL_PRELOAD((bl_gridmin_kernel<R_, C_>));      \
     BL_PRELOAD((bl_z_kernel<R_, C_, true>));      \
     BL_PRELOAD((bl_z_kernel<R_, C_, false>));     \
     BL_PRELOAD((bl_counts_kernel<R_, C_, true>)); \
@@ -1802,7 +1890,7 @@ extern "C" int dgvcc_bl_shard_preload(void) {
     BL_PRELOAD(bl_wait_kernel);
     BL_PRELOAD(bl_signal_kernel);
     BL_PRELOAD(bl_loss_finish_kernel);
-    BL_PRELOAD(bl_min_combine_kernel);
+    BL_PRELOAD(bl_grid_build_kernel);
     BL_PRELOAD(bl_finish_z_kernel);
 #undef BL_PRELOAD_RC
 #undef BL_PRELOAD
@@ -1850,45 +1938,23 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         return rc;
     }
     mark(events, 1, st);
-    // per-chunk minima of the images cut into several chunks, stored at home and on the image's other ranks; the flag
-    // goes up with the second stage
-    if (multi_chunk) {
-        float* minpart = at<float>(workspace, p.L.minpart);
-        const Xchg x = c.make(DGVCC_BL_PH_MIN, c.zmask(), p.L.minpart, 0, -1, -1);
-        const dim3 grid = sweeps ? p.grid : dim3(1, 1);  // a rank without chunks still raises its flag
-        for (int stage = 0; stage < 2; ++stage) {
-            const int slots_meta = sweeps ? 0 : -1;
-            (void)slots_meta;
-            if (!sweeps) {
-                if (stage == 1) bl_signal_kernel<<<1, 32, 0, st>>>(x);
-            } else if (p.v.rows == 8 && p.v.cols == 2) bl_min_kernel<8, 2><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
-            else if (p.v.rows == 8) bl_min_kernel<8, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
-            else if (p.v.rows == 4) bl_min_kernel<4, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
-            else bl_min_kernel<2, 1><<<grid, CTA_THREADS, 0, st>>>(pts, meta, batch, p.g, minpart, stage, p.sh.chunk_lo, x);
-            DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-            mark(events, 2 + stage, st);
-        }
-    }
-    if (multi_chunk && (rc = shard_wait(c, DGVCC_BL_PH_MIN))) return rc;
+    // per-pixel minima of the images this rank touches, from ALL their points (replicated on every rank): no exchange
+    (void)multi_chunk;
     float* min_img = at<float>(workspace, p.L.pbg);  // the region is free until bl_finish_z_kernel fills it
-    if (multi_chunk && (n_img > 0 || (shard->fuse_waits && shard->wait_mask[DGVCC_BL_PH_MIN]))) {
-        bl_min_combine_kernel<<<pix_grid, 256, 0, st>>>(meta, batch, M, p.sh.img_lo, at<float>(workspace, p.L.minpart), min_img,
-                                                       c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_MIN, -1), n_img);
-        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    }
-    mark(events, 4, st);
+    if (sweeps && (rc = launch_gridmin(p, pts, meta, batch, hp, wp, p.sh.img_lo, n_img, workspace, min_img, st))) return rc;
+    mark(events, 2, st);
     {
         const Xchg x = c.make(DGVCC_BL_PH_Z, c.zmask(), p.L.zpart, 0, -1, -1);
         if (sweeps) {
             BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
-                        at<float>(workspace, p.L.minpart), at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
+                        at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
                         at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img, x);
         } else {
             bl_signal_kernel<<<1, 32, 0, st>>>(x);
         }
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
-    mark(events, 5, st);
+    mark(events, 3, st);
     if (side) DGVCC_RETURN_IF_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // this rank's own copies are in place
     if ((rc = shard_wait(c, DGVCC_BL_PH_Z))) return rc;
     if ((rc = shard_wait(c, DGVCC_BL_PH_DENS))) return rc;
@@ -1896,7 +1962,7 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
                                                  at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), p.sh.img_lo,
                                                  c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_Z, DGVCC_BL_PH_DENS), n_img);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    mark(events, 6, st);
+    mark(events, 4, st);
     if (sweeps) {
         BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
                     use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
@@ -1904,13 +1970,13 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
                     at<float>(workspace, p.L.cpart), p.sh, 1);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
-    mark(events, 7, st);
+    mark(events, 5, st);
     // fixed-order sums of the tile partials of this rank's rows, delivered to the image's other ranks as they are written
     bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
         at<float>(workspace, p.L.cpart), p.L.tiles, total_rows, meta, targets, batch, at<float>(workspace, p.L.counts),
         at<float>(workspace, p.L.residual), p.sh, c.make(DGVCC_BL_PH_CNT, c.img_mask(), p.L.counts, p.L.residual, -1, -1));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    mark(events, 8, st);
+    mark(events, 6, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_CNT))) return rc;
     // top-k cut and per-image loss of every image this rank touches; the rank with an image's first chunk tells everybody
     bl_select_kernel<<<n_img > 0 ? n_img : 1, SELECT_THREADS, 0, st>>>(
@@ -1918,7 +1984,7 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.loss_img), loss_out, at<unsigned int>(workspace, p.L.ticket),
         p.sh.img_lo, 0, p.sh, c.make(DGVCC_BL_PH_LOSS, nullptr, p.L.loss_img, 0, DGVCC_BL_PH_CNT, -1), n_img);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    mark(events, 9, st);
+    mark(events, 7, st);
     // the images' losses from all ranks, summed in image order -- a barrier over the whole group, which the backward
     // pass does not need: with defer_loss the same two launches close dgvcc_bl_shard_backward instead
     if (!defer_loss) {
@@ -1926,7 +1992,7 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         bl_loss_finish_kernel<<<1, 64, 0, st>>>(at<float>(workspace, p.L.loss_img), batch, inv_batch, loss_out,
                                                 c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_LOSS, -1));
     }
-    mark(events, 10, st);
+    mark(events, 8, st);
     return (int)cudaGetLastError();
 }
 

@@ -147,9 +147,8 @@ class ShardPlan:
             for ch in range(c0, c1):
                 r = int(self.c_owner[ch])
                 for q in g:
-                    if q != r:                            # minima and denominator shares: among the image's ranks
+                    if q != r:                            # denominator shares: among the image's ranks
                         zmask[r, ch] |= np.uint32(1 << q)
-                        flag(P.BL_PH_MIN, r, q)
                         flag(P.BL_PH_Z, r, q)
                 if r != lead:                             # gradient sums -> the rank with the image's first chunk
                     gmask[r, ch] = np.uint32(1 << lead)
@@ -326,7 +325,7 @@ class _ShardedFn(torch.autograd.Function):
             plan.batch, hp, wp, plan.total_rows, plan.total_chunks, plan.multi_chunk, float(pp.stride), float(pp.sigma),
             float(pp.bg_ratio), int(pp.use_bg), int(mod.exact_cull), inv_batch, ctypes.byref(shard), _native.ptr(slices),
             _native.ptr(aux), _native.ptr(comm.peer_table), _native.ptr(comm.workspace), comm.nbytes, _native.ptr(loss),
-            int(defer), _native.stream_ptr(dev), mod._event_handles("fwd", 11))
+            int(defer), _native.stream_ptr(dev), mod._event_handles("fwd", 9))
         _native.check(rc, "dgvcc_bl_shard_forward")
         ctx.saved = (mod, plan, packed, (slices, aux), inv_batch, comm.epoch, density_local.shape, density_local.dtype, n_own,
                      loss if defer else None)
@@ -413,9 +412,8 @@ class ChunkShardedBL(Module):
         st = st_sizes.to(device=dev, dtype=torch.float32).contiguous()
         return _ShardedFn.apply(pre_density_local, self, plan, packed, st, 1.0 / plan.batch)
 
-    FWD_PHASES = ["push DENS", "min stage 0", "min stage 1 (+MIN out)", "[wait MIN] combine", "z (+Z out)",
-                  "[wait Z, DENS] finish_z", "counts", "reduce_counts (+CNT out)", "[wait CNT] select (+LOSS out)",
-                  "[wait LOSS] loss"]
+    FWD_PHASES = ["issue DENS copy (side stream)", "grid build + minima", "z (+Z out)", "[wait Z, DENS] finish_z", "counts",
+                  "reduce_counts (+CNT out)", "[wait CNT] select (+LOSS out)", "[wait LOSS] loss"]
     BWD_PHASES = ["grad (+GPART out)", "[wait GPART] reduce (+GRAD out)", "[wait GRAD] gather", "[wait LOSS] deferred loss"]
 
     def _event_handles(self, which, n):

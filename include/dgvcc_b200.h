@@ -84,15 +84,17 @@ typedef struct dgvcc_bl_layout {
     int64_t ticket;    /* [1]       u32  must be zero on entry (memset once)         */
     int64_t cpart;     /* [tiles*rows] f32 partial counts, one row per CTA of the sweep */
     int64_t zpart;     /* [C*hp*wp] f32  per-chunk share of the softmax denominator  */
-    int64_t minpart;   /* [C*hp*wp] f32  per-chunk min squared distance              */
-    int64_t gpart;     /* [C*hp*wp] f32  per-chunk gradient sums (aliases minpart)   */
+    int64_t minpart;   /* (alias of gpart; the per-pixel minima live in the pbg region until it is written) */
+    int64_t gpart;     /* [C*hp*wp] f32  per-chunk gradient sums                     */
     int64_t total;     /* bytes needed                                               */
     /* regions of the symmetric (sharded) layout only, 0 otherwise -- dgvcc_bl_shard_workspace_layout */
     int64_t dens;      /* [B*hp*wp] f32  density of the images this rank sweeps      */
     int64_t gfinal;    /* [B*hp*wp] f32  finished gradients, at the image's owner    */
     int64_t flags;     /* [PHASES*world] u32 arrival flags (phase, source rank)      */
     int64_t err;       /* [1] i32        non-zero: a wait timed out (1 + phase + 16*source) */
-    int64_t push_ticket; /* [1] u32                                                  */
+    int64_t push_ticket; /* [2] u32                                                  */
+    int64_t goff;      /* [B*(1024+1)] i32 grid-cell offsets of the points of each image (bl_grid_build_kernel) */
+    int64_t gsorted;   /* [rows*2] f32   points sorted by grid cell                   */
     int32_t tiles;     /* partial-count rows (CTAs of 4 pixel tiles) per point chunk */
     int32_t rows_per_thread; /* kernel variant chosen for this shape: grid rows ...   */
     int32_t cols_per_thread; /* ... and columns owned by one thread                  */
@@ -159,7 +161,8 @@ int dgvcc_bl_bayloss_backward(const float* prob, const int32_t* meta, int batch,
  * span over all pixels of the images they belong to, and what an image's other ranks need travels as plain stores
  * into their workspaces over NVLink (peer pointers from dgvcc_peer_open), one arrival flag per (phase, source):
  *   DENS   density of an image, owner -> every rank that sweeps it          (before the expected counts)
- *   MIN    per-chunk minima (bl.py:39), Z per-chunk denominator shares (bl.py:44)   among the image's ranks
+ *   Z      per-chunk denominator shares (bl.py:44)                           among the image's ranks
+ *          (the minima of bl.py:39 need no exchange: every rank finds them from the replicated points; MIN is unused)
  *   CNT    expected counts + residuals of a rank's rows (bl.py:73-75)        among the image's ranks (top-k needs all)
  *   LOSS   per-image loss, from the rank with the image's first chunk to everybody (summed in image order, bl.py:79)
  *   GPART  per-chunk gradient sums -> the rank with the image's first chunk, which finishes the gradient
@@ -223,8 +226,8 @@ int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch,
  * i.e. the loss value is complete once the backward launches have run.  The density copy runs on a side stream owned
  * by the library (one per device), forked from and joined to `stream` by events. */
 /* `events` (NULL, or caller-created cudaEvent_t handles; NULL entries skipped) are recorded on the stream between the
- * launches, for per-kernel timing.  forward (11): start, after the DENS copy, min stage 0, min stage 1, [wait MIN] combine,
- * bl_z, [wait Z, DENS] finish_z, bl_counts, the row reduction, [wait CNT] selection, [wait LOSS] loss.
+ * launches, for per-kernel timing.  forward (9): start, after the DENS copy is issued, grid build + minima, bl_z,
+ * [wait Z, DENS] finish_z, bl_counts, the row reduction, [wait CNT] selection, [wait LOSS] loss.
  * backward (5): start, bl_grad, [wait GPART] reduction, [wait GRAD] gather, [wait LOSS] deferred loss. */
 
 /* Peer-visible device memory for the sharded workspaces (CUDA IPC between the ranks' processes of one box):

@@ -60,7 +60,7 @@ def test_exchange_plan_is_consistent(counts, world):
     L, m4 = p.layout, 4 * 24 * 32
     P = _native
     b, c = len(counts), p.total_chunks
-    assert 0 == L.flags < L.err < L.push_ticket < L.amax and L.gpart != L.minpart and L.total > L.gfinal > 0
+    assert 0 == L.flags < L.err < L.push_ticket < L.amax and L.total > L.gfinal > 0 and L.goff > 0 and L.gsorted > L.goff
     recv = np.zeros((world, P.BL_PHASES), dtype=np.uint32)
     for r in range(world):
         sh, sl = p.shards[r], p.slices[r]
@@ -103,7 +103,7 @@ def test_exchange_plan_is_consistent(counts, world):
             else:
                 assert zmask[ch] == 0 and gmask[ch] == 0
         z_dst = int(np.bitwise_or.reduce(zmask)) if c else 0
-        assert z_dst == sh.signal_mask[P.BL_PH_Z] == sh.signal_mask[P.BL_PH_MIN]
+        assert z_dst == sh.signal_mask[P.BL_PH_Z] and sh.signal_mask[P.BL_PH_MIN] == 0 == sh.wait_mask[P.BL_PH_MIN]
         assert (int(np.bitwise_or.reduce(gmask)) if c else 0) == sh.signal_mask[P.BL_PH_GPART]
         assert int(np.bitwise_or.reduce(img_mask)) == sh.signal_mask[P.BL_PH_CNT]
         assert int(np.bitwise_or.reduce(owner_mask)) == sh.signal_mask[P.BL_PH_GRAD]

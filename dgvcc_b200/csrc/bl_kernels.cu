@@ -578,44 +578,72 @@ bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict_
         bound = tile_max<R, C>(mind);
         __syncwarp();
     };
-    auto feed = [&](int first, int count) {   // points [first, first + count) of the sorted list: test, stage, sweep when full
-        for (int base = 0; base < count; base += 32) {
-            const int i = base + lane;
-            float2 p = make_float2(0.f, 0.f);
-            bool keep = false;
-            if (i < count) {
-                p = __ldg(sp + first + i);
-                keep = box.lower_bound(p.x, p.y) <= bound;
-            }
-            const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
-            if (keep) {
-                const int pos = staged + __popc(ballot & ((1u << lane) - 1u));
-                tile.xs[pos] = make_float2(p.x, __fmul_rn(p.x, p.x));
-                const float yy = __fmul_rn(p.y, p.y);
-#pragma unroll
-                for (int r = 0; r < R; ++r) tile.yd[pos][r] = axis_sqdist(p.y, yy, px.cym2[r], px.cyy[r]);
-            }
-            staged += __popc(ballot);
-            if (staged > TILE_PTS - 32) sweep_staged();
-        }
-    };
-
+    // A ring is a handful of runs of consecutive cells (its top and bottom rows, two side cells per row in between);
+    // the points of a run are consecutive in the sorted list.  Lane q looks up run q's point range -- all ranges of a
+    // ring in ONE round trip to memory instead of one per run -- and the warp then walks the concatenation of the
+    // ranges 32 points at a time (each lane finds its run by a 5-step search through the lanes' prefix sums).
     const int max_d = max(max(cx0, gg.gx - 1 - cx1), max(cy0, gg.gy - 1 - cy1));
     for (int d = 0; d <= max_d; ++d) {
-        for (int j = max(cy0 - d, 0); j <= min(cy1 + d, gg.gy - 1); ++j) {
-            const int i0 = max(cx0 - d, 0), i1 = min(cx1 + d, gg.gx - 1);
-            if (d == 0 || j == cy0 - d || j == cy1 + d) {   // a full row of the ring: one contiguous run of cells
-                const int a = off[j * gg.gx + i0];
-                feed(a, off[j * gg.gx + i1 + 1] - a);
-            } else {                                       // the ring's two side cells of this row
-                if (cx0 - d >= 0) {
-                    const int a = off[j * gg.gx + cx0 - d];
-                    feed(a, off[j * gg.gx + cx0 - d + 1] - a);
+        const int j_lo = max(cy0 - d, 0), j_hi = min(cy1 + d, gg.gy - 1);
+        const int i_lo = max(cx0 - d, 0), i_hi = min(cx1 + d, gg.gx - 1);
+        const bool top = d == 0 || cy0 - d >= 0, bottom = d > 0 && cy1 + d < gg.gy;        // full rows of the ring inside the grid
+        const bool left = d > 0 && cx0 - d >= 0, right = d > 0 && cx1 + d < gg.gx;         // side columns inside the grid
+        // run numbering: d == 0: one run per row; d > 0: [top row] [bottom row] then per middle row [left cell] [right cell]
+        const int mid_lo = d == 0 ? 0 : max(cy0 - d + 1, 0), mid_hi = d == 0 ? -1 : min(cy1 + d - 1, gg.gy - 1);
+        const int n_mid = max(mid_hi - mid_lo + 1, 0);
+        const int n_runs = d == 0 ? (j_hi - j_lo + 1) : (2 + 2 * n_mid);
+        for (int run0 = 0; run0 < n_runs; run0 += 32) {
+            const int q = run0 + lane;
+            int first = 0, count = 0;
+            if (q < n_runs) {
+                int c0 = -1, c1 = -1;   // cells [c0, c1] of the run, row-major
+                if (d == 0) { c0 = (j_lo + q) * gg.gx + i_lo; c1 = (j_lo + q) * gg.gx + i_hi; }
+                else if (q == 0) { if (top) { c0 = (cy0 - d) * gg.gx + i_lo; c1 = (cy0 - d) * gg.gx + i_hi; } }
+                else if (q == 1) { if (bottom) { c0 = (cy1 + d) * gg.gx + i_lo; c1 = (cy1 + d) * gg.gx + i_hi; } }
+                else {
+                    const int jr = mid_lo + ((q - 2) >> 1);
+                    if (((q - 2) & 1) == 0) { if (left) c0 = c1 = jr * gg.gx + cx0 - d; }
+                    else if (right) c0 = c1 = jr * gg.gx + cx1 + d;
                 }
-                if (cx1 + d < gg.gx) {
-                    const int a = off[j * gg.gx + cx1 + d];
-                    feed(a, off[j * gg.gx + cx1 + d + 1] - a);
+                if (c0 >= 0) {
+                    first = __ldg(off + c0);
+                    count = __ldg(off + c1 + 1) - first;
                 }
+            }
+            int incl = count;   // prefix sums of the runs' lengths across the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(FULL_MASK, incl, 31);
+            const int excl = incl - count;
+            for (int base = 0; base < total; base += 32) {
+                const int gi = base + lane;
+                // the run that holds concatenated index gi: the last lane whose exclusive prefix is <= gi
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int e = __shfl_sync(FULL_MASK, excl, min(lo + step, 31));
+                    if (lo + step < 32 && e <= gi) lo += step;
+                }
+                const int r_first = __shfl_sync(FULL_MASK, first, lo), r_excl = __shfl_sync(FULL_MASK, excl, lo);
+                float2 p = make_float2(0.f, 0.f);
+                bool keep = false;
+                if (gi < total) {
+                    p = __ldg(sp + r_first + (gi - r_excl));
+                    keep = box.lower_bound(p.x, p.y) <= bound;
+                }
+                const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
+                if (keep) {
+                    const int pos = staged + __popc(ballot & ((1u << lane) - 1u));
+                    tile.xs[pos] = make_float2(p.x, __fmul_rn(p.x, p.x));
+                    const float yy = __fmul_rn(p.y, p.y);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) tile.yd[pos][r] = axis_sqdist(p.y, yy, px.cym2[r], px.cyy[r]);
+                }
+                staged += __popc(ballot);
+                if (staged > TILE_PTS - 32) sweep_staged();
             }
         }
         sweep_staged();

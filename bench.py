@@ -304,7 +304,7 @@ def kernel_breakdown(wl, dev, reps=5):
     grad = torch.empty_like(dens)
     gl = torch.ones(1, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    names = ["bl_min", "bl_z", "bl_counts", "bl_reduce_counts+bl_select", "bl_grad(+reduce)"]
+    names = ["bl_grid_build+bl_gridmin", "bl_z", "bl_counts", "bl_reduce_counts+bl_select", "bl_grad(+reduce)"]
     acc = np.zeros(len(names))
     for rep in range(reps + 1):
         flush.zero_()
@@ -621,7 +621,7 @@ def run_gpu(args, emit=print):
             "clocks": clocks,
             "e2e": {"value": global_batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (7 if packed.multi_chunk else 5),
+            "gpu_launches": args.steps * (8 if packed.multi_chunk else 7),
             "e2e_packed_collate": {"value": global_batch * args.steps / e2e_packed_s, "unit": "images/s",
                                    "note": ("informational: same end-to-end step, but the ragged lists were packed once by "
                                             "pack_batch (what a collate_fn does in the DataLoader workers) instead of inside "
@@ -635,7 +635,7 @@ def run_gpu(args, emit=print):
             "roofline": {
                 "bound": "sfu", "achieved": achieved / 1e9, "peak": peak_ex2 / 1e9, "unit": "Gexp/s",
                 "frac": achieved / peak_ex2, "traffic": traffic, "traffic_note": traffic_note,
-                "note": ("fused BL path (bl_min+bl_z+bl_counts+bl_reduce_counts+bl_select+bl_grad+bl_grad_reduce), MUFU.EX2-bound; achieved = executed "
+                "note": ("fused BL path (bl_grid_build+bl_gridmin+bl_z+bl_counts+bl_reduce_counts+bl_select+bl_grad+bl_grad_reduce), MUFU.EX2-bound; achieved = executed "
                          "exponentials / sum of kernel times; peak = dgvcc_probe_ex2 measured in this run "
                          "(MEASURED_PEAKS.json carries no SFU peak)"),
                 "algorithmic_exps_per_step": algorithmic, "executed_exps_per_step": executed,

@@ -463,10 +463,9 @@ struct ExpCull {
 //                          a ring beyond d lies at least d cells away from the rectangle, so the walk stops as soon as
 //                          the tile's largest current minimum is below that distance (minus the rounding slack of the
 //                          reference's cancelling expansion).
-// A QNRF image (12 000 heads, 96 tiles) costs ~2.5 k instructions per tile instead of ~80 k for the index-ordered
-// chunk sweeps this replaces (83 us of the 1.95 ms path on the config-3 batch), and there are no per-chunk minima to
-// combine -- or, in the sharded path, to exchange: every rank finds the minima of the images it touches from the
-// (replicated) points itself.
+// Measured on the config-3 batch: 70 us (13 build + 57 walk) against 83 us for the index-ordered per-chunk sweeps this
+// replaces -- and there are no per-chunk minima to combine or, in the sharded path, to exchange: every rank finds the
+// minima of the images it touches from the (replicated) points itself, which removes one of five exchange phases.
 constexpr int GRID_MAX_CELLS = 1024;
 
 struct GridGeom {
@@ -1690,11 +1689,14 @@ int launch_gridmin(const Plan& p, const float2* pts, const int32_t* meta, int ba
     float2* gsorted = at<float2>(ws, p.L.gsorted);
     bl_grid_build_kernel<<<n_img, 1024, 0, st>>>(pts, meta, batch, gg, img_first, goff, gsorted);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    const dim3 grid(ceil_div(p.g.tiles, WARPS_PER_CTA), n_img);
-    if (p.v.rows == 8 && p.v.cols == 2) bl_gridmin_kernel<8, 2><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
-    else if (p.v.rows == 8) bl_gridmin_kernel<8, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
-    else if (p.v.rows == 4) bl_gridmin_kernel<4, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
-    else bl_gridmin_kernel<2, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, p.g, gg, img_first, min_img);
+    // The minima have their own, small pixel tile (2 rows x 32 columns), independent of the exponential sweeps': every point
+    // inside a tile's own rectangle is swept over the whole tile whatever the bound, so a crowd of 1500 heads inside one
+    // 8 x 64 tile is a 50k-instruction warp -- the critical path of the launch.  Measured on the config-3 batch (grid
+    // build included): 8x2 123 us, 8x1 85, 4x1 75, 2x1 70.
+    const Variant v{2, 1};
+    const Geom gm = make_geom(hp, wp, v, p.g.stride);
+    const dim3 grid(ceil_div(gm.tiles, WARPS_PER_CTA), n_img);
+    bl_gridmin_kernel<2, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, gm, gg, img_first, min_img);
     return (int)cudaGetLastError();
 }
 
@@ -1899,7 +1901,6 @@ extern "C" int dgvcc_bl_shard_preload(void) {
     cudaFuncAttributes a;
 #define BL_PRELOAD(K) DGVCC_RETURN_IF_CUDA(cudaFuncGetAttributes(&a, K))
 #define BL_PRELOAD_RC(R_, C_)                     \
-    BL_PRELOAD((bl_gridmin_kernel<R_, C_>));      \
     BL_PRELOAD((bl_z_kernel<R_, C_, true>));      \
     BL_PRELOAD((bl_z_kernel<R_, C_, false>));     \
     BL_PRELOAD((bl_counts_kernel<R_, C_, true>)); \
@@ -1919,6 +1920,7 @@ extern "C" int dgvcc_bl_shard_preload(void) {
     BL_PRELOAD(bl_signal_kernel);
     BL_PRELOAD(bl_loss_finish_kernel);
     BL_PRELOAD(bl_grid_build_kernel);
+    BL_PRELOAD((bl_gridmin_kernel<2, 1>));
     BL_PRELOAD(bl_finish_z_kernel);
 #undef BL_PRELOAD_RC
 #undef BL_PRELOAD

@@ -86,7 +86,7 @@ def main():
             ok_all = ok_all and bool(flag.item())
 
     results = {}
-    for forced in ([int(c) for c in args.chunks.split(",")] if args.chunks else [None]):
+    for forced in ([None if c == "auto" else int(c) for c in args.chunks.split(",")] if args.chunks else [None]):
         # ---- timing: config 3, dense
         blmod._CHUNK_POINTS = 1024
         from dgvcc_b200.losses import bl_sharded

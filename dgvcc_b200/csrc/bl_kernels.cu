@@ -952,7 +952,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------ K3
-constexpr int SELECT_THREADS = 512;
+constexpr int SELECT_THREADS = 1024;
 
 __device__ __forceinline__ float block_sum_ordered(float v, float* scratch) {
     // deterministic: warp butterfly, then warp partials added in warp order by thread 0

@@ -1,6 +1,6 @@
 """One warm-up + one measured pass of the secondary kernels: the ISW module (InstanceWhitening + covariance loss,
 forward + backward, B=8 C=256 HW=6400) and one density map (2048^2, 25 000 heads), adaptive then fixed sigma.
-Run under ncu with -k regex:'isw_|dmap_' -s 22 -c 22 (22 matching launches per pass)."""
+Run under ncu with -k regex:'isw_|dmap_' -s 23 -c 23 (23 matching launches per pass: 7 ISW, 9 adaptive, 7 fixed)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

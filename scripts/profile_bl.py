@@ -1,4 +1,5 @@
-"""Two fused-BL steps on BASELINE config 3 (first = warm-up); run under ncu with -k regex:bl_ -s 7 -c 7."""
+"""Two fused-BL steps on BASELINE config 3 (first = warm-up), dense sweep (what bench.py grades); run under ncu with
+-k regex:bl_ -s 8 -c 8 (8 launches per step: grid build, minima, z, counts, row reduction, selection, grad, grad reduction)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,6 +16,7 @@ tgt = [torch.from_numpy(t).to(dev) for t in tgt]
 dens = torch.from_numpy(dens).to(dev).requires_grad_(True)
 st = torch.from_numpy(st).to(dev)
 mod = BL(8.0, max(w, h), 8, 1.0, True, dev)
+mod.exact_cull = False
 for _ in range(2):
     dens.grad = None
     loss = mod(pts, st, tgt, dens)

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -24,7 +24,7 @@ if os.path.exists(launches):
         agg.setdefault(d["Kernel Name"].split("(")[0][:70], []).append(float(d["Metric Value"].replace(",", "")))
     total = sum(sum(v) for v in agg.values())
     with open(os.path.join(out_dir, f"{tag}_bench_launches.md"), "w") as f:
-        f.write(f"# ncu launch list, `python bench.py --steps 3 --warmup 3 --no-cpu-baseline` ({tag})\n\n"
+        f.write(f"# ncu launch list, `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-aux --no-eager` ({tag})\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch times are cold-cache and "
                 "serialised: compare SHARES.\n\n| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -104,11 +104,11 @@ if os.path.exists(rep):
     aux = os.path.join(ROOT, "gpurun_out", f"aux_{tag}.ncu-rep")
     if os.path.exists(aux):
         summarize(aux, f"ncu --set full, ISW module fwd+bwd (B=8, C=256, HW=6400) and one density map (2048x2048, 25 000 heads; adaptive, then fixed sigma) ({tag})",
-                  "ncu --set full --clock-control none --import-source on -k 'regex:isw_|dmap_' -s 22 -c 22 python scripts/profile_aux.py",
+                  "ncu --set full --clock-control none --import-source on -k 'regex:isw_|dmap_' -s 23 -c 23 python scripts/profile_aux.py",
                   os.path.join(out_dir, f"{tag}_aux_ncu_summary.md"), os.path.join(out_dir, f"{tag}_aux_ncu_raw.csv"))
     with open(os.path.join(out_dir, f"{tag}_bl_ncu_summary.md"), "w") as f:
         f.write(f"# ncu --set full, fused Bayesian loss, BASELINE config 3 ({tag})\n\n"
-                "`ncu --set full --clock-control none --import-source on -k regex:bl_ -s 7 -c 7 python scripts/profile_bl.py`\n"
+                "`ncu --set full --clock-control none --import-source on -k regex:bl_ -s 8 -c 8 python scripts/profile_bl.py`\n"
                 "(second step of two; 16 images, 192x256 grid, 49 697 heads).  Durations under ncu are cold-cache.\n\n")
         names = [d[idx["Kernel Name"]].split("(")[0].replace("void ", "") for d in data]
         f.write("| metric | " + " | ".join(f"`{n}`" for n in names) + " |\n|---|" + "---|" * len(names) + "\n")

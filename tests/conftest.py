@@ -68,8 +68,12 @@ _install_margin_hooks()
 
 def pytest_terminal_summary(terminalreporter):
     import helpers
-    worst = {}
+    worst, info = {}, {}
     for test, what, ratio, rtol, atol in helpers.MARGINS:
+        if "(informational)" in what:   # never asserted: e.g. the same data against SURVEY 8d's tighter floor
+            if test not in info or ratio > info[test][1]:
+                info[test] = (what, ratio, rtol, atol)
+            continue
         if test not in worst or ratio > worst[test][1]:
             worst[test] = (what, ratio, rtol, atol)
     gpu_only = {t: v for t, v in worst.items() if "_gpu.py" in t}
@@ -80,3 +84,8 @@ def pytest_terminal_summary(terminalreporter):
     tr.write_line(f"parity margins: worst |err| / gate per test (1.0 = at the gate), {len(gpu_only)} tests")
     for test, (what, ratio, rtol, atol) in sorted(gpu_only.items(), key=lambda kv: -kv[1][1]):
         tr.write_line(f"  {ratio:8.3g}  {test}  [{what}; rtol {rtol:g}, atol {atol:.3g}]")
+    over = {t: v for t, v in info.items() if v[1] > 1.0}
+    if info:
+        tr.write_line(f"informational margins (not asserted): {len(info)} tests, {len(over)} of them beyond 1.0:")
+        for test, (what, ratio, rtol, atol) in sorted(info.items(), key=lambda kv: -kv[1][1])[:12]:
+            tr.write_line(f"  {ratio:8.3g}  {test}  [{what}]")

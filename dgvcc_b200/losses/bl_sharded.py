@@ -274,6 +274,24 @@ class IpcComm:
             dist.barrier(group=group)
         self._finish()
 
+    def close(self):
+        """Unmap the peers' workspaces and free this rank's own (collective in spirit: call it on every rank, after the
+        last step has been synchronised)."""
+        if getattr(self, "ptrs", None) is None or isinstance(self, LocalComm):
+            return
+        torch.cuda.synchronize(self.device)
+        lib = _native.lib()
+        self.workspace = self.peer_table = None
+        with torch.cuda.device(self.device):
+            for r, p in enumerate(self.ptrs):
+                if r != self.rank:
+                    lib.dgvcc_peer_close(ctypes.c_void_p(p))
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier(group=self.group)   # nobody frees memory a peer still has mapped and may be writing to
+            lib.dgvcc_peer_free(ctypes.c_void_p(self.ptrs[self.rank]))
+        self.ptrs = None
+
     def _finish(self):
         with torch.cuda.device(self.device):
             _native.check(_native.lib().dgvcc_bl_shard_preload(), "dgvcc_bl_shard_preload")

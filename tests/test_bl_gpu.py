@@ -1,6 +1,6 @@
 """Parity of the fused CUDA Bayesian loss (through the C ABI) against the CPU oracle and the
 reference-generated fixtures.  Tolerance (BASELINE.json north_star): rtol 1e-5 in fp32; absolute
-floors: 1e-30 for posteriors (entries that underflow), 1e-6*max|ref| for gradients (sums with
+floors: 1e-30 for posteriors (entries that underflow), 2e-7*max|ref| for gradients (sums with
 cancellation -- the reference's own fp32 error against its fp64 evaluation is larger than that)."""
 import numpy as np
 import pytest
@@ -40,7 +40,10 @@ def run_cuda(points, st_sizes, targets, density, stride, sigma, bg_ratio, use_bg
 
 def check_against(loss, grad, counts, ref_loss, ref_grad, ref_counts):
     assert_close(loss, ref_loss, RTOL, 0, "loss")
-    assert_close(grad, ref_grad, RTOL, 1e-6 * float(ref_grad.abs().max()), "density gradient")
+    # floor: 2e-7 * max|ref| since round 2 (1e-6 before).  SURVEY 8d's 1e-7 is recorded below, not asserted: the worst
+    # case sits at 1.1 of that gate (profiles/r2_gputest_margins.txt) -- the gradient is a signed sum of posteriors and
+    # the reference's own fp32 sum order is not the kernels'
+    assert_close(grad, ref_grad, RTOL, 2e-7 * float(ref_grad.abs().max()), "density gradient")
     # informational (not asserted): the same comparison with SURVEY 8d's floor of 1e-7 * max|ref|, so that the log shows
     # which cases need the wider floor (the gradient is a signed sum of posteriors: cancellation, see the module docstring)
     from helpers import record_margin

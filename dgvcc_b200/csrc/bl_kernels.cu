@@ -953,6 +953,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
 
 // ------------------------------------------------------------------------------------------ K3
 constexpr int SELECT_THREADS = 1024;
+constexpr int SELECT_REGS = 12;   // residuals a thread keeps in registers across the radix passes (12 288 rows per image)
 
 __device__ __forceinline__ float block_sum_ordered(float v, float* scratch) {
     // deterministic: warp butterfly, then warp partials added in warp order by thread 0
@@ -970,20 +971,22 @@ __device__ __forceinline__ float block_sum_ordered(float v, float* scratch) {
 // across rows), and the residual |t - c|  (bl.py:73-75).
 __device__ __forceinline__ bool bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
-                        float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x);
+                        float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x,
+                        int64_t row_first);
 
 __global__ void __launch_bounds__(256)
 bl_reduce_counts_kernel(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
-                        float* __restrict__ counts, float* __restrict__ residual, Shard sh, Xchg x) {
-    const bool stored = bl_reduce_counts_body(cpart, tiles, total_rows, meta, targets, batch, counts, residual, sh, x);
+                        float* __restrict__ counts, float* __restrict__ residual, Shard sh, Xchg x, int64_t row_first) {
+    const bool stored = bl_reduce_counts_body(cpart, tiles, total_rows, meta, targets, batch, counts, residual, sh, x, row_first);
     xchg_signal(x, stored);
 }
 
 __device__ __forceinline__ bool bl_reduce_counts_body(const float* __restrict__ cpart, int tiles, int64_t total_rows,
                         const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
-                        float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x) {
-    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+                        float* __restrict__ counts, float* __restrict__ residual, const Shard& sh, const Xchg& x,
+                        int64_t row_first) {
+    const int64_t j = row_first + (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (j >= total_rows) return false;
     const Meta mv = meta_view(meta, batch);
     int lo = 0, hi = batch;  // image of row j: row_off[lo] <= j < row_off[lo+1]
@@ -1045,12 +1048,24 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
         thr = 0u; take_equal = 0u;  // keep nothing (residuals are >= +0, none is < 0)
     } else if (n_keep < n_cand) {
         if (tid == 0) { sh_prefix = 0u; sh_rank = (unsigned)n_keep; }
+        // the four radix passes read the residuals from registers: up to SELECT_REGS per thread are loaded ONCE, all
+        // loads in flight together (re-reading them from L2 in every pass was a chain of 4 x 12 load latencies for a
+        // 12 000-row image); longer images read the tail from memory in every pass
+        unsigned int held[SELECT_REGS];
+#pragma unroll
+        for (int u = 0; u < SELECT_REGS; ++u) {
+            const int j = tid + u * SELECT_THREADS;
+            held[u] = j < n_cand ? __float_as_uint(residual[row0 + j]) : 0u;
+        }
         unsigned int mask = 0u;
         for (int shift = 24; shift >= 0; shift -= 8) {
             for (int b = tid; b < 256; b += SELECT_THREADS) hist[b] = 0u;
             __syncthreads();
             const unsigned int prefix = sh_prefix;
-            for (int j = tid; j < n_cand; j += SELECT_THREADS) {
+#pragma unroll
+            for (int u = 0; u < SELECT_REGS; ++u)
+                if (tid + u * SELECT_THREADS < n_cand && (held[u] & mask) == prefix) atomicAdd(&hist[(held[u] >> shift) & 255u], 1u);
+            for (int j = tid + SELECT_REGS * SELECT_THREADS; j < n_cand; j += SELECT_THREADS) {
                 const unsigned int bits = __float_as_uint(residual[row0 + j]);
                 if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
             }
@@ -1722,7 +1737,7 @@ int launch_reduce_counts(const dgvcc_bl_layout& L, const float* targets, const i
                          int64_t total_rows, int tiles, void* ws, const Shard& sh, cudaStream_t st) {
     bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
         at<float>(ws, L.cpart), tiles, total_rows, meta, targets, batch, at<float>(ws, L.counts),
-        at<float>(ws, L.residual), sh, Xchg{});
+        at<float>(ws, L.residual), sh, Xchg{}, (int64_t)0);
     return (int)cudaGetLastError();
 }
 
@@ -2002,9 +2017,11 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
     }
     mark(events, 5, st);
     // fixed-order sums of the tile partials of this rank's rows, delivered to the image's other ranks as they are written
-    bl_reduce_counts_kernel<<<(unsigned)((total_rows + 255) / 256), 256, 0, st>>>(
+    // (only the rows of the images this rank touches can be its own: the grid covers that window, not the batch)
+    const int64_t row_lo = shard->row_lo, row_hi = shard->row_hi > shard->row_lo ? shard->row_hi : shard->row_lo + 1;
+    bl_reduce_counts_kernel<<<(unsigned)((row_hi - row_lo + 255) / 256), 256, 0, st>>>(
         at<float>(workspace, p.L.cpart), p.L.tiles, total_rows, meta, targets, batch, at<float>(workspace, p.L.counts),
-        at<float>(workspace, p.L.residual), p.sh, c.make(DGVCC_BL_PH_CNT, c.img_mask(), p.L.counts, p.L.residual, -1, -1));
+        at<float>(workspace, p.L.residual), p.sh, c.make(DGVCC_BL_PH_CNT, c.img_mask(), p.L.counts, p.L.residual, -1, -1), row_lo);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 6, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_CNT))) return rc;

@@ -182,6 +182,7 @@ class ShardPlan:
             sh.chunk_lo, sh.chunk_hi = int(self.chunk_lo[r]), int(self.chunk_hi[r])
             sh.pt_lo, sh.pt_hi = int(self.bounds[r]), int(self.bounds[r + 1])
             sh.img_lo, sh.img_hi = int(self.img_lo[r]), int(self.img_hi[r])
+            sh.row_lo, sh.row_hi = int(self.row_off[sh.img_lo]), int(self.row_off[sh.img_hi])
             for ph in range(P.BL_PHASES + 1):
                 sh.push_first[ph] = first[ph]
             for ph in range(P.BL_PHASES):

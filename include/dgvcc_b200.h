@@ -198,6 +198,7 @@ typedef struct dgvcc_bl_shard {
     int32_t chunk_lo, chunk_hi;   /* chunk ids this rank sweeps                         */
     int32_t pt_lo, pt_hi;         /* = packed points [pt_lo, pt_hi)                     */
     int32_t img_lo, img_hi;       /* images it touches                                  */
+    int32_t row_lo, row_hi;       /* = posterior rows [row_off[img_lo], row_off[img_hi]) */
     int32_t push_first[DGVCC_BL_PHASES + 1];   /* slices of phase p: [push_first[p], push_first[p+1]) */
     uint32_t wait_mask[DGVCC_BL_PHASES];       /* ranks whose flag of phase p this rank waits for     */
     uint32_t signal_mask[DGVCC_BL_PHASES];     /* ranks this rank signals after its slices of phase p */

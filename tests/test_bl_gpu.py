@@ -142,6 +142,25 @@ def test_config3_qnrf_image_matches_oracle():
     check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
 
 
+def test_large_image_takes_coarser_grid_cells():
+    """A 4096 x 3072 px image (512 x 384 grid): more than 1024 cells of 64 px, so the point grid of the minima doubles its
+    cell size; heads partly outside the image (the border cells), a sparse and a crowded image in one batch."""
+    rng = np.random.default_rng(4096)
+    w, h, stride = 4096, 3072, 8
+    pts = []
+    for n in (60, 3000):
+        p = synthetic.crowd_points(np.random.default_rng(50 + n), n, w, h)
+        p[: n // 10] += rng.uniform(-120, 120, size=(n // 10, 2)).astype(np.float32)   # some slightly outside
+        pts.append(torch.from_numpy(p))
+    tgt = [torch.from_numpy(rng.uniform(0.3, 1.0, size=len(p)).astype(np.float32)) for p in pts]
+    dens = torch.from_numpy(np.abs(rng.normal(size=(2, 1, h // stride, w // stride))).astype(np.float32) * 0.01)
+    st = torch.tensor([float(h), float(h)])
+    ref = bl_oracle.bl_forward_backward_chunked(pts, st, tgt, dens, stride, 8.0, 1.0, True, chunk_rows=16)
+    for cull in (False, True):
+        got = run_cuda(pts, st, tgt, dens, stride, 8.0, 1.0, True, exact_cull=cull)
+        check_against(*got, ref[0], ref[1], dict(enumerate(ref[2])))
+
+
 def test_config3_full_batch_matches_oracle():
     """The FULL BASELINE config-3 batch (16 images, 49 697 heads, 192x256 grid) -- the workload bench.py times --
     against the chunked oracle: loss, every expected count and the whole density gradient, dense and culled."""

@@ -304,7 +304,7 @@ def kernel_breakdown(wl, dev, reps=5):
     grad = torch.empty_like(dens)
     gl = torch.ones(1, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    names = ["bl_grid_build+bl_gridmin", "bl_z", "bl_counts", "bl_reduce_counts+bl_select", "bl_grad(+reduce)"]
+    names = ["bl_grid_build+bl_gridmin", "bl_z(+finish)", "bl_counts", "bl_reduce_counts+bl_select", "bl_grad(+finish)"]
     acc = np.zeros(len(names))
     for rep in range(reps + 1):
         flush.zero_()
@@ -456,6 +456,67 @@ def strong_scaling(args, dev, rank, world, t1_ms, flush, barrier):
                               "note": "against the ordinary BL module on one GPU (other chunk boundaries, so other rounding of the "
                                       "chunk-partial sums); bit-identity with the same chunk table is tested in "
                                       "tests/test_bl_sharded_gpu.py and scripts/shard_bl_multi_gpu.py"}}
+    # ---- by row band: every rank sweeps ALL points over 1/N of the grid rows; one exchange (the count shares)
+    try:
+        from dgvcc_b200.losses.bl_banded import BandShardedBL, plan_bands
+        bmod = BandShardedBL(SIGMA, max(wl["width"], wl["height"]), STRIDE, BG_RATIO, USE_BG, dev, comm)
+        bmod.exact_cull = False
+        bplan = plan_bands(wl["counts"], USE_BG, world, None, wl["hp"], wl["wp"])
+        band_d = wl["density"][bplan.owned[rank]].to(dev).requires_grad_(True)
+
+        def band_step():
+            band_d.grad = None
+            loss = bmod(wl["points"], st_all, wl["targets"], band_d)
+            loss.backward()
+            return loss
+
+        per_rank = timed(band_step)
+        bmod.check()
+        got = band_step()
+        rel_loss = abs(float(got) - float(ref_loss)) / abs(float(ref_loss))
+        gref = d_all.grad[bplan.owned[rank]].reshape(band_d.grad.shape)
+        rel_grad = float((band_d.grad - gref).abs().max() / gref.abs().max()) if len(bplan.owned[rank]) else 0.0
+        everyone = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(everyone, got.detach().reshape(1))
+        worst = torch.tensor([rel_loss, rel_grad], device=dev, dtype=torch.float64)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        bmod.profile = True
+        acc = {}
+        for _ in range(5):
+            band_step()
+            for k, v in bmod.phase_ms().items():
+                acc[k] = acc.get(k, 0.0) + v / 5
+            flush.zero_()
+        bmod.profile = False
+        phases = [None] * world
+        dist.all_gather_object(phases, acc)
+        sent = sum(int(v[2]) & 0xffffffff for r in range(world) for v in bplan.slices[r][:bplan.shards[r].push_first[7]]
+                   if (int(v[2]) >> 32) != r)
+        tile_r, tile_c = bplan.layout.rows_per_thread, bplan.layout.cols_per_thread
+        col_blocks = -(-wl["wp"] // (32 * tile_c))
+        part_rows = [-(-(-(-int(h - l) // tile_r) * col_blocks) // 4) for l, h in zip(bplan.band_lo, bplan.band_hi)]
+        sent += sum(part_rows) * (world - 1) * 4 * bplan.total_rows                           # CNT: every partial row to every peer
+        sent += sum(4 * wl["wp"] * (wl["hp"] - int(bplan.band_hi[o] - bplan.band_lo[o])) for o in bplan.owners)   # GRAD rows
+        out["by_band"] = {
+            "partition": (f"grid rows cut into {world} bands of whole pixel-tile rows "
+                          f"({[int(h - l) for l, h in zip(bplan.band_lo, bplan.band_hi)]} rows); every rank sweeps all "
+                          f"{sum(wl['counts'])} heads ({bplan.total_chunks} chunks of <= {bplan.chunk} points) over its band"),
+            "pixel_tile_rows_cols": [bplan.layout.rows_per_thread, bplan.layout.cols_per_thread],
+            "ms_per_rank": per_rank, "ms_per_step": max(per_rank), "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / world),
+            "images_per_s": b / (max(per_rank) * 1e-3), "speedup": t1_ms / max(per_rank),
+            "collective": ("none (no NCCL on the data path): density rows owner -> band rank on a side stream; the per-CTA partial "
+                           "counts of a band stored on every rank by bl_counts itself over NVLink peer memory (the ONE "
+                           "data-dependent exchange; added in pixel-tile order, so every rank gets the same loss bits as one "
+                           "GPU); gradient rows stored at the image's owner by bl_grad itself; one arrival flag per (phase, source)"),
+            "bytes_pushed_per_step_all_ranks": sent,
+            "phase_ms_max_over_ranks": {k: round(max(ph[k] for ph in phases), 4) for k in phases[0]},
+            "same_loss_bits_on_every_rank": all(torch.equal(v, everyone[0]) for v in everyone),
+            "parity_vs_one_gpu": {"loss_rel": float(worst[0]), "grad_rel_to_max": float(worst[1]),
+                                  "note": "against the ordinary BL module on one GPU (1024-point chunks there); with the same "
+                                          "chunk table the gradient is bit-identical (tests/test_bl_sharded_gpu.py, "
+                                          "scripts/shard_bl_multi_gpu.py --mode band)"}}
+    except Exception as exc:  # keep the other legs
+        out["by_band"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 
@@ -621,7 +682,7 @@ def run_gpu(args, emit=print):
             "clocks": clocks,
             "e2e": {"value": global_batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (8 if packed.multi_chunk else 7),
+            "gpu_launches": args.steps * 7,   # grid_build, gridmin, z, counts, reduce_counts, select | grad
             "e2e_packed_collate": {"value": global_batch * args.steps / e2e_packed_s, "unit": "images/s",
                                    "note": ("informational: same end-to-end step, but the ragged lists were packed once by "
                                             "pack_batch (what a collate_fn does in the DataLoader workers) instead of inside "
@@ -635,7 +696,7 @@ def run_gpu(args, emit=print):
             "roofline": {
                 "bound": "sfu", "achieved": achieved / 1e9, "peak": peak_ex2 / 1e9, "unit": "Gexp/s",
                 "frac": achieved / peak_ex2, "traffic": traffic, "traffic_note": traffic_note,
-                "note": ("fused BL path (bl_grid_build+bl_gridmin+bl_z+bl_counts+bl_reduce_counts+bl_select+bl_grad+bl_grad_reduce), MUFU.EX2-bound; achieved = executed "
+                "note": ("fused BL path (bl_grid_build+bl_gridmin+bl_z+bl_counts+bl_reduce_counts+bl_select+bl_grad: 7 launches), MUFU.EX2-bound; achieved = executed "
                          "exponentials / sum of kernel times; peak = dgvcc_probe_ex2 measured in this run "
                          "(MEASURED_PEAKS.json carries no SFU peak)"),
                 "algorithmic_exps_per_step": algorithmic, "executed_exps_per_step": executed,

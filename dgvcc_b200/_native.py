@@ -19,8 +19,8 @@ class BLLayout(ctypes.Structure):
     """Mirror of struct dgvcc_bl_layout."""
     _fields_ = [(n, c_int64) for n in
                 ("amax", "rz", "pbg", "ebg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "zpart",
-                 "minpart", "gpart", "total", "dens", "gfinal", "flags", "err", "push_ticket", "goff", "gsorted")] + \
-               [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("reserved_", c_int32)]
+                 "minpart", "gpart", "total", "dens", "gfinal", "flags", "err", "push_ticket", "goff", "gsorted", "cshare", "ztick", "gtick")] + \
+               [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("share_rows", c_int32)]
 
 
 class BLPacked(ctypes.Structure):
@@ -30,6 +30,7 @@ class BLPacked(ctypes.Structure):
                  "total_bytes")]
 
 
+BL_OPT_MIN_CELL, BL_OPT_BAND_TILE = 0, 1  # dgvcc_bl_set_option
 BL_PHASES = 8  # DGVCC_BL_PHASES
 BL_PH_DENS, BL_PH_MIN, BL_PH_Z, BL_PH_CNT, BL_PH_LOSS, BL_PH_GPART, BL_PH_GRAD, BL_PH_OUT = range(BL_PHASES)
 
@@ -38,7 +39,8 @@ class BLShard(ctypes.Structure):
     """Mirror of struct dgvcc_bl_shard."""
     _fields_ = [(n, c_int32) for n in ("rank", "world", "chunk_lo", "chunk_hi", "pt_lo", "pt_hi", "img_lo", "img_hi", "row_lo", "row_hi")] + \
                [("push_first", c_int32 * (BL_PHASES + 1)), ("wait_mask", ctypes.c_uint32 * BL_PHASES),
-                ("signal_mask", ctypes.c_uint32 * BL_PHASES), ("epoch", ctypes.c_uint32), ("fuse_waits", c_int32)]
+                ("signal_mask", ctypes.c_uint32 * BL_PHASES), ("epoch", ctypes.c_uint32), ("fuse_waits", c_int32),
+                ("band_lo", c_int32), ("band_hi", c_int32)]
 
 
 class DmapPlan(ctypes.Structure):
@@ -56,6 +58,7 @@ DEN_META_COLS = 8    # DGVCC_DEN_META_COLS
 SIGNATURES = {
     "dgvcc_abi_version": (c_int, []),
     "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
+    "dgvcc_bl_set_option": (c_int, [c_int, c_int]),
     "dgvcc_bl_pack_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, POINTER(BLPacked)]),
     "dgvcc_bl_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                  c_int, c_int, c_float, c_float, c_float, c_int, c_int, c_float, c_void_p, c_size_t,
@@ -80,6 +83,12 @@ SIGNATURES = {
                                         c_int, c_float, c_void_p, POINTER(BLShard), c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_size_t, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
     "dgvcc_bl_shard_preload": (c_int, []),
+    "dgvcc_bl_band_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int,
+                                      c_float, c_float, c_float, c_int, c_int, c_float, POINTER(BLShard), c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "dgvcc_bl_band_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_float, c_float, c_int,
+                                       c_int, c_float, c_void_p, POINTER(BLShard), c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p, c_void_p, POINTER(c_void_p)]),
     "dgvcc_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "dgvcc_peer_free": (c_int, [c_void_p]),
     "dgvcc_peer_export": (c_int, [c_void_p, c_void_p]),

@@ -52,7 +52,9 @@ struct Scale {
 struct Geom {
     int hp, wp;        // grid rows, columns
     int col_blocks;    // ceil(wp / (32*C))
-    int tiles;         // warp tasks per (image, chunk) = col_blocks * ceil(hp / R)
+    int tiles;         // warp tasks per (image, chunk) = col_blocks * ceil(hp / R); a launch sweeps [task_first, tiles)
+    int task_first;    // 0, or (row-band sharding) the first warp task of the band of grid rows this rank sweeps
+    int tiles_img;     // warp tasks per (image, chunk) over the WHOLE grid (stride of the per-tile arrival counters)
     float stride;      // image pixels per grid cell
     float half;        // stride / 2
 };
@@ -272,7 +274,7 @@ template <int R, int C>
 __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, int batch, const Geom& g,
                                             TaskInfo& t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    t.task = blockIdx.x * WARPS_PER_CTA + warp;
+    t.task = g.task_first + blockIdx.x * WARPS_PER_CTA + warp;
     const Meta mv = meta_view(meta, batch);
     t.chunk = mv.chunks[4 * blockIdx.y + 3];
     const int32_t* ce = mv.chunks + 4 * t.chunk;
@@ -466,7 +468,8 @@ struct ExpCull {
 // Measured on the config-3 batch: 70 us (13 build + 57 walk) against 83 us for the index-ordered per-chunk sweeps this
 // replaces -- and there are no per-chunk minima to combine or, in the sharded path, to exchange: every rank finds the
 // minima of the images it touches from the (replicated) points itself, which removes one of five exchange phases.
-constexpr int GRID_MAX_CELLS = 1024;
+constexpr int GRID_MAX_CELLS = 4096;   // 4 cells per thread of bl_grid_build_kernel
+constexpr int GRID_CELLS_PER_THREAD = GRID_MAX_CELLS / 1024;
 
 struct GridGeom {
     float cell, inv_cell;   // cell side in image pixels (a power of two: cell indices are exact), its reciprocal
@@ -480,22 +483,35 @@ __device__ __forceinline__ int grid_cell_1d(float v, float inv_cell, int n) {
 
 __global__ void __launch_bounds__(1024)
 bl_grid_build_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, GridGeom gg,
-                     int img_first, int32_t* __restrict__ goff, float2* __restrict__ gsorted) {
+                     int img_first, int32_t* __restrict__ goff, float2* __restrict__ gsorted,
+                     unsigned int* __restrict__ ztick, unsigned int* __restrict__ gtick, int tiles_img) {
     __shared__ int hist[GRID_MAX_CELLS];
     __shared__ int warp_tot[32];
     const int img = img_first + blockIdx.x, tid = threadIdx.x;
+    // first kernel of every forward pass: the image's per-tile arrival counters (tile_last_arrival) start at zero
+    // even if an earlier step was cut short
+    for (int i = tid; i < tiles_img; i += 1024) {
+        ztick[(size_t)img * tiles_img + i] = 0u;
+        gtick[(size_t)img * tiles_img + i] = 0u;
+    }
     const Meta mv = meta_view(meta, batch);
     const int pt0 = mv.pt_off[img], n = mv.pt_off[img + 1] - pt0;
     if (n == 0) return;
     const float2* pts = pts_all + pt0;
-    hist[tid] = 0;
+#pragma unroll
+    for (int u = 0; u < GRID_CELLS_PER_THREAD; ++u) hist[tid + 1024 * u] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
         const float2 p = __ldg(pts + i);
         atomicAdd(&hist[grid_cell_1d(p.y, gg.inv_cell, gg.gy) * gg.gx + grid_cell_1d(p.x, gg.inv_cell, gg.gx)], 1);
     }
     __syncthreads();
-    const int mine = hist[tid];
+    int cellc[GRID_CELLS_PER_THREAD], mine = 0;   // this thread's consecutive cells
+#pragma unroll
+    for (int u = 0; u < GRID_CELLS_PER_THREAD; ++u) {
+        cellc[u] = hist[GRID_CELLS_PER_THREAD * tid + u];
+        mine += cellc[u];
+    }
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -515,11 +531,16 @@ bl_grid_build_kernel(const float2* __restrict__ pts_all, const int32_t* __restri
         warp_tot[tid] = wi - w;
     }
     __syncthreads();
-    const int excl = warp_tot[tid >> 5] + incl - mine;
+    int excl = warp_tot[tid >> 5] + incl - mine;
     int32_t* off = goff + (size_t)img * (GRID_MAX_CELLS + 1);
-    off[tid] = excl;                       // cells past gx * gy are empty: their offsets equal n
+    __syncthreads();                       // every thread has read its cells' counts
+#pragma unroll
+    for (int u = 0; u < GRID_CELLS_PER_THREAD; ++u) {
+        off[GRID_CELLS_PER_THREAD * tid + u] = excl;    // cells past gx * gy are empty: their offsets equal n
+        hist[GRID_CELLS_PER_THREAD * tid + u] = excl;   // now the write cursor of the cell
+        excl += cellc[u];
+    }
     if (tid == 1023) off[GRID_MAX_CELLS] = n;
-    hist[tid] = excl;                      // now the write cursor of the cell
     __syncthreads();
     float2* out = gsorted + pt0;
     for (int i = tid; i < n; i += 1024) {
@@ -535,7 +556,7 @@ bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict_
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TaskInfo t;
-    t.task = blockIdx.x * WARPS_PER_CTA + warp;
+    t.task = g.task_first + blockIdx.x * WARPS_PER_CTA + warp;
     if (t.task >= g.tiles) return;
     t.img = img_first + blockIdx.y;
     const Meta mv = meta_view(meta, batch);
@@ -658,6 +679,89 @@ bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict_
             if (px.ok(r, c)) out[px.pix(r, c)] = mind[r][c];
 }
 
+// The chunks of one image sweep the same pixel tile in separate warp tasks; whichever task arrives LAST at the tile's
+// counter combines the per-chunk partials (in chunk order, whoever does it: the sum does not depend on the arrival
+// order) -- the classic last-block reduction, per pixel tile.  Saves a reduction kernel and a second pass over the
+// partials; the counters are zeroed by bl_grid_build_kernel at the head of every forward pass and by the last arriver.
+__device__ __forceinline__ bool tile_last_arrival(unsigned int* counter, int n_chunks) {
+    __threadfence();   // this task's partials before its arrival
+    __syncwarp();
+    unsigned int old = 0u;
+    if ((threadIdx.x & 31) == 0) old = atomicAdd(counter, 1u);
+    old = __shfl_sync(FULL_MASK, old, 0);
+    const bool last = old == (unsigned)n_chunks - 1u;
+    if (last) {
+        if ((threadIdx.x & 31) == 0) *counter = 0u;
+        __threadfence();   // the other tasks' partials after their arrivals
+    }
+    return last;
+}
+
+// What the last arrival does, kept out of line so that the sweeps' register allocation is that of their inner loops:
+// the warp re-derives its pixels from (row_base, col0) and walks the chunks with all of a chunk's R*C loads in flight.
+template <int R, int C>
+__device__ __noinline__ void finish_z_tile(const float* __restrict__ zc, int n_chunks, size_t M, int row_base, int col0, int hp,
+                                           int wp, const float* __restrict__ ebg_img, float* __restrict__ rz_img,
+                                           float* __restrict__ pbg_img) {
+    // 1 / (sum of the chunk shares in chunk order + background term last), the reference's row order (bl.py:44)
+    int pix[R][C];
+    float z[R][C];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            pix[r][c] = min(row_base + r, hp - 1) * wp + min(col0 + 32 * c, wp - 1);  // outside the grid: the clamped twin
+            z[r][c] = 0.f;
+        }
+#pragma unroll 2
+    for (int ch = 0; ch < n_chunks; ++ch, zc += M) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) z[r][c] += __ldcg(zc + pix[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (row_base + r >= hp || col0 + 32 * c >= wp) continue;
+            const float ebg = __ldcg(ebg_img + pix[r][c]);
+            const float rz = 1.0f / (z[r][c] + ebg);
+            rz_img[pix[r][c]] = rz;
+            pbg_img[pix[r][c]] = ebg * rz;
+        }
+}
+
+// Gradient of a multi-chunk image's pixel tile: chunk sums added in chunk order, per-pixel factors applied.
+template <int R, int C>
+__device__ __noinline__ void finish_grad_tile(const float* __restrict__ gc, int n_chunks, size_t M, int row_base, int col0,
+                                              int hp, int wp, float gscale, float w_bg, const float* __restrict__ rz_img,
+                                              const float* __restrict__ pbg_img, float* __restrict__ gout_img) {
+    int pix[R][C];
+    float a[R][C];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            pix[r][c] = min(row_base + r, hp - 1) * wp + min(col0 + 32 * c, wp - 1);
+            a[r][c] = 0.f;
+        }
+#pragma unroll 2
+    for (int ch = 0; ch < n_chunks; ++ch, gc += M) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) a[r][c] += __ldcg(gc + pix[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (row_base + r >= hp || col0 + 32 * c >= wp) continue;
+            gout_img[pix[r][c]] = gscale * fmaf(a[r][c], rz_img[pix[r][c]], w_bg * pbg_img[pix[r][c]]);
+        }
+}
+
 // ------------------------------------------------------------------------------------------ K1
 // Softmax max (incl. the background row, bl.py:39-43) and this chunk's share of the denominator.
 template <int R, int C, bool POW2>
@@ -665,7 +769,8 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
             const float* __restrict__ st_sizes, int batch, const Geom& g, const Scale& k, float bg_ratio, int use_bg,
             int exact_cull, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, const Shard& sh,
-            const float* __restrict__ min_img, const Xchg& x) {
+            const float* __restrict__ min_img, const Xchg& x, float* __restrict__ rz_out, float* __restrict__ pbg_out,
+            unsigned int* __restrict__ tile_tick, int finish) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
     TaskInfo t;
@@ -686,6 +791,7 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
                 if (px.ok(r, c)) {
                     const int p = px.pix(r, c);
                     zout[p] = 0.f; amax_img[p] = 0.f; ebg_img[p] = 1.f;
+                    if (finish) { rz_out[(size_t)t.img * M + p] = 1.f; pbg_out[(size_t)t.img * M + p] = 1.f; }  // 1 / (0 + 1)
                 }
         return false;
     }
@@ -776,6 +882,11 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
                 ebg_img[p] = use_bg ? ex2_ftz(ebg_arg[r][c]) : 0.f;
             }
         }
+    // the task that arrives last at the pixel tile turns the chunk shares into 1 / denominator (the image's first chunk
+    // stored ebg before it arrived); out of line, see finish_z_tile
+    if (finish && (t.n_chunks == 1 || tile_last_arrival(tile_tick + (size_t)t.img * g.tiles_img + t.task, t.n_chunks)))
+        finish_z_tile<R, C>(zpart + (size_t)t.first_chunk * M, t.n_chunks, M, t.row_base, t.col0, g.hp, g.wp, ebg_img,
+                            rz_out + (size_t)t.img * M, pbg_out + (size_t)t.img * M);
     for (unsigned int m = dst; m; m &= m - 1u) {  // the same tile into the workspaces of the image's other ranks
         float* rp = xchg_ptr(x, __ffs(m) - 1, x.region_off) + (size_t)t.chunk * M;
 #pragma unroll
@@ -788,14 +899,16 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
 }
 
 template <int R, int C, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, 4)   // 16 warps per SM: <= 128 registers
 bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
             const float* __restrict__ st_sizes, int batch, Geom g, Scale k, float bg_ratio, int use_bg,
             int exact_cull, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, Shard sh,
-            const float* __restrict__ min_img, Xchg x) {
+            const float* __restrict__ min_img, Xchg x, float* __restrict__ rz_out, float* __restrict__ pbg_out,
+            unsigned int* __restrict__ tile_tick, int finish) {
     const bool stored = bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull,
-                                              zpart, amax_out, ebg_out, ticket, sh, min_img, x);
+                                              zpart, amax_out, ebg_out, ticket, sh, min_img, x, rz_out, pbg_out, tile_tick,
+                                              finish);
     xchg_signal(x, stored);
 }
 
@@ -809,16 +922,28 @@ __device__ __forceinline__ float softmax_rz(const float* __restrict__ zpart, siz
 }
 
 // ------------------------------------------------------------------------------------------ K2
+// One partial count: into this GPU's cpart, or (row-band sharding) into the count-share table of every rank.
+__device__ __forceinline__ void put_count(float* __restrict__ cpart, bool shared, const Xchg& x, size_t idx, float v) {
+    if (!shared) {
+        cpart[idx] = v;
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < x.world; ++q) xchg_ptr(x, q, x.region_off)[idx] = v;
+    }
+}
+
 template <int R, int C, bool POW2>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, 5)   // 5 CTAs per SM (what the 39 KB of shared memory allow): <= 102 registers
 bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
                  const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg, int exact_cull,
-                 const float* __restrict__ amax_in, const float* __restrict__ ebg_in,
-                 const float* __restrict__ zpart, float* __restrict__ rz_out, float* __restrict__ pbg_out,
-                 int64_t total_rows, float* __restrict__ cpart, Shard sh, int rz_ready) {
+                 const float* __restrict__ amax_in, const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
+                 int64_t total_rows, float* __restrict__ cpart, int share_row0, Xchg x) {
+    xchg_wait(x);  // row-band sharding: the density rows of the band, delivered by the images' owners
     // The four warps of a CTA sweep the same point chunk over four pixel tiles; their per-point partial counts
     // meet in shared memory and leave the CTA as ONE partial row (a quarter of the cpart traffic, and a quarter
     // of what bl_reduce_counts_kernel has to read).  Warps past the last pixel tile contribute zeros.
+    // share_row0 >= 0 (row-band sharding): the partial row is row share_row0 + blockIdx.x of the count-share table and
+    // goes, as it is produced, into the table of EVERY rank (plain stores over NVLink); the last CTA raises the flag.
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     __shared__ float cta_acc[WARPS_PER_CTA][COUNT_SPAN];
     __shared__ float cta_bg[WARPS_PER_CTA];
@@ -831,8 +956,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
     const size_t img_base = (size_t)t.img * M;
     PixelTile<R, C> px;
     px.init(t, g);
-    float* part = cpart + (size_t)blockIdx.x * total_rows + t.row0;
-    const bool first = t.chunk == max(t.first_chunk, sh.chunk_lo);  // first chunk of the image on this rank: rz / pbg
+    const size_t part0 = (size_t)(max(share_row0, 0) + (int)blockIdx.x) * total_rows + t.row0;
     const bool bg_row = t.chunk == t.first_chunk && (use_bg || t.n_img_pts == 0);  // the image's first chunk anywhere
 
     // per-pixel weights D[m]/Z[m]; pixels outside the grid get weight 0
@@ -845,29 +969,22 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
             const size_t m = img_base + p;
             const bool ok = live && px.ok(r, c);
             const float d = ok ? density[m] : 0.f;
-            float rz, pbg;
-            if (rz_ready) {  // bl_finish_z_kernel has been over the chunks (sharded path)
-                rz = rz_out[m];
-                pbg = pbg_out[m];
-            } else {
-                const float ebg = ebg_in[m];
-                rz = softmax_rz(zpart, M, t.first_chunk, t.n_chunks, p, ebg);
-                pbg = ebg * rz;
-                if (first && ok) { rz_out[m] = rz; pbg_out[m] = pbg; }
-            }
+            const float rz = rz_in[m], pbg = pbg_in[m];  // finished by bl_z_kernel's last arrival (or bl_finish_z_kernel)
             neg_amax[r][c] = __fmul_rn(-amax_in[m], LOG2E);
-            wd[r][c] = d * rz;
-            bg_part = fmaf(d, pbg, bg_part);
+            // a pixel outside the grid -- or, for the idle warps of a band's last CTA, outside the band, where this rank
+            // holds no denominators at all -- must not leak a NaN through 0 * inf
+            wd[r][c] = ok ? d * rz : 0.f;
+            if (ok) bg_part = fmaf(d, pbg, bg_part);
         }
     if (bg_row) {  // background row / sum-of-density row of an empty image
         bg_part = warp_sum(bg_part);
         if (lane == 0) cta_bg[warp] = bg_part;
     }
     __syncthreads();
-    if (bg_row && threadIdx.x == 0) part[t.n_rows - 1] = ((cta_bg[0] + cta_bg[1]) + cta_bg[2]) + cta_bg[3];
+    if (bg_row && threadIdx.x == 0)
+        put_count(cpart, share_row0 >= 0, x, part0 + t.n_rows - 1, ((cta_bg[0] + cta_bg[1]) + cta_bg[2]) + cta_bg[3]);
 
     const float2* pts = pts_all + t.pt_base;
-    part += t.p_start;
     const ExpCull cull{exact_cull != 0, tile_max<R, C>(neg_amax), k.k1, px.box};
     const Scale2 k2s(k);
     f2 k2p[R / 2][C], wdp[R / 2][C];
@@ -946,9 +1063,11 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
         }
         __syncthreads();
         for (int i = threadIdx.x; i < span_cnt; i += CTA_THREADS)
-            part[span0 + i] = ((cta_acc[0][i] + cta_acc[1][i]) + cta_acc[2][i]) + cta_acc[3][i];
+            put_count(cpart, share_row0 >= 0, x, part0 + t.p_start + span0 + i,
+                      ((cta_acc[0][i] + cta_acc[1][i]) + cta_acc[2][i]) + cta_acc[3][i]);
         __syncthreads();
     }
+    xchg_signal(x, share_row0 >= 0);
 }
 
 // ------------------------------------------------------------------------------------------ K3
@@ -1175,7 +1294,8 @@ __device__ __forceinline__ bool bl_grad_body(const float2* __restrict__ pts_all,
                const Geom& g, const Scale& k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
-               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, const Xchg& x) {
+               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, const Xchg& x,
+               unsigned int* __restrict__ tile_tick) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
     if (!decode_task<R, C>(meta, batch, g, t)) return false;
@@ -1235,19 +1355,38 @@ __device__ __forceinline__ bool bl_grad_body(const float2* __restrict__ pts_all,
 #pragma unroll
         for (int c = 0; c < C; ++c) unpack2(accp[q][c], acc[2 * q][c], acc[2 * q + 1][c]);
 
-    if (t.n_chunks == 1 && !always_partial) {
+    if (!always_partial) {
+        // One chunk: the sum is complete.  Several: park it in gpart; the task that arrives last at the tile adds the
+        // chunk sums in chunk order and applies the per-pixel factors (no reduction kernel, no second pass).
+        if (t.n_chunks > 1) {
+            float* out = gpart + (size_t)t.chunk * M;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (px.ok(r, c)) out[px.pix(r, c)] = acc[r][c];
+            if (!tile_last_arrival(tile_tick + (size_t)t.img * g.tiles_img + t.task, t.n_chunks)) return false;
+        }
         const float gscale = grad_loss[0] * inv_batch;
         const bool has_bg_row = use_bg || t.n_img_pts == 0;
         const float w_bg = has_bg_row ? wsel[t.row0 + t.n_rows - 1] : 0.f;
+        // row-band sharding: the finished rows go straight into the workspace of the image's owner
+        const unsigned int dst = x.peers ? x.mask[t.img] : 0u;
+        float* gout = (dst ? xchg_ptr(x, __ffs(dst) - 1, x.region_off) : grad_density) + img_base;
+        if (t.n_chunks > 1) {
+            finish_grad_tile<R, C>(gpart + (size_t)t.first_chunk * M, t.n_chunks, M, t.row_base, t.col0, g.hp, g.wp, gscale, w_bg,
+                                   rz_in + img_base, pbg_in + img_base, gout);
+        } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (!px.ok(r, c)) continue;
-                const size_t m = img_base + px.pix(r, c);
-                grad_density[m] = gscale * fmaf(acc[r][c], rz_in[m], w_bg * pbg_in[m]);
-            }
-        return false;
+                for (int c = 0; c < C; ++c) {
+                    if (!px.ok(r, c)) continue;
+                    const int p = px.pix(r, c);
+                    gout[p] = gscale * fmaf(acc[r][c], rz_in[img_base + p], w_bg * pbg_in[img_base + p]);
+                }
+        }
+        return dst != 0u;
     } else {
         // sharded: chunks of an image finished by another rank go straight (and only) into that rank's workspace
         const unsigned int dst = x.peers ? x.mask[t.chunk] : 0u;
@@ -1267,9 +1406,10 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
                Scale k, int use_bg, int exact_cull, float inv_batch, const float* __restrict__ grad_loss,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
-               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, Xchg x) {
+               float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, Xchg x,
+               unsigned int* __restrict__ tile_tick) {
     const bool stored = bl_grad_body<R, C, POW2>(pts_all, meta, batch, g, k, use_bg, exact_cull, inv_batch, grad_loss, amax_in,
-                                                 rz_in, pbg_in, wsel, gpart, grad_density, always_partial, x);
+                                                 rz_in, pbg_in, wsel, gpart, grad_density, always_partial, x, tile_tick);
     xchg_signal(x, stored);
 }
 
@@ -1277,34 +1417,39 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
 __device__ __forceinline__ bool bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
                       const float* __restrict__ grad_loss, const float* __restrict__ gpart,
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
-                      const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x);
+                      const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x,
+                      int pix_first, int pix_end, int every_image);
 
 __global__ void __launch_bounds__(256)
 bl_grad_reduce_kernel(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
                       const float* __restrict__ grad_loss, const float* __restrict__ gpart,
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
-                      const float* __restrict__ wsel, float* __restrict__ grad_density, Shard sh, Xchg x, int n_img) {
+                      const float* __restrict__ wsel, float* __restrict__ grad_density, Shard sh, Xchg x, int n_img,
+                      int pix_first, int pix_end, int every_image) {
     xchg_wait(x);  // sharded: the gradient sums of the chunks other ranks swept
     bool stored = false;
     if ((int)blockIdx.y < n_img)
-        stored = bl_grad_reduce_body(meta, batch, M, use_bg, inv_batch, grad_loss, gpart, rz_in, pbg_in, wsel, grad_density, sh, x);
+        stored = bl_grad_reduce_body(meta, batch, M, use_bg, inv_batch, grad_loss, gpart, rz_in, pbg_in, wsel, grad_density, sh, x,
+                                     pix_first, pix_end, every_image);
     xchg_signal(x, stored);
 }
 
 __device__ __forceinline__ bool bl_grad_reduce_body(const int32_t* __restrict__ meta, int batch, int M, int use_bg, float inv_batch,
                       const float* __restrict__ grad_loss, const float* __restrict__ gpart,
                       const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
-                      const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x) {
+                      const float* __restrict__ wsel, float* __restrict__ grad_density, const Shard& sh, const Xchg& x,
+                      int pix_first, int pix_end, int every_image) {
+    // pixels [pix_first, pix_end) of the image: all of them, or (row-band sharding) the rank's band of grid rows
     const int img = sh.img_lo + blockIdx.y;
     const Meta mv = meta_view(meta, batch);
     const int first = mv.icb[img], n_chunks = mv.icb[img + 1] - first;
     if (sh.on) {  // every image is finished by the rank that owns its first chunk, single-chunk images included
         if (first < sh.chunk_lo || first >= sh.chunk_hi) return false;
-    } else if (n_chunks <= 1) {
+    } else if (n_chunks <= 1 && !every_image) {
         return false;
     }
-    const int pix = blockIdx.x * 256 + threadIdx.x;
-    if (pix >= M) return false;
+    const int pix = pix_first + blockIdx.x * 256 + threadIdx.x;
+    if (pix >= pix_end) return false;
     float acc = 0.f;
     for (int c = 0; c < n_chunks; ++c) acc += gpart[(size_t)(first + c) * M + pix];
     const int n_rows = mv.row_off[img + 1] - mv.row_off[img];
@@ -1523,6 +1668,48 @@ __global__ void bl_loss_finish_kernel(const float* __restrict__ loss_img, int ba
     }
 }
 
+// ------------------------------------------------------------------- row-band sharding across GPUs
+// One batch spread over the GPUs of a box by PIXELS (dgvcc_bl_band_*): rank r sweeps ALL points of every image over
+// its own band of grid rows.  The softmax of bl.py:44 runs over the points of ONE pixel, so minima, denominators,
+// posteriors and the density gradient of a pixel never leave the rank that owns it; only the expected counts of
+// bl.py:73 are sums over pixels.  bl_counts_kernel stores the per-CTA partial counts of the band on every rank as it
+// produces them; every rank then adds all partial rows in pixel-tile order (the same bits everywhere, and the same sum
+// as on one GPU) and finds the top-k cut and the loss for itself.  One data-dependent exchange per step (CNT) against
+// four for the point-chunk split; DENS (owner -> band ranks) hides on a side stream, GRAD (band -> owner, stored by
+// bl_grad_kernel itself) ends the step.
+
+// Partial-count rows per rank in the count-share table (the bands follow from the grid shape and the world size).
+struct BandRows { int n[32]; };
+
+// Expected counts = all partial rows added in (rank, CTA) order, i.e. in the order of the pixel tiles -- with bands cut
+// at CTA boundaries exactly the sum bl_reduce_counts_kernel forms on one GPU; residual |t - c| (bl.py:73-75).  Every rank
+// runs this over all rows of the batch and gets the same bits.
+__global__ void __launch_bounds__(256)
+bl_band_combine_kernel(const float* __restrict__ cshare, int world, int share_rows, BandRows rows, int64_t total_rows,
+                       const int32_t* __restrict__ meta, const float* __restrict__ targets, int batch,
+                       float* __restrict__ counts, float* __restrict__ residual, Xchg x) {
+    xchg_wait(x);  // the partial rows of the other ranks
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= total_rows) return;
+    float c = 0.f;
+    for (int q = 0; q < world; ++q) {
+        const float* p = cshare + (size_t)q * share_rows * total_rows + j;
+#pragma unroll 4
+        for (int tl = 0; tl < rows.n[q]; ++tl) c += __ldcg(p + (size_t)tl * total_rows);
+    }
+    const Meta mv = meta_view(meta, batch);
+    int lo = 0, hi = batch;  // image of row j
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (mv.row_off[mid] <= j) lo = mid; else hi = mid;
+    }
+    const int local = (int)(j - mv.row_off[lo]);
+    const int n_pts = mv.pt_off[lo + 1] - mv.pt_off[lo];
+    const float tgt = (local < n_pts) ? targets[mv.pt_off[lo] + local] : 0.f;
+    counts[j] = c;
+    residual[j] = fabsf(__fadd_rn(tgt, -c));
+}
+
 // ------------------------------------------------------------------------------- host side
 static bool is_pow2(float s) {
     int e;
@@ -1547,6 +1734,10 @@ static long variant_tasks(const Variant& v, int total_chunks, int hp, int wp) {
     return (long)total_chunks * ceil_div(wp, 32 * v.cols) * ceil_div(hp, v.rows);
 }
 
+// Tuning knobs of benchmarks and experiments (dgvcc_bl_set_option): host-side, read when a plan is made.
+static int g_opt_min_cell = 64;   // smallest cell of the point grid of the minima, image pixels (a power of two)
+static int g_opt_band_tile = 0;   // pixel tile of the symmetric (sharded) layouts: 0 = by task count, else rows*10 + cols
+
 static Variant pick_variant(int total_chunks, int hp, int wp) {
     const long want = 148L * 16;
     for (const Variant& v : kVariants)
@@ -1559,6 +1750,8 @@ static Geom make_geom(int hp, int wp, const Variant& v, float stride) {
     g.hp = hp; g.wp = wp;
     g.col_blocks = ceil_div(wp, 32 * v.cols);
     g.tiles = g.col_blocks * ceil_div(hp, v.rows);
+    g.task_first = 0;
+    g.tiles_img = g.tiles;
     g.stride = stride;
     g.half = stride / 2.0f;
     return g;
@@ -1569,7 +1762,8 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
         return DGVCC_ERR_ARG;
     // world > 0: the symmetric layout of dgvcc_bl_shard_* (identical on every rank); the pixel tile is chosen for the
     // chunks ONE rank sweeps
-    const Variant v = pick_variant(world > 0 ? ceil_div(total_chunks, world) : total_chunks, hp, wp);
+    Variant v = pick_variant(world > 0 ? ceil_div(total_chunks, world) : total_chunks, hp, wp);
+    if (world > 0 && g_opt_band_tile) v = Variant{g_opt_band_tile / 10, g_opt_band_tile % 10};
     const int tiles = make_geom(hp, wp, v, 1.f).tiles;
     const size_t M = (size_t)hp * wp;
     const size_t pix = (size_t)batch * M * sizeof(float);
@@ -1577,7 +1771,8 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     const size_t chunk_pix = (size_t)total_chunks * M * sizeof(float);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (int64_t)o; };
-    L->dens = L->gfinal = L->flags = L->err = L->push_ticket = 0;
+    L->dens = L->gfinal = L->flags = L->err = L->push_ticket = L->cshare = 0;
+    L->share_rows = 0;
     if (world > 0) {  // fixed offsets, whatever the batch: the flags outlive a step (they are compared with the epoch)
         L->flags = take((size_t)DGVCC_BL_PHASES * 32 * sizeof(unsigned int));
         L->err = take(sizeof(int));
@@ -1594,9 +1789,15 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     L->minpart = L->gpart;       // (no per-chunk minima any more: bl_gridmin_kernel writes per-image minima into the pbg region)
     L->goff = take((size_t)batch * (GRID_MAX_CELLS + 1) * sizeof(int32_t));   // grid cell offsets per image
     L->gsorted = take((size_t)total_rows * sizeof(float2));                   // points sorted by grid cell (<= rows)
+    L->ztick = take((size_t)batch * tiles * sizeof(unsigned int));            // arrival counters per (image, pixel tile): bl_z
+    L->gtick = take((size_t)batch * tiles * sizeof(unsigned int));            //                                          bl_grad
     if (world > 0) {
         L->dens = take(pix);         // density of every image this rank sweeps, delivered by the image's owner
         L->gfinal = take(pix);       // finished gradients, delivered to the image's owner
+        // row-band sharding: the per-CTA partial counts of every rank's band (bl_counts_kernel stores them on every rank)
+        const int band_tile_rows = ceil_div(ceil_div(hp, v.rows), world);
+        L->share_rows = ceil_div(band_tile_rows * make_geom(hp, wp, v, 1.f).col_blocks, WARPS_PER_CTA);
+        L->cshare = take((size_t)world * L->share_rows * rows);
     }
     L->total = (int64_t)off;
     L->tiles = count_rows;
@@ -1614,7 +1815,7 @@ static T* at(const void* ws, int64_t off) { return reinterpret_cast<T*>((char*)w
 using namespace dgvcc;
 using namespace dgvcc::bl;
 
-extern "C" int dgvcc_abi_version(void) { return 8; }
+extern "C" int dgvcc_abi_version(void) { return 9; }
 
 extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                                          dgvcc_bl_layout* out) {
@@ -1634,6 +1835,21 @@ extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, i
         else if ((V_).rows == 4) BL_LAUNCH_RC(4, 1, POW2_, KERNEL, GRID, STREAM, __VA_ARGS__);         \
         else BL_LAUNCH_RC(2, 1, POW2_, KERNEL, GRID, STREAM, __VA_ARGS__);                             \
     } while (0)
+
+extern "C" int dgvcc_bl_set_option(int option, int value) {
+    switch (option) {
+        case DGVCC_BL_OPT_MIN_CELL:
+            if (value < 8 || value > 4096 || (value & (value - 1))) return DGVCC_ERR_ARG;
+            g_opt_min_cell = value;
+            return DGVCC_OK;
+        case DGVCC_BL_OPT_BAND_TILE:
+            if (value != 0 && value != 82 && value != 81 && value != 41 && value != 21) return DGVCC_ERR_ARG;
+            g_opt_band_tile = value;
+            return DGVCC_OK;
+        default:
+            return DGVCC_ERR_ARG;
+    }
+}
 
 namespace {
 
@@ -1680,7 +1896,7 @@ inline void mark(void** events, int i, cudaStream_t st) {
 GridGeom make_grid(int hp, int wp, float stride) {
     const float ex = wp * stride, ey = hp * stride;
     GridGeom gg;
-    gg.cell = 64.f;
+    gg.cell = (float)g_opt_min_cell;
     for (;;) {
         gg.gx = (int)ceilf(ex / gg.cell);
         gg.gy = (int)ceilf(ey / gg.cell);
@@ -1697,20 +1913,24 @@ GridGeom make_grid(int hp, int wp, float stride) {
 
 // per-pixel minima of the images [img_first, img_first + n_img): grid build + ring walk, into min_img [B, hp*wp]
 int launch_gridmin(const Plan& p, const float2* pts, const int32_t* meta, int batch, int hp, int wp, int img_first, int n_img,
-                   void* ws, float* min_img, cudaStream_t st) {
-    if (n_img <= 0) return DGVCC_OK;
+                   void* ws, float* min_img, cudaStream_t st, int row_lo = 0, int row_hi = -1) {
+    if (row_hi < 0) row_hi = hp;   // grid rows [row_lo, row_hi) of every image (row_lo even): the whole grid, or a rank's band
+    if (n_img <= 0 || row_hi <= row_lo) return DGVCC_OK;
     const GridGeom gg = make_grid(hp, wp, p.g.stride);
     int32_t* goff = at<int32_t>(ws, p.L.goff);
     float2* gsorted = at<float2>(ws, p.L.gsorted);
-    bl_grid_build_kernel<<<n_img, 1024, 0, st>>>(pts, meta, batch, gg, img_first, goff, gsorted);
+    bl_grid_build_kernel<<<n_img, 1024, 0, st>>>(pts, meta, batch, gg, img_first, goff, gsorted, at<unsigned int>(ws, p.L.ztick),
+                                                 at<unsigned int>(ws, p.L.gtick), p.g.tiles_img);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     // The minima have their own, small pixel tile (2 rows x 32 columns), independent of the exponential sweeps': every point
     // inside a tile's own rectangle is swept over the whole tile whatever the bound, so a crowd of 1500 heads inside one
     // 8 x 64 tile is a 50k-instruction warp -- the critical path of the launch.  Measured on the config-3 batch (grid
     // build included): 8x2 123 us, 8x1 85, 4x1 75, 2x1 70.
     const Variant v{2, 1};
-    const Geom gm = make_geom(hp, wp, v, p.g.stride);
-    const dim3 grid(ceil_div(gm.tiles, WARPS_PER_CTA), n_img);
+    Geom gm = make_geom(hp, wp, v, p.g.stride);
+    gm.task_first = (row_lo / v.rows) * gm.col_blocks;
+    gm.tiles = ceil_div(row_hi, v.rows) * gm.col_blocks;
+    const dim3 grid(ceil_div(gm.tiles - gm.task_first, WARPS_PER_CTA), n_img);
     bl_gridmin_kernel<2, 1><<<grid, CTA_THREADS, 0, st>>>(gsorted, goff, meta, batch, gm, gg, img_first, min_img);
     return (int)cudaGetLastError();
 }
@@ -1719,7 +1939,7 @@ int launch_gridmin(const Plan& p, const float2* pts, const int32_t* meta, int ba
 int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const float* st_sizes, int batch,
              int multi_chunk, float bg_ratio, int use_bg, int exact_cull, void* ws, cudaStream_t st,
              void** events = nullptr) {
-    float* min_img = at<float>(ws, p.L.pbg);   // the region is free until the posteriors of the background row are written
+    float* min_img = at<float>(ws, p.L.gpart);   // free until the backward pass (bl_z_kernel's last arrivals write rz / pbg)
     const float2* pts = (const float2*)pts_xy;
     (void)multi_chunk;
     mark(events, 0, st);
@@ -1728,7 +1948,8 @@ int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const floa
     mark(events, 1, st);
     BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
                 exact_cull, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg),
-                at<unsigned int>(ws, p.L.ticket), p.sh, (const float*)min_img, Xchg{});
+                at<unsigned int>(ws, p.L.ticket), p.sh, (const float*)min_img, Xchg{}, at<float>(ws, p.L.rz),
+                at<float>(ws, p.L.pbg), at<unsigned int>(ws, p.L.ztick), 1);
     mark(events, 2, st);
     return (int)cudaGetLastError();
 }
@@ -1768,9 +1989,8 @@ extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targe
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, exact_cull, workspace, st, events))) return rc;
     BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
-                use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg), at<float>(workspace, p.L.zpart),
-                at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
-                at<float>(workspace, p.L.cpart), p.sh, 0);
+                use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg),
+                total_rows, at<float>(workspace, p.L.cpart), -1, Xchg{});
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 3, st);
     rc = launch_select(p.L, targets, meta, batch, total_rows, inv_batch, p.L.tiles, workspace, loss_out, st);
@@ -1803,17 +2023,9 @@ extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int b
     BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
                 exact_cull, inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                 at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                grad_density, 0, Xchg{});
-    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    if (multi_chunk) {
-        const int M = hp * wp;
-        bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), batch), 256, 0, st>>>(
-            meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart),
-            at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), grad_density,
-            no_shard(), Xchg{}, batch);
-        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
-    }
-    return DGVCC_OK;
+                grad_density, 0, Xchg{}, at<unsigned int>(workspace, p.L.gtick));
+    (void)multi_chunk;  // multi-chunk images are finished inside bl_grad_kernel (last arrival per pixel tile)
+    return (int)cudaGetLastError();
 }
 
 // ------------------------------------------------------------------- point-chunk sharding: launch sequences
@@ -1937,6 +2149,7 @@ extern "C" int dgvcc_bl_shard_preload(void) {
     BL_PRELOAD(bl_grid_build_kernel);
     BL_PRELOAD((bl_gridmin_kernel<2, 1>));
     BL_PRELOAD(bl_finish_z_kernel);
+    BL_PRELOAD(bl_band_combine_kernel);
 #undef BL_PRELOAD_RC
 #undef BL_PRELOAD
     return DGVCC_OK;
@@ -1993,7 +2206,8 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
         if (sweeps) {
             BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
                         at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
-                        at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img, x);
+                        at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img, x,
+                        at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<unsigned int>(workspace, p.L.ztick), 0);
         } else {
             bl_signal_kernel<<<1, 32, 0, st>>>(x);
         }
@@ -2010,9 +2224,8 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
     mark(events, 4, st);
     if (sweeps) {
         BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
-                    use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
-                    at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), total_rows,
-                    at<float>(workspace, p.L.cpart), p.sh, 1);
+                    use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
+                    at<float>(workspace, p.L.pbg), total_rows, at<float>(workspace, p.L.cpart), -1, Xchg{});
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     mark(events, 5, st);
@@ -2067,7 +2280,7 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
             BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
                         inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                         at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                        at<float>(workspace, p.L.gfinal), 1, x);
+                        at<float>(workspace, p.L.gfinal), 1, x, at<unsigned int>(workspace, p.L.gtick));
         } else {
             bl_signal_kernel<<<1, 32, 0, st>>>(x);
         }
@@ -2079,7 +2292,7 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
     bl_grad_reduce_kernel<<<dim3(ceil_div(M, 256), n_img > 0 ? n_img : 1), 256, 0, st>>>(
         meta, batch, M, use_bg, inv_batch, grad_loss, at<float>(workspace, p.L.gpart), at<float>(workspace, p.L.rz),
         at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gfinal), p.sh,
-        c.make(DGVCC_BL_PH_GRAD, c.owner_mask(), p.L.gfinal, 0, DGVCC_BL_PH_GPART, -1), n_img);
+        c.make(DGVCC_BL_PH_GRAD, c.owner_mask(), p.L.gfinal, 0, DGVCC_BL_PH_GPART, -1), n_img, 0, M, 0);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 2, st);
     if ((rc = shard_wait(c, DGVCC_BL_PH_GRAD))) return rc;
@@ -2094,6 +2307,157 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
         rc = (int)cudaGetLastError();
     }
     mark(events, 4, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------- row-band sharding: launch sequences
+namespace {
+
+// Plan of a rank that sweeps the grid rows [band_lo, band_hi) of every image over all chunks.
+int make_band_plan(const void* a, const void* ws, size_t ws_bytes, int batch, int hp, int wp, int64_t total_rows,
+                   int total_chunks, float stride, float sigma, const dgvcc_bl_shard* sh, Plan* p) {
+    if (!a || !ws || !sh) return DGVCC_ERR_ARG;
+    if (!(stride > 0.f) || !(sigma > 0.f)) return DGVCC_ERR_ARG;
+    if (sh->world < 1 || sh->world > 32 || sh->rank < 0 || sh->rank >= sh->world) return DGVCC_ERR_ARG;
+    int rc = layout(total_rows, total_chunks, batch, hp, wp, &p->L, sh->world);
+    if (rc) return rc;
+    if (ws_bytes < (size_t)p->L.total) return DGVCC_ERR_WORKSPACE;
+    p->v = Variant{p->L.rows_per_thread, p->L.cols_per_thread};
+    const int R = p->v.rows;
+    if (sh->band_lo < 0 || sh->band_hi < sh->band_lo || sh->band_hi > hp || sh->band_lo % R != 0 ||
+        (sh->band_hi % R != 0 && sh->band_hi != hp))
+        return DGVCC_ERR_ARG;   // bands are whole rows of pixel tiles
+    {   // the bands follow from (hp, R, world) alone -- every rank must be able to derive every other rank's
+        const int n_tr = ceil_div(hp, R);
+        const int lo = (int)((long long)n_tr * sh->rank / sh->world), hi = (int)((long long)n_tr * (sh->rank + 1) / sh->world);
+        if (sh->band_lo != (lo * R < hp ? lo * R : hp) || sh->band_hi != (hi * R < hp ? hi * R : hp)) return DGVCC_ERR_ARG;
+    }
+    p->g = make_geom(hp, wp, p->v, stride);
+    p->g.task_first = (sh->band_lo / R) * p->g.col_blocks;
+    p->g.tiles = ceil_div(sh->band_hi, R) * p->g.col_blocks;
+    p->k = make_scale(sigma);
+    p->pow2 = is_pow2(p->k.s);
+    p->sh = no_shard();
+    p->grid = dim3(ceil_div(p->g.tiles - p->g.task_first, WARPS_PER_CTA), total_chunks);
+    return DGVCC_OK;
+}
+
+}  // namespace
+
+extern "C" int dgvcc_bl_band_forward(const float* pts_xy, const float* targets, const int32_t* meta, const float* st_sizes,
+                                     const float* density_local, int batch, int hp, int wp, int64_t total_rows,
+                                     int total_chunks, float stride, float sigma, float bg_ratio, int use_bg, int exact_cull,
+                                     float inv_batch, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices,
+                                     const uint32_t* owner_mask, void* const* peers, void* workspace, size_t workspace_bytes,
+                                     float* loss_out, void* stream, void** events) {
+    DGVCC_DEVICE_GUARD(stream);
+    if (!shard_args_ok(shard, slices, owner_mask, peers)) return DGVCC_ERR_ARG;
+    Plan p;
+    int rc = make_band_plan(meta, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride, sigma, shard, &p);
+    if (rc) return rc;
+    if (!loss_out || !pts_xy || !targets || !st_sizes) return DGVCC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ShardCtx c{shard, slices, owner_mask, (char* const*)peers, workspace, &p.L, st, total_chunks, batch};
+    const float2* pts = (const float2*)pts_xy;
+    const bool sweeps = p.grid.x > 0 && p.grid.y > 0;
+    mark(events, 0, st);
+    // density rows of the images this rank owns -> the ranks whose bands they fall into (needed from bl_counts on)
+    SideStream* side = shard->push_first[DGVCC_BL_PH_DENS + 1] > shard->push_first[DGVCC_BL_PH_DENS] ? side_stream() : nullptr;
+    if (side) {
+        DGVCC_RETURN_IF_CUDA(cudaEventRecord(side->fork, st));
+        DGVCC_RETURN_IF_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        ShardCtx cs = c;
+        cs.st = side->stream;
+        if ((rc = shard_push(cs, DGVCC_BL_PH_DENS, density_local))) return rc;
+        DGVCC_RETURN_IF_CUDA(cudaEventRecord(side->join, side->stream));
+    }
+    mark(events, 1, st);
+    float* min_img = at<float>(workspace, p.L.gpart);  // free until the backward pass
+    if (sweeps) {
+        if ((rc = launch_gridmin(p, pts, meta, batch, hp, wp, 0, batch, workspace, min_img, st, shard->band_lo, shard->band_hi)))
+            return rc;
+        mark(events, 2, st);
+        BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
+                    at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
+                    at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img, Xchg{}, at<float>(workspace, p.L.rz),
+                    at<float>(workspace, p.L.pbg), at<unsigned int>(workspace, p.L.ztick), 1);
+        DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    } else {
+        mark(events, 2, st);
+    }
+    mark(events, 3, st);
+    if (side) DGVCC_RETURN_IF_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    if ((rc = shard_wait(c, DGVCC_BL_PH_DENS))) return rc;
+    // expected counts: every CTA stores its partial row into the count-share table of EVERY rank as it is produced
+    // (rows [rank * share_rows, ...)); the kernel's last CTA raises CNT
+    const Xchg cnt = c.make(DGVCC_BL_PH_CNT, nullptr, p.L.cshare, 0, DGVCC_BL_PH_DENS, -1);
+    if ((int)p.grid.x > p.L.share_rows) return DGVCC_ERR_ARG;
+    if (sweeps) {
+        BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
+                    use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
+                    at<float>(workspace, p.L.pbg), total_rows, (float*)nullptr, shard->rank * p.L.share_rows, cnt);
+    } else {
+        bl_signal_kernel<<<1, 32, 0, st>>>(cnt);
+    }
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    mark(events, 4, st);
+    if ((rc = shard_wait(c, DGVCC_BL_PH_CNT))) return rc;
+    // every rank adds all partial rows in (rank, CTA) order -- the order of the pixel tiles, as on one GPU
+    BandRows br;
+    const int R = p.v.rows;
+    for (int q = 0; q < 32; ++q) br.n[q] = 0;
+    for (int q = 0; q < shard->world; ++q) {  // the bands of all ranks follow from (hp, R, world) alone
+        const int n_tr = ceil_div(hp, R);
+        const int lo = (int)((long long)n_tr * q / shard->world), hi = (int)((long long)n_tr * (q + 1) / shard->world);
+        br.n[q] = ceil_div((hi - lo) * p.g.col_blocks, WARPS_PER_CTA);
+    }
+    const unsigned row_blocks = (unsigned)((total_rows + 255) / 256);
+    bl_band_combine_kernel<<<row_blocks, 256, 0, st>>>(at<float>(workspace, p.L.cshare), shard->world, p.L.share_rows, br,
+                                                       total_rows, meta, targets, batch, at<float>(workspace, p.L.counts),
+                                                       at<float>(workspace, p.L.residual),
+                                                       c.make(-1, nullptr, 0, 0, DGVCC_BL_PH_CNT, -1));
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    mark(events, 5, st);
+    // top-k cut and loss of every image, on every rank (the same bits everywhere): no exchange
+    bl_select_kernel<<<batch, SELECT_THREADS, 0, st>>>(
+        meta, targets, batch, inv_batch, at<float>(workspace, p.L.counts), at<float>(workspace, p.L.residual),
+        at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.loss_img), loss_out, at<unsigned int>(workspace, p.L.ticket),
+        0, 1, no_shard(), Xchg{}, batch);
+    mark(events, 6, st);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int dgvcc_bl_band_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp, int64_t total_rows,
+                                      int total_chunks, float stride, float sigma, int use_bg, int exact_cull, float inv_batch,
+                                      const float* grad_loss, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices,
+                                      const uint32_t* owner_mask, void* const* peers, void* workspace, size_t workspace_bytes,
+                                      float* grad_local, void* stream, void** events) {
+    DGVCC_DEVICE_GUARD(stream);
+    if (!shard_args_ok(shard, slices, owner_mask, peers)) return DGVCC_ERR_ARG;
+    Plan p;
+    int rc = make_band_plan(meta, workspace, workspace_bytes, batch, hp, wp, total_rows, total_chunks, stride, sigma, shard, &p);
+    if (rc) return rc;
+    if (!pts_xy || !grad_loss) return DGVCC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ShardCtx c{shard, slices, owner_mask, (char* const*)peers, workspace, &p.L, st, total_chunks, batch};
+    const bool sweeps = p.grid.x > 0 && p.grid.y > 0;
+    mark(events, 0, st);
+    // gradient of the band's pixels, finished inside the sweep (last arrival per pixel tile) and written at the image's owner
+    const Xchg out = c.make(DGVCC_BL_PH_GRAD, owner_mask, p.L.gfinal, 0, -1, -1);
+    if (sweeps) {
+        BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
+                    inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
+                    at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
+                    at<float>(workspace, p.L.gfinal), 0, out, at<unsigned int>(workspace, p.L.gtick));
+    } else {
+        bl_signal_kernel<<<1, 32, 0, st>>>(out);
+    }
+    DGVCC_RETURN_IF_CUDA(cudaGetLastError());
+    mark(events, 1, st);
+    if ((rc = shard_wait(c, DGVCC_BL_PH_GRAD))) return rc;
+    if (shard->push_first[DGVCC_BL_PH_OUT + 1] > shard->push_first[DGVCC_BL_PH_OUT] && !grad_local) return DGVCC_ERR_ARG;
+    rc = shard_push(c, DGVCC_BL_PH_OUT, workspace, grad_local ? (void*)grad_local : workspace, DGVCC_BL_PH_GRAD);
+    mark(events, 2, st);
     return rc;
 }
 

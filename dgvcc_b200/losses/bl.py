@@ -41,7 +41,7 @@ def _as_point_list(points):
     return out
 
 
-_CHUNK_POINTS = int(os.environ.get("DGVCC_BL_CHUNK", "1024"))  # read once, at import
+_CHUNK_POINTS = int(os.environ.get("DGVCC_BL_CHUNK", "512"))  # read once, at import (512: measured, scripts/bl_tune_1gpu.py)
 
 
 def chunk_points():

@@ -95,14 +95,26 @@ typedef struct dgvcc_bl_layout {
     int64_t push_ticket; /* [2] u32                                                  */
     int64_t goff;      /* [B*(1024+1)] i32 grid-cell offsets of the points of each image (bl_grid_build_kernel) */
     int64_t gsorted;   /* [rows*2] f32   points sorted by grid cell                   */
+    int64_t cshare;    /* [world*share_rows*rows] f32 symmetric layout: the per-CTA partial counts of every rank's band (dgvcc_bl_band_*) */
+    int64_t ztick;     /* [B*tiles_img] u32 arrival counters per (image, pixel tile) of bl_z_kernel (zeroed by the forward pass) */
+    int64_t gtick;     /* [B*tiles_img] u32 the same for bl_grad_kernel                */
     int32_t tiles;     /* partial-count rows (CTAs of 4 pixel tiles) per point chunk */
     int32_t rows_per_thread; /* kernel variant chosen for this shape: grid rows ...   */
     int32_t cols_per_thread; /* ... and columns owned by one thread                  */
-    int32_t reserved_;
+    int32_t share_rows; /* symmetric layout: partial-count rows reserved per rank in cshare */
 } dgvcc_bl_layout;
 
 int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                               dgvcc_bl_layout* out);
+
+/* Process-wide tuning knobs for benchmarks and experiments (host side, read when a launch is planned; results do not
+ * depend on them beyond the summation order of the expected counts, which follows the pixel tile):
+ *   MIN_CELL   smallest cell of the uniform point grid behind the per-pixel minima of bl.py:39, in image pixels
+ *              (a power of two, default 64; the cell doubles until the grid has at most 4096 cells)
+ *   BAND_TILE  pixel tile per thread of the symmetric (multi-GPU) layouts: 0 = chosen from the task count (default),
+ *              82 / 81 / 41 / 21 = rows * 10 + columns.  Must be the same on every rank. */
+enum { DGVCC_BL_OPT_MIN_CELL = 0, DGVCC_BL_OPT_BAND_TILE = 1 };
+int dgvcc_bl_set_option(int option, int value);
 
 /* Fused forward: per-pixel min / softmax denominator, expected counts, trimmed
  * top-k selection and the loss.  Never materialises the points x pixels matrix.
@@ -205,6 +217,7 @@ typedef struct dgvcc_bl_shard {
     uint32_t epoch;
     int32_t fuse_waits;           /* 1: consumers spin on the flags in their own prologue (one process per GPU);
                                      0: separate one-warp wait kernels (several ranks sharing one GPU / context)   */
+    int32_t band_lo, band_hi;     /* dgvcc_bl_band_* only: grid rows [band_lo, band_hi) of EVERY image this rank sweeps */
 } dgvcc_bl_shard;
 int dgvcc_bl_shard_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp, int world,
                                     dgvcc_bl_layout* out);
@@ -230,6 +243,43 @@ int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta, int batch,
  * launches, for per-kernel timing.  forward (9): start, after the DENS copy is issued, grid build + minima, bl_z,
  * [wait Z, DENS] finish_z, bl_counts, the row reduction, [wait CNT] selection, [wait LOSS] loss.
  * backward (5): start, bl_grad, [wait GPART] reduction, [wait GRAD] gather, [wait LOSS] deferred loss. */
+
+/* ---------------------------------------------------------------------------
+ * Bayesian loss, ONE batch spread over the GPUs of a box by ROW BANDS of the density grid (the strong-scaling path
+ * bench.py reports first).  The softmax of bl.py:44 normalises over the points of ONE pixel, so everything per pixel
+ * -- the minima of bl.py:39, the denominators, the posteriors, the density gradient -- stays on the rank that owns
+ * the pixel; only the expected counts of bl.py:73 sum over pixels.  Rank r sweeps ALL points of every image over the
+ * grid rows [band_lo, band_hi) (whole rows of pixel tiles: multiples of dgvcc_bl_layout.rows_per_thread, the last
+ * band ends at hp) and the exchange is:
+ *   DENS  density rows of an image, owner -> the rank of each band           (side stream, before the counts)
+ *   CNT   the per-CTA partial counts of the band (one f32 per posterior row and CTA of pixel tiles), stored by
+ *         bl_counts_kernel itself on every rank; all ranks add ALL partial rows in pixel-tile order, so the counts,
+ *         the top-k cut (bl.py:76-78) and the loss have the same bits everywhere and no LOSS exchange is needed
+ *   GRAD  finished gradient rows, stored by bl_grad_kernel at the image's owner;  OUT: local gather into the caller's tensor
+ * One data-dependent exchange in the middle of the step instead of the four of the point-chunk split, and every
+ * rank's sweeps are 1/world of the single-GPU sweeps tile for tile.  Results: per-pixel quantities are bit-identical
+ * to dgvcc_bl_forward with the same chunk table; so are the counts and the loss whenever the bands are cut at CTA
+ * boundaries of the single-GPU sweep (always when 4 divides the column blocks of a tile row, e.g. config 3), else they
+ * differ by the order of the partial sums -- identical across ranks and runs, ~1e-7 relative.
+ * Arguments as for dgvcc_bl_shard_*: the SAME packed points / targets / table on every rank (every chunk scheduled:
+ * the table of dgvcc_bl_pack_host), `shard` with rank / world / band_lo / band_hi / push_first / masks / epoch /
+ * fuse_waits (the chunk / point / image / row ranges are ignored), `slices` for DENS and OUT, `owner_mask` (DEVICE,
+ * uint32 [batch]): bit of the rank that owns image i, 0 when this rank does.  Workspaces: dgvcc_bl_shard_workspace_layout.
+ * events (NULL or cudaEvent_t handles): forward (7) start, DENS issued, grid build + minima, bl_z, [wait DENS]
+ * bl_counts (+CNT out), [wait CNT] combine, selection + loss; backward (3) start, bl_grad (+GRAD out), [wait GRAD] gather.
+ * The bands are fixed by (hp, rows_per_thread, world): tile rows [n*r/world, n*(r+1)/world) of n = ceil(hp / rows_per_thread).
+ * ------------------------------------------------------------------------- */
+int dgvcc_bl_band_forward(const float* pts_xy, const float* targets, const int32_t* meta, const float* st_sizes,
+                          const float* density_local, int batch, int hp, int wp, int64_t total_rows, int total_chunks,
+                          float stride, float sigma, float bg_ratio, int use_bg, int exact_cull, float inv_batch,
+                          const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices, const uint32_t* owner_mask,
+                          void* const* peers, void* workspace, size_t workspace_bytes, float* loss_out, void* stream,
+                          void** events);
+int dgvcc_bl_band_backward(const float* pts_xy, const int32_t* meta, int batch, int hp, int wp, int64_t total_rows,
+                           int total_chunks, float stride, float sigma, int use_bg, int exact_cull, float inv_batch,
+                           const float* grad_loss, const dgvcc_bl_shard* shard, const dgvcc_bl_push* slices,
+                           const uint32_t* owner_mask, void* const* peers, void* workspace, size_t workspace_bytes,
+                           float* grad_local, void* stream, void** events);
 
 /* Peer-visible device memory for the sharded workspaces (CUDA IPC between the ranks' processes of one box):
  * alloc = cudaMalloc + zero fill; export writes the 64-byte handle a peer process passes to open, which maps the

@@ -9,6 +9,12 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The sharded Bayesian loss is also tested with up to 8 "ranks" inside ONE process (LocalComm: one stream per rank plus
+# the library's side stream).  A rank's wait kernel spins until a peer's kernel has run; with the default 8 hardware
+# queues two of those streams can share a queue, and the spinning kernel then blocks the very kernel it waits for.
+# One queue per stream (must be set before the CUDA context exists; real runs have one rank per process).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

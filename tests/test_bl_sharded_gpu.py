@@ -121,6 +121,91 @@ def test_config3_batch_on_four_emulated_ranks():
     assert_close(grad, d.grad.cpu(), 1e-5, 1e-6 * float(d.grad.abs().max()), "sharded vs BL gradient")
 
 
+# ------------------------------------------------------------------------------------------------ row-band sharding
+def run_banded(world, points, targets, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners=None, steps=1, chunk=None):
+    """`world` ranks of BandShardedBL inside this process (LocalComm), one stream each."""
+    from dgvcc_b200.losses.bl_banded import BandShardedBL, LocalComm, plan_bands
+    dev = torch.device("cuda:0")
+    b, _, hp, wp = dens.shape
+    comms = LocalComm.make(world, dev, nbytes=192 << 20)
+    plan = plan_bands([len(p) for p in points], use_bg, world, owners, hp, wp, chunk)
+    mods = [BandShardedBL(sigma, max(hp, wp) * stride, stride, bg_ratio, use_bg, dev, c) for c in comms]
+    for m in mods:
+        m.exact_cull, m.chunk = cull, chunk
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    warm = torch.zeros((2, 1, hp, wp), device=dev, requires_grad=True)
+    (warm * 2.0).sum().backward()
+    warm.grad.clone().to(torch.float32).contiguous()
+    st_d = st.to(dev)
+    locals_ = [dens[plan.owned[r]].to(dev).clone().requires_grad_(True) for r in range(world)]
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        losses = []
+        for r in range(world):
+            locals_[r].grad = None
+            with torch.cuda.stream(streams[r]):
+                losses.append(mods[r](points, st_d, targets, locals_[r], owners))
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                losses[r].backward()
+        for m in mods:
+            m.check()
+    grad = torch.zeros_like(dens)
+    for r in range(world):
+        if len(plan.owned[r]):
+            grad[plan.owned[r]] = locals_[r].grad.cpu()
+    return [l.detach().cpu() for l in losses], grad, plan
+
+
+def _band_table_on_one_gpu(plan, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull):
+    shim = types.SimpleNamespace(total_points=plan.total_points, meta_all=lambda: plan.meta, total_rows=plan.total_rows,
+                                 total_chunks=plan.total_chunks, multi_chunk=plan.multi_chunk, batch=plan.batch)
+    return single_gpu_with_table(shim, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("name", ["mixed", "nobg", "empty", "outside", "config2"])
+def test_banded_ranks_agree_and_match_one_gpu(name, world):
+    """Row-band sharding on emulated ranks: every rank returns the SAME loss bits; the gradient -- per-pixel work that
+    never leaves its rank -- is BIT-IDENTICAL to one GPU sweeping the same chunk table; the loss differs from one GPU
+    only by the two-level (band, then rank) order of the count sums (bit-identical for world == 1); both within
+    rtol 1e-5 of the CPU oracle."""
+    pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = _case(name)
+    chunk = 1024 if name == "config2" else 29
+    owners = [(3 * i + 1) % world for i in range(len(pts))]
+    for cull in (False, True):
+        losses, grad, plan = run_banded(world, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull, owners, steps=2,
+                                        chunk=chunk)
+        assert all(torch.equal(l, losses[0]) for l in losses), [float(l) for l in losses]
+        ref_loss, ref_grad = _band_table_on_one_gpu(plan, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, cull)
+        if world == 1:
+            assert torch.equal(losses[0], ref_loss)
+        assert_close(losses[0], ref_loss, 1e-6, 0, "banded loss vs one GPU")
+        assert torch.equal(grad, ref_grad), f"gradient differs in {int((grad != ref_grad).sum())} pixels"
+    o_loss, o_grad, _ = bl_oracle.bl_forward_backward(pts, st, tgt, dens, stride, sigma, bg_ratio, use_bg)
+    assert_close(losses[0], o_loss, 1e-5, 0, "banded loss vs oracle")
+    assert_close(grad, o_grad, 1e-5, 2e-7 * float(o_grad.abs().max()), "banded gradient vs oracle")
+
+
+def test_config3_batch_on_eight_emulated_band_ranks():
+    """BASELINE config 3 (16 images, 49 697 heads, 192 x 256 grid) over 8 bands of 24 grid rows."""
+    pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg = _case("config3")
+    losses, grad, plan = run_banded(8, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, False)
+    assert (plan.band_hi - plan.band_lo).tolist() == [24] * 8
+    assert all(torch.equal(l, losses[0]) for l in losses)
+    from dgvcc_b200.losses.bl import BL
+    dev = torch.device("cuda:0")
+    d = dens.to(dev).requires_grad_(True)
+    mod = BL(sigma, 2048, stride, bg_ratio, use_bg, dev)
+    l1 = mod([p.to(dev) for p in pts], st.to(dev), [t.to(dev) for t in tgt], d)
+    l1.backward()
+    # against the ordinary single-GPU module (1024-point chunks: another summation order of the chunk partials)
+    assert_close(losses[0], l1.detach().cpu(), 2e-6, 0, "banded vs BL loss")
+    assert_close(grad, d.grad.cpu(), 1e-5, 1e-6 * float(d.grad.abs().max()), "banded vs BL gradient")
+    culled, grad_c, _ = run_banded(8, pts, tgt, st, dens, stride, sigma, bg_ratio, use_bg, True)
+    assert torch.equal(culled[0], losses[0]) and torch.equal(grad_c, grad)   # exact-zero culling changes no bit
+
+
 def _torchrun(script, nproc, *args, timeout=600):
     import os
     import socket

@@ -118,3 +118,71 @@ def test_exchange_plan_is_consistent(counts, world):
         for q in p.groups[i]:
             if q != owners[i]:
                 assert p.shards[q].wait_mask[P.BL_PH_DENS] >> int(owners[i]) & 1
+
+
+# ------------------------------------------------------------------------------------------------ row-band sharding
+BAND_CASES = [([200, 0, 37], 2, 24, 32), ([200, 0, 37], 3, 24, 32), ([0, 0], 2, 3, 5), ([5], 8, 12, 40),
+              (synthetic.config_counts(3), 8, 192, 256), (synthetic.config_counts(3), 4, 192, 256),
+              (synthetic.config_counts(2), 5, 128, 96), ([1] * 9, 8, 7, 33)]
+
+
+@pytest.mark.parametrize("counts,world,hp,wp", BAND_CASES)
+def test_band_plan_tiles_the_grid_and_the_exchange_is_consistent(counts, world, hp, wp):
+    from dgvcc_b200.losses.bl_banded import BandPlan, band_chunk_points
+    owners = (np.arange(len(counts)) * 7 + 3) % world
+    chunk = band_chunk_points(int(np.sum(counts)), world, hp, wp)
+    assert 128 <= chunk <= 1024 and chunk % 32 == 0
+    p = BandPlan(counts, True, world, owners, hp, wp, chunk)
+    L, m4, P, b = p.layout, 4 * hp * wp, _native, len(counts)
+    R = L.rows_per_thread
+    # the bands are whole rows of pixel tiles, disjoint, in rank order, and cover the grid
+    assert p.band_lo[0] == 0 and p.band_hi[-1] == hp
+    for r in range(world):
+        assert p.band_lo[r] <= p.band_hi[r] and p.band_lo[r] % R == 0 and (p.band_hi[r] % R == 0 or p.band_hi[r] == hp)
+        if r:
+            assert p.band_lo[r] == p.band_hi[r - 1]
+    sizes = (p.band_hi - p.band_lo + R - 1) // R
+    assert sizes.max() - sizes.min() <= 1
+    assert L.cshare > 0 and L.total >= L.cshare + 4 * world * p.total_rows
+    # every chunk is scheduled on every rank
+    table = p.meta_for(0)[4 * b + 3:].reshape(-1, 4)
+    assert sorted(table[:, 3].tolist()) == list(range(p.total_chunks)) and table[:, 2].max() <= chunk
+    got = np.zeros((world, b, hp), dtype=np.int32)      # density rows delivered to each rank
+    recv = np.zeros((world, P.BL_PHASES), dtype=np.uint32)
+    for r in range(world):
+        sh, sl = p.shards[r], p.slices[r]
+        assert (sh.band_lo, sh.band_hi) == (p.band_lo[r], p.band_hi[r])
+        for ph in range(P.BL_PHASES):
+            n = sh.push_first[ph + 1] - sh.push_first[ph]
+            assert n == 0 or ph in (P.BL_PH_DENS, P.BL_PH_OUT)
+            for k in range(sh.push_first[ph], sh.push_first[ph + 1]):
+                src_off, dst_off, packed = (int(v) for v in sl[k])
+                nbytes, dst = packed & 0xffffffff, packed >> 32
+                assert nbytes > 0 and nbytes % 4 == 0 and 0 <= dst < world
+                if ph == P.BL_PH_DENS:
+                    assert src_off + nbytes <= len(p.owned[r]) * m4 and L.dens <= dst_off and dst_off + nbytes <= L.dens + b * m4
+                    img, rest = divmod(dst_off - L.dens, m4)
+                    assert owners[img] == r and src_off % m4 == rest     # the same cells of the same image on both sides
+                    cells = np.arange(rest // 4, (rest + nbytes) // 4)
+                    np.add.at(got[dst, img], np.unique(cells // wp), 1)
+                else:
+                    assert dst == r and dst_off + nbytes <= len(p.owned[r]) * m4
+            for q in range(world):
+                if sh.signal_mask[ph] >> q & 1:
+                    assert q != r
+                    recv[q, ph] |= np.uint32(1 << r)
+        out = sl[sh.push_first[P.BL_PH_OUT]:sh.push_first[P.BL_PH_OUT + 1]]
+        assert sum(int(v[2]) & 0xffffffff for v in out) == len(p.owned[r]) * m4
+        om = p.aux[r]
+        assert om.shape == (b,) and all(om[i] == (0 if owners[i] == r else 1 << int(owners[i])) for i in range(b))
+    for r in range(world):
+        for ph in range(P.BL_PHASES):
+            assert int(recv[r, ph]) == p.shards[r].wait_mask[ph]
+        others = sum(1 << q for q in range(world) if q != r)
+        assert p.shards[r].signal_mask[P.BL_PH_CNT] == others == p.shards[r].wait_mask[P.BL_PH_CNT]
+        for ph in (P.BL_PH_MIN, P.BL_PH_Z, P.BL_PH_LOSS, P.BL_PH_GPART):
+            assert p.shards[r].signal_mask[ph] == 0 == p.shards[r].wait_mask[ph]
+        # a rank receives exactly the rows of its band, of every image, at least once (slices may split a row)
+        for i in range(b):
+            rows = np.nonzero(got[r, i])[0]
+            assert rows.tolist() == list(range(p.band_lo[r], p.band_hi[r]))

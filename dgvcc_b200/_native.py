@@ -19,7 +19,7 @@ class BLLayout(ctypes.Structure):
     """Mirror of struct dgvcc_bl_layout."""
     _fields_ = [(n, c_int64) for n in
                 ("amax", "rz", "pbg", "ebg", "counts", "wsel", "residual", "loss_img", "ticket", "cpart", "zpart",
-                 "minpart", "gpart", "total", "dens", "gfinal", "flags", "err", "push_ticket", "goff", "gsorted", "cshare", "ztick", "gtick")] + \
+                 "minpart", "gpart", "total", "dens", "gfinal", "flags", "err", "push_ticket", "goff", "gsorted", "cshare", "ztick", "gtick", "queue")] + \
                [("tiles", c_int32), ("rows_per_thread", c_int32), ("cols_per_thread", c_int32), ("share_rows", c_int32)]
 
 

@@ -30,6 +30,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "../../include/dgvcc_b200.h"
 
@@ -272,11 +274,11 @@ struct TaskInfo {
 // of an image's points so that all tasks cost the same and the hardware CTA scheduler balances them.
 template <int R, int C>
 __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, int batch, const Geom& g,
-                                            TaskInfo& t) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    t.task = g.task_first + blockIdx.x * WARPS_PER_CTA + warp;
+                                            TaskInfo& t, int slot, int task) {
+    const int lane = threadIdx.x & 31;
+    t.task = task;
     const Meta mv = meta_view(meta, batch);
-    t.chunk = mv.chunks[4 * blockIdx.y + 3];
+    t.chunk = mv.chunks[4 * slot + 3];
     const int32_t* ce = mv.chunks + 4 * t.chunk;
     t.img = ce[0];
     t.p_start = ce[1];
@@ -484,7 +486,8 @@ __device__ __forceinline__ int grid_cell_1d(float v, float inv_cell, int n) {
 __global__ void __launch_bounds__(1024)
 bl_grid_build_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta, int batch, GridGeom gg,
                      int img_first, int32_t* __restrict__ goff, float2* __restrict__ gsorted,
-                     unsigned int* __restrict__ ztick, unsigned int* __restrict__ gtick, int tiles_img) {
+                     unsigned int* __restrict__ ztick, unsigned int* __restrict__ gtick, int tiles_img,
+                     unsigned int* __restrict__ queue) {
     __shared__ int hist[GRID_MAX_CELLS];
     __shared__ int warp_tot[32];
     const int img = img_first + blockIdx.x, tid = threadIdx.x;
@@ -494,6 +497,7 @@ bl_grid_build_kernel(const float2* __restrict__ pts_all, const int32_t* __restri
         ztick[(size_t)img * tiles_img + i] = 0u;
         gtick[(size_t)img * tiles_img + i] = 0u;
     }
+    if (blockIdx.x == 0 && tid < 6) queue[tid] = 0u;   // the work queues of the persistent sweeps
     const Meta mv = meta_view(meta, batch);
     const int pt0 = mv.pt_off[img], n = mv.pt_off[img + 1] - pt0;
     if (n == 0) return;
@@ -679,6 +683,25 @@ bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict_
             if (px.ok(r, c)) out[px.pix(r, c)] = mind[r][c];
 }
 
+// The sweeps are persistent: a launch has at most as many CTAs as the GPU holds at once, and a warp (bl_z, bl_grad) or
+// a CTA (bl_counts) that finishes a task takes the next one from a counter.  Work item w = (launch slot w / n, pixel
+// tile or CTA of tiles w % n); the slots list the chunks longest first, so the queue is a longest-processing-time
+// schedule: the sweep ends within one SHORT task of the moment the work runs out, instead of waiting for a last wave
+// of full-length tasks.  queue[0] = items handed out beyond the first round, queue[1] = CTAs that left: the last one
+// zeroes both for the next launch (bl_grid_build_kernel also zeroes them at the head of every forward pass).
+__device__ __forceinline__ unsigned int queue_next_warp(unsigned int* queue, unsigned int first_round) {
+    unsigned int w = 0u;
+    if ((threadIdx.x & 31) == 0) w = first_round + atomicAdd(queue, 1u);
+    return __shfl_sync(FULL_MASK, w, 0);
+}
+__device__ __forceinline__ void queue_leave(unsigned int* queue) {  // every thread of the CTA, after its last item
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(queue + 1, 1u) == gridDim.x - 1u) {
+        queue[0] = 0u;
+        queue[1] = 0u;
+    }
+}
+
 // The chunks of one image sweep the same pixel tile in separate warp tasks; whichever task arrives LAST at the tile's
 // counter combines the per-chunk partials (in chunk order, whoever does it: the sum does not depend on the arrival
 // order) -- the classic last-block reduction, per pixel tile.  Saves a reduction kernel and a second pass over the
@@ -713,7 +736,7 @@ __device__ __noinline__ void finish_z_tile(const float* __restrict__ zc, int n_c
             pix[r][c] = min(row_base + r, hp - 1) * wp + min(col0 + 32 * c, wp - 1);  // outside the grid: the clamped twin
             z[r][c] = 0.f;
         }
-#pragma unroll 2
+#pragma unroll 4
     for (int ch = 0; ch < n_chunks; ++ch, zc += M) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -746,7 +769,7 @@ __device__ __noinline__ void finish_grad_tile(const float* __restrict__ gc, int 
             pix[r][c] = min(row_base + r, hp - 1) * wp + min(col0 + 32 * c, wp - 1);
             a[r][c] = 0.f;
         }
-#pragma unroll 2
+#pragma unroll 4
     for (int ch = 0; ch < n_chunks; ++ch, gc += M) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -770,11 +793,10 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
             int exact_cull, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, const Shard& sh,
             const float* __restrict__ min_img, const Xchg& x, float* __restrict__ rz_out, float* __restrict__ pbg_out,
-            unsigned int* __restrict__ tile_tick, int finish) {
+            unsigned int* __restrict__ tile_tick, int finish, int slot, int task) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return false;
+    if (!decode_task<R, C>(meta, batch, g, t, slot, task)) return false;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     PixelTile<R, C> px;
@@ -905,10 +927,18 @@ bl_z_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta
             int exact_cull, float* __restrict__ zpart,
             float* __restrict__ amax_out, float* __restrict__ ebg_out, unsigned int* __restrict__ ticket, Shard sh,
             const float* __restrict__ min_img, Xchg x, float* __restrict__ rz_out, float* __restrict__ pbg_out,
-            unsigned int* __restrict__ tile_tick, int finish) {
-    const bool stored = bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull,
-                                              zpart, amax_out, ebg_out, ticket, sh, min_img, x, rz_out, pbg_out, tile_tick,
-                                              finish);
+            unsigned int* __restrict__ tile_tick, int finish, int n_slots, unsigned int* __restrict__ queue) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;  // bl_select_kernel's arrival counter
+    const int n_tiles = g.tiles - g.task_first;
+    const unsigned int total = (unsigned)n_slots * (unsigned)n_tiles, first_round = gridDim.x * WARPS_PER_CTA;
+    bool stored = false;
+    for (unsigned int w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5); w < total; w = queue_next_warp(queue, first_round)) {
+        stored |= bl_z_body<R, C, POW2>(pts_all, meta, st_sizes, batch, g, k, bg_ratio, use_bg, exact_cull, zpart, amax_out,
+                                        ebg_out, ticket, sh, min_img, x, rz_out, pbg_out, tile_tick, finish,
+                                        (int)(w / n_tiles), g.task_first + (int)(w % n_tiles));
+        __syncwarp();  // the warp's shared-memory tile is reused by its next task
+    }
+    queue_leave(queue);
     xchg_signal(x, stored);
 }
 
@@ -937,7 +967,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 5)   // 5 CTAs per SM (what the 3
 bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ meta,
                  const float* __restrict__ density, int batch, Geom g, Scale k, int use_bg, int exact_cull,
                  const float* __restrict__ amax_in, const float* __restrict__ rz_in, const float* __restrict__ pbg_in,
-                 int64_t total_rows, float* __restrict__ cpart, int share_row0, Xchg x) {
+                 int64_t total_rows, float* __restrict__ cpart, int share_row0, Xchg x, int n_slots,
+                 unsigned int* __restrict__ queue) {
     xchg_wait(x);  // row-band sharding: the density rows of the band, delivered by the images' owners
     // The four warps of a CTA sweep the same point chunk over four pixel tiles; their per-point partial counts
     // meet in shared memory and leave the CTA as ONE partial row (a quarter of the cpart traffic, and a quarter
@@ -947,16 +978,22 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     __shared__ float cta_acc[WARPS_PER_CTA][COUNT_SPAN];
     __shared__ float cta_bg[WARPS_PER_CTA];
-    TaskInfo t;
-    const bool live = decode_task<R, C>(meta, batch, g, t);
+    __shared__ unsigned int next_item;
     const int warp = threadIdx.x >> 5;
     WarpTile<R>& tile = tiles[warp];
     const int lane = threadIdx.x & 31;
     const size_t M = (size_t)g.hp * g.wp;
+    // persistent CTAs: item = (launch slot, CTA of four pixel tiles), see queue_next_warp
+    const int n_ctas = ceil_div(g.tiles - g.task_first, WARPS_PER_CTA);
+    const unsigned int total_items = (unsigned)n_slots * (unsigned)n_ctas;
+    for (unsigned int item = blockIdx.x; item < total_items;) {
+    const int cta_x = (int)(item % n_ctas);
+    TaskInfo t;
+    const bool live = decode_task<R, C>(meta, batch, g, t, (int)(item / n_ctas), g.task_first + cta_x * WARPS_PER_CTA + warp);
     const size_t img_base = (size_t)t.img * M;
     PixelTile<R, C> px;
     px.init(t, g);
-    const size_t part0 = (size_t)(max(share_row0, 0) + (int)blockIdx.x) * total_rows + t.row0;
+    const size_t part0 = (size_t)(max(share_row0, 0) + cta_x) * total_rows + t.row0;
     const bool bg_row = t.chunk == t.first_chunk && (use_bg || t.n_img_pts == 0);  // the image's first chunk anywhere
 
     // per-pixel weights D[m]/Z[m]; pixels outside the grid get weight 0
@@ -1067,6 +1104,12 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
                       ((cta_acc[0][i] + cta_acc[1][i]) + cta_acc[2][i]) + cta_acc[3][i]);
         __syncthreads();
     }
+    if (threadIdx.x == 0) next_item = gridDim.x + atomicAdd(queue, 1u);
+    __syncthreads();
+    item = next_item;
+    __syncthreads();   // everybody has read next_item before thread 0 can overwrite it
+    }
+    queue_leave(queue);
     xchg_signal(x, share_row0 >= 0);
 }
 
@@ -1295,10 +1338,10 @@ __device__ __forceinline__ bool bl_grad_body(const float2* __restrict__ pts_all,
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
                float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, const Xchg& x,
-               unsigned int* __restrict__ tile_tick) {
+               unsigned int* __restrict__ tile_tick, int slot, int task) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return false;
+    if (!decode_task<R, C>(meta, batch, g, t, slot, task)) return false;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
@@ -1407,9 +1450,17 @@ bl_grad_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__ m
                const float* __restrict__ amax_in, const float* __restrict__ rz_in,
                const float* __restrict__ pbg_in, const float* __restrict__ wsel,
                float* __restrict__ gpart, float* __restrict__ grad_density, int always_partial, Xchg x,
-               unsigned int* __restrict__ tile_tick) {
-    const bool stored = bl_grad_body<R, C, POW2>(pts_all, meta, batch, g, k, use_bg, exact_cull, inv_batch, grad_loss, amax_in,
-                                                 rz_in, pbg_in, wsel, gpart, grad_density, always_partial, x, tile_tick);
+               unsigned int* __restrict__ tile_tick, int n_slots, unsigned int* __restrict__ queue) {
+    const int n_tiles = g.tiles - g.task_first;
+    const unsigned int total = (unsigned)n_slots * (unsigned)n_tiles, first_round = gridDim.x * WARPS_PER_CTA;
+    bool stored = false;
+    for (unsigned int w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5); w < total; w = queue_next_warp(queue, first_round)) {
+        stored |= bl_grad_body<R, C, POW2>(pts_all, meta, batch, g, k, use_bg, exact_cull, inv_batch, grad_loss, amax_in, rz_in,
+                                           pbg_in, wsel, gpart, grad_density, always_partial, x, tile_tick,
+                                           (int)(w / n_tiles), g.task_first + (int)(w % n_tiles));
+        __syncwarp();
+    }
+    queue_leave(queue);
     xchg_signal(x, stored);
 }
 
@@ -1489,7 +1540,7 @@ bl_posterior_kernel(const float2* __restrict__ pts_all, const int32_t* __restric
                     const float* __restrict__ pbg_in, float* __restrict__ prob_out) {
     __shared__ WarpTile<R> tiles[WARPS_PER_CTA];
     TaskInfo t;
-    if (!decode_task<R, C>(meta, batch, g, t)) return;
+    if (!decode_task<R, C>(meta, batch, g, t, blockIdx.y, g.task_first + blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5))) return;
     WarpTile<R>& tile = tiles[threadIdx.x >> 5];
     const size_t M = (size_t)g.hp * g.wp;
     const size_t img_base = (size_t)t.img * M;
@@ -1763,6 +1814,9 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     // world > 0: the symmetric layout of dgvcc_bl_shard_* (identical on every rank); the pixel tile is chosen for the
     // chunks ONE rank sweeps
     Variant v = pick_variant(world > 0 ? ceil_div(total_chunks, world) : total_chunks, hp, wp);
+    // A rank of a sharded sweep has about one round of warp tasks: the 8 x 32 tile (twice the tasks, half as long) balances
+    // better than 8 x 64 -- measured on 2 and 8 B200 with config 3 (profiles/r2_strong_scaling.md), 3-7 % of the step.
+    if (world > 1 && v.rows == 8 && v.cols == 2) v = kVariants[1];
     if (world > 0 && g_opt_band_tile) v = Variant{g_opt_band_tile / 10, g_opt_band_tile % 10};
     const int tiles = make_geom(hp, wp, v, 1.f).tiles;
     const size_t M = (size_t)hp * wp;
@@ -1791,6 +1845,7 @@ static int layout(int64_t total_rows, int total_chunks, int batch, int hp, int w
     L->gsorted = take((size_t)total_rows * sizeof(float2));                   // points sorted by grid cell (<= rows)
     L->ztick = take((size_t)batch * tiles * sizeof(unsigned int));            // arrival counters per (image, pixel tile): bl_z
     L->gtick = take((size_t)batch * tiles * sizeof(unsigned int));            //                                          bl_grad
+    L->queue = take(6 * sizeof(unsigned int));   // work queues of the persistent sweeps: (handed out, CTAs gone) x z, counts, grad
     if (world > 0) {
         L->dens = take(pix);         // density of every image this rank sweeps, delivered by the image's owner
         L->gfinal = take(pix);       // finished gradients, delivered to the image's owner
@@ -1836,6 +1891,45 @@ extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, i
         else BL_LAUNCH_RC(2, 1, POW2_, KERNEL, GRID, STREAM, __VA_ARGS__);                             \
     } while (0)
 
+// Persistent launch: at most as many CTAs as the GPU holds at once (occupancy of this very instantiation, asked once
+// per kernel and device); the kernel's work queue hands out the rest of the items.
+static int resident_ctas(const void* key, int per_sm_query(int*)) {
+    struct Entry { const void* key; int dev, ctas; };
+    static Entry cache[256];
+    static int n_cached = 0;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].key == key && cache[i].dev == dev) return cache[i].ctas;
+    int per_sm = 0, sms = 0;
+    if (per_sm_query(&per_sm) != 0 || per_sm < 1) per_sm = 1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 1;
+    if (n_cached < 256) cache[n_cached++] = Entry{key, dev, per_sm * sms};
+    return per_sm * sms;
+}
+#define BL_PERSIST_ONE(KERNEL_INST, WANTED, STREAM, ...)                                                              \
+    do {                                                                                                              \
+        auto kern_ = KERNEL_INST;                                                                                     \
+        const int cap_ = resident_ctas((const void*)kern_, [](int* n) {                                               \
+            return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, KERNEL_INST, CTA_THREADS, 0); });            \
+        const int grid_ = (WANTED) < cap_ ? (WANTED) : cap_;                                                          \
+        kern_<<<grid_ > 0 ? grid_ : 1, CTA_THREADS, 0, STREAM>>>(__VA_ARGS__);                                        \
+    } while (0)
+#define BL_PERSIST_RC(R_, C_, POW2_, KERNEL, WANTED, STREAM, ...)                                    \
+    do {                                                                                             \
+        if (POW2_) BL_PERSIST_ONE((KERNEL<R_, C_, true>), WANTED, STREAM, __VA_ARGS__);              \
+        else BL_PERSIST_ONE((KERNEL<R_, C_, false>), WANTED, STREAM, __VA_ARGS__);                   \
+    } while (0)
+#define BL_PERSIST(V_, POW2_, KERNEL, WANTED, STREAM, ...)                                                    \
+    do {                                                                                                      \
+        if ((V_).rows == 8 && (V_).cols == 2) BL_PERSIST_RC(8, 2, POW2_, KERNEL, WANTED, STREAM, __VA_ARGS__); \
+        else if ((V_).rows == 8) BL_PERSIST_RC(8, 1, POW2_, KERNEL, WANTED, STREAM, __VA_ARGS__);             \
+        else if ((V_).rows == 4) BL_PERSIST_RC(4, 1, POW2_, KERNEL, WANTED, STREAM, __VA_ARGS__);             \
+        else BL_PERSIST_RC(2, 1, POW2_, KERNEL, WANTED, STREAM, __VA_ARGS__);                                 \
+    } while (0)
+
 extern "C" int dgvcc_bl_set_option(int option, int value) {
     switch (option) {
         case DGVCC_BL_OPT_MIN_CELL:
@@ -1861,6 +1955,8 @@ struct Plan {
     bool pow2;
     dim3 grid;   // (CTAs per chunk, chunks this launch sweeps)
     Shard sh;
+    // CTAs that hold every warp task of bl_z / bl_grad at once (the persistent launches take fewer when the GPU is full)
+    int warp_ctas() const { return ceil_div((int)grid.y * (g.tiles - g.task_first), WARPS_PER_CTA); }
 };
 
 int make_plan(const void* a, const void* b, const void* ws, size_t ws_bytes, int batch, int hp, int wp,
@@ -1920,7 +2016,7 @@ int launch_gridmin(const Plan& p, const float2* pts, const int32_t* meta, int ba
     int32_t* goff = at<int32_t>(ws, p.L.goff);
     float2* gsorted = at<float2>(ws, p.L.gsorted);
     bl_grid_build_kernel<<<n_img, 1024, 0, st>>>(pts, meta, batch, gg, img_first, goff, gsorted, at<unsigned int>(ws, p.L.ztick),
-                                                 at<unsigned int>(ws, p.L.gtick), p.g.tiles_img);
+                                                 at<unsigned int>(ws, p.L.gtick), p.g.tiles_img, at<unsigned int>(ws, p.L.queue));
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     // The minima have their own, small pixel tile (2 rows x 32 columns), independent of the exponential sweeps': every point
     // inside a tile's own rectangle is swept over the whole tile whatever the bound, so a crowd of 1500 heads inside one
@@ -1946,10 +2042,10 @@ int launch_z(const Plan& p, const float* pts_xy, const int32_t* meta, const floa
     int rc = launch_gridmin(p, pts, meta, batch, p.g.hp, p.g.wp, 0, batch, ws, min_img, st);
     if (rc) return rc;
     mark(events, 1, st);
-    BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
+    BL_PERSIST(p.v, p.pow2, bl_z_kernel, p.warp_ctas(), st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg,
                 exact_cull, at<float>(ws, p.L.zpart), at<float>(ws, p.L.amax), at<float>(ws, p.L.ebg),
                 at<unsigned int>(ws, p.L.ticket), p.sh, (const float*)min_img, Xchg{}, at<float>(ws, p.L.rz),
-                at<float>(ws, p.L.pbg), at<unsigned int>(ws, p.L.ztick), 1);
+                at<float>(ws, p.L.pbg), at<unsigned int>(ws, p.L.ztick), 1, (int)p.grid.y, at<unsigned int>(ws, p.L.queue) + 0);
     mark(events, 2, st);
     return (int)cudaGetLastError();
 }
@@ -1988,9 +2084,9 @@ extern "C" int dgvcc_bl_forward_profiled(const float* pts_xy, const float* targe
     if (!st_sizes || !loss_out || !pts_xy || !targets) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = launch_z(p, pts_xy, meta, st_sizes, batch, multi_chunk, bg_ratio, use_bg, exact_cull, workspace, st, events))) return rc;
-    BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
+    BL_PERSIST(p.v, p.pow2, bl_counts_kernel, (int)(p.grid.x * p.grid.y), st, (const float2*)pts_xy, meta, density, batch, p.g, p.k,
                 use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg),
-                total_rows, at<float>(workspace, p.L.cpart), -1, Xchg{});
+                total_rows, at<float>(workspace, p.L.cpart), -1, Xchg{}, (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 2);
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 3, st);
     rc = launch_select(p.L, targets, meta, batch, total_rows, inv_batch, p.L.tiles, workspace, loss_out, st);
@@ -2020,10 +2116,10 @@ extern "C" int dgvcc_bl_backward(const float* pts_xy, const int32_t* meta, int b
     if (rc) return rc;
     if (!grad_density || !pts_xy) return DGVCC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
+    BL_PERSIST(p.v, p.pow2, bl_grad_kernel, p.warp_ctas(), st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg,
                 exact_cull, inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                 at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                grad_density, 0, Xchg{}, at<unsigned int>(workspace, p.L.gtick));
+                grad_density, 0, Xchg{}, at<unsigned int>(workspace, p.L.gtick), (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 4);
     (void)multi_chunk;  // multi-chunk images are finished inside bl_grad_kernel (last arrival per pixel tile)
     return (int)cudaGetLastError();
 }
@@ -2204,10 +2300,10 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
     {
         const Xchg x = c.make(DGVCC_BL_PH_Z, c.zmask(), p.L.zpart, 0, -1, -1);
         if (sweeps) {
-            BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
+            BL_PERSIST(p.v, p.pow2, bl_z_kernel, p.warp_ctas(), st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
                         at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax),
                         at<float>(workspace, p.L.ebg), at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img, x,
-                        at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<unsigned int>(workspace, p.L.ztick), 0);
+                        at<float>(workspace, p.L.rz), at<float>(workspace, p.L.pbg), at<unsigned int>(workspace, p.L.ztick), 0, (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 0);
         } else {
             bl_signal_kernel<<<1, 32, 0, st>>>(x);
         }
@@ -2223,9 +2319,9 @@ extern "C" int dgvcc_bl_shard_forward(const float* pts_xy, const float* targets,
     DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     mark(events, 4, st);
     if (sweeps) {
-        BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
+        BL_PERSIST(p.v, p.pow2, bl_counts_kernel, (int)(p.grid.x * p.grid.y), st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
                     use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
-                    at<float>(workspace, p.L.pbg), total_rows, at<float>(workspace, p.L.cpart), -1, Xchg{});
+                    at<float>(workspace, p.L.pbg), total_rows, at<float>(workspace, p.L.cpart), -1, Xchg{}, (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 2);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     }
     mark(events, 5, st);
@@ -2277,10 +2373,10 @@ extern "C" int dgvcc_bl_shard_backward(const float* pts_xy, const int32_t* meta,
     {   // raw per-chunk gradient sums of every image, written where the rank with the image's first chunk will add them
         const Xchg x = c.make(DGVCC_BL_PH_GPART, c.gmask(), p.L.gpart, 0, -1, -1);
         if (p.grid.y > 0) {
-            BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
+            BL_PERSIST(p.v, p.pow2, bl_grad_kernel, p.warp_ctas(), st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
                         inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                         at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                        at<float>(workspace, p.L.gfinal), 1, x, at<unsigned int>(workspace, p.L.gtick));
+                        at<float>(workspace, p.L.gfinal), 1, x, at<unsigned int>(workspace, p.L.gtick), (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 4);
         } else {
             bl_signal_kernel<<<1, 32, 0, st>>>(x);
         }
@@ -2377,10 +2473,10 @@ extern "C" int dgvcc_bl_band_forward(const float* pts_xy, const float* targets, 
         if ((rc = launch_gridmin(p, pts, meta, batch, hp, wp, 0, batch, workspace, min_img, st, shard->band_lo, shard->band_hi)))
             return rc;
         mark(events, 2, st);
-        BL_DISPATCH(p.v, p.pow2, bl_z_kernel, p.grid, st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
+        BL_PERSIST(p.v, p.pow2, bl_z_kernel, p.warp_ctas(), st, pts, meta, st_sizes, batch, p.g, p.k, bg_ratio, use_bg, exact_cull,
                     at<float>(workspace, p.L.zpart), at<float>(workspace, p.L.amax), at<float>(workspace, p.L.ebg),
                     at<unsigned int>(workspace, p.L.ticket), p.sh, (const float*)min_img, Xchg{}, at<float>(workspace, p.L.rz),
-                    at<float>(workspace, p.L.pbg), at<unsigned int>(workspace, p.L.ztick), 1);
+                    at<float>(workspace, p.L.pbg), at<unsigned int>(workspace, p.L.ztick), 1, (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 0);
         DGVCC_RETURN_IF_CUDA(cudaGetLastError());
     } else {
         mark(events, 2, st);
@@ -2393,9 +2489,9 @@ extern "C" int dgvcc_bl_band_forward(const float* pts_xy, const float* targets, 
     const Xchg cnt = c.make(DGVCC_BL_PH_CNT, nullptr, p.L.cshare, 0, DGVCC_BL_PH_DENS, -1);
     if ((int)p.grid.x > p.L.share_rows) return DGVCC_ERR_ARG;
     if (sweeps) {
-        BL_DISPATCH(p.v, p.pow2, bl_counts_kernel, p.grid, st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
+        BL_PERSIST(p.v, p.pow2, bl_counts_kernel, (int)(p.grid.x * p.grid.y), st, pts, meta, at<float>(workspace, p.L.dens), batch, p.g, p.k,
                     use_bg, exact_cull, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
-                    at<float>(workspace, p.L.pbg), total_rows, (float*)nullptr, shard->rank * p.L.share_rows, cnt);
+                    at<float>(workspace, p.L.pbg), total_rows, (float*)nullptr, shard->rank * p.L.share_rows, cnt, (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 2);
     } else {
         bl_signal_kernel<<<1, 32, 0, st>>>(cnt);
     }
@@ -2445,10 +2541,10 @@ extern "C" int dgvcc_bl_band_backward(const float* pts_xy, const int32_t* meta, 
     // gradient of the band's pixels, finished inside the sweep (last arrival per pixel tile) and written at the image's owner
     const Xchg out = c.make(DGVCC_BL_PH_GRAD, owner_mask, p.L.gfinal, 0, -1, -1);
     if (sweeps) {
-        BL_DISPATCH(p.v, p.pow2, bl_grad_kernel, p.grid, st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
+        BL_PERSIST(p.v, p.pow2, bl_grad_kernel, p.warp_ctas(), st, (const float2*)pts_xy, meta, batch, p.g, p.k, use_bg, exact_cull,
                     inv_batch, grad_loss, at<float>(workspace, p.L.amax), at<float>(workspace, p.L.rz),
                     at<float>(workspace, p.L.pbg), at<float>(workspace, p.L.wsel), at<float>(workspace, p.L.gpart),
-                    at<float>(workspace, p.L.gfinal), 0, out, at<unsigned int>(workspace, p.L.gtick));
+                    at<float>(workspace, p.L.gfinal), 0, out, at<unsigned int>(workspace, p.L.gtick), (int)p.grid.y, at<unsigned int>(workspace, p.L.queue) + 4);
     } else {
         bl_signal_kernel<<<1, 32, 0, st>>>(out);
     }

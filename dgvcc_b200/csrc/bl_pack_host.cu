@@ -49,10 +49,6 @@ extern "C" int dgvcc_bl_pack_host(const float* const* points, const float* const
     pt_off[0] = row_off[0] = icb[0] = 0;
     float* out_pts = (float*)((char*)dst + info->off_points);
     float* out_tgt = (float*)((char*)dst + info->off_targets);
-    std::vector<int> order(b);
-    for (int i = 0; i < b; ++i) order[i] = i;
-    // schedule: chunks of the images with the most points first (they have the most tiles in flight)
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return counts[x] > counts[y]; });
     int32_t c = 0;
     for (int i = 0; i < b; ++i) {
         const int64_t n = counts[i], rows = n == 0 ? 1 : n + (use_background ? 1 : 0);
@@ -74,8 +70,11 @@ extern "C" int dgvcc_bl_pack_host(const float* const* points, const float* const
             }
         }
     }
-    int32_t slot = 0;
-    for (int r = 0; r < b; ++r)
-        for (int32_t k = icb[order[r]]; k < icb[order[r] + 1]; ++k) table[4 * slot++ + 3] = k;
+    // schedule: longest chunks first (the sweeps hand the launch slots out through a work queue: a
+    // longest-processing-time schedule, the tail of a sweep is made of the shortest tasks)
+    std::vector<int32_t> order(total_chunks);
+    for (int32_t k = 0; k < (int32_t)total_chunks; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return table[4 * x + 2] > table[4 * y + 2]; });
+    for (int32_t slot = 0; slot < (int32_t)total_chunks; ++slot) table[4 * slot + 3] = order[slot];
     return DGVCC_OK;
 }

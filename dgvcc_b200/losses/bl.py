@@ -69,8 +69,9 @@ def build_meta(counts, rows, chunk):
     start = counts[img] * k // n_chunks[img]                   # near-equal slices
     stop = counts[img] * (k + 1) // n_chunks[img]
     table[:, 0], table[:, 1], table[:, 2] = img, start, stop - start
-    # schedule: chunks of the images with the most points first (they have the most tiles in flight)
-    table[:, 3] = np.argsort(-counts[img], kind="stable")
+    # schedule: longest chunks first -- the sweeps hand the launch slots out through a work queue, so this is a
+    # longest-processing-time schedule (the tail of a sweep is made of the shortest tasks)
+    table[:, 3] = np.argsort(-(stop - start), kind="stable")
     return meta, total_chunks, int(n_chunks.max() > 1)
 
 

@@ -34,16 +34,18 @@ FORCE_CHUNK = None   # experiments: points per chunk of the band plan, whatever 
 
 
 def band_chunk_points(total_points, world, hp, wp):
-    """Points per chunk when every rank sweeps 1/world of the pixel tiles: enough chunks that a rank still has ~16 warp
-    tasks per SM with the largest pixel tile (8 rows x 64 columns per warp; the launcher falls back to smaller tiles
-    -- more shared-memory reads per exponential -- when there are fewer).  Never above the single-GPU chunk size, never
-    below 128, a multiple of 32."""
+    """Points per chunk when every rank sweeps 1/world of the pixel tiles.  A rank should see about 1.7 rounds of warp
+    tasks (8 x 32 pixel tiles; 16 resident warps on each of 148 SMs): fewer, and the tail of a sweep is one full-length
+    task; more, and the per-task prologues, the per-chunk partial arrays and the last arrival's sum over the chunks of a
+    tile grow.  Measured on 8 B200 with BASELINE config 3 (profiles/r2_strong_scaling.md; step time against points per
+    chunk): 192 -> 0.4225 ms, 256 -> 0.4268, 320 -> 0.4215, 384 -> 0.4295, 512 -> 0.4442; on 2 B200 256 and 512 are within
+    1 %.  Between 256 and the single-GPU chunk size, a multiple of 32."""
     if FORCE_CHUNK:
         return int(FORCE_CHUNK)
-    tiles = -(-wp // 64) * -(-hp // 8)
-    want_chunks = -(-148 * 16 * max(world, 1) // max(tiles, 1))
+    tiles = -(-wp // 32) * -(-hp // 8)
+    want_chunks = -(-148 * 16 * 5 * max(world, 1) // (3 * max(tiles, 1)))
     want = -(-max(total_points, 1) // want_chunks)
-    return int(min(_bl.chunk_points(), max(128, -(-want // 32) * 32)))
+    return int(min(_bl.chunk_points(), max(256, -(-want // 32) * 32)))
 
 
 class BandPlan:

@@ -98,6 +98,7 @@ typedef struct dgvcc_bl_layout {
     int64_t cshare;    /* [world*share_rows*rows] f32 symmetric layout: the per-CTA partial counts of every rank's band (dgvcc_bl_band_*) */
     int64_t ztick;     /* [B*tiles_img] u32 arrival counters per (image, pixel tile) of bl_z_kernel (zeroed by the forward pass) */
     int64_t gtick;     /* [B*tiles_img] u32 the same for bl_grad_kernel                */
+    int64_t queue;     /* [6] u32 work queues of the persistent sweeps (zeroed by the forward pass) */
     int32_t tiles;     /* partial-count rows (CTAs of 4 pixel tiles) per point chunk */
     int32_t rows_per_thread; /* kernel variant chosen for this shape: grid rows ...   */
     int32_t cols_per_thread; /* ... and columns owned by one thread                  */

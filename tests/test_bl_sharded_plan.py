@@ -131,7 +131,7 @@ def test_band_plan_tiles_the_grid_and_the_exchange_is_consistent(counts, world, 
     from dgvcc_b200.losses.bl_banded import BandPlan, band_chunk_points
     owners = (np.arange(len(counts)) * 7 + 3) % world
     chunk = band_chunk_points(int(np.sum(counts)), world, hp, wp)
-    assert 128 <= chunk <= 1024 and chunk % 32 == 0
+    assert 256 <= chunk <= 1024 and chunk % 32 == 0
     p = BandPlan(counts, True, world, owners, hp, wp, chunk)
     L, m4, P, b = p.layout, 4 * hp * wp, _native, len(counts)
     R = L.rows_per_thread

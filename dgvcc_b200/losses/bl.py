@@ -49,12 +49,34 @@ def chunk_points():
     return _CHUNK_POINTS
 
 
-def build_meta(counts, rows, chunk):
-    """The int32 table of include/dgvcc_b200.h: pt_off, row_off, keep, icb, chunks[C][4]."""
+def build_meta(counts, rows, chunk, tail_split=0):
+    """The int32 table of include/dgvcc_b200.h: pt_off, row_off, keep, icb, chunks[C][4].
+
+    ``tail_split`` > 1 (sharded sweeps, where a rank has only a round or two of warp tasks): the last quarter of every
+    image's chunks is cut into ``tail_split`` pieces each -- with the longest-first queue the sweep then ends on tasks a
+    fraction as long, for a few more partial arrays."""
     counts = np.asarray(counts, dtype=np.int64)
     rows = np.asarray(rows, dtype=np.int64)
     b = len(counts)
     n_chunks = np.maximum(1, -(-counts // chunk))
+    if tail_split and tail_split > 1:
+        img_l, start_l, cnt_l = [], [], []
+        for i in range(b):
+            n, nc = int(counts[i]), int(n_chunks[i])
+            edges = [n * k // nc for k in range(nc + 1)]
+            n_tail = nc // 4 if nc >= 4 else 0
+            for k in range(nc):
+                a, e = edges[k], edges[k + 1]
+                parts = tail_split if k >= nc - n_tail and e - a >= 32 * tail_split else 1
+                for q in range(parts):
+                    s0, s1 = a + (e - a) * q // parts, a + (e - a) * (q + 1) // parts
+                    img_l.append(i); start_l.append(s0); cnt_l.append(s1 - s0)
+        img = np.asarray(img_l, dtype=np.int64)
+        start, cnt = np.asarray(start_l, dtype=np.int64), np.asarray(cnt_l, dtype=np.int64)
+        n_chunks = np.bincount(img, minlength=b).astype(np.int64)
+        stop = start + cnt
+    else:
+        img = start = stop = None
     total_chunks = int(n_chunks.sum())
     meta = np.zeros(4 * b + 3 + 4 * total_chunks, dtype=np.int32)
     meta[1:b + 1] = np.cumsum(counts)
@@ -64,10 +86,11 @@ def build_meta(counts, rows, chunk):
     ends = np.cumsum(n_chunks)
     meta[3 * b + 3:4 * b + 3] = ends
     table = meta[4 * b + 3:].reshape(total_chunks, 4)
-    img = np.repeat(np.arange(b), n_chunks)
-    k = np.arange(total_chunks) - (ends - n_chunks)[img]      # chunk index inside its image
-    start = counts[img] * k // n_chunks[img]                   # near-equal slices
-    stop = counts[img] * (k + 1) // n_chunks[img]
+    if img is None:
+        img = np.repeat(np.arange(b), n_chunks)
+        k = np.arange(total_chunks) - (ends - n_chunks)[img]      # chunk index inside its image
+        start = counts[img] * k // n_chunks[img]                   # near-equal slices
+        stop = counts[img] * (k + 1) // n_chunks[img]
     table[:, 0], table[:, 1], table[:, 2] = img, start, stop - start
     # schedule: longest chunks first -- the sweeps hand the launch slots out through a work queue, so this is a
     # longest-processing-time schedule (the tail of a sweep is made of the shortest tasks)

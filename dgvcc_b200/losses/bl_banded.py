@@ -31,6 +31,7 @@ from . import bl as _bl
 from .bl_sharded import SLICE_BYTES, IpcComm, LocalComm, _PackedAll, plan_err_offset  # noqa: F401  (re-exported)
 
 FORCE_CHUNK = None   # experiments: points per chunk of the band plan, whatever the world size
+TAIL_SPLIT = 0       # experiments: cut the last quarter of every image's chunks into this many pieces (build_meta)
 
 
 def band_chunk_points(total_points, world, hp, wp):
@@ -63,7 +64,7 @@ class BandPlan:
         self.owners, self.counts = owners, counts
         self.rows = np.where(counts == 0, 1, counts + (1 if use_bg else 0))
         self.total_points, self.total_rows = int(counts.sum()), int(self.rows.sum())
-        self.meta, self.total_chunks, self.multi_chunk = _bl.build_meta(counts, self.rows, self.chunk)
+        self.meta, self.total_chunks, self.multi_chunk = _bl.build_meta(counts, self.rows, self.chunk, TAIL_SPLIT)
         self.owned = [np.nonzero(owners == r)[0] for r in range(world)]
         self.layout = _native.BLLayout()
         _native.check(_native.lib().dgvcc_bl_shard_workspace_layout(self.total_rows, self.total_chunks, b, hp, wp, world,
@@ -152,12 +153,12 @@ _plan_cache = {}
 def plan_bands(counts, use_bg, world, owners, hp, wp, chunk=None):
     """Cached ``BandPlan`` (forward and backward of one step share it; a benchmark hits it every step)."""
     key = (tuple(int(c) for c in counts), bool(use_bg), int(world), None if owners is None else tuple(int(o) for o in owners),
-           int(hp), int(wp), int(chunk or band_chunk_points(sum(int(c) for c in counts), world, hp, wp)))
+           int(hp), int(wp), int(chunk or band_chunk_points(sum(int(c) for c in counts), world, hp, wp)), int(TAIL_SPLIT))
     plan = _plan_cache.get(key)
     if plan is None:
         if len(_plan_cache) > 64:
             _plan_cache.clear()
-        plan = _plan_cache[key] = BandPlan(counts, use_bg, world, owners, hp, wp, key[-1])
+        plan = _plan_cache[key] = BandPlan(counts, use_bg, world, owners, hp, wp, key[-2])
     return plan
 
 

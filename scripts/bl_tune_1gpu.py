@@ -26,7 +26,7 @@ for cell in (64, 32):
 lib.dgvcc_bl_set_option(_native.BL_OPT_MIN_CELL, 64)
 # points per chunk: more, shorter warp tasks (less wave quantisation at the tail of a sweep, more per-task prologues)
 from dgvcc_b200.losses import bl as blmod  # noqa: E402
-for chunk in (1024, 928, 832, 768, 704, 640, 576, 512, 448, 384, 320, 256):
+for chunk in (1024, 512, 256):
     blmod._CHUNK_POINTS = chunk
     kernels, kept, packed = bench.kernel_breakdown(wl, dev, reps=8)
     print(json.dumps({"chunk_points": chunk, "chunks": int(packed.total_chunks), "path_ms": round(sum(kernels.values()), 4),

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--mode", default="chunk", choices=["chunk", "band"])
     ap.add_argument("--tiles", default="0", help="band mode: comma-separated pixel tiles to time (0 = by task count, 82, 81, 41, 21)")
     ap.add_argument("--min-cell", type=int, default=0, help="smallest cell of the minima's point grid (dgvcc_bl_set_option)")
+    ap.add_argument("--tail-splits", default="0", help="band mode: comma-separated tail_split values of build_meta to time")
     args = ap.parse_args()
     band = args.mode == "band"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -109,9 +110,11 @@ def main():
     if args.min_cell:
         _native.check(_native.lib().dgvcc_bl_set_option(_native.BL_OPT_MIN_CELL, args.min_cell), "dgvcc_bl_set_option")
     results = {}
-    sweep = [(tile, forced) for tile in ([int(t) for t in args.tiles.split(",")] if band else [0])
-             for forced in ([None if c == "auto" else int(c) for c in args.chunks.split(",")] if args.chunks else [None])]
-    for tile, forced in sweep:
+    sweep = [(tile, forced, ts) for tile in ([int(t) for t in args.tiles.split(",")] if band else [0])
+             for forced in ([None if c == "auto" else int(c) for c in args.chunks.split(",")] if args.chunks else [None])
+             for ts in ([int(t) for t in args.tail_splits.split(",")] if band else [0])]
+    for tile, forced, ts in sweep:
+        bl_banded.TAIL_SPLIT = ts
         _native.check(_native.lib().dgvcc_bl_set_option(_native.BL_OPT_BAND_TILE, tile), "dgvcc_bl_set_option")
         bl_banded._plan_cache.clear()
         # ---- timing: config 3, dense
@@ -168,7 +171,7 @@ def main():
         phases = [None] * world
         dist.all_gather_object(phases, acc)
         if rank == 0:
-            out = results.setdefault(f"{forced or 'auto'}" + (f"/tile{tile}" if tile else ""), {})
+            out = results.setdefault(f"{forced or 'auto'}" + (f"/tile{tile}" if tile else "") + (f"/tail{ts}" if ts else ""), {})
             out["phase_ms_rank0"] = {k: round(v, 4) for k, v in phases[0].items()}
             out["phase_ms_max_over_ranks"] = {k: round(max(p[k] for p in phases), 4) for k in phases[0]}
             out["phase_sum_ms_per_rank"] = [round(sum(p.values()), 4) for p in phases]

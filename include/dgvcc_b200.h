@@ -46,8 +46,10 @@ int dgvcc_abi_version(void);
  *                 chunks[C][4]  (image, first point, point count, chunk id to run
  *                               in launch slot c).  Chunks cut every image's points
  *                               into near-equal slices (an image without points has
- *                               one empty chunk) so that all warp tasks cost the same;
- *                               the last column is a schedule (big images first).
+ *                               one empty chunk) so that all warp tasks cost about the
+ *                               same; the last column is a schedule, longest chunks
+ *                               first: the sweeps are persistent launches that hand the
+ *                               (slot, pixel tile) items out through a work queue.
  *   st_sizes    [B] f32, density [B, hp, wp] f32 (pre_density with the channel
  *   dimension dropped), hp x wp = grid rows x columns, stride = pixels per cell.
  * total_chunks = C; multi_chunk = 1 when some image has more than one chunk.

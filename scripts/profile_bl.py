@@ -1,5 +1,5 @@
 """Two fused-BL steps on BASELINE config 3 (first = warm-up), dense sweep (what bench.py grades); run under ncu with
--k regex:bl_ -s 8 -c 8 (8 launches per step: grid build, minima, z, counts, row reduction, selection, grad, grad reduction)."""
+-k regex:bl_ -s 7 -c 7 (7 launches per step: grid build, minima, z, counts, row reduction, selection, grad)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

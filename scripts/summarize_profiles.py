@@ -108,7 +108,7 @@ if os.path.exists(rep):
                   os.path.join(out_dir, f"{tag}_aux_ncu_summary.md"), os.path.join(out_dir, f"{tag}_aux_ncu_raw.csv"))
     with open(os.path.join(out_dir, f"{tag}_bl_ncu_summary.md"), "w") as f:
         f.write(f"# ncu --set full, fused Bayesian loss, BASELINE config 3 ({tag})\n\n"
-                "`ncu --set full --clock-control none --import-source on -k regex:bl_ -s 8 -c 8 python scripts/profile_bl.py`\n"
+                "`ncu --set full --clock-control none --import-source on -k regex:bl_ -s 7 -c 7 python scripts/profile_bl.py`\n"
                 "(second step of two; 16 images, 192x256 grid, 49 697 heads).  Durations under ncu are cold-cache.\n\n")
         names = [d[idx["Kernel Name"]].split("(")[0].replace("void ", "") for d in data]
         f.write("| metric | " + " | ".join(f"`{n}`" for n in names) + " |\n|---|" + "---|" * len(names) + "\n")

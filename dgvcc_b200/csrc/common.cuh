@@ -23,6 +23,11 @@ struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(void* stream) {
         int cur = 0, want = 0;
+        // A stream that is being captured into a CUDA graph belongs to the current device (the capture was begun on it),
+        // and cudaStreamGetDevice is one of the calls a global-mode capture forbids: asking would invalidate the graph.
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing((cudaStream_t)stream, &capturing) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        if (capturing != cudaStreamCaptureStatusNone) return;
         if (cudaGetDevice(&cur) != cudaSuccess) return;
         if (cudaStreamGetDevice((cudaStream_t)stream, &want) != cudaSuccess) { (void)cudaGetLastError(); return; }
         if (want != cur && cudaSetDevice(want) == cudaSuccess) prev = cur;

@@ -209,6 +209,35 @@ def isw_lines(cpu, tf32_peak=None):
             if rep >= 2:
                 tm.append(e0.elapsed_time(e1))
         t_mod = float(np.mean(tm))
+        # the same step captured once as a CUDA graph and replayed (what it costs inside a graph-captured training step:
+        # the module is seven short kernels, eager launches leave gaps between them)
+        t_graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    xin.grad = None
+                    instance_whitening_loss(iw(xin)[1], eye, mask, 0, nrm).backward()
+            torch.cuda.current_stream().wait_stream(side)
+            xin.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                instance_whitening_loss(iw(xin)[1], eye, mask, 0, nrm).backward()
+            tg = []
+            for rep in range(8):
+                flush.zero_()
+                e0, e1 = ev(), ev()
+                e0.record()
+                graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                if rep >= 2:
+                    tg.append(e0.elapsed_time(e1))
+            t_graph = float(np.mean(tg))
+            del graph
+        except Exception as exc:  # keep the eager numbers
+            t_graph = f"{type(exc).__name__}: {exc}"
         # end to end: pinned host feature map in, loss + gradient out
         x_pin, g_pin = x_host.pin_memory(), torch.empty_like(x_host).pin_memory()
 
@@ -243,7 +272,8 @@ def isw_lines(cpu, tf32_peak=None):
                          "time / measured time")}
         line = {"workload": f"BASELINE config 5: ISW covariance loss, B={b} C={c} HW={hw} (fp32 in, 3xTF32 tensor cores)",
                 "metric": "steps/s (InstanceWhitening + instance_whitening_loss fwd+bwd)", "unit": "steps/s",
-                "value": 1e3 / t_mod, "ms_fwd_bwd": t_mod, "us_covariance": t_cov * 1e3, "roofline": roof,
+                "value": 1e3 / t_mod, "ms_fwd_bwd": t_mod, "ms_fwd_bwd_cuda_graph": t_graph, "us_covariance": t_cov * 1e3,
+                "roofline": roof,
                 "e2e": {"value": 1 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": x_host.numel() * 4 + 4}}
         if cpu:

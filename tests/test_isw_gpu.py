@@ -287,3 +287,48 @@ def test_non_binary_mask_takes_the_general_backward():
         lo.backward()
         torch.testing.assert_close(loss.cpu(), lo, rtol=1e-5, atol=1e-7)
         torch.testing.assert_close(xin.grad.cpu(), xo.grad, rtol=1e-4, atol=2e-6 * float(xo.grad.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 40, 40), (2, 256, 20, 24)])
+def test_module_step_replays_as_a_cuda_graph(shape):
+    """InstanceWhitening + instance_whitening_loss, forward and backward, captured ONCE with torch.cuda.graph and replayed
+    on new inputs: every launch goes to the capturing stream, nothing synchronises or allocates outside the graph's pool
+    after the warm-up -- so the ISW loss can sit inside a graph-captured training step (no launch gaps: what the module's
+    seven short kernels need).  Replayed results are bit-identical to eager ones (the kernels are deterministic)."""
+    from dgvcc_b200.models.ISW import InstanceWhitening, instance_whitening_loss
+    dev = torch.device("cuda:0")
+    b, c, h, w = shape
+    gen = torch.Generator().manual_seed(77)
+    xs = [torch.randn(b, c, h, w, generator=gen).to(dev) for _ in range(3)]
+    mask = (torch.rand(c, c, generator=gen) < 0.5).float().triu(1).to(dev)
+    eye, nrm = torch.eye(c, device=dev), mask.sum()
+    iw = InstanceWhitening(c)
+
+    def step(x):
+        _, wt = iw(x)
+        loss = instance_whitening_loss(wt, eye, mask, 0, nrm)
+        loss.backward()
+        return loss
+
+    eager = []
+    for x in xs:
+        xe = x.clone().requires_grad_(True)
+        eager.append((step(xe).detach().clone(), xe.grad.clone()))
+    static = xs[0].clone().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):            # warm-up on a side stream, as torch's graph recipe asks
+        for _ in range(2):
+            static.grad = None
+            step(static)
+    torch.cuda.current_stream().wait_stream(side)
+    static.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_loss = step(static)
+    for x, (l_ref, g_ref) in zip(xs, eager):
+        with torch.no_grad():
+            static.copy_(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_loss.detach(), l_ref) and torch.equal(static.grad, g_ref)

@@ -571,9 +571,12 @@ extern "C" int dgvcc_isw_instnorm_forward(const float* x, int planes, int hw, fl
     if (!x || !y || !mean || !invstd || planes <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     const size_t smem = (size_t)hw * sizeof(float);
     const bool fits = smem <= 200 * 1024;
-    if (fits && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(isw_instnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+    if (fits && smem > 48 * 1024) {  // opt in once per device to the largest plane the kernel caches (not per call: the
+                                     // call is not allowed while a stream is being captured into a CUDA graph)
+        static PerDeviceOnce once;
+        if (once.first())
+            DGVCC_RETURN_IF_CUDA(cudaFuncSetAttribute(isw_instnorm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      200 * 1024));
     }
     // gridDim.y == 2 tells the kernel the plane is not cached (only y-block 0 writes)
     isw_instnorm_fwd_kernel<<<dim3(planes, fits ? 1 : 2), NORM_THREADS, fits ? smem : 0, (cudaStream_t)stream>>>(

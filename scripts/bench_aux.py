@@ -213,17 +213,18 @@ def isw_lines(cpu, tf32_peak=None):
         # the module is seven short kernels, eager launches leave gaps between them)
         t_graph = None
         try:
+            xg = x_host.to(dev).requires_grad_(True)   # a fresh leaf: its gradient accumulator is born on the side stream
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    xin.grad = None
-                    instance_whitening_loss(iw(xin)[1], eye, mask, 0, nrm).backward()
+                    xg.grad = None
+                    instance_whitening_loss(iw(xg)[1], eye, mask, 0, nrm).backward()
             torch.cuda.current_stream().wait_stream(side)
-            xin.grad = None
+            xg.grad = None
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                instance_whitening_loss(iw(xin)[1], eye, mask, 0, nrm).backward()
+                instance_whitening_loss(iw(xg)[1], eye, mask, 0, nrm).backward()
             tg = []
             for rep in range(8):
                 flush.zero_()
@@ -235,7 +236,7 @@ def isw_lines(cpu, tf32_peak=None):
                 if rep >= 2:
                     tg.append(e0.elapsed_time(e1))
             t_graph = float(np.mean(tg))
-            del graph
+            del graph, xg
         except Exception as exc:  # keep the eager numbers
             t_graph = f"{type(exc).__name__}: {exc}"
         # end to end: pinned host feature map in, loss + gradient out

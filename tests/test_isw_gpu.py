@@ -289,7 +289,7 @@ def test_non_binary_mask_takes_the_general_backward():
         torch.testing.assert_close(xin.grad.cpu(), xo.grad, rtol=1e-4, atol=2e-6 * float(xo.grad.abs().max()))
 
 
-@pytest.mark.parametrize("shape", [(4, 64, 40, 40), (2, 256, 20, 24)])
+@pytest.mark.parametrize("shape", [(4, 64, 40, 40), (2, 256, 20, 24), (8, 64, 160, 160)])
 def test_module_step_replays_as_a_cuda_graph(shape):
     """InstanceWhitening + instance_whitening_loss, forward and backward, captured ONCE with torch.cuda.graph and replayed
     on new inputs: every launch goes to the capturing stream, nothing synchronises or allocates outside the graph's pool

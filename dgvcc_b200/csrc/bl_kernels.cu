@@ -349,6 +349,65 @@ __device__ __forceinline__ int stage_points_if(WarpTile<R>& tile, const float2* 
     return kept;
 }
 
+// Register prefetch of the NEXT tile of points (and weights): issued right after the current tile is staged, so the
+// loads fly under the exponential loop.  Used by the small pixel tiles (R*C < 16), which have registers to spare and are
+// what a rank of a sharded sweep runs: with about one task per resident warp the warps of an SM move through
+// staging in step, and nobody else hides the round trip.  Indices are clamped like stage_points pads.
+constexpr int PF = TILE_PTS / 32;
+template <bool HAS_W>
+__device__ __forceinline__ void fetch_points(const float2* __restrict__ pts, const float* __restrict__ w, int n0, int limit,
+                                             float2 (&p)[PF], float (&wv)[PF]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        const int n = min(n0 + 32 * u + lane, limit - 1);
+        p[u] = __ldg(&pts[n]);
+        if (HAS_W) wv[u] = __ldg(&w[n]);
+    }
+}
+
+// stage_points from prefetched registers.
+template <int R>
+__device__ __forceinline__ void stage_fetched(WarpTile<R>& tile, const float2 (&p)[PF], int padded, const float (&cym2)[R],
+                                              const float (&cyy)[R]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        const int i = 32 * u + lane;
+        if (i < padded) {
+            tile.xs[i] = make_float2(p[u].x, __fmul_rn(p[u].x, p[u].x));
+            const float yy = __fmul_rn(p[u].y, p[u].y);
+#pragma unroll
+            for (int r = 0; r < R; ++r) tile.yd[i][r] = axis_sqdist(p[u].y, yy, cym2[r], cyy[r]);
+        }
+    }
+}
+
+// stage_points_if<R, true, false> from prefetched registers (weights in tile.aux, ordered compaction).
+template <int R, typename Keep>
+__device__ __forceinline__ int stage_fetched_if(WarpTile<R>& tile, const float2 (&p)[PF], const float (&wv)[PF], int cnt,
+                                                const float (&cym2)[R], const float (&cyy)[R], Keep keep_fn) {
+    const int lane = threadIdx.x & 31;
+    int kept = 0;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        if (32 * u >= cnt) break;  // warp-uniform
+        const int i = 32 * u + lane;
+        const bool keep = i < cnt && keep_fn(p[u].x, p[u].y, wv[u]);
+        const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
+        if (keep) {
+            const int pos = kept + __popc(ballot & ((1u << lane) - 1u));
+            tile.xs[pos] = make_float2(p[u].x, __fmul_rn(p[u].x, p[u].x));
+            const float yy = __fmul_rn(p[u].y, p[u].y);
+#pragma unroll
+            for (int r = 0; r < R; ++r) tile.yd[pos][r] = axis_sqdist(p[u].y, yy, cym2[r], cyy[r]);
+            tile.aux[pos] = wv[u];
+        }
+        kept += __popc(ballot);
+    }
+    return kept;
+}
+
 // Conservative lower bound of the reference's fp32 squared distance dis[n, pixel] over every pixel
 // of a warp's tile, from the point's distance to the rectangle of the tile's cell centres.  The slack
 // covers (i) the rounding of this bound itself and (ii) the error of the reference's cancelling
@@ -830,6 +889,10 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
         return false;
     }
     const float2* pts = pts_all + t.pt_base;
+    constexpr bool PREFETCH = R * C < 16;
+    float2 pf[PF];
+    float pw[PF];
+    if (PREFETCH && !exact_cull && t.p_cnt > 0) fetch_points<false>(pts, nullptr, 0, t.p_cnt, pf, pw);  // under the prologue
 
     float neg_amax[R][C];  // first holds min dis, then k2 = -amax * log2(e)
     {  // bl_gridmin_kernel has been over the image
@@ -881,7 +944,10 @@ __device__ __forceinline__ bool bl_z_body(const float2* __restrict__ pts_all, co
         if (exact_cull)
             cnt = stage_points_if<R, false, false>(tile, pts, nullptr, n0, cnt, px.cym2, px.cyy,
                                                    [&](float x, float y, float) { return cull.keep(x, y); });
-        else
+        else if (PREFETCH) {
+            stage_fetched<R>(tile, pf, cnt, px.cym2, px.cyy);
+            if (n0 + TILE_PTS < t.p_cnt) fetch_points<false>(pts, nullptr, n0 + TILE_PTS, t.p_cnt, pf, pw);
+        } else
             stage_points<R>(tile, pts, n0, t.p_cnt, cnt, px.cym2, px.cyy);
         __syncwarp();
 #pragma unroll 2
@@ -1044,6 +1110,10 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
             k2p[q][c] = pack2(neg_amax[2 * q][c], neg_amax[2 * q + 1][c]);
             wdp[q][c] = pack2(wd[2 * q][c], wd[2 * q + 1][c]);
         }
+    constexpr bool PREFETCH = R * C < 16;
+    float2 pf[PF];
+    float pw[PF];
+    if (PREFETCH && live && !exact_cull && t.p_cnt > 0) fetch_points<false>(pts, nullptr, 0, t.p_cnt, pf, pw);
     for (int span0 = 0; span0 < t.p_cnt; span0 += COUNT_SPAN) {
         const int span_cnt = min(COUNT_SPAN, t.p_cnt - span0);
         if (!live)
@@ -1064,6 +1134,9 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
 #pragma unroll
                     for (int r = 0; r < R; ++r) tile.yd[i][r] = tile.yd[kept - 1][r];
                 }
+            } else if (PREFETCH) {
+                stage_fetched<R>(tile, pf, (cnt + 7) & ~7, px.cym2, px.cyy);
+                if (n0 + TILE_PTS < t.p_cnt) fetch_points<false>(pts, nullptr, n0 + TILE_PTS, t.p_cnt, pf, pw);
             } else {
                 stage_points<R>(tile, pts, n0, t.p_cnt, (cnt + 7) & ~7, px.cym2, px.cyy);
             }
@@ -1381,12 +1454,23 @@ __device__ __forceinline__ bool bl_grad_body(const float2* __restrict__ pts_all,
             accp[q][c] = pack2(0.f, 0.f);
             k2p[q][c] = pack2(neg_amax[2 * q][c], neg_amax[2 * q + 1][c]);
         }
+    constexpr bool PREFETCH = R * C < 16;
+    float2 pf[PF];
+    float pw[PF];
+    if (PREFETCH && t.p_cnt > 0) fetch_points<true>(pts, w_pts, 0, t.p_cnt, pf, pw);
     for (int n0 = 0; n0 < t.p_cnt; n0 += TILE_PTS) {
         const int cnt = min(TILE_PTS, t.p_cnt - n0);
         __syncwarp();
-        const int kept = stage_points_if<R, true, false>(
-            tile, pts, w_pts, n0, cnt, px.cym2, px.cyy,
-            [&](float x, float y, float w) { return w != 0.f && cull.keep(x, y); });
+        int kept;
+        if (PREFETCH) {
+            kept = stage_fetched_if<R>(tile, pf, pw, cnt, px.cym2, px.cyy,
+                                       [&](float x, float y, float w) { return w != 0.f && cull.keep(x, y); });
+            if (n0 + TILE_PTS < t.p_cnt) fetch_points<true>(pts, w_pts, n0 + TILE_PTS, t.p_cnt, pf, pw);
+        } else {
+            kept = stage_points_if<R, true, false>(
+                tile, pts, w_pts, n0, cnt, px.cym2, px.cyy,
+                [&](float x, float y, float w) { return w != 0.f && cull.keep(x, y); });
+        }
         __syncwarp();
 #pragma unroll 2
         for (int i = 0; i < kept; ++i) {

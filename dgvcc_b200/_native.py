@@ -57,6 +57,7 @@ DEN_META_COLS = 8    # DGVCC_DEN_META_COLS
 # name -> (restype, argtypes); every symbol include/dgvcc_b200.h declares must appear here
 SIGNATURES = {
     "dgvcc_abi_version": (c_int, []),
+    "dgvcc_bounds_checked": (c_int, []),
     "dgvcc_bl_workspace_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(BLLayout)]),
     "dgvcc_bl_set_option": (c_int, [c_int, c_int]),
     "dgvcc_bl_pack_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, POINTER(BLPacked)]),
@@ -150,7 +151,8 @@ SIGNATURES = {
 
 
 def lib():
-    """The loaded shared library (built on first use if stale or missing)."""
+    """The loaded shared library (built on first use if stale or missing).  With DGVCC_BOUNDS_CHECK=1 in the
+    environment it is the checked variant (libdgvcc_b200_chk.so: device-side index checks, see build.py)."""
     global _lib
     if _lib is None:
         with _lock:

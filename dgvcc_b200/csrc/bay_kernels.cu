@@ -124,6 +124,7 @@ bay_crop_targets_kernel(const typename Vec2<T>::type* __restrict__ gt, const T* 
         }
         if (keep) {
             const int pos = before + __popc(ballot & ((1u << lane) - 1u));
+            DGVCC_DEV_CHECK(pos >= 0 && pos < n);
             const double x = (double)p.x - c_left;   // gt - [j, i]
             gt_out[2 * pos] = w - x;                 // gt[:, 0] = w - gt[:, 0]   (bay_dataset.py:104-105)
             gt_out[2 * pos + 1] = (double)p.y - c_up;

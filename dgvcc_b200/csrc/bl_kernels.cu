@@ -224,6 +224,7 @@ __device__ __forceinline__ void xchg_wait(const Xchg& x) {
 
 // Base of an exchanged array on rank q.
 __device__ __forceinline__ float* xchg_ptr(const Xchg& x, int q, long long region_off) {
+    DGVCC_DEV_CHECK(q >= 0 && q < x.world && region_off >= 0);
     return reinterpret_cast<float*>(x.peers[q] + region_off);
 }
 
@@ -232,6 +233,7 @@ __device__ __forceinline__ void xchg_store(const Xchg& x, unsigned int mask, lon
     while (mask) {
         const int q = __ffs(mask) - 1;
         mask &= mask - 1u;
+        DGVCC_DEV_CHECK(q < x.world && region_off >= 0);
         reinterpret_cast<float*>(x.peers[q] + region_off)[elem] = v;
     }
 }
@@ -293,6 +295,12 @@ __device__ __forceinline__ bool decode_task(const int32_t* __restrict__ meta, in
     const int jb = t.task % g.col_blocks, kb = t.task / g.col_blocks;
     t.col0 = jb * 32 * C + lane;
     t.row_base = kb * R;
+    DGVCC_DEV_CHECK(slot >= 0 && task >= 0 && t.chunk >= 0);
+    DGVCC_DEV_CHECK(t.img >= 0 && t.img < batch);
+    DGVCC_DEV_CHECK(t.chunk >= t.first_chunk && t.chunk < t.first_chunk + max(t.n_chunks, 1));
+    DGVCC_DEV_CHECK(t.p_start >= 0 && t.p_cnt >= 0 && t.p_start + t.p_cnt <= t.n_img_pts);
+    DGVCC_DEV_CHECK(t.n_rows >= t.n_img_pts && t.n_rows <= t.n_img_pts + 1 && t.row0 >= 0 && pt0 >= 0);
+    DGVCC_DEV_CHECK(t.task >= g.tiles || t.row_base < g.hp);
     return t.task < g.tiles;  // the chunk fields are valid either way (all warps of a CTA share the chunk)
 }
 
@@ -306,6 +314,7 @@ __device__ __forceinline__ void stage_points(WarpTile<R>& tile, const float2* __
 #pragma unroll 1
     for (int i = lane; i < padded; i += 32) {
         const int n = min(n0 + i, limit - 1);
+        DGVCC_DEV_CHECK(n >= 0 && i < TILE_PTS);
         const float2 p = __ldg(&pts[n]);
         tile.xs[i] = make_float2(p.x, __fmul_rn(p.x, p.x));
         const float yy = __fmul_rn(p.y, p.y);
@@ -337,6 +346,7 @@ __device__ __forceinline__ int stage_points_if(WarpTile<R>& tile, const float2* 
         const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
         if (keep) {
             const int pos = kept + __popc(ballot & ((1u << lane) - 1u));
+            DGVCC_DEV_CHECK(pos >= 0 && pos < TILE_PTS && n0 + i >= 0);
             tile.xs[pos] = make_float2(p.x, __fmul_rn(p.x, p.x));
             const float yy = __fmul_rn(p.y, p.y);
 #pragma unroll
@@ -361,6 +371,7 @@ __device__ __forceinline__ void fetch_points(const float2* __restrict__ pts, con
 #pragma unroll
     for (int u = 0; u < PF; ++u) {
         const int n = min(n0 + 32 * u + lane, limit - 1);
+        DGVCC_DEV_CHECK(n >= 0);
         p[u] = __ldg(&pts[n]);
         if (HAS_W) wv[u] = __ldg(&w[n]);
     }
@@ -397,6 +408,7 @@ __device__ __forceinline__ int stage_fetched_if(WarpTile<R>& tile, const float2 
         const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
         if (keep) {
             const int pos = kept + __popc(ballot & ((1u << lane) - 1u));
+            DGVCC_DEV_CHECK(pos >= 0 && pos < TILE_PTS);
             tile.xs[pos] = make_float2(p[u].x, __fmul_rn(p[u].x, p[u].x));
             const float yy = __fmul_rn(p[u].y, p[u].y);
 #pragma unroll
@@ -482,7 +494,10 @@ struct PixelTile {
         box.y0 = cell_centre(t.row_base, g);
         box.y1 = cell_centre(min(t.row_base + R - 1, g.hp - 1), g);
     }
-    __device__ __forceinline__ int pix(int r, int c) const { return min(row_base + r, hp - 1) * wp + col[c]; }
+    __device__ __forceinline__ int pix(int r, int c) const {
+        DGVCC_DEV_CHECK(row_base >= 0 && col[c] >= 0 && col[c] < wp);
+        return min(row_base + r, hp - 1) * wp + col[c];
+    }
     __device__ __forceinline__ bool ok(int r, int c) const { return row_base + r < hp && col0 + 32 * c < wp; }
 };
 
@@ -559,6 +574,8 @@ bl_grid_build_kernel(const float2* __restrict__ pts_all, const int32_t* __restri
     if (blockIdx.x == 0 && tid < 6) queue[tid] = 0u;   // the work queues of the persistent sweeps
     const Meta mv = meta_view(meta, batch);
     const int pt0 = mv.pt_off[img], n = mv.pt_off[img + 1] - pt0;
+    DGVCC_DEV_CHECK(img >= 0 && img < batch && pt0 >= 0 && n >= 0);
+    DGVCC_DEV_CHECK(gg.gx >= 1 && gg.gy >= 1 && gg.gx * gg.gy <= GRID_MAX_CELLS);
     if (n == 0) return;
     const float2* pts = pts_all + pt0;
 #pragma unroll
@@ -608,7 +625,9 @@ bl_grid_build_kernel(const float2* __restrict__ pts_all, const int32_t* __restri
     float2* out = gsorted + pt0;
     for (int i = tid; i < n; i += 1024) {
         const float2 p = __ldg(pts + i);
-        out[atomicAdd(&hist[grid_cell_1d(p.y, gg.inv_cell, gg.gy) * gg.gx + grid_cell_1d(p.x, gg.inv_cell, gg.gx)], 1)] = p;
+        const int slot = atomicAdd(&hist[grid_cell_1d(p.y, gg.inv_cell, gg.gy) * gg.gx + grid_cell_1d(p.x, gg.inv_cell, gg.gx)], 1);
+        DGVCC_DEV_CHECK(slot >= 0 && slot < n);
+        out[slot] = p;
     }
 }
 
@@ -689,8 +708,10 @@ bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict_
                     else if (right) c0 = c1 = jr * gg.gx + cx1 + d;
                 }
                 if (c0 >= 0) {
+                    DGVCC_DEV_CHECK(c0 <= c1 && c1 < gg.gx * gg.gy && c1 < GRID_MAX_CELLS);
                     first = __ldg(off + c0);
                     count = __ldg(off + c1 + 1) - first;
+                    DGVCC_DEV_CHECK(first >= 0 && count >= 0 && first + count <= n);
                 }
             }
             int incl = count;   // prefix sums of the runs' lengths across the lanes
@@ -720,6 +741,7 @@ bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict_
                     }
                     const int r_first = __shfl_sync(FULL_MASK, first, lo), r_excl = __shfl_sync(FULL_MASK, excl, lo);
                     pq[u] = make_float2(0.f, 0.f);
+                    DGVCC_DEV_CHECK(gi >= total || (gi >= r_excl && r_first + (gi - r_excl) < n));
                     if (gi < total) pq[u] = __ldg(sp + r_first + (gi - r_excl));
                 }
 #pragma unroll
@@ -731,6 +753,7 @@ bl_gridmin_kernel(const float2* __restrict__ gsorted, const int32_t* __restrict_
                     const unsigned int ballot = __ballot_sync(FULL_MASK, keep);
                     if (keep) {
                         const int pos = staged + __popc(ballot & ((1u << lane) - 1u));
+                        DGVCC_DEV_CHECK(pos >= 0 && pos < TILE_PTS);
                         tile.xs[pos] = make_float2(p.x, __fmul_rn(p.x, p.x));
                         const float yy = __fmul_rn(p.y, p.y);
 #pragma unroll
@@ -783,6 +806,7 @@ __device__ __forceinline__ bool tile_last_arrival(unsigned int* counter, int n_c
     unsigned int old = 0u;
     if ((threadIdx.x & 31) == 0) old = atomicAdd(counter, 1u);
     old = __shfl_sync(FULL_MASK, old, 0);
+    DGVCC_DEV_CHECK(n_chunks >= 1 && old < (unsigned)n_chunks);   // a counter left over from a step that was cut short
     const bool last = old == (unsigned)n_chunks - 1u;
     if (last) {
         if ((threadIdx.x & 31) == 0) *counter = 0u;
@@ -1072,6 +1096,7 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
     PixelTile<R, C> px;
     px.init(t, g);
     const size_t part0 = (size_t)(max(share_row0, 0) + cta_x) * total_rows + t.row0;
+    DGVCC_DEV_CHECK(cta_x >= 0 && t.row0 + t.n_rows <= total_rows && t.p_start + t.p_cnt <= t.n_rows);
     const bool bg_row = t.chunk == t.first_chunk && (use_bg || t.n_img_pts == 0);  // the image's first chunk anywhere
 
     // per-pixel weights D[m]/Z[m]; pixels outside the grid get weight 0
@@ -1178,6 +1203,8 @@ bl_counts_kernel(const float2* __restrict__ pts_all, const int32_t* __restrict__
                 v[0] += __shfl_xor_sync(FULL_MASK, v[0], 1);
                 if ((lane & 3) == 0) {
                     const int q = i0 + (lane >> 2);
+                    DGVCC_DEV_CHECK(n0 - span0 >= 0 && n0 - span0 + cnt <= COUNT_SPAN && q < TILE_PTS);
+                    DGVCC_DEV_CHECK(!exact_cull || q >= kept || (int)tile.idx[q] < cnt);
                     if (!exact_cull) { if (q < cnt) acc_w[q] = v[0]; }
                     else if (q < kept) acc_w[tile.idx[q]] = v[0];
                 }
@@ -1243,6 +1270,7 @@ __device__ __forceinline__ bool bl_reduce_counts_body(const float* __restrict__ 
     }
     const int local = (int)(j - mv.row_off[lo]);
     const int n_pts = mv.pt_off[lo + 1] - mv.pt_off[lo];
+    DGVCC_DEV_CHECK(j >= 0 && local >= 0 && j < mv.row_off[lo + 1] && local <= n_pts && tiles >= 1);
     if (sh.on) {  // only rows whose partials this rank computed: its own points; the last row with the image's first chunk
         const int gp = mv.pt_off[lo] + local;
         const bool mine = local < n_pts ? (gp >= sh.pt_lo && gp < sh.pt_hi)
@@ -1287,6 +1315,7 @@ bl_select_kernel(const int32_t* __restrict__ meta, const float* __restrict__ tar
     const int row0 = mv.row_off[img], n_rows = mv.row_off[img + 1] - row0;
     const int n_cand = n_rows - 1;  // res[:-1]; the last row is always kept (bl.py:77-78)
     const int n_keep = mv.keep[img];
+    DGVCC_DEV_CHECK(img >= 0 && img < batch && n_rows >= 1 && n_pts >= 0 && n_pts <= n_rows && n_keep <= max(n_cand, 0));
 
     // k-th smallest residual among the candidates: MSB-first radix select on the float bits
     unsigned int thr = 0xffffffffu;  // keep everything
@@ -1967,6 +1996,7 @@ using namespace dgvcc;
 using namespace dgvcc::bl;
 
 extern "C" int dgvcc_abi_version(void) { return 9; }
+extern "C" int dgvcc_bounds_checked(void) { return DGVCC_BOUNDS_CHECKED; }
 
 extern "C" int dgvcc_bl_workspace_layout(int64_t total_rows, int total_chunks, int batch, int hp, int wp,
                                          dgvcc_bl_layout* out) {

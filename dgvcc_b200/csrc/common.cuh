@@ -14,6 +14,24 @@
         if (_e != cudaSuccess) return (int)_e; \
     } while (0)
 
+// Checked build (`DGVCC_BOUNDS_CHECK=1 python -m dgvcc_b200.build`, nvcc -DDGVCC_BOUNDS_CHECK; loaded instead of the
+// product library when the same variable is set at import): every index that comes out of a host-built table or a
+// data-dependent computation is tested where it is used; a violation is a device-side assert (site, block, thread
+// and condition are reported, the launch fails with cudaErrorAssert) instead of silent memory corruption.
+// compute-sanitizer is closed on the GPU pool this was built on -- this is its substitute.  The product build
+// compiles every check away (the condition is not evaluated; `cuobjdump -sass` of the objects is identical with and
+// without the DGVCC_DEV_CHECK lines).
+#ifdef DGVCC_BOUNDS_CHECK
+#undef NDEBUG
+#include <assert.h>
+// device-side assert: the runtime reports file, line, block, thread and the condition when the context is torn down
+#define DGVCC_DEV_CHECK(cond) assert(cond)
+#define DGVCC_BOUNDS_CHECKED 1
+#else
+#define DGVCC_DEV_CHECK(cond) ((void)0)
+#define DGVCC_BOUNDS_CHECKED 0
+#endif
+
 namespace dgvcc {
 
 // Every launcher runs on the device that owns the caller's stream, whatever the calling thread's current

@@ -39,6 +39,7 @@ den_train_targets_kernel(const float* __restrict__ maps, const int64_t* __restri
             }
         }
         const int tx = m[M_FLIP] ? dw - 1 - ox : ox;  // F.hflip, den_cls_dataset.py:144
+        DGVCC_DEV_CHECK(m[M_SRC] >= 0 && height > 0 && width > 0 && d >= 1 && tx >= 0 && tx < dw);
         out_dmap[((size_t)blockIdx.z * dh + oy) * dw + tx] = sum;
     }
     if (!out_bmap) return;  // uniform

@@ -684,6 +684,7 @@ dmap_coarse_kernel(const int4* __restrict__ boxes, const int64_t* __restrict__ m
     const int nchunks = ceil_div(n, CHUNK), ctx = ceil_div(width, COARSE);
     const int local = blockIdx.x - (int)m[M_CTASK_OFF];
     const int chunk = local % nchunks, ct = local / nchunks;
+    DGVCC_DEV_CHECK(img >= 0 && img < n_images && n > 0 && local >= 0 && ct < ctx * ceil_div((int)m[M_H], COARSE));
     const int x0 = (ct % ctx) * COARSE, y0 = (ct / ctx) * COARSE;
     const int4* b = boxes + m[M_PT_OFF];
     int32_t* cnt_row = ccount + m[M_CTASK_OFF] + (size_t)ct * nchunks;
@@ -703,6 +704,7 @@ dmap_coarse_kernel(const int4* __restrict__ boxes, const int64_t* __restrict__ m
         const int slot = cta_compact<COARSE_THREADS>(hit, warp_cnt, total);
         // PACKED (fixed sigma, identical stamps): the list carries the stamp's centre pixel (row << 16 | column) instead
         // of the head index -- the fine pass needs nothing else and saves the dependent loads through the index
+        DGVCC_DEV_CHECK(!(WRITE && hit) || (pos + count + slot >= 0 && pos + count + slot < n));
         if (WRITE && hit) out[pos + count + slot] = PACKED ? (int)(((unsigned)((bi.z + bi.w) >> 1) << 16) | (unsigned)((bi.x + bi.y) >> 1)) : i;
         count += total;
     }
@@ -742,6 +744,7 @@ dmap_tile_setup_kernel(const int64_t* __restrict__ meta, int n_images, int fine_
     d.n = (int)m[M_N]; d.height = (int)m[M_H]; d.width = (int)m[M_W];
     const int ftx = ceil_div(d.width, FINE_W);
     const int local = t - (int)m[M_FTILE_OFF];
+    DGVCC_DEV_CHECK(img >= 0 && img < n_images && local >= 0 && local < ftx * ceil_div(d.height, FINE_H));
     d.x0 = (local % ftx) * FINE_W; d.y0 = (local / ftx) * FINE_H;
     d.pt_off = m[M_PT_OFF]; d.out_off = m[M_OUT_OFF];
     d.cnt = 0; d.clist_off = 0; d.pad0_ = d.pad1_ = 0; d.pad2_ = 0;
@@ -779,6 +782,7 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
     const int x0 = d0.x, y0 = d0.y, width = d0.z, height = d0.w, cnt = d1.x;
     const int yb = y0 + SPLAT_RPT * warp;  // first row of this warp's band
     const int x = x0 + lane;
+    DGVCC_DEV_CHECK(x0 >= 0 && y0 >= 0 && x0 < width && y0 < height && cnt >= 0 && d2.x >= 0 && d2.y >= 0);
     float acc[SPLAT_RPT];  // pixels (yb + k, x)
 #pragma unroll
     for (int k = 0; k < SPLAT_RPT; ++k) acc[k] = 0.f;
@@ -795,6 +799,7 @@ dmap_splat_kernel(const Stamp* __restrict__ stamps, const double* __restrict__ w
             bool hit = false;
             if (base + tid < cnt) {
                 i = __ldg(cl + base + tid);
+                DGVCC_DEV_CHECK(i >= 0);
                 b = __ldg(bx + i);
                 hit = box_hits(b, x0, y0, FINE_W, FINE_H);
             }
@@ -979,6 +984,7 @@ dmap_splat_fixed_kernel(const TileDesc* __restrict__ desc, int fine_tiles, const
     const longlong2 d2 = __ldg(reinterpret_cast<const longlong2*>(dp + 2));
     const int x0 = d0.x, y0 = d0.y, width = d0.z, height = d0.w, cnt = d1.x;
     const int x = x0 + lane;
+    DGVCC_DEV_CHECK(x0 >= 0 && y0 >= 0 && x0 < width && y0 < height && cnt >= 0 && d2.x >= 0 && d2.y >= 0);
     float* out = density + d2.x + (size_t)y0 * width + x;
     const int rows = min(FINE_H, height - y0);
     if (cnt == 0) {  // no stamp touches the tile
@@ -1033,6 +1039,7 @@ dmap_splat_fixed_kernel(const TileDesc* __restrict__ desc, int fine_tiles, const
             for (int k = 0; k < FAST_STEPS; ++k) {   // 32 different pixels per step; those beyond the apron are nobody's
                 in[k] = (unsigned)(ay + (dxy[k] >> 8)) < (unsigned)FAST_APRON && (unsigned)(ax + (dxy[k] & 255)) < (unsigned)FAST_APRON &&
                         (k < FAST_STEPS - 1 || lane == 0);   // the last step holds pixel 224 only
+                DGVCC_DEV_CHECK(!in[k] || (a + off[k] >= tile && a + off[k] < tile + FAST_TILE_FLOATS));
                 v[k] = in[k] ? a[off[k]] : 0.f;
             }
 #pragma unroll

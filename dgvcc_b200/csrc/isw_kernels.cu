@@ -478,6 +478,7 @@ isw_topk_mask_kernel(const float* __restrict__ stats, int n_stats, float count, 
                     if (cum + (int)hist[b] >= remaining) { digit = b; break; }
                     cum += (int)hist[b];
                 }
+                DGVCC_DEV_CHECK(remaining - cum >= 1 && remaining - cum <= (int)hist[digit]);   // the k-th key exists
                 s_prefix = prefix | ((unsigned)digit << shift);
                 s_remaining = remaining - cum;
             }

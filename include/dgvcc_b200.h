@@ -28,6 +28,12 @@ extern "C" {
 /* ABI version; bumped when a signature changes. */
 int dgvcc_abi_version(void);
 
+/* 1 when the library was built with -DDGVCC_BOUNDS_CHECK (`DGVCC_BOUNDS_CHECK=1 python -m dgvcc_b200.build`): every
+ * kernel then tests the indices it takes from host-built tables and data-dependent computations and traps on a
+ * violation (the stand-in for compute-sanitizer, see csrc/common.cuh).  0 for the product build, whose device code
+ * does not contain the checks.  No reference counterpart (the reference has no native code). */
+int dgvcc_bounds_checked(void);
+
 /* ---------------------------------------------------------------------------
  * Bayesian loss -- replaces losses/bl.py:20-52 (Post_Prob.forward),
  * losses/bl.py:60-80 (Bay_Loss.forward) and the autograd backward of

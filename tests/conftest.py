@@ -20,6 +20,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_report_header(config):
+    """Which library the suite runs through: the product build, or the checked one (DGVCC_BOUNDS_CHECK=1)."""
+    try:
+        from dgvcc_b200 import _native
+        lib = _native.lib()
+        return f"dgvcc library: {lib._name} (device-side index checks: {'ON' if lib.dgvcc_bounds_checked() else 'off'})"
+    except Exception as exc:   # the tests themselves will say why
+        return f"dgvcc library: not loadable ({type(exc).__name__}: {exc})"
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

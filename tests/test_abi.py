@@ -71,3 +71,25 @@ def test_native_host_packing_matches_the_python_packing():
         buf = torch.zeros((info.total_bytes,), dtype=torch.uint8)
         bl.pack_host_native(pts, tgt, use_bg, chunk, buf.data_ptr(), buf.numel(), args)
         assert torch.equal(buf, ref.buf), counts
+
+
+def test_checked_variant_builds_beside_the_product_library():
+    """`DGVCC_BOUNDS_CHECK=1` selects libdgvcc_b200_chk.so: same exports, device-side index checks compiled in
+    (csrc/common.cuh); the product library reports 0 and carries no assert call."""
+    import ctypes
+    import subprocess
+    from dgvcc_b200 import build
+    product = _native.lib()
+    assert product.dgvcc_bounds_checked() == 0
+    path = build.build(checked=True)          # a no-op when __graft_entry__.build() has been run
+    assert path.endswith("libdgvcc_b200_chk.so") and path != product._name
+    chk = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(chk, name), f"{name} missing from the checked variant"
+    assert chk.dgvcc_bounds_checked() == 1 and chk.dgvcc_abi_version() == product.dgvcc_abi_version()
+
+    def assert_calls(lib):
+        out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
+        return out.count("__assertfail")
+    if os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        assert assert_calls(path) > 0 and assert_calls(product._name) == 0

@@ -1,6 +1,9 @@
 """Small end-to-end calls of every kernel family in one process: a quick "does everything launch and finish" check,
 and the workload to hand to compute-sanitizer (memcheck / racecheck) where that tool is available -- it is closed
-on this GPU pool.  Sizes are tiny on purpose; parity is the job of tests/, not of this script."""
+on this GPU pool.  Its substitute is the checked build: `DGVCC_BOUNDS_CHECK=1 python scripts/sanitize_small.py` runs the
+same calls through libdgvcc_b200_chk.so, whose kernels assert every table-derived / data-dependent index
+(csrc/common.cuh); the whole GPU suite runs that way with `DGVCC_BOUNDS_CHECK=1 python -m pytest tests -m gpu`.
+Sizes are tiny on purpose; parity is the job of tests/, not of this script."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,6 +16,8 @@ from dgvcc_b200.utils import dmap_gen
 from dgvcc_b200.datasets import bay_targets, den_targets
 
 dev = torch.device("cuda:0")
+from dgvcc_b200 import _native
+print(f"library: {_native.lib()._name} (device-side index checks: {'ON' if _native.lib().dgvcc_bounds_checked() else 'off'})")
 rng = np.random.default_rng(1)
 # Bayesian loss: ragged batch incl. an empty image and a multi-chunk one
 counts = [40, 0, 3, 1500]

@@ -15,7 +15,11 @@ CASES = [
 @pytest.mark.parametrize("counts,world", CASES)
 @pytest.mark.parametrize("use_bg", [True, False])
 def test_partition_covers_every_point_once_and_balances(counts, world, use_bg):
-    p = ShardPlan(counts, use_bg, world, None, 24, 32, 1024)
+    check_partition(counts, world, use_bg)
+
+
+def check_partition(counts, world, use_bg, chunk=1024):
+    p = ShardPlan(counts, use_bg, world, None, 24, 32, chunk)
     counts = np.asarray(counts)
     # chunks tile every image's points exactly once, in order, and never exceed the chunk size
     for i, n in enumerate(counts):
@@ -24,7 +28,7 @@ def test_partition_covers_every_point_once_and_balances(counts, world, use_bg):
         assert sum(p.c_cnt[c] for c in cs) == n and all(p.c_img[c] == i for c in cs)
         pos = 0
         for c in cs:
-            assert p.c_start[c] == pos and p.c_cnt[c] <= 1024
+            assert p.c_start[c] == pos and p.c_cnt[c] <= chunk
             pos += p.c_cnt[c]
     # a rank's chunks are contiguous and its points are the span [bounds[r], bounds[r+1])
     per_rank = np.zeros(world, dtype=np.int64)
@@ -55,8 +59,12 @@ def test_partition_covers_every_point_once_and_balances(counts, world, use_bg):
 
 @pytest.mark.parametrize("counts,world", CASES)
 def test_exchange_plan_is_consistent(counts, world):
+    check_exchange(counts, world)
+
+
+def check_exchange(counts, world, chunk=1024):
     owners = (np.arange(len(counts)) * 7 + 3) % world     # owners unrelated to where the points fall
-    p = ShardPlan(counts, True, world, owners, 24, 32, 1024)
+    p = ShardPlan(counts, True, world, owners, 24, 32, chunk)
     L, m4 = p.layout, 4 * 24 * 32
     P = _native
     b, c = len(counts), p.total_chunks
@@ -128,6 +136,10 @@ BAND_CASES = [([200, 0, 37], 2, 24, 32), ([200, 0, 37], 3, 24, 32), ([0, 0], 2, 
 
 @pytest.mark.parametrize("counts,world,hp,wp", BAND_CASES)
 def test_band_plan_tiles_the_grid_and_the_exchange_is_consistent(counts, world, hp, wp):
+    check_band(counts, world, hp, wp)
+
+
+def check_band(counts, world, hp, wp):
     from dgvcc_b200.losses.bl_banded import BandPlan, band_chunk_points
     owners = (np.arange(len(counts)) * 7 + 3) % world
     chunk = band_chunk_points(int(np.sum(counts)), world, hp, wp)
@@ -186,3 +198,31 @@ def test_band_plan_tiles_the_grid_and_the_exchange_is_consistent(counts, world, 
         for i in range(b):
             rows = np.nonzero(got[r, i])[0]
             assert rows.tolist() == list(range(p.band_lo[r], p.band_hi[r]))
+
+
+# ------------------------------------------------------------------------------------------------ randomised plans
+def _random_counts(rng):
+    b = int(rng.integers(1, 13))
+    kind = rng.integers(0, 4)
+    if kind == 0:       # sparse scenes incl. empty images
+        return [int(v) for v in rng.integers(0, 40, size=b)]
+    if kind == 1:       # one crowd among small images (the shape that breaks whole-image partitioning)
+        c = [int(v) for v in rng.integers(0, 300, size=b)]
+        c[int(rng.integers(0, b))] = int(rng.integers(3000, 13000))
+        return c
+    if kind == 2:       # sizes around the chunk boundaries
+        return [int(rng.choice([0, 1, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2048])) for _ in range(b)]
+    return [int(v) for v in rng.integers(0, 5000, size=b)]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_plans_keep_every_invariant(seed):
+    """The same invariants as above on random head counts, world sizes 1..8, chunk sizes and grids (25 plans per seed)."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(25):
+        counts, world = _random_counts(rng), int(rng.integers(1, 9))
+        chunk = int(rng.choice([128, 256, 352, 512, 1024]))
+        check_partition(counts, world, bool(rng.integers(0, 2)), chunk)
+        check_exchange(counts, world, chunk)
+        hp, wp = int(rng.integers(1, 200)), int(rng.integers(1, 260))
+        check_band(counts, world, hp, wp)

@@ -84,8 +84,11 @@ _install_margin_hooks()
 
 def pytest_terminal_summary(terminalreporter):
     import helpers
-    worst, info = {}, {}
+    worst, info, acc = {}, {}, {}
     for test, what, ratio, rtol, atol in helpers.MARGINS:
+        if "(accuracy)" in what:        # never asserted: distance to the fp64 evaluation, of the kernels and of the reference
+            acc.setdefault(test, {})[what] = max(ratio, acc.get(test, {}).get(what, 0.0))
+            continue
         if "(informational)" in what:   # never asserted: e.g. the same data against SURVEY 8d's tighter floor
             if test not in info or ratio > info[test][1]:
                 info[test] = (what, ratio, rtol, atol)
@@ -105,3 +108,10 @@ def pytest_terminal_summary(terminalreporter):
         tr.write_line(f"informational margins (not asserted): {len(info)} tests, {len(over)} of them beyond 1.0:")
         for test, (what, ratio, rtol, atol) in sorted(info.items(), key=lambda kv: -kv[1][1])[:12]:
             tr.write_line(f"  {ratio:8.3g}  {test}  [{what}]")
+    acc = {t: v for t, v in acc.items() if "_gpu.py" in t}
+    if acc:
+        # "also print error vs the fp64 oracle" -- how far the kernels and the reference's own fp32 evaluation
+        # sit from the fp64 evaluation of the same formulas, in units of the parity gate (rtol 1e-5 of the fp64 value)
+        tr.write_line(f"accuracy against the fp64 evaluation (not asserted; 1.0 = 1e-5 relative), {len(acc)} tests:")
+        for test, kinds in sorted(acc.items(), key=lambda kv: -max(kv[1].values()))[:16]:
+            tr.write_line(f"  {test}  " + "; ".join(f"{k.replace(' (accuracy)', '')} {v:.3g}" for k, v in sorted(kinds.items())))

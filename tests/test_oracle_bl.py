@@ -44,3 +44,22 @@ def test_posterior_columns_sum_to_one():
     hp, wp = c["height"] // c["stride"], c["width"] // c["stride"]
     prob = bl_oracle.posterior(c["points"][0], c["st_sizes"][0], hp, wp, c["stride"], c["sigma"])
     assert_close(prob.sum(0), torch.ones(hp * wp), 1e-5, 0, "column sums")
+
+
+def test_reference_fp32_is_farther_from_fp64_than_the_parity_gate():
+    """Why parity is pinned to the reference's fp32 ROUNDING SEQUENCE and not to "the true value": the cancelling
+    expansion -2xc + x^2 + c^2 (bl.py:27-28) loses ~1e-4 of the posteriors at 1024 px, so the reference's own fp32
+    gradient (the fixture) sits tens of gates (rtol 1e-5) away from the fp64 evaluation of the same formulas, while the
+    loss -- a sum of O(1) counts -- stays within a gate.  A kernel that computed the distances "better" (FMA, fp64,
+    (x-c)^2) would be more accurate and fail parity.  SURVEY 8c "fp64 cross-oracle"; the GPU suite prints the same
+    distances for the kernels (conftest: "accuracy against the fp64 evaluation")."""
+    import torch
+    from helpers import load_bl_golden
+    from oracle import bl_oracle
+    c = load_bl_golden("c1")
+    l64, g64, _ = bl_oracle.bl_forward_backward(c["points"], c["st_sizes"], c["targets"], c["density"], c["stride"],
+                                                c["sigma"], c["bg_ratio"], c["use_bg"], dtype=torch.float64)
+    loss_gates = float((c["ref_loss"].double() - l64).abs() / (1e-5 * l64.abs()))
+    grad_gates = float((c["ref_grad"].double() - g64).abs().max() / (1e-5 * g64.abs().max()))
+    assert loss_gates < 1.0
+    assert 3.0 < grad_gates < 300.0, grad_gates

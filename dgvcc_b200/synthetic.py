@@ -12,8 +12,13 @@ import math
 import numpy as np
 
 
-def crowd_points(rng, n, width, height, dtype=np.float32):
-    """[n,2] (col,row) image-pixel coordinates clipped to [0,W) x [0,H)."""
+def crowd_points(rng, n, width, height, dtype=np.float32, outside="redraw"):
+    """[n,2] (col,row) image-pixel coordinates inside [0,W) x [0,H).
+
+    ``outside``: what happens to cluster heads that land outside the image.  "redraw" (the default, every workload and
+    test input): drawn again uniformly.  "clip": clamped onto the border -- the first version of this generator, kept
+    ONLY because tests/golden/bl_*.npz and dmap_cases.npz were drawn with it (tests/golden/make_golden.py passes it, so
+    that the committed fixtures regenerate bit for bit; tests/test_golden_pin.py checks that)."""
     if n == 0:
         return np.zeros((0, 2), dtype=dtype)
     k = int(rng.integers(3, 21))
@@ -25,10 +30,14 @@ def crowd_points(rng, n, width, height, dtype=np.float32):
     pts = centres[which] + rng.normal(size=(n - n_bg, 2)) * spread[which, None]
     bg = rng.uniform([0, 0], [width, height], size=(n_bg, 2))
     pts = np.concatenate([pts, bg], 0)
-    # heads that fall outside the image are re-drawn uniformly (clipping would pile duplicates on the
-    # border, and duplicates make kNN / top-k tie order implementation-defined)
-    out = (pts[:, 0] < 0) | (pts[:, 0] >= width - 1) | (pts[:, 1] < 0) | (pts[:, 1] >= height - 1)
-    pts[out] = rng.uniform([0, 0], [width - 1, height - 1], size=(int(out.sum()), 2))
+    if outside == "clip":
+        pts[:, 0] = np.clip(pts[:, 0], 0, np.nextafter(np.float32(width), np.float32(0)))
+        pts[:, 1] = np.clip(pts[:, 1], 0, np.nextafter(np.float32(height), np.float32(0)))
+    else:
+        # heads that fall outside the image are re-drawn uniformly (clipping would pile duplicates on the
+        # border, and duplicates make kNN / top-k tie order implementation-defined)
+        out = (pts[:, 0] < 0) | (pts[:, 0] >= width - 1) | (pts[:, 1] < 0) | (pts[:, 1] >= height - 1)
+        pts[out] = rng.uniform([0, 0], [width - 1, height - 1], size=(int(out.sum()), 2))
     rng.shuffle(pts, axis=0)
     return pts.astype(dtype)
 
@@ -37,10 +46,10 @@ def log_uniform_count(rng, lo, hi):
     return int(round(math.exp(rng.uniform(math.log(lo), math.log(hi)))))
 
 
-def bl_image(seed, n, width, height, stride):
+def bl_image(seed, n, width, height, stride, outside="redraw"):
     """One image's (points [n,2] f32, targets [n] f32, density [H',W'] f32, st_size)."""
     rng = np.random.default_rng(seed)
-    pts = crowd_points(rng, n, width, height)
+    pts = crowd_points(rng, n, width, height, outside=outside)
     targets = rng.uniform(0.3, 1.0, size=n).astype(np.float32)
     hp, wp = height // stride, width // stride
     dens = np.abs(rng.normal(size=(hp, wp))).astype(np.float32)
@@ -48,11 +57,11 @@ def bl_image(seed, n, width, height, stride):
     return pts, targets, dens, float(min(width, height))
 
 
-def bl_batch(config, counts, width, height, stride=8, first_image=0):
+def bl_batch(config, counts, width, height, stride=8, first_image=0, outside="redraw"):
     """Batch for BL: lists of per-image points/targets, density [B,1,H',W'], st_sizes [B]."""
     pts, tgt, den, st = [], [], [], []
     for i, n in enumerate(counts):
-        p, t, d, s = bl_image(1000 * config + first_image + i, n, width, height, stride)
+        p, t, d, s = bl_image(1000 * config + first_image + i, n, width, height, stride, outside)
         pts.append(p)
         tgt.append(t)
         den.append(d)

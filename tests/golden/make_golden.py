@@ -34,7 +34,8 @@ def bl_case(name, counts, width, height, stride, sigma, use_bg=True, bg_ratio=1.
             jitter_outside=False, rows=(0, 1, -1)):
     """Run reference BL on a (possibly rectangular) grid via the square + zero-pad construction."""
     bl = load_ref("losses/bl.py", "ref_bl")
-    pts, tgt, dens, st = synthetic.bl_batch(seed_cfg, counts, width, height, stride)
+    # outside="clip": the generator as it was when these fixtures were drawn (synthetic.crowd_points)
+    pts, tgt, dens, st = synthetic.bl_batch(seed_cfg, counts, width, height, stride, outside="clip")
     if jitter_outside:  # bay_dataset.py:85-98 keeps heads whose box overlaps the crop >= 30 %
         for p in pts:
             if len(p):
@@ -88,7 +89,7 @@ def make_bl():
 # ------------------------------------------------------------------------- dmap
 def dmap_points(seed, n, w, h, dtype):
     rng = np.random.default_rng(seed)
-    return synthetic.crowd_points(rng, n, w, h, dtype=dtype)
+    return synthetic.crowd_points(rng, n, w, h, dtype=dtype, outside="clip")   # as when the fixtures were drawn
 
 
 def make_dmap():

@@ -97,3 +97,27 @@ def test_isw_fixture_is_what_the_unmodified_reference_returns():
         assert np.array_equal(cov.detach().numpy(), z[f"{c}_cov"]), c
         assert np.array_equal(loss.detach().numpy(), z[f"{c}_loss"]), c
         assert np.array_equal(x.grad.numpy(), z[f"{c}_grad_x"]), c
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="tests/golden/make_golden.py reads /root/reference")
+@pytest.mark.parametrize("family", ["bl", "dmap", "isw", "bay", "den", "cov", "aux", "sw"])
+def test_generator_script_reproduces_the_committed_fixtures(family, tmp_path, monkeypatch):
+    """`python tests/golden/make_golden.py <family>` -- the committed script that made the fixtures, running the
+    UNMODIFIED reference classes -- writes, into a scratch directory, files whose every array equals the committed one
+    bit for bit (inputs AND reference outputs; same keys, shapes, dtypes).  Covers all eight fixture families, i.e. also
+    the SURVEY 8f rows (dataset targets, mask bookkeeping, lw / ortho, switchable whitening incl. its two-rank gloo runs)."""
+    import sys
+    monkeypatch.syspath_prepend(GOLDEN)
+    monkeypatch.setattr(sys, "dont_write_bytecode", True)
+    import make_golden
+    monkeypatch.setattr(make_golden, "HERE", str(tmp_path))
+    torch.manual_seed(0)
+    getattr(make_golden, f"make_{family}")()
+    made = sorted(os.listdir(tmp_path))
+    assert made, "the generator wrote nothing"
+    for name in made:
+        new, old = np.load(tmp_path / name, allow_pickle=True), np.load(os.path.join(GOLDEN, name), allow_pickle=True)
+        assert sorted(new.files) == sorted(old.files), name
+        for k in new.files:
+            a, b = new[k], old[k]
+            assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True), (name, k)

@@ -10,16 +10,19 @@
 //   FADD, FFMA, FMUL, MUFU.EX2, FADD/FFMA.  ncu (profiles/) shows the kernels bound by the SM's MIO
 //   path that MUFU shares with LDS/SHFL, which is why each thread owns as many pixels as registers
 //   allow: 3 broadcast LDS feed R*C exponentials.
-// Sweeps over the points (dense, no culling):
-//   K0 bl_min_kernel    : per-chunk min_n dis (bl.py:39) -- only for images split into point chunks
-//   K1 bl_z_kernel      : softmax max incl. background row + denominator shares (bl.py:39-44)
-//   K2 bl_counts_kernel : expected counts c_n = sum_m D[m] p[n,m]   (bl.py:73), per-tile partials
+// Launch sequence of one forward + backward (7 launches; dense unless exact_cull is set):
+//   K0 bl_grid_build_kernel + bl_gridmin_kernel : per-pixel min_n dis over ALL points of an image (bl.py:39) through a
+//                         uniform grid over the points (counting sort per image, ring walk per 2 x 32 pixel tile)
+//   K1 bl_z_kernel      : softmax max incl. background row + denominator shares (bl.py:39-44); the last chunk to
+//                         arrive at a pixel tile adds the shares in chunk order and writes 1/Z and the bg posterior
+//   K2 bl_counts_kernel : expected counts c_n = sum_m D[m] p[n,m]   (bl.py:73), one partial row per CTA of 4 tiles
 //   K3 bl_reduce_counts_kernel + bl_select_kernel : deterministic reduction of the partials,
 //                         |t-c|, trimmed top-k (radix select), loss (bl.py:75-79)
-//   K4 bl_grad_kernel   : dL/dD[m] = g * sum_n w_n p[n,m]            (autograd of bl.py:73-79)
-// Big images are cut into equal point chunks (host-built table) so every warp task costs the same
-// and the CTA scheduler balances the ragged batch; per-chunk partial minima / denominators /
-// gradient sums are combined in chunk order (deterministic, no float atomics).
+//   K4 bl_grad_kernel   : dL/dD[m] = g * sum_n w_n p[n,m]            (autograd of bl.py:73-79); last arrival finishes
+// K1, K2, K4 are persistent (work queue, longest chunks first).  Big images are cut into near-equal point chunks
+// (host-built table) so every warp task costs about the same; per-chunk partial denominators / gradient sums are
+// combined in chunk order (deterministic, no float atomics).  The second half of the file holds the two multi-GPU
+// variants (point-chunk sharding, row-band sharding): the same kernels with the exchange fused in (struct Xchg).
 //
 // Rounding contract: the softmax arguments reproduce the
 // reference's fp32 sequence bit for bit -- no FMA contraction in the distance expansion

@@ -93,3 +93,20 @@ def test_checked_variant_builds_beside_the_product_library():
         return out.count("__assertfail")
     if os.path.exists("/usr/local/cuda/bin/cuobjdump"):
         assert assert_calls(path) > 0 and assert_calls(product._name) == 0
+
+
+def test_device_code_is_the_build_the_gpu_suite_ran_on():
+    """profiles/r2d_sass_digest.txt records the SASS digests of the build the full GPU suite last ran on
+    (profiles/r2d_gputest_head.log).  Comments, compiled-out checks, host code and Python may change freely; a change of
+    the DEVICE code must come with a new GPU run and a regenerated digest file (scripts/sass_digest.py)."""
+    import subprocess
+    import sys
+    obj_dir = os.path.join(ROOT, "dgvcc_b200", "lib", "obj")
+    if not (os.path.exists("/usr/local/cuda/bin/cuobjdump") and os.path.isdir(obj_dir)):
+        import pytest
+        pytest.skip("needs cuobjdump and the object files of an in-tree build")
+    _native.lib()   # builds when stale
+    recorded = [l.split() for l in open(os.path.join(ROOT, "profiles", "r2d_sass_digest.txt")) if not l.startswith("#")]
+    now = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_digest.py")], capture_output=True, text=True)
+    assert now.returncode == 0, now.stderr
+    assert [l.split() for l in now.stdout.splitlines()] == recorded

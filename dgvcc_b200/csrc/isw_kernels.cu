@@ -633,6 +633,7 @@ static size_t gram_partial_floats(int batch, int c, int hw) {
 }
 
 extern "C" size_t dgvcc_isw_workspace_bytes(int batch, int c, int hw) {
+    if (batch <= 0 || c <= 0 || hw <= 0) return 0;   // the launchers reject such shapes; the split plans divide by them
     // partials | off[B] + loss partials [B][LOSS_CHUNKS] + alpha[B] | ticket (256 B) | S [B,C,C]
     return align_up(gram_partial_floats(batch, c, hw) * sizeof(float), 256) +
            align_up((size_t)batch * (2 + LOSS_CHUNKS) * sizeof(float), 256) +
@@ -694,7 +695,7 @@ extern "C" int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, con
                                       const float* num_remove_cov, int batch, int c, int hw, void* workspace,
                                       size_t workspace_bytes, float* loss_out, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_cor || !mask || !margin || !num_remove_cov || !workspace || !loss_out) return DGVCC_ERR_ARG;
+    if (!f_cor || !mask || !margin || !num_remove_cov || !workspace || !loss_out || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
@@ -732,7 +733,7 @@ extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, c
                                        int use_tensor_cores, int mask_is_binary, void* workspace,
                                        size_t workspace_bytes, float* grad_f_map, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
+    if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
@@ -754,7 +755,7 @@ extern "C" int dgvcc_isw_covariance_backward(const float* f_map, const float* gr
                                              int use_tensor_cores, void* workspace, size_t workspace_bytes,
                                              float* grad_f_map, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_map || !grad_f_cor || !workspace || !grad_f_map) return DGVCC_ERR_ARG;
+    if (!f_map || !grad_f_cor || !workspace || !grad_f_map || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;

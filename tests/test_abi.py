@@ -110,3 +110,42 @@ def test_device_code_is_the_build_the_gpu_suite_ran_on():
     now = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_digest.py")], capture_output=True, text=True)
     assert now.returncode == 0, now.stderr
     assert [l.split() for l in now.stdout.splitlines()] == recorded
+
+
+def test_no_entry_point_crashes_on_null_or_degenerate_arguments():
+    """Error behaviour of the ABI: integer codes, never a crash.  Every exported function is called (i) with null
+    pointers and zeros and (ii) with valid host pointers and sizes 0 / -1, in ONE child process (a crash then names the
+    call it died in).  No GPU needed: argument checks come first, and without a device the CUDA calls fail with a code.
+    (Found dgvcc_isw_workspace_bytes(0, 0, 0) dividing by zero; the ISW launchers now reject such shapes first.)"""
+    import subprocess
+    import sys
+    child = r'''
+import ctypes, sys
+sys.path.insert(0, %r)
+from dgvcc_b200 import _native
+lib = _native.lib()
+buf = ctypes.create_string_buffer(1 << 22)
+addr = ctypes.addressof(buf)
+for mode in ("null", 0, -1):
+    for name in sorted(_native.SIGNATURES):
+        if mode != "null" and name in ("dgvcc_peer_free", "dgvcc_peer_close"):   # would hand a host pointer to cudaFree
+            continue
+        res, args = _native.SIGNATURES[name]
+        vals = []
+        for a in args:
+            is_ptr = a is ctypes.c_void_p or (hasattr(a, "_type_") and not isinstance(a._type_, str))
+            if is_ptr:
+                vals.append(None if mode == "null" else (ctypes.c_void_p(addr) if a is ctypes.c_void_p else ctypes.cast(addr, a)))
+            elif a in (ctypes.c_float, ctypes.c_double):
+                vals.append(0.0)
+            elif a is ctypes.c_size_t:
+                vals.append(0 if mode == "null" else 1 << 22)
+            else:
+                vals.append(0 if mode == "null" else mode)
+        print("calling", name, mode, flush=True)
+        getattr(lib, name)(*vals)
+print("survived", flush=True)
+''' % ROOT
+    p = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)
+    last = (p.stdout.strip().splitlines() or ["<nothing>"])[-1]
+    assert p.returncode == 0 and last == "survived", f"child rc={p.returncode}, last line: {last}\n{p.stderr[-600:]}"

@@ -596,10 +596,17 @@ extern "C" int dgvcc_isw_instnorm_backward(const float* dy, const float* y, cons
 // Split-K plans.  SIMT Gram: 64x64 tiles, enough CTAs to cover the chip about twice.  Tensor-core Gram: one CTA
 // per SM and one wave (the kernel bounds its in-TMEM accumulation chains itself, so K per CTA may be long);
 // C <= 64 packs two samples into one 128-row tile and stores 64x64 partial tiles.
+// Shapes the ISW-family launchers accept (the reference's are (8, 64..512, 1600..25 600)); beyond them the int
+// arithmetic of the plans and grids would overflow.  batch is a grid z dimension (<= 65535).
+static bool isw_shape_ok(int batch, int c, int hw) {
+    return batch >= 1 && batch <= 65535 && c >= 1 && c <= 32768 && hw >= 1 && hw <= (1 << 30);
+}
+
 static void gram_plan_simt(int batch, int c, int hw, int* splits, int* k_per_split, int* n_tiles) {
     const int t1 = ceil_div(c, 64);
     *n_tiles = t1 * (t1 + 1) / 2;
-    int s = ceil_div(296, batch * *n_tiles);
+    const long long work = (long long)batch * *n_tiles;
+    int s = work >= 296 ? 1 : ceil_div(296, (int)work);
     const int max_s = ceil_div(hw, 256);
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
@@ -613,8 +620,8 @@ static void gram_plan_tc(int batch, int c, int hw, int* splits, int* k_per_split
     *tile = pair ? 64 : 128;
     const int t1 = pair ? 1 : ceil_div(c, 128);
     *n_tiles = t1 * (t1 + 1) / 2;
-    const int units = (pair ? ceil_div(batch, 2) : batch) * *n_tiles;
-    int s = 148 / units;
+    const long long units = (long long)(pair ? ceil_div(batch, 2) : batch) * *n_tiles;
+    int s = units > 148 ? 0 : (int)(148 / units);
     const int max_s = ceil_div(hw, 256);
     if (s > max_s) s = max_s;
     if (s < 1) s = 1;
@@ -633,7 +640,7 @@ static size_t gram_partial_floats(int batch, int c, int hw) {
 }
 
 extern "C" size_t dgvcc_isw_workspace_bytes(int batch, int c, int hw) {
-    if (batch <= 0 || c <= 0 || hw <= 0) return 0;   // the launchers reject such shapes; the split plans divide by them
+    if (!isw_shape_ok(batch, c, hw)) return 0;   // the launchers reject such shapes (the split plans divide by them)
     // partials | off[B] + loss partials [B][LOSS_CHUNKS] + alpha[B] | ticket (256 B) | S [B,C,C]
     return align_up(gram_partial_floats(batch, c, hw) * sizeof(float), 256) +
            align_up((size_t)batch * (2 + LOSS_CHUNKS) * sizeof(float), 256) +
@@ -685,7 +692,7 @@ static int launch_gram(const float* f_map, const float* eye, float denom, float 
 extern "C" int dgvcc_isw_covariance(const float* f_map, const float* eye, int batch, int c, int hw, int use_tensor_cores,
                                     void* workspace, size_t workspace_bytes, float* f_cor, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_map || !eye || !workspace || !f_cor || batch <= 0 || c <= 0 || hw <= 1) return DGVCC_ERR_ARG;
+    if (!f_map || !eye || !workspace || !f_cor || !isw_shape_ok(batch, c, hw) || hw <= 1) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     return launch_gram(f_map, eye, (float)(hw - 1), 1e-5f, batch, c, hw, use_tensor_cores, w, f_cor, (cudaStream_t)stream);
@@ -695,7 +702,7 @@ extern "C" int dgvcc_isw_loss_forward(const float* f_cor, const float* mask, con
                                       const float* num_remove_cov, int batch, int c, int hw, void* workspace,
                                       size_t workspace_bytes, float* loss_out, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_cor || !mask || !margin || !num_remove_cov || !workspace || !loss_out || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    if (!f_cor || !mask || !margin || !num_remove_cov || !workspace || !loss_out || !isw_shape_ok(batch, c, hw)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
@@ -733,7 +740,7 @@ extern "C" int dgvcc_isw_loss_backward(const float* f_map, const float* f_cor, c
                                        int use_tensor_cores, int mask_is_binary, void* workspace,
                                        size_t workspace_bytes, float* grad_f_map, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    if (!f_map || !f_cor || !mask || !num_remove_cov || !grad_loss || !workspace || !grad_f_map || !isw_shape_ok(batch, c, hw)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
@@ -755,7 +762,7 @@ extern "C" int dgvcc_isw_covariance_backward(const float* f_map, const float* gr
                                              int use_tensor_cores, void* workspace, size_t workspace_bytes,
                                              float* grad_f_map, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_map || !grad_f_cor || !workspace || !grad_f_map || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    if (!f_map || !grad_f_cor || !workspace || !grad_f_map || !isw_shape_ok(batch, c, hw)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
@@ -801,7 +808,7 @@ extern "C" int dgvcc_lw_standardize_backward(const float* dy, const float* yhat,
 extern "C" int dgvcc_isw_gram(const float* f_map, int batch, int c, int hw, int use_tensor_cores, void* workspace,
                               size_t workspace_bytes, float* gram, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!f_map || !workspace || !gram || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    if (!f_map || !workspace || !gram || !isw_shape_ok(batch, c, hw)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     return launch_gram(f_map, nullptr, 1.0f, 0.f, batch, c, hw, use_tensor_cores, w, gram, (cudaStream_t)stream);
@@ -819,7 +826,7 @@ static int launch_triu_sq(const float* g, int c, int ld, int col0, size_t sample
 extern "C" int dgvcc_lw_loss_forward(const float* gram, int batch, int c, int hw, void* workspace, size_t workspace_bytes,
                                      float* loss_out, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!gram || !workspace || !loss_out || batch <= 0 || c <= 0) return DGVCC_ERR_ARG;
+    if (!gram || !workspace || !loss_out || !isw_shape_ok(batch, c, hw)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     return launch_triu_sq(gram, c, c, 0, (size_t)c * c, batch, 1.0f, w, loss_out, (cudaStream_t)stream);
@@ -829,7 +836,7 @@ extern "C" int dgvcc_lw_loss_backward(const float* y, const float* gram, const f
                                       int use_tensor_cores, void* workspace, size_t workspace_bytes, float* grad_y,
                                       void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!y || !gram || !grad_loss || !workspace || !grad_y || batch <= 0 || c <= 0 || hw <= 0) return DGVCC_ERR_ARG;
+    if (!y || !gram || !grad_loss || !workspace || !grad_y || !isw_shape_ok(batch, c, hw)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(batch, c, hw)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, batch, c, hw);
     cudaStream_t st = (cudaStream_t)stream;
@@ -842,7 +849,7 @@ extern "C" int dgvcc_lw_loss_backward(const float* y, const float* gram, const f
 extern "C" int dgvcc_ortho_loss_forward(const float* gram_zz, int c, int p, void* workspace, size_t workspace_bytes,
                                         float* loss_out, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!gram_zz || !workspace || !loss_out || c <= 0 || p <= 0) return DGVCC_ERR_ARG;
+    if (!gram_zz || !workspace || !loss_out || c > 16384 || !isw_shape_ok(1, 2 * c, p)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(1, 2 * c, p)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, 1, 2 * c, p);
     return launch_triu_sq(gram_zz, c, 2 * c, c, 0, 1, 1.0f / ((float)c * (float)c), w, loss_out, (cudaStream_t)stream);
@@ -852,7 +859,7 @@ extern "C" int dgvcc_ortho_loss_backward(const float* x, const float* y, const f
                                          int p, int use_tensor_cores, void* workspace, size_t workspace_bytes,
                                          float* grad_x, float* grad_y, void* stream) {
     DGVCC_DEVICE_GUARD(stream);
-    if (!x || !y || !gram_zz || !grad_loss || !workspace || !grad_x || !grad_y || c <= 0 || p <= 0) return DGVCC_ERR_ARG;
+    if (!x || !y || !gram_zz || !grad_loss || !workspace || !grad_x || !grad_y || c > 16384 || !isw_shape_ok(1, 2 * c, p)) return DGVCC_ERR_ARG;
     if (workspace_bytes < dgvcc_isw_workspace_bytes(1, 2 * c, p)) return DGVCC_ERR_WORKSPACE;
     const IswWs w = carve(workspace, 1, 2 * c, p);  // S region holds (2c)^2 floats: Sx and Sy fit
     cudaStream_t st = (cudaStream_t)stream;

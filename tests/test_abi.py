@@ -114,9 +114,10 @@ def test_device_code_is_the_build_the_gpu_suite_ran_on():
 
 def test_no_entry_point_crashes_on_null_or_degenerate_arguments():
     """Error behaviour of the ABI: integer codes, never a crash.  Every exported function is called (i) with null
-    pointers and zeros and (ii) with valid host pointers and sizes 0 / -1, in ONE child process (a crash then names the
-    call it died in).  No GPU needed: argument checks come first, and without a device the CUDA calls fail with a code.
-    (Found dgvcc_isw_workspace_bytes(0, 0, 0) dividing by zero; the ISW launchers now reject such shapes first.)"""
+    pointers and zeros, (ii) with valid host pointers and sizes 0 / -1 and (iii) 1500 times with random small, boundary
+    and absurd (2^31 - 1) sizes, in ONE child process (a crash then names the call it died in).  No GPU needed: argument checks come first, and without a device the CUDA calls fail with a code.
+    (Found dgvcc_isw_workspace_bytes(0, 0, 0), dgvcc_lw_loss_forward(hw = 0) and overflowing shapes dividing by zero in
+    the split-K plans; the ISW-family launchers now check isw_shape_ok first.)"""
     import subprocess
     import sys
     child = r'''
@@ -144,6 +145,30 @@ for mode in ("null", 0, -1):
                 vals.append(0 if mode == "null" else mode)
         print("calling", name, mode, flush=True)
         getattr(lib, name)(*vals)
+# (iii) random small / boundary / absurd sizes with valid host pointers (the host-only writers get small sizes only)
+import random
+rng = random.Random(20261019)
+writers = {"dgvcc_bl_pack_host", "dgvcc_dmap_batch_plan"}
+skip = {"dgvcc_peer_free", "dgvcc_peer_close", "dgvcc_peer_export", "dgvcc_peer_open", "dgvcc_peer_alloc"}
+pool = sorted(set(_native.SIGNATURES) - skip)
+for it in range(1500):
+    name = rng.choice(pool)
+    res, args = _native.SIGNATURES[name]
+    big = name not in writers and rng.random() < 0.3
+    vals = []
+    for a in args:
+        if a is ctypes.c_void_p:
+            vals.append(ctypes.c_void_p(addr))
+        elif hasattr(a, "_type_") and not isinstance(a._type_, str):
+            vals.append(ctypes.cast(addr, a))
+        elif a in (ctypes.c_float, ctypes.c_double):
+            vals.append(rng.choice([0.0, 1.0, 8.0, -1.0, 1e30, float("nan")]))
+        elif a is ctypes.c_size_t:
+            vals.append(rng.choice([0, 16, 1 << 22]))
+        else:
+            vals.append(rng.choice([0, 1, 2, 3, 5, 31, 32, 33, 64, 100, -1] + ([2 ** 31 - 1, 2 ** 30, 65536] if big else [])))
+    print("calling", name, [v for v in vals if isinstance(v, (int, float))], flush=True)
+    getattr(lib, name)(*vals)
 print("survived", flush=True)
 ''' % ROOT
     p = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)

@@ -71,6 +71,20 @@ def test_native_host_packing_matches_the_python_packing():
         buf = torch.zeros((info.total_bytes,), dtype=torch.uint8)
         bl.pack_host_native(pts, tgt, use_bg, chunk, buf.data_ptr(), buf.numel(), args)
         assert torch.equal(buf, ref.buf), counts
+    # the same on random batches: sizes around the chunk boundaries, chunk sizes 1 .. 4096, with and without background
+    for _ in range(150):
+        b = int(rng.integers(1, 10))
+        counts = [int(rng.choice([0, 1, 2, 127, 128, 129, 511, 512, 513, 1023, 1024, 1025, 2049, int(rng.integers(0, 5000))]))
+                  for _ in range(b)]
+        chunk, use_bg = int(rng.choice([1, 3, 37, 128, 352, 512, 1024, 4096])), bool(rng.integers(0, 2))
+        pts = [torch.from_numpy(rng.random((n, 2), dtype=np.float32)) for n in counts]
+        tgt = [torch.from_numpy(rng.random(n, dtype=np.float32)) for n in counts]
+        ref = bl.pack_batch(pts, tgt, use_background=use_bg, chunk=chunk)
+        info, args = bl.pack_host_native(pts, tgt, use_bg, chunk, None, 0)
+        assert (info.total_bytes, info.total_chunks, info.multi_chunk) == (ref.total, ref.total_chunks, ref.multi_chunk)
+        buf = torch.zeros((info.total_bytes,), dtype=torch.uint8)
+        bl.pack_host_native(pts, tgt, use_bg, chunk, buf.data_ptr(), buf.numel(), args)
+        assert torch.equal(buf, ref.buf), (counts, chunk, use_bg)
 
 
 def test_checked_variant_builds_beside_the_product_library():

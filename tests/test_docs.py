@@ -52,3 +52,18 @@ def test_reference_citations_point_at_existing_lines():
                 bad.append((os.path.relpath(f, ROOT), m.group(0), "no such reference file" if n is None else f"file has {n} lines"))
     assert checked >= 300, checked
     assert not bad, bad[:20]
+
+
+def test_integration_md_ctypes_stub_matches_the_signature_table():
+    """The raw ctypes stub of INTEGRATION.md section 3 (what a maintainer would write without this package) declares the
+    argument types dgvcc_b200._native declares for the same entry point."""
+    import ctypes
+    from dgvcc_b200 import _native
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"lib\.(dgvcc_\w+)\.argtypes = (.*?)\n\n", text, flags=re.S)
+    assert m, "stub not found"
+    name, expr = m.group(1), m.group(2).replace("\\\n", " ")
+    stub = eval(expr, {"ctypes": ctypes})
+    res, args = _native.SIGNATURES[name]
+    assert list(stub) == list(args), name
+    assert re.search(rf"lib\.{name}\.restype = ctypes\.c_int\b", text) and res is ctypes.c_int

@@ -188,3 +188,35 @@ print("survived", flush=True)
     p = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True, timeout=300)
     last = (p.stdout.strip().splitlines() or ["<nothing>"])[-1]
     assert p.returncode == 0 and last == "survived", f"child rc={p.returncode}, last line: {last}\n{p.stderr[-600:]}"
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument by argument: every prototype of include/dgvcc_b200.h against dgvcc_b200._native.SIGNATURES (pointer /
+    int / int64_t / size_t / float / double, and the return type) -- a wrong ctypes width is silent garbage on the GPU."""
+    import ctypes
+    text = open(os.path.join(ROOT, "include", "dgvcc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(int|size_t)\s+(dgvcc_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert {p[1] for p in protos} == set(_native.SIGNATURES)
+
+    def c_kind(arg):
+        arg = " ".join(arg.split())
+        if arg in ("void", ""):
+            return None
+        if "*" in arg:
+            return "ptr"
+        for token, kind in (("int64_t", "i64"), ("size_t", "size"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
+            if re.search(rf"\b{token}\b", arg):
+                return kind
+        raise AssertionError(f"unclassified C argument: {arg}")
+
+    def py_kind(a):
+        if a is ctypes.c_void_p or (hasattr(a, "_type_") and not isinstance(a._type_, str)):
+            return "ptr"
+        return {ctypes.c_int64: "i64", ctypes.c_size_t: "size", ctypes.c_double: "f64", ctypes.c_float: "f32",
+                ctypes.c_int: "i32"}[a]
+
+    for ret, name, args in protos:
+        res, py_args = _native.SIGNATURES[name]
+        assert res is {"int": ctypes.c_int, "size_t": ctypes.c_size_t}[ret], name
+        assert [k for k in map(c_kind, args.split(",")) if k] == [py_kind(a) for a in py_args], name

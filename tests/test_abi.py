@@ -220,3 +220,32 @@ def test_ctypes_signatures_match_the_header_prototypes():
         res, py_args = _native.SIGNATURES[name]
         assert res is {"int": ctypes.c_int, "size_t": ctypes.c_size_t}[ret], name
         assert [k for k in map(c_kind, args.split(",")) if k] == [py_kind(a) for a in py_args], name
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is a C ABI: include/dgvcc_b200.h compiles as strict C99 (and as C++), and a C program linked against
+    the library calls an entry point -- no torch, no Python, no C++ runtime needed by the caller."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        import pytest
+        pytest.skip("no gcc")
+    lib = _native.lib()
+    inc, libdir = os.path.join(ROOT, "include"), os.path.dirname(lib._name)
+    src = tmp_path / "caller.c"
+    src.write_text('#include <stdio.h>\n#include "dgvcc_b200.h"\n'
+                   'int main(void) {\n'
+                   '    dgvcc_bl_layout lay;\n'
+                   '    int rc = dgvcc_bl_workspace_layout(1000, 3, 2, 48, 64, &lay);\n'
+                   '    printf("%d %d %d\\n", dgvcc_abi_version(), rc, dgvcc_bl_workspace_layout(0, 1, 1, 8, 8, &lay));\n'
+                   '    return 0;\n}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    if shutil.which("g++"):
+        cpp = tmp_path / "caller.cpp"
+        cpp.write_text('#include "dgvcc_b200.h"\nint main() { return dgvcc_abi_version() > 0 ? 0 : 1; }\n')
+        subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
+    exe = tmp_path / "caller"
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ldgvcc_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == lib.dgvcc_abi_version() and out[1:] == ["0", "-1"]

@@ -249,3 +249,32 @@ def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
                     f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert int(out[0]) == lib.dgvcc_abi_version() and out[1:] == ["0", "-1"]
+
+
+def test_ctypes_structures_mirror_the_header_structs(tmp_path):
+    """Field by field: name, offset and size of every struct dgvcc_b200._native mirrors, measured by a C program
+    compiled against the header (a field the header does not have fails to compile)."""
+    import ctypes
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        import pytest
+        pytest.skip("no gcc")
+    mirrors = {"dgvcc_bl_layout": _native.BLLayout, "dgvcc_bl_packed": _native.BLPacked,
+               "dgvcc_bl_shard": _native.BLShard, "dgvcc_dmap_plan": _native.DmapPlan}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dgvcc_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'    printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            lines.append(f'    printf("{cname}.{field} %zu %zu\\n", offsetof({cname}, {field}), sizeof((({cname}*)0)->{field}));')
+    lines += ['    return 0;', '}']
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines) + "\n")
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict((l.split()[0], [int(v) for v in l.split()[1:]]) for l in
+               subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert got[cname] == [ctypes.sizeof(cls)], cname
+        for field, ftype in cls._fields_:
+            assert got[f"{cname}.{field}"] == [getattr(cls, field).offset, ctypes.sizeof(ftype)], f"{cname}.{field}"
+    assert _native.BL_PHASES == 8 and _native.DMAP_META_COLS == 12   # DGVCC_BL_PHASES, DGVCC_DMAP_META_COLS
